@@ -1,0 +1,109 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container only).
+
+    PYTHONDONTWRITEBYTECODE=1 PYTHONPATH=/root/reference python oracle/make_golden.py
+
+Imports ``Codebook`` from ``/root/reference/models/vitvqgan.py:140-176`` and
+``/root/reference/models/vqgan.py:138-182`` (read-only mount, nothing is copied),
+feeds them the seeded inputs of SURVEY.md section 8(d) and stores what they return.
+Inputs are NOT stored: they are regenerated bit-identically from the seeds by
+``oracle.vq_oracle.make_codebook / make_latents`` (CPU ``torch.Generator``).
+The reference never runs on the GPU box; these files are how it travels.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import vq_oracle as vo  # noqa: E402  (input generators only)
+
+REF = "/root/reference"
+if REF not in sys.path:
+    sys.path.insert(0, REF)
+from models.vitvqgan import Codebook as RefVitCodebook    # noqa: E402
+from models.vqgan import Codebook as RefVqganCodebook      # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+torch.set_num_threads(1)            # fixed CPU reduction order for the fixtures
+torch.use_deterministic_algorithms(True)
+
+
+def _module(form, K, D, beta, weight):
+    cls = RefVitCodebook if form == vo.VIT else RefVqganCodebook
+    m = cls(K, D, beta)
+    with torch.no_grad():
+        m.embedding.weight.copy_(weight)
+    return m
+
+
+def forward_case(name, form, K, D, shape, w_seed, z_seed, beta=0.25, edit=None):
+    w = vo.make_codebook(form, K, D, w_seed)
+    z = vo.make_latents(shape, z_seed)
+    if edit is not None:
+        edit(z, w)
+    m = _module(form, K, D, beta, w)
+    with torch.no_grad():
+        z_q, idx, loss = m(z)
+    idx_dtype = np.uint16 if K <= 65536 else np.int64
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), form=form, K=K, D=D, shape=np.array(shape),
+                        w_seed=w_seed, z_seed=z_seed, beta=beta, edit=(edit.__name__ if edit else ""),
+                        z_q=z_q.numpy(), indices=idx.numpy().astype(idx_dtype), idx_shape=np.array(idx.shape),
+                        loss=loss.numpy())
+    print(name, "loss", float(loss), "idx[:4]", idx.reshape(-1)[:4].tolist())
+
+
+def step_case(name, form, K, D, shape, w_seed, z_seed, g_seed, beta=0.25):
+    w = vo.make_codebook(form, K, D, w_seed)
+    z = vo.make_latents(shape, z_seed).requires_grad_(True)
+    up = vo.make_latents(shape, g_seed)
+    m = _module(form, K, D, beta, w)
+    z_q, idx, loss = m(z)
+    ((z_q * up).sum() + loss).backward()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), form=form, K=K, D=D, shape=np.array(shape),
+                        w_seed=w_seed, z_seed=z_seed, g_seed=g_seed, beta=beta,
+                        z_q=z_q.detach().numpy(), indices=idx.numpy().astype(np.uint16),
+                        idx_shape=np.array(idx.shape), loss=loss.detach().numpy(),
+                        grad_z=z.grad.numpy(), grad_weight=m.embedding.weight.grad.numpy())
+    print(name, "loss", float(loss), "|grad_w|", float(m.embedding.weight.grad.norm()))
+
+
+def decode_case(name, form, K, D, b, n, w_seed, i_seed):
+    w = vo.make_codebook(form, K, D, w_seed)
+    g = torch.Generator().manual_seed(i_seed)
+    idx = torch.randint(0, K, (b, n), generator=g)
+    m = _module(form, K, D, 0.25, w)
+    with torch.no_grad():
+        e = m.indices_to_embeddings(idx)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), form=form, K=K, D=D, b=b, n=n, w_seed=w_seed,
+                        i_seed=i_seed, embeds=e.contiguous().numpy(), embeds_shape=np.array(e.shape))
+    print(name, tuple(e.shape))
+
+
+def degenerate_rows(z, w):
+    """zero row, NaN row, a row equal to a code, a zero code (SURVEY.md section 7 'Degenerate rows')."""
+    z[0, 0] = 0.0
+    z[0, 1, 3] = float("nan")
+    z[0, 2] = w[5] * 3.0
+    z[1, 0] = -w[7]
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    # BASELINE.json configs[0]: ViT form K=8192 D=32, 2 x 1024 tokens
+    forward_case("vit_cfg1_fwd", vo.VIT, 8192, 32, (2, 1024, 32), 0, 1)
+    # a slice of configs[1]: VQGAN form K=8192 D=256, NCHW 16x16 latents
+    forward_case("vqgan_cfg2_slice_fwd", vo.VQGAN, 8192, 256, (4, 256, 16, 16), 0, 2)
+    # fwd + bwd (configs[2] objective) at sizes whose gradients stay small on disk
+    step_case("vit_step_small", vo.VIT, 1024, 32, (4, 256, 32), 10, 11, 12)
+    step_case("vit_step_beta", vo.VIT, 512, 32, (2, 128, 32), 13, 14, 15, beta=0.7)
+    step_case("vqgan_step_small", vo.VQGAN, 512, 256, (2, 256, 8, 8), 20, 21, 22)
+    step_case("vqgan_step_d64", vo.VQGAN, 256, 64, (3, 64, 4, 4), 23, 24, 25, beta=0.4)
+    # decode_indices side
+    decode_case("vit_decode", vo.VIT, 8192, 32, 2, 1024, 0, 30)
+    decode_case("vqgan_decode", vo.VQGAN, 1024, 256, 2, 64, 31, 32)
+    # edge rows
+    forward_case("vit_degenerate_fwd", vo.VIT, 64, 32, (2, 8, 32), 40, 41, edit=degenerate_rows)
