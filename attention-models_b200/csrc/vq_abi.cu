@@ -1,0 +1,405 @@
+// extern "C" entry points of libvq_b200.so (declared in include/vq_b200.h).
+// Orchestration only: argument checks, workspace carving, kernel sequencing on the caller's stream.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/vq_b200.h"
+#include "vq_kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(VQ_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define VQ_CUDA(call)                                             \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);     \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// measurement hooks: event pairs around the search kernel while profiling is on
+bool g_profiling = false;
+long long g_launches_at_begin = 0;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_search_events;
+
+struct SearchTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t s;
+    explicit SearchTimer(cudaStream_t stream) : s(stream) {
+        if (g_profiling && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, s);
+    }
+    void stop() {
+        if (a && b) { cudaEventRecord(b, s); g_search_events.emplace_back(a, b); a = b = nullptr; }
+    }
+};
+
+struct Bump {
+    char* base; size_t off = 0;
+    explicit Bump(void* p) : base(static_cast<char*>(p)) {}
+    template <typename T> T* take(size_t n) {
+        T* r = reinterpret_cast<T*>(base ? base + off : nullptr);
+        off += align_up(sizeof(T) * n, 256);
+        return r;
+    }
+};
+
+struct FwdWs {
+    float* zn32; float* denom; float* row_sq; __half* zn16; int* cand; int* flagged; int* n_flagged;
+    int64_t* stats; float* zq_tok; void* tc_ws; size_t bytes;
+};
+
+// Sized for the worst case over the optional outputs so one size serves every flag combination.
+FwdWs carve_forward(void* ws, int64_t T, int K, int D) {
+    Bump b(ws);
+    FwdWs w;
+    const size_t n = (size_t)(T > 0 ? T : 1);
+    w.zn32 = b.take<float>(n * D);
+    w.denom = b.take<float>(n);
+    w.row_sq = b.take<float>(n);
+    w.zn16 = b.take<__half>(n * D);
+    w.cand = b.take<int>(n);
+    w.flagged = b.take<int>(n);
+    w.n_flagged = b.take<int>(64);
+    w.stats = b.take<int64_t>(VQ_STATS_LEN);
+    w.zq_tok = b.take<float>(n * D);
+    const size_t tcb = vq::tc_workspace_bytes(T, K, D);
+    w.tc_ws = b.take<char>(tcb ? tcb : 1);
+    w.bytes = b.off;
+    return w;
+}
+
+int check_dims(int64_t T, int K, int D) {
+    if (!vq::dim_supported(D)) return fail(VQ_ERR_ARG, "codebook_dim %d unsupported (powers of two in [16, 512])", D);
+    if (K <= 0 || K >= (1 << 30)) return fail(VQ_ERR_ARG, "codebook_size %d out of range", K);
+    if (T < 0 || T >= (1ll << 31)) return fail(VQ_ERR_ARG, "token count %lld out of range", (long long)T);
+    return VQ_OK;
+}
+
+int check_layout(int layout, int64_t T, int64_t hw) {
+    if (layout == VQ_LAYOUT_TOKEN_MAJOR) return VQ_OK;
+    if (layout != VQ_LAYOUT_NCHW) return fail(VQ_ERR_ARG, "unknown layout %d", layout);
+    if (hw <= 0 || T % hw != 0) return fail(VQ_ERR_ARG, "NCHW layout needs hw > 0 dividing T (T=%lld hw=%lld)",
+                                            (long long)T, (long long)hw);
+    return VQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vq_abi_version(void) { return VQ_ABI_VERSION; }
+
+const char* vq_last_error(void) { return g_last_error.c_str(); }
+
+int vq_uses_tensor_cores(int64_t T, int K, int D) {
+    if (check_dims(T, K, D) != VQ_OK) return 0;
+    return vq::tc_supported(T, K, D) ? 1 : 0;
+}
+
+int vq_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    cudaDeviceProp p;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+        cudaGetLastError();
+        if (sm_count) *sm_count = 0;
+        if (cc_major) *cc_major = 0;
+        if (cc_minor) *cc_minor = 0;
+        return fail(VQ_ERR_CUDA, "no CUDA device");
+    }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return VQ_OK;
+}
+
+int vq_codebook_bytes(int K, int D, size_t* out) {
+    if (!out) return fail(VQ_ERR_ARG, "out is NULL");
+    if (int r = check_dims(0, K, D)) return r;
+    *out = vq::codebook_bytes(K, D);
+    return VQ_OK;
+}
+
+int vq_codebook_prepare(const float* weight, int K, int D, void* cb, size_t cb_bytes, void* stream) {
+    if (int r = check_dims(0, K, D)) return r;
+    if (!weight || !cb) return fail(VQ_ERR_ARG, "weight/cb is NULL");
+    if (cb_bytes < vq::codebook_bytes(K, D)) return fail(VQ_ERR_WORKSPACE, "codebook blob too small");
+    vq::CodebookView v = vq::codebook_view(cb, K, D);
+    VQ_CUDA(vq::launch_prep_codebook(weight, v, static_cast<cudaStream_t>(stream)));
+    return VQ_OK;
+}
+
+int vq_workspace_bytes(int64_t T, int K, int D, int flags, size_t* out) {
+    (void)flags;
+    if (!out) return fail(VQ_ERR_ARG, "out is NULL");
+    if (int r = check_dims(T, K, D)) return r;
+    *out = carve_forward(nullptr, T, K, D).bytes;
+    return VQ_OK;
+}
+
+int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb, int K, int D, int form, float beta,
+               int flags, int64_t n_elem_total, float* z_q, int64_t* idx, float* loss, int32_t* hist, int64_t* stats,
+               float* saved_zn, float* saved_denom, void* ws, size_t ws_bytes, void* stream) {
+    if (int r = check_dims(T, K, D)) return r;
+    if (int r = check_layout(layout, T, hw)) return r;
+    if (form != VQ_FORM_VIT && form != VQ_FORM_VQGAN) return fail(VQ_ERR_ARG, "unknown form %d", form);
+    if (!cb || !idx || (!z && T > 0)) return fail(VQ_ERR_ARG, "z/cb/idx is NULL");
+    const bool indices_only = (flags & VQ_FLAG_INDICES_ONLY) != 0;
+    if (!indices_only && !z_q) return fail(VQ_ERR_ARG, "z_q is NULL without VQ_FLAG_INDICES_ONLY");
+    if (!ws) return fail(VQ_ERR_WORKSPACE, "workspace is NULL");
+    FwdWs w = carve_forward(ws, T, K, D);
+    if (ws_bytes < w.bytes) return fail(VQ_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, w.bytes);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    vq::CodebookView cbv = vq::codebook_view(const_cast<void*>(cb), K, D);
+
+    float* zn32 = saved_zn ? saved_zn : w.zn32;
+    float* denom = saved_denom ? saved_denom : w.denom;
+    int64_t* st = stats ? stats : w.stats;
+    VQ_CUDA(cudaMemsetAsync(st, 0, sizeof(int64_t) * VQ_STATS_LEN, s));
+    if (hist) VQ_CUDA(cudaMemsetAsync(hist, 0, sizeof(int32_t) * (size_t)K, s));
+
+    const bool use_tc = !(flags & VQ_FLAG_EXACT_SCAN) && vq::tc_supported(T, K, D);
+    __half* zn16 = use_tc ? w.zn16 : nullptr;
+
+    // 1. unit rows (ATen-order norms), fp16 copy for the tensor cores
+    if (layout == VQ_LAYOUT_TOKEN_MAJOR) {
+        VQ_CUDA(vq::launch_prep_tokens(z, T, D, zn32, w.row_sq, denom, zn16, s));
+    } else {
+        if (hw % 4 == 0) {
+            VQ_CUDA(vq::launch_norm_nchw(z, T, hw, D, denom, s));
+            VQ_CUDA(vq::launch_nchw_to_tok(z, T, hw, D, denom, zn32, zn16, s));
+            VQ_CUDA(vq::launch_row_sumsq(zn32, T, D, w.row_sq, s));
+        } else {   // ATen picks another schedule here; the contiguous order is used (<= 1 ulp apart)
+            VQ_CUDA(vq::launch_nchw_to_tok(z, T, hw, D, nullptr, w.zq_tok, nullptr, s));
+            VQ_CUDA(vq::launch_prep_tokens(w.zq_tok, T, D, zn32, w.row_sq, denom, zn16, s));
+        }
+    }
+
+    // 2. nearest code per row -> cand[]
+    SearchTimer timer(s);
+    if (use_tc) {
+        VQ_CUDA(cudaMemsetAsync(w.n_flagged, 0, sizeof(int) * 64, s));
+        VQ_CUDA(vq::launch_dist_tc(zn16, zn32, w.row_sq, cbv, T, w.cand, w.flagged, w.n_flagged, st, w.tc_ws, s));
+        VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, T, w.cand, st, s));
+    } else {
+        VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, nullptr, nullptr, T, w.cand, st, s));
+    }
+    timer.stop();
+
+    // 3. idx, hist, z_q, loss partial
+    float* zq_tok = indices_only ? nullptr : (layout == VQ_LAYOUT_NCHW ? w.zq_tok : z_q);
+    VQ_CUDA(vq::launch_finish(zn32, w.cand, cbv, T, zq_tok, idx, hist, st, s));
+    if (!indices_only && layout == VQ_LAYOUT_NCHW) VQ_CUDA(vq::launch_tok_to_nchw(zq_tok, T, hw, D, z_q, s));
+    if (loss && !indices_only) {
+        if (n_elem_total <= 0) return fail(VQ_ERR_ARG, "n_elem_total must be positive");
+        VQ_CUDA(vq::launch_loss_finalize(st, n_elem_total, form, beta, loss, s));
+    }
+    return VQ_OK;
+}
+
+int vq_loss_finalize(const int64_t* stats, int64_t n_elem_total, int form, float beta, float* loss, void* stream) {
+    if (!stats || !loss || n_elem_total <= 0) return fail(VQ_ERR_ARG, "bad argument to vq_loss_finalize");
+    VQ_CUDA(vq::launch_loss_finalize(stats, n_elem_total, form, beta, loss, static_cast<cudaStream_t>(stream)));
+    return VQ_OK;
+}
+
+int vq_backward_workspace_bytes(int64_t T, int K, int D, size_t* out) {
+    if (!out) return fail(VQ_ERR_ARG, "out is NULL");
+    if (int r = check_dims(T, K, D)) return r;
+    const size_t n = (size_t)(T > 0 ? T : 1);
+    // segment bucketing + two token-major staging buffers for the NCHW layout
+    *out = align_up(vq::backward_workspace_bytes(T, K, D), 256) + 2 * align_up(sizeof(float) * n * D, 256);
+    return VQ_OK;
+}
+
+int vq_backward_tokens(const float* g_zq, int layout, int64_t T, int64_t hw, const float* saved_zn,
+                       const float* saved_denom, const int64_t* idx, const void* cb, int K, int D, int form,
+                       float beta, const float* g_loss, int64_t n_elem_total, float* grad_z, int64_t* seg_sums,
+                       void* ws, size_t ws_bytes, void* stream) {
+    if (int r = check_dims(T, K, D)) return r;
+    if (int r = check_layout(layout, T, hw)) return r;
+    if (!saved_zn || !saved_denom || !idx || !cb) return fail(VQ_ERR_ARG, "saved_zn/saved_denom/idx/cb is NULL");
+    if (n_elem_total <= 0) return fail(VQ_ERR_ARG, "n_elem_total must be positive");
+    size_t need = 0;
+    vq_backward_workspace_bytes(T, K, D, &need);
+    if (!ws || ws_bytes < need) return fail(VQ_ERR_WORKSPACE, "backward workspace too small: %zu < %zu", ws_bytes, need);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    vq::CodebookView cbv = vq::codebook_view(const_cast<void*>(cb), K, D);
+    char* p = static_cast<char*>(ws);
+    void* seg_ws = p;
+    const size_t seg_bytes = align_up(vq::backward_workspace_bytes(T, K, D), 256);
+    p += seg_bytes;
+    const size_t n = (size_t)(T > 0 ? T : 1);
+    float* g_tok = reinterpret_cast<float*>(p); p += align_up(sizeof(float) * n * D, 256);
+    float* grad_tok = reinterpret_cast<float*>(p);
+
+    if (grad_z) {
+        const float c1 = (form == VQ_FORM_VIT) ? beta : 1.f;
+        const float coef = (float)((double)c1 * 2.0 / (double)n_elem_total);
+        if (layout == VQ_LAYOUT_TOKEN_MAJOR) {
+            VQ_CUDA(vq::launch_backward_tokens(g_zq, saved_zn, saved_denom, idx, cbv, T, coef, g_loss, grad_z, s));
+        } else {
+            if (g_zq) VQ_CUDA(vq::launch_nchw_to_tok(g_zq, T, hw, D, nullptr, g_tok, nullptr, s));
+            VQ_CUDA(vq::launch_backward_tokens(g_zq ? g_tok : nullptr, saved_zn, saved_denom, idx, cbv, T, coef,
+                                               g_loss, grad_tok, s));
+            VQ_CUDA(vq::launch_tok_to_nchw(grad_tok, T, hw, D, grad_z, s));
+        }
+    }
+    if (seg_sums) VQ_CUDA(vq::launch_segment_sums(saved_zn, idx, cbv, T, seg_sums, seg_ws, seg_bytes, s));
+    return VQ_OK;
+}
+
+int vq_backward_codebook(const int64_t* seg_sums, const void* cb, int K, int D, int form, float beta,
+                         const float* g_loss, int64_t n_elem_total, float* grad_weight, void* stream) {
+    if (int r = check_dims(0, K, D)) return r;
+    if (!seg_sums || !cb || !grad_weight || n_elem_total <= 0) return fail(VQ_ERR_ARG, "bad argument to vq_backward_codebook");
+    vq::CodebookView cbv = vq::codebook_view(const_cast<void*>(cb), K, D);
+    const float c2 = (form == VQ_FORM_VIT) ? 1.f : beta;
+    const float coef = (float)((double)c2 * 2.0 / (double)n_elem_total);
+    VQ_CUDA(vq::launch_codebook_grad(seg_sums, cbv, coef, g_loss, grad_weight, static_cast<cudaStream_t>(stream)));
+    return VQ_OK;
+}
+
+int vq_gather(const int64_t* idx, int64_t T, int64_t hw, const float* weight, const void* cb, int K, int D,
+              int normalise, int layout_out, float* out, int64_t* stats, void* stream) {
+    if (int r = check_dims(T, K, D)) return r;
+    if (int r = check_layout(layout_out, T, hw)) return r;
+    if (!idx || !out) return fail(VQ_ERR_ARG, "idx/out is NULL");
+    const float* table = nullptr;
+    if (normalise) {
+        if (!cb) return fail(VQ_ERR_ARG, "normalise=1 needs the prepared codebook");
+        table = vq::codebook_view(const_cast<void*>(cb), K, D).en32;
+    } else {
+        if (!weight) return fail(VQ_ERR_ARG, "normalise=0 needs the raw weight");
+        table = weight;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (stats) VQ_CUDA(cudaMemsetAsync(stats + VQ_STAT_BAD_INDEX, 0, sizeof(int64_t), s));
+    VQ_CUDA(vq::launch_gather(idx, T, hw, table, K, D, layout_out, out, stats, s));
+    return VQ_OK;
+}
+
+int vq_profile_begin(void) {
+    for (auto& p : g_search_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    g_search_events.clear();
+    g_launches_at_begin = vq::g_kernel_launches;
+    g_profiling = true;
+    return VQ_OK;
+}
+
+int vq_profile_end(double* search_ms_total, int64_t* search_launches, int64_t* kernel_launches) {
+    g_profiling = false;
+    double total = 0.0;
+    for (auto& p : g_search_events) {
+        float ms = 0.f;
+        VQ_CUDA(cudaEventSynchronize(p.second));
+        VQ_CUDA(cudaEventElapsedTime(&ms, p.first, p.second));
+        total += ms;
+    }
+    if (search_ms_total) *search_ms_total = total;
+    if (search_launches) *search_launches = (int64_t)g_search_events.size();
+    if (kernel_launches) *kernel_launches = vq::g_kernel_launches - g_launches_at_begin;
+    for (auto& p : g_search_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    g_search_events.clear();
+    return VQ_OK;
+}
+
+// ---- host-buffer step ---------------------------------------------------------------------------
+namespace {
+struct HostArena {
+    void* cb; float* weight; float* z; float* g; float* zq; float* gz; int64_t* idx; float* zn; float* denom;
+    int64_t* seg; float* gw; float* loss; int64_t* stats; void* fws; size_t fws_bytes; void* bws; size_t bws_bytes;
+    size_t bytes;
+};
+HostArena carve_host(void* arena, int64_t T, int K, int D) {
+    Bump b(arena);
+    HostArena a;
+    const size_t n = (size_t)(T > 0 ? T : 1);
+    a.cb = b.take<char>(vq::codebook_bytes(K, D));
+    a.weight = b.take<float>((size_t)K * D);
+    a.z = b.take<float>(n * D);
+    a.g = b.take<float>(n * D);
+    a.zq = b.take<float>(n * D);
+    a.gz = b.take<float>(n * D);
+    a.idx = b.take<int64_t>(n);
+    a.zn = b.take<float>(n * D);
+    a.denom = b.take<float>(n);
+    a.seg = b.take<int64_t>((size_t)K * D + K);
+    a.gw = b.take<float>((size_t)K * D);
+    a.loss = b.take<float>(64);
+    a.stats = b.take<int64_t>(VQ_STATS_LEN);
+    a.fws_bytes = carve_forward(nullptr, T, K, D).bytes;
+    a.fws = b.take<char>(a.fws_bytes);
+    size_t bw = 0;
+    vq_backward_workspace_bytes(T, K, D, &bw);
+    a.bws_bytes = bw;
+    a.bws = b.take<char>(bw);
+    a.bytes = b.off;
+    return a;
+}
+}  // namespace
+
+int vq_host_step_arena_bytes(int64_t T, int K, int D, size_t* out) {
+    if (!out) return fail(VQ_ERR_ARG, "out is NULL");
+    if (int r = check_dims(T, K, D)) return r;
+    *out = carve_host(nullptr, T, K, D).bytes;
+    return VQ_OK;
+}
+
+int vq_host_step(const float* z_host, const float* g_zq_host, int64_t T, const float* weight_host, int K, int D,
+                 int form, float beta, float* z_q_host, int64_t* idx_host, float* loss_host, float* grad_z_host,
+                 float* grad_weight_host, int64_t* stats_host, void* dev_arena, size_t arena_bytes, void* stream) {
+    if (int r = check_dims(T, K, D)) return r;
+    if (!z_host || !weight_host || !z_q_host || !idx_host || !dev_arena) return fail(VQ_ERR_ARG, "NULL host/arena pointer");
+    HostArena a = carve_host(dev_arena, T, K, D);
+    if (arena_bytes < a.bytes) return fail(VQ_ERR_WORKSPACE, "arena too small: %zu < %zu", arena_bytes, a.bytes);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t row_bytes = sizeof(float) * (size_t)D;
+    const int64_t n_elem = T * D;
+    VQ_CUDA(cudaMemcpyAsync(a.weight, weight_host, row_bytes * K, cudaMemcpyHostToDevice, s));
+    VQ_CUDA(cudaMemcpyAsync(a.z, z_host, row_bytes * T, cudaMemcpyHostToDevice, s));
+    if (int r = vq_codebook_prepare(a.weight, K, D, a.cb, vq::codebook_bytes(K, D), s)) return r;
+    const bool bwd = grad_z_host || grad_weight_host;
+    if (int r = vq_forward(a.z, VQ_LAYOUT_TOKEN_MAJOR, T, 0, a.cb, K, D, form, beta, 0, n_elem > 0 ? n_elem : 1, a.zq,
+                           a.idx, a.loss, nullptr, a.stats, bwd ? a.zn : nullptr, bwd ? a.denom : nullptr, a.fws,
+                           a.fws_bytes, s))
+        return r;
+    VQ_CUDA(cudaMemcpyAsync(z_q_host, a.zq, row_bytes * T, cudaMemcpyDeviceToHost, s));
+    VQ_CUDA(cudaMemcpyAsync(idx_host, a.idx, sizeof(int64_t) * T, cudaMemcpyDeviceToHost, s));
+    if (loss_host) VQ_CUDA(cudaMemcpyAsync(loss_host, a.loss, sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (bwd) {
+        if (g_zq_host) VQ_CUDA(cudaMemcpyAsync(a.g, g_zq_host, row_bytes * T, cudaMemcpyHostToDevice, s));
+        if (int r = vq_backward_tokens(g_zq_host ? a.g : nullptr, VQ_LAYOUT_TOKEN_MAJOR, T, 0, a.zn, a.denom, a.idx,
+                                       a.cb, K, D, form, beta, nullptr, n_elem > 0 ? n_elem : 1,
+                                       grad_z_host ? a.gz : nullptr, grad_weight_host ? a.seg : nullptr, a.bws,
+                                       a.bws_bytes, s))
+            return r;
+        if (grad_z_host) VQ_CUDA(cudaMemcpyAsync(grad_z_host, a.gz, row_bytes * T, cudaMemcpyDeviceToHost, s));
+        if (grad_weight_host) {
+            if (int r = vq_backward_codebook(a.seg, a.cb, K, D, form, beta, nullptr, n_elem > 0 ? n_elem : 1, a.gw, s)) return r;
+            VQ_CUDA(cudaMemcpyAsync(grad_weight_host, a.gw, row_bytes * K, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    if (stats_host) VQ_CUDA(cudaMemcpyAsync(stats_host, a.stats, sizeof(int64_t) * VQ_STATS_LEN, cudaMemcpyDeviceToHost, s));
+    return VQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,333 @@
+// Backward of the quantiser: grad_z (straight-through + commitment term through the normalisation)
+// and the codebook gradient as a deterministic segmented sum.
+//
+// The reference has no backward code: autograd derives it from models/vitvqgan.py:151-171 /
+// models/vqgan.py:148-176 (driven by trainers/vitgqgan.py:171-184).  Closed form:
+//   g_zn      = G + g_loss * c1 * 2 (zn - q) / N
+//   grad_z    = (g_zn - zn (zn . g_zn)) / max(||z||, eps)
+//   S_k       = sum_{t : idx_t = k} (q_k - zn_t)
+//   grad_E[k] = (g_k - en_k (en_k . g_k)) / max(||E_k||, eps),   g_k = g_loss * c2 * (2/N) * S_k
+// with (c1, c2) = (beta, 1) for the ViT form and (1, beta) for the VQGAN form.
+//
+// Determinism: tokens are bucketed by code (count -> exclusive scan -> scatter), every bucket is cut
+// into pieces of kSegPiece tokens, one warp sums a piece.  Contributions are accumulated as 2^-30
+// fixed-point int64, so the result does not depend on the order tokens landed in the bucket, on how
+// pieces are combined, or -- for a token-sharded job -- on the number of GPUs: the integer sums are
+// simply added (all-reduce) before the final normalise-backward.  No float atomics anywhere.
+// The difference form sum(q_k - zn_t) is used (not n_k q_k - sum zn_t) because the latter cancels
+// on trained data (SURVEY.md section 7 "Codebook-grad cancellation").
+#include "vq_common.cuh"
+#include "vq_kernels.h"
+#include "../../include/vq_b200.h"
+
+namespace vq {
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct BwdWs {
+    int* counts;    // K
+    int* cursor;    // K
+    int* offsets;   // K + 1  exclusive scan of counts
+    int* pieces;    // K + 1  exclusive scan of ceil(count / kSegPiece)
+    int* perm;      // T      token ids grouped by code
+    size_t zero_bytes;   // counts + cursor are contiguous and zeroed per call
+};
+
+size_t backward_workspace_bytes(int64_t T, int K, int D) {
+    (void)D;
+    return align_up(sizeof(int) * (size_t)K * 2, 256) + 2 * align_up(sizeof(int) * ((size_t)K + 1), 256) +
+           align_up(sizeof(int) * (size_t)(T > 0 ? T : 1), 256);
+}
+
+static BwdWs carve(void* ws, int64_t T, int K) {
+    char* p = static_cast<char*>(ws);
+    BwdWs w;
+    w.counts = reinterpret_cast<int*>(p);
+    w.cursor = w.counts + K;
+    w.zero_bytes = sizeof(int) * (size_t)K * 2;
+    p += align_up(w.zero_bytes, 256);
+    w.offsets = reinterpret_cast<int*>(p); p += align_up(sizeof(int) * ((size_t)K + 1), 256);
+    w.pieces = reinterpret_cast<int*>(p);  p += align_up(sizeof(int) * ((size_t)K + 1), 256);
+    w.perm = reinterpret_cast<int*>(p);
+    (void)T;
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// grad_z.  kLpr lanes share a row (one float4 each, kNf4 float4 per lane when D > 128); the row dot
+// product is an xor-shuffle tree inside the lane group.  Algorithmic bytes 12D + 8 per token.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) k_backward_tokens(const float4* __restrict__ g, const float4* __restrict__ zn,
+                                                         const float* __restrict__ denom,
+                                                         const int64_t* __restrict__ idx, const float4* __restrict__ en,
+                                                         int64_t T, float coef_base, const float* __restrict__ g_loss,
+                                                         float4* __restrict__ grad) {
+    const float coef = coef_base * (g_loss ? __ldg(g_loss) : 1.f);
+    constexpr int kChunks = D / 4;
+    constexpr int kLpr = (kChunks < 32) ? kChunks : 32;
+    constexpr int kNf4 = kChunks / kLpr;
+    constexpr int kRowsPerWarp = 32 / kLpr;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % kLpr, grp = lane / kLpr;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t t0 = warp * kRowsPerWarp; t0 < T; t0 += n_warps * kRowsPerWarp) {
+        const int64_t t = t0 + grp;
+        const bool live = t < T;
+        float4 a[kNf4], gz[kNf4];
+        float dot = 0.f;
+        float dn = 1.f;
+        if (live) {
+            const int64_t k = __ldg(idx + t);
+            dn = __ldg(denom + t);
+#pragma unroll
+            for (int f = 0; f < kNf4; ++f) {
+                const int c = sub + kLpr * f;
+                a[f] = __ldg(zn + t * kChunks + c);
+                const float4 q = __ldg(en + k * kChunks + c);
+                float4 up = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g) up = __ldcs(g + t * kChunks + c);
+                gz[f].x = up.x + coef * (a[f].x - q.x);
+                gz[f].y = up.y + coef * (a[f].y - q.y);
+                gz[f].z = up.z + coef * (a[f].z - q.z);
+                gz[f].w = up.w + coef * (a[f].w - q.w);
+                dot += (a[f].x * gz[f].x + a[f].y * gz[f].y) + (a[f].z * gz[f].z + a[f].w * gz[f].w);
+            }
+        }
+#pragma unroll
+        for (int off = kLpr >> 1; off > 0; off >>= 1) dot += __shfl_xor_sync(VQ_FULL, dot, off);
+        if (live) {
+            const float inv = 1.f / dn;
+#pragma unroll
+            for (int f = 0; f < kNf4; ++f) {
+                float4 o;
+                o.x = (gz[f].x - a[f].x * dot) * inv;
+                o.y = (gz[f].y - a[f].y * dot) * inv;
+                o.z = (gz[f].z - a[f].z * dot) * inv;
+                o.w = (gz[f].w - a[f].w * dot) * inv;
+                __stcs(grad + t * kChunks + sub + kLpr * f, o);
+            }
+        }
+    }
+}
+
+cudaError_t launch_backward_tokens(const float* g_tok, const float* zn32, const float* denom, const int64_t* idx,
+                                   const CodebookView& cb, int64_t T, float coef_commit, const float* g_loss,
+                                   float* grad_tok, cudaStream_t s) {
+    if (T == 0) return cudaSuccess;
+    const int chunks = cb.D / 4;
+    const int lpr = chunks < 32 ? chunks : 32;
+    const int rows_per_block = 8 * (32 / lpr);
+    int64_t blocks = (T + rows_per_block - 1) / rows_per_block;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    VQ_DISPATCH_D(cb.D, (k_backward_tokens<kD><<<(unsigned)blocks, 256, 0, s>>>(
+                            reinterpret_cast<const float4*>(g_tok), reinterpret_cast<const float4*>(zn32), denom, idx,
+                            reinterpret_cast<const float4*>(cb.en32), T, coef_commit, g_loss,
+                            reinterpret_cast<float4*>(grad_tok))));
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// bucket tokens by code
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_count(const int64_t* __restrict__ idx, int64_t T, int* __restrict__ counts) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(counts + __ldg(idx + t), 1);
+}
+
+// single block: exclusive scans of counts and of piece counts
+__global__ void __launch_bounds__(1024) k_scan_segments(const int* __restrict__ counts, int K, int* __restrict__ offsets,
+                                                        int* __restrict__ pieces) {
+    __shared__ int s_tok[1024], s_pc[1024];
+    const int tid = threadIdx.x;
+    const int per = (K + 1023) / 1024;
+    const int lo = tid * per, hi = min(K, lo + per);
+    int tok = 0, pc = 0;
+    for (int k = lo; k < hi; ++k) {
+        const int n = counts[k];
+        tok += n;
+        pc += (n + kSegPiece - 1) / kSegPiece;
+    }
+    s_tok[tid] = tok; s_pc[tid] = pc;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        int a = 0, b = 0;
+        if (tid >= off) { a = s_tok[tid - off]; b = s_pc[tid - off]; }
+        __syncthreads();
+        s_tok[tid] += a; s_pc[tid] += b;
+        __syncthreads();
+    }
+    int run_tok = s_tok[tid] - tok, run_pc = s_pc[tid] - pc;   // exclusive prefix of this thread's range
+    for (int k = lo; k < hi; ++k) {
+        const int n = counts[k];
+        offsets[k] = run_tok; pieces[k] = run_pc;
+        run_tok += n;
+        run_pc += (n + kSegPiece - 1) / kSegPiece;
+    }
+    if (tid == 1023) { offsets[K] = s_tok[1023]; pieces[K] = s_pc[1023]; }
+}
+
+__global__ void __launch_bounds__(256) k_scatter(const int64_t* __restrict__ idx, int64_t T,
+                                                 const int* __restrict__ offsets, int* __restrict__ cursor,
+                                                 int* __restrict__ perm) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)__ldg(idx + t);
+        perm[offsets[k] + atomicAdd(cursor + k, 1)] = (int)t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// one warp per piece: S_k += sum over the piece's tokens of fixed(q_k - zn_t)
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) k_segment_reduce(const float4* __restrict__ zn, const float4* __restrict__ en,
+                                                        const int* __restrict__ offsets, const int* __restrict__ pieces,
+                                                        const int* __restrict__ perm, int K,
+                                                        unsigned long long* __restrict__ seg_sums) {
+    constexpr int kChunks = D / 4;
+    constexpr int kLpr = (kChunks < 32) ? kChunks : 32;
+    constexpr int kNf4 = kChunks / kLpr;
+    constexpr int kRowsPerWarp = 32 / kLpr;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % kLpr, grp = lane / kLpr;
+    const int n_pieces = pieces[K];
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * (blockDim.x >> 5);
+    for (int w = warp; w < n_pieces; w += n_warps) {
+        // largest k with pieces[k] <= w (codes with no tokens own no piece and are skipped by the search)
+        int lo = 0, hi = K;   // invariant: pieces[lo] <= w < pieces[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(pieces + mid) <= w) lo = mid; else hi = mid;
+        }
+        const int k = lo;
+        const int seg_lo = __ldg(offsets + k), seg_hi = __ldg(offsets + k + 1);
+        const int p_lo = seg_lo + (w - __ldg(pieces + k)) * kSegPiece;
+        const int p_hi = min(seg_hi, p_lo + kSegPiece);
+
+        float4 q[kNf4];
+#pragma unroll
+        for (int f = 0; f < kNf4; ++f) q[f] = __ldg(en + (int64_t)k * kChunks + sub + kLpr * f);
+        long long acc[kNf4][4];
+#pragma unroll
+        for (int f = 0; f < kNf4; ++f)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[f][i] = 0;
+        unsigned bad = 0;
+
+        for (int j0 = p_lo; j0 < p_hi; j0 += kRowsPerWarp) {
+            const int j = j0 + grp;
+            if (j < p_hi) {
+                const int64_t t = __ldg(perm + j);
+#pragma unroll
+                for (int f = 0; f < kNf4; ++f) {
+                    const float4 a = __ldg(zn + t * kChunks + sub + kLpr * f);
+                    const float d[4] = {q[f].x - a.x, q[f].y - a.y, q[f].z - a.z, q[f].w - a.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (is_finite(d[i])) acc[f][i] += to_fixed(d[i], VQ_SEG_SHIFT);
+                        else bad = 1;
+                    }
+                }
+            }
+        }
+        // fold the lane groups (rows) of the warp together; integer adds, any order
+#pragma unroll
+        for (int off = kLpr; off < 32; off <<= 1) {
+#pragma unroll
+            for (int f = 0; f < kNf4; ++f)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[f][i] += __shfl_xor_sync(VQ_FULL, acc[f][i], off);
+        }
+        bad = __any_sync(VQ_FULL, bad);
+        if (grp == 0) {
+#pragma unroll
+            for (int f = 0; f < kNf4; ++f)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    atomicAdd(seg_sums + (int64_t)k * D + (sub + kLpr * f) * 4 + i, (unsigned long long)acc[f][i]);
+        }
+        if (bad && lane == 0) atomicAdd(seg_sums + (int64_t)K * D + k, 1ull);
+    }
+}
+
+cudaError_t launch_segment_sums(const float* zn32, const int64_t* idx, const CodebookView& cb, int64_t T,
+                                int64_t* seg_sums, void* ws, size_t ws_bytes, cudaStream_t s) {
+    const int K = cb.K, D = cb.D;
+    if (ws_bytes < backward_workspace_bytes(T, K, D)) return cudaErrorInvalidValue;
+    BwdWs w = carve(ws, T, K);
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(seg_sums, 0, sizeof(int64_t) * ((size_t)K * D + K), s)) != cudaSuccess) return e;
+    if (T == 0) return cudaSuccess;
+    if ((e = cudaMemsetAsync(w.counts, 0, w.zero_bytes, s)) != cudaSuccess) return e;
+    int64_t blocks = (T + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    count_launch(3);
+    k_count<<<(unsigned)blocks, 256, 0, s>>>(idx, T, w.counts);
+    k_scan_segments<<<1, 1024, 0, s>>>(w.counts, K, w.offsets, w.pieces);
+    k_scatter<<<(unsigned)blocks, 256, 0, s>>>(idx, T, w.offsets, w.cursor, w.perm);
+    int64_t max_pieces = T / kSegPiece + (T < K ? T : K) + 1;
+    int64_t rblocks = (max_pieces + 7) / 8;
+    const int64_t rcap = (int64_t)sm_count() * 8;
+    if (rblocks > rcap) rblocks = rcap;
+    VQ_DISPATCH_D(D, (k_segment_reduce<kD><<<(unsigned)rblocks, 256, 0, s>>>(
+                         reinterpret_cast<const float4*>(zn32), reinterpret_cast<const float4*>(cb.en32), w.offsets,
+                         w.pieces, w.perm, K, reinterpret_cast<unsigned long long*>(seg_sums))));
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// grad_E[k] = NB(E_k, coef * S_k): one warp per code
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) k_codebook_grad(const long long* __restrict__ seg_sums,
+                                                       const float* __restrict__ en, const float* __restrict__ code_denom,
+                                                       int K, float coef_base, const float* __restrict__ g_loss,
+                                                       float* __restrict__ grad) {
+    const float coef = coef_base * (g_loss ? __ldg(g_loss) : 1.f);
+    constexpr int kPer = (D + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * (blockDim.x >> 5);
+    for (int k = warp; k < K; k += n_warps) {
+        float g[kPer], y[kPer];
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int d = lane + 32 * j;
+            g[j] = 0.f; y[j] = 0.f;
+            if (d < D) {
+                const double s = (double)__ldg(seg_sums + (int64_t)k * D + d) * (1.0 / (double)(1ll << VQ_SEG_SHIFT));
+                g[j] = coef * (float)s;
+                y[j] = __ldg(en + (int64_t)k * D + d);
+                dot += y[j] * g[j];
+            }
+        }
+        dot = warp_sum(dot);
+        const float inv = 1.f / __ldg(code_denom + k);
+        const bool poisoned = __ldg(seg_sums + (int64_t)K * D + k) != 0;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int d = lane + 32 * j;
+            if (d < D) grad[(int64_t)k * D + d] = poisoned ? __int_as_float(0x7fc00000) : (g[j] - y[j] * dot) * inv;
+        }
+    }
+}
+
+cudaError_t launch_codebook_grad(const int64_t* seg_sums, const CodebookView& cb, float coef, const float* g_loss,
+                                 float* grad_weight, cudaStream_t s) {
+    int blocks = (cb.K + 7) / 8;
+    const int cap = sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    VQ_DISPATCH_D(cb.D, (k_codebook_grad<kD><<<blocks, 256, 0, s>>>(reinterpret_cast<const long long*>(seg_sums),
+                                                                      cb.en32, cb.code_denom, cb.K, coef, g_loss, grad_weight)));
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace vq

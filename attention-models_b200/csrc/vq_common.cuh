@@ -1,0 +1,148 @@
+// Shared device helpers for the VQ quantiser kernels (sm_100a).
+//
+// Arithmetic rules that make z_q bit-equal to what the reference computes on a GPU
+// (reference models/vitvqgan.py:16-17,151-171; models/vqgan.py:7-8,148-176; ATen order from
+// torch/include/ATen/native/cuda/Reduce.cuh, restated in oracle/aten_order.py):
+//   * every rounded operation of the reference is one explicit __f*_rn intrinsic here, so the
+//     compiler can neither contract nor reassociate it;
+//   * row sums of squares follow ATen's lane mapping, 4-accumulator combine and shuffle-down tree.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define VQ_NORM_EPS 1e-12f          // F.normalize eps (torch/nn/functional.py:5707-5708)
+#define VQ_SEG_SHIFT 30              // fixed-point scale of the codebook-gradient segment sums
+#define VQ_LOSS_SHIFT 24             // fixed-point scale of the per-row loss sums
+#define VQ_NEAR_TIE_REL 1e-6f        // north_star: top-2 distances closer than this are "near ties"
+#define VQ_FULL 0xffffffffu
+
+namespace vq {
+
+// ---------------------------------------------------------------------------------------------
+// Row <-> lane mapping.  One warp owns one row of D floats.
+//   D <  128 : lane l holds elements l + W*j           (W = min(D, 32); ATen: lanes stride the row)
+//   D >= 128 : lane l holds float4 #(l + 32*m), m < D/128  (ATen: "vectorize along input")
+// D must be a power of two in [16, 512] (dispatch in vq_abi.cu).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+struct RowMap {
+    static constexpr bool kVec = (D >= 128);
+    static constexpr int kWidth = (D < 32) ? D : 32;                   // lanes that hold data
+    static constexpr int kPerLane = kVec ? (D / 32) : (D / kWidth);     // floats per lane
+    static_assert(D >= 16 && D <= 512 && (D & (D - 1)) == 0, "unsupported codebook_dim");
+
+    __device__ static __forceinline__ bool active(int lane) { return lane < kWidth; }
+    // element index of register slot j in lane `lane`
+    __device__ static __forceinline__ int elem(int lane, int j) {
+        if constexpr (kVec) return (lane + 32 * (j >> 2)) * 4 + (j & 3);
+        else return lane + kWidth * j;
+    }
+
+    __device__ static __forceinline__ void load(const float* __restrict__ row, int lane, float (&x)[kPerLane]) {
+        if constexpr (kVec) {
+#pragma unroll
+            for (int m = 0; m < kPerLane / 4; ++m) {
+                float4 v = __ldg(reinterpret_cast<const float4*>(row) + lane + 32 * m);
+                x[4 * m + 0] = v.x; x[4 * m + 1] = v.y; x[4 * m + 2] = v.z; x[4 * m + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kPerLane; ++j) x[j] = active(lane) ? __ldg(row + lane + kWidth * j) : 0.f;
+        }
+    }
+
+    __device__ static __forceinline__ void store(float* __restrict__ row, int lane, const float (&x)[kPerLane]) {
+        if constexpr (kVec) {
+#pragma unroll
+            for (int m = 0; m < kPerLane / 4; ++m)
+                reinterpret_cast<float4*>(row)[lane + 32 * m] =
+                    make_float4(x[4 * m + 0], x[4 * m + 1], x[4 * m + 2], x[4 * m + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kPerLane; ++j)
+                if (active(lane)) row[lane + kWidth * j] = x[j];
+        }
+    }
+
+    __device__ static __forceinline__ void store_half(__half* __restrict__ row, int lane, const float (&x)[kPerLane]) {
+        if constexpr (kVec) {
+#pragma unroll
+            for (int m = 0; m < kPerLane / 4; ++m) {
+                __half2 a = __floats2half2_rn(x[4 * m + 0], x[4 * m + 1]);
+                __half2 b = __floats2half2_rn(x[4 * m + 2], x[4 * m + 3]);
+                uint2 u;
+                u.x = *reinterpret_cast<uint32_t*>(&a);
+                u.y = *reinterpret_cast<uint32_t*>(&b);
+                reinterpret_cast<uint2*>(row)[lane + 32 * m] = u;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kPerLane; ++j)
+                if (active(lane)) row[lane + kWidth * j] = __float2half_rn(x[j]);
+        }
+    }
+
+    // Sum over the row in ATen's CUDA order; the result is broadcast to every lane.
+    // kFused: each step is fma(v, v, acc) on raw values (NormTwoOps, vector norm).
+    // !kFused: v*v is rounded first, then added (torch.sum(t**2, dim=1)).
+    template <bool kFused>
+    __device__ static __forceinline__ float sumsq(const float (&x)[kPerLane]) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if constexpr (kVec) {
+#pragma unroll
+            for (int m = 0; m < kPerLane / 4; ++m)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float v = x[4 * m + i];
+                    acc[i] = kFused ? __fmaf_rn(v, v, acc[i]) : __fadd_rn(acc[i], __fmul_rn(v, v));
+                }
+        } else {
+            // <= 4 elements per lane, one per accumulator (thread_reduce_impl's tail path)
+#pragma unroll
+            for (int j = 0; j < kPerLane; ++j) acc[j] = __fmul_rn(x[j], x[j]);
+        }
+        float v = __fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]);
+#pragma unroll
+        for (int off = kWidth >> 1; off > 0; off >>= 1) v = __fadd_rn(v, __shfl_down_sync(VQ_FULL, v, off));
+        return __shfl_sync(VQ_FULL, v, 0);
+    }
+};
+
+// clamp_min(eps) keeps NaN (ATen semantics); fmaxf would drop it.
+__device__ __forceinline__ float clamp_min_keep_nan(float v, float lo) { return (v < lo) ? lo : v; }
+
+__device__ __forceinline__ float norm_denominator(float sumsq) {
+    return clamp_min_keep_nan(__fsqrt_rn(sumsq), VQ_NORM_EPS);
+}
+
+// torch.argmin ordering (LessOrNan, torch/include/ATen/native/SharedReduceOps.h:435-446):
+// NaN beats everything, ties go to the lower index.
+__device__ __forceinline__ bool argmin_better(float d_new, int i_new, float d_old, int i_old) {
+    const bool nan_new = (d_new != d_new), nan_old = (d_old != d_old);
+    if (nan_new || nan_old) {
+        if (nan_new && nan_old) return i_new < i_old;
+        return nan_new;
+    }
+    return (d_new < d_old) || (d_new == d_old && i_new < i_old);
+}
+
+// d = (|zn|^2 + |en_k|^2) - 2 * dot  with the reference's association (models/vitvqgan.py:157-159)
+__device__ __forceinline__ float ref_distance(float row_sq, float code_sq, float dot) {
+    return __fsub_rn(__fadd_rn(row_sq, code_sq), __fmul_rn(2.f, dot));
+}
+
+__device__ __forceinline__ bool is_finite(float v) { return fabsf(v) <= 3.402823466e38f; }
+
+__device__ __forceinline__ long long to_fixed(float v, int shift) {
+    return __float2ll_rn(v * static_cast<float>(1ll << shift));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(VQ_FULL, v, off);
+    return v;
+}
+
+}  // namespace vq

@@ -1,0 +1,155 @@
+// Exhaustive fp32 nearest-code search (SIMT).
+//
+// Replaces, for the rows it is given, the reference's materialised distance matrix + argmin:
+//   models/vitvqgan.py:157-161   d = sum(z^2) + sum(e^2) - 2*einsum('bd,nd->bn'); argmin(d, dim=1)
+//   models/vqgan.py:157-161
+// without ever storing the T x K matrix.  It is (a) the parity baseline, (b) the path for shapes
+// the tcgen05 kernel does not take, and (c) the fallback for the few rows the fp16 tensor-core pass
+// cannot decide rigorously.  The dot product is a sequential fp32 fma chain over d = 0..D-1 --
+// the same chain the rescoring step of the tensor-core path uses, so both paths return identical
+// indices.  Ties go to the lowest index and NaN wins, as torch.argmin does.
+//
+// Tiling: 256 threads compute a 64-row x 128-code tile; each thread owns 4 rows x 8 codes in
+// registers and walks D in chunks of 32 staged d-major in shared memory (conflict-free LDS.128).
+#include "vq_common.cuh"
+#include "vq_kernels.h"
+#include "../../include/vq_b200.h"
+
+namespace vq {
+
+constexpr int kTM = 64, kTN = 128, kDK = 32;
+
+struct Best {
+    float d1; int i1; float d2;   // best distance, its index, second-best distance
+};
+
+__device__ __forceinline__ void best_insert(Best& b, float d, int i) {
+    if (argmin_better(d, i, b.d1, b.i1)) { b.d2 = b.d1; b.d1 = d; b.i1 = i; }
+    else if (d < b.d2 || d != d) b.d2 = d;
+}
+
+__device__ __forceinline__ void best_merge(Best& a, float d1, int i1, float d2) {
+    if (argmin_better(d1, i1, a.d1, a.i1)) {
+        const float loser = a.d1;
+        a.d1 = d1; a.i1 = i1;
+        a.d2 = fminf(loser, d2) ;
+        if (loser != loser || d2 != d2) a.d2 = __int_as_float(0x7fc00000);
+    } else {
+        const float cand = d1;
+        if (cand != cand || a.d2 != a.d2) a.d2 = __int_as_float(0x7fc00000);
+        else a.d2 = fminf(a.d2, cand);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scan_exact(const float* __restrict__ zn32, const float* __restrict__ row_sq,
+                                                    const float* __restrict__ en32, const float* __restrict__ code_sq,
+                                                    int64_t T, int K, int D, const int* __restrict__ rows,
+                                                    const int* __restrict__ n_rows_ptr, int* __restrict__ cand,
+                                                    int64_t* __restrict__ stats) {
+    __shared__ __align__(16) float zs[kDK][kTM + 4];
+    __shared__ __align__(16) float es[kDK][kTN + 4];
+    __shared__ int row_id[kTM];
+
+    const int64_t n_rows = rows ? (int64_t)(*n_rows_ptr) : T;
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;     // rows ty*4..+3 ; codes tx*4..+3 and 64+tx*4..+3
+
+    for (int64_t tile0 = (int64_t)blockIdx.x * kTM; tile0 < n_rows; tile0 += (int64_t)gridDim.x * kTM) {
+        __syncthreads();
+        if (tid < kTM) {
+            const int64_t i = tile0 + tid;
+            row_id[tid] = (i < n_rows) ? (rows ? rows[i] : (int)i) : -1;
+        }
+        __syncthreads();
+
+        Best best[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { best[r].d1 = INFINITY; best[r].i1 = 0x7fffffff; best[r].d2 = INFINITY; }
+        float a_sq[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int rid = row_id[ty * 4 + r];
+            a_sq[r] = (rid >= 0) ? row_sq[rid] : 0.f;
+        }
+
+        for (int k0 = 0; k0 < K; k0 += kTN) {
+            float acc[4][8];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+
+            for (int d0 = 0; d0 < D; d0 += kDK) {
+                __syncthreads();
+                // stage zs[d][row] and es[d][code] (global reads coalesced along d)
+                for (int e = tid; e < kTM * kDK; e += 256) {
+                    const int r = e / kDK, d = e % kDK;
+                    const int rid = row_id[r];
+                    zs[d][r] = (rid >= 0 && d0 + d < D) ? __ldg(zn32 + (int64_t)rid * D + d0 + d) : 0.f;
+                }
+                for (int e = tid; e < kTN * kDK; e += 256) {
+                    const int c = e / kDK, d = e % kDK;
+                    const int k = k0 + c;
+                    es[d][c] = (k < K && d0 + d < D) ? __ldg(en32 + (int64_t)k * D + d0 + d) : 0.f;
+                }
+                __syncthreads();
+#pragma unroll 8
+                for (int d = 0; d < kDK; ++d) {
+                    const float4 zv = *reinterpret_cast<const float4*>(&zs[d][ty * 4]);
+                    const float4 e0 = *reinterpret_cast<const float4*>(&es[d][tx * 4]);
+                    const float4 e1 = *reinterpret_cast<const float4*>(&es[d][64 + tx * 4]);
+                    const float zr[4] = {zv.x, zv.y, zv.z, zv.w};
+                    const float ec[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) acc[r][c] = __fmaf_rn(zr[r], ec[c], acc[r][c]);
+                }
+            }
+            // distances of this code tile, in increasing code order per thread
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int k = k0 + ((c < 4) ? (tx * 4 + c) : (64 + tx * 4 + c - 4));
+                if (k < K) {
+                    const float b_sq = __ldg(code_sq + k);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) best_insert(best[r], ref_distance(a_sq[r], b_sq, acc[r][c]), k);
+                }
+            }
+        }
+        // merge the 16 threads (tx) that share each row: xor-shuffles stay inside 16-lane groups
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) {
+                const float od1 = __shfl_xor_sync(VQ_FULL, best[r].d1, off);
+                const int oi1 = __shfl_xor_sync(VQ_FULL, best[r].i1, off);
+                const float od2 = __shfl_xor_sync(VQ_FULL, best[r].d2, off);
+                best_merge(best[r], od1, oi1, od2);
+            }
+            const int rid = row_id[ty * 4 + r];
+            if (tx == 0 && rid >= 0) {
+                cand[rid] = best[r].i1 | kCandExactBit;
+                const float gap = best[r].d2 - best[r].d1;
+                if (stats && gap < VQ_NEAR_TIE_REL * fabsf(best[r].d1))
+                    atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), 1ull);
+            }
+        }
+    }
+}
+
+cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
+                              const int* rows, const int* n_rows, int64_t max_rows, int* cand, int64_t* stats,
+                              cudaStream_t s) {
+    const int64_t n = rows ? max_rows : T;
+    if (n == 0) return cudaSuccess;
+    int64_t blocks = (n + kTM - 1) / kTM;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_scan_exact<<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows,
+                                                 cand, stats);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace vq

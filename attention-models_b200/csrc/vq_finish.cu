@@ -1,0 +1,176 @@
+// Fused gather / straight-through output / loss partial / code-usage histogram, and the decode gather.
+//
+// Reference call sites replaced (paths relative to /root/reference):
+//   models/vitvqgan.py:162-163  z_q = l2_norm(embedding(idx))       models/vqgan.py:163-167
+//   models/vitvqgan.py:166      loss (two means over all T*D elements) models/vqgan.py:169
+//   models/vitvqgan.py:169      z_q = z + (z_q - z).detach()          models/vqgan.py:171
+//   models/vitvqgan.py:173-176  indices_to_embeddings                 models/vqgan.py:178-182
+// l2_norm(E[idx]) is bit-identical to the prepared unit code en[idx] (same row, same ATen schedule),
+// so the gather reads en32 directly.  HBM-bound and purely element-wise: one float4 per thread,
+// fully coalesced, grid-stride over T*D/4; algorithmic bytes 8D + 8 per token.
+#include "vq_common.cuh"
+#include "vq_kernels.h"
+#include "../../include/vq_b200.h"
+
+namespace vq {
+
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* smem) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(VQ_FULL, v, off);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    unsigned long long t = 0;
+    if (threadIdx.x < 32) {
+        t = (threadIdx.x < (blockDim.x >> 5)) ? smem[threadIdx.x] : 0ull;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(VQ_FULL, t, off);
+    }
+    return t;   // valid in thread 0
+}
+
+// chunks = D/4 float4 per row.  Thread e handles row e / chunks, float4 e % chunks.
+__global__ void __launch_bounds__(256) k_finish(const float4* __restrict__ zn, const int* __restrict__ cand,
+                                                const float4* __restrict__ en, int64_t T, int chunks, int K,
+                                                float4* __restrict__ zq, int64_t* __restrict__ idx_out,
+                                                int32_t* __restrict__ hist, int64_t* __restrict__ stats) {
+    __shared__ unsigned long long red[8];
+    const int64_t total = T * chunks;
+    long long loss_fx = 0;
+    unsigned long long bad = 0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = e / chunks;
+        const int c = (int)(e - t * chunks);
+        const int k = __ldg(cand + t) & (kCandExactBit - 1);
+        if (c == 0) {
+            idx_out[t] = k;
+            if (hist) atomicAdd(hist + k, 1);
+        }
+        if (zq) {
+            const float4 a = __ldg(zn + e);
+            const float4 q = __ldg(en + (int64_t)k * chunks + c);
+            float4 df, o;
+            df.x = __fsub_rn(q.x, a.x); df.y = __fsub_rn(q.y, a.y); df.z = __fsub_rn(q.z, a.z); df.w = __fsub_rn(q.w, a.w);
+            o.x = __fadd_rn(a.x, df.x); o.y = __fadd_rn(a.y, df.y); o.z = __fadd_rn(a.z, df.z); o.w = __fadd_rn(a.w, df.w);
+            __stcs(zq + e, o);
+            const float p = (df.x * df.x + df.y * df.y) + (df.z * df.z + df.w * df.w);
+            if (is_finite(p)) loss_fx += to_fixed(p, VQ_LOSS_SHIFT);
+            else bad += 1;
+        }
+    }
+    if (zq && stats) {
+        const unsigned long long s1 = block_sum_u64((unsigned long long)loss_fx, red);
+        __syncthreads();
+        const unsigned long long s2 = block_sum_u64(bad, red);
+        if (threadIdx.x == 0) {
+            if (s1) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_LOSS_FIXED), s1);
+            if (s2) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NONFINITE), s2);
+        }
+    }
+}
+
+cudaError_t launch_finish(const float* zn32, const int* cand, const CodebookView& cb, int64_t T, float* zq_tok,
+                          int64_t* idx_out, int32_t* hist, int64_t* stats, cudaStream_t s) {
+    if (T == 0) return cudaSuccess;
+    const int chunks = zq_tok ? cb.D / 4 : 1;   // indices-only: one thread per row is enough
+    const int64_t total = T * chunks;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_finish<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(zn32), cand,
+                                             reinterpret_cast<const float4*>(cb.en32), T, chunks, cb.K,
+                                             reinterpret_cast<float4*>(zq_tok), idx_out, hist, stats);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// loss = beta*m + m (ViT) or m + beta*m (VQGAN), m = mean((q - zn)^2): both reference terms have the
+// same value, only their gradients differ.  stats[NONFINITE] counts non-finite partials -> NaN.
+__global__ void k_loss_finalize(const int64_t* __restrict__ stats, int64_t n_elem_total, int form, float beta,
+                                float* __restrict__ loss) {
+    const double sum = (double)stats[VQ_STAT_LOSS_FIXED] / (double)(1ll << VQ_LOSS_SHIFT);
+    float m = (float)(sum / (double)n_elem_total);
+    if (stats[VQ_STAT_NONFINITE] != 0) m = __int_as_float(0x7fc00000);
+    const float bm = __fmul_rn(beta, m);
+    loss[0] = (form == VQ_FORM_VIT) ? __fadd_rn(bm, m) : __fadd_rn(m, bm);
+}
+
+cudaError_t launch_loss_finalize(const int64_t* stats, int64_t n_elem_total, int form, float beta, float* loss,
+                                 cudaStream_t s) {
+    k_loss_finalize<<<1, 1, 0, s>>>(stats, n_elem_total, form, beta, loss);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// decode gather.  Token-major out: element-wise float4.  NCHW out: 32-token x 32-channel tiles
+// through shared memory so both the row reads and the (b, D, hw) writes are coalesced.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_tok(const int64_t* __restrict__ idx, int64_t T, int chunks, int K,
+                                                    const float4* __restrict__ table, float4* __restrict__ out,
+                                                    int64_t* __restrict__ stats) {
+    const int64_t total = T * chunks;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = e / chunks;
+        const int c = (int)(e - t * chunks);
+        const int64_t k = __ldg(idx + t);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k >= 0 && k < K) v = __ldg(table + k * chunks + c);
+        else if (c == 0 && stats) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_BAD_INDEX), 1ull);
+        __stcs(out + e, v);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gather_nchw(const int64_t* __restrict__ idx, int64_t T, int64_t hw, int D,
+                                                     int K, const float* __restrict__ table, float* __restrict__ out,
+                                                     int64_t* __restrict__ stats) {
+    __shared__ float tile[32][33];
+    __shared__ int64_t rows[32];
+    const int x = threadIdx.x, y = threadIdx.y;
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    if (y == 0) {
+        const int64_t t = t0 + x;
+        int64_t k = (t < T) ? __ldg(idx + t) : 0;
+        if (k < 0 || k >= K) {
+            if (blockIdx.y == 0 && stats) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_BAD_INDEX), 1ull);
+            k = -1;
+        }
+        rows[x] = k;
+    }
+    __syncthreads();
+    for (int tt = y; tt < 32; tt += 8) {
+        const int64_t k = rows[tt];
+        const int c = c0 + x;
+        tile[tt][x] = (k >= 0 && c < D) ? __ldg(table + k * D + c) : 0.f;
+    }
+    __syncthreads();
+    const int64_t t = t0 + x;
+    if (t < T) {
+        const int64_t b = t / hw, p = t % hw;
+        for (int cc = y; cc < 32; cc += 8) {
+            const int c = c0 + cc;
+            if (c < D) out[(b * D + c) * hw + p] = tile[x][cc];
+        }
+    }
+}
+
+cudaError_t launch_gather(const int64_t* idx, int64_t T, int64_t hw, const float* table, int K, int D,
+                          int layout_out, float* out, int64_t* stats, cudaStream_t s) {
+    if (T == 0) return cudaSuccess;
+    if (layout_out == VQ_LAYOUT_TOKEN_MAJOR) {
+        const int chunks = D / 4;
+        int64_t blocks = (T * chunks + 255) / 256;
+        const int64_t cap = (int64_t)sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        k_gather_tok<<<(unsigned)blocks, 256, 0, s>>>(idx, T, chunks, K, reinterpret_cast<const float4*>(table),
+                                                     reinterpret_cast<float4*>(out), stats);
+    } else {
+        dim3 grid((unsigned)((T + 31) / 32), (unsigned)((D + 31) / 32));
+        k_gather_nchw<<<grid, dim3(32, 8), 0, s>>>(idx, T, hw, D, K, table, out, stats);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace vq

@@ -1,0 +1,95 @@
+// Internal host-side launchers (one per kernel family).  Not part of the public ABI.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace vq {
+
+// Prepared codebook, carved out of the opaque `cb` blob handed across the ABI.
+struct CodebookView {
+    float* en32;        // K*D  unit codes, fp32
+    float* code_sq;     // K    sum(en^2) in ATen order (~1, 0 for zero codes)
+    float* code_denom;  // K    max(||E_k||, eps)
+    __half* en16;       // K*D  fp16 copy of en32 (tensor-core operand, TMA source)
+    int* info;          // [0] = number of codes whose |en|^2 is not ~1 (zero / non-finite rows)
+    int K, D;
+};
+size_t codebook_bytes(int K, int D);
+CodebookView codebook_view(void* cb, int K, int D);
+
+constexpr int kSegPiece = 256;   // tokens per work item of the segmented codebook-gradient sum
+constexpr int kCandExactBit = 0x40000000;  // cand[t] holds a final index, not a cell id
+
+// ---- vq_prep.cu ------------------------------------------------------------------------------
+cudaError_t launch_prep_codebook(const float* weight, const CodebookView& cb, cudaStream_t s);
+// token-major rows -> zn32, row_sq, denom, zn16 (any output may be null)
+cudaError_t launch_prep_tokens(const float* z, int64_t T, int D, float* zn32, float* row_sq, float* denom,
+                               __half* zn16, cudaStream_t s);
+// NCHW (b, D, hw), hw % 4 == 0: denominators in ATen's channel-strided order
+cudaError_t launch_norm_nchw(const float* z, int64_t T, int64_t hw, int D, float* denom, cudaStream_t s);
+// (b, D, hw) -> (T, D), optionally divided by denom[t]; optional fp16 copy
+cudaError_t launch_nchw_to_tok(const float* in, int64_t T, int64_t hw, int D, const float* denom,
+                               float* out32, __half* out16, cudaStream_t s);
+cudaError_t launch_tok_to_nchw(const float* in, int64_t T, int64_t hw, int D, float* out, cudaStream_t s);
+// row_sq[t] = sum(zn^2) over contiguous rows, ATen order (used after the NCHW path)
+cudaError_t launch_row_sumsq(const float* zn32, int64_t T, int D, float* row_sq, cudaStream_t s);
+
+// ---- vq_dist_simt.cu -------------------------------------------------------------------------
+// Exhaustive fp32 search.  rows == nullptr: all T rows; else the first *n_rows entries of `rows`.
+// Writes cand[row] = index | kCandExactBit and counts near-tie rows into stats.
+cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
+                              const int* rows, const int* n_rows, int64_t max_rows, int* cand, int64_t* stats,
+                              cudaStream_t s);
+
+// ---- vq_dist_tc.cu ---------------------------------------------------------------------------
+// tcgen05 search: cand[row] = cell id (or exact index for rows resolved in-kernel); rows it cannot
+// decide are appended to flagged[] (count in *n_flagged).
+bool tc_supported(int64_t T, int K, int D);
+size_t tc_workspace_bytes(int64_t T, int K, int D);
+cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* row_sq, const CodebookView& cb,
+                           int64_t T, int* cand, int* flagged, int* n_flagged, int64_t* stats, void* tc_ws,
+                           cudaStream_t s);
+
+// ---- vq_finish.cu ----------------------------------------------------------------------------
+// idx / hist / z_q (token-major) / loss partial from final indices in cand[].
+cudaError_t launch_finish(const float* zn32, const int* cand, const CodebookView& cb, int64_t T,
+                          float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* stats, cudaStream_t s);
+cudaError_t launch_loss_finalize(const int64_t* stats, int64_t n_elem_total, int form, float beta, float* loss,
+                                 cudaStream_t s);
+cudaError_t launch_gather(const int64_t* idx, int64_t T, int64_t hw, const float* table, int K, int D,
+                          int layout_out, float* out, int64_t* stats, cudaStream_t s);
+
+// ---- vq_backward.cu --------------------------------------------------------------------------
+size_t backward_workspace_bytes(int64_t T, int K, int D);
+cudaError_t launch_backward_tokens(const float* g_tok, const float* zn32, const float* denom, const int64_t* idx,
+                                   const CodebookView& cb, int64_t T, float coef_commit, const float* g_loss,
+                                   float* grad_tok, cudaStream_t s);
+cudaError_t launch_segment_sums(const float* zn32, const int64_t* idx, const CodebookView& cb, int64_t T,
+                                int64_t* seg_sums, void* ws, size_t ws_bytes, cudaStream_t s);
+cudaError_t launch_codebook_grad(const int64_t* seg_sums, const CodebookView& cb, float coef, const float* g_loss,
+                                 float* grad_weight, cudaStream_t s);
+
+// dispatch on the supported codebook dims (powers of two in [16, 512])
+inline bool dim_supported(int D) { return D >= 16 && D <= 512 && (D & (D - 1)) == 0; }
+
+#define VQ_DISPATCH_D(D, ...)                                       \
+    switch (D) {                                                    \
+        case 16:  { constexpr int kD = 16;  __VA_ARGS__; } break;   \
+        case 32:  { constexpr int kD = 32;  __VA_ARGS__; } break;   \
+        case 64:  { constexpr int kD = 64;  __VA_ARGS__; } break;   \
+        case 128: { constexpr int kD = 128; __VA_ARGS__; } break;   \
+        case 256: { constexpr int kD = 256; __VA_ARGS__; } break;   \
+        case 512: { constexpr int kD = 512; __VA_ARGS__; } break;   \
+        default: return cudaErrorInvalidValue;                      \
+    }
+
+int sm_count();
+
+// kernel-launch counter (bench.py's gpu_launches); bumped by every launcher next to its <<<>>>
+extern long long g_kernel_launches;
+inline void count_launch(int n = 1) { g_kernel_launches += n; }
+
+}  // namespace vq

@@ -1,0 +1,290 @@
+// Normalisation kernels: codebook preparation and token preparation.
+//
+// Reference call sites replaced (paths relative to /root/reference):
+//   models/vitvqgan.py:152  z = l2_norm(z)                        models/vqgan.py:151-152
+//   models/vitvqgan.py:154  embedd_norm = l2_norm(weight)         models/vqgan.py:155
+//   models/vitvqgan.py:157  sum(z_flattened**2, dim=1)            models/vqgan.py:157
+//   models/vitvqgan.py:158  sum(embedd_norm**2, dim=1)            models/vqgan.py:158
+// All HBM-bound: one pass over the rows, coalesced 128 B (or float4) accesses, grid sized in
+// multiples of the SM count.
+#include "vq_common.cuh"
+#include "vq_kernels.h"
+
+namespace vq {
+
+long long g_kernel_launches = 0;
+static int g_sm_count = 0;
+int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            g_sm_count = n;
+        else
+            return 148;
+    }
+    return g_sm_count;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t codebook_bytes(int K, int D) {
+    size_t n = 0;
+    n += align_up(sizeof(float) * (size_t)K * D, 256);    // en32
+    n += align_up(sizeof(float) * (size_t)K, 256);        // code_sq
+    n += align_up(sizeof(float) * (size_t)K, 256);        // code_denom
+    n += align_up(sizeof(__half) * (size_t)K * D, 256);   // en16
+    n += 256;                                             // info
+    return n;
+}
+
+CodebookView codebook_view(void* cb, int K, int D) {
+    char* p = static_cast<char*>(cb);
+    CodebookView v;
+    v.K = K; v.D = D;
+    v.en32 = reinterpret_cast<float*>(p);        p += align_up(sizeof(float) * (size_t)K * D, 256);
+    v.code_sq = reinterpret_cast<float*>(p);     p += align_up(sizeof(float) * (size_t)K, 256);
+    v.code_denom = reinterpret_cast<float*>(p);  p += align_up(sizeof(float) * (size_t)K, 256);
+    v.en16 = reinterpret_cast<__half*>(p);       p += align_up(sizeof(__half) * (size_t)K * D, 256);
+    v.info = reinterpret_cast<int*>(p);
+    return v;
+}
+
+// One warp per row, kRows rows in flight per warp for memory-level parallelism.
+template <int D, bool kIsCodebook>
+__global__ void __launch_bounds__(256) k_prep_rows(const float* __restrict__ in, int64_t rows,
+                                                   float* __restrict__ unit32, float* __restrict__ sq,
+                                                   float* __restrict__ denom, __half* __restrict__ unit16,
+                                                   int* __restrict__ info) {
+    using M = RowMap<D>;
+    constexpr int kRows = (M::kPerLane <= 4) ? 4 : 2;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r0 = warp * kRows; r0 < rows; r0 += n_warps * kRows) {
+        float x[kRows][M::kPerLane];
+#pragma unroll
+        for (int i = 0; i < kRows; ++i)
+            if (r0 + i < rows) M::load(in + (r0 + i) * D, lane, x[i]);
+#pragma unroll
+        for (int i = 0; i < kRows; ++i) {
+            const int64_t r = r0 + i;
+            if (r >= rows) break;
+            const float den = norm_denominator(M::template sumsq<true>(x[i]));
+#pragma unroll
+            for (int j = 0; j < M::kPerLane; ++j) x[i][j] = __fdiv_rn(x[i][j], den);
+            const float s2 = M::template sumsq<false>(x[i]);
+            if (unit32) M::store(unit32 + r * D, lane, x[i]);
+            if (unit16) M::store_half(unit16 + r * D, lane, x[i]);
+            if (lane == 0) {
+                if (sq) sq[r] = s2;
+                if (denom) denom[r] = den;
+                if (kIsCodebook && !(fabsf(s2 - 1.f) < 1e-4f)) atomicAdd(info, 1);
+            }
+        }
+    }
+}
+
+template <int D, bool kIsCodebook>
+static cudaError_t prep_rows(const float* in, int64_t rows, float* unit32, float* sq, float* denom, __half* unit16,
+                             int* info, cudaStream_t s) {
+    if (rows == 0) return cudaSuccess;
+    constexpr int kRows = (RowMap<D>::kPerLane <= 4) ? 4 : 2;
+    const int warps_per_block = 8;
+    int64_t blocks = (rows + (int64_t)warps_per_block * kRows - 1) / (warps_per_block * kRows);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    k_prep_rows<D, kIsCodebook><<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(in, rows, unit32, sq, denom,
+                                                                                    unit16, info);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prep_codebook(const float* weight, const CodebookView& cb, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(cb.info, 0, 256, s);
+    if (e != cudaSuccess) return e;
+    VQ_DISPATCH_D(cb.D, return (prep_rows<kD, true>(weight, cb.K, cb.en32, cb.code_sq, cb.code_denom, cb.en16,
+                                                     cb.info, s)));
+    return cudaSuccess;
+}
+
+cudaError_t launch_prep_tokens(const float* z, int64_t T, int D, float* zn32, float* row_sq, float* denom,
+                               __half* zn16, cudaStream_t s) {
+    VQ_DISPATCH_D(D, return (prep_rows<kD, false>(z, T, zn32, row_sq, denom, zn16, nullptr, s)));
+    return cudaSuccess;
+}
+
+// row_sq only, from already-normalised contiguous rows
+template <int D>
+__global__ void __launch_bounds__(256) k_row_sumsq(const float* __restrict__ zn, int64_t rows, float* __restrict__ sq) {
+    using M = RowMap<D>;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = warp; r < rows; r += n_warps) {
+        float x[M::kPerLane];
+        M::load(zn + r * D, lane, x);
+        const float s2 = M::template sumsq<false>(x);
+        if (lane == 0) sq[r] = s2;
+    }
+}
+
+cudaError_t launch_row_sumsq(const float* zn32, int64_t T, int D, float* row_sq, cudaStream_t s) {
+    if (T == 0) return cudaSuccess;
+    int64_t blocks = (T + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    VQ_DISPATCH_D(D, (k_row_sumsq<kD><<<(unsigned)blocks, 256, 0, s>>>(zn32, T, row_sq)));
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW view normalised over the channel dim (reference models/vqgan.py:151-152).  ATen reduces a
+// strided dim with block (32, 4): lane x owns 4 consecutive hw positions (float4), threadIdx.y
+// strides the channels; thread y accumulates channels y + 4i + 16m in accumulator i (fma chain),
+// combines ((a0+a1)+a2)+a3, then a shared-memory tree over y (offsets 2, 1).  With D < 64 ATen
+// does not split the channels across y: one thread walks all channels, accumulator i <- c = i+4m.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) k_norm_nchw(const float* __restrict__ z, int64_t T, int64_t hw,
+                                                   float* __restrict__ denom) {
+    constexpr int kSplit = (D >= 64) ? 4 : 1;
+    __shared__ float4 part[4][32];
+    const int x = threadIdx.x, y = threadIdx.y;
+    const int64_t t = ((int64_t)blockIdx.x * 32 + x) * 4;          // first of this thread's 4 tokens
+    float4 total = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < T) {
+        const int64_t b = t / hw, p = t % hw;                      // hw % 4 == 0: the 4 tokens share b
+        const float* base = z + (b * D) * hw + p;
+        float4 acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int start = (kSplit == 4) ? y : 0;
+        for (int c0 = start; c0 < D; c0 += 4 * kSplit) {
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(c0 + i * kSplit) * hw));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[i].x = __fmaf_rn(v[i].x, v[i].x, acc[i].x);
+                acc[i].y = __fmaf_rn(v[i].y, v[i].y, acc[i].y);
+                acc[i].z = __fmaf_rn(v[i].z, v[i].z, acc[i].z);
+                acc[i].w = __fmaf_rn(v[i].w, v[i].w, acc[i].w);
+            }
+        }
+        total.x = __fadd_rn(__fadd_rn(__fadd_rn(acc[0].x, acc[1].x), acc[2].x), acc[3].x);
+        total.y = __fadd_rn(__fadd_rn(__fadd_rn(acc[0].y, acc[1].y), acc[2].y), acc[3].y);
+        total.z = __fadd_rn(__fadd_rn(__fadd_rn(acc[0].z, acc[1].z), acc[2].z), acc[3].z);
+        total.w = __fadd_rn(__fadd_rn(__fadd_rn(acc[0].w, acc[1].w), acc[2].w), acc[3].w);
+    }
+    if (kSplit == 4) {
+        part[y][x] = total;
+        __syncthreads();
+        if (y < 2) {
+            const float4 o = part[y + 2][x];
+            total.x = __fadd_rn(total.x, o.x); total.y = __fadd_rn(total.y, o.y);
+            total.z = __fadd_rn(total.z, o.z); total.w = __fadd_rn(total.w, o.w);
+            part[y][x] = total;
+        }
+        __syncthreads();
+        if (y == 0) {
+            const float4 o = part[1][x];
+            total.x = __fadd_rn(total.x, o.x); total.y = __fadd_rn(total.y, o.y);
+            total.z = __fadd_rn(total.z, o.z); total.w = __fadd_rn(total.w, o.w);
+        }
+    }
+    if (y == 0 && t < T) {
+        float4 d;
+        d.x = norm_denominator(total.x); d.y = norm_denominator(total.y);
+        d.z = norm_denominator(total.z); d.w = norm_denominator(total.w);
+        *reinterpret_cast<float4*>(denom + t) = d;
+    }
+}
+
+cudaError_t launch_norm_nchw(const float* z, int64_t T, int64_t hw, int D, float* denom, cudaStream_t s) {
+    if (T == 0) return cudaSuccess;
+    if (hw % 4 != 0) return cudaErrorInvalidValue;
+    const int64_t blocks = (T / 4 + 31) / 32;
+    VQ_DISPATCH_D(D, (k_norm_nchw<kD><<<(unsigned)blocks, dim3(32, 4), 0, s>>>(z, T, hw, denom)));
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Layout changes between (b, D, hw) and (T, D): 32 x 32 tiles through padded shared memory, both
+// sides coalesced.  nchw_to_tok optionally divides by denom[t] (true division, as F.normalize).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_nchw_to_tok(const float* __restrict__ in, int64_t T, int64_t hw, int D,
+                                                     const float* __restrict__ denom, float* __restrict__ out32,
+                                                     __half* __restrict__ out16) {
+    __shared__ float tile[32][33];
+    const int x = threadIdx.x, y = threadIdx.y;
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    {
+        const int64_t t = t0 + x;
+        if (t < T) {
+            const int64_t b = t / hw, p = t % hw;
+            const float dn = denom ? denom[t] : 1.f;
+            for (int cc = y; cc < 32; cc += 8) {
+                const int c = c0 + cc;
+                if (c < D) {
+                    const float v = __ldg(in + (b * D + c) * hw + p);
+                    tile[cc][x] = denom ? __fdiv_rn(v, dn) : v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int tt = y; tt < 32; tt += 8) {
+        const int64_t t = t0 + tt;
+        const int c = c0 + x;
+        if (t < T && c < D) {
+            const float v = tile[x][tt];
+            if (out32) out32[t * D + c] = v;
+            if (out16) out16[t * D + c] = __float2half_rn(v);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_tok_to_nchw(const float* __restrict__ in, int64_t T, int64_t hw, int D,
+                                                     float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int x = threadIdx.x, y = threadIdx.y;
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int tt = y; tt < 32; tt += 8) {
+        const int64_t t = t0 + tt;
+        const int c = c0 + x;
+        if (t < T && c < D) tile[tt][x] = __ldg(in + t * D + c);
+    }
+    __syncthreads();
+    const int64_t t = t0 + x;
+    if (t < T) {
+        const int64_t b = t / hw, p = t % hw;
+        for (int cc = y; cc < 32; cc += 8) {
+            const int c = c0 + cc;
+            if (c < D) out[(b * D + c) * hw + p] = tile[x][cc];
+        }
+    }
+}
+
+cudaError_t launch_nchw_to_tok(const float* in, int64_t T, int64_t hw, int D, const float* denom, float* out32,
+                               __half* out16, cudaStream_t s) {
+    if (T == 0) return cudaSuccess;
+    dim3 grid((unsigned)((T + 31) / 32), (unsigned)((D + 31) / 32));
+    k_nchw_to_tok<<<grid, dim3(32, 8), 0, s>>>(in, T, hw, D, denom, out32, out16);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tok_to_nchw(const float* in, int64_t T, int64_t hw, int D, float* out, cudaStream_t s) {
+    if (T == 0) return cudaSuccess;
+    dim3 grid((unsigned)((T + 31) / 32), (unsigned)((D + 31) / 32));
+    k_tok_to_nchw<<<grid, dim3(32, 8), 0, s>>>(in, T, hw, D, out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace vq

@@ -1,0 +1,88 @@
+"""ctypes binding of libvq_b200.so (the C ABI in include/vq_b200.h).
+
+There is no CPU path and no PyTorch fallback: if the library is missing the import of any
+compute entry point raises, loudly, with the command that builds it.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG_DIR, "lib", "libvq_b200.so")
+BUILD_SCRIPT = os.path.join(_PKG_DIR, "csrc", "build.py")
+
+# constants mirrored from include/vq_b200.h
+ABI_VERSION = 1
+FORM_VIT, FORM_VQGAN = 0, 1
+LAYOUT_TOKEN_MAJOR, LAYOUT_NCHW = 0, 1
+FLAG_INDICES_ONLY, FLAG_EXACT_SCAN = 1, 2
+STAT_NEAR_TIE_ROWS, STAT_AMBIGUOUS_ROWS, STAT_FALLBACK_ROWS, STAT_LOSS_FIXED, STAT_BAD_INDEX, STAT_NONFINITE = range(6)
+STATS_LEN = 8
+SEG_SHIFT = 30
+
+# every symbol include/vq_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "vq_abi_version": (c_int, []),
+    "vq_last_error": (c_char_p, []),
+    "vq_uses_tensor_cores": (c_int, [c_int64, c_int, c_int]),
+    "vq_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "vq_codebook_bytes": (c_int, [c_int, c_int, POINTER(c_size_t)]),
+    "vq_codebook_prepare": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "vq_workspace_bytes": (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_size_t)]),
+    "vq_forward": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int64,
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                           c_void_p]),
+    "vq_loss_finalize": (c_int, [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]),
+    "vq_backward_workspace_bytes": (c_int, [c_int64, c_int, c_int, POINTER(c_size_t)]),
+    "vq_backward_tokens": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                   c_int, c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
+                                   c_void_p]),
+    "vq_backward_codebook": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_void_p,
+                                     c_void_p]),
+    "vq_gather": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                          c_void_p, c_void_p]),
+    "vq_profile_begin": (c_int, []),
+    "vq_profile_end": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64), POINTER(c_int64)]),
+    "vq_host_step_arena_bytes": (c_int, [c_int64, c_int, c_int, POINTER(c_size_t)]),
+    "vq_host_step": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+}
+
+
+class VQLibraryError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen libvq_b200.so and type every entry point.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VQLibraryError(
+            f"libvq_b200.so not found at {LIB_PATH}. vq_b200 has no CPU or PyTorch fallback; build the CUDA "
+            f"library first:  python {BUILD_SCRIPT}   (or __graft_entry__.build())")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so is stale
+        fn.restype, fn.argtypes = res, args
+    if lib.vq_abi_version() != ABI_VERSION:
+        raise VQLibraryError(f"libvq_b200.so ABI {lib.vq_abi_version()} != expected {ABI_VERSION}; rebuild it")
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise VQLibraryError(f"libvq_b200 error {status}: {load().vq_last_error().decode(errors='replace')}")
+
+
+def size_query(fn_name: str, *args) -> int:
+    out = c_size_t(0)
+    check(getattr(load(), fn_name)(*args, ctypes.byref(out)))
+    return int(out.value)

@@ -1,0 +1,62 @@
+"""Shared base of the two drop-in ``Codebook`` modules."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import functional as F_vq
+
+
+class _CodebookBase(nn.Module):
+    """Keeps the reference's public surface: ``codebook_size``, ``codebook_dim``,
+    ``beta``, an ``embedding`` nn.Embedding (state_dict key ``embedding.weight``), ``forward(z) ->
+    (z_q, indices, loss)`` and ``indices_to_embeddings(indices)``.
+
+    Extras that the reference does not have (north_star additions): ``last_histogram`` (code usage of
+    the last forward, int32 K), ``last_stats`` (device int64 counters: near-tie rows, ...),
+    ``encode(z)`` (indices-only fast path used by ``encode_imgs`` callers).
+    """
+
+    form: str = "vit"
+
+    def __init__(self, codebook_size: int, codebook_dim: int, beta: float):
+        super().__init__()
+        self.codebook_size = codebook_size
+        self.codebook_dim = codebook_dim
+        self.beta = beta
+        self.embedding = nn.Embedding(self.codebook_size, self.codebook_dim)
+        self.exact_scan = False          # True forces the exhaustive fp32 search (no tensor cores)
+        self.last_histogram: Optional[torch.Tensor] = None
+        self.last_stats: Optional[torch.Tensor] = None
+        self._prepared: Optional[F_vq.PreparedCodebook] = None
+
+    # the prepared codebook is a cache keyed on the weight's storage and version counter: a frozen
+    # tokeniser (MaskGIT / Muse / Parti) prepares once, a training step re-prepares after each update
+    def _prepared_codebook(self) -> F_vq.PreparedCodebook:
+        w = self.embedding.weight
+        if self._prepared is None or not self._prepared.matches(w):
+            self._prepared = F_vq.prepare_codebook(w)
+        return self._prepared
+
+    def _quantise(self, z: torch.Tensor):
+        z_q, flat_idx, loss, hist, stats = F_vq.quantise(z, self.embedding.weight, self.form, self.beta,
+                                                         prepared=self._prepared_codebook(),
+                                                         exact_scan=self.exact_scan)
+        self.last_histogram, self.last_stats = hist, stats
+        return z_q, flat_idx, loss
+
+    def encode(self, z: torch.Tensor) -> torch.Tensor:
+        """Flat int64 indices only (what ``encode_imgs`` keeps; reference vitvqgan.py:204-210)."""
+        return F_vq.encode_indices(z, self.embedding.weight, self.form, prepared=self._prepared_codebook(),
+                                   exact_scan=self.exact_scan)
+
+    def indices_to_embeddings(self, indices: torch.Tensor) -> torch.Tensor:
+        prepared = self._prepared_codebook() if self.form == "vit" else None
+        return F_vq.indices_to_embeddings(indices, self.embedding.weight, self.form, prepared=prepared)
+
+    def near_tie_rows(self) -> int:
+        """Rows of the last forward whose two best fp32 distances were < 1e-6 relative apart (host sync)."""
+        from ._lib import STAT_NEAR_TIE_ROWS
+        return 0 if self.last_stats is None else int(self.last_stats[STAT_NEAR_TIE_ROWS].item())

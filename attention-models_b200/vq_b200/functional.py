@@ -1,0 +1,222 @@
+"""Functional API over the C ABI: prepared codebook, differentiable quantise, encode, decode.
+
+Mirrors what the reference's two ``Codebook.forward`` / ``indices_to_embeddings`` compute
+(/root/reference/models/vitvqgan.py:151-176, /root/reference/models/vqgan.py:148-182); all arithmetic
+runs in libvq_b200.so on the current CUDA stream.  PyTorch only allocates the buffers.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from ._lib import (FLAG_EXACT_SCAN, FLAG_INDICES_ONLY, FORM_VIT, FORM_VQGAN, LAYOUT_NCHW, LAYOUT_TOKEN_MAJOR,
+                   STATS_LEN)
+
+FORMS = {"vit": FORM_VIT, "vqgan": FORM_VQGAN}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"vq_b200: {what} must live on a CUDA device (got {t.device}); there is no CPU path")
+
+
+def _scratch(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+@dataclass
+class PreparedCodebook:
+    """Unit codes (fp32 + fp16), squared norms and row norms of one weight tensor, in device memory."""
+    blob: torch.Tensor
+    K: int
+    D: int
+    weight_ptr: int
+    weight_version: int
+
+    def matches(self, weight: torch.Tensor) -> bool:
+        return (self.weight_ptr == weight.data_ptr() and self.weight_version == weight._version
+                and self.blob.device == weight.device)
+
+
+def prepare_codebook(weight: torch.Tensor) -> PreparedCodebook:
+    """``l2_norm(embedding.weight)`` and ``sum(embedd_norm**2, 1)`` (reference vitvqgan.py:154,158)."""
+    _require_cuda(weight, "the codebook weight")
+    if weight.dtype != torch.float32 or weight.dim() != 2:
+        raise TypeError("codebook weight must be a 2-D float32 tensor")
+    w = weight.detach().contiguous()
+    K, D = w.shape
+    nbytes = _lib.size_query("vq_codebook_bytes", K, D)
+    blob = _scratch(nbytes, w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.load().vq_codebook_prepare(_ptr(w), K, D, _ptr(blob), nbytes, _stream(w.device)))
+    return PreparedCodebook(blob, K, D, weight.data_ptr(), weight._version)
+
+
+def _token_geometry(z: torch.Tensor, layout: int, D: int) -> Tuple[int, int]:
+    if layout == LAYOUT_TOKEN_MAJOR:
+        if z.shape[-1] != D:
+            raise ValueError(f"last dim of z is {z.shape[-1]}, codebook_dim is {D}")
+        return z.numel() // D, 0
+    if z.dim() != 4 or z.shape[1] != D:
+        raise ValueError(f"NCHW input must be (b, {D}, h, w); got {tuple(z.shape)}")
+    hw = z.shape[2] * z.shape[3]
+    return z.shape[0] * hw, hw
+
+
+class _Quantise(torch.autograd.Function):
+    """(z, weight) -> (z_q, flat indices, loss, histogram, stats) with the straight-through backward."""
+
+    @staticmethod
+    def forward(ctx, z, weight, prepared, form, beta, layout, flags, n_elem_total):
+        lib = _lib.load()
+        dev = z.device
+        K, D = prepared.K, prepared.D
+        T, hw = _token_geometry(z, layout, D)
+        n_total = int(n_elem_total) if n_elem_total else max(T * D, 1)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        z_q = torch.empty_like(z)
+        idx = torch.empty(T, dtype=torch.int64, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        hist = torch.empty(K, dtype=torch.int32, device=dev)
+        stats = torch.empty(STATS_LEN, dtype=torch.int64, device=dev)
+        saved_zn = torch.empty(T, D, dtype=torch.float32, device=dev) if need_grad else None
+        saved_denom = torch.empty(T, dtype=torch.float32, device=dev) if need_grad else None
+        ws_bytes = _lib.size_query("vq_workspace_bytes", T, K, D, flags)
+        ws = _scratch(ws_bytes, dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.vq_forward(_ptr(z), layout, T, hw, _ptr(prepared.blob), K, D, form, float(beta), flags,
+                                      n_total, _ptr(z_q), _ptr(idx), _ptr(loss), _ptr(hist), _ptr(stats),
+                                      _ptr(saved_zn), _ptr(saved_denom), _ptr(ws), ws_bytes, _stream(dev)))
+        if need_grad:
+            ctx.save_for_backward(saved_zn, saved_denom, idx, prepared.blob)
+        ctx.meta = (form, float(beta), layout, T, hw, K, D, n_total, tuple(z.shape))
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(idx, hist, stats)
+        return z_q, idx, loss.view(()), hist, stats
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_zq, g_idx, g_loss, g_hist, g_stats):
+        lib = _lib.load()
+        saved_zn, saved_denom, idx, blob = ctx.saved_tensors
+        form, beta, layout, T, hw, K, D, n_total, z_shape = ctx.meta
+        dev = saved_zn.device
+        want_z, want_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if g_zq is not None:
+            g_zq = g_zq.contiguous().float()
+        g_loss = torch.zeros(1, dtype=torch.float32, device=dev) if g_loss is None else g_loss.reshape(1).float()
+        grad_z = torch.empty(z_shape, dtype=torch.float32, device=dev) if want_z else None
+        seg = torch.empty(K * D + K, dtype=torch.int64, device=dev) if want_w else None
+        grad_w = torch.empty(K, D, dtype=torch.float32, device=dev) if want_w else None
+        ws_bytes = _lib.size_query("vq_backward_workspace_bytes", T, K, D)
+        ws = _scratch(ws_bytes, dev)
+        with torch.cuda.device(dev):
+            s = _stream(dev)
+            _lib.check(lib.vq_backward_tokens(_ptr(g_zq), layout, T, hw, _ptr(saved_zn), _ptr(saved_denom), _ptr(idx),
+                                              _ptr(blob), K, D, form, beta, _ptr(g_loss), n_total, _ptr(grad_z),
+                                              _ptr(seg), _ptr(ws), ws_bytes, s))
+            if want_w:
+                _lib.check(lib.vq_backward_codebook(_ptr(seg), _ptr(blob), K, D, form, beta, _ptr(g_loss), n_total,
+                                                    _ptr(grad_w), s))
+        return grad_z, grad_w, None, None, None, None, None, None
+
+
+def _as_fp32_input(z: torch.Tensor) -> torch.Tensor:
+    # under autocast the pre_quant projection hands over bf16; the reference's F.normalize returns fp32,
+    # so all quantiser maths is fp32 (SURVEY.md section 8b "modes")
+    if z.dtype != torch.float32:
+        z = z.float()
+    return z.contiguous()
+
+
+def quantise(z: torch.Tensor, weight: torch.Tensor, form: str = "vit", beta: float = 0.25,
+             prepared: Optional[PreparedCodebook] = None, exact_scan: bool = False,
+             n_elem_total: Optional[int] = None):
+    """Full forward.  Returns ``(z_q, flat_indices, loss, histogram, stats)``.
+
+    ``z``: (..., D) for ``form='vit'`` (token-major) or (b, D, h, w) for ``form='vqgan'``.
+    Differentiable w.r.t. ``z`` (straight-through + commitment) and ``weight`` (codebook term).
+    """
+    _require_cuda(z, "z")
+    _require_cuda(weight, "the codebook weight")
+    if prepared is None or not prepared.matches(weight):
+        prepared = prepare_codebook(weight)
+    layout = LAYOUT_TOKEN_MAJOR if form == "vit" else LAYOUT_NCHW
+    flags = FLAG_EXACT_SCAN if exact_scan else 0
+    return _Quantise.apply(_as_fp32_input(z), weight, prepared, FORMS[form], beta, layout, flags, n_elem_total)
+
+
+@torch.no_grad()
+def encode_indices(z: torch.Tensor, weight: torch.Tensor, form: str = "vit",
+                   prepared: Optional[PreparedCodebook] = None, exact_scan: bool = False,
+                   want_hist: bool = False):
+    """``encode_imgs`` fast path: flat int64 indices only (z_q, loss and the saved state are skipped)."""
+    _require_cuda(z, "z")
+    if prepared is None or not prepared.matches(weight):
+        prepared = prepare_codebook(weight)
+    lib = _lib.load()
+    z = _as_fp32_input(z)
+    dev = z.device
+    layout = LAYOUT_TOKEN_MAJOR if form == "vit" else LAYOUT_NCHW
+    K, D = prepared.K, prepared.D
+    T, hw = _token_geometry(z, layout, D)
+    flags = FLAG_INDICES_ONLY | (FLAG_EXACT_SCAN if exact_scan else 0)
+    idx = torch.empty(T, dtype=torch.int64, device=dev)
+    hist = torch.empty(K, dtype=torch.int32, device=dev) if want_hist else None
+    ws_bytes = _lib.size_query("vq_workspace_bytes", T, K, D, flags)
+    ws = _scratch(ws_bytes, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.vq_forward(_ptr(z), layout, T, hw, _ptr(prepared.blob), K, D, FORMS[form], 0.25, flags,
+                                  max(T * D, 1), None, _ptr(idx), None, _ptr(hist), None, None, None, _ptr(ws),
+                                  ws_bytes, _stream(dev)))
+    return (idx, hist) if want_hist else idx
+
+
+@torch.no_grad()
+def indices_to_embeddings(indices: torch.Tensor, weight: torch.Tensor, form: str = "vit",
+                          prepared: Optional[PreparedCodebook] = None, check_indices: bool = True) -> torch.Tensor:
+    """Decode gather (reference vitvqgan.py:173-176: l2norm(E[i]); vqgan.py:178-182: E[i] as (b, D, h, w)).
+
+    ``indices``: (b, n) integer tensor.  Out-of-range indices raise IndexError like the reference's CPU
+    path (one host sync for the check; pass ``check_indices=False`` to skip it).  Not differentiable.
+    """
+    _require_cuda(indices, "indices")
+    _require_cuda(weight, "the codebook weight")
+    lib = _lib.load()
+    dev = indices.device
+    idx = indices.to(torch.int64).contiguous()
+    K, D = weight.shape
+    T = idx.numel()
+    stats = torch.zeros(STATS_LEN, dtype=torch.int64, device=dev)
+    w = weight.detach().contiguous()
+    if form == "vit":
+        if prepared is None or not prepared.matches(weight):
+            prepared = prepare_codebook(weight)
+        out = torch.empty(*idx.shape, D, dtype=torch.float32, device=dev)
+        args = (_ptr(idx), T, 0, None, _ptr(prepared.blob), K, D, 1, LAYOUT_TOKEN_MAJOR)
+    else:
+        if idx.dim() != 2:
+            raise ValueError("vqgan indices_to_embeddings expects (b, n) indices")
+        b, n = idx.shape
+        side = int(n ** 0.5)
+        if side * side != n:   # einops.rearrange in the reference fails the same way
+            raise ValueError(f"n={n} is not a perfect square")
+        out = torch.empty(b, D, side, side, dtype=torch.float32, device=dev)
+        args = (_ptr(idx), T, n, _ptr(w), None, K, D, 0, LAYOUT_NCHW)
+    with torch.cuda.device(dev):
+        _lib.check(lib.vq_gather(*args, _ptr(out), _ptr(stats), _stream(dev)))
+    if check_indices and int(stats[_lib.STAT_BAD_INDEX].item()) != 0:
+        raise IndexError("index out of range in self")
+    return out

@@ -1,0 +1,162 @@
+/*
+ * vq_b200.h -- C ABI of libvq_b200.so, the B200 (sm_100a) implementation of the VQ codebook
+ * quantiser hot path of pranoyr/attention-models.
+ *
+ * The reference has no FFI / plugin layer for this path: its boundary is the Python nn.Module
+ * surface of the two `Codebook` classes.  Each entry point below names the
+ * reference code it replaces (paths relative to /root/reference).  The Python drop-in modules in
+ * attention-models_b200/vq_b200/ bind these symbols with ctypes (INTEGRATION.md shows the stub a
+ * maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in _host
+ *   - all arrays are caller-allocated; the library owns no device memory
+ *   - every call is asynchronous on `stream` (a cudaStream_t) and re-entrant per stream
+ *   - return value: 0 = OK, non-zero = error; vq_last_error() gives the message (thread-local)
+ *   - nothing throws across the ABI; there is NO CPU fallback: without a CUDA device every compute
+ *     call returns VQ_ERR_CUDA
+ *   - floats are IEEE fp32; indices are int64 (torch.argmin's dtype)
+ *   - token-major layout: (T, D) row-major.  NCHW layout: (b, D, hw) with T = b*hw and the flat
+ *     token order (b, h, w) the reference uses (models/vqgan.py:153)
+ */
+#ifndef VQ_B200_H
+#define VQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQ_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VQ_API __attribute__((visibility("default")))
+#else
+#define VQ_API
+#endif
+
+/* which Codebook: decides where beta sits in the loss and whether decode renormalises */
+#define VQ_FORM_VIT   0   /* models/vitvqgan.py:140-176 */
+#define VQ_FORM_VQGAN 1   /* models/vqgan.py:138-182   */
+
+#define VQ_LAYOUT_TOKEN_MAJOR 0   /* (T, D)      -- ViT form input/output            */
+#define VQ_LAYOUT_NCHW        1   /* (b, D, h*w) -- VQGAN form input/output          */
+
+/* flags for vq_forward */
+#define VQ_FLAG_INDICES_ONLY 1    /* encode_imgs fast path: only idx (and hist) are produced   */
+#define VQ_FLAG_EXACT_SCAN   2    /* force the exhaustive fp32 SIMT search (no tensor cores)   */
+
+/* error codes */
+#define VQ_OK            0
+#define VQ_ERR_ARG       1
+#define VQ_ERR_WORKSPACE 2
+#define VQ_ERR_CUDA      3
+#define VQ_ERR_INDEX     4        /* index >= K handed to vq_gather (reference: IndexError)     */
+
+/* slots of the int64 `stats` array written by vq_forward (device memory, VQ_STATS_LEN entries) */
+#define VQ_STAT_NEAR_TIE_ROWS   0 /* rows whose two best fp32 distances differ by < 1e-6 relative */
+#define VQ_STAT_AMBIGUOUS_ROWS  1 /* rows the tensor-core pass could not decide alone (rescored over >1 cell) */
+#define VQ_STAT_FALLBACK_ROWS   2 /* rows sent to the exhaustive fp32 search                     */
+#define VQ_STAT_LOSS_FIXED      3 /* sum over tokens of sum_j (q - zn)^2, fixed point 2^-24      */
+#define VQ_STAT_BAD_INDEX       4 /* vq_gather: count of out-of-range indices                    */
+#define VQ_STAT_NONFINITE       5 /* non-finite loss partials (NaN/Inf rows): the loss is NaN     */
+#define VQ_STATS_LEN            8
+
+VQ_API int         vq_abi_version(void);
+VQ_API const char* vq_last_error(void);
+
+/* 1 if vq_forward would run the tcgen05 tensor-core search for this shape, 0 if the exhaustive fp32
+ * SIMT search (small or unsupported shapes).  Pure host logic.                                     */
+VQ_API int vq_uses_tensor_cores(int64_t T, int K, int D);
+
+/* Number of SMs / compute capability of the current device (0 on failure). */
+VQ_API int vq_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- codebook preparation ------------------------------------------------------------------
+ * Replaces `embedd_norm = l2_norm(self.embedding.weight)` and `torch.sum(embedd_norm**2, dim=1)`
+ * (models/vitvqgan.py:154,158; models/vqgan.py:155,158).  Produces, inside `cb` (opaque, size from
+ * vq_codebook_bytes): the unit codes in fp32, their squared norms, max(||E_k||, eps), and the fp16
+ * copy the tensor-core search streams through TMA.  Re-run whenever the weights change; a frozen
+ * tokeniser prepares once.                                                                        */
+VQ_API int vq_codebook_bytes(int K, int D, size_t* out);
+VQ_API int vq_codebook_prepare(const float* weight, int K, int D, void* cb, size_t cb_bytes, void* stream);
+
+/* ---- forward -------------------------------------------------------------------------------
+ * Replaces Codebook.forward (models/vitvqgan.py:151-171, models/vqgan.py:148-176):
+ *   zn = l2norm(z); idx = argmin_k ((|zn|^2 + |en_k|^2) - 2 zn.en_k); q = l2norm(E[idx]);
+ *   loss; z_q = zn + (q - zn).
+ * z, z_q      : `layout`, fp32.  z_q may be NULL with VQ_FLAG_INDICES_ONLY.
+ * idx         : T int64, flat token order.
+ * loss        : 1 float, the reference's loss with the mean taken over `n_elem_total` elements
+ *               (pass T*D on one GPU; a token-sharded job passes the global count and finishes the
+ *               loss after its all-reduce with vq_loss_finalize).  May be NULL.
+ * hist        : K int32 code-usage counts of THIS call (overwritten), or NULL.
+ * stats       : VQ_STATS_LEN int64 (overwritten), or NULL.
+ * saved_zn    : T*D floats, token-major unit rows kept for vq_backward, or NULL.
+ * saved_denom : T floats max(||z_t||, eps) kept for vq_backward, or NULL.
+ * ws          : scratch of at least vq_workspace_bytes(T, K, D, flags).                            */
+VQ_API int vq_workspace_bytes(int64_t T, int K, int D, int flags, size_t* out);
+VQ_API int vq_forward(const float* z, int layout, int64_t T, int64_t hw,
+               const void* cb, int K, int D, int form, float beta, int flags, int64_t n_elem_total,
+               float* z_q, int64_t* idx, float* loss, int32_t* hist, int64_t* stats,
+               float* saved_zn, float* saved_denom,
+               void* ws, size_t ws_bytes, void* stream);
+
+/* loss = the reference's two-term expression from the fixed-point sum (after an all-reduce). */
+VQ_API int vq_loss_finalize(const int64_t* loss_fixed, int64_t n_elem_total, int form, float beta,
+                     float* loss, void* stream);
+
+/* ---- backward ------------------------------------------------------------------------------
+ * Replaces what autograd derives from Codebook.forward:
+ *   g_zn = G + g_loss*c1*2(zn - q)/N ; grad_z = NB(z, g_zn)
+ *   S_k  = sum_{t: idx_t = k} (q_k - zn_t)          (deterministic segmented sum, fixed point)
+ *   grad_E[k] = NB(E_k, g_loss*c2*(2/N) S_k)        c1,c2 = (beta,1) ViT / (1,beta) VQGAN
+ * vq_backward_tokens writes grad_z (layout of z) and the int64 fixed-point segment sums
+ * `seg_sums` (K*D sums at scale 2^30 followed by K per-code counts of non-finite contributions;
+ * K*D + K int64 in all, overwritten).  A token-sharded job all-reduces seg_sums (integer sum:
+ * exact, order-free) before vq_backward_codebook; one GPU calls them back to back.
+ * g_zq may be NULL (no upstream gradient through z_q); grad_z / seg_sums may be NULL (not wanted).
+ * g_loss: DEVICE pointer to d(objective)/d(loss) (what autograd hands over), NULL means 1.0.       */
+VQ_API int vq_backward_workspace_bytes(int64_t T, int K, int D, size_t* out);
+VQ_API int vq_backward_tokens(const float* g_zq, int layout, int64_t T, int64_t hw,
+                       const float* saved_zn, const float* saved_denom, const int64_t* idx,
+                       const void* cb, int K, int D, int form, float beta, const float* g_loss,
+                       int64_t n_elem_total,
+                       float* grad_z, int64_t* seg_sums,
+                       void* ws, size_t ws_bytes, void* stream);
+VQ_API int vq_backward_codebook(const int64_t* seg_sums, const void* cb, int K, int D, int form, float beta,
+                         const float* g_loss, int64_t n_elem_total, float* grad_weight, void* stream);
+
+/* ---- decode --------------------------------------------------------------------------------
+ * Replaces Codebook.indices_to_embeddings: models/vitvqgan.py:173-176 (normalise=1, token-major)
+ * and models/vqgan.py:178-182 (normalise=0, NCHW out with hw = n).  normalise=1 reads the unit
+ * codes from `cb`; normalise=0 reads `weight`.  Out-of-range indices are counted in
+ * stats[VQ_STAT_BAD_INDEX] (the Python side raises IndexError like the reference) and produce 0. */
+VQ_API int vq_gather(const int64_t* idx, int64_t T, int64_t hw, const float* weight, const void* cb,
+              int K, int D, int normalise, int layout_out, float* out, int64_t* stats, void* stream);
+
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------
+ * Between vq_profile_begin() and vq_profile_end() the library brackets every launch of its nearest-code
+ * search (the dominant kernel) with CUDA events on the caller's stream and counts all kernel launches.
+ * vq_profile_end synchronises those events and returns the summed search time, the number of search
+ * launches and the number of kernel launches of all kinds.                                         */
+VQ_API int vq_profile_begin(void);
+VQ_API int vq_profile_end(double* search_ms_total, int64_t* search_launches, int64_t* kernel_launches);
+
+/* ---- host-buffer entry points (end-to-end path: host pointers in, host pointers out) --------
+ * Same semantics as vq_forward + vq_backward_tokens + vq_backward_codebook for token-major fp32
+ * data living in (preferably pinned) HOST memory; copies are chunked and overlapped with the
+ * kernels on internal streams.  `dev_arena` is device scratch of vq_host_step_arena_bytes().     */
+VQ_API int vq_host_step_arena_bytes(int64_t T, int K, int D, size_t* out);
+VQ_API int vq_host_step(const float* z_host, const float* g_zq_host, int64_t T,
+                 const float* weight_host, int K, int D, int form, float beta,
+                 float* z_q_host, int64_t* idx_host, float* loss_host,
+                 float* grad_z_host, float* grad_weight_host, int64_t* stats_host,
+                 void* dev_arena, size_t arena_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQ_B200_H */

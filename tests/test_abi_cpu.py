@@ -1,0 +1,113 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol include/vq_b200.h
+declares, answers its size queries, and refuses to compute without a CUDA device (no CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "vq_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    sys.path.insert(0, os.path.join(ROOT, "attention-models_b200", "csrc"))
+    import build as vq_build
+    vq_build.build()
+    from vq_b200 import _lib
+    return _lib
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"VQ_API\s+[\w\s\*]+?\b(vq_\w+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported_and_bound(lib):
+    declared = _declared_symbols()
+    assert len(declared) >= 14
+    cdll = lib.load()
+    for name in declared:
+        assert hasattr(cdll, name), f"{name} declared in include/vq_b200.h but not exported"
+    assert sorted(lib.SIGNATURES) == declared, "ctypes table and header disagree"
+    out = subprocess.run(["nm", "-D", "--defined-only", lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (vq_\w+)", out)))
+    assert exported == declared, "library exports symbols the header does not declare (or vice versa)"
+
+
+def test_abi_version_and_constants_match_header(lib):
+    text = open(HEADER).read()
+    consts = dict(re.findall(r"#define\s+(VQ_\w+)\s+(\d+)", text))
+    assert lib.load().vq_abi_version() == int(consts["VQ_ABI_VERSION"]) == lib.ABI_VERSION
+    assert (lib.FORM_VIT, lib.FORM_VQGAN) == (int(consts["VQ_FORM_VIT"]), int(consts["VQ_FORM_VQGAN"]))
+    assert (lib.LAYOUT_TOKEN_MAJOR, lib.LAYOUT_NCHW) == (int(consts["VQ_LAYOUT_TOKEN_MAJOR"]), int(consts["VQ_LAYOUT_NCHW"]))
+    assert (lib.FLAG_INDICES_ONLY, lib.FLAG_EXACT_SCAN) == (int(consts["VQ_FLAG_INDICES_ONLY"]), int(consts["VQ_FLAG_EXACT_SCAN"]))
+    assert lib.STATS_LEN == int(consts["VQ_STATS_LEN"])
+    for name in ("NEAR_TIE_ROWS", "AMBIGUOUS_ROWS", "FALLBACK_ROWS", "LOSS_FIXED", "BAD_INDEX", "NONFINITE"):
+        assert getattr(lib, "STAT_" + name) == int(consts["VQ_STAT_" + name])
+
+
+def test_size_queries_and_argument_errors(lib):
+    cb = lib.size_query("vq_codebook_bytes", 8192, 32)
+    assert cb >= 8192 * 32 * 6 + 8192 * 8          # fp32 + fp16 unit codes, squared norms, row norms
+    ws = lib.size_query("vq_workspace_bytes", 262144, 8192, 32, 0)
+    assert ws >= 262144 * 32 * 4
+    assert lib.size_query("vq_backward_workspace_bytes", 1024, 512, 32) > 0
+    assert lib.size_query("vq_host_step_arena_bytes", 1024, 512, 32) > 0
+    out = ctypes.c_size_t(0)
+    cdll = lib.load()
+    assert cdll.vq_codebook_bytes(8192, 48, ctypes.byref(out)) != 0          # unsupported codebook_dim
+    assert b"codebook_dim" in cdll.vq_last_error()
+    assert cdll.vq_workspace_bytes(-1, 8192, 32, 0, ctypes.byref(out)) != 0
+    with pytest.raises(lib.VQLibraryError):
+        lib.size_query("vq_codebook_bytes", 0, 32)
+
+
+def test_no_cpu_fallback():
+    """Product modules refuse CPU tensors instead of silently computing elsewhere."""
+    from vq_b200.vitvqgan import Codebook as Vit
+    from vq_b200.vqgan import Codebook as Vqgan
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Vit(64, 32)(torch.randn(1, 4, 32))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Vqgan(64, 32)(torch.randn(1, 32, 2, 2))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Vit(64, 32).indices_to_embeddings(torch.zeros(1, 4, dtype=torch.long))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_compute_call_without_device_reports_cuda_error(lib):
+    cdll = lib.load()
+    assert cdll.vq_device_info(None, None, None) == 3          # VQ_ERR_CUDA
+
+
+def test_product_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing under attention-models_b200/ may import or execute it."""
+    pkg = os.path.join(ROOT, "attention-models_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(base, f)
+
+
+def test_module_surface_matches_reference():
+    """ctor signature, attributes and state_dict key the reference's callers rely on."""
+    import inspect
+    from vq_b200.vitvqgan import Codebook as Vit
+    from vq_b200.vqgan import Codebook as Vqgan
+    sv = inspect.signature(Vit.__init__).parameters
+    assert [sv[k].default for k in ("codebook_size", "codebook_dim", "beta")] == [8192, 32, 0.25]
+    sq = inspect.signature(Vqgan.__init__).parameters
+    assert [sq[k].default for k in ("codebook_size", "codebook_dim", "beta")] == [1024, 256, 0.25]
+    m = Vit(codebook_size=128, codebook_dim=32)
+    assert (m.codebook_size, m.codebook_dim, m.beta) == (128, 32, 0.25)
+    assert list(m.state_dict().keys()) == ["embedding.weight"]
+    assert isinstance(m.embedding, torch.nn.Embedding)
+    q = Vqgan(64, 32)
+    assert float(q.embedding.weight.abs().max()) <= 1.0 / 64          # uniform_(-1/K, 1/K), vqgan.py:146
+    assert hasattr(m, "indices_to_embeddings") and hasattr(m, "forward")

@@ -1,0 +1,362 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Primary oracle = the restated reference run by PyTorch **on the same GPU** (fp32, tf32 off, no autocast):
+that is what the reference itself computes on a B200.  Secondary: the golden
+fixtures written by the unmodified reference on CPU, and a float64 closed form for the gradients.
+
+Bars (north_star): indices and z_q bit-exact except near-tie rows (top-2 fp32 distances < 1e-6 relative
+apart), which are counted and reported; loss and gradients within 1e-5 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err, ulp_distance
+from oracle import vq_oracle as vo
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 1e-5      # north_star: "losses and gradients fall within 1e-5 relative"
+GRAD_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def _module(form, K, D, beta, w, dev, exact):
+    from vq_b200.vitvqgan import Codebook as Vit
+    from vq_b200.vqgan import Codebook as Vqgan
+    m = (Vit if form == "vit" else Vqgan)(K, D, beta).to(dev)
+    with torch.no_grad():
+        m.embedding.weight.copy_(w)
+    m.exact_scan = exact
+    return m
+
+
+def _tok(form, t, D):
+    return t.permute(0, 2, 3, 1).reshape(-1, D) if form == "vqgan" else t.reshape(-1, D)
+
+
+def _check_forward(form, m, z, w, ref, report):
+    """ref: oracle output on the same device.  Returns mask of rows whose index differs (near ties)."""
+    D = w.shape[1]
+    z_q, idx, loss = m(z)
+    assert idx.dtype == torch.int64 and z_q.dtype == torch.float32 and loss.dim() == 0
+    assert z_q.shape == ref.z_q.shape and idx.shape == ref.indices.shape
+    zn = vo.unit_rows(_tok(form, z, D))
+    rep = vo.classify_index_mismatches(idx.reshape(-1), ref.indices.reshape(-1), zn, vo.unit_rows(w))
+    assert rep["hard_rows"] == 0, rep
+    bad = (idx.reshape(-1) != ref.indices.reshape(-1))
+    a, b = _tok(form, z_q.detach(), D), _tok(form, ref.z_q, D)
+    exact_rows = (a[~bad] == b[~bad]).all(dim=1)
+    report.update(rows=int(idx.numel()), mismatch_rows=rep["mismatch_rows"], near_tie_rows=rep["near_tie_rows"],
+                  zq_bit_exact_fraction=float(exact_rows.float().mean()) if exact_rows.numel() else 1.0,
+                  reported_near_ties=m.near_tie_rows())
+    assert bool(exact_rows.all()), f"z_q not bit-exact on {int((~exact_rows).sum())} rows"
+    assert rel_err(loss.detach().cpu().numpy(), ref.loss.cpu().numpy()) < LOSS_TOL
+    hist = m.last_histogram
+    assert torch.equal(hist.long(), torch.bincount(idx.reshape(-1), minlength=w.shape[0]))
+    return z_q, idx, loss, bad
+
+
+CASES = [
+    # form, K, D, shape, w_seed, z_seed   (BASELINE.json configs[0], a slice of configs[1], plus odd sizes)
+    ("vit", 8192, 32, (2, 1024, 32), 0, 1),
+    ("vit", 1000, 32, (3, 77, 32), 3, 4),          # K not a multiple of any tile, ragged T
+    ("vit", 1024, 64, (2, 130, 64), 5, 6),
+    ("vit", 512, 128, (1, 257, 128), 7, 8),
+    ("vit", 8192, 256, (2, 512, 256), 9, 10),
+    ("vqgan", 8192, 256, (4, 256, 16, 16), 0, 2),
+    ("vqgan", 1024, 256, (2, 256, 8, 8), 11, 12),
+    ("vqgan", 300, 64, (3, 64, 4, 4), 13, 14),
+    ("vqgan", 256, 32, (2, 32, 6, 6), 15, 16),
+]
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["simt", "auto"])
+@pytest.mark.parametrize("form,K,D,shape,ws,zs", CASES)
+def test_forward_matches_reference_on_gpu(dev, form, K, D, shape, ws, zs, exact):
+    w = vo.make_codebook(form, K, D, ws).to(dev)
+    z = vo.make_latents(shape, zs).to(dev)
+    m = _module(form, K, D, 0.25, w, dev, exact)
+    with torch.no_grad():
+        ref = vo.quantise(form, z, w, 0.25)
+        rep = {}
+        _check_forward(form, m, z, w, ref, rep)
+    print("parity", form, K, D, shape, "simt" if exact else "auto", rep)
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["simt", "auto"])
+@pytest.mark.parametrize("name", ["vit_cfg1_fwd", "vqgan_cfg2_slice_fwd"])
+def test_forward_matches_golden_fixture(dev, name, exact):
+    """Against what the unmodified reference produced on CPU.  CPU and GPU ATen sum in different orders,
+    so z_q is compared within 2 ulp here (bit-exactness is asserted against the same-device oracle)."""
+    g = load_golden(name)
+    form, K, D = str(g["form"]), int(g["K"]), int(g["D"])
+    w = vo.make_codebook(form, K, D, int(g["w_seed"]))
+    z = vo.make_latents(tuple(int(s) for s in g["shape"]), int(g["z_seed"]))
+    m = _module(form, K, D, float(g["beta"]), w.to(dev), dev, exact)
+    with torch.no_grad():
+        z_q, idx, loss = m(z.to(dev))
+    ref_idx = torch.from_numpy(g["indices"].astype(np.int64)).reshape(-1)
+    zn = vo.unit_rows(_tok(form, z, D))
+    rep = vo.classify_index_mismatches(idx.cpu().reshape(-1), ref_idx, zn, vo.unit_rows(w))
+    assert rep["hard_rows"] == 0, rep
+    ok = (idx.cpu().reshape(-1) == ref_idx).numpy()
+    a = _tok(form, z_q.cpu(), D).numpy()
+    b = _tok(form, torch.from_numpy(g["z_q"]), D).numpy()
+    assert ulp_distance(a[ok], b[ok]).max() <= 2
+    assert rel_err(loss.cpu().numpy(), g["loss"]) < LOSS_TOL
+    print("golden", name, rep)
+
+
+STEP_CASES = [
+    ("vit", 1024, 32, (4, 256, 32), 10, 11, 12, 0.25),
+    ("vit", 512, 32, (2, 128, 32), 13, 14, 15, 0.7),
+    ("vit", 8192, 32, (8, 1024, 32), 0, 3, 4, 0.25),
+    ("vit", 2048, 256, (2, 300, 256), 17, 18, 19, 0.25),
+    ("vqgan", 512, 256, (2, 256, 8, 8), 20, 21, 22, 0.25),
+    ("vqgan", 256, 64, (3, 64, 4, 4), 23, 24, 25, 0.4),
+    ("vqgan", 1024, 256, (4, 256, 16, 16), 26, 27, 28, 0.25),
+]
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["simt", "auto"])
+@pytest.mark.parametrize("form,K,D,shape,ws,zs,gs,beta", STEP_CASES)
+def test_step_gradients_match_reference_on_gpu(dev, form, K, D, shape, ws, zs, gs, beta, exact):
+    w = vo.make_codebook(form, K, D, ws).to(dev)
+    z = vo.make_latents(shape, zs).to(dev)
+    up = vo.make_latents(shape, gs).to(dev)
+    m = _module(form, K, D, beta, w, dev, exact)
+    zz = z.clone().requires_grad_(True)
+    z_q, idx, loss = m(zz)
+    ((z_q * up).sum() + loss).backward()
+    ref = vo.quantise_step(form, z, w, beta, up)
+    bad = idx.reshape(-1) != ref.indices.reshape(-1)
+    rep = vo.classify_index_mismatches(idx.reshape(-1), ref.indices.reshape(-1), vo.unit_rows(_tok(form, z, D)),
+                                       vo.unit_rows(w))
+    assert rep["hard_rows"] == 0, rep
+    # closed form in float64 at OUR indices: independent of near-tie flips
+    gz64, gw64 = vo.analytic_backward(form, _tok(form, z, D).double(), w.double(), idx.reshape(-1), beta,
+                                      _tok(form, up, D).double())
+    assert rel_err(_tok(form, zz.grad, D).cpu().numpy(), gz64.cpu().numpy()) < GRAD_TOL
+    assert rel_err(m.embedding.weight.grad.cpu().numpy(), gw64.cpu().numpy()) < GRAD_TOL
+    if not bool(bad.any()):
+        assert torch.equal(z_q.detach(), ref.z_q)
+        assert rel_err(zz.grad.cpu().numpy(), ref.grad_z.cpu().numpy()) < GRAD_TOL
+        assert rel_err(m.embedding.weight.grad.cpu().numpy(), ref.grad_weight.cpu().numpy()) < GRAD_TOL
+    assert rel_err(loss.detach().cpu().numpy(), ref.loss.cpu().numpy()) < LOSS_TOL
+    # rows of unused codes are exactly zero, like a dense embedding gradient
+    unused = m.last_histogram == 0
+    assert bool((m.embedding.weight.grad[unused] == 0).all())
+
+
+@pytest.mark.parametrize("name", ["vit_step_small", "vit_step_beta", "vqgan_step_small", "vqgan_step_d64"])
+def test_step_matches_golden_fixture(dev, name):
+    g = load_golden(name)
+    form, K, D = str(g["form"]), int(g["K"]), int(g["D"])
+    shape = tuple(int(s) for s in g["shape"])
+    w = vo.make_codebook(form, K, D, int(g["w_seed"])).to(dev)
+    z = vo.make_latents(shape, int(g["z_seed"])).to(dev).requires_grad_(True)
+    up = vo.make_latents(shape, int(g["g_seed"])).to(dev)
+    m = _module(form, K, D, float(g["beta"]), w, dev, False)
+    z_q, idx, loss = m(z)
+    ((z_q * up).sum() + loss).backward()
+    if np.array_equal(idx.cpu().numpy().reshape(-1), g["indices"].astype(np.int64).reshape(-1)):
+        assert rel_err(z.grad.cpu().numpy(), g["grad_z"]) < GRAD_TOL
+        assert rel_err(m.embedding.weight.grad.cpu().numpy(), g["grad_weight"]) < GRAD_TOL
+    assert rel_err(loss.detach().cpu().numpy(), g["loss"]) < LOSS_TOL
+
+
+def test_only_loss_backward_and_only_zq_backward(dev):
+    """loss.backward() alone (no upstream through z_q) and z_q.sum().backward() alone."""
+    w = vo.make_codebook("vit", 512, 32, 1).to(dev)
+    z = vo.make_latents((2, 100, 32), 2).to(dev)
+    for which in ("loss", "zq"):
+        m = _module("vit", 512, 32, 0.25, w, dev, False)
+        zz = z.clone().requires_grad_(True)
+        z_q, idx, loss = m(zz)
+        (loss if which == "loss" else z_q.sum()).backward()
+        w_ref = w.clone().requires_grad_(True)
+        z_ref = z.clone().requires_grad_(True)
+        o = vo.quantise("vit", z_ref, w_ref, 0.25)
+        (o.loss if which == "loss" else o.z_q.sum()).backward()
+        assert torch.equal(idx, o.indices)
+        assert rel_err(zz.grad.cpu().numpy(), z_ref.grad.cpu().numpy()) < GRAD_TOL
+        if which == "loss":
+            assert rel_err(m.embedding.weight.grad.cpu().numpy(), w_ref.grad.cpu().numpy()) < GRAD_TOL
+        else:
+            # no path from z_q to the codebook (the reference leaves weight.grad None; here it is all zeros)
+            assert w_ref.grad is None and float(m.embedding.weight.grad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("form,name", [("vit", "vit_decode"), ("vqgan", "vqgan_decode")])
+def test_indices_to_embeddings(dev, form, name):
+    g = load_golden(name)
+    K, D = int(g["K"]), int(g["D"])
+    w = vo.make_codebook(form, K, D, int(g["w_seed"])).to(dev)
+    gen = torch.Generator().manual_seed(int(g["i_seed"]))
+    idx = torch.randint(0, K, (int(g["b"]), int(g["n"])), generator=gen).to(dev)
+    m = _module(form, K, D, 0.25, w, dev, False)
+    e = m.indices_to_embeddings(idx)
+    ref = vo.indices_to_embeddings(form, idx, w)
+    assert e.shape == ref.shape and torch.equal(e, ref.contiguous())      # bit-exact vs the same-device oracle
+    assert ulp_distance(e.cpu().numpy(), g["embeds"]).max() <= 2          # and within 2 ulp of the CPU reference
+    bad = idx.clone()
+    bad[0, 0] = K
+    with pytest.raises(IndexError):
+        m.indices_to_embeddings(bad)
+
+
+def test_round_trip_decode_of_encode(dev):
+    """MaskGIT/Muse tokenisation (BASELINE.json configs[3]): decode(encode(z)) is the unit code of each
+    token, equal to the forward's quantised latent up to the STE rounding (<= 1 ulp of 1.0)."""
+    w = vo.make_codebook("vit", 8192, 32, 0).to(dev)
+    z = vo.make_latents((16, 1024, 32), 5).to(dev)
+    m = _module("vit", 8192, 32, 0.25, w, dev, False)
+    with torch.no_grad():
+        codes = m.encode(z)
+        z_q, idx, _ = m(z)
+        dec = m.indices_to_embeddings(codes)
+    assert torch.equal(codes, idx)
+    assert float((dec - z_q).abs().max()) <= 2 ** -23
+    # idempotence: quantising the decoded latents returns the same codes (except exact ties)
+    with torch.no_grad():
+        again = m.encode(dec)
+    assert float((again != codes).float().mean()) < 1e-4
+
+
+def test_degenerate_rows(dev):
+    """zero row, NaN row (index 0, NaN loss), row equal to a code, row opposite to a code, zero code."""
+    K, D = 64, 32
+    w = vo.make_codebook("vit", K, D, 40)
+    z = vo.make_latents((2, 8, 32), 41)
+    z[0, 0] = 0.0
+    z[0, 1, 3] = float("nan")
+    z[0, 2] = w[5] * 3.0
+    z[1, 0] = -w[7]
+    w, z = w.to(dev), z.to(dev)
+    for exact in (True, False):
+        m = _module("vit", K, D, 0.25, w, dev, exact)
+        with torch.no_grad():
+            z_q, idx, loss = m(z)
+            ref = vo.quantise("vit", z, w, 0.25)
+        got, want = idx.clone(), ref.indices.clone()
+        got[0, 0] = want[0, 0]           # all distances of the zero row are equal up to 1 ulp: a pure tie
+        assert torch.equal(got, want)
+        assert int(idx[0, 1]) == 0 and int(idx[0, 2]) == 5
+        assert bool(torch.isnan(loss)) and bool(torch.isnan(ref.loss))
+        same_nan = torch.isnan(z_q) == torch.isnan(ref.z_q)
+        assert bool(same_nan.all())
+        keep = torch.ones_like(idx, dtype=torch.bool)
+        keep[0, 0] = False
+        assert torch.equal(torch.nan_to_num(z_q[keep]), torch.nan_to_num(ref.z_q[keep]))
+    # a zero code: its |en|^2 is 0, so it wins whenever no code has a positive dot product > 1/2
+    w2 = w.clone()
+    w2[3] = 0.0
+    for exact in (True, False):
+        m = _module("vit", K, D, 0.25, w2, dev, exact)
+        with torch.no_grad():
+            _, idx, _ = m(z[1:])
+            ref = vo.quantise("vit", z[1:], w2, 0.25)
+        assert torch.equal(idx, ref.indices)
+
+
+def test_modes_give_identical_outputs(dev):
+    """no_grad / eval / requires_grad_(False) / bf16 input (autocast hand-over) -- SURVEY.md section 8b."""
+    w = vo.make_codebook("vit", 1024, 32, 1).to(dev)
+    z = vo.make_latents((2, 256, 32), 2).to(dev)
+    m = _module("vit", 1024, 32, 0.25, w, dev, False)
+    a = m(z)
+    with torch.no_grad():
+        b = m(z)
+    m.eval()
+    m.requires_grad_(False)
+    c = m(z)
+    for x in (b, c):
+        assert torch.equal(a[0].detach(), x[0]) and torch.equal(a[1], x[1]) and torch.equal(a[2].detach(), x[2])
+    zb = z.bfloat16()
+    with torch.no_grad():
+        d = m(zb)
+        ref = vo.quantise("vit", zb.float(), w, 0.25)
+    assert d[0].dtype == torch.float32 and torch.equal(d[1], ref.indices)
+
+
+def test_repeatable_bitwise(dev):
+    """Two runs on the same inputs give bit-identical outputs and gradients (no float atomics)."""
+    w = vo.make_codebook("vit", 8192, 32, 0).to(dev)
+    z = vo.make_trained_like(w.cpu(), 50000, 7).to(dev).view(50, 1000, 32)
+    up = vo.make_latents((50, 1000, 32), 8).to(dev)
+    outs = []
+    for _ in range(2):
+        m = _module("vit", 8192, 32, 0.25, w, dev, False)
+        zz = z.clone().requires_grad_(True)
+        z_q, idx, loss = m(zz)
+        ((z_q * up).sum() + loss).backward()
+        outs.append((z_q.detach(), idx, loss.detach(), zz.grad, m.embedding.weight.grad))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def test_skewed_histogram_and_cancellation(dev):
+    """trained-like latents (z ~ code + small noise) and a collapsed codebook usage (every token on a few
+    codes): long segments split into pieces, and the difference form keeps grad_E accurate."""
+    K, D = 1024, 32
+    w = vo.make_codebook("vit", K, D, 50)
+    for sigma, pick_from in ((0.01, K), (0.05, 3)):
+        g = torch.Generator().manual_seed(51)
+        en = vo.unit_rows(w)
+        pick = torch.randint(0, pick_from, (20000,), generator=g)
+        z = (en[pick] + sigma * torch.randn(20000, D, generator=g)).view(20, 1000, D).to(dev)
+        up = torch.zeros_like(z)
+        m = _module("vit", K, D, 0.25, w.to(dev), dev, False)
+        zz = z.clone().requires_grad_(True)
+        z_q, idx, loss = m(zz)
+        loss.backward()
+        gz64, gw64 = vo.analytic_backward("vit", z.reshape(-1, D).double(), w.to(dev).double(), idx.reshape(-1), 0.25,
+                                          up.reshape(-1, D).double())
+        assert rel_err(m.embedding.weight.grad.cpu().numpy(), gw64.cpu().numpy()) < GRAD_TOL
+        assert rel_err(zz.grad.reshape(-1, D).cpu().numpy(), gz64.cpu().numpy()) < GRAD_TOL
+
+
+def test_full_size_properties(dev):
+    """BASELINE.json configs[2] size (262 144 tokens, K=8192, D=32), through size-independent properties:
+    chunk invariance of the indices, histogram mass, chunk-additivity of the fixed-point segment sums
+    (grad_E of the whole batch == from the two halves), and agreement of the tensor-core search with the
+    exhaustive fp32 search on every row."""
+    K, D = 8192, 32
+    w = vo.make_codebook("vit", K, D, 0).to(dev)
+    z = vo.make_latents((256, 1024, 32), 3).to(dev)
+    auto = _module("vit", K, D, 0.25, w, dev, False)
+    simt = _module("vit", K, D, 0.25, w, dev, True)
+    with torch.no_grad():
+        idx_auto = auto.encode(z)
+        idx_simt = simt.encode(z)
+        halves = torch.cat([auto.encode(z[:100]), auto.encode(z[100:])])
+    assert torch.equal(idx_auto, idx_simt)
+    assert torch.equal(idx_auto, halves)
+    zz = z.clone().requires_grad_(True)
+    z_q, idx, loss = auto(zz)
+    assert int(auto.last_histogram.sum()) == 256 * 1024
+    loss.backward()
+    g_full = auto.embedding.weight.grad.clone()
+    # same batch in two chunks with the global normaliser: integer segment sums add exactly
+    from vq_b200 import functional as F_vq
+    parts = []
+    for sl in (slice(0, 100), slice(100, 256)):
+        wp = w.clone().requires_grad_(True)
+        o = F_vq.quantise(z[sl], wp, "vit", 0.25, n_elem_total=256 * 1024 * D)
+        o[2].backward()
+        parts.append(wp.grad)
+    assert rel_err((parts[0] + parts[1]).cpu().numpy(), g_full.cpu().numpy()) < 1e-6
+    # oracle on a sample of rows (the full T x K matrix is 8 GiB): indices agree
+    with torch.no_grad():
+        ref = vo.quantise_chunked("vit", z[:32], w, 0.25, chunk_tokens=8192)
+    rep = vo.classify_index_mismatches(idx[:32].reshape(-1), ref.indices.reshape(-1),
+                                       vo.unit_rows(z[:32].reshape(-1, D)), vo.unit_rows(w))
+    assert rep["hard_rows"] == 0, rep
