@@ -183,14 +183,9 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
     if (layout == VQ_LAYOUT_TOKEN_MAJOR) {
         VQ_CUDA(vq::launch_prep_tokens(z, T, D, zn32, w.row_sq, denom, zn16, s));
     } else {
-        if (hw % 4 == 0) {
-            VQ_CUDA(vq::launch_norm_nchw(z, T, hw, D, denom, s));
-            VQ_CUDA(vq::launch_nchw_to_tok(z, T, hw, D, denom, zn32, zn16, s));
-            VQ_CUDA(vq::launch_row_sumsq(zn32, T, D, w.row_sq, s));
-        } else {   // ATen picks another schedule here; the contiguous order is used (<= 1 ulp apart)
-            VQ_CUDA(vq::launch_nchw_to_tok(z, T, hw, D, nullptr, w.zq_tok, nullptr, s));
-            VQ_CUDA(vq::launch_prep_tokens(w.zq_tok, T, D, zn32, w.row_sq, denom, zn16, s));
-        }
+        VQ_CUDA(vq::launch_norm_nchw(z, T, hw, D, denom, s));
+        VQ_CUDA(vq::launch_nchw_to_tok(z, T, hw, D, denom, zn32, zn16, s));
+        VQ_CUDA(vq::launch_row_sumsq(zn32, T, D, w.row_sq, s));
     }
 
     // 2. nearest code per row -> cand[]

@@ -1,11 +1,504 @@
-// tcgen05 / TMA / TMEM nearest-code search -- placeholder until the tensor-core kernel lands.
+// Nearest-code search on the 5th-generation tensor cores (sm_100a): TMA -> shared memory ->
+// tcgen05.mma (fp16 in, fp32 accumulators in TMEM) -> tcgen05.ld -> running maxima in registers,
+// followed by exact fp32 rescoring of the few surviving candidates.
+//
+// Replaces the dense part of the reference's search (paths relative to /root/reference):
+//   models/vitvqgan.py:157-161 / models/vqgan.py:157-161
+//     d = sum(z^2) + sum(e^2) - 2 * einsum('bd,nd->bn', z, e);  argmin(d, dim=1)
+// The T x K matrix never exists: a CTA owns 256 token rows (two M = 128 MMA row tiles), streams the
+// fp16 unit codebook through a TMA ring in tiles of 128 codes, and keeps 2 x 2 accumulator tiles of
+// 128 x 128 fp32 in TMEM (all 512 columns) so the tensor core fills one stage while eight epilogue
+// warps drain the other.
+//
+// Exactness.  The tensor-core scores are only a filter.  With unit rows, |fp16 dot - exact dot| <= eps
+// (eps = 1.1e-3 covers fp16 rounding of both operands, fp32 accumulation, and the |en|^2 term, which
+// the filter ignores).  Any code whose approximate score is more than 2*eps below the best approximate
+// score cannot be the fp32 argmin, so it is dropped; every survivor is rescored with the reference
+// formula in fp32 (same fma chain as the exhaustive SIMT search => identical indices).  Rows the
+// filter cannot narrow down to one 256-code group are handed to the exhaustive search instead.
+//
+// Epilogue arithmetic (the bound at D = 32, where a 128x128 tile is only 128 MMA cycles): one thread
+// owns one row; per 32-column chunk pair it does r[j] = max3(r[j], a[j], b[j]) -- 0.5 ALU op per
+// distance (FMNMX3).  Every 256 columns (a "group") the 32 slot maxima are reduced, the group enters a
+// running top-3, and the slot maxima of the best group are kept.  At the end the row knows its best
+// group, which of its 32 slots can still win (8 codes each), and bounds on every other group.
+#include <cuda.h>
+#include <cstdio>
+
+#include "../../include/vq_b200.h"
+#include "vq_common.cuh"
 #include "vq_kernels.h"
 
 namespace vq {
-bool tc_supported(int64_t, int, int) { return false; }
-size_t tc_workspace_bytes(int64_t, int, int) { return 0; }
-cudaError_t launch_dist_tc(const __half*, const float*, const float*, const CodebookView&, int64_t, int*, int*, int*,
-                           int64_t*, void*, cudaStream_t) {
-    return cudaErrorNotSupported;
+
+namespace tc {
+
+constexpr int kRowsPerCta = 256;     // two MMA row tiles of 128
+constexpr int kTileN = 128;          // codes per accumulator stage
+constexpr int kGroupTiles = 2;       // tiles per group (256 columns)
+constexpr int kGroupCols = kTileN * kGroupTiles;
+constexpr int kKBlock = 32;          // halfs per K block: 64-byte rows, SWIZZLE_64B
+constexpr int kABlockBytes = kRowsPerCta * kKBlock * 2;   // 16 KiB
+constexpr int kBStageBytes = kTileN * kKBlock * 2;        // 8 KiB
+constexpr int kBStages = 8;
+constexpr int kThreads = 384;        // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr float kTwoEps = 2.2e-3f;   // 2 * eps, see header comment
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// c_format = F32 (bit 4), a/b = F16 (0), K-major both, N = 128 (bits 17..22), M = 128 (bits 24..28)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a broken pipeline traps (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000ll) {
+            printf("vq_dist_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+                   threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_64B operand tile: rows of 64 B, 8-row atoms 512 B apart (SBO), LBO = 1, version 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (16-byte units)
+    d |= (uint64_t)(512 >> 4) << 32;        // stride byte offset
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
+    return d;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 columns of fp32: thread i gets columns [col, col + 32) of TMEM lane (lane_base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+          "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+          "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+struct SmemLayout {
+    uint32_t a, b, bars, tmem_slot, total;
+};
+__host__ __device__ constexpr int a_stages(int kb) { return kb <= 2 ? 2 : 1; }
+__host__ __device__ inline SmemLayout smem_layout(int kb) {
+    SmemLayout L;
+    L.a = 0;
+    L.b = L.a + a_stages(kb) * kb * kABlockBytes;
+    L.bars = L.b + kBStages * kBStageBytes;
+    L.tmem_slot = L.bars + 8 * (2 * kBStages + 2 * 2 + 4);
+    L.total = L.tmem_slot + 16;
+    return L;
+}
+
+// One CTA per SM, persistent over row tiles.  KB = D / 32.
+template <int KB>
+__global__ void __launch_bounds__(kThreads, 1)
+k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int T, int K,
+          const int* __restrict__ cb_info, int* __restrict__ cand, uint32_t* __restrict__ slot_mask,
+          int* __restrict__ flagged, int* __restrict__ n_flagged, int64_t* __restrict__ stats) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int AS = a_stages(KB);
+    const SmemLayout L = smem_layout(KB);
+    // swizzled TMA/UMMA tiles want a 1024-byte aligned base; the launch reserves 1 KiB of slack for this
+    const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + L.bars;
+    // barrier map (8 bytes each)
+    auto b_full = [&](int s) { return bar_base + 8 * s; };
+    auto b_empty = [&](int s) { return bar_base + 8 * (kBStages + s); };
+    auto t_full = [&](int s) { return bar_base + 8 * (2 * kBStages + s); };
+    auto t_empty = [&](int s) { return bar_base + 8 * (2 * kBStages + 2 + s); };
+    auto a_full = [&](int s) { return bar_base + 8 * (2 * kBStages + 4 + s); };
+    auto a_empty = [&](int s) { return bar_base + 8 * (2 * kBStages + 6 + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_slot);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_row_tiles = (T + kRowsPerCta - 1) / kRowsPerCta;
+    const int n_tiles = K / kTileN;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + L.tmem_slot),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t b_cnt = 0;
+            int it = 0;
+            for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
+                const int as = it % AS;
+                mbar_wait(a_empty(as), (((uint32_t)(it / AS)) & 1u) ^ 1u);
+                mbar_expect_tx(a_full(as), KB * kABlockBytes);
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(smem_base + L.a + (as * KB + kb) * kABlockBytes, &tm_a, a_full(as), kb * kKBlock,
+                                rt * kRowsPerCta);
+                for (int n = 0; n < n_tiles; ++n) {
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb, ++b_cnt) {
+                        const int s = b_cnt % kBStages;
+                        mbar_wait(b_empty(s), ((b_cnt / kBStages) & 1u) ^ 1u);
+                        mbar_expect_tx(b_full(s), kBStageBytes);
+                        tma_load_2d(smem_base + L.b + s * kBStageBytes, &tm_b, b_full(s), kb * kKBlock, n * kTileN);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            uint32_t b_cnt = 0, t_cnt = 0;
+            int it = 0;
+            for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
+                const int as = it % AS;
+                mbar_wait(a_full(as), ((uint32_t)(it / AS)) & 1u);
+                tc_fence_after();
+                for (int n = 0; n < n_tiles; ++n, ++t_cnt) {
+                    const int acc = t_cnt & 1;
+                    mbar_wait(t_empty(acc), ((t_cnt >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb, ++b_cnt) {
+                        const int s = b_cnt % kBStages;
+                        mbar_wait(b_full(s), (b_cnt / kBStages) & 1u);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_base + L.a + (as * KB + kb) * kABlockBytes;
+                        const uint32_t b_addr = smem_base + L.b + s * kBStageBytes;
+#pragma unroll
+                        for (int r = 0; r < 2; ++r)
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                umma_f16(tmem_base + (uint32_t)((acc * 2 + r) * kTileN),
+                                         umma_desc(a_addr + r * (128 * 64) + k * 32), umma_desc(b_addr + k * 32), kIdesc,
+                                         (uint32_t)((kb | k) != 0));
+                        umma_commit(b_empty(s));     // smem stage free once these MMAs retire
+                    }
+                    umma_commit(t_full(acc));        // accumulators of this tile complete
+                }
+                umma_commit(a_empty(as));            // row tile's A operand no longer needed
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: 8 warps, one thread per row =====================
+        const int e = warp - 4;
+        const int r_sub = e >> 2;                    // which 128-row MMA tile
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may read
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        const bool force_exhaustive = (cb_info[0] != 0);
+        uint32_t t_cnt = 0;
+        for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
+            const int row = rt * kRowsPerCta + r_sub * 128 + quarter * 32 + lane;
+            float slot[32], kept[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) kept[j] = -INFINITY;
+            float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+            int g1 = 0;
+            for (int n = 0; n < n_tiles; ++n, ++t_cnt) {
+                const int acc = t_cnt & 1;
+                mbar_wait(t_full(acc), (t_cnt >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + lane_base + (uint32_t)((acc * 2 + r_sub) * kTileN);
+                float va[32], vb[32];
+                tmem_ld32(taddr, va);
+                tmem_ld32(taddr + 32, vb);
+                tmem_ld_wait();
+                if ((n % kGroupTiles) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) slot[j] = fmaxf(va[j], vb[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) slot[j] = max3(slot[j], va[j], vb[j]);
+                }
+                tmem_ld32(taddr + 64, va);
+                tmem_ld32(taddr + 96, vb);
+                tmem_ld_wait();
+                // all four chunks are in registers: hand the accumulator stage back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty(acc));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) slot[j] = max3(slot[j], va[j], vb[j]);
+
+                if ((n % kGroupTiles) == kGroupTiles - 1) {
+                    // group maximum: 3-input tree over the 32 slots
+                    float t[11];
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) t[j] = max3(slot[3 * j], slot[3 * j + 1], slot[3 * j + 2]);
+                    t[10] = fmaxf(slot[30], slot[31]);
+                    const float u0 = max3(t[0], t[1], t[2]), u1 = max3(t[3], t[4], t[5]), u2 = max3(t[6], t[7], t[8]);
+                    const float c1 = max3(max3(u0, u1, u2), t[9], t[10]);
+                    // running top-3 of group maxima (values), identity of the best group
+                    const bool new_best = c1 > m1;
+                    const float lo1 = fminf(c1, m1);
+                    m1 = fmaxf(c1, m1);
+                    const float lo2 = fminf(lo1, m2);
+                    m2 = fmaxf(lo1, m2);
+                    m3 = fmaxf(lo2, m3);
+                    g1 = new_best ? (n / kGroupTiles) : g1;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) kept[j] = new_best ? slot[j] : kept[j];
+                }
+            }
+            // ---- row verdict ----
+            const float thr = m1 - kTwoEps;
+            uint32_t mask = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mask |= (kept[j] >= thr) ? (1u << j) : 0u;
+            // decided iff no other group can hold the winner (NaN / -inf rows fail the comparison)
+            const bool decided = (m2 < thr) && (mask != 0) && !force_exhaustive;
+            const bool in_range = row < T;
+            const bool flag = in_range && !decided;
+            if (in_range) {
+                cand[row] = decided ? g1 : -1;
+                slot_mask[row] = mask;
+            }
+            const uint32_t ballot = __ballot_sync(VQ_FULL, flag);
+            if (ballot) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(n_flagged, __popc(ballot));
+                base = __shfl_sync(VQ_FULL, base, 0);
+                if (flag) flagged[base + __popc(ballot & ((1u << lane) - 1))] = row;
+                if (lane == 0 && stats)
+                    atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_FALLBACK_ROWS),
+                              (unsigned long long)__popc(ballot));
+            }
+            (void)m3;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact fp32 rescoring of the surviving cells: one warp per row, one candidate code per lane
+// (8 codes per surviving slot: g*256 + j + 32*s).  Same fma chain as the exhaustive search.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) k_rescore(const float* __restrict__ zn32, const float* __restrict__ row_sq,
+                                                 const float* __restrict__ en32, const float* __restrict__ code_sq,
+                                                 int64_t T, int* __restrict__ cand, const uint32_t* __restrict__ slot_mask,
+                                                 int64_t* __restrict__ stats) {
+    __shared__ __align__(16) float zrow[8][D];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + wib;
+    const int64_t n_warps = (int64_t)gridDim.x * 8;
+    constexpr int kSlotCodes = kGroupCols / 32;
+    unsigned long long ties = 0, multi = 0;
+    for (int64_t row = warp; row < T; row += n_warps) {
+        const int g = cand[row];
+        if (g < 0) continue;                        // handed to the exhaustive search
+        const uint32_t mask = slot_mask[row];
+        __syncwarp();
+        for (int d = lane; d < D; d += 32) zrow[wib][d] = __ldg(zn32 + row * D + d);
+        __syncwarp();
+        const float a_sq = __ldg(row_sq + row);
+        const int n_cand = __popc(mask) * kSlotCodes;
+        float best_d = INFINITY, second_d = INFINITY;
+        int best_i = 0x7fffffff;
+        for (int i = lane; i < n_cand; i += 32) {
+            const int j = __fns(mask, 0, i / kSlotCodes + 1);
+            const int code = g * kGroupCols + j + 32 * (i % kSlotCodes);
+            const float4* e4 = reinterpret_cast<const float4*>(en32 + (int64_t)code * D);
+            float dot = 0.f;
+#pragma unroll 8
+            for (int c = 0; c < D / 4; ++c) {
+                const float4 ev = __ldg(e4 + c);
+                const float4 zv = *reinterpret_cast<const float4*>(&zrow[wib][4 * c]);
+                dot = __fmaf_rn(zv.x, ev.x, dot);
+                dot = __fmaf_rn(zv.y, ev.y, dot);
+                dot = __fmaf_rn(zv.z, ev.z, dot);
+                dot = __fmaf_rn(zv.w, ev.w, dot);
+            }
+            const float dist = ref_distance(a_sq, __ldg(code_sq + code), dot);
+            if (argmin_better(dist, code, best_d, best_i)) { second_d = best_d; best_d = dist; best_i = code; }
+            else if (dist < second_d) second_d = dist;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float od = __shfl_xor_sync(VQ_FULL, best_d, off);
+            const int oi = __shfl_xor_sync(VQ_FULL, best_i, off);
+            const float os = __shfl_xor_sync(VQ_FULL, second_d, off);
+            if (argmin_better(od, oi, best_d, best_i)) { second_d = fminf(best_d, os); best_d = od; best_i = oi; }
+            else second_d = fminf(second_d, od);
+        }
+        if (lane == 0) {
+            cand[row] = best_i | kCandExactBit;
+            if (second_d - best_d < VQ_NEAR_TIE_REL * fabsf(best_d)) ++ties;
+            if (__popc(mask) > 1) ++multi;
+        }
+    }
+    if (lane == 0 && stats) {
+        if (ties) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), ties);
+        if (multi) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_AMBIGUOUS_ROWS), multi);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// (rows, D) fp16 row-major -> boxes of box_rows x 32 halfs, 64-byte swizzle, OOB rows read as zero
+static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, int D, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)D * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kKBlock, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace tc
+
+bool tc_supported(int64_t T, int K, int D) {
+    const bool d_ok = (D == 32 || D == 64 || D == 128 || D == 256);
+    return d_ok && K >= tc::kGroupCols && (K % tc::kGroupCols) == 0 && K <= (1 << 20) && T >= 256;
+}
+
+size_t tc_workspace_bytes(int64_t T, int K, int D) {
+    (void)K; (void)D;
+    return sizeof(uint32_t) * (size_t)(T > 0 ? T : 1);
+}
+
+template <int KB>
+static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, int T, int K, const int* info,
+                                    int* cand, uint32_t* mask, int* flagged, int* n_flagged, int64_t* stats,
+                                    cudaStream_t s) {
+    const tc::SmemLayout L = tc::smem_layout(KB);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::k_dist_tc<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int n_row_tiles = (T + tc::kRowsPerCta - 1) / tc::kRowsPerCta;
+    const int grid = n_row_tiles < sm_count() ? n_row_tiles : sm_count();
+    tc::k_dist_tc<KB><<<grid, tc::kThreads, L.total + 1024, s>>>(ma, mb, T, K, info, cand, mask, flagged, n_flagged, stats);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* row_sq, const CodebookView& cb,
+                           int64_t T, int* cand, int* flagged, int* n_flagged, int64_t* stats, void* tc_ws,
+                           cudaStream_t s) {
+    if (T == 0) return cudaSuccess;
+    CUtensorMap ma, mb;
+    if (!tc::make_map(&ma, zn16, (uint64_t)T, cb.D, tc::kRowsPerCta) ||
+        !tc::make_map(&mb, cb.en16, (uint64_t)cb.K, cb.D, tc::kTileN))
+        return cudaErrorInvalidValue;
+    uint32_t* mask = static_cast<uint32_t*>(tc_ws);
+    cudaError_t e;
+    switch (cb.D / tc::kKBlock) {
+        case 1: e = launch_tc_kernel<1>(ma, mb, (int)T, cb.K, cb.info, cand, mask, flagged, n_flagged, stats, s); break;
+        case 2: e = launch_tc_kernel<2>(ma, mb, (int)T, cb.K, cb.info, cand, mask, flagged, n_flagged, stats, s); break;
+        case 4: e = launch_tc_kernel<4>(ma, mb, (int)T, cb.K, cb.info, cand, mask, flagged, n_flagged, stats, s); break;
+        case 8: e = launch_tc_kernel<8>(ma, mb, (int)T, cb.K, cb.info, cand, mask, flagged, n_flagged, stats, s); break;
+        default: return cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) return e;
+    int64_t blocks = (T + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    switch (cb.D) {
+        case 32:  tc::k_rescore<32><<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cand, mask, stats); break;
+        case 64:  tc::k_rescore<64><<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cand, mask, stats); break;
+        case 128: tc::k_rescore<128><<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cand, mask, stats); break;
+        case 256: tc::k_rescore<256><<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cand, mask, stats); break;
+        default: return cudaErrorInvalidValue;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace vq

@@ -28,7 +28,7 @@ cudaError_t launch_prep_codebook(const float* weight, const CodebookView& cb, cu
 // token-major rows -> zn32, row_sq, denom, zn16 (any output may be null)
 cudaError_t launch_prep_tokens(const float* z, int64_t T, int D, float* zn32, float* row_sq, float* denom,
                                __half* zn16, cudaStream_t s);
-// NCHW (b, D, hw), hw % 4 == 0: denominators in ATen's channel-strided order
+// NCHW (b, D, hw): denominators in ATen's channel-strided order (schedule chosen from T, hw, D)
 cudaError_t launch_norm_nchw(const float* z, int64_t T, int64_t hw, int D, float* denom, cudaStream_t s);
 // (b, D, hw) -> (T, D), optionally divided by denom[t]; optional fp16 copy
 cudaError_t launch_nchw_to_tok(const float* in, int64_t T, int64_t hw, int D, const float* denom,

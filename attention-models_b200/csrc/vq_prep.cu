@@ -202,11 +202,62 @@ __global__ void __launch_bounds__(128) k_norm_nchw(const float* __restrict__ z, 
     }
 }
 
+// Any other ATen schedule (few tokens, hw % 4 != 0): one thread per token walks the S channel
+// stripes in turn (stripe y: accumulator i <- channels y + S*(i + 4m)) and folds them with the same
+// tree (offsets S/2 ... 1).  Only small or odd-shaped inputs come here, so simplicity wins.
+__global__ void __launch_bounds__(128) k_norm_nchw_generic(const float* __restrict__ z, int64_t T, int64_t hw, int D,
+                                                           int S, float* __restrict__ denom) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int64_t b = t / hw, p = t % hw;
+    const float* base = z + (b * D) * hw + p;
+    float part[128];
+    for (int y = 0; y < S; ++y) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        int c = y;
+        for (; c + 3 * S < D; c += 4 * S)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float v = __ldg(base + (int64_t)(c + i * S) * hw);
+                acc[i] = __fmaf_rn(v, v, acc[i]);
+            }
+        for (int i = 0; i < 4 && c < D; ++i, c += S) {
+            const float v = __ldg(base + (int64_t)c * hw);
+            acc[i] = __fmaf_rn(v, v, acc[i]);
+        }
+        part[y] = __fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]);
+    }
+    for (int off = S >> 1; off > 0; off >>= 1)
+        for (int y = 0; y < off; ++y) part[y] = __fadd_rn(part[y], part[y + off]);
+    denom[t] = norm_denominator(part[0]);
+}
+
+// ATen's launch shape for a reduction over a non-fastest dim (Reduce.cuh:1034-1180, :99-108):
+// returns S, the number of channel stripes combined by block_y_reduce (1 = no split).
+static int aten_strided_stripes(int64_t T, int64_t hw, int D) {
+    const int vec = (hw % 4 == 0) ? 4 : ((hw % 2 == 0) ? 2 : 1);
+    const int64_t max_threads = 512 / vec;
+    auto last_pow2 = [](int64_t n) { int64_t p = 1; while (p * 2 <= n) p *= 2; return p; };
+    const int64_t dim0 = T / vec > 0 ? T / vec : 1;
+    const int64_t dim0_pow2 = dim0 < max_threads ? last_pow2(dim0) : max_threads;
+    const int64_t dim1_pow2 = D < max_threads ? last_pow2(D) : max_threads;
+    int64_t bw = dim0_pow2 < 32 ? dim0_pow2 : 32;
+    const int64_t bh = dim1_pow2 < max_threads / bw ? dim1_pow2 : max_threads / bw;
+    const int64_t thresh = bh * 16 < 256 ? bh * 16 : 256;
+    return (D >= thresh) ? (int)bh : 1;
+}
+
 cudaError_t launch_norm_nchw(const float* z, int64_t T, int64_t hw, int D, float* denom, cudaStream_t s) {
     if (T == 0) return cudaSuccess;
-    if (hw % 4 != 0) return cudaErrorInvalidValue;
-    const int64_t blocks = (T / 4 + 31) / 32;
-    VQ_DISPATCH_D(D, (k_norm_nchw<kD><<<(unsigned)blocks, dim3(32, 4), 0, s>>>(z, T, hw, denom)));
+    const int S = aten_strided_stripes(T, hw, D);
+    const bool fast = (hw % 4 == 0) && ((D >= 64 && S == 4) || (D < 64 && S == 1));
+    if (fast) {
+        const int64_t blocks = (T / 4 + 31) / 32;
+        VQ_DISPATCH_D(D, (k_norm_nchw<kD><<<(unsigned)blocks, dim3(32, 4), 0, s>>>(z, T, hw, denom)));
+    } else {
+        if (S > 128) return cudaErrorInvalidValue;
+        k_norm_nchw_generic<<<(unsigned)((T + 127) / 128), 128, 0, s>>>(z, T, hw, D, S, denom);
+    }
     count_launch();
     return cudaGetLastError();
 }

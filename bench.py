@@ -56,47 +56,62 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    In-process NVML polling (a few ms period) because the timed region can be shorter than one
+    `nvidia-smi -lms 200` tick; falls back to nvidia-smi if pynvml is unavailable."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index: int):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.samples, self._stop, self._thread, self._h = gpu_index, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv, self._h, self.max_mhz = None, None, None
+
+    def _poll(self):
+        nv = self._nv
+        while not self._stop:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.samples.append((float(mhz), int(mask)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        if self._h is not None:
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except subprocess.TimeoutExpired:
-                self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6),
-                              ("sw_power_cap", 7)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop = True
+        if self._thread is not None:
+            self._thread.join(timeout=1)
+        if not self.samples:
+            return self._smi_once()
+        sm = [s[0] for s in self.samples]
+        reasons = sorted({name for _, mask in self.samples for name, bit in self.REASONS if mask & bit})
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "source": "nvml polled during the timed region"}
+
+    def _smi_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                  "-i", str(self.gpu)], capture_output=True, text=True, timeout=10).stdout.split(",")
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "samples": 1,
+                    "source": "nvidia-smi after the timed region (nvml unavailable)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "unavailable"}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -126,15 +126,27 @@ def rowsum_contiguous(x: np.ndarray, fused: bool) -> np.ndarray:
     return _tree(per_lane)
 
 
+def strided_stripes(T: int, hw: int, D: int) -> int:
+    """Number of channel stripes ATen's block_y_reduce combines for a (b, D, hw) view reduced over D
+    (Reduce.cuh:1034-1180 with :99-108): depends on the vector width (hw % 4 / % 2) and on how many
+    outputs there are, because few outputs shrink block.x and grow block.y."""
+    vec = 4 if hw % 4 == 0 else (2 if hw % 2 == 0 else 1)
+    max_threads = 512 // vec
+    dim0 = max(T // vec, 1)
+    dim0_pow2 = _last_pow2(dim0) if dim0 < max_threads else max_threads
+    dim1_pow2 = _last_pow2(D) if D < max_threads else max_threads
+    bw = min(dim0_pow2, 32)
+    bh = min(dim1_pow2, max_threads // bw)
+    return bh if D >= min(bh * 16, 256) else 1
+
+
 def rowsum_channel_strided(x: np.ndarray, fused: bool) -> np.ndarray:
     """Sum over dim 1 of a (b, D, hw) float32 array (the NCHW view the VQGAN form normalises),
-    ATen CUDA order when hw % 4 == 0 (vectorise-along-output, block = 32 x 4)."""
+    ATen CUDA order: thread y accumulates channels y + S*(i + 4m) in accumulator i, then a tree over y."""
     x = np.ascontiguousarray(x, dtype=F32)
     b, D, hw = x.shape
-    if hw % 4 != 0:
-        raise NotImplementedError("hw % 4 != 0 selects a different ATen schedule")
     rows = np.ascontiguousarray(x.transpose(0, 2, 1)).reshape(b * hw, D)
-    split = 4 if D >= 64 else 1      # warps split the reduced dim iff values_per_thread >= 64
+    split = strided_stripes(b * hw, hw, D)
     parts = np.stack([_thread_reduce(rows, y, split, fused) for y in range(split)], axis=1)
     return _tree(parts)
 

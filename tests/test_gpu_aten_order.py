@@ -33,16 +33,18 @@ def test_contiguous_norm_and_sum_order(dev, D):
     assert np.array_equal(zn_gpu, zn_emu)
 
 
-@pytest.mark.parametrize("b,D,h", [(4, 256, 16), (2, 64, 8), (3, 32, 4), (2, 128, 8)])
-def test_channel_strided_norm_order(dev, b, D, h):
+@pytest.mark.parametrize("b,D,h,w", [(4, 256, 16, 16), (2, 64, 8, 8), (3, 32, 4, 4), (2, 128, 8, 8), (3, 64, 4, 4),
+                                     (1, 256, 8, 8), (1, 256, 4, 4), (2, 256, 5, 6), (2, 256, 5, 5), (1, 64, 3, 3),
+                                     (5, 512, 2, 2), (2, 16, 8, 8)])
+def test_channel_strided_norm_order(dev, b, D, h, w):
     g = torch.Generator().manual_seed(D + h)
-    x = torch.randn(b, D, h, h, generator=g)
+    x = torch.randn(b, D, h, w, generator=g)
     view = x.to(dev).permute(0, 2, 3, 1)                     # what models/vqgan.py:151 normalises
     norm_gpu = view.norm(p=2, dim=-1).reshape(-1).cpu().numpy()
-    emu = np.sqrt(ao.rowsum_channel_strided(x.numpy().reshape(b, D, h * h), fused=True)).astype(np.float32)
+    emu = np.sqrt(ao.rowsum_channel_strided(x.numpy().reshape(b, D, h * w), fused=True)).astype(np.float32)
     assert np.array_equal(norm_gpu, emu), f"strided norm order differs on {(norm_gpu != emu).mean():.3%} of rows"
     zn_gpu = F.normalize(view, p=2, dim=-1).reshape(-1, D).cpu().numpy()
-    zn_emu, _ = ao.normalise_nchw(x.numpy().reshape(b, D, h * h))
+    zn_emu, _ = ao.normalise_nchw(x.numpy().reshape(b, D, h * w))
     assert np.array_equal(zn_gpu, zn_emu)
 
 

@@ -75,6 +75,9 @@ CASES = [
     ("vqgan", 1024, 256, (2, 256, 8, 8), 11, 12),
     ("vqgan", 300, 64, (3, 64, 4, 4), 13, 14),
     ("vqgan", 256, 32, (2, 32, 6, 6), 15, 16),
+    ("vqgan", 512, 256, (1, 256, 8, 8), 17, 18),      # few tokens: ATen reshapes its reduce block
+    ("vqgan", 512, 256, (2, 256, 5, 5), 19, 20),      # odd h*w: scalar (non-vectorised) ATen schedule
+    ("vqgan", 512, 64, (2, 64, 3, 6), 21, 22),        # h*w % 4 == 2
 ]
 
 
@@ -110,7 +113,9 @@ def test_forward_matches_golden_fixture(dev, name, exact):
     ok = (idx.cpu().reshape(-1) == ref_idx).numpy()
     a = _tok(form, z_q.cpu(), D).numpy()
     b = _tok(form, torch.from_numpy(g["z_q"]), D).numpy()
-    assert ulp_distance(a[ok], b[ok]).max() <= 2
+    # elements are <= 1 in magnitude and z_q = zn + (q - zn) rounds at the magnitude of zn, so the honest
+    # bound is absolute: 2 ulp of 1.0 (ulp counts explode on near-zero elements)
+    assert np.abs(a[ok] - b[ok]).max() <= 2 * 2.0 ** -23
     assert rel_err(loss.cpu().numpy(), g["loss"]) < LOSS_TOL
     print("golden", name, rep)
 
@@ -206,7 +211,7 @@ def test_indices_to_embeddings(dev, form, name):
     e = m.indices_to_embeddings(idx)
     ref = vo.indices_to_embeddings(form, idx, w)
     assert e.shape == ref.shape and torch.equal(e, ref.contiguous())      # bit-exact vs the same-device oracle
-    assert ulp_distance(e.cpu().numpy(), g["embeds"]).max() <= 2          # and within 2 ulp of the CPU reference
+    assert np.abs(e.cpu().numpy() - g["embeds"]).max() <= 2 * 2.0 ** -23   # and within 2 ulp(1.0) of the CPU reference
     bad = idx.clone()
     bad[0, 0] = K
     with pytest.raises(IndexError):
