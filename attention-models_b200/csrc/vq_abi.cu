@@ -64,7 +64,7 @@ struct Bump {
 
 struct FwdWs {
     float* zn32; float* denom; float* row_sq; __half* zn16; int* cand; int* flagged; int* n_flagged;
-    int64_t* stats; float* zq_tok; void* tc_ws; size_t bytes;
+    int64_t* stats; float* zq_tok; void* tc_ws; void* scan_ws; size_t bytes;
 };
 
 // Sized for the worst case over the optional outputs so one size serves every flag combination.
@@ -83,6 +83,7 @@ FwdWs carve_forward(void* ws, int64_t T, int K, int D) {
     w.zq_tok = b.take<float>(n * D);
     const size_t tcb = vq::tc_workspace_bytes(T, K, D);
     w.tc_ws = b.take<char>(tcb ? tcb : 1);
+    w.scan_ws = b.take<char>(vq::scan_partial_bytes(T));
     w.bytes = b.off;
     return w;
 }
@@ -193,9 +194,9 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
     if (use_tc) {
         VQ_CUDA(cudaMemsetAsync(w.n_flagged, 0, sizeof(int) * 64, s));
         VQ_CUDA(vq::launch_dist_tc(zn16, zn32, w.row_sq, cbv, T, w.cand, w.flagged, w.n_flagged, st, w.tc_ws, s));
-        VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, T, w.cand, st, s));
+        VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, T, w.cand, st, w.scan_ws, s));
     } else {
-        VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, nullptr, nullptr, T, w.cand, st, s));
+        VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, nullptr, nullptr, T, w.cand, st, nullptr, s));
     }
     timer.stop();
 

@@ -18,6 +18,8 @@
 namespace vq {
 
 constexpr int kTM = 64, kTN = 128, kDK = 32;
+constexpr int kScanSplits = 32;          // code ranges per listed row tile
+constexpr int64_t kScanSplitCap = 8192;  // listed rows that get the split treatment
 
 struct Best {
     float d1; int i1; float d2;   // best distance, its index, second-best distance
@@ -41,20 +43,33 @@ __device__ __forceinline__ void best_merge(Best& a, float d1, int i1, float d2) 
     }
 }
 
+// rows == nullptr: every row 0..T-1.  Otherwise the listed rows [row_begin, min(*n_rows_ptr, row_end)).
+// partial == nullptr: the block scans all K codes and writes cand[] itself.  Otherwise blockIdx.y selects
+// one of gridDim.y code ranges and the (best, index, second) triple goes to partial[split][list slot];
+// k_merge_partials folds the ranges in order (no atomics, deterministic).
 __global__ void __launch_bounds__(256) k_scan_exact(const float* __restrict__ zn32, const float* __restrict__ row_sq,
                                                     const float* __restrict__ en32, const float* __restrict__ code_sq,
                                                     int64_t T, int K, int D, const int* __restrict__ rows,
-                                                    const int* __restrict__ n_rows_ptr, int* __restrict__ cand,
+                                                    const int* __restrict__ n_rows_ptr, int64_t row_begin,
+                                                    int64_t row_end, int* __restrict__ cand,
+                                                    float4* __restrict__ partial, int partial_cap,
                                                     int64_t* __restrict__ stats) {
     __shared__ __align__(16) float zs[kDK][kTM + 4];
     __shared__ __align__(16) float es[kDK][kTN + 4];
     __shared__ int row_id[kTM];
 
-    const int64_t n_rows = rows ? (int64_t)(*n_rows_ptr) : T;
+    int64_t n_rows = rows ? (int64_t)(*n_rows_ptr) : T;
+    if (n_rows > row_end) n_rows = row_end;
     const int tid = threadIdx.x;
+    int k_lo = 0, k_hi = K;
+    if (partial) {
+        const int per = ((K + (int)gridDim.y - 1) / (int)gridDim.y + kTN - 1) / kTN * kTN;
+        k_lo = min(K, (int)blockIdx.y * per);
+        k_hi = min(K, k_lo + per);
+    }
     const int ty = tid >> 4, tx = tid & 15;     // rows ty*4..+3 ; codes tx*4..+3 and 64+tx*4..+3
 
-    for (int64_t tile0 = (int64_t)blockIdx.x * kTM; tile0 < n_rows; tile0 += (int64_t)gridDim.x * kTM) {
+    for (int64_t tile0 = row_begin + (int64_t)blockIdx.x * kTM; tile0 < n_rows; tile0 += (int64_t)gridDim.x * kTM) {
         __syncthreads();
         if (tid < kTM) {
             const int64_t i = tile0 + tid;
@@ -72,7 +87,7 @@ __global__ void __launch_bounds__(256) k_scan_exact(const float* __restrict__ zn
             a_sq[r] = (rid >= 0) ? row_sq[rid] : 0.f;
         }
 
-        for (int k0 = 0; k0 < K; k0 += kTN) {
+        for (int k0 = k_lo; k0 < k_hi; k0 += kTN) {
             float acc[4][8];
 #pragma unroll
             for (int r = 0; r < 4; ++r)
@@ -129,26 +144,75 @@ __global__ void __launch_bounds__(256) k_scan_exact(const float* __restrict__ zn
             }
             const int rid = row_id[ty * 4 + r];
             if (tx == 0 && rid >= 0) {
-                cand[rid] = best[r].i1 | kCandExactBit;
-                const float gap = best[r].d2 - best[r].d1;
-                if (stats && gap < VQ_NEAR_TIE_REL * fabsf(best[r].d1))
-                    atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), 1ull);
+                if (partial) {
+                    const int64_t slot = tile0 + ty * 4 + r;
+                    partial[(int64_t)blockIdx.y * partial_cap + slot] =
+                        make_float4(best[r].d1, __int_as_float(best[r].i1), best[r].d2, 0.f);
+                } else {
+                    cand[rid] = best[r].i1 | kCandExactBit;
+                    const float gap = best[r].d2 - best[r].d1;
+                    if (stats && gap < VQ_NEAR_TIE_REL * fabsf(best[r].d1))
+                        atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), 1ull);
+                }
             }
         }
     }
 }
 
+__global__ void __launch_bounds__(256) k_merge_partials(const float4* __restrict__ partial, int n_splits, int cap,
+                                                        const int* __restrict__ rows, const int* __restrict__ n_rows_ptr,
+                                                        int* __restrict__ cand, int64_t* __restrict__ stats) {
+    const int n = min(*n_rows_ptr, cap);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Best b;
+    b.d1 = INFINITY; b.i1 = 0x7fffffff; b.d2 = INFINITY;
+    for (int s = 0; s < n_splits; ++s) {
+        const float4 p = partial[(int64_t)s * cap + i];
+        best_merge(b, p.x, __float_as_int(p.y), p.z);
+    }
+    cand[rows[i]] = b.i1 | kCandExactBit;
+    if (stats && (b.d2 - b.d1) < VQ_NEAR_TIE_REL * fabsf(b.d1))
+        atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), 1ull);
+}
+
+size_t scan_partial_bytes(int64_t T) {
+    const int64_t cap = T < kScanSplitCap ? T : kScanSplitCap;
+    return sizeof(float4) * (size_t)kScanSplits * (size_t)(cap > 0 ? cap : 1);
+}
+
 cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
                               const int* rows, const int* n_rows, int64_t max_rows, int* cand, int64_t* stats,
-                              cudaStream_t s) {
+                              void* partial_ws, cudaStream_t s) {
     const int64_t n = rows ? max_rows : T;
     if (n == 0) return cudaSuccess;
-    int64_t blocks = (n + kTM - 1) / kTM;
-    const int64_t cap = (int64_t)sm_count() * 16;
-    if (blocks > cap) blocks = cap;
-    k_scan_exact<<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows,
-                                                 cand, stats);
-    count_launch();
+    const int64_t cap_blocks = (int64_t)sm_count() * 16;
+    if (!rows || !partial_ws) {
+        int64_t blocks = (n + kTM - 1) / kTM;
+        if (blocks > cap_blocks) blocks = cap_blocks;
+        k_scan_exact<<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, 0,
+                                                     n, cand, nullptr, 0, stats);
+        count_launch();
+        return cudaGetLastError();
+    }
+    // listed rows: the first `cap` of them with the codebook split over blockIdx.y, the rest unsplit
+    const int cap = (int)(n < kScanSplitCap ? n : kScanSplitCap);
+    int splits = cb.K / kTN;
+    if (splits > kScanSplits) splits = kScanSplits;
+    if (splits < 1) splits = 1;
+    float4* partial = static_cast<float4*>(partial_ws);
+    dim3 grid((unsigned)((cap + kTM - 1) / kTM), (unsigned)splits);
+    k_scan_exact<<<grid, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, 0, cap, cand,
+                                      partial, cap, stats);
+    k_merge_partials<<<(cap + 255) / 256, 256, 0, s>>>(partial, splits, cap, rows, n_rows, cand, stats);
+    count_launch(2);
+    if (n > cap) {
+        int64_t blocks = (n - cap + kTM - 1) / kTM;
+        if (blocks > cap_blocks) blocks = cap_blocks;
+        k_scan_exact<<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, cap,
+                                                     n, cand, nullptr, 0, stats);
+        count_launch();
+    }
     return cudaGetLastError();
 }
 

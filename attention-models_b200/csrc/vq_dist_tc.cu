@@ -20,8 +20,10 @@
 // Epilogue arithmetic (the bound at D = 32, where a 128x128 tile is only 128 MMA cycles): one thread
 // owns one row; per 32-column chunk pair it does r[j] = max3(r[j], a[j], b[j]) -- 0.5 ALU op per
 // distance (FMNMX3).  Every 256 columns (a "group") the 32 slot maxima are reduced, the group enters a
-// running top-3, and the slot maxima of the best group are kept.  At the end the row knows its best
-// group, which of its 32 slots can still win (8 codes each), and bounds on every other group.
+// running top-3 of group maxima, and the slot maxima of the two best groups are parked in shared memory
+// (predicated STS.128 on the LSU pipe, so the ALU pipe -- the bottleneck -- is not charged).  At the end
+// the row knows its two best groups, which of their 32 slots can still win (8 codes each), and a bound
+// on every other group; it is undecided only if a third group is within 2*eps of the best.
 #include <cuda.h>
 #include <cstdio>
 
@@ -40,7 +42,6 @@ constexpr int kGroupCols = kTileN * kGroupTiles;
 constexpr int kKBlock = 32;          // halfs per K block: 64-byte rows, SWIZZLE_64B
 constexpr int kABlockBytes = kRowsPerCta * kKBlock * 2;   // 16 KiB
 constexpr int kBStageBytes = kTileN * kKBlock * 2;        // 8 KiB
-constexpr int kBStages = 8;
 constexpr int kThreads = 384;        // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
 constexpr float kTwoEps = 2.2e-3f;   // 2 * eps, see header comment
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -57,25 +58,31 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a broken pipeline traps (launch failure) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done;
+}
+// Bounded wait: a broken pipeline traps (launch failure) instead of hanging the GPU.  The common case
+// (already complete, or completes within the hardware's try_wait window) costs one instruction.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
-    while (true) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
+    while (!mbar_try(bar, parity)) {
         if (clock64() - t0 > 4000000000ll) {
             printf("vq_dist_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
                    threadIdx.x, bar, parity);
             __trap();
         }
     }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
 }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -135,15 +142,21 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 }
 
 struct SmemLayout {
-    uint32_t a, b, bars, tmem_slot, total;
+    uint32_t a, b, snap, bars, tmem_slot, total;
 };
 __host__ __device__ constexpr int a_stages(int kb) { return kb <= 2 ? 2 : 1; }
+__host__ __device__ constexpr int b_stages(int kb) { return kb <= 4 ? 8 : 4; }
+// slot-maxima snapshots: 2 areas x 256 rows x 32 floats; rows padded by 16 B (conflict-free STS.128)
+// except at D = 256 where shared memory is tight
+__host__ __device__ constexpr int snap_row_bytes(int kb) { return kb <= 4 ? 144 : 128; }
+constexpr int kMaxBStages = 8;
 __host__ __device__ inline SmemLayout smem_layout(int kb) {
     SmemLayout L;
     L.a = 0;
     L.b = L.a + a_stages(kb) * kb * kABlockBytes;
-    L.bars = L.b + kBStages * kBStageBytes;
-    L.tmem_slot = L.bars + 8 * (2 * kBStages + 2 * 2 + 4);
+    L.snap = L.b + b_stages(kb) * kBStageBytes;
+    L.bars = L.snap + 2 * kRowsPerCta * snap_row_bytes(kb);
+    L.tmem_slot = L.bars + 8 * (2 * kMaxBStages + 2 * 2 + 4);
     L.total = L.tmem_slot + 16;
     return L;
 }
@@ -152,10 +165,13 @@ __host__ __device__ inline SmemLayout smem_layout(int kb) {
 template <int KB>
 __global__ void __launch_bounds__(kThreads, 1)
 k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int T, int K,
-          const int* __restrict__ cb_info, int* __restrict__ cand, uint32_t* __restrict__ slot_mask,
-          int* __restrict__ flagged, int* __restrict__ n_flagged, int64_t* __restrict__ stats) {
+          const int* __restrict__ cb_info, int* __restrict__ cand, uint32_t* __restrict__ mask1_out,
+          uint32_t* __restrict__ mask2_out, int* __restrict__ flagged, int* __restrict__ n_flagged,
+          int64_t* __restrict__ stats) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int AS = a_stages(KB);
+    constexpr int BS = b_stages(KB);
+    constexpr int kSnapRow = snap_row_bytes(KB);
     const SmemLayout L = smem_layout(KB);
     // swizzled TMA/UMMA tiles want a 1024-byte aligned base; the launch reserves 1 KiB of slack for this
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -164,20 +180,21 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     const uint32_t bar_base = smem_base + L.bars;
     // barrier map (8 bytes each)
     auto b_full = [&](int s) { return bar_base + 8 * s; };
-    auto b_empty = [&](int s) { return bar_base + 8 * (kBStages + s); };
-    auto t_full = [&](int s) { return bar_base + 8 * (2 * kBStages + s); };
-    auto t_empty = [&](int s) { return bar_base + 8 * (2 * kBStages + 2 + s); };
-    auto a_full = [&](int s) { return bar_base + 8 * (2 * kBStages + 4 + s); };
-    auto a_empty = [&](int s) { return bar_base + 8 * (2 * kBStages + 6 + s); };
+    auto b_empty = [&](int s) { return bar_base + 8 * (kMaxBStages + s); };
+    auto t_full = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + s); };
+    auto t_empty = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 2 + s); };
+    auto a_full = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 4 + s); };
+    auto a_empty = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 6 + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_slot);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_row_tiles = (T + kRowsPerCta - 1) / kRowsPerCta;
     const int n_tiles = K / kTileN;
+    const int n_groups = n_tiles / kGroupTiles;
 
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), 8); }
+        for (int s = 0; s < BS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), 256); }
         for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -208,8 +225,8 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                 for (int n = 0; n < n_tiles; ++n) {
 #pragma unroll
                     for (int kb = 0; kb < KB; ++kb, ++b_cnt) {
-                        const int s = b_cnt % kBStages;
-                        mbar_wait(b_empty(s), ((b_cnt / kBStages) & 1u) ^ 1u);
+                        const int s = b_cnt % BS;
+                        mbar_wait(b_empty(s), ((b_cnt / BS) & 1u) ^ 1u);
                         mbar_expect_tx(b_full(s), kBStageBytes);
                         tma_load_2d(smem_base + L.b + s * kBStageBytes, &tm_b, b_full(s), kb * kKBlock, n * kTileN);
                     }
@@ -231,8 +248,8 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                     tc_fence_after();
 #pragma unroll
                     for (int kb = 0; kb < KB; ++kb, ++b_cnt) {
-                        const int s = b_cnt % kBStages;
-                        mbar_wait(b_full(s), (b_cnt / kBStages) & 1u);
+                        const int s = b_cnt % BS;
+                        mbar_wait(b_full(s), (b_cnt / BS) & 1u);
                         tc_fence_after();
                         const uint32_t a_addr = smem_base + L.a + (as * KB + kb) * kABlockBytes;
                         const uint32_t b_addr = smem_base + L.b + s * kBStageBytes;
@@ -255,74 +272,102 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         const int e = warp - 4;
         const int r_sub = e >> 2;                    // which 128-row MMA tile
         const int quarter = warp & 3;                // TMEM lane quarter this warp may read
-        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        const int row_in_cta = r_sub * 128 + quarter * 32 + lane;
+        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(r_sub * kTileN);
+        const uint32_t snap0 = smem_base + L.snap + (uint32_t)row_in_cta * kSnapRow;
+        constexpr uint32_t kSnapArea = kRowsPerCta * kSnapRow;
         const bool force_exhaustive = (cb_info[0] != 0);
-        uint32_t t_cnt = 0;
+        uint32_t phase = 0;                          // parity of t_full: flips once per group (2 tiles, 2 stages)
         for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
-            const int row = rt * kRowsPerCta + r_sub * 128 + quarter * 32 + lane;
-            float slot[32], kept[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) kept[j] = -INFINITY;
+            float slot[32];
             float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-            int g1 = 0;
-            for (int n = 0; n < n_tiles; ++n, ++t_cnt) {
-                const int acc = t_cnt & 1;
-                mbar_wait(t_full(acc), (t_cnt >> 1) & 1u);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + lane_base + (uint32_t)((acc * 2 + r_sub) * kTileN);
-                float va[32], vb[32];
-                tmem_ld32(taddr, va);
-                tmem_ld32(taddr + 32, vb);
-                tmem_ld_wait();
-                if ((n % kGroupTiles) == 0) {
+            int g1 = 0, g2 = 0;
+            uint32_t best_area = 0;                  // which snapshot area holds the best group's slots
+            for (int g = 0; g < n_groups; ++g, phase ^= 1u) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) slot[j] = fmaxf(va[j], vb[j]);
-                } else {
+                for (int tsub = 0; tsub < kGroupTiles; ++tsub) {
+                    mbar_wait(t_full(tsub), phase);
+                    tc_fence_after();
+                    const uint32_t taddr = tbase + (uint32_t)(tsub * 2 * kTileN);
+                    float va[32], vb[32];
+                    tmem_ld32(taddr, va);
+                    tmem_ld32(taddr + 32, vb);
+                    tmem_ld_wait();
+                    if (tsub == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) slot[j] = fmaxf(va[j], vb[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) slot[j] = max3(slot[j], va[j], vb[j]);
+                    }
+                    tmem_ld32(taddr + 64, va);
+                    tmem_ld32(taddr + 96, vb);
+                    tmem_ld_wait();
+                    // all four chunks are in registers: hand the accumulator stage back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(t_empty(tsub));
 #pragma unroll
                     for (int j = 0; j < 32; ++j) slot[j] = max3(slot[j], va[j], vb[j]);
                 }
-                tmem_ld32(taddr + 64, va);
-                tmem_ld32(taddr + 96, vb);
-                tmem_ld_wait();
-                // all four chunks are in registers: hand the accumulator stage back to the MMA warp
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(t_empty(acc));
+                // group maximum: 3-input tree over the 32 slots
+                float t[11];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) slot[j] = max3(slot[j], va[j], vb[j]);
-
-                if ((n % kGroupTiles) == kGroupTiles - 1) {
-                    // group maximum: 3-input tree over the 32 slots
-                    float t[11];
+                for (int j = 0; j < 10; ++j) t[j] = max3(slot[3 * j], slot[3 * j + 1], slot[3 * j + 2]);
+                t[10] = fmaxf(slot[30], slot[31]);
+                const float u0 = max3(t[0], t[1], t[2]), u1 = max3(t[3], t[4], t[5]), u2 = max3(t[6], t[7], t[8]);
+                const float c1 = max3(max3(u0, u1, u2), t[9], t[10]);
+                const bool new_best = c1 > m1, new_second = c1 > m2;
+                if (new_second) {
+                    // the evicted group is always the current second: its area is the one the best does not use
+                    const uint32_t dst = snap0 + (best_area ^ 1u) * kSnapArea;
 #pragma unroll
-                    for (int j = 0; j < 10; ++j) t[j] = max3(slot[3 * j], slot[3 * j + 1], slot[3 * j + 2]);
-                    t[10] = fmaxf(slot[30], slot[31]);
-                    const float u0 = max3(t[0], t[1], t[2]), u1 = max3(t[3], t[4], t[5]), u2 = max3(t[6], t[7], t[8]);
-                    const float c1 = max3(max3(u0, u1, u2), t[9], t[10]);
-                    // running top-3 of group maxima (values), identity of the best group
-                    const bool new_best = c1 > m1;
-                    const float lo1 = fminf(c1, m1);
-                    m1 = fmaxf(c1, m1);
-                    const float lo2 = fminf(lo1, m2);
-                    m2 = fmaxf(lo1, m2);
-                    m3 = fmaxf(lo2, m3);
-                    g1 = new_best ? (n / kGroupTiles) : g1;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) kept[j] = new_best ? slot[j] : kept[j];
+                    for (int q = 0; q < 8; ++q)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16 * q), "f"(slot[4 * q]),
+                                     "f"(slot[4 * q + 1]), "f"(slot[4 * q + 2]), "f"(slot[4 * q + 3])
+                                     : "memory");
                 }
+                const float lo1 = fminf(c1, m1);
+                m1 = fmaxf(c1, m1);
+                const float lo2 = fminf(lo1, m2);
+                m2 = fmaxf(lo1, m2);
+                m3 = fmaxf(lo2, m3);
+                g2 = new_best ? g1 : (new_second ? g : g2);
+                g1 = new_best ? g : g1;
+                best_area ^= new_best ? 1u : 0u;
             }
             // ---- row verdict ----
             const float thr = m1 - kTwoEps;
-            uint32_t mask = 0;
+            float kept[32];
+            uint32_t mask1 = 0, mask2 = 0;
+            {
+                const uint32_t src = snap0 + best_area * kSnapArea;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mask |= (kept[j] >= thr) ? (1u << j) : 0u;
-            // decided iff no other group can hold the winner (NaN / -inf rows fail the comparison)
-            const bool decided = (m2 < thr) && (mask != 0) && !force_exhaustive;
+                for (int q = 0; q < 8; ++q)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(kept[4 * q]), "=f"(kept[4 * q + 1]), "=f"(kept[4 * q + 2]), "=f"(kept[4 * q + 3])
+                                 : "r"(src + 16 * q));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mask1 |= (kept[j] >= thr) ? (1u << j) : 0u;
+            }
+            if (m2 >= thr) {
+                const uint32_t src = snap0 + (best_area ^ 1u) * kSnapArea;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(kept[4 * q]), "=f"(kept[4 * q + 1]), "=f"(kept[4 * q + 2]), "=f"(kept[4 * q + 3])
+                                 : "r"(src + 16 * q));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mask2 |= (kept[j] >= thr) ? (1u << j) : 0u;
+            }
+            // decided iff no third group can hold the winner (NaN / -inf rows fail the comparisons)
+            const bool decided = (m3 < thr) && (mask1 != 0) && !force_exhaustive;
+            const int row = rt * kRowsPerCta + row_in_cta;
             const bool in_range = row < T;
             const bool flag = in_range && !decided;
             if (in_range) {
-                cand[row] = decided ? g1 : -1;
-                slot_mask[row] = mask;
+                cand[row] = decided ? (g1 | (g2 << 12)) : -1;
+                mask1_out[row] = mask1;
+                mask2_out[row] = mask2;
             }
             const uint32_t ballot = __ballot_sync(VQ_FULL, flag);
             if (ballot) {
@@ -334,7 +379,6 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                     atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_FALLBACK_ROWS),
                               (unsigned long long)__popc(ballot));
             }
-            (void)m3;
         }
     }
     tc_fence_before();
@@ -346,40 +390,49 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
 }
 
 // ---------------------------------------------------------------------------------------------
-// Exact fp32 rescoring of the surviving cells: one warp per row, one candidate code per lane
-// (8 codes per surviving slot: g*256 + j + 32*s).  Same fma chain as the exhaustive search.
+// Exact fp32 rescoring of the surviving cells.  A cell is the 8 codes g*256 + j + 32*s (s = 0..7) of
+// one slot j; 8 lanes share a row (one code of the cell each), 4 rows per warp, and rows with several
+// surviving cells loop over them.  Same fma chain as the exhaustive search => identical indices.
 // ---------------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(256) k_rescore(const float* __restrict__ zn32, const float* __restrict__ row_sq,
                                                  const float* __restrict__ en32, const float* __restrict__ code_sq,
-                                                 int64_t T, int* __restrict__ cand, const uint32_t* __restrict__ slot_mask,
-                                                 int64_t* __restrict__ stats) {
-    __shared__ __align__(16) float zrow[8][D];
+                                                 int64_t T, int* __restrict__ cand, const uint32_t* __restrict__ mask1_in,
+                                                 const uint32_t* __restrict__ mask2_in, int64_t* __restrict__ stats) {
+    static_assert(kGroupCols / 32 == 8, "8 lanes per row assume 8 codes per cell");
+    __shared__ __align__(16) float zrow[32][D];      // 8 warps x 4 rows
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t warp = (int64_t)blockIdx.x * 8 + wib;
-    const int64_t n_warps = (int64_t)gridDim.x * 8;
-    constexpr int kSlotCodes = kGroupCols / 32;
-    unsigned long long ties = 0, multi = 0;
-    for (int64_t row = warp; row < T; row += n_warps) {
-        const int g = cand[row];
-        if (g < 0) continue;                        // handed to the exhaustive search
-        const uint32_t mask = slot_mask[row];
+    const int sub = lane & 7, grp = lane >> 3;
+    float* zr = zrow[wib * 4 + grp];
+    const int64_t first = ((int64_t)blockIdx.x * 8 + wib) * 4;
+    const int64_t stride = (int64_t)gridDim.x * 32;
+    unsigned ties = 0, multi = 0;
+    for (int64_t row0 = first; row0 < T; row0 += stride) {
+        const int64_t row = row0 + grp;
+        const bool live = row < T;
+        const int packed = live ? __ldg(cand + row) : -1;
+        const bool work = packed >= 0;               // -1: handed to the exhaustive search
+        const uint32_t m1 = work ? __ldg(mask1_in + row) : 0u;
+        const uint32_t m2 = work ? __ldg(mask2_in + row) : 0u;
+        const int g1 = packed & 0xFFF, g2 = (packed >> 12) & 0xFFF;
         __syncwarp();
-        for (int d = lane; d < D; d += 32) zrow[wib][d] = __ldg(zn32 + row * D + d);
+        if (work)
+            for (int d = sub * 4; d < D; d += 32)
+                *reinterpret_cast<float4*>(zr + d) = __ldg(reinterpret_cast<const float4*>(zn32 + row * D + d));
         __syncwarp();
-        const float a_sq = __ldg(row_sq + row);
-        const int n_cand = __popc(mask) * kSlotCodes;
+        const float a_sq = work ? __ldg(row_sq + row) : 0.f;
+        const int n1 = __popc(m1), n_cells = n1 + __popc(m2);
         float best_d = INFINITY, second_d = INFINITY;
         int best_i = 0x7fffffff;
-        for (int i = lane; i < n_cand; i += 32) {
-            const int j = __fns(mask, 0, i / kSlotCodes + 1);
-            const int code = g * kGroupCols + j + 32 * (i % kSlotCodes);
+        for (int c = 0; c < n_cells; ++c) {
+            const int j = (c < n1) ? __fns(m1, 0, c + 1) : __fns(m2, 0, c - n1 + 1);
+            const int code = ((c < n1) ? g1 : g2) * kGroupCols + j + 32 * sub;
             const float4* e4 = reinterpret_cast<const float4*>(en32 + (int64_t)code * D);
             float dot = 0.f;
 #pragma unroll 8
-            for (int c = 0; c < D / 4; ++c) {
-                const float4 ev = __ldg(e4 + c);
-                const float4 zv = *reinterpret_cast<const float4*>(&zrow[wib][4 * c]);
+            for (int q = 0; q < D / 4; ++q) {
+                const float4 ev = __ldg(e4 + q);
+                const float4 zv = *reinterpret_cast<const float4*>(zr + 4 * q);
                 dot = __fmaf_rn(zv.x, ev.x, dot);
                 dot = __fmaf_rn(zv.y, ev.y, dot);
                 dot = __fmaf_rn(zv.z, ev.z, dot);
@@ -390,22 +443,26 @@ __global__ void __launch_bounds__(256) k_rescore(const float* __restrict__ zn32,
             else if (dist < second_d) second_d = dist;
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
+        for (int off = 4; off > 0; off >>= 1) {      // fold the 8 lanes of the row
             const float od = __shfl_xor_sync(VQ_FULL, best_d, off);
             const int oi = __shfl_xor_sync(VQ_FULL, best_i, off);
             const float os = __shfl_xor_sync(VQ_FULL, second_d, off);
             if (argmin_better(od, oi, best_d, best_i)) { second_d = fminf(best_d, os); best_d = od; best_i = oi; }
             else second_d = fminf(second_d, od);
         }
-        if (lane == 0) {
+        if (work && sub == 0) {
             cand[row] = best_i | kCandExactBit;
             if (second_d - best_d < VQ_NEAR_TIE_REL * fabsf(best_d)) ++ties;
-            if (__popc(mask) > 1) ++multi;
+            if (n_cells > 1) ++multi;
         }
     }
-    if (lane == 0 && stats) {
-        if (ties) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), ties);
-        if (multi) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_AMBIGUOUS_ROWS), multi);
+    if (stats) {
+        ties = __reduce_add_sync(VQ_FULL, ties);
+        multi = __reduce_add_sync(VQ_FULL, multi);
+        if (lane == 0) {
+            if (ties) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), (unsigned long long)ties);
+            if (multi) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_AMBIGUOUS_ROWS), (unsigned long long)multi);
+        }
     }
 }
 
@@ -443,18 +500,19 @@ static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, int D, u
 
 bool tc_supported(int64_t T, int K, int D) {
     const bool d_ok = (D == 32 || D == 64 || D == 128 || D == 256);
-    return d_ok && K >= tc::kGroupCols && (K % tc::kGroupCols) == 0 && K <= (1 << 20) && T >= 256;
+    // group ids are packed 12 bits each into cand[]
+    return d_ok && K >= tc::kGroupCols && (K % tc::kGroupCols) == 0 && K / tc::kGroupCols <= 4096 && T >= 256;
 }
 
 size_t tc_workspace_bytes(int64_t T, int K, int D) {
     (void)K; (void)D;
-    return sizeof(uint32_t) * (size_t)(T > 0 ? T : 1);
+    return 2 * sizeof(uint32_t) * (size_t)(T > 0 ? T : 1);     // two slot masks per row
 }
 
 template <int KB>
 static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, int T, int K, const int* info,
-                                    int* cand, uint32_t* mask, int* flagged, int* n_flagged, int64_t* stats,
-                                    cudaStream_t s) {
+                                    int* cand, uint32_t* mask, uint32_t* mask2, int* flagged, int* n_flagged,
+                                    int64_t* stats, cudaStream_t s) {
     const tc::SmemLayout L = tc::smem_layout(KB);
     static bool configured = false;
     if (!configured) {
@@ -464,7 +522,8 @@ static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb
     }
     const int n_row_tiles = (T + tc::kRowsPerCta - 1) / tc::kRowsPerCta;
     const int grid = n_row_tiles < sm_count() ? n_row_tiles : sm_count();
-    tc::k_dist_tc<KB><<<grid, tc::kThreads, L.total + 1024, s>>>(ma, mb, T, K, info, cand, mask, flagged, n_flagged, stats);
+    tc::k_dist_tc<KB><<<grid, tc::kThreads, L.total + 1024, s>>>(ma, mb, T, K, info, cand, mask, mask2, flagged, n_flagged,
+                                                                 stats);
     count_launch();
     return cudaGetLastError();
 }
@@ -478,23 +537,24 @@ cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* r
         !tc::make_map(&mb, cb.en16, (uint64_t)cb.K, cb.D, tc::kTileN))
         return cudaErrorInvalidValue;
     uint32_t* mask = static_cast<uint32_t*>(tc_ws);
+    uint32_t* mask2 = mask + T;
     cudaError_t e;
     switch (cb.D / tc::kKBlock) {
-        case 1: e = launch_tc_kernel<1>(ma, mb, (int)T, cb.K, cb.info, cand, mask, flagged, n_flagged, stats, s); break;
-        case 2: e = launch_tc_kernel<2>(ma, mb, (int)T, cb.K, cb.info, cand, mask, flagged, n_flagged, stats, s); break;
-        case 4: e = launch_tc_kernel<4>(ma, mb, (int)T, cb.K, cb.info, cand, mask, flagged, n_flagged, stats, s); break;
-        case 8: e = launch_tc_kernel<8>(ma, mb, (int)T, cb.K, cb.info, cand, mask, flagged, n_flagged, stats, s); break;
+        case 1: e = launch_tc_kernel<1>(ma, mb, (int)T, cb.K, cb.info, cand, mask, mask2, flagged, n_flagged, stats, s); break;
+        case 2: e = launch_tc_kernel<2>(ma, mb, (int)T, cb.K, cb.info, cand, mask, mask2, flagged, n_flagged, stats, s); break;
+        case 4: e = launch_tc_kernel<4>(ma, mb, (int)T, cb.K, cb.info, cand, mask, mask2, flagged, n_flagged, stats, s); break;
+        case 8: e = launch_tc_kernel<8>(ma, mb, (int)T, cb.K, cb.info, cand, mask, mask2, flagged, n_flagged, stats, s); break;
         default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;
-    int64_t blocks = (T + 7) / 8;
-    const int64_t cap = (int64_t)sm_count() * 8;
+    int64_t blocks = (T + 31) / 32;
+    const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     switch (cb.D) {
-        case 32:  tc::k_rescore<32><<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cand, mask, stats); break;
-        case 64:  tc::k_rescore<64><<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cand, mask, stats); break;
-        case 128: tc::k_rescore<128><<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cand, mask, stats); break;
-        case 256: tc::k_rescore<256><<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cand, mask, stats); break;
+        case 32:  tc::k_rescore<32><<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cand, mask, mask2, stats); break;
+        case 64:  tc::k_rescore<64><<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cand, mask, mask2, stats); break;
+        case 128: tc::k_rescore<128><<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cand, mask, mask2, stats); break;
+        case 256: tc::k_rescore<256><<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cand, mask, mask2, stats); break;
         default: return cudaErrorInvalidValue;
     }
     count_launch();

@@ -40,9 +40,11 @@ cudaError_t launch_row_sumsq(const float* zn32, int64_t T, int D, float* row_sq,
 // ---- vq_dist_simt.cu -------------------------------------------------------------------------
 // Exhaustive fp32 search.  rows == nullptr: all T rows; else the first *n_rows entries of `rows`.
 // Writes cand[row] = index | kCandExactBit and counts near-tie rows into stats.
+// partial_ws (scan_partial_bytes) lets listed rows split the codebook over blocks; may be null.
+size_t scan_partial_bytes(int64_t T);
 cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
                               const int* rows, const int* n_rows, int64_t max_rows, int* cand, int64_t* stats,
-                              cudaStream_t s);
+                              void* partial_ws, cudaStream_t s);
 
 // ---- vq_dist_tc.cu ---------------------------------------------------------------------------
 // tcgen05 search: cand[row] = cell id (or exact index for rows resolved in-kernel); rows it cannot
