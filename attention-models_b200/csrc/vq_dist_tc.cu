@@ -133,6 +133,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
         : "r"(taddr));
 }
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float max3(float a, float b, float c) {
@@ -142,10 +152,11 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 }
 
 struct SmemLayout {
-    uint32_t a, b, snap, bars, tmem_slot, total;
+    uint32_t a, b, snap, hand, bars, tmem_slot, total;
 };
+constexpr int kHandBytes = kRowsPerCta * 16;     // per row: g1|g2<<12 (or -1), mask1, mask2, pad; double buffered
 __host__ __device__ constexpr int a_stages(int kb) { return kb <= 2 ? 2 : 1; }
-__host__ __device__ constexpr int b_stages(int kb) { return kb <= 4 ? 8 : 4; }
+__host__ __device__ constexpr int b_stages(int kb) { return kb <= 4 ? 8 : 3; }
 // slot-maxima snapshots: 2 areas x 256 rows x 32 floats; rows padded by 16 B (conflict-free STS.128)
 // except at D = 256 where shared memory is tight
 __host__ __device__ constexpr int snap_row_bytes(int kb) { return kb <= 4 ? 144 : 128; }
@@ -155,20 +166,31 @@ __host__ __device__ inline SmemLayout smem_layout(int kb) {
     L.a = 0;
     L.b = L.a + a_stages(kb) * kb * kABlockBytes;
     L.snap = L.b + b_stages(kb) * kBStageBytes;
-    L.bars = L.snap + 2 * kRowsPerCta * snap_row_bytes(kb);
-    L.tmem_slot = L.bars + 8 * (2 * kMaxBStages + 2 * 2 + 4);
+    L.hand = L.snap + 2 * kRowsPerCta * snap_row_bytes(kb);
+    L.bars = L.hand + 2 * kHandBytes;
+    L.tmem_slot = L.bars + 8 * (2 * kMaxBStages + 2 * 2 + 4 + 4);
     L.total = L.tmem_slot + 16;
     return L;
 }
 
+// Codes of one cell: slot s of group g covers columns 64*m + (s < 16 ? 0 : 32) + (s & 15) + {0, 16}, m = 0..3
+// (an epilogue "unit" is two x16 TMEM loads, 16 columns apart, folded into 16 slots by one max3 each; even
+// units feed slots 0..15, odd units slots 16..31).
+__device__ __forceinline__ int cell_code(int g, int slot, int i) {
+    return g * kGroupCols + 64 * (i >> 1) + ((slot & 16) << 1) + (slot & 15) + 16 * (i & 1);
+}
+
 // One CTA per SM, persistent over row tiles.  KB = D / 32.
+// warp 0: TMA producer   warp 1: MMA issuer   warps 2-3: exact fp32 rescoring of the previous row tile
+// (hidden under the ALU-bound main loop)   warps 4-11: epilogue, one thread per row
 template <int KB>
 __global__ void __launch_bounds__(kThreads, 1)
 k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int T, int K,
-          const int* __restrict__ cb_info, int* __restrict__ cand, uint32_t* __restrict__ mask1_out,
-          uint32_t* __restrict__ mask2_out, int* __restrict__ flagged, int* __restrict__ n_flagged,
-          int64_t* __restrict__ stats) {
+          const float* __restrict__ zn32, const float* __restrict__ row_sq, const float* __restrict__ en32,
+          const float* __restrict__ code_sq, const int* __restrict__ cb_info, int* __restrict__ cand,
+          int* __restrict__ flagged, int* __restrict__ n_flagged, int64_t* __restrict__ stats) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int D = KB * kKBlock;
     constexpr int AS = a_stages(KB);
     constexpr int BS = b_stages(KB);
     constexpr int kSnapRow = snap_row_bytes(KB);
@@ -185,6 +207,8 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     auto t_empty = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 2 + s); };
     auto a_full = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 4 + s); };
     auto a_empty = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 6 + s); };
+    auto h_full = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 8 + s); };
+    auto h_empty = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 10 + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_slot);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -196,6 +220,7 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         for (int s = 0; s < BS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), 256); }
         for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(h_full(s), 256); mbar_init(h_empty(s), 64); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -267,7 +292,83 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                 umma_commit(a_empty(as));            // row tile's A operand no longer needed
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < 4) {
+        // ===================== rescoring: 64 threads, 4 rows each per row tile =====================
+        const int rtid = threadIdx.x - 64;
+        unsigned ties = 0, multi = 0;
+        int it = 0;
+        for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
+            const int hb = it & 1;
+            mbar_wait(h_full(hb), ((uint32_t)(it >> 1)) & 1u);
+            const int4* hand = reinterpret_cast<const int4*>(smem + L.hand + hb * kHandBytes);
+#pragma unroll 1
+            for (int rr = 0; rr < kRowsPerCta / 64; ++rr) {
+                const int r = rtid + 64 * rr;
+                const int row = rt * kRowsPerCta + r;
+                const int4 h = hand[r];
+                if (row >= T || h.x < 0) continue;                 // out of range, or left to the exhaustive search
+                const int g1 = h.x & 0xFFF, g2 = (h.x >> 12) & 0xFFF;
+                const uint32_t m1 = (uint32_t)h.y, m2 = (uint32_t)h.z;
+                // small rows live in registers; wide rows are re-read chunk-wise (L1 hits after the first code)
+                constexpr bool kRowInRegs = (D <= 64);
+                float4 z[kRowInRegs ? D / 4 : 1];
+                const float4* z4 = reinterpret_cast<const float4*>(zn32 + (int64_t)row * D);
+                if (kRowInRegs) {
+#pragma unroll
+                    for (int q = 0; q < (kRowInRegs ? D / 4 : 1); ++q) z[q] = __ldg(z4 + q);
+                }
+                const float a_sq = __ldg(row_sq + row);
+                const int n1 = __popc(m1), n_cells = n1 + __popc(m2);
+                float best_d = INFINITY, second_d = INFINITY;
+                int best_i = 0x7fffffff;
+                for (int c = 0; c < n_cells; ++c) {
+                    const int slot = (c < n1) ? __fns(m1, 0, c + 1) : __fns(m2, 0, c - n1 + 1);
+                    const int g = (c < n1) ? g1 : g2;
+#pragma unroll 2
+                    for (int i = 0; i < 8; ++i) {
+                        const int code = cell_code(g, slot, i);
+                        const float4* e4 = reinterpret_cast<const float4*>(en32 + (int64_t)code * D);
+                        float dot = 0.f;
+                        if constexpr (kRowInRegs) {
+#pragma unroll
+                            for (int q = 0; q < D / 4; ++q) {
+                                const float4 ev = __ldg(e4 + q);
+                                dot = __fmaf_rn(z[q].x, ev.x, dot);
+                                dot = __fmaf_rn(z[q].y, ev.y, dot);
+                                dot = __fmaf_rn(z[q].z, ev.z, dot);
+                                dot = __fmaf_rn(z[q].w, ev.w, dot);
+                            }
+                        } else {
+#pragma unroll 8
+                            for (int q = 0; q < D / 4; ++q) {
+                                const float4 ev = __ldg(e4 + q);
+                                const float4 zv = __ldg(z4 + q);
+                                dot = __fmaf_rn(zv.x, ev.x, dot);
+                                dot = __fmaf_rn(zv.y, ev.y, dot);
+                                dot = __fmaf_rn(zv.z, ev.z, dot);
+                                dot = __fmaf_rn(zv.w, ev.w, dot);
+                            }
+                        }
+                        const float dist = ref_distance(a_sq, __ldg(code_sq + code), dot);
+                        if (argmin_better(dist, code, best_d, best_i)) { second_d = best_d; best_d = dist; best_i = code; }
+                        else if (dist < second_d) second_d = dist;
+                    }
+                }
+                cand[row] = best_i | kCandExactBit;
+                if (second_d - best_d < VQ_NEAR_TIE_REL * fabsf(best_d)) ++ties;
+                if (n_cells > 1) ++multi;
+            }
+            mbar_arrive(h_empty(hb));
+        }
+        if (stats) {
+            ties = __reduce_add_sync(VQ_FULL, ties);
+            multi = __reduce_add_sync(VQ_FULL, multi);
+            if (lane == 0) {
+                if (ties) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), (unsigned long long)ties);
+                if (multi) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_AMBIGUOUS_ROWS), (unsigned long long)multi);
+            }
+        }
+    } else {
         // ===================== epilogue: 8 warps, one thread per row =====================
         const int e = warp - 4;
         const int r_sub = e >> 2;                    // which 128-row MMA tile
@@ -278,37 +379,48 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         constexpr uint32_t kSnapArea = kRowsPerCta * kSnapRow;
         const bool force_exhaustive = (cb_info[0] != 0);
         uint32_t phase = 0;                          // parity of t_full: flips once per group (2 tiles, 2 stages)
-        for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
+        int it = 0;
+        for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
             float slot[32];
             float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
             int g1 = 0, g2 = 0;
             uint32_t best_area = 0;                  // which snapshot area holds the best group's slots
-            for (int g = 0; g < n_groups; ++g, phase ^= 1u) {
+            // software pipeline over "units" (2 x16 loads = 32 columns -> 16 slots): unit u+1 is in flight
+            // while unit u is folded.  8 units per group; tile = unit >> 2.
+            float buf[2][32];
+            mbar_wait(t_full(0), phase);
+            tc_fence_after();
+            tmem_ld16(tbase, &buf[0][0]);
+            tmem_ld16(tbase + 16, &buf[0][16]);
+            for (int g = 0; g < n_groups; ++g) {
 #pragma unroll
-                for (int tsub = 0; tsub < kGroupTiles; ++tsub) {
-                    mbar_wait(t_full(tsub), phase);
-                    tc_fence_after();
-                    const uint32_t taddr = tbase + (uint32_t)(tsub * 2 * kTileN);
-                    float va[32], vb[32];
-                    tmem_ld32(taddr, va);
-                    tmem_ld32(taddr + 32, vb);
-                    tmem_ld_wait();
-                    if (tsub == 0) {
+                for (int u = 0; u < 8; ++u) {
+                    tmem_ld_wait();                                   // unit u has landed in buf[u & 1]
+                    if (u == 3) { tc_fence_before(); mbar_arrive(t_empty(0)); }   // tile 0 fully in registers
+                    if (u == 7) { tc_fence_before(); mbar_arrive(t_empty(1)); }
+                    // prefetch the next unit (of this group, or unit 0 of the next group)
+                    if (u < 7) {
+                        if (u == 3) { mbar_wait(t_full(1), phase); tc_fence_after(); }
+                        const uint32_t ta = tbase + (uint32_t)(((u + 1) >> 2) * 2 * kTileN + ((u + 1) & 3) * 32);
+                        tmem_ld16(ta, &buf[(u + 1) & 1][0]);
+                        tmem_ld16(ta + 16, &buf[(u + 1) & 1][16]);
+                    } else if (g + 1 < n_groups) {
+                        mbar_wait(t_full(0), phase ^ 1u);
+                        tc_fence_after();
+                        tmem_ld16(tbase, &buf[0][0]);
+                        tmem_ld16(tbase + 16, &buf[0][16]);
+                    }
+                    const float* v = buf[u & 1];
+                    float* sl = slot + 16 * (u & 1);
+                    if (u < 2) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) slot[j] = fmaxf(va[j], vb[j]);
+                        for (int j = 0; j < 16; ++j) sl[j] = fmaxf(v[j], v[16 + j]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) slot[j] = max3(slot[j], va[j], vb[j]);
+                        for (int j = 0; j < 16; ++j) sl[j] = max3(sl[j], v[j], v[16 + j]);
                     }
-                    tmem_ld32(taddr + 64, va);
-                    tmem_ld32(taddr + 96, vb);
-                    tmem_ld_wait();
-                    // all four chunks are in registers: hand the accumulator stage back to the MMA warp
-                    tc_fence_before();
-                    mbar_arrive(t_empty(tsub));
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) slot[j] = max3(slot[j], va[j], vb[j]);
                 }
+                phase ^= 1u;
                 // group maximum: 3-input tree over the 32 slots
                 float t[11];
 #pragma unroll
@@ -364,11 +476,13 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             const int row = rt * kRowsPerCta + row_in_cta;
             const bool in_range = row < T;
             const bool flag = in_range && !decided;
-            if (in_range) {
-                cand[row] = decided ? (g1 | (g2 << 12)) : -1;
-                mask1_out[row] = mask1;
-                mask2_out[row] = mask2;
-            }
+            // hand the verdict to the rescoring warps (double-buffered)
+            const int hb = it & 1;
+            mbar_wait(h_empty(hb), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+            reinterpret_cast<int4*>(smem + L.hand + hb * kHandBytes)[row_in_cta] =
+                make_int4(decided ? (g1 | (g2 << 12)) : -1, (int)mask1, (int)mask2, 0);
+            mbar_arrive(h_full(hb));
+            if (flag) cand[row] = -1;
             const uint32_t ballot = __ballot_sync(VQ_FULL, flag);
             if (ballot) {
                 int base = 0;
@@ -386,83 +500,6 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Exact fp32 rescoring of the surviving cells.  A cell is the 8 codes g*256 + j + 32*s (s = 0..7) of
-// one slot j; 8 lanes share a row (one code of the cell each), 4 rows per warp, and rows with several
-// surviving cells loop over them.  Same fma chain as the exhaustive search => identical indices.
-// ---------------------------------------------------------------------------------------------
-template <int D>
-__global__ void __launch_bounds__(256) k_rescore(const float* __restrict__ zn32, const float* __restrict__ row_sq,
-                                                 const float* __restrict__ en32, const float* __restrict__ code_sq,
-                                                 int64_t T, int* __restrict__ cand, const uint32_t* __restrict__ mask1_in,
-                                                 const uint32_t* __restrict__ mask2_in, int64_t* __restrict__ stats) {
-    static_assert(kGroupCols / 32 == 8, "8 lanes per row assume 8 codes per cell");
-    __shared__ __align__(16) float zrow[32][D];      // 8 warps x 4 rows
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int sub = lane & 7, grp = lane >> 3;
-    float* zr = zrow[wib * 4 + grp];
-    const int64_t first = ((int64_t)blockIdx.x * 8 + wib) * 4;
-    const int64_t stride = (int64_t)gridDim.x * 32;
-    unsigned ties = 0, multi = 0;
-    for (int64_t row0 = first; row0 < T; row0 += stride) {
-        const int64_t row = row0 + grp;
-        const bool live = row < T;
-        const int packed = live ? __ldg(cand + row) : -1;
-        const bool work = packed >= 0;               // -1: handed to the exhaustive search
-        const uint32_t m1 = work ? __ldg(mask1_in + row) : 0u;
-        const uint32_t m2 = work ? __ldg(mask2_in + row) : 0u;
-        const int g1 = packed & 0xFFF, g2 = (packed >> 12) & 0xFFF;
-        __syncwarp();
-        if (work)
-            for (int d = sub * 4; d < D; d += 32)
-                *reinterpret_cast<float4*>(zr + d) = __ldg(reinterpret_cast<const float4*>(zn32 + row * D + d));
-        __syncwarp();
-        const float a_sq = work ? __ldg(row_sq + row) : 0.f;
-        const int n1 = __popc(m1), n_cells = n1 + __popc(m2);
-        float best_d = INFINITY, second_d = INFINITY;
-        int best_i = 0x7fffffff;
-        for (int c = 0; c < n_cells; ++c) {
-            const int j = (c < n1) ? __fns(m1, 0, c + 1) : __fns(m2, 0, c - n1 + 1);
-            const int code = ((c < n1) ? g1 : g2) * kGroupCols + j + 32 * sub;
-            const float4* e4 = reinterpret_cast<const float4*>(en32 + (int64_t)code * D);
-            float dot = 0.f;
-#pragma unroll 8
-            for (int q = 0; q < D / 4; ++q) {
-                const float4 ev = __ldg(e4 + q);
-                const float4 zv = *reinterpret_cast<const float4*>(zr + 4 * q);
-                dot = __fmaf_rn(zv.x, ev.x, dot);
-                dot = __fmaf_rn(zv.y, ev.y, dot);
-                dot = __fmaf_rn(zv.z, ev.z, dot);
-                dot = __fmaf_rn(zv.w, ev.w, dot);
-            }
-            const float dist = ref_distance(a_sq, __ldg(code_sq + code), dot);
-            if (argmin_better(dist, code, best_d, best_i)) { second_d = best_d; best_d = dist; best_i = code; }
-            else if (dist < second_d) second_d = dist;
-        }
-#pragma unroll
-        for (int off = 4; off > 0; off >>= 1) {      // fold the 8 lanes of the row
-            const float od = __shfl_xor_sync(VQ_FULL, best_d, off);
-            const int oi = __shfl_xor_sync(VQ_FULL, best_i, off);
-            const float os = __shfl_xor_sync(VQ_FULL, second_d, off);
-            if (argmin_better(od, oi, best_d, best_i)) { second_d = fminf(best_d, os); best_d = od; best_i = oi; }
-            else second_d = fminf(second_d, od);
-        }
-        if (work && sub == 0) {
-            cand[row] = best_i | kCandExactBit;
-            if (second_d - best_d < VQ_NEAR_TIE_REL * fabsf(best_d)) ++ties;
-            if (n_cells > 1) ++multi;
-        }
-    }
-    if (stats) {
-        ties = __reduce_add_sync(VQ_FULL, ties);
-        multi = __reduce_add_sync(VQ_FULL, multi);
-        if (lane == 0) {
-            if (ties) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), (unsigned long long)ties);
-            if (multi) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_AMBIGUOUS_ROWS), (unsigned long long)multi);
-        }
     }
 }
 
@@ -505,14 +542,14 @@ bool tc_supported(int64_t T, int K, int D) {
 }
 
 size_t tc_workspace_bytes(int64_t T, int K, int D) {
-    (void)K; (void)D;
-    return 2 * sizeof(uint32_t) * (size_t)(T > 0 ? T : 1);     // two slot masks per row
+    (void)T; (void)K; (void)D;
+    return 0;
 }
 
 template <int KB>
-static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, int T, int K, const int* info,
-                                    int* cand, uint32_t* mask, uint32_t* mask2, int* flagged, int* n_flagged,
-                                    int64_t* stats, cudaStream_t s) {
+static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, int T, const float* zn32,
+                                    const float* row_sq, const CodebookView& cb, int* cand, int* flagged,
+                                    int* n_flagged, int64_t* stats, cudaStream_t s) {
     const tc::SmemLayout L = tc::smem_layout(KB);
     static bool configured = false;
     if (!configured) {
@@ -522,8 +559,8 @@ static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb
     }
     const int n_row_tiles = (T + tc::kRowsPerCta - 1) / tc::kRowsPerCta;
     const int grid = n_row_tiles < sm_count() ? n_row_tiles : sm_count();
-    tc::k_dist_tc<KB><<<grid, tc::kThreads, L.total + 1024, s>>>(ma, mb, T, K, info, cand, mask, mask2, flagged, n_flagged,
-                                                                 stats);
+    tc::k_dist_tc<KB><<<grid, tc::kThreads, L.total + 1024, s>>>(ma, mb, T, cb.K, zn32, row_sq, cb.en32, cb.code_sq, cb.info,
+                                                                 cand, flagged, n_flagged, stats);
     count_launch();
     return cudaGetLastError();
 }
@@ -531,34 +568,19 @@ static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb
 cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* row_sq, const CodebookView& cb,
                            int64_t T, int* cand, int* flagged, int* n_flagged, int64_t* stats, void* tc_ws,
                            cudaStream_t s) {
+    (void)tc_ws;
     if (T == 0) return cudaSuccess;
     CUtensorMap ma, mb;
     if (!tc::make_map(&ma, zn16, (uint64_t)T, cb.D, tc::kRowsPerCta) ||
         !tc::make_map(&mb, cb.en16, (uint64_t)cb.K, cb.D, tc::kTileN))
         return cudaErrorInvalidValue;
-    uint32_t* mask = static_cast<uint32_t*>(tc_ws);
-    uint32_t* mask2 = mask + T;
-    cudaError_t e;
     switch (cb.D / tc::kKBlock) {
-        case 1: e = launch_tc_kernel<1>(ma, mb, (int)T, cb.K, cb.info, cand, mask, mask2, flagged, n_flagged, stats, s); break;
-        case 2: e = launch_tc_kernel<2>(ma, mb, (int)T, cb.K, cb.info, cand, mask, mask2, flagged, n_flagged, stats, s); break;
-        case 4: e = launch_tc_kernel<4>(ma, mb, (int)T, cb.K, cb.info, cand, mask, mask2, flagged, n_flagged, stats, s); break;
-        case 8: e = launch_tc_kernel<8>(ma, mb, (int)T, cb.K, cb.info, cand, mask, mask2, flagged, n_flagged, stats, s); break;
+        case 1: return launch_tc_kernel<1>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, s);
+        case 2: return launch_tc_kernel<2>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, s);
+        case 4: return launch_tc_kernel<4>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, s);
+        case 8: return launch_tc_kernel<8>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, s);
         default: return cudaErrorInvalidValue;
     }
-    if (e != cudaSuccess) return e;
-    int64_t blocks = (T + 31) / 32;
-    const int64_t cap = (int64_t)sm_count() * 16;
-    if (blocks > cap) blocks = cap;
-    switch (cb.D) {
-        case 32:  tc::k_rescore<32><<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cand, mask, mask2, stats); break;
-        case 64:  tc::k_rescore<64><<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cand, mask, mask2, stats); break;
-        case 128: tc::k_rescore<128><<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cand, mask, mask2, stats); break;
-        case 256: tc::k_rescore<256><<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cand, mask, mask2, stats); break;
-        default: return cudaErrorInvalidValue;
-    }
-    count_launch();
-    return cudaGetLastError();
 }
 
 }  // namespace vq
