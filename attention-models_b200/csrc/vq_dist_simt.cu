@@ -46,17 +46,18 @@ __device__ __forceinline__ void best_merge(Best& a, float d1, int i1, float d2) 
 // rows == nullptr: every row 0..T-1.  Otherwise the listed rows [row_begin, min(*n_rows_ptr, row_end)).
 // partial == nullptr: the block scans all K codes and writes cand[] itself.  Otherwise blockIdx.y selects
 // one of gridDim.y code ranges and the (best, index, second) triple goes to partial[split][list slot];
-// k_merge_partials folds the ranges in order (no atomics, deterministic).
+// the last range to finish a row tile folds them (order-independent argmin => deterministic).
 __global__ void __launch_bounds__(256) k_scan_exact(const float* __restrict__ zn32, const float* __restrict__ row_sq,
                                                     const float* __restrict__ en32, const float* __restrict__ code_sq,
                                                     int64_t T, int K, int D, const int* __restrict__ rows,
                                                     const int* __restrict__ n_rows_ptr, int64_t row_begin,
                                                     int64_t row_end, int* __restrict__ cand,
                                                     float4* __restrict__ partial, int partial_cap,
-                                                    int64_t* __restrict__ stats) {
+                                                    int* __restrict__ tile_done, int64_t* __restrict__ stats) {
     __shared__ __align__(16) float zs[kDK][kTM + 4];
     __shared__ __align__(16) float es[kDK][kTN + 4];
     __shared__ int row_id[kTM];
+    __shared__ int s_last;
 
     int64_t n_rows = rows ? (int64_t)(*n_rows_ptr) : T;
     if (n_rows > row_end) n_rows = row_end;
@@ -156,29 +157,51 @@ __global__ void __launch_bounds__(256) k_scan_exact(const float* __restrict__ zn
                 }
             }
         }
+        if (partial) {
+            // the last code range to finish a row tile folds all ranges: lane = range, shuffle tree.
+            // argmin with index tie-break and "second smallest" do not depend on the fold order.
+            __threadfence();
+            __syncthreads();
+            const int tile_idx = (int)(tile0 / kTM);
+            if (tid == 0) s_last = (atomicAdd(tile_done + tile_idx, 1) == (int)gridDim.y - 1);
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                const int lane = tid & 31, w = tid >> 5;
+                for (int rr = w * 8; rr < w * 8 + 8; ++rr) {
+                    const int64_t slot = tile0 + rr;
+                    if (slot >= n_rows) break;
+                    Best b;
+                    b.d1 = INFINITY; b.i1 = 0x7fffffff; b.d2 = INFINITY;
+                    if (lane < (int)gridDim.y) {
+                        const float4 p = __ldcg(partial + (int64_t)lane * partial_cap + slot);
+                        b.d1 = p.x; b.i1 = __float_as_int(p.y); b.d2 = p.z;
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const float od1 = __shfl_xor_sync(VQ_FULL, b.d1, off);
+                        const int oi1 = __shfl_xor_sync(VQ_FULL, b.i1, off);
+                        const float od2 = __shfl_xor_sync(VQ_FULL, b.d2, off);
+                        best_merge(b, od1, oi1, od2);
+                    }
+                    if (lane == 0) {
+                        cand[row_id[rr]] = b.i1 | kCandExactBit;
+                        if (stats && (b.d2 - b.d1) < VQ_NEAR_TIE_REL * fabsf(b.d1))
+                            atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), 1ull);
+                    }
+                }
+                if (tid == 0) tile_done[tile_idx] = 0;      // ready for the next call
+            }
+        }
     }
 }
 
-__global__ void __launch_bounds__(256) k_merge_partials(const float4* __restrict__ partial, int n_splits, int cap,
-                                                        const int* __restrict__ rows, const int* __restrict__ n_rows_ptr,
-                                                        int* __restrict__ cand, int64_t* __restrict__ stats) {
-    const int n = min(*n_rows_ptr, cap);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Best b;
-    b.d1 = INFINITY; b.i1 = 0x7fffffff; b.d2 = INFINITY;
-    for (int s = 0; s < n_splits; ++s) {
-        const float4 p = partial[(int64_t)s * cap + i];
-        best_merge(b, p.x, __float_as_int(p.y), p.z);
-    }
-    cand[rows[i]] = b.i1 | kCandExactBit;
-    if (stats && (b.d2 - b.d1) < VQ_NEAR_TIE_REL * fabsf(b.d1))
-        atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), 1ull);
-}
-
+// [tile-done counters (one int per 64-row tile, 1 KiB)] [partials: splits x cap float4]
+constexpr size_t kTileDoneBytes = 1024;
+static_assert(kScanSplitCap / kTM * sizeof(int) <= kTileDoneBytes, "tile counters do not fit");
 size_t scan_partial_bytes(int64_t T) {
     const int64_t cap = T < kScanSplitCap ? T : kScanSplitCap;
-    return sizeof(float4) * (size_t)kScanSplits * (size_t)(cap > 0 ? cap : 1);
+    return kTileDoneBytes + sizeof(float4) * (size_t)kScanSplits * (size_t)(cap > 0 ? cap : 1);
 }
 
 cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
@@ -191,7 +214,7 @@ cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const Code
         int64_t blocks = (n + kTM - 1) / kTM;
         if (blocks > cap_blocks) blocks = cap_blocks;
         k_scan_exact<<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, 0,
-                                                     n, cand, nullptr, 0, stats);
+                                                     n, cand, nullptr, 0, nullptr, stats);
         count_launch();
         return cudaGetLastError();
     }
@@ -200,17 +223,19 @@ cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const Code
     int splits = cb.K / kTN;
     if (splits > kScanSplits) splits = kScanSplits;
     if (splits < 1) splits = 1;
-    float4* partial = static_cast<float4*>(partial_ws);
+    int* tile_done = static_cast<int*>(partial_ws);
+    float4* partial = reinterpret_cast<float4*>(static_cast<char*>(partial_ws) + kTileDoneBytes);
+    cudaError_t e = cudaMemsetAsync(tile_done, 0, kTileDoneBytes, s);
+    if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((cap + kTM - 1) / kTM), (unsigned)splits);
     k_scan_exact<<<grid, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, 0, cap, cand,
-                                      partial, cap, stats);
-    k_merge_partials<<<(cap + 255) / 256, 256, 0, s>>>(partial, splits, cap, rows, n_rows, cand, stats);
-    count_launch(2);
+                                      partial, cap, tile_done, stats);
+    count_launch();
     if (n > cap) {
         int64_t blocks = (n - cap + kTM - 1) / kTM;
         if (blocks > cap_blocks) blocks = cap_blocks;
         k_scan_exact<<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, cap,
-                                                     n, cand, nullptr, 0, stats);
+                                                     n, cand, nullptr, 0, nullptr, stats);
         count_launch();
     }
     return cudaGetLastError();

@@ -26,6 +26,7 @@
 // on every other group; it is undecided only if a third group is within 2*eps of the best.
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/vq_b200.h"
 #include "vq_common.cuh"
@@ -69,20 +70,18 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
         : "memory");
     return done;
 }
-// Bounded wait: a broken pipeline traps (launch failure) instead of hanging the GPU.  The common case
-// (already complete, or completes within the hardware's try_wait window) costs one instruction.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
-    const long long t0 = clock64();
-    while (!mbar_try(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) {
-            printf("vq_dist_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-                   threadIdx.x, bar, parity);
-            __trap();
-        }
-    }
+// Bounded wait: a broken pipeline traps (launch failure) instead of hanging the GPU.  try_wait itself
+// suspends the thread for a hardware-defined window, so the retry loop is just try_wait + counter:
+// no clock reads, (almost) no issue slots stolen from the epilogue warps sharing the scheduler.
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+    printf("vq_dist_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
+           parity);
+    __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
+    uint32_t spins = 0;
+    while (!mbar_try(bar, parity))
+        if (++spins > (1u << 27)) mbar_timeout(bar, parity);
 }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -188,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int T, int K,
           const float* __restrict__ zn32, const float* __restrict__ row_sq, const float* __restrict__ en32,
           const float* __restrict__ code_sq, const int* __restrict__ cb_info, int* __restrict__ cand,
-          int* __restrict__ flagged, int* __restrict__ n_flagged, int64_t* __restrict__ stats) {
+          int* __restrict__ flagged, int* __restrict__ n_flagged, int64_t* __restrict__ stats, int debug_flags) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int D = KB * kKBlock;
     constexpr int AS = a_stages(KB);
@@ -307,6 +306,7 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                 const int row = rt * kRowsPerCta + r;
                 const int4 h = hand[r];
                 if (row >= T || h.x < 0) continue;                 // out of range, or left to the exhaustive search
+                if (debug_flags & 1) { cand[row] = kCandExactBit; continue; }   // timing experiment only
                 const int g1 = h.x & 0xFFF, g2 = (h.x >> 12) & 0xFFF;
                 const uint32_t m1 = (uint32_t)h.y, m2 = (uint32_t)h.z;
                 // small rows live in registers; wide rows are re-read chunk-wise (L1 hits after the first code)
@@ -559,8 +559,9 @@ static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb
     }
     const int n_row_tiles = (T + tc::kRowsPerCta - 1) / tc::kRowsPerCta;
     const int grid = n_row_tiles < sm_count() ? n_row_tiles : sm_count();
+    static const int debug_flags = getenv("VQ_TC_DEBUG") ? atoi(getenv("VQ_TC_DEBUG")) : 0;
     tc::k_dist_tc<KB><<<grid, tc::kThreads, L.total + 1024, s>>>(ma, mb, T, cb.K, zn32, row_sq, cb.en32, cb.code_sq, cb.info,
-                                                                 cand, flagged, n_flagged, stats);
+                                                                 cand, flagged, n_flagged, stats, debug_flags);
     count_launch();
     return cudaGetLastError();
 }

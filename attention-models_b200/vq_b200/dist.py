@@ -82,14 +82,43 @@ class ShardedQuantiser:
         if world_size is None:
             world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.world_size = world_size
+        self._plans: Dict[tuple, Dict[str, torch.Tensor]] = {}
 
     @staticmethod
     def uses_tensor_cores(T: int, K: int, D: int) -> bool:
         return bool(_lib.load().vq_uses_tensor_cores(T, K, D))
 
+    def _plan(self, z: torch.Tensor, K: int, D: int, T: int, flags: int) -> Dict[str, torch.Tensor]:
+        """Buffers of one (shape, device) are allocated once and reused by every later step: the step
+        itself then costs a handful of ctypes calls and no allocator traffic.  Outputs of step() are
+        views of these buffers and are overwritten by the next step() with the same shape."""
+        from .functional import _scratch
+        dev = z.device
+        key = (dev, tuple(z.shape), K, D, flags)
+        plan = self._plans.get(key)
+        if plan is None:
+            pack = PackedReduce(K, D)
+            fws_bytes = _lib.size_query("vq_workspace_bytes", T, K, D, flags)
+            bws_bytes = _lib.size_query("vq_backward_workspace_bytes", T, K, D)
+            cb_bytes = _lib.size_query("vq_codebook_bytes", K, D)
+            plan = {
+                "pack": pack, "fws_bytes": fws_bytes, "bws_bytes": bws_bytes, "cb_bytes": cb_bytes,
+                "cb": _scratch(cb_bytes, dev), "fws": _scratch(fws_bytes, dev), "bws": _scratch(bws_bytes, dev),
+                "z_q": torch.empty_like(z), "grad_z": torch.empty_like(z),
+                "idx": torch.empty(T, dtype=torch.int64, device=dev),
+                "loss": torch.empty(1, dtype=torch.float32, device=dev),
+                "hist": torch.empty(K, dtype=torch.int32, device=dev),
+                "stats": torch.empty(STATS_LEN, dtype=torch.int64, device=dev),
+                "zn": torch.empty(T, D, dtype=torch.float32, device=dev),
+                "denom": torch.empty(T, dtype=torch.float32, device=dev),
+                "grad_w": torch.empty(K, D, dtype=torch.float32, device=dev),
+                "buf": pack.allocate(dev),
+            }
+            self._plans[key] = plan
+        return plan
+
     def step(self, z: torch.Tensor, upstream: Optional[torch.Tensor], weight: torch.Tensor) -> Dict[str, torch.Tensor]:
-        from .functional import (FORMS, LAYOUT_NCHW, LAYOUT_TOKEN_MAJOR, _ptr, _require_cuda, _scratch, _stream,
-                                 _token_geometry, prepare_codebook)
+        from .functional import FORMS, LAYOUT_NCHW, LAYOUT_TOKEN_MAJOR, _ptr, _require_cuda, _stream, _token_geometry
         _require_cuda(z, "z")
         lib = _lib.load()
         dev = z.device
@@ -100,40 +129,30 @@ class ShardedQuantiser:
         T, hw = _token_geometry(z, layout, D)
         n_total = max(T * D * self.world_size, 1)
         flags = _lib.FLAG_EXACT_SCAN if self.exact_scan else 0
-        prepared = prepare_codebook(weight)
-        pack = PackedReduce(K, D)
-
-        z_q = torch.empty_like(z)
-        idx = torch.empty(T, dtype=torch.int64, device=dev)
-        loss = torch.empty(1, dtype=torch.float32, device=dev)
-        hist = torch.empty(K, dtype=torch.int32, device=dev)
-        stats = torch.empty(STATS_LEN, dtype=torch.int64, device=dev)
-        zn = torch.empty(T, D, dtype=torch.float32, device=dev)
-        denom = torch.empty(T, dtype=torch.float32, device=dev)
-        grad_z = torch.empty_like(z)
-        grad_w = torch.empty(K, D, dtype=torch.float32, device=dev)
-        buf = pack.allocate(dev)
-        fws_bytes = _lib.size_query("vq_workspace_bytes", T, K, D, flags)
-        bws_bytes = _lib.size_query("vq_backward_workspace_bytes", T, K, D)
-        fws, bws = _scratch(fws_bytes, dev), _scratch(bws_bytes, dev)
+        p = self._plan(z, K, D, T, flags)
+        pack, buf = p["pack"], p["buf"]
+        w = weight.detach()
+        if not w.is_contiguous():
+            w = w.contiguous()
         up = None if upstream is None else upstream.contiguous()
+        cb, seg = _ptr(p["cb"]), _ptr(buf)          # the segment sums are the head of the packed buffer
         with torch.cuda.device(dev):
             s = _stream(dev)
-            _lib.check(lib.vq_forward(_ptr(z), layout, T, hw, _ptr(prepared.blob), K, D, form_id, self.beta, flags,
-                                      n_total, _ptr(z_q), _ptr(idx), None, _ptr(hist), _ptr(stats), _ptr(zn),
-                                      _ptr(denom), _ptr(fws), fws_bytes, s))
-            _lib.check(lib.vq_backward_tokens(_ptr(up), layout, T, hw, _ptr(zn), _ptr(denom), _ptr(idx),
-                                              _ptr(prepared.blob), K, D, form_id, self.beta, None, n_total,
-                                              _ptr(grad_z), _ptr(pack.seg(buf)), _ptr(bws), bws_bytes, s))
+            _lib.check(lib.vq_codebook_prepare(_ptr(w), K, D, cb, p["cb_bytes"], s))
+            _lib.check(lib.vq_forward(_ptr(z), layout, T, hw, cb, K, D, form_id, self.beta, flags, n_total,
+                                      _ptr(p["z_q"]), _ptr(p["idx"]), None, _ptr(p["hist"]), _ptr(p["stats"]),
+                                      _ptr(p["zn"]), _ptr(p["denom"]), _ptr(p["fws"]), p["fws_bytes"], s))
+            _lib.check(lib.vq_backward_tokens(_ptr(up), layout, T, hw, _ptr(p["zn"]), _ptr(p["denom"]), _ptr(p["idx"]),
+                                              cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_z"]), seg,
+                                              _ptr(p["bws"]), p["bws_bytes"], s))
             if self.world_size > 1:
-                pack.fill_side_channels(buf, hist, stats)
+                pack.fill_side_channels(buf, p["hist"], p["stats"])
                 pack.all_reduce(buf, self.group)
                 red_stats = pack.stats_from(buf)
                 hist_out = pack.hist(buf)
             else:
-                red_stats, hist_out = stats, hist
-            _lib.check(lib.vq_loss_finalize(_ptr(red_stats), n_total, form_id, self.beta, _ptr(loss), s))
-            _lib.check(lib.vq_backward_codebook(_ptr(pack.seg(buf)), _ptr(prepared.blob), K, D, form_id, self.beta,
-                                                None, n_total, _ptr(grad_w), s))
-        return {"z_q": z_q, "indices": idx, "loss": loss.view(()), "grad_z": grad_z, "grad_weight": grad_w,
-                "histogram": hist_out, "stats": stats}
+                red_stats, hist_out = p["stats"], p["hist"]
+            _lib.check(lib.vq_loss_finalize(_ptr(red_stats), n_total, form_id, self.beta, _ptr(p["loss"]), s))
+            _lib.check(lib.vq_backward_codebook(seg, cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_w"]), s))
+        return {"z_q": p["z_q"], "indices": p["idx"], "loss": p["loss"].view(()), "grad_z": p["grad_z"],
+                "grad_weight": p["grad_w"], "histogram": hist_out, "stats": p["stats"]}
