@@ -227,7 +227,7 @@ int vq_backward_workspace_bytes(int64_t T, int K, int D, size_t* out) {
 }
 
 int vq_backward_tokens(const float* g_zq, int layout, int64_t T, int64_t hw, const float* saved_zn,
-                       const float* saved_denom, const int64_t* idx, const void* cb, int K, int D, int form,
+                       const float* saved_denom, const int64_t* idx, const int32_t* hist, const void* cb, int K, int D, int form,
                        float beta, const float* g_loss, int64_t n_elem_total, float* grad_z, int64_t* seg_sums,
                        void* ws, size_t ws_bytes, void* stream) {
     if (int r = check_dims(T, K, D)) return r;
@@ -259,7 +259,7 @@ int vq_backward_tokens(const float* g_zq, int layout, int64_t T, int64_t hw, con
             VQ_CUDA(vq::launch_tok_to_nchw(grad_tok, T, hw, D, grad_z, s));
         }
     }
-    if (seg_sums) VQ_CUDA(vq::launch_segment_sums(saved_zn, idx, cbv, T, seg_sums, seg_ws, seg_bytes, s));
+    if (seg_sums) VQ_CUDA(vq::launch_segment_sums(saved_zn, idx, hist, cbv, T, seg_sums, seg_ws, seg_bytes, s));
     return VQ_OK;
 }
 
@@ -322,7 +322,7 @@ int vq_profile_end(double* search_ms_total, int64_t* search_launches, int64_t* k
 namespace {
 struct HostArena {
     void* cb; float* weight; float* z; float* g; float* zq; float* gz; int64_t* idx; float* zn; float* denom;
-    int64_t* seg; float* gw; float* loss; int64_t* stats; void* fws; size_t fws_bytes; void* bws; size_t bws_bytes;
+    int64_t* seg; float* gw; float* loss; int64_t* stats; int32_t* hist; void* fws; size_t fws_bytes; void* bws; size_t bws_bytes;
     size_t bytes;
 };
 HostArena carve_host(void* arena, int64_t T, int K, int D) {
@@ -342,6 +342,7 @@ HostArena carve_host(void* arena, int64_t T, int K, int D) {
     a.gw = b.take<float>((size_t)K * D);
     a.loss = b.take<float>(64);
     a.stats = b.take<int64_t>(VQ_STATS_LEN);
+    a.hist = b.take<int32_t>((size_t)K);
     a.fws_bytes = carve_forward(nullptr, T, K, D).bytes;
     a.fws = b.take<char>(a.fws_bytes);
     size_t bw = 0;
@@ -375,7 +376,7 @@ int vq_host_step(const float* z_host, const float* g_zq_host, int64_t T, const f
     if (int r = vq_codebook_prepare(a.weight, K, D, a.cb, vq::codebook_bytes(K, D), s)) return r;
     const bool bwd = grad_z_host || grad_weight_host;
     if (int r = vq_forward(a.z, VQ_LAYOUT_TOKEN_MAJOR, T, 0, a.cb, K, D, form, beta, 0, n_elem > 0 ? n_elem : 1, a.zq,
-                           a.idx, a.loss, nullptr, a.stats, bwd ? a.zn : nullptr, bwd ? a.denom : nullptr, a.fws,
+                           a.idx, a.loss, a.hist, a.stats, bwd ? a.zn : nullptr, bwd ? a.denom : nullptr, a.fws,
                            a.fws_bytes, s))
         return r;
     VQ_CUDA(cudaMemcpyAsync(z_q_host, a.zq, row_bytes * T, cudaMemcpyDeviceToHost, s));
@@ -384,7 +385,7 @@ int vq_host_step(const float* z_host, const float* g_zq_host, int64_t T, const f
     if (bwd) {
         if (g_zq_host) VQ_CUDA(cudaMemcpyAsync(a.g, g_zq_host, row_bytes * T, cudaMemcpyHostToDevice, s));
         if (int r = vq_backward_tokens(g_zq_host ? a.g : nullptr, VQ_LAYOUT_TOKEN_MAJOR, T, 0, a.zn, a.denom, a.idx,
-                                       a.cb, K, D, form, beta, nullptr, n_elem > 0 ? n_elem : 1,
+                                       a.hist, a.cb, K, D, form, beta, nullptr, n_elem > 0 ? n_elem : 1,
                                        grad_z_host ? a.gz : nullptr, grad_weight_host ? a.seg : nullptr, a.bws,
                                        a.bws_bytes, s))
             return r;

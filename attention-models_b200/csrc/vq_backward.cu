@@ -138,36 +138,61 @@ __global__ void __launch_bounds__(256) k_count(const int64_t* __restrict__ idx, 
         atomicAdd(counts + __ldg(idx + t), 1);
 }
 
-// single block: exclusive scans of counts and of piece counts
+// single block: exclusive scans of counts and of piece counts (loads first, then warp-shuffle scans)
 __global__ void __launch_bounds__(1024) k_scan_segments(const int* __restrict__ counts, int K, int* __restrict__ offsets,
                                                         int* __restrict__ pieces) {
-    __shared__ int s_tok[1024], s_pc[1024];
-    const int tid = threadIdx.x;
+    constexpr int kMaxPer = 16;                   // K <= 16384 keeps every thread's codes in registers
+    __shared__ int w_tok[32], w_pc[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per = (K + 1023) / 1024;
-    const int lo = tid * per, hi = min(K, lo + per);
+    const int lo = tid * per;
+    int n[kMaxPer];
     int tok = 0, pc = 0;
-    for (int k = lo; k < hi; ++k) {
-        const int n = counts[k];
-        tok += n;
-        pc += (n + kSegPiece - 1) / kSegPiece;
+    if (per <= kMaxPer) {
+#pragma unroll
+        for (int i = 0; i < kMaxPer; ++i) n[i] = (i < per && lo + i < K) ? __ldg(counts + lo + i) : 0;
+#pragma unroll
+        for (int i = 0; i < kMaxPer; ++i) { tok += n[i]; pc += (n[i] + kSegPiece - 1) / kSegPiece; }
+    } else {
+        for (int k = lo; k < min(K, lo + per); ++k) { const int c = counts[k]; tok += c; pc += (c + kSegPiece - 1) / kSegPiece; }
     }
-    s_tok[tid] = tok; s_pc[tid] = pc;
+    int s_tok = tok, s_pc = pc;                   // inclusive scan inside the warp
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int a = __shfl_up_sync(VQ_FULL, s_tok, off), b = __shfl_up_sync(VQ_FULL, s_pc, off);
+        if (lane >= off) { s_tok += a; s_pc += b; }
+    }
+    if (lane == 31) { w_tok[warp] = s_tok; w_pc[warp] = s_pc; }
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        int a = 0, b = 0;
-        if (tid >= off) { a = s_tok[tid - off]; b = s_pc[tid - off]; }
-        __syncthreads();
-        s_tok[tid] += a; s_pc[tid] += b;
-        __syncthreads();
+    if (warp == 0) {
+        int a = w_tok[lane], b = w_pc[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int x = __shfl_up_sync(VQ_FULL, a, off), y = __shfl_up_sync(VQ_FULL, b, off);
+            if (lane >= off) { a += x; b += y; }
+        }
+        w_tok[lane] = a; w_pc[lane] = b;          // inclusive warp totals
     }
-    int run_tok = s_tok[tid] - tok, run_pc = s_pc[tid] - pc;   // exclusive prefix of this thread's range
-    for (int k = lo; k < hi; ++k) {
-        const int n = counts[k];
-        offsets[k] = run_tok; pieces[k] = run_pc;
-        run_tok += n;
-        run_pc += (n + kSegPiece - 1) / kSegPiece;
+    __syncthreads();
+    int run_tok = s_tok - tok + (warp ? w_tok[warp - 1] : 0);
+    int run_pc = s_pc - pc + (warp ? w_pc[warp - 1] : 0);
+    if (per <= kMaxPer) {
+#pragma unroll
+        for (int i = 0; i < kMaxPer; ++i)
+            if (i < per && lo + i < K) {
+                offsets[lo + i] = run_tok; pieces[lo + i] = run_pc;
+                run_tok += n[i];
+                run_pc += (n[i] + kSegPiece - 1) / kSegPiece;
+            }
+    } else {
+        for (int k = lo; k < min(K, lo + per); ++k) {
+            const int c = counts[k];
+            offsets[k] = run_tok; pieces[k] = run_pc;
+            run_tok += c;
+            run_pc += (c + kSegPiece - 1) / kSegPiece;
+        }
     }
-    if (tid == 1023) { offsets[K] = s_tok[1023]; pieces[K] = s_pc[1023]; }
+    if (tid == 1023) { offsets[K] = w_tok[31]; pieces[K] = w_pc[31]; }
 }
 
 __global__ void __launch_bounds__(256) k_scatter(const int64_t* __restrict__ idx, int64_t T,
@@ -218,14 +243,28 @@ __global__ void __launch_bounds__(256) k_segment_reduce(const float4* __restrict
             for (int i = 0; i < 4; ++i) acc[f][i] = 0;
         unsigned bad = 0;
 
-        for (int j0 = p_lo; j0 < p_hi; j0 += kRowsPerWarp) {
-            const int j = j0 + grp;
-            if (j < p_hi) {
-                const int64_t t = __ldg(perm + j);
+        for (int j0 = p_lo; j0 < p_hi; j0 += 2 * kRowsPerWarp) {
+            const int ja = j0 + grp, jb = j0 + kRowsPerWarp + grp;
+            const bool la = ja < p_hi, lb = jb < p_hi;
+            const int64_t ta = la ? __ldg(perm + ja) : 0, tb = lb ? __ldg(perm + jb) : 0;
+            float4 a[kNf4], b[kNf4];
 #pragma unroll
-                for (int f = 0; f < kNf4; ++f) {
-                    const float4 a = __ldg(zn + t * kChunks + sub + kLpr * f);
-                    const float d[4] = {q[f].x - a.x, q[f].y - a.y, q[f].z - a.z, q[f].w - a.w};
+            for (int f = 0; f < kNf4; ++f) {
+                if (la) a[f] = __ldg(zn + ta * kChunks + sub + kLpr * f);
+                if (lb) b[f] = __ldg(zn + tb * kChunks + sub + kLpr * f);
+            }
+#pragma unroll
+            for (int f = 0; f < kNf4; ++f) {
+                if (la) {
+                    const float d[4] = {q[f].x - a[f].x, q[f].y - a[f].y, q[f].z - a[f].z, q[f].w - a[f].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (is_finite(d[i])) acc[f][i] += to_fixed(d[i], VQ_SEG_SHIFT);
+                        else bad = 1;
+                    }
+                }
+                if (lb) {
+                    const float d[4] = {q[f].x - b[f].x, q[f].y - b[f].y, q[f].z - b[f].z, q[f].w - b[f].w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         if (is_finite(d[i])) acc[f][i] += to_fixed(d[i], VQ_SEG_SHIFT);
@@ -254,8 +293,8 @@ __global__ void __launch_bounds__(256) k_segment_reduce(const float4* __restrict
     }
 }
 
-cudaError_t launch_segment_sums(const float* zn32, const int64_t* idx, const CodebookView& cb, int64_t T,
-                                int64_t* seg_sums, void* ws, size_t ws_bytes, cudaStream_t s) {
+cudaError_t launch_segment_sums(const float* zn32, const int64_t* idx, const int32_t* hist, const CodebookView& cb,
+                                int64_t T, int64_t* seg_sums, void* ws, size_t ws_bytes, cudaStream_t s) {
     const int K = cb.K, D = cb.D;
     if (ws_bytes < backward_workspace_bytes(T, K, D)) return cudaErrorInvalidValue;
     BwdWs w = carve(ws, T, K);
@@ -267,8 +306,10 @@ cudaError_t launch_segment_sums(const float* zn32, const int64_t* idx, const Cod
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     count_launch(3);
-    k_count<<<(unsigned)blocks, 256, 0, s>>>(idx, T, w.counts);
-    k_scan_segments<<<1, 1024, 0, s>>>(w.counts, K, w.offsets, w.pieces);
+    // the forward's code-usage histogram is exactly the per-code token count; recount only without it
+    const int* counts = hist ? reinterpret_cast<const int*>(hist) : w.counts;
+    if (!hist) k_count<<<(unsigned)blocks, 256, 0, s>>>(idx, T, w.counts);
+    k_scan_segments<<<1, 1024, 0, s>>>(counts, K, w.offsets, w.pieces);
     k_scatter<<<(unsigned)blocks, 256, 0, s>>>(idx, T, w.offsets, w.cursor, w.perm);
     int64_t max_pieces = T / kSegPiece + (T < K ? T : K) + 1;
     int64_t rblocks = (max_pieces + 7) / 8;

@@ -43,7 +43,11 @@ constexpr int kGroupCols = kTileN * kGroupTiles;
 constexpr int kKBlock = 32;          // halfs per K block: 64-byte rows, SWIZZLE_64B
 constexpr int kABlockBytes = kRowsPerCta * kKBlock * 2;   // 16 KiB
 constexpr int kBStageBytes = kTileN * kKBlock * 2;        // 8 KiB
-constexpr int kThreads = 384;        // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr int kThreads = 512;        // warps 0-3 service (TMA, MMA, TMEM alloc, idle), 4-7 rescoring, 8-15 epilogue
+constexpr int kRescoreThreads = 128;
+// register budget after setmaxnreg (the kernel launches with 128 per thread = the whole register file):
+constexpr int kRegsService = 40, kRegsRescore = 96, kRegsEpilogue = 184;
+static_assert(128 * kRegsService + 128 * kRegsRescore + 256 * kRegsEpilogue <= 65536, "register file overcommitted");
 constexpr float kTwoEps = 2.2e-3f;   // 2 * eps, see header comment
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 // c_format = F32 (bit 4), a/b = F16 (0), K-major both, N = 128 (bits 17..22), M = 128 (bits 24..28)
@@ -73,15 +77,11 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
 // Bounded wait: a broken pipeline traps (launch failure) instead of hanging the GPU.  try_wait itself
 // suspends the thread for a hardware-defined window, so the retry loop is just try_wait + counter:
 // no clock reads, (almost) no issue slots stolen from the epilogue warps sharing the scheduler.
-__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
-    printf("vq_dist_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
-           parity);
-    __trap();
-}
+// (tools: a trapped kernel surfaces as cudaErrorLaunchFailure on the next API call.)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try(bar, parity))
-        if (++spins > (1u << 27)) mbar_timeout(bar, parity);
+        if (++spins > (1u << 27)) __trap();      // no call here: an ABI call would pin the register budget
 }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -153,11 +153,12 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 struct SmemLayout {
     uint32_t a, b, snap, hand, bars, tmem_slot, total;
 };
-constexpr int kHandBytes = kRowsPerCta * 16;     // per row: g1|g2<<12 (or -1), mask1, mask2, pad; double buffered
+constexpr int kHandBytes = kRowsPerCta * 32;     // per row: {g1|g2<<16 or -1, g3, mask1, mask2} {mask3, -, -, -}
 __host__ __device__ constexpr int a_stages(int kb) { return kb <= 2 ? 2 : 1; }
-__host__ __device__ constexpr int b_stages(int kb) { return kb <= 4 ? 8 : 3; }
-// slot-maxima snapshots: 2 areas x 256 rows x 32 floats; rows padded by 16 B (conflict-free STS.128)
-// except at D = 256 where shared memory is tight
+__host__ __device__ constexpr int b_stages(int kb) { return kb == 1 ? 8 : (kb <= 4 ? 4 : 2); }
+// slot-maxima snapshots of the best groups: kAreas x 256 rows x 32 floats; rows padded by 16 B
+// (conflict-free STS.128) except at D = 256 where shared memory is tight (2 areas, unpadded)
+__host__ __device__ constexpr int snap_areas(int kb) { return kb <= 4 ? 3 : 2; }
 __host__ __device__ constexpr int snap_row_bytes(int kb) { return kb <= 4 ? 144 : 128; }
 constexpr int kMaxBStages = 8;
 __host__ __device__ inline SmemLayout smem_layout(int kb) {
@@ -165,7 +166,7 @@ __host__ __device__ inline SmemLayout smem_layout(int kb) {
     L.a = 0;
     L.b = L.a + a_stages(kb) * kb * kABlockBytes;
     L.snap = L.b + b_stages(kb) * kBStageBytes;
-    L.hand = L.snap + 2 * kRowsPerCta * snap_row_bytes(kb);
+    L.hand = L.snap + snap_areas(kb) * kRowsPerCta * snap_row_bytes(kb);
     L.bars = L.hand + 2 * kHandBytes;
     L.tmem_slot = L.bars + 8 * (2 * kMaxBStages + 2 * 2 + 4 + 4);
     L.total = L.tmem_slot + 16;
@@ -179,9 +180,53 @@ __device__ __forceinline__ int cell_code(int g, int slot, int i) {
     return g * kGroupCols + 64 * (i >> 1) + ((slot & 16) << 1) + (slot & 15) + 16 * (i & 1);
 }
 
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// exact fp32 distance of one row to the 8 codes of cell (g, slot): same fma chain as the exhaustive search
+template <int D, bool kRowInRegs>
+__device__ __forceinline__ void rescore_cell(int g, int slot, const float4* __restrict__ z4, const float4 (&z)[kRowInRegs ? D / 4 : 1],
+                                             float a_sq, const float* __restrict__ en32, const float* __restrict__ code_sq,
+                                             float& best_d, int& best_i, float& second_d) {
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+        const int code = cell_code(g, slot, i);
+        const float4* e4 = reinterpret_cast<const float4*>(en32 + (int64_t)code * D);
+        float dot = 0.f;
+        if constexpr (kRowInRegs) {
+            float4 ev[D / 4];
+#pragma unroll
+            for (int q = 0; q < D / 4; ++q) ev[q] = __ldg(e4 + q);
+#pragma unroll
+            for (int q = 0; q < D / 4; ++q) {
+                dot = __fmaf_rn(z[q].x, ev[q].x, dot);
+                dot = __fmaf_rn(z[q].y, ev[q].y, dot);
+                dot = __fmaf_rn(z[q].z, ev[q].z, dot);
+                dot = __fmaf_rn(z[q].w, ev[q].w, dot);
+            }
+        } else {
+#pragma unroll 8
+            for (int q = 0; q < D / 4; ++q) {
+                const float4 ev = __ldg(e4 + q);
+                const float4 zv = __ldg(z4 + q);
+                dot = __fmaf_rn(zv.x, ev.x, dot);
+                dot = __fmaf_rn(zv.y, ev.y, dot);
+                dot = __fmaf_rn(zv.z, ev.z, dot);
+                dot = __fmaf_rn(zv.w, ev.w, dot);
+            }
+        }
+        const float dist = ref_distance(a_sq, __ldg(code_sq + code), dot);
+        if (argmin_better(dist, code, best_d, best_i)) { second_d = best_d; best_d = dist; best_i = code; }
+        else if (dist < second_d) second_d = dist;
+    }
+}
+
 // One CTA per SM, persistent over row tiles.  KB = D / 32.
-// warp 0: TMA producer   warp 1: MMA issuer   warps 2-3: exact fp32 rescoring of the previous row tile
-// (hidden under the ALU-bound main loop)   warps 4-11: epilogue, one thread per row
+// warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM alloc   warps 4-7: exact fp32 rescoring of the
+// previous row tile (one warp per scheduler, hidden under the ALU-bound main loop)
+// warps 8-15: epilogue, one thread per row.  Registers are redistributed with setmaxnreg.
 template <int KB>
 __global__ void __launch_bounds__(kThreads, 1)
 k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int T, int K,
@@ -192,6 +237,7 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     constexpr int D = KB * kKBlock;
     constexpr int AS = a_stages(KB);
     constexpr int BS = b_stages(KB);
+    constexpr int kAreas = snap_areas(KB);
     constexpr int kSnapRow = snap_row_bytes(KB);
     const SmemLayout L = smem_layout(KB);
     // swizzled TMA/UMMA tiles want a 1024-byte aligned base; the launch reserves 1 KiB of slack for this
@@ -219,7 +265,7 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         for (int s = 0; s < BS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), 256); }
         for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(h_full(s), 256); mbar_init(h_empty(s), 64); }
+        for (int s = 0; s < 2; ++s) { mbar_init(h_full(s), 256); mbar_init(h_empty(s), kRescoreThreads); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -233,9 +279,10 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+    if (warp < 4) {
+        reg_dec<kRegsService>();
+        if (warp == 0 && lane == 0) {
+            // ===================== TMA producer =====================
             uint32_t b_cnt = 0;
             int it = 0;
             for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
@@ -256,10 +303,8 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                     }
                 }
             }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        } else if (warp == 1 && lane == 0) {
+            // ===================== MMA issuer (one thread) =====================
             uint32_t b_cnt = 0, t_cnt = 0;
             int it = 0;
             for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
@@ -291,9 +336,11 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                 umma_commit(a_empty(as));            // row tile's A operand no longer needed
             }
         }
-    } else if (warp < 4) {
-        // ===================== rescoring: 64 threads, 4 rows each per row tile =====================
-        const int rtid = threadIdx.x - 64;
+    } else if (warp < 8) {
+        // ===================== rescoring: 128 threads, 2 rows each per row tile =====================
+        reg_dec<kRegsRescore>();
+        constexpr bool kRowInRegs = (D <= 32);
+        const int rtid = threadIdx.x - 128;
         unsigned ties = 0, multi = 0;
         int it = 0;
         for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
@@ -301,16 +348,14 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             mbar_wait(h_full(hb), ((uint32_t)(it >> 1)) & 1u);
             const int4* hand = reinterpret_cast<const int4*>(smem + L.hand + hb * kHandBytes);
 #pragma unroll 1
-            for (int rr = 0; rr < kRowsPerCta / 64; ++rr) {
-                const int r = rtid + 64 * rr;
+            for (int rr = 0; rr < kRowsPerCta / kRescoreThreads; ++rr) {
+                const int r = rtid + kRescoreThreads * rr;
                 const int row = rt * kRowsPerCta + r;
-                const int4 h = hand[r];
-                if (row >= T || h.x < 0) continue;                 // out of range, or left to the exhaustive search
+                const int4 h0 = hand[2 * r], h1 = hand[2 * r + 1];
+                if (row >= T || h0.x < 0) continue;                 // out of range, or left to the exhaustive search
                 if (debug_flags & 1) { cand[row] = kCandExactBit; continue; }   // timing experiment only
-                const int g1 = h.x & 0xFFF, g2 = (h.x >> 12) & 0xFFF;
-                const uint32_t m1 = (uint32_t)h.y, m2 = (uint32_t)h.z;
-                // small rows live in registers; wide rows are re-read chunk-wise (L1 hits after the first code)
-                constexpr bool kRowInRegs = (D <= 64);
+                const int gs[3] = {h0.x & 0xFFFF, (h0.x >> 16) & 0x7FFF, h0.y};
+                const uint32_t ms[3] = {(uint32_t)h0.z, (uint32_t)h0.w, (uint32_t)h1.x};
                 float4 z[kRowInRegs ? D / 4 : 1];
                 const float4* z4 = reinterpret_cast<const float4*>(zn32 + (int64_t)row * D);
                 if (kRowInRegs) {
@@ -318,40 +363,16 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                     for (int q = 0; q < (kRowInRegs ? D / 4 : 1); ++q) z[q] = __ldg(z4 + q);
                 }
                 const float a_sq = __ldg(row_sq + row);
-                const int n1 = __popc(m1), n_cells = n1 + __popc(m2);
                 float best_d = INFINITY, second_d = INFINITY;
-                int best_i = 0x7fffffff;
-                for (int c = 0; c < n_cells; ++c) {
-                    const int slot = (c < n1) ? __fns(m1, 0, c + 1) : __fns(m2, 0, c - n1 + 1);
-                    const int g = (c < n1) ? g1 : g2;
-#pragma unroll 2
-                    for (int i = 0; i < 8; ++i) {
-                        const int code = cell_code(g, slot, i);
-                        const float4* e4 = reinterpret_cast<const float4*>(en32 + (int64_t)code * D);
-                        float dot = 0.f;
-                        if constexpr (kRowInRegs) {
+                int best_i = 0x7fffffff, n_cells = 0;
 #pragma unroll
-                            for (int q = 0; q < D / 4; ++q) {
-                                const float4 ev = __ldg(e4 + q);
-                                dot = __fmaf_rn(z[q].x, ev.x, dot);
-                                dot = __fmaf_rn(z[q].y, ev.y, dot);
-                                dot = __fmaf_rn(z[q].z, ev.z, dot);
-                                dot = __fmaf_rn(z[q].w, ev.w, dot);
-                            }
-                        } else {
-#pragma unroll 8
-                            for (int q = 0; q < D / 4; ++q) {
-                                const float4 ev = __ldg(e4 + q);
-                                const float4 zv = __ldg(z4 + q);
-                                dot = __fmaf_rn(zv.x, ev.x, dot);
-                                dot = __fmaf_rn(zv.y, ev.y, dot);
-                                dot = __fmaf_rn(zv.z, ev.z, dot);
-                                dot = __fmaf_rn(zv.w, ev.w, dot);
-                            }
-                        }
-                        const float dist = ref_distance(a_sq, __ldg(code_sq + code), dot);
-                        if (argmin_better(dist, code, best_d, best_i)) { second_d = best_d; best_d = dist; best_i = code; }
-                        else if (dist < second_d) second_d = dist;
+                for (int a = 0; a < 3; ++a) {
+                    uint32_t m = ms[a];
+                    while (m) {
+                        const int slot = __ffs(m) - 1;
+                        m &= m - 1;
+                        ++n_cells;
+                        rescore_cell<D, kRowInRegs>(gs[a], slot, z4, z, a_sq, en32, code_sq, best_d, best_i, second_d);
                     }
                 }
                 cand[row] = best_i | kCandExactBit;
@@ -370,7 +391,8 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         }
     } else {
         // ===================== epilogue: 8 warps, one thread per row =====================
-        const int e = warp - 4;
+        reg_inc<kRegsEpilogue>();
+        const int e = warp - 8;
         const int r_sub = e >> 2;                    // which 128-row MMA tile
         const int quarter = warp & 3;                // TMEM lane quarter this warp may read
         const int row_in_cta = r_sub * 128 + quarter * 32 + lane;
@@ -380,44 +402,47 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         const bool force_exhaustive = (cb_info[0] != 0);
         uint32_t phase = 0;                          // parity of t_full: flips once per group (2 tiles, 2 stages)
         int it = 0;
+        // a "batch" is 64 accumulator columns = 4 x16 TMEM loads; batch b+1 is in flight while batch b is
+        // folded into the 32 slots (columns 0-31 of the batch -> slots 0-15, columns 32-63 -> slots 16-31)
+        auto load_batch = [&](uint32_t ta, float* v) {
+            tmem_ld16(ta, v);
+            tmem_ld16(ta + 16, v + 16);
+            tmem_ld16(ta + 32, v + 32);
+            tmem_ld16(ta + 48, v + 48);
+        };
         for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
             float slot[32];
-            float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-            int g1 = 0, g2 = 0;
-            uint32_t best_area = 0;                  // which snapshot area holds the best group's slots
-            // software pipeline over "units" (2 x16 loads = 32 columns -> 16 slots): unit u+1 is in flight
-            // while unit u is folded.  8 units per group; tile = unit >> 2.
-            float buf[2][32];
+            float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY, m4 = -INFINITY;
+            int g1 = 0, g2 = 0, g3 = 0;
+            uint32_t a1 = 0, a2 = 1, a3 = (kAreas == 3) ? 2 : 1;   // snapshot areas of the best / second / third group
+            float buf[2][64];
             mbar_wait(t_full(0), phase);
             tc_fence_after();
-            tmem_ld16(tbase, &buf[0][0]);
-            tmem_ld16(tbase + 16, &buf[0][16]);
+            load_batch(tbase, buf[0]);
             for (int g = 0; g < n_groups; ++g) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    tmem_ld_wait();                                   // unit u has landed in buf[u & 1]
-                    if (u == 3) { tc_fence_before(); mbar_arrive(t_empty(0)); }   // tile 0 fully in registers
-                    if (u == 7) { tc_fence_before(); mbar_arrive(t_empty(1)); }
-                    // prefetch the next unit (of this group, or unit 0 of the next group)
-                    if (u < 7) {
-                        if (u == 3) { mbar_wait(t_full(1), phase); tc_fence_after(); }
-                        const uint32_t ta = tbase + (uint32_t)(((u + 1) >> 2) * 2 * kTileN + ((u + 1) & 3) * 32);
-                        tmem_ld16(ta, &buf[(u + 1) & 1][0]);
-                        tmem_ld16(ta + 16, &buf[(u + 1) & 1][16]);
+                for (int b = 0; b < 4; ++b) {
+                    tmem_ld_wait();                                   // batch b has landed in buf[b & 1]
+                    if (b == 1) { tc_fence_before(); mbar_arrive(t_empty(0)); }   // tile 0 fully in registers
+                    if (b == 3) { tc_fence_before(); mbar_arrive(t_empty(1)); }
+                    if (b < 3) {
+                        if (b == 1) { mbar_wait(t_full(1), phase); tc_fence_after(); }
+                        load_batch(tbase + (uint32_t)(((b + 1) >> 1) * 2 * kTileN + ((b + 1) & 1) * 64), buf[(b + 1) & 1]);
                     } else if (g + 1 < n_groups) {
                         mbar_wait(t_full(0), phase ^ 1u);
                         tc_fence_after();
-                        tmem_ld16(tbase, &buf[0][0]);
-                        tmem_ld16(tbase + 16, &buf[0][16]);
+                        load_batch(tbase, buf[0]);
                     }
-                    const float* v = buf[u & 1];
-                    float* sl = slot + 16 * (u & 1);
-                    if (u < 2) {
+                    const float* v = buf[b & 1];
+                    if (b == 0) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) sl[j] = fmaxf(v[j], v[16 + j]);
+                        for (int j = 0; j < 16; ++j) { slot[j] = fmaxf(v[j], v[16 + j]); slot[16 + j] = fmaxf(v[32 + j], v[48 + j]); }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) sl[j] = max3(sl[j], v[j], v[16 + j]);
+                        for (int j = 0; j < 16; ++j) {
+                            slot[j] = max3(slot[j], v[j], v[16 + j]);
+                            slot[16 + j] = max3(slot[16 + j], v[32 + j], v[48 + j]);
+                        }
                     }
                 }
                 phase ^= 1u;
@@ -428,59 +453,71 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                 t[10] = fmaxf(slot[30], slot[31]);
                 const float u0 = max3(t[0], t[1], t[2]), u1 = max3(t[3], t[4], t[5]), u2 = max3(t[6], t[7], t[8]);
                 const float c1 = max3(max3(u0, u1, u2), t[9], t[10]);
-                const bool new_best = c1 > m1, new_second = c1 > m2;
-                if (new_second) {
-                    // the evicted group is always the current second: its area is the one the best does not use
-                    const uint32_t dst = snap0 + (best_area ^ 1u) * kSnapArea;
+                const bool is1 = c1 > m1, is2 = c1 > m2, is3 = (kAreas == 3) ? (c1 > m3) : is2;
+                if (is3) {
+                    // whichever rank the group takes, the group that drops out is the current last one: reuse its area
+                    const uint32_t dst = snap0 + a3 * kSnapArea;
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16 * q), "f"(slot[4 * q]),
                                      "f"(slot[4 * q + 1]), "f"(slot[4 * q + 2]), "f"(slot[4 * q + 3])
                                      : "memory");
                 }
+                // sorted insert of c1 into (m1 >= m2 >= m3 >= m4); identities and areas follow
                 const float lo1 = fminf(c1, m1);
                 m1 = fmaxf(c1, m1);
                 const float lo2 = fminf(lo1, m2);
                 m2 = fmaxf(lo1, m2);
-                m3 = fmaxf(lo2, m3);
-                g2 = new_best ? g1 : (new_second ? g : g2);
-                g1 = new_best ? g : g1;
-                best_area ^= new_best ? 1u : 0u;
+                if (kAreas == 3) {
+                    const float lo3 = fminf(lo2, m3);
+                    m3 = fmaxf(lo2, m3);
+                    m4 = fmaxf(lo3, m4);
+                    const int ng3 = is2 ? g2 : (is3 ? g : g3);
+                    const uint32_t na3 = is2 ? a2 : a3;
+                    const int ng2 = is1 ? g1 : (is2 ? g : g2);
+                    const uint32_t na2 = is1 ? a1 : (is2 ? a3 : a2);
+                    const uint32_t na1 = is1 ? a3 : a1;
+                    g1 = is1 ? g : g1; g2 = ng2; g3 = ng3;
+                    a1 = na1; a2 = na2; a3 = na3;
+                } else {
+                    m3 = fmaxf(lo2, m3);             // with two areas m3 is the bound on everything else
+                    const int ng2 = is1 ? g1 : (is2 ? g : g2);
+                    const uint32_t na1 = is1 ? a2 : a1, na2 = is1 ? a1 : a2;
+                    g1 = is1 ? g : g1; g2 = ng2;
+                    a1 = na1; a2 = na2; a3 = na2;
+                }
             }
             // ---- row verdict ----
             const float thr = m1 - kTwoEps;
             float kept[32];
-            uint32_t mask1 = 0, mask2 = 0;
-            {
-                const uint32_t src = snap0 + best_area * kSnapArea;
+            uint32_t mask[3] = {0u, 0u, 0u};
+            const float mv[3] = {m1, m2, m3};
+            const uint32_t av[3] = {a1, a2, a3};
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(kept[4 * q]), "=f"(kept[4 * q + 1]), "=f"(kept[4 * q + 2]), "=f"(kept[4 * q + 3])
-                                 : "r"(src + 16 * q));
+            for (int a = 0; a < kAreas; ++a) {
+                if (a == 0 || mv[a] >= thr) {
+                    const uint32_t src = snap0 + av[a] * kSnapArea;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mask1 |= (kept[j] >= thr) ? (1u << j) : 0u;
+                    for (int q = 0; q < 8; ++q)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(kept[4 * q]), "=f"(kept[4 * q + 1]), "=f"(kept[4 * q + 2]), "=f"(kept[4 * q + 3])
+                                     : "r"(src + 16 * q));
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mask[a] |= (kept[j] >= thr) ? (1u << j) : 0u;
+                }
             }
-            if (m2 >= thr) {
-                const uint32_t src = snap0 + (best_area ^ 1u) * kSnapArea;
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(kept[4 * q]), "=f"(kept[4 * q + 1]), "=f"(kept[4 * q + 2]), "=f"(kept[4 * q + 3])
-                                 : "r"(src + 16 * q));
-#pragma unroll
-                for (int j = 0; j < 32; ++j) mask2 |= (kept[j] >= thr) ? (1u << j) : 0u;
-            }
-            // decided iff no third group can hold the winner (NaN / -inf rows fail the comparisons)
-            const bool decided = (m3 < thr) && (mask1 != 0) && !force_exhaustive;
+            // decided iff no further group can hold the winner (NaN / -inf rows fail the comparisons)
+            const float bound = (kAreas == 3) ? m4 : m3;
+            const bool decided = (bound < thr) && (mask[0] != 0) && !force_exhaustive;
             const int row = rt * kRowsPerCta + row_in_cta;
             const bool in_range = row < T;
             const bool flag = in_range && !decided;
             // hand the verdict to the rescoring warps (double-buffered)
             const int hb = it & 1;
             mbar_wait(h_empty(hb), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
-            reinterpret_cast<int4*>(smem + L.hand + hb * kHandBytes)[row_in_cta] =
-                make_int4(decided ? (g1 | (g2 << 12)) : -1, (int)mask1, (int)mask2, 0);
+            int4* hand = reinterpret_cast<int4*>(smem + L.hand + hb * kHandBytes);
+            hand[2 * row_in_cta] = make_int4(decided ? (g1 | (g2 << 16)) : -1, g3, (int)mask[0], (int)mask[1]);
+            hand[2 * row_in_cta + 1] = make_int4((int)mask[2], 0, 0, 0);
             mbar_arrive(h_full(hb));
             if (flag) cand[row] = -1;
             const uint32_t ballot = __ballot_sync(VQ_FULL, flag);
@@ -503,6 +540,9 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     }
 }
 
+}  // namespace tc
+
+namespace tc {
 // ---- host side ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -537,8 +577,8 @@ static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, int D, u
 
 bool tc_supported(int64_t T, int K, int D) {
     const bool d_ok = (D == 32 || D == 64 || D == 128 || D == 256);
-    // group ids are packed 12 bits each into cand[]
-    return d_ok && K >= tc::kGroupCols && (K % tc::kGroupCols) == 0 && K / tc::kGroupCols <= 4096 && T >= 256;
+    // group ids travel as 15/16-bit fields
+    return d_ok && K >= tc::kGroupCols && (K % tc::kGroupCols) == 0 && K / tc::kGroupCols <= 32767 && T >= 256;
 }
 
 size_t tc_workspace_bytes(int64_t T, int K, int D) {

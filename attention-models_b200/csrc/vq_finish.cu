@@ -29,33 +29,58 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
     return t;   // valid in thread 0
 }
 
-// chunks = D/4 float4 per row.  Thread e handles row e / chunks, float4 e % chunks.
+// chunks = D/4 float4 per row.  Element e is float4 (e % chunks) of row e / chunks; a thread owns kUnroll
+// elements one grid-stride apart so that their loads are all in flight before the first use.
+template <int kUnroll>
 __global__ void __launch_bounds__(256) k_finish(const float4* __restrict__ zn, const int* __restrict__ cand,
                                                 const float4* __restrict__ en, int64_t T, int chunks, int K,
                                                 float4* __restrict__ zq, int64_t* __restrict__ idx_out,
                                                 int32_t* __restrict__ hist, int64_t* __restrict__ stats) {
     __shared__ unsigned long long red[8];
     const int64_t total = T * chunks;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     long long loss_fx = 0;
     unsigned long long bad = 0;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t t = e / chunks;
-        const int c = (int)(e - t * chunks);
-        const int k = __ldg(cand + t) & (kCandExactBit - 1);
-        if (c == 0) {
-            idx_out[t] = k;
-            if (hist) atomicAdd(hist + k, 1);
+    for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += stride * kUnroll) {
+        int k[kUnroll], c[kUnroll];
+        int64_t t[kUnroll];
+        float4 a[kUnroll], q[kUnroll];
+#pragma unroll
+        for (int i = 0; i < kUnroll; ++i) {
+            const int64_t e = e0 + i * stride;
+            t[i] = e / chunks;
+            c[i] = (int)(e - t[i] * chunks);
+            k[i] = (e < total) ? (__ldg(cand + t[i]) & (kCandExactBit - 1)) : 0;
         }
         if (zq) {
-            const float4 a = __ldg(zn + e);
-            const float4 q = __ldg(en + (int64_t)k * chunks + c);
-            float4 df, o;
-            df.x = __fsub_rn(q.x, a.x); df.y = __fsub_rn(q.y, a.y); df.z = __fsub_rn(q.z, a.z); df.w = __fsub_rn(q.w, a.w);
-            o.x = __fadd_rn(a.x, df.x); o.y = __fadd_rn(a.y, df.y); o.z = __fadd_rn(a.z, df.z); o.w = __fadd_rn(a.w, df.w);
-            __stcs(zq + e, o);
-            const float p = (df.x * df.x + df.y * df.y) + (df.z * df.z + df.w * df.w);
-            if (is_finite(p)) loss_fx += to_fixed(p, VQ_LOSS_SHIFT);
-            else bad += 1;
+#pragma unroll
+            for (int i = 0; i < kUnroll; ++i) {
+                const int64_t e = e0 + i * stride;
+                if (e < total) {
+                    a[i] = __ldcs(zn + e);
+                    q[i] = __ldg(en + (int64_t)k[i] * chunks + c[i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kUnroll; ++i) {
+            const int64_t e = e0 + i * stride;
+            if (e >= total) break;
+            if (c[i] == 0) {
+                idx_out[t[i]] = k[i];
+                if (hist) atomicAdd(hist + k[i], 1);
+            }
+            if (zq) {
+                float4 df, o;
+                df.x = __fsub_rn(q[i].x, a[i].x); df.y = __fsub_rn(q[i].y, a[i].y);
+                df.z = __fsub_rn(q[i].z, a[i].z); df.w = __fsub_rn(q[i].w, a[i].w);
+                o.x = __fadd_rn(a[i].x, df.x); o.y = __fadd_rn(a[i].y, df.y);
+                o.z = __fadd_rn(a[i].z, df.z); o.w = __fadd_rn(a[i].w, df.w);
+                __stcs(zq + e, o);
+                const float p = (df.x * df.x + df.y * df.y) + (df.z * df.z + df.w * df.w);
+                if (is_finite(p)) loss_fx += to_fixed(p, VQ_LOSS_SHIFT);
+                else bad += 1;
+            }
         }
     }
     if (zq && stats) {
@@ -74,10 +99,11 @@ cudaError_t launch_finish(const float* zn32, const int* cand, const CodebookView
     if (T == 0) return cudaSuccess;
     const int chunks = zq_tok ? cb.D / 4 : 1;   // indices-only: one thread per row is enough
     const int64_t total = T * chunks;
-    int64_t blocks = (total + 255) / 256;
-    const int64_t cap = (int64_t)sm_count() * 16;
+    constexpr int kUnroll = 4;
+    int64_t blocks = (total + 256 * kUnroll - 1) / (256 * kUnroll);
+    const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    k_finish<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(zn32), cand,
+    k_finish<kUnroll><<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(zn32), cand,
                                              reinterpret_cast<const float4*>(cb.en32), T, chunks, cb.K,
                                              reinterpret_cast<float4*>(zq_tok), idx_out, hist, stats);
     count_launch();

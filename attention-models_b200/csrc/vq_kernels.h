@@ -69,8 +69,8 @@ size_t backward_workspace_bytes(int64_t T, int K, int D);
 cudaError_t launch_backward_tokens(const float* g_tok, const float* zn32, const float* denom, const int64_t* idx,
                                    const CodebookView& cb, int64_t T, float coef_commit, const float* g_loss,
                                    float* grad_tok, cudaStream_t s);
-cudaError_t launch_segment_sums(const float* zn32, const int64_t* idx, const CodebookView& cb, int64_t T,
-                                int64_t* seg_sums, void* ws, size_t ws_bytes, cudaStream_t s);
+cudaError_t launch_segment_sums(const float* zn32, const int64_t* idx, const int32_t* hist, const CodebookView& cb,
+                                int64_t T, int64_t* seg_sums, void* ws, size_t ws_bytes, cudaStream_t s);
 cudaError_t launch_codebook_grad(const int64_t* seg_sums, const CodebookView& cb, float coef, const float* g_loss,
                                  float* grad_weight, cudaStream_t s);
 

@@ -85,17 +85,90 @@ __global__ void __launch_bounds__(256) k_prep_rows(const float* __restrict__ in,
     }
 }
 
+// D < 128 (ATen's non-vectorised schedule): D/4 lanes share a row, one float4 each, 32/(D/4) rows per
+// warp instruction.  ATen gives element e to lane e % W (W = min(D, 32)), folds the D/W elements of a lane
+// first and then runs the shuffle-down tree with element offsets W/2 ... 1.  With 4 consecutive elements
+// per thread those offsets become: thread offsets (D/4)/2 ... 1 (which include the per-lane fold when
+// D = 64), then the two in-thread steps (x0+x2, x1+x3) and their sum -- bit-identical to ATen.
+template <int D, bool kIsCodebook>
+__global__ void __launch_bounds__(256) k_prep_rows_small(const float4* __restrict__ in, int64_t rows,
+                                                         float4* __restrict__ unit32, float* __restrict__ sq,
+                                                         float* __restrict__ denom, uint2* __restrict__ unit16,
+                                                         int* __restrict__ info) {
+    static_assert(D == 16 || D == 32 || D == 64, "small-row prep covers D < 128");
+    constexpr int kLpr = D / 4;
+    constexpr int kRpw = 32 / kLpr;
+    constexpr int kUnroll = 4;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % kLpr, grp = lane / kLpr;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    auto tree = [&](float4 v) {
+#pragma unroll
+        for (int off = kLpr >> 1; off > 0; off >>= 1) {
+            v.x = __fadd_rn(v.x, __shfl_down_sync(VQ_FULL, v.x, off));
+            v.y = __fadd_rn(v.y, __shfl_down_sync(VQ_FULL, v.y, off));
+            v.z = __fadd_rn(v.z, __shfl_down_sync(VQ_FULL, v.z, off));
+            v.w = __fadd_rn(v.w, __shfl_down_sync(VQ_FULL, v.w, off));
+        }
+        const float total = __fadd_rn(__fadd_rn(v.x, v.z), __fadd_rn(v.y, v.w));
+        return __shfl_sync(VQ_FULL, total, grp * kLpr);
+    };
+    for (int64_t r0 = warp * kRpw * kUnroll; r0 < rows; r0 += n_warps * kRpw * kUnroll) {
+        float4 x[kUnroll];
+#pragma unroll
+        for (int i = 0; i < kUnroll; ++i) {
+            const int64_t r = r0 + i * kRpw + grp;
+            x[i] = (r < rows) ? __ldg(in + r * kLpr + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < kUnroll; ++i) {
+            const int64_t r = r0 + i * kRpw + grp;
+            float4 v = x[i];
+            const float den = norm_denominator(
+                tree(make_float4(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y), __fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w))));
+            v.x = __fdiv_rn(v.x, den); v.y = __fdiv_rn(v.y, den); v.z = __fdiv_rn(v.z, den); v.w = __fdiv_rn(v.w, den);
+            const float s2 =
+                tree(make_float4(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y), __fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w)));
+            if (r < rows) {
+                if (unit32) unit32[r * kLpr + sub] = v;
+                if (unit16) {
+                    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+                    uint2 u;
+                    u.x = *reinterpret_cast<const uint32_t*>(&a);
+                    u.y = *reinterpret_cast<const uint32_t*>(&b);
+                    unit16[r * kLpr + sub] = u;
+                }
+                if (sub == 0) {
+                    if (sq) sq[r] = s2;
+                    if (denom) denom[r] = den;
+                    if (kIsCodebook && !(fabsf(s2 - 1.f) < 1e-4f)) atomicAdd(info, 1);
+                }
+            }
+        }
+    }
+}
+
 template <int D, bool kIsCodebook>
 static cudaError_t prep_rows(const float* in, int64_t rows, float* unit32, float* sq, float* denom, __half* unit16,
                              int* info, cudaStream_t s) {
     if (rows == 0) return cudaSuccess;
-    constexpr int kRows = (RowMap<D>::kPerLane <= 4) ? 4 : 2;
-    const int warps_per_block = 8;
-    int64_t blocks = (rows + (int64_t)warps_per_block * kRows - 1) / (warps_per_block * kRows);
     const int64_t cap = (int64_t)sm_count() * 8;
-    if (blocks > cap) blocks = cap;
-    k_prep_rows<D, kIsCodebook><<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(in, rows, unit32, sq, denom,
-                                                                                    unit16, info);
+    if constexpr (D < 128) {
+        constexpr int rows_per_block = 8 * (32 / (D / 4)) * 4;
+        int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
+        if (blocks > cap) blocks = cap;
+        k_prep_rows_small<D, kIsCodebook><<<(unsigned)blocks, 256, 0, s>>>(
+            reinterpret_cast<const float4*>(in), rows, reinterpret_cast<float4*>(unit32), sq, denom,
+            reinterpret_cast<uint2*>(unit16), info);
+    } else {
+        constexpr int kRows = (RowMap<D>::kPerLane <= 4) ? 4 : 2;
+        const int warps_per_block = 8;
+        int64_t blocks = (rows + (int64_t)warps_per_block * kRows - 1) / (warps_per_block * kRows);
+        if (blocks > cap) blocks = cap;
+        k_prep_rows<D, kIsCodebook><<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(in, rows, unit32, sq, denom,
+                                                                                        unit16, info);
+    }
     count_launch();
     return cudaGetLastError();
 }

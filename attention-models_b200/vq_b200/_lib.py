@@ -36,9 +36,9 @@ SIGNATURES = {
                            c_void_p]),
     "vq_loss_finalize": (c_int, [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]),
     "vq_backward_workspace_bytes": (c_int, [c_int64, c_int, c_int, POINTER(c_size_t)]),
-    "vq_backward_tokens": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                   c_int, c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
-                                   c_void_p]),
+    "vq_backward_tokens": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int, c_int, c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                   c_size_t, c_void_p]),
     "vq_backward_codebook": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_void_p,
                                      c_void_p]),
     "vq_gather": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,

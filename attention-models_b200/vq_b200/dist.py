@@ -143,7 +143,7 @@ class ShardedQuantiser:
                                       _ptr(p["z_q"]), _ptr(p["idx"]), None, _ptr(p["hist"]), _ptr(p["stats"]),
                                       _ptr(p["zn"]), _ptr(p["denom"]), _ptr(p["fws"]), p["fws_bytes"], s))
             _lib.check(lib.vq_backward_tokens(_ptr(up), layout, T, hw, _ptr(p["zn"]), _ptr(p["denom"]), _ptr(p["idx"]),
-                                              cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_z"]), seg,
+                                              _ptr(p["hist"]), cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_z"]), seg,
                                               _ptr(p["bws"]), p["bws_bytes"], s))
             if self.world_size > 1:
                 pack.fill_side_channels(buf, p["hist"], p["stats"])

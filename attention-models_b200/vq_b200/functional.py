@@ -100,7 +100,7 @@ class _Quantise(torch.autograd.Function):
                                       n_total, _ptr(z_q), _ptr(idx), _ptr(loss), _ptr(hist), _ptr(stats),
                                       _ptr(saved_zn), _ptr(saved_denom), _ptr(ws), ws_bytes, _stream(dev)))
         if need_grad:
-            ctx.save_for_backward(saved_zn, saved_denom, idx, prepared.blob)
+            ctx.save_for_backward(saved_zn, saved_denom, idx, prepared.blob, hist)
         ctx.meta = (form, float(beta), layout, T, hw, K, D, n_total, tuple(z.shape))
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(idx, hist, stats)
@@ -110,7 +110,7 @@ class _Quantise(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g_zq, g_idx, g_loss, g_hist, g_stats):
         lib = _lib.load()
-        saved_zn, saved_denom, idx, blob = ctx.saved_tensors
+        saved_zn, saved_denom, idx, blob, hist = ctx.saved_tensors
         form, beta, layout, T, hw, K, D, n_total, z_shape = ctx.meta
         dev = saved_zn.device
         want_z, want_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
@@ -125,7 +125,7 @@ class _Quantise(torch.autograd.Function):
         with torch.cuda.device(dev):
             s = _stream(dev)
             _lib.check(lib.vq_backward_tokens(_ptr(g_zq), layout, T, hw, _ptr(saved_zn), _ptr(saved_denom), _ptr(idx),
-                                              _ptr(blob), K, D, form, beta, _ptr(g_loss), n_total, _ptr(grad_z),
+                                              _ptr(hist), _ptr(blob), K, D, form, beta, _ptr(g_loss), n_total, _ptr(grad_z),
                                               _ptr(seg), _ptr(ws), ws_bytes, s))
             if want_w:
                 _lib.check(lib.vq_backward_codebook(_ptr(seg), _ptr(blob), K, D, form, beta, _ptr(g_loss), n_total,
