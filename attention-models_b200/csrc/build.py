@@ -37,17 +37,21 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, instrument: bool = False) -> str:
+    """instrument=True builds lib/libvq_b200_instr.so with -DVQ_TC_INSTRUMENT (wait-cycle counters in the
+    tensor-core kernel; diagnostic only, selected with VQ_B200_LIB=<path>)."""
     os.makedirs(LIB_DIR, exist_ok=True)
-    stamp = os.path.join(LIB_DIR, "libvq_b200.stamp")
+    global LIB
+    lib_path = LIB.replace(".so", "_instr.so") if instrument else LIB
+    stamp = lib_path.replace(".so", ".stamp")
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
-        return LIB
+    if not force and os.path.exists(lib_path) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        return lib_path
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(HERE, src), "-o", obj]
+        obj = os.path.join(LIB_DIR, src.replace(".cu", "_instr.o" if instrument else ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, *(["-DVQ_TC_INSTRUMENT"] if instrument else []), "-c", os.path.join(HERE, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -60,15 +64,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libvq_b200.so")
-    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-cudart", "static"]
+    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path, *objs, "-cudart", "static"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         print(r.stdout, file=sys.stderr)
         raise RuntimeError("link failed for libvq_b200.so")
     with open(stamp, "w") as fh:
         fh.write(digest)
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, instrument="--instrument" in sys.argv))

@@ -227,13 +227,17 @@ cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const Code
     float4* partial = reinterpret_cast<float4*>(static_cast<char*>(partial_ws) + kTileDoneBytes);
     cudaError_t e = cudaMemsetAsync(tile_done, 0, kTileDoneBytes, s);
     if (e != cudaSuccess) return e;
-    dim3 grid((unsigned)((cap + kTM - 1) / kTM), (unsigned)splits);
+    // few rows are expected: a small grid that strides over the row tiles keeps the empty-list cost at
+    // a couple of microseconds (each block reads the device-side row count and leaves)
+    int tiles = (cap + kTM - 1) / kTM;
+    if (tiles > 16) tiles = 16;
+    dim3 grid((unsigned)tiles, (unsigned)splits);
     k_scan_exact<<<grid, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, 0, cap, cand,
                                       partial, cap, tile_done, stats);
     count_launch();
     if (n > cap) {
         int64_t blocks = (n - cap + kTM - 1) / kTM;
-        if (blocks > cap_blocks) blocks = cap_blocks;
+        if (blocks > sm_count()) blocks = sm_count();
         k_scan_exact<<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, cap,
                                                      n, cand, nullptr, 0, nullptr, stats);
         count_launch();

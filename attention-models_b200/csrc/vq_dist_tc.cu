@@ -83,6 +83,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try(bar, parity))
         if (++spins > (1u << 27)) __trap();      // no call here: an ABI call would pin the register budget
 }
+#ifdef VQ_TC_INSTRUMENT
+__device__ long long g_tc_wait[16];              // [role][what] cycle totals over all CTAs (diagnostic build only)
+#define VQ_TIMED_WAIT(slot, bar, parity)                                        \
+    do {                                                                        \
+        const long long t0__ = clock64();                                       \
+        mbar_wait(bar, parity);                                                 \
+        wait_acc[slot] += clock64() - t0__;                                     \
+    } while (0)
+#else
+#define VQ_TIMED_WAIT(slot, bar, parity) mbar_wait(bar, parity)
+#endif
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
@@ -285,9 +296,13 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             // ===================== TMA producer =====================
             uint32_t b_cnt = 0;
             int it = 0;
+#ifdef VQ_TC_INSTRUMENT
+            long long wait_acc[4] = {0, 0, 0, 0};
+            const long long t_begin = clock64();
+#endif
             for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
                 const int as = it % AS;
-                mbar_wait(a_empty(as), (((uint32_t)(it / AS)) & 1u) ^ 1u);
+                VQ_TIMED_WAIT(0, a_empty(as), (((uint32_t)(it / AS)) & 1u) ^ 1u);
                 mbar_expect_tx(a_full(as), KB * kABlockBytes);
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb)
@@ -297,28 +312,37 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
 #pragma unroll
                     for (int kb = 0; kb < KB; ++kb, ++b_cnt) {
                         const int s = b_cnt % BS;
-                        mbar_wait(b_empty(s), ((b_cnt / BS) & 1u) ^ 1u);
+                        VQ_TIMED_WAIT(1, b_empty(s), ((b_cnt / BS) & 1u) ^ 1u);
                         mbar_expect_tx(b_full(s), kBStageBytes);
                         tma_load_2d(smem_base + L.b + s * kBStageBytes, &tm_b, b_full(s), kb * kKBlock, n * kTileN);
                     }
                 }
             }
+#ifdef VQ_TC_INSTRUMENT
+            atomicAdd((unsigned long long*)&g_tc_wait[0], (unsigned long long)wait_acc[0]);
+            atomicAdd((unsigned long long*)&g_tc_wait[1], (unsigned long long)wait_acc[1]);
+            atomicAdd((unsigned long long*)&g_tc_wait[2], (unsigned long long)(clock64() - t_begin));
+#endif
         } else if (warp == 1 && lane == 0) {
             // ===================== MMA issuer (one thread) =====================
             uint32_t b_cnt = 0, t_cnt = 0;
             int it = 0;
+#ifdef VQ_TC_INSTRUMENT
+            long long wait_acc[4] = {0, 0, 0, 0};
+            const long long t_begin = clock64();
+#endif
             for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
                 const int as = it % AS;
-                mbar_wait(a_full(as), ((uint32_t)(it / AS)) & 1u);
+                VQ_TIMED_WAIT(0, a_full(as), ((uint32_t)(it / AS)) & 1u);
                 tc_fence_after();
                 for (int n = 0; n < n_tiles; ++n, ++t_cnt) {
                     const int acc = t_cnt & 1;
-                    mbar_wait(t_empty(acc), ((t_cnt >> 1) & 1u) ^ 1u);
+                    VQ_TIMED_WAIT(1, t_empty(acc), ((t_cnt >> 1) & 1u) ^ 1u);
                     tc_fence_after();
 #pragma unroll
                     for (int kb = 0; kb < KB; ++kb, ++b_cnt) {
                         const int s = b_cnt % BS;
-                        mbar_wait(b_full(s), (b_cnt / BS) & 1u);
+                        VQ_TIMED_WAIT(2, b_full(s), (b_cnt / BS) & 1u);
                         tc_fence_after();
                         const uint32_t a_addr = smem_base + L.a + (as * KB + kb) * kABlockBytes;
                         const uint32_t b_addr = smem_base + L.b + s * kBStageBytes;
@@ -335,6 +359,12 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                 }
                 umma_commit(a_empty(as));            // row tile's A operand no longer needed
             }
+#ifdef VQ_TC_INSTRUMENT
+            atomicAdd((unsigned long long*)&g_tc_wait[4], (unsigned long long)wait_acc[0]);
+            atomicAdd((unsigned long long*)&g_tc_wait[5], (unsigned long long)wait_acc[1]);
+            atomicAdd((unsigned long long*)&g_tc_wait[6], (unsigned long long)wait_acc[2]);
+            atomicAdd((unsigned long long*)&g_tc_wait[7], (unsigned long long)(clock64() - t_begin));
+#endif
         }
     } else if (warp < 8) {
         // ===================== rescoring: 128 threads, 2 rows each per row tile =====================
@@ -402,6 +432,10 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         const bool force_exhaustive = (cb_info[0] != 0);
         uint32_t phase = 0;                          // parity of t_full: flips once per group (2 tiles, 2 stages)
         int it = 0;
+#ifdef VQ_TC_INSTRUMENT
+        long long wait_acc[4] = {0, 0, 0, 0};
+        const long long t_begin = clock64();
+#endif
         // a "batch" is 64 accumulator columns = 4 x16 TMEM loads; batch b+1 is in flight while batch b is
         // folded into the 32 slots (columns 0-31 of the batch -> slots 0-15, columns 32-63 -> slots 16-31)
         auto load_batch = [&](uint32_t ta, float* v) {
@@ -416,7 +450,7 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             int g1 = 0, g2 = 0, g3 = 0;
             uint32_t a1 = 0, a2 = 1, a3 = (kAreas == 3) ? 2 : 1;   // snapshot areas of the best / second / third group
             float buf[2][64];
-            mbar_wait(t_full(0), phase);
+            VQ_TIMED_WAIT(0, t_full(0), phase);
             tc_fence_after();
             load_batch(tbase, buf[0]);
             for (int g = 0; g < n_groups; ++g) {
@@ -426,10 +460,10 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                     if (b == 1) { tc_fence_before(); mbar_arrive(t_empty(0)); }   // tile 0 fully in registers
                     if (b == 3) { tc_fence_before(); mbar_arrive(t_empty(1)); }
                     if (b < 3) {
-                        if (b == 1) { mbar_wait(t_full(1), phase); tc_fence_after(); }
+                        if (b == 1) { VQ_TIMED_WAIT(0, t_full(1), phase); tc_fence_after(); }
                         load_batch(tbase + (uint32_t)(((b + 1) >> 1) * 2 * kTileN + ((b + 1) & 1) * 64), buf[(b + 1) & 1]);
                     } else if (g + 1 < n_groups) {
-                        mbar_wait(t_full(0), phase ^ 1u);
+                        VQ_TIMED_WAIT(0, t_full(0), phase ^ 1u);
                         tc_fence_after();
                         load_batch(tbase, buf[0]);
                     }
@@ -514,7 +548,7 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             const bool flag = in_range && !decided;
             // hand the verdict to the rescoring warps (double-buffered)
             const int hb = it & 1;
-            mbar_wait(h_empty(hb), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+            VQ_TIMED_WAIT(1, h_empty(hb), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
             int4* hand = reinterpret_cast<int4*>(smem + L.hand + hb * kHandBytes);
             hand[2 * row_in_cta] = make_int4(decided ? (g1 | (g2 << 16)) : -1, g3, (int)mask[0], (int)mask[1]);
             hand[2 * row_in_cta + 1] = make_int4((int)mask[2], 0, 0, 0);
@@ -531,6 +565,13 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                               (unsigned long long)__popc(ballot));
             }
         }
+#ifdef VQ_TC_INSTRUMENT
+        if (threadIdx.x == 256) {   // one epilogue thread per CTA
+            atomicAdd((unsigned long long*)&g_tc_wait[8], (unsigned long long)wait_acc[0]);
+            atomicAdd((unsigned long long*)&g_tc_wait[9], (unsigned long long)wait_acc[1]);
+            atomicAdd((unsigned long long*)&g_tc_wait[10], (unsigned long long)(clock64() - t_begin));
+        }
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -603,6 +644,20 @@ static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb
     tc::k_dist_tc<KB><<<grid, tc::kThreads, L.total + 1024, s>>>(ma, mb, T, cb.K, zn32, row_sq, cb.en32, cb.code_sq, cb.info,
                                                                  cand, flagged, n_flagged, stats, debug_flags);
     count_launch();
+#ifdef VQ_TC_INSTRUMENT
+    {
+        cudaStreamSynchronize(s);
+        long long w[16];
+        cudaMemcpyFromSymbol(w, tc::g_tc_wait, sizeof(w));
+        const double n = grid;
+        printf("[tc instrument] per-CTA mean kcycles  producer: a_empty %.0f b_empty %.0f total %.0f | mma: a_full %.0f t_empty %.0f "
+               "b_full %.0f total %.0f | epilogue: t_full %.0f h_empty %.0f total %.0f\n",
+               w[0] / n / 1e3, w[1] / n / 1e3, w[2] / n / 1e3, w[4] / n / 1e3, w[5] / n / 1e3, w[6] / n / 1e3, w[7] / n / 1e3,
+               w[8] / n / 1e3, w[9] / n / 1e3, w[10] / n / 1e3);
+        long long z[16] = {0};
+        cudaMemcpyToSymbol(tc::g_tc_wait, z, sizeof(z));
+    }
+#endif
     return cudaGetLastError();
 }
 

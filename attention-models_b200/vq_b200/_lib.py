@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_DIR, "lib", "libvq_b200.so")
+LIB_PATH = os.environ.get("VQ_B200_LIB") or os.path.join(_PKG_DIR, "lib", "libvq_b200.so")   # env: diagnostic builds
 BUILD_SCRIPT = os.path.join(_PKG_DIR, "csrc", "build.py")
 
 # constants mirrored from include/vq_b200.h
