@@ -25,6 +25,12 @@ __global__ void k_alu(float* out, long long* cyc, int iters, float seed) {
             if (OP == 3) { asm volatile("lop3.b32 %0, %0, %1, %2, 0xEA;" : "+r"(*(unsigned*)&r[j]) : "r"(0xFFFFFFE0u), "r"(j)); }
             if (OP == 4) { asm volatile("{.reg .pred p; setp.ne.b32 p, %2, 0; selp.f32 %0, %1, %0, p;}" : "+f"(r[j]) : "f"(a), "r"(i & 1)); }
             if (OP == 5) r[j] = fmaf(r[j], a, b);                    // FFMA reference
+            if (OP == 6) { unsigned& u = *(unsigned*)&r[j]; asm volatile("{.reg .b32 t; max.s16x2 t, %0, %1; max.s16x2 %0, t, %2;}" : "+r"(u) : "r"(__float_as_uint(a)), "r"(__float_as_uint(b))); }   // VIMNMX3.S16x2
+            if (OP == 7) { unsigned& u = *(unsigned*)&r[j]; asm volatile("max.s16x2 %0, %0, %1;" : "+r"(u) : "r"(__float_as_uint(a))); }   // VIMNMX.S16x2
+            if (OP == 8) { unsigned& u = *(unsigned*)&r[j]; asm volatile("max.f16x2 %0, %0, %1;" : "+r"(u) : "r"(__float_as_uint(a))); }   // HMNMX2
+            if (OP == 9) { unsigned& u = *(unsigned*)&r[j]; asm volatile("fma.rn.relu.f16x2 %0, %0, %1, %2;" : "+r"(u) : "r"(__float_as_uint(a)), "r"(__float_as_uint(b))); }   // HFMA2.RELU
+            if (OP == 10) { unsigned& u = *(unsigned*)&r[j]; asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(u) : "r"(__float_as_uint(a))); }   // HADD2
+            if (OP == 11) { unsigned& u = *(unsigned*)&r[j]; asm volatile("{.reg .b32 t; max.s32 t, %0, %1; max.s32 %0, t, %2;}" : "+r"(u) : "r"(__float_as_uint(a)), "r"(__float_as_uint(b))); }   // VIMNMX3 (s32)
         }
         a += 1.f; b -= 1.f;
     }
@@ -81,7 +87,7 @@ template <int OP> void run_alu(const char* name, float* out, long long* cyc) {
         cudaDeviceSynchronize();
         long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
         const double instr = (double)iters * 32 * warps;              // warp-instructions per SM
-        printf("%-8s warps/SM=%2d  cycles=%lld  warp-instr/clk/SM=%.3f (lanes/clk/SM=%.1f)\n", name, warps, c,
+        printf("%-14s warps/SM=%2d  cycles=%lld  warp-instr/clk/SM=%.3f (lanes/clk/SM=%.1f)\n", name, warps, c,
                instr / c, instr * 32 / c);
     }
 }
@@ -94,6 +100,12 @@ int main() {
     run_alu<3>("LOP3", out, cyc);
     run_alu<4>("SELP", out, cyc);
     run_alu<5>("FFMA", out, cyc);
+    run_alu<6>("VIMNMX3.S16x2", out, cyc);
+    run_alu<7>("VIMNMX.S16x2", out, cyc);
+    run_alu<8>("HMNMX2", out, cyc);
+    run_alu<9>("HFMA2.RELU", out, cyc);
+    run_alu<10>("HADD2", out, cyc);
+    run_alu<11>("VIMNMX3.S32", out, cyc);
     for (int warps : {4, 8, 16}) {
         const int iters = 2000;
         k_ldtm<<<148, warps * 32>>>(out, cyc, iters);
