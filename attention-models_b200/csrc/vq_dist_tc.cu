@@ -31,6 +31,7 @@
 #include "../../include/vq_b200.h"
 #include "vq_common.cuh"
 #include "vq_kernels.h"
+#include "vq_tc_common.cuh"
 
 namespace vq {
 
@@ -51,115 +52,6 @@ static_assert(128 * kRegsService + 128 * kRegsRescore + 256 * kRegsEpilogue <= 6
 constexpr float kTwoEps = 2.2e-3f;   // 2 * eps, see header comment
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 // c_format = F32 (bit 4), a/b = F16 (0), K-major both, N = 128 (bits 17..22), M = 128 (bits 24..28)
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return done;
-}
-// Bounded wait: a broken pipeline traps (launch failure) instead of hanging the GPU.  try_wait itself
-// suspends the thread for a hardware-defined window, so the retry loop is just try_wait + counter:
-// no clock reads, (almost) no issue slots stolen from the epilogue warps sharing the scheduler.
-// (tools: a trapped kernel surfaces as cudaErrorLaunchFailure on the next API call.)
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try(bar, parity))
-        if (++spins > (1u << 27)) __trap();      // no call here: an ABI call would pin the register budget
-}
-#ifdef VQ_TC_INSTRUMENT
-__device__ long long g_tc_wait[16];              // [role][what] cycle totals over all CTAs (diagnostic build only)
-#define VQ_TIMED_WAIT(slot, bar, parity)                                        \
-    do {                                                                        \
-        const long long t0__ = clock64();                                       \
-        mbar_wait(bar, parity);                                                 \
-        wait_acc[slot] += clock64() - t0__;                                     \
-    } while (0)
-#else
-#define VQ_TIMED_WAIT(slot, bar, parity) mbar_wait(bar, parity)
-#endif
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, SWIZZLE_64B operand tile: rows of 64 B, 8-row atoms 512 B apart (SBO), LBO = 1, version 1.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;                 // leading byte offset (16-byte units)
-    d |= (uint64_t)(512 >> 4) << 32;        // stride byte offset
-    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
-    d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
-    return d;
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                         uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// 32 lanes x 32 columns of fp32: thread i gets columns [col, col + 32) of TMEM lane (lane_base + i)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t* u = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
-          "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
-          "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-        : "r"(taddr));
-}
-// 32 lanes x 16 columns
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t* u = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float max3(float a, float b, float c) {
-    float r;
-    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-    return r;
-}
 
 struct SmemLayout {
     uint32_t a, b, snap, hand, bars, tmem_slot, total;
@@ -190,11 +82,6 @@ __host__ __device__ inline SmemLayout smem_layout(int kb) {
 __device__ __forceinline__ int cell_code(int g, int slot, int i) {
     return g * kGroupCols + 64 * (i >> 1) + ((slot & 16) << 1) + (slot & 15) + 16 * (i & 1);
 }
-
-template <int N>
-__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // exact fp32 distance of one row to the 8 codes of cell (g, slot): same fma chain as the exhaustive search
 template <int D, bool kRowInRegs>
@@ -616,6 +503,12 @@ static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, int D, u
 
 }  // namespace tc
 
+// vq_dist_tc16.cu: D = 32 with fp16 accumulators and packed 16-bit maxima
+bool tc16_supported(int64_t T, int K, int D);
+cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T, const float* zn32, const float* row_sq,
+                             const CodebookView& cb, int* cand, int* flagged, int* n_flagged, int64_t* stats,
+                             cudaStream_t s);
+
 bool tc_supported(int64_t T, int K, int D) {
     const bool d_ok = (D == 32 || D == 64 || D == 128 || D == 256);
     // group ids travel as 15/16-bit fields
@@ -667,6 +560,12 @@ cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* r
     (void)tc_ws;
     if (T == 0) return cudaSuccess;
     CUtensorMap ma, mb;
+    if (tc16_supported(T, cb.K, cb.D)) {
+        // one 256-row box per row tile, one 256-code box per two n-tiles
+        if (!tc::make_map(&ma, zn16, (uint64_t)T, cb.D, 256) || !tc::make_map(&mb, cb.en16, (uint64_t)cb.K, cb.D, 256))
+            return cudaErrorInvalidValue;
+        return launch_dist_tc16(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, s);
+    }
     if (!tc::make_map(&ma, zn16, (uint64_t)T, cb.D, tc::kRowsPerCta) ||
         !tc::make_map(&mb, cb.en16, (uint64_t)cb.K, cb.D, tc::kTileN))
         return cudaErrorInvalidValue;
