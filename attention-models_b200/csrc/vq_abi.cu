@@ -78,7 +78,7 @@ FwdWs carve_forward(void* ws, int64_t T, int K, int D) {
     w.zn16 = b.take<__half>(n * D);
     w.cand = b.take<int>(n);
     w.flagged = b.take<int>(n);
-    w.n_flagged = b.take<int>(64);
+    w.n_flagged = b.take<int>(64 + vq::kFlaggedCap);   // [0]: count, [64..]: done counters of the sliced fallback
     w.stats = b.take<int64_t>(VQ_STATS_LEN);
     w.zq_tok = b.take<float>(n * D);
     const size_t tcb = vq::tc_workspace_bytes(T, K, D);
@@ -192,9 +192,12 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
     // 2. nearest code per row -> cand[]
     SearchTimer timer(s);
     if (use_tc) {
-        VQ_CUDA(cudaMemsetAsync(w.n_flagged, 0, sizeof(int) * 64, s));
+        VQ_CUDA(cudaMemsetAsync(w.n_flagged, 0, sizeof(int) * (64 + vq::kFlaggedCap), s));
         VQ_CUDA(vq::launch_dist_tc(zn16, zn32, w.row_sq, cbv, T, w.cand, w.flagged, w.n_flagged, st, w.tc_ws, s));
-        VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, T, w.cand, st, w.scan_ws, s));
+        if (vq::tc16_supported(T, K, D))
+            VQ_CUDA(vq::launch_scan_flagged16(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, w.n_flagged + 64, w.scan_ws, w.cand, st, s));
+        else
+            VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, T, w.cand, st, w.scan_ws, s));
     } else {
         VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, nullptr, nullptr, T, w.cand, st, nullptr, s));
     }

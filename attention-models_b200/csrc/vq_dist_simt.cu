@@ -245,4 +245,17 @@ cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const Code
     return cudaGetLastError();
 }
 
+// listed rows [row_begin, *n_rows) without the code split (used behind the D = 32 per-row fallback)
+cudaError_t launch_scan_listed_tail(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
+                                    const int* rows, const int* n_rows, int64_t row_begin, int* cand, int64_t* stats,
+                                    cudaStream_t s) {
+    int64_t blocks = (T - row_begin + kTM - 1) / kTM;
+    if (blocks <= 0) return cudaSuccess;
+    if (blocks > sm_count()) blocks = sm_count();
+    k_scan_exact<<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, row_begin, T,
+                                                 cand, nullptr, 0, nullptr, stats);
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace vq

@@ -507,7 +507,8 @@ static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, int D, u
 bool tc16_supported(int64_t T, int K, int D);
 cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T, const float* zn32, const float* row_sq,
                              const CodebookView& cb, int* cand, int* flagged, int* n_flagged, int64_t* stats,
-                             cudaStream_t s);
+                             void* records, cudaStream_t s);
+size_t tc16_workspace_bytes(int64_t T);
 
 bool tc_supported(int64_t T, int K, int D) {
     const bool d_ok = (D == 32 || D == 64 || D == 128 || D == 256);
@@ -516,8 +517,7 @@ bool tc_supported(int64_t T, int K, int D) {
 }
 
 size_t tc_workspace_bytes(int64_t T, int K, int D) {
-    (void)T; (void)K; (void)D;
-    return 0;
+    return tc16_supported(T, K, D) ? tc16_workspace_bytes(T) : 0;
 }
 
 template <int KB>
@@ -557,14 +557,13 @@ static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb
 cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* row_sq, const CodebookView& cb,
                            int64_t T, int* cand, int* flagged, int* n_flagged, int64_t* stats, void* tc_ws,
                            cudaStream_t s) {
-    (void)tc_ws;
     if (T == 0) return cudaSuccess;
     CUtensorMap ma, mb;
     if (tc16_supported(T, cb.K, cb.D)) {
-        // one 256-row box per row tile, one 256-code box per two n-tiles
-        if (!tc::make_map(&ma, zn16, (uint64_t)T, cb.D, 256) || !tc::make_map(&mb, cb.en16, (uint64_t)cb.K, cb.D, 256))
+        // one 256-row box per row tile, one 128-code box per n-tile
+        if (!tc::make_map(&ma, zn16, (uint64_t)T, cb.D, 256) || !tc::make_map(&mb, cb.en16, (uint64_t)cb.K, cb.D, 128))
             return cudaErrorInvalidValue;
-        return launch_dist_tc16(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, s);
+        return launch_dist_tc16(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, s);
     }
     if (!tc::make_map(&ma, zn16, (uint64_t)T, cb.D, tc::kRowsPerCta) ||
         !tc::make_map(&mb, cb.en16, (uint64_t)cb.K, cb.D, tc::kTileN))

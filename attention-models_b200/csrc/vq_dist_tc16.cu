@@ -18,6 +18,15 @@
 // exhaustive search.  eps covers fp16 rounding of both operands plus the two fp16 roundings of the
 // accumulator (one per K = 16 MMA).
 //
+// Two kernels.  k_dist_tc16 is the filter: it writes one 32-byte verdict record per row (the best three groups
+// and, per group, a 64-bit mask of the cells that can still win).  k_rescore16 turns records into indices with
+// the exact fp32 formula.  Rescoring inside the tensor-core kernel was tried first and cost more than it hid: four
+// rescoring warps per SM are instruction-latency bound (~300 dependent instructions per item at IPC 0.2) and
+// their scattered 16-byte loads saturate the L1 wavefront pipe under the epilogue; as its own kernel the same
+// work runs at full occupancy.  Rescoring is warp-cooperative: 8 lanes share one row, each load instruction
+// fetches whole 128-byte code rows (the cell's 8 rows are transposed through shared memory), so the L1 sees one
+// wavefront per code row instead of eight.
+//
 // Shape of the computation: one persistent CTA per SM, 256 token rows per CTA (two M = 128 MMA row tiles),
 // codebook streamed by TMA in 256-code stages (two n-tiles of 128 codes), 2 x 2 accumulator tiles in TMEM.
 // A "group" is 4 n-tiles = 512 codes; a row keeps 64 slot maxima per group (32 packed registers; slot hs
@@ -45,35 +54,36 @@ constexpr int kGroupTiles = 4;
 constexpr int kGroupCols = kTileN * kGroupTiles;    // 512 codes per group
 constexpr int kCellCodes = 8;                       // codes per (group, slot) cell
 constexpr int kABytes = kRowsPerCta * kD * 2;       // 16 KiB: one row tile of fp16 unit rows
-constexpr int kBStageCodes = 2 * kTileN;            // one TMA = two n-tiles
-constexpr int kBStageBytes = kBStageCodes * kD * 2; // 16 KiB
-constexpr int kBStages = 4;
+constexpr int kBStageBytes = kTileN * kD * 2;       // 8 KiB: one n-tile of fp16 unit codes per TMA
+constexpr int kBStages = 6;
 constexpr int kAStages = 2;
-constexpr int kThreads = 512;
-constexpr int kRescoreThreads = 128;
-constexpr int kRegsService = 40, kRegsRescore = 104, kRegsEpilogue = 184;
-static_assert(128 * kRegsService + 128 * kRegsRescore + 256 * kRegsEpilogue <= 65536, "register file overcommitted");
+constexpr int kThreads = 384;          // warps 0-7 epilogue, 8 TMA, 9 + 11 MMA (one per row half), 10 TMEM allocator
+constexpr int kRegsService = 40, kRegsEpilogue = 232;
+static_assert(128 * kRegsService + 256 * kRegsEpilogue <= 65536, "register file overcommitted");
 // |fp16-pipeline score - exact dot| <= eps: 1.1e-3 for the fp16 operands (as in vq_dist_tc.cu) + one fp16 ulp
 // per accumulator rounding (2^-11 below 1, 2^-10 in [1, 2)); the threshold is additionally rounded down to fp16
-constexpr float kTwoEps = 2.f * (1.1e-3f + 4.8829e-4f + 9.7657e-4f);
+constexpr float kTwoEps = 2.f * (1.1e-3f + 4.8829e-4f + 4.8829e-4f);
+constexpr float kTwoEpsNearOne = 2.f * (1.1e-3f + 9.7657e-4f + 9.7657e-4f);
 constexpr float kMinThreshold = 1e-3f;              // the filter only trusts rows whose threshold is safely positive
 // c_format = F16 (0), a/b = F16 (0), K-major both, N = 128, M = 128
 constexpr uint32_t kIdesc = ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 constexpr int kSnapRow = 144;                       // 32 packed slot registers + 16 B pad (conflict-free STS.128)
 constexpr int kSnapArea = kRowsPerCta * kSnapRow;
-constexpr int kHandBytes = kRowsPerCta * 32;        // per row: {g1|g2<<16 or -1, g3, mask0 lo, hi} {mask1 lo, hi, mask2 lo, hi}
+// verdict record, 48 bytes per row: {g1 | g2 << 16 or -1 (undecided), g3 | g4 << 16, mask0 lo, hi}
+// {mask1 lo, hi, mask2 lo, hi} {mask3 lo, hi, -, -}: the best four groups and, per group, the cells that can still win
+constexpr int kRecordBytes = 48;
+constexpr int kAreas = 4;
 
 struct SmemLayout {
-    uint32_t a, b, snap, hand, bars, tmem_slot, total;
+    uint32_t a, b, snap, bars, tmem_slot, total;
 };
 __host__ __device__ inline SmemLayout smem_layout() {
     SmemLayout L;
     L.a = 0;
     L.b = L.a + kAStages * kABytes;
     L.snap = L.b + kBStages * kBStageBytes;
-    L.hand = L.snap + 3 * kSnapArea;
-    L.bars = L.hand + 2 * kHandBytes;
+    L.bars = L.snap + kAreas * kSnapArea;
     L.tmem_slot = L.bars + 8 * 32;
     L.total = L.tmem_slot + 16;
     return L;
@@ -101,36 +111,19 @@ __device__ __forceinline__ void tmem_ld_tile(uint32_t taddr, uint32_t (&v)[64]) 
 __device__ __forceinline__ int lo16(uint32_t p) { return (int)(p << 16) >> 16; }
 __device__ __forceinline__ int hi16(uint32_t p) { return (int)p >> 16; }
 
-// exact fp32 distances of one row to the 8 codes of cell (g, hs).  Per code the dot product is the same
-// sequential fma chain over d = 0..31 as the exhaustive search; the 8 chains are interleaved so that the 8
-// code rows (8 different 128-byte lines) are fetched with one L2 round trip instead of eight.
-__device__ __forceinline__ void rescore_cell(int g, int hs, const float4 (&z)[kD / 4], float a_sq,
-                                             const float* __restrict__ en32, const float* __restrict__ code_sq,
-                                             float& best_d, int& best_i, float& second_d) {
-    const int code0 = g * kGroupCols + hs;
-    const float4* e4 = reinterpret_cast<const float4*>(en32 + (int64_t)code0 * kD);
-    float csq[kCellCodes], dot[kCellCodes];
-#pragma unroll
-    for (int m = 0; m < kCellCodes; ++m) { csq[m] = __ldg(code_sq + code0 + 64 * m); dot[m] = 0.f; }
-#pragma unroll
-    for (int q = 0; q < kD / 4; ++q) {
-        float4 ev[kCellCodes];
-#pragma unroll
-        for (int m = 0; m < kCellCodes; ++m) ev[m] = __ldg(e4 + m * (64 * kD / 4) + q);
-#pragma unroll
-        for (int m = 0; m < kCellCodes; ++m) {
-            dot[m] = __fmaf_rn(z[q].x, ev[m].x, dot[m]);
-            dot[m] = __fmaf_rn(z[q].y, ev[m].y, dot[m]);
-            dot[m] = __fmaf_rn(z[q].z, ev[m].z, dot[m]);
-            dot[m] = __fmaf_rn(z[q].w, ev[m].w, dot[m]);
-        }
-    }
-#pragma unroll
-    for (int m = 0; m < kCellCodes; ++m) {
-        const int code = code0 + 64 * m;
-        const float dist = ref_distance(a_sq, csq[m], dot[m]);
-        if (argmin_better(dist, code, best_d, best_i)) { second_d = best_d; best_d = dist; best_i = code; }
-        else if (dist < second_d) second_d = dist;
+// running (best distance, its index, second-best distance) of one row, torch.argmin ordering
+struct Best3 {
+    float d1; int i1; float d2;
+};
+// fold another lane's triple in (codes are disjoint between lanes): same rules as vq_dist_simt.cu's merge
+__device__ __forceinline__ void best3_merge(Best3& a, float d1, int i1, float d2) {
+    const float nan = __int_as_float(0x7fc00000);
+    if (argmin_better(d1, i1, a.d1, a.i1)) {
+        const float loser = a.d1;
+        a.d1 = d1; a.i1 = i1;
+        a.d2 = (loser != loser || d2 != d2) ? nan : fminf(loser, d2);
+    } else {
+        a.d2 = (d1 != d1 || a.d2 != a.d2) ? nan : fminf(a.d2, d1);
     }
 }
 
@@ -138,9 +131,8 @@ __device__ __forceinline__ void rescore_cell(int g, int hs, const float4 (&z)[kD
 template <bool kServiceHigh>
 __global__ void __launch_bounds__(kThreads, 1)
 k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int T, int K,
-            const float* __restrict__ zn32, const float* __restrict__ row_sq, const float* __restrict__ en32,
-            const float* __restrict__ code_sq, const int* __restrict__ cb_info, int* __restrict__ cand,
-            int* __restrict__ flagged, int* __restrict__ n_flagged, int64_t* __restrict__ stats, int debug_flags) {
+            const int* __restrict__ cb_info, int4* __restrict__ rec, int* __restrict__ cand,
+            int* __restrict__ flagged, int* __restrict__ n_flagged, int64_t* __restrict__ stats) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const SmemLayout L = smem_layout();
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -148,22 +140,19 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_base + L.bars;
     auto b_full = [&](int s) { return bar_base + 8 * s; };
-    auto b_empty = [&](int s) { return bar_base + 8 * (4 + s); };
+    auto b_empty = [&](int s) { return bar_base + 8 * (8 + s); };
     // accumulator stage q = 2 * (n-tile parity) + (row half): 128 rows x 128 codes, i.e. 128 TMEM columns
-    auto t_full = [&](int q) { return bar_base + 8 * (8 + q); };
-    auto t_empty = [&](int q) { return bar_base + 8 * (12 + q); };
-    auto a_full = [&](int s) { return bar_base + 8 * (16 + s); };
-    auto a_empty = [&](int s) { return bar_base + 8 * (18 + s); };
-    auto h_full = [&](int s) { return bar_base + 8 * (20 + s); };
-    auto h_empty = [&](int s) { return bar_base + 8 * (22 + s); };
+    auto t_full = [&](int q) { return bar_base + 8 * (16 + q); };
+    auto t_empty = [&](int q) { return bar_base + 8 * (20 + q); };
+    auto a_full = [&](int s) { return bar_base + 8 * (24 + s); };
+    auto a_empty = [&](int s) { return bar_base + 8 * (26 + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_slot);
 
     // shuffled so the compiler knows the warp index is warp-uniform: role branches and everything the
     // service warps derive from it then live in the uniform datapath (no R2UR / elect loops around tcgen05 ops)
     const int warp = __shfl_sync(VQ_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    constexpr int kEpiWarp0 = kServiceHigh ? 0 : 8;
-    constexpr int kRescoreWarp0 = kServiceHigh ? 8 : 4;
-    constexpr int kTmaWarp = kServiceHigh ? 12 : 0, kMmaWarp = kTmaWarp + 1, kAllocWarp = kTmaWarp + 2;   // second MMA warp: kTmaWarp + 3
+    constexpr int kEpiWarp0 = kServiceHigh ? 0 : 4;
+    constexpr int kTmaWarp = kServiceHigh ? 8 : 0, kMmaWarp = kTmaWarp + 1, kAllocWarp = kTmaWarp + 2;   // second MMA warp: kTmaWarp + 3
     const int n_row_tiles = (T + kRowsPerCta - 1) / kRowsPerCta;
     const int n_tiles = K / kTileN;
     const int n_groups = n_tiles / kGroupTiles;
@@ -172,7 +161,6 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
         for (int s = 0; s < kBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 2); }   // both MMA warps commit
         for (int q = 0; q < 4; ++q) { mbar_init(t_full(q), 1); mbar_init(t_empty(q), 4); }     // one arrive per epilogue warp of the half
         for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 2); }
-        for (int s = 0; s < 2; ++s) { mbar_init(h_full(s), 256); mbar_init(h_empty(s), kRescoreThreads); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kAllocWarp) {
@@ -202,12 +190,12 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                     tma_load_2d(smem_base + L.a + as * kABytes, &tm_a, a_full(as), 0, rt * kRowsPerCta);
                 }
                 __syncwarp();
-                for (int nb = 0; nb < n_tiles / 2; ++nb, ++b_cnt) {
+                for (int n = 0; n < n_tiles; ++n, ++b_cnt) {
                     const int s = b_cnt % kBStages;
                     VQ_TIMED_WAIT(1, b_empty(s), ((b_cnt / kBStages) & 1u) ^ 1u);
                     if (elect_one()) {
                         mbar_expect_tx(b_full(s), kBStageBytes);
-                        tma_load_2d(smem_base + L.b + s * kBStageBytes, &tm_b, b_full(s), 0, nb * kBStageCodes);
+                        tma_load_2d(smem_base + L.b + s * kBStageBytes, &tm_b, b_full(s), 0, n * kTileN);
                     }
                     __syncwarp();
                 }
@@ -227,98 +215,40 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                 VQ_TIMED_WAIT(0, a_full(as), ((uint32_t)(it >> 1)) & 1u);
                 tc_fence_after();
                 const uint32_t a_addr = smem_base + L.a + as * kABytes + r * (128 * 64);
-                for (int nb = 0; nb < n_tiles / 2; ++nb, ++b_cnt) {
-                    const int s = b_cnt % kBStages;
-                    VQ_TIMED_WAIT(2, b_full(s), (b_cnt / kBStages) & 1u);
-                    tc_fence_after();
-                    const uint32_t b_addr = smem_base + L.b + s * kBStageBytes;
+                for (int n = 0; n < n_tiles; n += 2) {
 #pragma unroll
-                    for (int p = 0; p < 2; ++p, ++t_cnt) {      // n-tile p of this B stage -> accumulator stage 2p + r
+                    for (int p = 0; p < 2; ++p, ++t_cnt, ++b_cnt) {      // n-tile n + p -> accumulator stage 2p + r
+                        const int s = b_cnt % kBStages;
+                        VQ_TIMED_WAIT(2, b_full(s), (b_cnt / kBStages) & 1u);
                         VQ_TIMED_WAIT(1, t_empty(2 * p + r), ((t_cnt >> 1) & 1u) ^ 1u);
                         tc_fence_after();
+                        if (r == 0 && lane == 0) VQ_TRACE(0, (int)t_cnt, 0);
+                        const uint32_t b_addr = smem_base + L.b + s * kBStageBytes;
                         VQ_TIMED_BEGIN();
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < 2; ++k)
                                 umma_f16(tmem_base + (uint32_t)((p * 2 + r) * kTileN), umma_desc(a_addr + k * 32),
-                                         umma_desc(b_addr + p * (kTileN * 64) + k * 32), kIdesc, (uint32_t)k);
+                                         umma_desc(b_addr + k * 32), kIdesc, (uint32_t)k);
                             umma_commit(t_full(2 * p + r));
+                            umma_commit(b_empty(s));
                         }
                         __syncwarp();
+                        if (r == 0 && lane == 0) VQ_TRACE(0, (int)t_cnt, 1);
                         VQ_TIMED_END(3);
                     }
-                    if (elect_one()) umma_commit(b_empty(s));
-                    __syncwarp();
                 }
                 if (elect_one()) umma_commit(a_empty(as));
                 __syncwarp();
             }
             if (r == 0) { VQ_INSTR_END(3, 4); }
         }
-    } else if (warp >= kRescoreWarp0 && warp < kRescoreWarp0 + 4) {
-        // ===================== rescoring: 128 threads, 2 rows each per row tile =====================
-        reg_dec<kRegsRescore>();
-        const int rtid = threadIdx.x - kRescoreWarp0 * 32;
-        unsigned ties = 0, multi = 0;
-        int it = 0;
-        for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
-            const int hb = it & 1;
-            mbar_wait(h_full(hb), ((uint32_t)(it >> 1)) & 1u);
-            const int4* hand = reinterpret_cast<const int4*>(smem + L.hand + hb * kHandBytes);
-#pragma unroll 1
-            for (int rr = 0; rr < kRowsPerCta / kRescoreThreads; ++rr) {
-                const int r = rtid + kRescoreThreads * rr;
-                const int row = rt * kRowsPerCta + r;
-                const int4 h0 = hand[2 * r], h1 = hand[2 * r + 1];
-                if (row >= T || h0.x < 0) continue;                 // out of range, or left to the exhaustive search
-                if (debug_flags & 1) { cand[row] = kCandExactBit; continue; }   // timing experiment only
-                const int gs1 = (h0.x >> 16) & 0x7FFF, gs2 = h0.y;
-                const unsigned long long m1 = (unsigned long long)(uint32_t)h1.x | ((unsigned long long)(uint32_t)h1.y << 32);
-                const unsigned long long m2 = (unsigned long long)(uint32_t)h1.z | ((unsigned long long)(uint32_t)h1.w << 32);
-                float4 z[kD / 4];
-                const float4* z4 = reinterpret_cast<const float4*>(zn32 + (int64_t)row * kD);
-#pragma unroll
-                for (int q = 0; q < kD / 4; ++q) z[q] = __ldg(z4 + q);
-                const float a_sq = __ldg(row_sq + row);
-                float best_d = INFINITY, second_d = INFINITY;
-                int best_i = 0x7fffffff, n_cells = 0;
-                // ONE loop over the row's cells, whichever area they come from: lanes of a warp that sit in
-                // different areas / mask halves still share every iteration (a loop per area would serialise them)
-                unsigned long long cur = (unsigned long long)(uint32_t)h0.z | ((unsigned long long)(uint32_t)h0.w << 32);
-                int a = 0, g = h0.x & 0xFFFF;
-                for (;;) {
-                    if (cur == 0ull) {
-                        if (a == 2) break;
-                        ++a;
-                        cur = (a == 1) ? m1 : m2;
-                        g = (a == 1) ? gs1 : gs2;
-                        continue;
-                    }
-                    const int hs = __ffsll((long long)cur) - 1;
-                    cur &= cur - 1;
-                    ++n_cells;
-                    rescore_cell(g, hs, z, a_sq, en32, code_sq, best_d, best_i, second_d);
-                }
-                cand[row] = best_i | kCandExactBit;
-                if (second_d - best_d < VQ_NEAR_TIE_REL * fabsf(best_d)) ++ties;
-                if (n_cells > 1) ++multi;
-            }
-            mbar_arrive(h_empty(hb));
-        }
-        if (stats) {
-            ties = __reduce_add_sync(VQ_FULL, ties);
-            multi = __reduce_add_sync(VQ_FULL, multi);
-            if (lane == 0) {
-                if (ties) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), (unsigned long long)ties);
-                if (multi) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_AMBIGUOUS_ROWS), (unsigned long long)multi);
-            }
-        }
     } else {
         // ===================== epilogue: 8 warps, one thread per row =====================
         reg_inc<kRegsEpilogue>();
         const int e = warp - kEpiWarp0;
         const int r_sub = e >> 2;                    // which 128-row MMA tile
-        const int quarter = warp & 3;                // TMEM lane quarter this warp may read
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may read (warp id mod 4)
         const int row_in_cta = r_sub * 128 + quarter * 32 + lane;
         const uint32_t tbase = *tmem_slot + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(r_sub * kTileN);
         const uint32_t snap0 = smem_base + L.snap + (uint32_t)row_in_cta * kSnapRow;
@@ -329,9 +259,9 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
         VQ_INSTR_BEGIN();
         for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
             uint32_t slot[32];
-            int m1 = -32768, m2 = -32768, m3 = -32768, m4 = -32768;
-            int g1 = 0, g2 = 0, g3 = 0;
-            uint32_t a1 = 0, a2 = 1, a3 = 2;         // snapshot areas of the best / second / third group
+            int m1 = -32768, m2 = -32768, m3 = -32768, m4 = -32768, m5 = -32768;
+            int g1 = 0, g2 = 0, g3 = 0, g4 = 0;
+            uint32_t a1 = 0, a2 = 1, a3 = 2, a4 = 3;  // snapshot areas of the best four groups
             VQ_TIMED_WAIT(0, t_full(r_sub), (t_cnt >> 1) & 1u);
             tc_fence_after();
             tmem_ld_tile(tbase, bufA);
@@ -343,11 +273,16 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                     VQ_TIMED_BEGIN();
                     tmem_ld_wait();                                   // tile b is in registers: its TMEM stage is free
                     VQ_TIMED_END(2);
+#ifdef VQ_TC_INSTRUMENT
+                    if (e == 0 && lane == 0) { asm volatile("" ::"r"(cur[0]), "r"(cur[63])); VQ_TRACE(1, (int)t_cnt, 1); }
+#endif
                     tc_fence_before();
                     if (lane == 0) mbar_arrive(t_empty(2 * (b & 1) + r_sub));
+                    if (e == 0 && lane == 0) VQ_TRACE(1, (int)t_cnt, 2);
                     ++t_cnt;
                     if (b < kGroupTiles - 1 || g + 1 < n_groups) {
                         VQ_TIMED_WAIT(0, t_full(2 * ((b + 1) & 1) + r_sub), (t_cnt >> 1) & 1u);
+                        if (e == 0 && lane == 0) VQ_TRACE(1, (int)t_cnt, 0);
                         tc_fence_after();
                         tmem_ld_tile(tbase + (uint32_t)(((b + 1) & 1) * 2 * kTileN), nxt);
                     }
@@ -358,6 +293,9 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 #pragma unroll
                         for (int j = 0; j < 32; ++j) slot[j] = __vimax3_s16x2(slot[j], cur[j], cur[j + 32]);
                     }
+#ifdef VQ_TC_INSTRUMENT
+                    if (e == 0 && lane == 0) { asm volatile("" ::"r"(slot[0]), "r"(slot[31])); VQ_TRACE(1, (int)t_cnt - 1, 3); }
+#endif
                 }
                 // group maximum: 3-input tree over the 32 packed registers, then the two halves
                 uint32_t t[11];
@@ -368,45 +306,51 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                                u2 = __vimax3_s16x2(t[6], t[7], t[8]);
                 const uint32_t pk = __vimax3_s16x2(__vimax3_s16x2(u0, u1, u2), t[9], t[10]);
                 const int c1 = max(lo16(pk), hi16(pk));
-                const bool is1 = c1 > m1, is2 = c1 > m2, is3 = c1 > m3;
-                if (is3) {
+                const bool is1 = c1 > m1, is2 = c1 > m2, is3 = c1 > m3, is4 = c1 > m4;
+                if (is4) {
                     // whichever rank the group takes, the group that drops out is the current last one: reuse its area
-                    const uint32_t dst = snap0 + a3 * kSnapArea;
+                    const uint32_t dst = snap0 + a4 * kSnapArea;
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16 * q), "r"(slot[4 * q]),
                                      "r"(slot[4 * q + 1]), "r"(slot[4 * q + 2]), "r"(slot[4 * q + 3])
                                      : "memory");
                 }
-                // sorted insert of c1 into (m1 >= m2 >= m3 >= m4); identities and areas follow
+                // sorted insert of c1 into (m1 >= m2 >= m3 >= m4 >= m5); identities and areas follow
                 const int lo1 = min(c1, m1);
                 m1 = max(c1, m1);
                 const int lo2 = min(lo1, m2);
                 m2 = max(lo1, m2);
                 const int lo3 = min(lo2, m3);
                 m3 = max(lo2, m3);
+                const int lo4 = min(lo3, m4);
                 m4 = max(lo3, m4);
+                m5 = max(lo4, m5);
+                const int ng4 = is3 ? g3 : (is4 ? g : g4);
+                const uint32_t na4 = is3 ? a3 : a4;
                 const int ng3 = is2 ? g2 : (is3 ? g : g3);
-                const uint32_t na3 = is2 ? a2 : a3;
+                const uint32_t na3 = is2 ? a2 : (is3 ? a4 : a3);
                 const int ng2 = is1 ? g1 : (is2 ? g : g2);
-                const uint32_t na2 = is1 ? a1 : (is2 ? a3 : a2);
-                const uint32_t na1 = is1 ? a3 : a1;
-                g1 = is1 ? g : g1; g2 = ng2; g3 = ng3;
-                a1 = na1; a2 = na2; a3 = na3;
+                const uint32_t na2 = is1 ? a1 : (is2 ? a4 : a2);
+                const uint32_t na1 = is1 ? a4 : a1;
+                g1 = is1 ? g : g1; g2 = ng2; g3 = ng3; g4 = ng4;
+                a1 = na1; a2 = na2; a3 = na3; a4 = na4;
             }
             // ---- row verdict ----
             // m1 is a non-negative finite fp16 pattern for every row the filter may decide; NaN / Inf patterns,
             // negative best scores and thresholds near zero leave the row to the exhaustive search
             const float m1f = __half2float(__ushort_as_half((unsigned short)(m1 & 0xFFFF)));
-            const float thr_f = m1f - kTwoEps;
+            // a code whose K = 16 partial sum reaches 1 has a final score >= 0.95, so below 0.9 both accumulator
+            // roundings are at most one ulp of [0.5, 1)
+            const float thr_f = m1f - (m1f < 0.9f ? kTwoEps : kTwoEpsNearOne);
             const bool thr_ok = (m1 >= 0) && (m1 < 0x7C00) && (thr_f >= kMinThreshold);
             const int thr = thr_ok ? (int)__half_as_ushort(__float2half_rd(thr_f)) : 0x7BFF;
             const uint32_t thr2 = (uint32_t)thr * 0x10001u;
-            uint32_t mask[6] = {0u, 0u, 0u, 0u, 0u, 0u};
-            const int mv[3] = {m1, m2, m3};
-            const uint32_t av[3] = {a1, a2, a3};
+            uint32_t mask[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            const int mv[4] = {m1, m2, m3, m4};
+            const uint32_t av[4] = {a1, a2, a3, a4};
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
+            for (int a = 0; a < 4; ++a) {
                 if (a == 0 || mv[a] >= thr) {
                     const uint32_t src = snap0 + av[a] * kSnapArea;
                     uint32_t kept[32];
@@ -425,17 +369,17 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                 }
             }
             // decided iff no further group can hold the winner
-            const bool decided = thr_ok && (m4 < thr) && ((mask[0] | mask[1]) != 0) && !force_exhaustive;
+            const int n_cand = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]) + __popc(mask[4]) + __popc(mask[5]) +
+                               __popc(mask[6]) + __popc(mask[7]);
+            const bool decided = thr_ok && (m5 < thr) && ((mask[0] | mask[1]) != 0) && (n_cand <= 16) && !force_exhaustive;
             const int row = rt * kRowsPerCta + row_in_cta;
             const bool in_range = row < T;
             const bool flag = in_range && !decided;
-            // hand the verdict to the rescoring warps (double-buffered)
-            const int hb = it & 1;
-            VQ_TIMED_WAIT(1, h_empty(hb), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
-            int4* hand = reinterpret_cast<int4*>(smem + L.hand + hb * kHandBytes);
-            hand[2 * row_in_cta] = make_int4(decided ? (g1 | (g2 << 16)) : -1, g3, (int)mask[0], (int)mask[1]);
-            hand[2 * row_in_cta + 1] = make_int4((int)mask[2], (int)mask[3], (int)mask[4], (int)mask[5]);
-            mbar_arrive(h_full(hb));
+            if (in_range) {
+                rec[3 * (int64_t)row] = make_int4(decided ? (g1 | (g2 << 16)) : -1, g3 | (g4 << 16), (int)mask[0], (int)mask[1]);
+                rec[3 * (int64_t)row + 1] = make_int4((int)mask[2], (int)mask[3], (int)mask[4], (int)mask[5]);
+                rec[3 * (int64_t)row + 2] = make_int4((int)mask[6], (int)mask[7], 0, 0);
+            }
             if (flag) cand[row] = -1;
             const uint32_t ballot = __ballot_sync(VQ_FULL, flag);
             if (ballot) {
@@ -458,20 +402,222 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Exact fp32 kernels behind the filter.  Both read the cell copies of the codebook (CodebookView::en32c): the 8
+// lanes of a group each own one code of a cell and read whole 128-byte lines together, and every lane runs the
+// same sequential fma chain over d = 0..31 as the exhaustive search of vq_dist_simt.cu, so all paths return
+// identical indices.  (distance, index) pairs are compared as one 64-bit key: sign-corrected float bits, ties to
+// the lower index, NaN below everything (torch.argmin: NaN wins).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long dist_key(float d, int code) {
+    const uint32_t b = __float_as_uint(d);
+    const uint32_t o = (d != d) ? 0u : (b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u));
+    return ((unsigned long long)o << 32) | (uint32_t)code;
+}
+__device__ __forceinline__ float key_dist(unsigned long long key) {
+    const uint32_t o = (uint32_t)(key >> 32);
+    return (o == 0u) ? __int_as_float(0x7fc00000) : __uint_as_float(o ^ ((o >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+struct Top2 {
+    unsigned long long best;   // key of the best (distance, index)
+    float second;              // second-smallest distance (NaN if a NaN lost)
+    __device__ __forceinline__ void init() { best = ~0ull; second = INFINITY; }
+    __device__ __forceinline__ void lose(unsigned long long key) {
+        if (key != ~0ull) {
+            const float d = key_dist(key);
+            second = (d != d || second != second) ? __int_as_float(0x7fc00000) : fminf(second, d);
+        }
+    }
+    __device__ __forceinline__ void add(unsigned long long key) {
+        const bool wins = key < best;
+        const unsigned long long loser = wins ? best : key;
+        best = wins ? key : best;
+        lose(loser);
+    }
+    __device__ __forceinline__ void merge(unsigned long long obest, float osecond) {
+        add(obest);
+        second = (osecond != osecond || second != second) ? __int_as_float(0x7fc00000) : fminf(second, osecond);
+    }
+};
+
+// distances of one row (z in registers) to the 8 codes of cell ci: this lane's code is m
+__device__ __forceinline__ float cell_distance(const float4* __restrict__ en32c, const float* __restrict__ csq_cell, int ci,
+                                               int m, const float4 (&z)[kD / 4], float a_sq) {
+    const float4* e4 = en32c + (int64_t)ci * 64 + m;
+    float4 ev[kD / 4];
+#pragma unroll
+    for (int q = 0; q < kD / 4; ++q) ev[q] = __ldg(e4 + 8 * q);
+    const float csq = __ldg(csq_cell + ci * 8 + m);
+    float dot = 0.f;
+#pragma unroll
+    for (int q = 0; q < kD / 4; ++q) {
+        dot = __fmaf_rn(z[q].x, ev[q].x, dot);
+        dot = __fmaf_rn(z[q].y, ev[q].y, dot);
+        dot = __fmaf_rn(z[q].z, ev[q].z, dot);
+        dot = __fmaf_rn(z[q].w, ev[q].w, dot);
+    }
+    return ref_distance(a_sq, csq, dot);
+}
+
+// Rescoring of the verdict records: cand[row] = argmin over the row's surviving cells.  One 8-lane group per row.
+constexpr int kRescoreThreads = 128;
+__global__ void __launch_bounds__(kRescoreThreads)
+k_rescore16(const int4* __restrict__ rec, const float* __restrict__ zn32, const float* __restrict__ row_sq,
+            const float4* __restrict__ en32c, const float* __restrict__ csq_cell, int T, int* __restrict__ cand,
+            int64_t* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int m = lane & 7;
+    unsigned ties = 0, multi = 0;
+    const int groups = gridDim.x * (kRescoreThreads / 8);
+    for (int row0 = (blockIdx.x * kRescoreThreads + threadIdx.x - lane) >> 3; row0 < T; row0 += groups) {
+        const int row = row0 + (lane >> 3);
+        int4 h0 = make_int4(-1, 0, 0, 0), h1 = make_int4(0, 0, 0, 0), h2 = make_int4(0, 0, 0, 0);
+        if (row < T) { h0 = __ldg(rec + 3 * (int64_t)row); h1 = __ldg(rec + 3 * (int64_t)row + 1); h2 = __ldg(rec + 3 * (int64_t)row + 2); }
+        const bool valid = (row < T) && (h0.x >= 0);
+        auto u64 = [](int lo, int hi) { return (unsigned long long)(uint32_t)lo | ((unsigned long long)(uint32_t)hi << 32); };
+        unsigned long long cur = valid ? u64(h0.z, h0.w) : 0ull;
+        const unsigned long long m1 = valid ? u64(h1.x, h1.y) : 0ull, m2 = valid ? u64(h1.z, h1.w) : 0ull,
+                                 m3 = valid ? u64(h2.x, h2.y) : 0ull;
+        const int gs1 = (h0.x >> 16) & 0x7FFF, gs2 = h0.y & 0xFFFF, gs3 = (h0.y >> 16) & 0x7FFF;
+        int a = 0, g = h0.x & 0xFFFF;
+        const int n_cells = __popcll(cur) + __popcll(m1) + __popcll(m2) + __popcll(m3);
+        const int n_iter = __reduce_max_sync(VQ_FULL, n_cells);
+        float4 z[kD / 4];
+        float a_sq = 0.f;
+        if (valid) {
+            const float4* z4 = reinterpret_cast<const float4*>(zn32 + (int64_t)row * kD);
+#pragma unroll
+            for (int q = 0; q < kD / 4; ++q) z[q] = __ldg(z4 + q);
+            a_sq = __ldg(row_sq + row);
+        }
+        Top2 top;
+        top.init();
+#pragma unroll 1
+        for (int c = 0; c < n_iter; ++c) {
+#pragma unroll
+            for (int skip = 0; skip < 3; ++skip)
+                if (cur == 0ull && a < 3) { ++a; cur = (a == 1) ? m1 : (a == 2 ? m2 : m3); g = (a == 1) ? gs1 : (a == 2 ? gs2 : gs3); }
+            if (cur != 0ull) {
+                const int hs = __ffsll((long long)cur) - 1;
+                cur &= cur - 1;
+                const float dist = cell_distance(en32c, csq_cell, g * 64 + hs, m, z, a_sq);
+                top.add(dist_key(dist, g * kGroupCols + hs + 64 * m));
+            }
+        }
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) {
+            const unsigned long long ob = __shfl_xor_sync(VQ_FULL, top.best, off);
+            const float os = __shfl_xor_sync(VQ_FULL, top.second, off);
+            top.merge(ob, os);
+        }
+        if (valid && m == 0) {
+            const float bd = key_dist(top.best);
+            cand[row] = (int)(uint32_t)top.best | kCandExactBit;
+            if (top.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) ++ties;
+            if (n_cells > 1) ++multi;
+        }
+    }
+    if (stats) {
+        ties = __reduce_add_sync(VQ_FULL, ties);
+        multi = __reduce_add_sync(VQ_FULL, multi);
+        if (lane == 0) {
+            if (ties) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), (unsigned long long)ties);
+            if (multi) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_AMBIGUOUS_ROWS), (unsigned long long)multi);
+        }
+    }
+}
+
+// Exhaustive search of the rows the filter could not decide (a few dozen per 262 144).  Latency matters here, not
+// throughput: every listed row is split over kFlaggedSlices blocks (32 lane groups x 8 codes = 256 codes per
+// step); a slice leaves its (best, second) in `partial` and the last slice of a row to finish folds them.
+// Rows [0, min(*n_rows, cap)) of the list; `done` holds one zeroed counter per listed row.
+constexpr int kFlaggedSlices = 32;
+struct __align__(16) FlaggedPartial {
+    unsigned long long best; float second; float pad;
+};
+__global__ void __launch_bounds__(256)
+k_scan_flagged16(const int* __restrict__ rows, const int* __restrict__ n_rows, int cap, const float* __restrict__ zn32,
+                 const float* __restrict__ row_sq, const float4* __restrict__ en32c, const float* __restrict__ csq_cell,
+                 int K, int* __restrict__ cand, FlaggedPartial* __restrict__ partial, int* __restrict__ done,
+                 int64_t* __restrict__ stats) {
+    __shared__ unsigned long long s_best[8];
+    __shared__ float s_second[8];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = threadIdx.x & 7, grp = threadIdx.x >> 3;
+    int n = *n_rows;
+    if (n > cap) n = cap;
+    const int n_cells = K / kCellCodes;
+    const int per_slice = (n_cells + kFlaggedSlices - 1) / kFlaggedSlices;
+    for (int item = blockIdx.x; item < n * kFlaggedSlices; item += gridDim.x) {
+        const int i = item / kFlaggedSlices, slice = item % kFlaggedSlices;
+        const int row = rows[i];
+        float4 z[kD / 4];
+        const float4* z4 = reinterpret_cast<const float4*>(zn32 + (int64_t)row * kD);
+#pragma unroll
+        for (int q = 0; q < kD / 4; ++q) z[q] = __ldg(z4 + q);
+        const float a_sq = __ldg(row_sq + row);
+        Top2 top;
+        top.init();
+        const int c_end = min(n_cells, (slice + 1) * per_slice);
+#pragma unroll 2
+        for (int ci = slice * per_slice + grp; ci < c_end; ci += 32) {
+            const float dist = cell_distance(en32c, csq_cell, ci, m, z, a_sq);
+            top.add(dist_key(dist, (ci >> 6) * kGroupCols + (ci & 63) + 64 * m));
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long ob = __shfl_xor_sync(VQ_FULL, top.best, off);
+            const float os = __shfl_xor_sync(VQ_FULL, top.second, off);
+            top.merge(ob, os);
+        }
+        __syncthreads();                       // the previous item's shared values are consumed
+        if (lane == 0) { s_best[warp] = top.best; s_second[warp] = top.second; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Top2 all;
+            all.init();
+            for (int w = 0; w < 8; ++w) all.merge(s_best[w], s_second[w]);
+            FlaggedPartial p;
+            p.best = all.best; p.second = all.second; p.pad = 0.f;
+            partial[(int64_t)i * kFlaggedSlices + slice] = p;
+            __threadfence();
+            s_last = (atomicAdd(done + i, 1) == kFlaggedSlices - 1);
+            if (s_last) {
+                __threadfence();
+                Top2 fin;
+                fin.init();
+                for (int w = 0; w < kFlaggedSlices; ++w) {
+                    const FlaggedPartial* q = partial + (int64_t)i * kFlaggedSlices + w;
+                    fin.merge(__ldcg(&q->best), __ldcg(&q->second));
+                }
+                const float bd = key_dist(fin.best);
+                cand[row] = (int)(uint32_t)fin.best | kCandExactBit;
+                if (stats && (fin.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)))
+                    atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), 1ull);
+                done[i] = 0;                   // ready for the next call
+            }
+        }
+    }
+}
+
 }  // namespace tc16
 
 bool tc16_supported(int64_t T, int K, int D) {
     static const bool disabled = getenv("VQ_TC16_DISABLE") && atoi(getenv("VQ_TC16_DISABLE")) != 0;
-    // group ids travel as 15/16-bit fields; the threshold logic needs whole 512-code groups
-    return !disabled && D == tc16::kD && K >= tc16::kGroupCols && (K % tc16::kGroupCols) == 0 &&
-           K / tc16::kGroupCols <= 32767 && T >= 256;
+    // code ids travel as 16-bit fields of the rescoring items; the threshold logic needs whole 512-code groups
+    return !disabled && D == tc16::kD && K >= tc16::kGroupCols && (K % tc16::kGroupCols) == 0 && K <= 65536 && T >= 256;
 }
+
+size_t tc16_workspace_bytes(int64_t T) { return (size_t)(T > 0 ? T : 1) * tc16::kRecordBytes; }
 
 cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T, const float* zn32, const float* row_sq,
                              const CodebookView& cb, int* cand, int* flagged, int* n_flagged, int64_t* stats,
-                             cudaStream_t s) {
+                             void* records, cudaStream_t s) {
     const tc16::SmemLayout L = tc16::smem_layout();
     static const bool service_low = getenv("VQ_TC16_SERVICE_LOW") && atoi(getenv("VQ_TC16_SERVICE_LOW")) != 0;
+    static const int debug_flags = getenv("VQ_TC_DEBUG") ? atoi(getenv("VQ_TC_DEBUG")) : 0;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc16::k_dist_tc16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
@@ -480,18 +626,43 @@ cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T
         if (e != cudaSuccess) return e;
         configured = true;
     }
+    int4* rec = static_cast<int4*>(records);
     const int n_row_tiles = (T + tc16::kRowsPerCta - 1) / tc16::kRowsPerCta;
     const int grid = n_row_tiles < sm_count() ? n_row_tiles : sm_count();
-    static const int debug_flags = getenv("VQ_TC_DEBUG") ? atoi(getenv("VQ_TC_DEBUG")) : 0;
     if (service_low)
-        tc16::k_dist_tc16<false><<<grid, tc16::kThreads, L.total + 1024, s>>>(ma, mb, T, cb.K, zn32, row_sq, cb.en32, cb.code_sq,
-                                                                             cb.info, cand, flagged, n_flagged, stats, debug_flags);
+        tc16::k_dist_tc16<false><<<grid, tc16::kThreads, L.total + 1024, s>>>(ma, mb, T, cb.K, cb.info, rec, cand, flagged,
+                                                                             n_flagged, stats);
     else
-        tc16::k_dist_tc16<true><<<grid, tc16::kThreads, L.total + 1024, s>>>(ma, mb, T, cb.K, zn32, row_sq, cb.en32, cb.code_sq,
-                                                                            cb.info, cand, flagged, n_flagged, stats, debug_flags);
+        tc16::k_dist_tc16<true><<<grid, tc16::kThreads, L.total + 1024, s>>>(ma, mb, T, cb.K, cb.info, rec, cand, flagged,
+                                                                            n_flagged, stats);
     count_launch();
     tc::instrument_report(s, grid);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || (debug_flags & 1)) return e;       // debug bit 0: timing experiment without rescoring
+    const int rows_per_block = tc16::kRescoreThreads / 8;
+    int blocks = (T + rows_per_block - 1) / rows_per_block;
+    const int cap = sm_count() * 16 * 2;                         // resident blocks, two passes
+    if (blocks > cap) blocks = cap;
+    tc16::k_rescore16<<<blocks, tc16::kRescoreThreads, 0, s>>>(rec, zn32, row_sq, reinterpret_cast<const float4*>(cb.en32c),
+                                                               cb.csq_cell, T, cand, stats);
+    count_launch();
     return cudaGetLastError();
+}
+
+// rows the filter left undecided: the first kFlaggedCap of them here (32 blocks per row), the rest (degenerate inputs
+// only) through the throughput-oriented exhaustive kernel of vq_dist_simt.cu.  done_counters: kFlaggedCap zeroed ints;
+// partial_ws: kFlaggedCap * 32 * 16 bytes.
+cudaError_t launch_scan_flagged16(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T, const int* flagged,
+                                  const int* n_flagged, int* done_counters, void* partial_ws, int* cand, int64_t* stats,
+                                  cudaStream_t s) {
+    const int cap = (int)(T < kFlaggedCap ? T : kFlaggedCap);
+    tc16::k_scan_flagged16<<<sm_count() * 4, 256, 0, s>>>(flagged, n_flagged, cap, zn32, row_sq,
+                                                          reinterpret_cast<const float4*>(cb.en32c), cb.csq_cell, cb.K, cand,
+                                                          static_cast<tc16::FlaggedPartial*>(partial_ws), done_counters, stats);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || T <= cap) return e;
+    return launch_scan_listed_tail(zn32, row_sq, cb, T, flagged, n_flagged, cap, cand, stats, s);
 }
 
 }  // namespace vq

@@ -15,6 +15,10 @@ struct CodebookView {
     float* code_denom;  // K    max(||E_k||, eps)
     __half* en16;       // K*D  fp16 copy of en32 (tensor-core operand, TMA source)
     int* info;          // [0] = number of codes whose |en|^2 is not ~1 (zero / non-finite rows)
+    // D = 32, K % 512 == 0 only (else null): "cell" copies for the fp16-accumulator search.  A cell is the 8 codes
+    // g*512 + hs + 64*m (m = 0..7) that share one slot of group g; cell id ci = g*64 + hs.
+    float* en32c;       // K*D  [ci][q][m][4]: 16-byte chunk q of code m -- 8 lanes, one per code, read whole lines
+    float* csq_cell;    // K    [ci][m] = code_sq of that code
     int K, D;
 };
 size_t codebook_bytes(int K, int D);
@@ -46,6 +50,17 @@ cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const Code
                               const int* rows, const int* n_rows, int64_t max_rows, int* cand, int64_t* stats,
                               void* partial_ws, cudaStream_t s);
 
+cudaError_t launch_scan_listed_tail(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
+                                    const int* rows, const int* n_rows, int64_t row_begin, int* cand, int64_t* stats,
+                                    cudaStream_t s);
+
+// ---- vq_dist_tc16.cu (D = 32: fp16 accumulators, packed 16-bit maxima) ------------------------
+bool tc16_supported(int64_t T, int K, int D);
+constexpr int kFlaggedCap = 4096;     // listed rows that get the sliced per-row search (and a done counter each)
+cudaError_t launch_scan_flagged16(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
+                                  const int* flagged, const int* n_flagged, int* done_counters, void* partial_ws,
+                                  int* cand, int64_t* stats, cudaStream_t s);
+
 // ---- vq_dist_tc.cu ---------------------------------------------------------------------------
 // tcgen05 search: cand[row] = cell id (or exact index for rows resolved in-kernel); rows it cannot
 // decide are appended to flagged[] (count in *n_flagged).
@@ -75,6 +90,7 @@ cudaError_t launch_codebook_grad(const int64_t* seg_sums, const CodebookView& cb
                                  float* grad_weight, cudaStream_t s);
 
 // dispatch on the supported codebook dims (powers of two in [16, 512])
+inline bool has_cell_layout(int K, int D) { return D == 32 && K >= 512 && (K % 512) == 0; }
 inline bool dim_supported(int D) { return D >= 16 && D <= 512 && (D & (D - 1)) == 0; }
 
 #define VQ_DISPATCH_D(D, ...)                                       \

@@ -35,6 +35,10 @@ size_t codebook_bytes(int K, int D) {
     n += align_up(sizeof(float) * (size_t)K, 256);        // code_denom
     n += align_up(sizeof(__half) * (size_t)K * D, 256);   // en16
     n += 256;                                             // info
+    if (has_cell_layout(K, D)) {
+        n += align_up(sizeof(float) * (size_t)K * D, 256);   // en32c
+        n += align_up(sizeof(float) * (size_t)K, 256);       // csq_cell
+    }
     return n;
 }
 
@@ -46,7 +50,12 @@ CodebookView codebook_view(void* cb, int K, int D) {
     v.code_sq = reinterpret_cast<float*>(p);     p += align_up(sizeof(float) * (size_t)K, 256);
     v.code_denom = reinterpret_cast<float*>(p);  p += align_up(sizeof(float) * (size_t)K, 256);
     v.en16 = reinterpret_cast<__half*>(p);       p += align_up(sizeof(__half) * (size_t)K * D, 256);
-    v.info = reinterpret_cast<int*>(p);
+    v.info = reinterpret_cast<int*>(p);          p += 256;
+    v.en32c = nullptr; v.csq_cell = nullptr;
+    if (has_cell_layout(K, D)) {
+        v.en32c = reinterpret_cast<float*>(p);   p += align_up(sizeof(float) * (size_t)K * D, 256);
+        v.csq_cell = reinterpret_cast<float*>(p);
+    }
     return v;
 }
 
@@ -173,12 +182,36 @@ static cudaError_t prep_rows(const float* in, int64_t rows, float* unit32, float
     return cudaGetLastError();
 }
 
-cudaError_t launch_prep_codebook(const float* weight, const CodebookView& cb, cudaStream_t s) {
-    cudaError_t e = cudaMemsetAsync(cb.info, 0, 256, s);
-    if (e != cudaSuccess) return e;
+// cell copies of the unit codes (see CodebookView): one thread per 16-byte chunk
+__global__ void __launch_bounds__(256) k_cell_layout32(const float4* __restrict__ en32, const float* __restrict__ code_sq,
+                                                       int K, float4* __restrict__ en32c, float* __restrict__ csq_cell) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= K * 8) return;
+    const int code = idx >> 3, q = idx & 7;
+    const int g = code >> 9, w = code & 511, m = w >> 6, hs = w & 63;
+    const int ci = g * 64 + hs;
+    en32c[(ci * 8 + q) * 8 + m] = en32[idx];
+    if (q == 0) csq_cell[ci * 8 + m] = code_sq[code];
+}
+
+static cudaError_t prep_codebook_rows(const float* weight, const CodebookView& cb, cudaStream_t s) {
     VQ_DISPATCH_D(cb.D, return (prep_rows<kD, true>(weight, cb.K, cb.en32, cb.code_sq, cb.code_denom, cb.en16,
                                                      cb.info, s)));
     return cudaSuccess;
+}
+
+cudaError_t launch_prep_codebook(const float* weight, const CodebookView& cb, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(cb.info, 0, 256, s);
+    if (e != cudaSuccess) return e;
+    e = prep_codebook_rows(weight, cb, s);
+    if (e != cudaSuccess) return e;
+    if (cb.en32c) {
+        k_cell_layout32<<<(cb.K * 8 + 255) / 256, 256, 0, s>>>(reinterpret_cast<const float4*>(cb.en32), cb.code_sq, cb.K,
+                                                              reinterpret_cast<float4*>(cb.en32c), cb.csq_cell);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    return e;
 }
 
 cudaError_t launch_prep_tokens(const float* z, int64_t T, int D, float* zn32, float* row_sq, float* denom,

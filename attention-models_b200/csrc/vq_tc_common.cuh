@@ -25,7 +25,11 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
+#ifdef VQ_MBAR_TEST_WAIT
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(bar), "r"(parity)
@@ -49,6 +53,9 @@ __device__ long long g_tc_wait[16];              // [role][what] cycle totals ov
         mbar_wait(bar, parity);                                                 \
         wait_acc[slot] += clock64() - t0__;                                     \
     } while (0)
+__device__ long long g_tc_trace[2][96][4];          // [role][event #][timestamp kind], CTA 0 only
+#define VQ_TRACE(role, idx, kind) do { if (blockIdx.x == 0 && (idx) < 96) g_tc_trace[role][idx][kind] = clock64(); } while (0)
+#define VQ_COUNT(slot) wait_acc[slot] += 1000
 #define VQ_TIMED_BEGIN() const long long tb__ = clock64()
 #define VQ_TIMED_END(slot) wait_acc[slot] += clock64() - tb__
 // role-local bookkeeping: wait_acc[] + start time, flushed to g_tc_wait[base + i] (i < n) and the total at base + n
@@ -65,6 +72,8 @@ __device__ long long g_tc_wait[16];              // [role][what] cycle totals ov
 #define VQ_TIMED_WAIT(slot, bar, parity) mbar_wait(bar, parity)
 #define VQ_INSTR_BEGIN() do { } while (0)
 #define VQ_INSTR_END(base, n) do { } while (0)
+#define VQ_TRACE(role, idx, kind) do { } while (0)
+#define VQ_COUNT(slot) do { } while (0)
 #define VQ_TIMED_BEGIN() do { } while (0)
 #define VQ_TIMED_END(slot) do { } while (0)
 #endif
@@ -162,8 +171,20 @@ static inline void instrument_report(cudaStream_t s, int grid) {
            "b_full %.0f issue %.0f total %.0f | epilogue: t_full %.0f h_empty %.0f ld_wait %.0f total %.0f\n",
            w[0] / n / 1e3, w[1] / n / 1e3, w[2] / n / 1e3, w[3] / n / 1e3, w[4] / n / 1e3, w[5] / n / 1e3, w[6] / n / 1e3,
            w[7] / n / 1e3, w[8] / n / 1e3, w[9] / n / 1e3, w[10] / n / 1e3, w[11] / n / 1e3);
+    printf("[tc instrument] rescoring warp 0: h_full wait %.0f steps %.0f total %.0f\n", w[12] / n / 1e3, w[13] / n / 1e3,
+           w[14] / n / 1e3);
     long long z[16] = {0};
     cudaMemcpyToSymbol(g_tc_wait, z, sizeof(z));
+    static int traced = 0;
+    if (traced++ == 3) {
+        static long long tr[2][96][4];
+        cudaMemcpyFromSymbol(tr, g_tc_trace, sizeof(tr));
+        const long long t0 = tr[0][8][0];
+        printf("[tc trace] tile: mma(t_empty ok, committed) | epi(t_full ok, data in regs, arrived, processed)  [cycles rel.]\n");
+        for (int i = 8; i < 40; ++i)
+            printf("[tc trace] %2d: %6lld %6lld | %6lld %6lld %6lld %6lld\n", i, tr[0][i][0] - t0, tr[0][i][1] - t0, tr[1][i][0] - t0,
+                   tr[1][i][1] - t0, tr[1][i][2] - t0, tr[1][i][3] - t0);
+    }
 #else
     (void)s; (void)grid;
 #endif
