@@ -174,8 +174,10 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
     float* zn32 = saved_zn ? saved_zn : w.zn32;
     float* denom = saved_denom ? saved_denom : w.denom;
     int64_t* st = stats ? stats : w.stats;
-    VQ_CUDA(cudaMemsetAsync(st, 0, sizeof(int64_t) * VQ_STATS_LEN, s));
-    if (hist) VQ_CUDA(cudaMemsetAsync(hist, 0, sizeof(int32_t) * (size_t)K, s));
+    if (!(flags & VQ_FLAG_KEEP_STATS)) {
+        VQ_CUDA(cudaMemsetAsync(st, 0, sizeof(int64_t) * VQ_STATS_LEN, s));
+        if (hist) VQ_CUDA(cudaMemsetAsync(hist, 0, sizeof(int32_t) * (size_t)K, s));
+    }
 
     const bool use_tc = !(flags & VQ_FLAG_EXACT_SCAN) && vq::tc_supported(T, K, D);
     __half* zn16 = use_tc ? w.zn16 : nullptr;
@@ -364,6 +366,34 @@ int vq_host_step_arena_bytes(int64_t T, int K, int D, size_t* out) {
     return VQ_OK;
 }
 
+namespace {
+// copy streams and events of the chunked host step (created once per process, on first use)
+constexpr int kMaxChunks = 64;
+constexpr int64_t kChunkTokens = 32768;
+struct HostPipe {
+    cudaStream_t in = nullptr, out = nullptr;
+    cudaEvent_t start = nullptr, weight = nullptr, tail = nullptr, finished = nullptr;
+    cudaEvent_t loaded[kMaxChunks], done[kMaxChunks];
+    bool ready = false;
+};
+HostPipe g_pipe;
+cudaError_t pipe_init() {
+    if (g_pipe.ready) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&g_pipe.in, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&g_pipe.out, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    cudaEvent_t* singles[4] = {&g_pipe.start, &g_pipe.weight, &g_pipe.tail, &g_pipe.finished};
+    for (auto ev : singles)
+        if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    for (int i = 0; i < kMaxChunks; ++i) {
+        if ((e = cudaEventCreateWithFlags(&g_pipe.loaded[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&g_pipe.done[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    g_pipe.ready = true;
+    return cudaSuccess;
+}
+}  // namespace
+
 int vq_host_step(const float* z_host, const float* g_zq_host, int64_t T, const float* weight_host, int K, int D,
                  int form, float beta, float* z_q_host, int64_t* idx_host, float* loss_host, float* grad_z_host,
                  float* grad_weight_host, int64_t* stats_host, void* dev_arena, size_t arena_bytes, void* stream) {
@@ -372,33 +402,72 @@ int vq_host_step(const float* z_host, const float* g_zq_host, int64_t T, const f
     HostArena a = carve_host(dev_arena, T, K, D);
     if (arena_bytes < a.bytes) return fail(VQ_ERR_WORKSPACE, "arena too small: %zu < %zu", arena_bytes, a.bytes);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    VQ_CUDA(pipe_init());
+    HostPipe& p = g_pipe;
     const size_t row_bytes = sizeof(float) * (size_t)D;
-    const int64_t n_elem = T * D;
-    VQ_CUDA(cudaMemcpyAsync(a.weight, weight_host, row_bytes * K, cudaMemcpyHostToDevice, s));
-    VQ_CUDA(cudaMemcpyAsync(a.z, z_host, row_bytes * T, cudaMemcpyHostToDevice, s));
-    if (int r = vq_codebook_prepare(a.weight, K, D, a.cb, vq::codebook_bytes(K, D), s)) return r;
+    const int64_t n_elem = T * D > 0 ? T * D : 1;
     const bool bwd = grad_z_host || grad_weight_host;
-    if (int r = vq_forward(a.z, VQ_LAYOUT_TOKEN_MAJOR, T, 0, a.cb, K, D, form, beta, 0, n_elem > 0 ? n_elem : 1, a.zq,
-                           a.idx, a.loss, a.hist, a.stats, bwd ? a.zn : nullptr, bwd ? a.denom : nullptr, a.fws,
-                           a.fws_bytes, s))
-        return r;
-    VQ_CUDA(cudaMemcpyAsync(z_q_host, a.zq, row_bytes * T, cudaMemcpyDeviceToHost, s));
-    VQ_CUDA(cudaMemcpyAsync(idx_host, a.idx, sizeof(int64_t) * T, cudaMemcpyDeviceToHost, s));
-    if (loss_host) VQ_CUDA(cudaMemcpyAsync(loss_host, a.loss, sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (bwd) {
-        if (g_zq_host) VQ_CUDA(cudaMemcpyAsync(a.g, g_zq_host, row_bytes * T, cudaMemcpyHostToDevice, s));
-        if (int r = vq_backward_tokens(g_zq_host ? a.g : nullptr, VQ_LAYOUT_TOKEN_MAJOR, T, 0, a.zn, a.denom, a.idx,
-                                       a.hist, a.cb, K, D, form, beta, nullptr, n_elem > 0 ? n_elem : 1,
-                                       grad_z_host ? a.gz : nullptr, grad_weight_host ? a.seg : nullptr, a.bws,
-                                       a.bws_bytes, s))
-            return r;
-        if (grad_z_host) VQ_CUDA(cudaMemcpyAsync(grad_z_host, a.gz, row_bytes * T, cudaMemcpyDeviceToHost, s));
-        if (grad_weight_host) {
-            if (int r = vq_backward_codebook(a.seg, a.cb, K, D, form, beta, nullptr, n_elem > 0 ? n_elem : 1, a.gw, s)) return r;
-            VQ_CUDA(cudaMemcpyAsync(grad_weight_host, a.gw, row_bytes * K, cudaMemcpyDeviceToHost, s));
-        }
+    // token chunks (multiples of 256 rows so that every chunk keeps the tensor-core path)
+    int64_t chunk = T;
+    if (T > 2 * kChunkTokens) {
+        chunk = kChunkTokens;
+        const int64_t need = (T + kMaxChunks - 1) / kMaxChunks;
+        if (chunk < need) chunk = (need + 255) / 256 * 256;
     }
-    if (stats_host) VQ_CUDA(cudaMemcpyAsync(stats_host, a.stats, sizeof(int64_t) * VQ_STATS_LEN, cudaMemcpyDeviceToHost, s));
+    const int n_chunks = T > 0 ? (int)((T + chunk - 1) / chunk) : 0;
+
+    // ---- host -> device on the `in` stream, ordered after whatever `stream` was doing ----
+    VQ_CUDA(cudaEventRecord(p.start, s));
+    VQ_CUDA(cudaStreamWaitEvent(p.in, p.start, 0));
+    VQ_CUDA(cudaStreamWaitEvent(p.out, p.start, 0));
+    VQ_CUDA(cudaMemcpyAsync(a.weight, weight_host, row_bytes * K, cudaMemcpyHostToDevice, p.in));
+    VQ_CUDA(cudaEventRecord(p.weight, p.in));
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t t0 = c * chunk, n = (T - t0 < chunk) ? T - t0 : chunk;
+        VQ_CUDA(cudaMemcpyAsync(a.z + t0 * D, z_host + t0 * D, row_bytes * n, cudaMemcpyHostToDevice, p.in));
+        if (bwd && g_zq_host)
+            VQ_CUDA(cudaMemcpyAsync(a.g + t0 * D, g_zq_host + t0 * D, row_bytes * n, cudaMemcpyHostToDevice, p.in));
+        VQ_CUDA(cudaEventRecord(p.loaded[c], p.in));
+    }
+    // ---- kernels on `stream`, device -> host on the `out` stream ----
+    VQ_CUDA(cudaStreamWaitEvent(s, p.weight, 0));
+    if (int r = vq_codebook_prepare(a.weight, K, D, a.cb, vq::codebook_bytes(K, D), s)) return r;
+    VQ_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(int64_t) * VQ_STATS_LEN, s));
+    VQ_CUDA(cudaMemsetAsync(a.hist, 0, sizeof(int32_t) * (size_t)K, s));
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t t0 = c * chunk, n = (T - t0 < chunk) ? T - t0 : chunk;
+        VQ_CUDA(cudaStreamWaitEvent(s, p.loaded[c], 0));
+        if (int r = vq_forward(a.z + t0 * D, VQ_LAYOUT_TOKEN_MAJOR, n, 0, a.cb, K, D, form, beta, VQ_FLAG_KEEP_STATS, n_elem,
+                               a.zq + t0 * D, a.idx + t0, nullptr, a.hist, a.stats, bwd ? a.zn + t0 * D : nullptr,
+                               bwd ? a.denom + t0 : nullptr, a.fws, a.fws_bytes, s))
+            return r;
+        if (grad_z_host)
+            if (int r = vq_backward_tokens(g_zq_host ? a.g + t0 * D : nullptr, VQ_LAYOUT_TOKEN_MAJOR, n, 0, a.zn + t0 * D,
+                                           a.denom + t0, a.idx + t0, nullptr, a.cb, K, D, form, beta, nullptr, n_elem,
+                                           a.gz + t0 * D, nullptr, a.bws, a.bws_bytes, s))
+                return r;
+        VQ_CUDA(cudaEventRecord(p.done[c], s));
+        VQ_CUDA(cudaStreamWaitEvent(p.out, p.done[c], 0));
+        VQ_CUDA(cudaMemcpyAsync(z_q_host + t0 * D, a.zq + t0 * D, row_bytes * n, cudaMemcpyDeviceToHost, p.out));
+        VQ_CUDA(cudaMemcpyAsync(idx_host + t0, a.idx + t0, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, p.out));
+        if (grad_z_host)
+            VQ_CUDA(cudaMemcpyAsync(grad_z_host + t0 * D, a.gz + t0 * D, row_bytes * n, cudaMemcpyDeviceToHost, p.out));
+    }
+    // ---- whole-batch tail: loss from the accumulated fixed-point sum, codebook gradient over all tokens ----
+    if (loss_host) VQ_CUDA(vq::launch_loss_finalize(a.stats, n_elem, form, beta, a.loss, s));
+    if (grad_weight_host) {
+        if (int r = vq_backward_tokens(nullptr, VQ_LAYOUT_TOKEN_MAJOR, T, 0, a.zn, a.denom, a.idx, a.hist, a.cb, K, D, form,
+                                       beta, nullptr, n_elem, nullptr, a.seg, a.bws, a.bws_bytes, s))
+            return r;
+        if (int r = vq_backward_codebook(a.seg, a.cb, K, D, form, beta, nullptr, n_elem, a.gw, s)) return r;
+    }
+    VQ_CUDA(cudaEventRecord(p.tail, s));
+    VQ_CUDA(cudaStreamWaitEvent(p.out, p.tail, 0));
+    if (loss_host) VQ_CUDA(cudaMemcpyAsync(loss_host, a.loss, sizeof(float), cudaMemcpyDeviceToHost, p.out));
+    if (grad_weight_host) VQ_CUDA(cudaMemcpyAsync(grad_weight_host, a.gw, row_bytes * K, cudaMemcpyDeviceToHost, p.out));
+    if (stats_host) VQ_CUDA(cudaMemcpyAsync(stats_host, a.stats, sizeof(int64_t) * VQ_STATS_LEN, cudaMemcpyDeviceToHost, p.out));
+    VQ_CUDA(cudaEventRecord(p.finished, p.out));
+    VQ_CUDA(cudaStreamWaitEvent(s, p.finished, 0));
     return VQ_OK;
 }
 

@@ -17,7 +17,7 @@ BUILD_SCRIPT = os.path.join(_PKG_DIR, "csrc", "build.py")
 ABI_VERSION = 1
 FORM_VIT, FORM_VQGAN = 0, 1
 LAYOUT_TOKEN_MAJOR, LAYOUT_NCHW = 0, 1
-FLAG_INDICES_ONLY, FLAG_EXACT_SCAN = 1, 2
+FLAG_INDICES_ONLY, FLAG_EXACT_SCAN, FLAG_KEEP_STATS = 1, 2, 4
 STAT_NEAR_TIE_ROWS, STAT_AMBIGUOUS_ROWS, STAT_FALLBACK_ROWS, STAT_LOSS_FIXED, STAT_BAD_INDEX, STAT_NONFINITE = range(6)
 STATS_LEN = 8
 SEG_SHIFT = 30

@@ -47,6 +47,8 @@ extern "C" {
 /* flags for vq_forward */
 #define VQ_FLAG_INDICES_ONLY 1    /* encode_imgs fast path: only idx (and hist) are produced   */
 #define VQ_FLAG_EXACT_SCAN   2    /* force the exhaustive fp32 SIMT search (no tensor cores)   */
+#define VQ_FLAG_KEEP_STATS   4    /* hist and stats accumulate (the caller zeroed them once): one
+                                     batch can be streamed through in token chunks               */
 
 /* error codes */
 #define VQ_OK            0
@@ -148,8 +150,11 @@ VQ_API int vq_profile_end(double* search_ms_total, int64_t* search_launches, int
 
 /* ---- host-buffer entry points (end-to-end path: host pointers in, host pointers out) --------
  * Same semantics as vq_forward + vq_backward_tokens + vq_backward_codebook for token-major fp32
- * data living in (preferably pinned) HOST memory; copies are chunked and overlapped with the
- * kernels on internal streams.  `dev_arena` is device scratch of vq_host_step_arena_bytes().     */
+ * data living in (preferably pinned) HOST memory.  Batches of more than 64 Ki tokens are streamed in
+ * token chunks: host->device copies, kernels and device->host copies of different chunks overlap on
+ * two internal copy streams (full-duplex PCIe), results are identical to the unchunked call (integer
+ * partial sums).  Everything is ordered after prior work on `stream`, and `stream` waits for the last
+ * copy.  `dev_arena` is device scratch of vq_host_step_arena_bytes().                              */
 VQ_API int vq_host_step_arena_bytes(int64_t T, int K, int D, size_t* out);
 VQ_API int vq_host_step(const float* z_host, const float* g_zq_host, int64_t T,
                  const float* weight_host, int K, int D, int form, float beta,

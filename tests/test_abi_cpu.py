@@ -46,6 +46,7 @@ def test_abi_version_and_constants_match_header(lib):
     assert (lib.FORM_VIT, lib.FORM_VQGAN) == (int(consts["VQ_FORM_VIT"]), int(consts["VQ_FORM_VQGAN"]))
     assert (lib.LAYOUT_TOKEN_MAJOR, lib.LAYOUT_NCHW) == (int(consts["VQ_LAYOUT_TOKEN_MAJOR"]), int(consts["VQ_LAYOUT_NCHW"]))
     assert (lib.FLAG_INDICES_ONLY, lib.FLAG_EXACT_SCAN) == (int(consts["VQ_FLAG_INDICES_ONLY"]), int(consts["VQ_FLAG_EXACT_SCAN"]))
+    assert lib.FLAG_KEEP_STATS == int(consts["VQ_FLAG_KEEP_STATS"])
     assert lib.STATS_LEN == int(consts["VQ_STATS_LEN"])
     for name in ("NEAR_TIE_ROWS", "AMBIGUOUS_ROWS", "FALLBACK_ROWS", "LOSS_FIXED", "BAD_INDEX", "NONFINITE"):
         assert getattr(lib, "STAT_" + name) == int(consts["VQ_STAT_" + name])

@@ -365,3 +365,39 @@ def test_full_size_properties(dev):
     rep = vo.classify_index_mismatches(idx[:32].reshape(-1), ref.indices.reshape(-1),
                                        vo.unit_rows(z[:32].reshape(-1, D)), vo.unit_rows(w))
     assert rep["hard_rows"] == 0, rep
+
+
+@pytest.mark.parametrize("T", [1000, 3 * 32768 + 100])
+def test_host_buffer_step_equals_device_step(dev, T):
+    """vq_host_step (host pointers in/out; above 64 Ki tokens it streams the batch in token chunks over two copy
+    streams) must return exactly what the device-pointer calls return: indices, z_q, grad_z, grad_weight and the
+    loss are bit-identical because every cross-token quantity is an integer (fixed-point) sum."""
+    import ctypes
+    from vq_b200 import _lib
+    from vq_b200 import dist as vq_dist
+    K, D, beta = 1024, 32, 0.25
+    lib = _lib.load()
+    w = vo.make_codebook("vit", K, D, 11)
+    z = vo.make_latents((T, D), 12)
+    up = vo.make_latents((T, D), 13)
+    ref = vq_dist.ShardedQuantiser("vit", beta, world_size=1).step(z.to(dev), up.to(dev), w.to(dev))
+    ref = {k: v.clone() for k, v in ref.items()}
+    arena_bytes = _lib.size_query("vq_host_step_arena_bytes", T, K, D)
+    arena = torch.empty(arena_bytes, dtype=torch.uint8, device=dev)
+    hz, hg, hw = z.pin_memory(), up.pin_memory(), w.pin_memory()
+    o_zq, o_gz = torch.empty(T, D).pin_memory(), torch.empty(T, D).pin_memory()
+    o_idx = torch.empty(T, dtype=torch.int64).pin_memory()
+    o_loss, o_gw = torch.empty(1).pin_memory(), torch.empty(K, D).pin_memory()
+    o_stats = torch.empty(_lib.STATS_LEN, dtype=torch.int64).pin_memory()
+    for _ in range(2):      # twice: the second call reuses streams, events and the arena
+        _lib.check(lib.vq_host_step(hz.data_ptr(), hg.data_ptr(), T, hw.data_ptr(), K, D, 0, beta, o_zq.data_ptr(),
+                                    o_idx.data_ptr(), o_loss.data_ptr(), o_gz.data_ptr(), o_gw.data_ptr(),
+                                    o_stats.data_ptr(), arena.data_ptr(), arena_bytes,
+                                    torch.cuda.current_stream(dev).cuda_stream))
+        torch.cuda.synchronize()
+        assert torch.equal(o_idx, ref["indices"].cpu())
+        assert torch.equal(o_zq, ref["z_q"].cpu())
+        assert torch.equal(o_gz, ref["grad_z"].cpu())
+        assert torch.equal(o_gw, ref["grad_weight"].cpu())
+        assert float(o_loss) == float(ref["loss"])
+        o_zq.zero_(); o_gz.zero_(); o_idx.zero_(); o_gw.zero_(); o_loss.zero_()
