@@ -39,16 +39,19 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // measurement hooks: event pairs around the search kernel while profiling is on
 bool g_profiling = false;
 long long g_launches_at_begin = 0;
-std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_search_events;
+// [0]: the search kernel proper (tensor-core filter, or the exhaustive scan); [1]: exact rescoring + finish behind it
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_search_events, g_exact_events;
 
 struct SearchTimer {
     cudaEvent_t a = nullptr, b = nullptr;
     cudaStream_t s;
-    explicit SearchTimer(cudaStream_t stream) : s(stream) {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* sink;
+    explicit SearchTimer(cudaStream_t stream, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* where = &g_search_events)
+        : s(stream), sink(where) {
         if (g_profiling && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, s);
     }
     void stop() {
-        if (a && b) { cudaEventRecord(b, s); g_search_events.emplace_back(a, b); a = b = nullptr; }
+        if (a && b) { cudaEventRecord(b, s); sink->emplace_back(a, b); a = b = nullptr; }
     }
 };
 
@@ -191,23 +194,36 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
         VQ_CUDA(vq::launch_row_sumsq(zn32, T, D, w.row_sq, s));
     }
 
-    // 2. nearest code per row -> cand[]
+    // 2. nearest code per row, 3. idx, hist, z_q, loss partial
+    float* zq_tok = indices_only ? nullptr : (layout == VQ_LAYOUT_NCHW ? w.zq_tok : z_q);
     SearchTimer timer(s);
-    if (use_tc) {
+    if (use_tc && vq::tc16_supported(T, K, D)) {
+        // D = 32: tensor-core filter -> records; one kernel then does the exact rescoring, the sliced search of
+        // the undecided rows and the finish pass.  Undecided rows beyond kFlaggedCap (degenerate inputs) overflow
+        // into the generic exhaustive kernel + a listed finish; both leave at once when there are none.
         VQ_CUDA(cudaMemsetAsync(w.n_flagged, 0, sizeof(int) * (64 + vq::kFlaggedCap), s));
         VQ_CUDA(vq::launch_dist_tc(zn16, zn32, w.row_sq, cbv, T, w.cand, w.flagged, w.n_flagged, st, w.tc_ws, s));
-        if (vq::tc16_supported(T, K, D))
-            VQ_CUDA(vq::launch_scan_flagged16(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, w.n_flagged + 64, w.scan_ws, w.cand, st, s));
-        else
-            VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, T, w.cand, st, w.scan_ws, s));
+        timer.stop();
+        SearchTimer exact_timer(s, &g_exact_events);
+        VQ_CUDA(vq::launch_exact_finish16(w.tc_ws, zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, w.n_flagged + 64, w.scan_ws,
+                                          nullptr, zq_tok, idx, hist, st, s));
+        exact_timer.stop();
+        if (T > vq::kFlaggedCap) {
+            VQ_CUDA(vq::launch_scan_listed_tail(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, vq::kFlaggedCap, w.cand, st, s));
+            VQ_CUDA(vq::launch_finish_listed(zn32, w.cand, cbv, T, w.flagged, w.n_flagged, vq::kFlaggedCap, zq_tok, idx, hist,
+                                             st, s));
+        }
     } else {
-        VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, nullptr, nullptr, T, w.cand, st, nullptr, s));
+        if (use_tc) {
+            VQ_CUDA(cudaMemsetAsync(w.n_flagged, 0, sizeof(int) * 64, s));
+            VQ_CUDA(vq::launch_dist_tc(zn16, zn32, w.row_sq, cbv, T, w.cand, w.flagged, w.n_flagged, st, w.tc_ws, s));
+            VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, T, w.cand, st, w.scan_ws, s));
+        } else {
+            VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, nullptr, nullptr, T, w.cand, st, nullptr, s));
+        }
+        timer.stop();
+        VQ_CUDA(vq::launch_finish(zn32, w.cand, cbv, T, zq_tok, idx, hist, st, s));
     }
-    timer.stop();
-
-    // 3. idx, hist, z_q, loss partial
-    float* zq_tok = indices_only ? nullptr : (layout == VQ_LAYOUT_NCHW ? w.zq_tok : z_q);
-    VQ_CUDA(vq::launch_finish(zn32, w.cand, cbv, T, zq_tok, idx, hist, st, s));
     if (!indices_only && layout == VQ_LAYOUT_NCHW) VQ_CUDA(vq::launch_tok_to_nchw(zq_tok, T, hw, D, z_q, s));
     if (loss && !indices_only) {
         if (n_elem_total <= 0) return fail(VQ_ERR_ARG, "n_elem_total must be positive");
@@ -299,8 +315,10 @@ int vq_gather(const int64_t* idx, int64_t T, int64_t hw, const float* weight, co
 }
 
 int vq_profile_begin(void) {
-    for (auto& p : g_search_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-    g_search_events.clear();
+    for (auto* v : {&g_search_events, &g_exact_events}) {
+        for (auto& p : *v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+        v->clear();
+    }
     g_launches_at_begin = vq::g_kernel_launches;
     g_profiling = true;
     return VQ_OK;
@@ -320,6 +338,21 @@ int vq_profile_end(double* search_ms_total, int64_t* search_launches, int64_t* k
     if (kernel_launches) *kernel_launches = vq::g_kernel_launches - g_launches_at_begin;
     for (auto& p : g_search_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     g_search_events.clear();
+    return VQ_OK;
+}
+
+int vq_profile_exact(double* exact_ms_total, int64_t* exact_launches) {
+    double total = 0.0;
+    for (auto& p : g_exact_events) {
+        float ms = 0.f;
+        VQ_CUDA(cudaEventSynchronize(p.second));
+        VQ_CUDA(cudaEventElapsedTime(&ms, p.first, p.second));
+        total += ms;
+    }
+    if (exact_ms_total) *exact_ms_total = total;
+    if (exact_launches) *exact_launches = (int64_t)g_exact_events.size();
+    for (auto& p : g_exact_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    g_exact_events.clear();
     return VQ_OK;
 }
 

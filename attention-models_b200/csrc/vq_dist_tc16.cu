@@ -460,17 +460,53 @@ __device__ __forceinline__ float cell_distance(const float4* __restrict__ en32c,
     return ref_distance(a_sq, csq, dot);
 }
 
-// Rescoring of the verdict records: cand[row] = argmin over the row's surviving cells.  One 8-lane group per row.
-constexpr int kRescoreThreads = 128;
-__global__ void __launch_bounds__(kRescoreThreads)
-k_rescore16(const int4* __restrict__ rec, const float* __restrict__ zn32, const float* __restrict__ row_sq,
-            const float4* __restrict__ en32c, const float* __restrict__ csq_cell, int T, int* __restrict__ cand,
-            int64_t* __restrict__ stats) {
-    const int lane = threadIdx.x & 31;
+// What vq_finish.cu does for one row, for the 8 lanes (or one thread looping over the chunks) that just found its
+// index: z_q = zn + (q - zn), loss partial in fixed point -- same expressions, so both routes give the same bits.
+struct FinishOut {
+    float4* zq; int64_t* idx; int32_t* hist;
+};
+__device__ __forceinline__ void finish_chunk(const float4* __restrict__ zn4, const float4* __restrict__ en4, const FinishOut& out,
+                                             int row, int code, int chunk, long long& loss_fx, unsigned& bad) {
+    const float4 a = __ldg(zn4 + (int64_t)row * (kD / 4) + chunk);
+    const float4 q = __ldg(en4 + (int64_t)code * (kD / 4) + chunk);
+    float4 df, o;
+    df.x = __fsub_rn(q.x, a.x); df.y = __fsub_rn(q.y, a.y); df.z = __fsub_rn(q.z, a.z); df.w = __fsub_rn(q.w, a.w);
+    o.x = __fadd_rn(a.x, df.x); o.y = __fadd_rn(a.y, df.y); o.z = __fadd_rn(a.z, df.z); o.w = __fadd_rn(a.w, df.w);
+    __stcs(out.zq + (int64_t)row * (kD / 4) + chunk, o);
+    const float p = (df.x * df.x + df.y * df.y) + (df.z * df.z + df.w * df.w);
+    if (is_finite(p)) loss_fx += to_fixed(p, VQ_LOSS_SHIFT);
+    else bad += 1;
+}
+
+// Everything behind the filter in one launch:
+//   phase A  rescoring of the verdict records, one 8-lane group per row: index = argmin over the row's surviving
+//            cells; the same lanes then write idx / hist / z_q / loss partial (the former k_finish pass);
+//   phase B  exhaustive search of the rows the filter could not decide (a few dozen per 262 144).  Latency
+//            matters there, not throughput: a listed row is split over kFlaggedSlices items, an item leaves its
+//            (best, second) in `partial`, the last item of a row to finish folds them and finishes the row.
+//            Rows [0, min(*n_rows, cap)) of the list; `done` holds one zeroed counter per listed row.
+constexpr int kExactThreads = 128;
+constexpr int kFlaggedSlices = 32;
+struct __align__(16) FlaggedPartial {
+    unsigned long long best; float second; float pad;
+};
+__global__ void __launch_bounds__(kExactThreads)
+k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, const float* __restrict__ row_sq,
+                 const float* __restrict__ en32, const float4* __restrict__ en32c, const float* __restrict__ csq_cell, int T,
+                 int K, const int* __restrict__ flagged, const int* __restrict__ n_flagged, int flagged_cap,
+                 FlaggedPartial* __restrict__ partial, int* __restrict__ done, int* __restrict__ cand, FinishOut out,
+                 int64_t* __restrict__ stats) {
+    __shared__ unsigned long long s_best[kExactThreads / 32];
+    __shared__ float s_second[kExactThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m = lane & 7;
-    unsigned ties = 0, multi = 0;
-    const int groups = gridDim.x * (kRescoreThreads / 8);
-    for (int row0 = (blockIdx.x * kRescoreThreads + threadIdx.x - lane) >> 3; row0 < T; row0 += groups) {
+    const float4* zn4 = reinterpret_cast<const float4*>(zn32);
+    const float4* en4 = reinterpret_cast<const float4*>(en32);
+    unsigned ties = 0, multi = 0, bad = 0;
+    long long loss_fx = 0;
+    // ---------------- phase A ----------------
+    const int groups = gridDim.x * (kExactThreads / 8);
+    for (int row0 = (blockIdx.x * kExactThreads + threadIdx.x - lane) >> 3; row0 < T; row0 += groups) {
         const int row = row0 + (lane >> 3);
         int4 h0 = make_int4(-1, 0, 0, 0), h1 = make_int4(0, 0, 0, 0), h2 = make_int4(0, 0, 0, 0);
         if (row < T) { h0 = __ldg(rec + 3 * (int64_t)row); h1 = __ldg(rec + 3 * (int64_t)row + 1); h2 = __ldg(rec + 3 * (int64_t)row + 2); }
@@ -486,9 +522,8 @@ k_rescore16(const int4* __restrict__ rec, const float* __restrict__ zn32, const 
         float4 z[kD / 4];
         float a_sq = 0.f;
         if (valid) {
-            const float4* z4 = reinterpret_cast<const float4*>(zn32 + (int64_t)row * kD);
 #pragma unroll
-            for (int q = 0; q < kD / 4; ++q) z[q] = __ldg(z4 + q);
+            for (int q = 0; q < kD / 4; ++q) z[q] = __ldg(zn4 + (int64_t)row * (kD / 4) + q);
             a_sq = __ldg(row_sq + row);
         }
         Top2 top;
@@ -511,93 +546,91 @@ k_rescore16(const int4* __restrict__ rec, const float* __restrict__ zn32, const 
             const float os = __shfl_xor_sync(VQ_FULL, top.second, off);
             top.merge(ob, os);
         }
-        if (valid && m == 0) {
-            const float bd = key_dist(top.best);
-            cand[row] = (int)(uint32_t)top.best | kCandExactBit;
-            if (top.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) ++ties;
-            if (n_cells > 1) ++multi;
+        if (valid) {
+            const int code = (int)(uint32_t)top.best;
+            if (m == 0) {
+                const float bd = key_dist(top.best);
+                if (cand) cand[row] = code | kCandExactBit;
+                out.idx[row] = code;
+                if (out.hist) atomicAdd(out.hist + code, 1);
+                if (top.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) ++ties;
+                if (n_cells > 1) ++multi;
+            }
+            if (out.zq) finish_chunk(zn4, en4, out, row, code, m, loss_fx, bad);
         }
     }
+    // ---------------- phase B ----------------
+    {
+        const int grp = threadIdx.x >> 3;
+        int n = *n_flagged;
+        if (n > flagged_cap) n = flagged_cap;
+        const int n_cells = K / kCellCodes;
+        const int per_slice = (n_cells + kFlaggedSlices - 1) / kFlaggedSlices;
+        for (int item = blockIdx.x; item < n * kFlaggedSlices; item += gridDim.x) {
+            const int i = item / kFlaggedSlices, slice = item % kFlaggedSlices;
+            const int row = flagged[i];
+            float4 z[kD / 4];
+#pragma unroll
+            for (int q = 0; q < kD / 4; ++q) z[q] = __ldg(zn4 + (int64_t)row * (kD / 4) + q);
+            const float a_sq = __ldg(row_sq + row);
+            Top2 top;
+            top.init();
+            const int c_end = min(n_cells, (slice + 1) * per_slice);
+            for (int ci = slice * per_slice + grp; ci < c_end; ci += kExactThreads / 8) {
+                const float dist = cell_distance(en32c, csq_cell, ci, m, z, a_sq);
+                top.add(dist_key(dist, (ci >> 6) * kGroupCols + (ci & 63) + 64 * m));
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const unsigned long long ob = __shfl_xor_sync(VQ_FULL, top.best, off);
+                const float os = __shfl_xor_sync(VQ_FULL, top.second, off);
+                top.merge(ob, os);
+            }
+            __syncthreads();                       // the previous item's shared values are consumed
+            if (lane == 0) { s_best[warp] = top.best; s_second[warp] = top.second; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                Top2 all;
+                all.init();
+                for (int w = 0; w < kExactThreads / 32; ++w) all.merge(s_best[w], s_second[w]);
+                FlaggedPartial pp;
+                pp.best = all.best; pp.second = all.second; pp.pad = 0.f;
+                partial[(int64_t)i * kFlaggedSlices + slice] = pp;
+                __threadfence();
+                if (atomicAdd(done + i, 1) == kFlaggedSlices - 1) {
+                    __threadfence();
+                    Top2 fin;
+                    fin.init();
+                    for (int w = 0; w < kFlaggedSlices; ++w) {
+                        const FlaggedPartial* q = partial + (int64_t)i * kFlaggedSlices + w;
+                        fin.merge(__ldcg(&q->best), __ldcg(&q->second));
+                    }
+                    const float bd = key_dist(fin.best);
+                    const int code = (int)(uint32_t)fin.best;
+                    if (cand) cand[row] = code | kCandExactBit;
+                    out.idx[row] = code;
+                    if (out.hist) atomicAdd(out.hist + code, 1);
+                    if (fin.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) ++ties;
+                    if (out.zq)
+                        for (int chunk = 0; chunk < kD / 4; ++chunk) finish_chunk(zn4, en4, out, row, code, chunk, loss_fx, bad);
+                    done[i] = 0;                   // ready for the next call
+                }
+            }
+        }
+    }
+    // ---------------- statistics ----------------
     if (stats) {
         ties = __reduce_add_sync(VQ_FULL, ties);
         multi = __reduce_add_sync(VQ_FULL, multi);
+        bad = __reduce_add_sync(VQ_FULL, bad);
+        unsigned long long lf = (unsigned long long)loss_fx;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) lf += __shfl_xor_sync(VQ_FULL, lf, off);
         if (lane == 0) {
             if (ties) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), (unsigned long long)ties);
             if (multi) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_AMBIGUOUS_ROWS), (unsigned long long)multi);
-        }
-    }
-}
-
-// Exhaustive search of the rows the filter could not decide (a few dozen per 262 144).  Latency matters here, not
-// throughput: every listed row is split over kFlaggedSlices blocks (32 lane groups x 8 codes = 256 codes per
-// step); a slice leaves its (best, second) in `partial` and the last slice of a row to finish folds them.
-// Rows [0, min(*n_rows, cap)) of the list; `done` holds one zeroed counter per listed row.
-constexpr int kFlaggedSlices = 32;
-struct __align__(16) FlaggedPartial {
-    unsigned long long best; float second; float pad;
-};
-__global__ void __launch_bounds__(256)
-k_scan_flagged16(const int* __restrict__ rows, const int* __restrict__ n_rows, int cap, const float* __restrict__ zn32,
-                 const float* __restrict__ row_sq, const float4* __restrict__ en32c, const float* __restrict__ csq_cell,
-                 int K, int* __restrict__ cand, FlaggedPartial* __restrict__ partial, int* __restrict__ done,
-                 int64_t* __restrict__ stats) {
-    __shared__ unsigned long long s_best[8];
-    __shared__ float s_second[8];
-    __shared__ int s_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int m = threadIdx.x & 7, grp = threadIdx.x >> 3;
-    int n = *n_rows;
-    if (n > cap) n = cap;
-    const int n_cells = K / kCellCodes;
-    const int per_slice = (n_cells + kFlaggedSlices - 1) / kFlaggedSlices;
-    for (int item = blockIdx.x; item < n * kFlaggedSlices; item += gridDim.x) {
-        const int i = item / kFlaggedSlices, slice = item % kFlaggedSlices;
-        const int row = rows[i];
-        float4 z[kD / 4];
-        const float4* z4 = reinterpret_cast<const float4*>(zn32 + (int64_t)row * kD);
-#pragma unroll
-        for (int q = 0; q < kD / 4; ++q) z[q] = __ldg(z4 + q);
-        const float a_sq = __ldg(row_sq + row);
-        Top2 top;
-        top.init();
-        const int c_end = min(n_cells, (slice + 1) * per_slice);
-#pragma unroll 2
-        for (int ci = slice * per_slice + grp; ci < c_end; ci += 32) {
-            const float dist = cell_distance(en32c, csq_cell, ci, m, z, a_sq);
-            top.add(dist_key(dist, (ci >> 6) * kGroupCols + (ci & 63) + 64 * m));
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long ob = __shfl_xor_sync(VQ_FULL, top.best, off);
-            const float os = __shfl_xor_sync(VQ_FULL, top.second, off);
-            top.merge(ob, os);
-        }
-        __syncthreads();                       // the previous item's shared values are consumed
-        if (lane == 0) { s_best[warp] = top.best; s_second[warp] = top.second; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            Top2 all;
-            all.init();
-            for (int w = 0; w < 8; ++w) all.merge(s_best[w], s_second[w]);
-            FlaggedPartial p;
-            p.best = all.best; p.second = all.second; p.pad = 0.f;
-            partial[(int64_t)i * kFlaggedSlices + slice] = p;
-            __threadfence();
-            s_last = (atomicAdd(done + i, 1) == kFlaggedSlices - 1);
-            if (s_last) {
-                __threadfence();
-                Top2 fin;
-                fin.init();
-                for (int w = 0; w < kFlaggedSlices; ++w) {
-                    const FlaggedPartial* q = partial + (int64_t)i * kFlaggedSlices + w;
-                    fin.merge(__ldcg(&q->best), __ldcg(&q->second));
-                }
-                const float bd = key_dist(fin.best);
-                cand[row] = (int)(uint32_t)fin.best | kCandExactBit;
-                if (stats && (fin.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)))
-                    atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), 1ull);
-                done[i] = 0;                   // ready for the next call
-            }
+            if (lf) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_LOSS_FIXED), lf);
+            if (bad) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NONFINITE), (unsigned long long)bad);
         }
     }
 }
@@ -617,7 +650,6 @@ cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T
                              void* records, cudaStream_t s) {
     const tc16::SmemLayout L = tc16::smem_layout();
     static const bool service_low = getenv("VQ_TC16_SERVICE_LOW") && atoi(getenv("VQ_TC16_SERVICE_LOW")) != 0;
-    static const int debug_flags = getenv("VQ_TC_DEBUG") ? atoi(getenv("VQ_TC_DEBUG")) : 0;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc16::k_dist_tc16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
@@ -637,32 +669,27 @@ cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T
                                                                             n_flagged, stats);
     count_launch();
     tc::instrument_report(s, grid);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess || (debug_flags & 1)) return e;       // debug bit 0: timing experiment without rescoring
-    const int rows_per_block = tc16::kRescoreThreads / 8;
-    int blocks = (T + rows_per_block - 1) / rows_per_block;
-    const int cap = sm_count() * 16 * 2;                         // resident blocks, two passes
-    if (blocks > cap) blocks = cap;
-    tc16::k_rescore16<<<blocks, tc16::kRescoreThreads, 0, s>>>(rec, zn32, row_sq, reinterpret_cast<const float4*>(cb.en32c),
-                                                               cb.csq_cell, T, cand, stats);
-    count_launch();
     return cudaGetLastError();
 }
 
-// rows the filter left undecided: the first kFlaggedCap of them here (32 blocks per row), the rest (degenerate inputs
-// only) through the throughput-oriented exhaustive kernel of vq_dist_simt.cu.  done_counters: kFlaggedCap zeroed ints;
-// partial_ws: kFlaggedCap * 32 * 16 bytes.
-cudaError_t launch_scan_flagged16(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T, const int* flagged,
-                                  const int* n_flagged, int* done_counters, void* partial_ws, int* cand, int64_t* stats,
-                                  cudaStream_t s) {
+// Exact indices and the finish pass behind the filter (see k_exact_finish16).  zq_tok / hist may be null.
+// done_counters: kFlaggedCap zeroed ints; partial_ws: kFlaggedCap * 32 * 16 bytes.  Listed rows beyond kFlaggedCap
+// (degenerate inputs only) are left in cand[] = -1 for the caller's overflow path.
+cudaError_t launch_exact_finish16(const void* records, const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
+                                  const int* flagged, const int* n_flagged, int* done_counters, void* partial_ws, int* cand,
+                                  float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* stats, cudaStream_t s) {
     const int cap = (int)(T < kFlaggedCap ? T : kFlaggedCap);
-    tc16::k_scan_flagged16<<<sm_count() * 4, 256, 0, s>>>(flagged, n_flagged, cap, zn32, row_sq,
-                                                          reinterpret_cast<const float4*>(cb.en32c), cb.csq_cell, cb.K, cand,
-                                                          static_cast<tc16::FlaggedPartial*>(partial_ws), done_counters, stats);
+    const int rows_per_block = tc16::kExactThreads / 8;
+    int64_t blocks = (T + rows_per_block - 1) / rows_per_block;
+    const int64_t grid_cap = (int64_t)sm_count() * 16 * 2;       // resident blocks, two passes
+    if (blocks > grid_cap) blocks = grid_cap;
+    tc16::FinishOut out;
+    out.zq = reinterpret_cast<float4*>(zq_tok); out.idx = idx_out; out.hist = hist;
+    tc16::k_exact_finish16<<<(unsigned)blocks, tc16::kExactThreads, 0, s>>>(
+        static_cast<const int4*>(records), zn32, row_sq, cb.en32, reinterpret_cast<const float4*>(cb.en32c), cb.csq_cell, (int)T,
+        cb.K, flagged, n_flagged, cap, static_cast<tc16::FlaggedPartial*>(partial_ws), done_counters, cand, out, stats);
     count_launch();
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess || T <= cap) return e;
-    return launch_scan_listed_tail(zn32, row_sq, cb, T, flagged, n_flagged, cap, cand, stats, s);
+    return cudaGetLastError();
 }
 
 }  // namespace vq

@@ -57,9 +57,10 @@ cudaError_t launch_scan_listed_tail(const float* zn32, const float* row_sq, cons
 // ---- vq_dist_tc16.cu (D = 32: fp16 accumulators, packed 16-bit maxima) ------------------------
 bool tc16_supported(int64_t T, int K, int D);
 constexpr int kFlaggedCap = 4096;     // listed rows that get the sliced per-row search (and a done counter each)
-cudaError_t launch_scan_flagged16(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
-                                  const int* flagged, const int* n_flagged, int* done_counters, void* partial_ws,
-                                  int* cand, int64_t* stats, cudaStream_t s);
+// exact rescoring of the filter's records + sliced search of the listed rows + the finish pass, one launch
+cudaError_t launch_exact_finish16(const void* records, const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
+                                  const int* flagged, const int* n_flagged, int* done_counters, void* partial_ws, int* cand,
+                                  float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* stats, cudaStream_t s);
 
 // ---- vq_dist_tc.cu ---------------------------------------------------------------------------
 // tcgen05 search: cand[row] = cell id (or exact index for rows resolved in-kernel); rows it cannot
@@ -74,6 +75,10 @@ cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* r
 // idx / hist / z_q (token-major) / loss partial from final indices in cand[].
 cudaError_t launch_finish(const float* zn32, const int* cand, const CodebookView& cb, int64_t T,
                           float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* stats, cudaStream_t s);
+// finish pass for the listed rows [row_begin, *n_rows) only (overflow of the D = 32 per-row fallback)
+cudaError_t launch_finish_listed(const float* zn32, const int* cand, const CodebookView& cb, int64_t T, const int* rows,
+                                 const int* n_rows, int64_t row_begin, float* zq_tok, int64_t* idx_out, int32_t* hist,
+                                 int64_t* stats, cudaStream_t s);
 cudaError_t launch_loss_finalize(const int64_t* stats, int64_t n_elem_total, int form, float beta, float* loss,
                                  cudaStream_t s);
 cudaError_t launch_gather(const int64_t* idx, int64_t T, int64_t hw, const float* table, int K, int D,

@@ -45,6 +45,7 @@ SIGNATURES = {
                           c_void_p, c_void_p]),
     "vq_profile_begin": (c_int, []),
     "vq_profile_end": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64), POINTER(c_int64)]),
+    "vq_profile_exact": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
     "vq_host_step_arena_bytes": (c_int, [c_int64, c_int, c_int, POINTER(c_size_t)]),
     "vq_host_step": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -39,6 +39,10 @@ for _p in (ROOT, PKG):
         sys.path.insert(0, _p)
 
 K_CODES, DIM, IMGS_PER_GPU, TOKENS_PER_IMG, BETA = 8192, 32, 256, 1024, 0.25
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_dist_tc16 launch (ncu --set full, profiles/r01_*): the
+# fp16 token rows (16.8 MB) + the 0.5 MB fp16 codebook; the verdict records (12.6 MB) are still in L2 when the
+# kernel ends, the codebook tiles stream from L2
+DRAM_TRAFFIC_FILTER = 17.33e6
 METRIC = "vq_tokens_per_sec_fwd_bwd_K8192_D32"
 UNIT = "tokens/s"
 WORKLOAD = ("cfg3: ViT-VQGAN quantiser fwd+bwd (STE + codebook grad), codebook 8192x32, "
@@ -211,6 +215,8 @@ def run_b200(args):
     ms_total = start.elapsed_time(stop)
     search_ms, search_n, launches = ctypes.c_double(0), ctypes.c_int64(0), ctypes.c_int64(0)
     _lib.check(lib.vq_profile_end(ctypes.byref(search_ms), ctypes.byref(search_n), ctypes.byref(launches)))
+    exact_ms, exact_n = ctypes.c_double(0), ctypes.c_int64(0)
+    _lib.check(lib.vq_profile_exact(ctypes.byref(exact_ms), ctypes.byref(exact_n)))
     clocks = sampler.stop()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -269,20 +275,30 @@ def run_b200(args):
     search_avg_ms = search_ms.value / max(1, search_n.value)
     achieved_tf = flops_per_launch / (search_avg_ms * 1e-3) / 1e12 if search_avg_ms > 0 else 0.0
     peak_tf = peaks["tf_sustained"]
-    roofline = {"kernel": "nearest-code search (vq_forward step 2: distance + argmin)",
+    tc_path = not (args.exact_scan or not stepper.uses_tensor_cores(T, K_CODES, DIM))
+    exact_avg_ms = exact_ms.value / max(1, exact_n.value)
+    roofline = {"kernel": "k_dist_tc16: tcgen05 distance + running-maximum filter (z.C^T for every token x code)" if tc_path
+                          else "k_scan_exact: exhaustive fp32 distance + argmin",
                 "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None,
+                "frac": achieved_tf / peak_tf, "traffic": DRAM_TRAFFIC_FILTER if tc_path else None,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "avg_launch_ms": search_avg_ms, "share_of_step": search_avg_ms / ms_step,
                 "algorithmic": "2*K*D = 524288 flop/token x 262144 tokens per launch",
-                "path": "exact fp32 SIMT scan" if (args.exact_scan or not stepper.uses_tensor_cores(T, K_CODES, DIM))
-                        else "tcgen05 fp16 search + exact fp32 rescoring"}
+                "path": "tcgen05 fp16 filter (fp16 accumulators) -> exact fp32 rescoring + finish kernel" if tc_path
+                        else "exact fp32 SIMT scan",
+                "traffic_note": "dram__bytes_read+write of one k_dist_tc16 launch, ncu --set full (profiles/)" if tc_path else None,
+                "behind_the_filter": {"kernel": "k_exact_finish16: exact fp32 rescoring of the surviving cells + idx/z_q/loss/hist",
+                                      "avg_launch_ms": exact_avg_ms, "bound": "L2 (scattered 128-byte code rows)",
+                                      "search_total_tflops": flops_per_launch / ((search_avg_ms + exact_avg_ms) * 1e-3) / 1e12,
+                                      "search_total_frac": flops_per_launch / ((search_avg_ms + exact_avg_ms) * 1e-3) / 1e12 / peak_tf}
+                                     if exact_n.value else None}
     hbm_bytes_step = (20 * DIM + 16) * T + 4 * K_CODES * DIM
-    non_search_ms = max(ms_step - search_avg_ms, 1e-6)
+    non_search_ms = max(ms_step - search_avg_ms - exact_avg_ms, 1e-6)
     hbm = {"algorithmic_bytes_per_step": hbm_bytes_step, "non_search_ms": non_search_ms,
            "achieved_gbs": hbm_bytes_step / (non_search_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
            "frac": hbm_bytes_step / (non_search_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-           "note": "all non-search kernels of the step together (prep, finish, backward) vs algorithmic 20D+16 B/token"}
+           "note": "all kernels of the step outside the search (filter + exact/finish) together: prep and backward, "
+                   "vs algorithmic 20D+16 B/token"}
 
     # ---- cpu_baseline: oracle port on this box's host cores, bounded sample -------------------------
     cpu = None

@@ -147,6 +147,9 @@ VQ_API int vq_gather(const int64_t* idx, int64_t T, int64_t hw, const float* wei
  * launches and the number of kernel launches of all kinds.                                         */
 VQ_API int vq_profile_begin(void);
 VQ_API int vq_profile_end(double* search_ms_total, int64_t* search_launches, int64_t* kernel_launches);
+/* Where the search is a tensor-core filter followed by an exact rescoring + finish kernel (D = 32), the filter is
+ * what vq_profile_end times; this returns the summed time of the kernel behind it (call after vq_profile_end). */
+VQ_API int vq_profile_exact(double* exact_ms_total, int64_t* exact_launches);
 
 /* ---- host-buffer entry points (end-to-end path: host pointers in, host pointers out) --------
  * Same semantics as vq_forward + vq_backward_tokens + vq_backward_codebook for token-major fp32
