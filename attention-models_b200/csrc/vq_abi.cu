@@ -161,13 +161,14 @@ int vq_workspace_bytes(int64_t T, int K, int D, int flags, size_t* out) {
 
 int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb, int K, int D, int form, float beta,
                int flags, int64_t n_elem_total, float* z_q, int64_t* idx, float* loss, int32_t* hist, int64_t* stats,
-               float* saved_zn, float* saved_denom, void* ws, size_t ws_bytes, void* stream) {
+               float* saved_zn, float* saved_denom, int64_t* seg_sums, void* ws, size_t ws_bytes, void* stream) {
     if (int r = check_dims(T, K, D)) return r;
     if (int r = check_layout(layout, T, hw)) return r;
     if (form != VQ_FORM_VIT && form != VQ_FORM_VQGAN) return fail(VQ_ERR_ARG, "unknown form %d", form);
     if (!cb || !idx || (!z && T > 0)) return fail(VQ_ERR_ARG, "z/cb/idx is NULL");
     const bool indices_only = (flags & VQ_FLAG_INDICES_ONLY) != 0;
     if (!indices_only && !z_q) return fail(VQ_ERR_ARG, "z_q is NULL without VQ_FLAG_INDICES_ONLY");
+    if (indices_only && seg_sums) return fail(VQ_ERR_ARG, "seg_sums needs the full forward (no VQ_FLAG_INDICES_ONLY)");
     if (!ws) return fail(VQ_ERR_WORKSPACE, "workspace is NULL");
     FwdWs w = carve_forward(ws, T, K, D);
     if (ws_bytes < w.bytes) return fail(VQ_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, w.bytes);
@@ -180,6 +181,7 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
     if (!(flags & VQ_FLAG_KEEP_STATS)) {
         VQ_CUDA(cudaMemsetAsync(st, 0, sizeof(int64_t) * VQ_STATS_LEN, s));
         if (hist) VQ_CUDA(cudaMemsetAsync(hist, 0, sizeof(int32_t) * (size_t)K, s));
+        if (seg_sums) VQ_CUDA(cudaMemsetAsync(seg_sums, 0, sizeof(int64_t) * ((size_t)K * D + K), s));
     }
 
     const bool use_tc = !(flags & VQ_FLAG_EXACT_SCAN) && vq::tc_supported(T, K, D);
@@ -206,12 +208,12 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
         timer.stop();
         SearchTimer exact_timer(s, &g_exact_events);
         VQ_CUDA(vq::launch_exact_finish16(w.tc_ws, zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, w.n_flagged + 64, w.scan_ws,
-                                          nullptr, zq_tok, idx, hist, st, s));
+                                          nullptr, zq_tok, idx, hist, seg_sums, st, s));
         exact_timer.stop();
         if (T > vq::kFlaggedCap) {
             VQ_CUDA(vq::launch_scan_listed_tail(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, vq::kFlaggedCap, w.cand, st, s));
             VQ_CUDA(vq::launch_finish_listed(zn32, w.cand, cbv, T, w.flagged, w.n_flagged, vq::kFlaggedCap, zq_tok, idx, hist,
-                                             st, s));
+                                             seg_sums, st, s));
         }
     } else {
         if (use_tc) {
@@ -222,7 +224,7 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
             VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, nullptr, nullptr, T, w.cand, st, nullptr, s));
         }
         timer.stop();
-        VQ_CUDA(vq::launch_finish(zn32, w.cand, cbv, T, zq_tok, idx, hist, st, s));
+        VQ_CUDA(vq::launch_finish(zn32, w.cand, cbv, T, zq_tok, idx, hist, seg_sums, st, s));
     }
     if (!indices_only && layout == VQ_LAYOUT_NCHW) VQ_CUDA(vq::launch_tok_to_nchw(zq_tok, T, hw, D, z_q, s));
     if (loss && !indices_only) {
@@ -292,6 +294,73 @@ int vq_backward_codebook(const int64_t* seg_sums, const void* cb, int K, int D, 
     const float c2 = (form == VQ_FORM_VIT) ? 1.f : beta;
     const float coef = (float)((double)c2 * 2.0 / (double)n_elem_total);
     VQ_CUDA(vq::launch_codebook_grad(seg_sums, cbv, coef, g_loss, grad_weight, static_cast<cudaStream_t>(stream)));
+    return VQ_OK;
+}
+
+int vq_exchange_bytes(int K, int D, size_t* out) {
+    if (!out) return fail(VQ_ERR_ARG, "out is NULL");
+    if (int r = check_dims(0, K, D)) return r;
+    *out = vq::exchange_layout(K, D).total;
+    return VQ_OK;
+}
+
+int vq_exchange_slot(void* exchange_buf, int K, int D, int slot, int64_t** seg_sums, int64_t** stats, int32_t** hist) {
+    if (int r = check_dims(0, K, D)) return r;
+    if (!exchange_buf || (slot != 0 && slot != 1)) return fail(VQ_ERR_ARG, "bad exchange buffer / slot");
+    const vq::ExchangeLayout L = vq::exchange_layout(K, D);
+    char* base = static_cast<char*>(exchange_buf) + L.slot0_off + (size_t)slot * L.slot_bytes;
+    if (seg_sums) *seg_sums = reinterpret_cast<int64_t*>(base);
+    if (stats) *stats = reinterpret_cast<int64_t*>(base + L.stats_off);
+    if (hist) *hist = reinterpret_cast<int32_t*>(base + L.hist_off);
+    return VQ_OK;
+}
+
+int vq_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out) {
+    if (!dev_ptr || !ipc_handle_out || bytes == 0) return fail(VQ_ERR_ARG, "bad argument to vq_peer_alloc");
+    static_assert(sizeof(cudaIpcMemHandle_t) == VQ_IPC_HANDLE_BYTES, "IPC handle size");
+    void* p = nullptr;
+    VQ_CUDA(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "vq_peer_alloc"); }
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    *dev_ptr = p;
+    return VQ_OK;
+}
+
+int vq_peer_open(const void* ipc_handle, void** dev_ptr) {
+    if (!ipc_handle || !dev_ptr) return fail(VQ_ERR_ARG, "bad argument to vq_peer_open");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    VQ_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return VQ_OK;
+}
+
+int vq_peer_close(void* dev_ptr) {
+    if (dev_ptr) VQ_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return VQ_OK;
+}
+
+int vq_peer_free(void* dev_ptr) {
+    if (dev_ptr) VQ_CUDA(cudaFree(dev_ptr));
+    return VQ_OK;
+}
+
+int vq_backward_codebook_sharded(const void* const* peer_bufs, int world, int rank, int slot, uint32_t epoch, const void* cb,
+                                 int K, int D, int form, float beta, const float* g_loss, int64_t n_elem_total,
+                                 float* grad_weight, int64_t* hist_total, float* loss, int64_t* stats_total, void* stream) {
+    if (int r = check_dims(0, K, D)) return r;
+    if (!peer_bufs || world < 1 || world > VQ_PEER_MAX_RANKS || rank < 0 || rank >= world || (slot != 0 && slot != 1))
+        return fail(VQ_ERR_ARG, "bad world / rank / slot for vq_backward_codebook_sharded");
+    for (int r = 0; r < world; ++r)
+        if (!peer_bufs[r]) return fail(VQ_ERR_ARG, "peer_bufs[%d] is NULL", r);
+    if (!cb || !grad_weight || n_elem_total <= 0) return fail(VQ_ERR_ARG, "bad argument to vq_backward_codebook_sharded");
+    vq::CodebookView cbv = vq::codebook_view(const_cast<void*>(cb), K, D);
+    const float c2 = (form == VQ_FORM_VIT) ? 1.f : beta;
+    const float coef = (float)((double)c2 * 2.0 / (double)n_elem_total);
+    VQ_CUDA(vq::launch_codebook_grad_sharded(peer_bufs, world, rank, slot, epoch, cbv, coef, g_loss, n_elem_total, form, beta,
+                                             grad_weight, hist_total, loss, stats_total, static_cast<cudaStream_t>(stream)));
     return VQ_OK;
 }
 
@@ -467,12 +536,13 @@ int vq_host_step(const float* z_host, const float* g_zq_host, int64_t T, const f
     if (int r = vq_codebook_prepare(a.weight, K, D, a.cb, vq::codebook_bytes(K, D), s)) return r;
     VQ_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(int64_t) * VQ_STATS_LEN, s));
     VQ_CUDA(cudaMemsetAsync(a.hist, 0, sizeof(int32_t) * (size_t)K, s));
+    if (grad_weight_host) VQ_CUDA(cudaMemsetAsync(a.seg, 0, sizeof(int64_t) * ((size_t)K * D + K), s));
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t t0 = c * chunk, n = (T - t0 < chunk) ? T - t0 : chunk;
         VQ_CUDA(cudaStreamWaitEvent(s, p.loaded[c], 0));
         if (int r = vq_forward(a.z + t0 * D, VQ_LAYOUT_TOKEN_MAJOR, n, 0, a.cb, K, D, form, beta, VQ_FLAG_KEEP_STATS, n_elem,
                                a.zq + t0 * D, a.idx + t0, nullptr, a.hist, a.stats, bwd ? a.zn + t0 * D : nullptr,
-                               bwd ? a.denom + t0 : nullptr, a.fws, a.fws_bytes, s))
+                               bwd ? a.denom + t0 : nullptr, grad_weight_host ? a.seg : nullptr, a.fws, a.fws_bytes, s))
             return r;
         if (grad_z_host)
             if (int r = vq_backward_tokens(g_zq_host ? a.g + t0 * D : nullptr, VQ_LAYOUT_TOKEN_MAJOR, n, 0, a.zn + t0 * D,
@@ -486,14 +556,10 @@ int vq_host_step(const float* z_host, const float* g_zq_host, int64_t T, const f
         if (grad_z_host)
             VQ_CUDA(cudaMemcpyAsync(grad_z_host + t0 * D, a.gz + t0 * D, row_bytes * n, cudaMemcpyDeviceToHost, p.out));
     }
-    // ---- whole-batch tail: loss from the accumulated fixed-point sum, codebook gradient over all tokens ----
+    // ---- whole-batch tail: loss and codebook gradient from the accumulated fixed-point sums ----
     if (loss_host) VQ_CUDA(vq::launch_loss_finalize(a.stats, n_elem, form, beta, a.loss, s));
-    if (grad_weight_host) {
-        if (int r = vq_backward_tokens(nullptr, VQ_LAYOUT_TOKEN_MAJOR, T, 0, a.zn, a.denom, a.idx, a.hist, a.cb, K, D, form,
-                                       beta, nullptr, n_elem, nullptr, a.seg, a.bws, a.bws_bytes, s))
-            return r;
+    if (grad_weight_host)   // the chunks' forwards accumulated the integer segment sums of the whole batch
         if (int r = vq_backward_codebook(a.seg, a.cb, K, D, form, beta, nullptr, n_elem, a.gw, s)) return r;
-    }
     VQ_CUDA(cudaEventRecord(p.tail, s));
     VQ_CUDA(cudaStreamWaitEvent(p.out, p.tail, 0));
     if (loss_host) VQ_CUDA(cudaMemcpyAsync(loss_host, a.loss, sizeof(float), cudaMemcpyDeviceToHost, p.out));

@@ -139,6 +139,14 @@ __device__ __forceinline__ long long to_fixed(float v, int shift) {
     return __float2ll_rn(v * static_cast<float>(1ll << shift));
 }
 
+// One term of the codebook-gradient segment sum S_k += fixed(q_k - zn_t) as a 64-bit integer reduction (RED.ADD.64):
+// integer sums are exact and order-free, so accumulating straight from the token pass is as deterministic as the
+// bucketed sum (vq_backward.cu).  Non-finite terms are not added; the caller counts them per code instead.
+__device__ __forceinline__ void seg_add(unsigned long long* __restrict__ slot, float d, unsigned& poison) {
+    if (is_finite(d)) atomicAdd(slot, (unsigned long long)to_fixed(d, VQ_SEG_SHIFT));
+    else poison = 1;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(VQ_FULL, v, off);

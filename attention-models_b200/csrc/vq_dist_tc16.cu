@@ -460,22 +460,36 @@ __device__ __forceinline__ float cell_distance(const float4* __restrict__ en32c,
     return ref_distance(a_sq, csq, dot);
 }
 
-// What vq_finish.cu does for one row, for the 8 lanes (or one thread looping over the chunks) that just found its
-// index: z_q = zn + (q - zn), loss partial in fixed point -- same expressions, so both routes give the same bits.
+// What vq_finish.cu does for one row, for lane m of the 8 lanes that just found its index (or one thread looping
+// over m): z_q = zn + (q - zn), loss partial in fixed point, and -- when the step trains the codebook -- the row's
+// terms of the segment sums S_code += fixed(q - zn).  Lane m owns elements m, m + 8, m + 16, m + 24 of the row, so
+// every load / store / RED instruction of the 8 lanes touches 8 consecutive elements: one 32-byte sector of
+// fp32, two of the int64 sums (4x fewer L2 reduction transactions than a float4-per-lane mapping; measured in
+// tools/ubench_red.cu: 8 us over the row stream for 262 144 rows against 35 us).
 struct FinishOut {
-    float4* zq; int64_t* idx; int32_t* hist;
+    float* zq; int64_t* idx; int32_t* hist; unsigned long long* seg;
 };
-__device__ __forceinline__ void finish_chunk(const float4* __restrict__ zn4, const float4* __restrict__ en4, const FinishOut& out,
-                                             int row, int code, int chunk, long long& loss_fx, unsigned& bad) {
-    const float4 a = __ldg(zn4 + (int64_t)row * (kD / 4) + chunk);
-    const float4 q = __ldg(en4 + (int64_t)code * (kD / 4) + chunk);
-    float4 df, o;
-    df.x = __fsub_rn(q.x, a.x); df.y = __fsub_rn(q.y, a.y); df.z = __fsub_rn(q.z, a.z); df.w = __fsub_rn(q.w, a.w);
-    o.x = __fadd_rn(a.x, df.x); o.y = __fadd_rn(a.y, df.y); o.z = __fadd_rn(a.z, df.z); o.w = __fadd_rn(a.w, df.w);
-    __stcs(out.zq + (int64_t)row * (kD / 4) + chunk, o);
-    const float p = (df.x * df.x + df.y * df.y) + (df.z * df.z + df.w * df.w);
+__device__ __forceinline__ void finish_lane(const float* __restrict__ zn32, const float* __restrict__ en32, const FinishOut& out,
+                                            int K, int row, int code, int m, long long& loss_fx, unsigned& bad) {
+    const float* a_row = zn32 + (int64_t)row * kD + m;
+    const float* q_row = en32 + (int64_t)code * kD + m;
+    float a[4], q[4], df[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { a[i] = __ldg(a_row + 8 * i); q[i] = __ldg(q_row + 8 * i); }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        df[i] = __fsub_rn(q[i], a[i]);
+        __stcs(out.zq + (int64_t)row * kD + m + 8 * i, __fadd_rn(a[i], df[i]));
+    }
+    const float p = (df[0] * df[0] + df[1] * df[1]) + (df[2] * df[2] + df[3] * df[3]);
     if (is_finite(p)) loss_fx += to_fixed(p, VQ_LOSS_SHIFT);
     else bad += 1;
+    if (out.seg) {
+        unsigned poison = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) seg_add(out.seg + (int64_t)code * kD + m + 8 * i, df[i], poison);
+        if (poison) atomicAdd(out.seg + (int64_t)K * kD + code, 1ull);
+    }
 }
 
 // Everything behind the filter in one launch:
@@ -501,7 +515,6 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m = lane & 7;
     const float4* zn4 = reinterpret_cast<const float4*>(zn32);
-    const float4* en4 = reinterpret_cast<const float4*>(en32);
     unsigned ties = 0, multi = 0, bad = 0;
     long long loss_fx = 0;
     // ---------------- phase A ----------------
@@ -556,7 +569,7 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
                 if (top.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) ++ties;
                 if (n_cells > 1) ++multi;
             }
-            if (out.zq) finish_chunk(zn4, en4, out, row, code, m, loss_fx, bad);
+            if (out.zq) finish_lane(zn32, en32, out, K, row, code, m, loss_fx, bad);
         }
     }
     // ---------------- phase B ----------------
@@ -612,7 +625,7 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
                     if (out.hist) atomicAdd(out.hist + code, 1);
                     if (fin.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) ++ties;
                     if (out.zq)
-                        for (int chunk = 0; chunk < kD / 4; ++chunk) finish_chunk(zn4, en4, out, row, code, chunk, loss_fx, bad);
+                        for (int mm = 0; mm < 8; ++mm) finish_lane(zn32, en32, out, K, row, code, mm, loss_fx, bad);
                     done[i] = 0;                   // ready for the next call
                 }
             }
@@ -677,14 +690,16 @@ cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T
 // (degenerate inputs only) are left in cand[] = -1 for the caller's overflow path.
 cudaError_t launch_exact_finish16(const void* records, const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
                                   const int* flagged, const int* n_flagged, int* done_counters, void* partial_ws, int* cand,
-                                  float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* stats, cudaStream_t s) {
+                                  float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats,
+                                  cudaStream_t s) {
     const int cap = (int)(T < kFlaggedCap ? T : kFlaggedCap);
     const int rows_per_block = tc16::kExactThreads / 8;
     int64_t blocks = (T + rows_per_block - 1) / rows_per_block;
     const int64_t grid_cap = (int64_t)sm_count() * 16 * 2;       // resident blocks, two passes
     if (blocks > grid_cap) blocks = grid_cap;
     tc16::FinishOut out;
-    out.zq = reinterpret_cast<float4*>(zq_tok); out.idx = idx_out; out.hist = hist;
+    out.zq = zq_tok; out.idx = idx_out; out.hist = hist;
+    out.seg = zq_tok ? reinterpret_cast<unsigned long long*>(seg_sums) : nullptr;
     tc16::k_exact_finish16<<<(unsigned)blocks, tc16::kExactThreads, 0, s>>>(
         static_cast<const int4*>(records), zn32, row_sq, cb.en32, reinterpret_cast<const float4*>(cb.en32c), cb.csq_cell, (int)T,
         cb.K, flagged, n_flagged, cap, static_cast<tc16::FlaggedPartial*>(partial_ws), done_counters, cand, out, stats);

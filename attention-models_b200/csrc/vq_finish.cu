@@ -6,8 +6,9 @@
 //   models/vitvqgan.py:169      z_q = z + (z_q - z).detach()          models/vqgan.py:171
 //   models/vitvqgan.py:173-176  indices_to_embeddings                 models/vqgan.py:178-182
 // l2_norm(E[idx]) is bit-identical to the prepared unit code en[idx] (same row, same ATen schedule),
-// so the gather reads en32 directly.  HBM-bound and purely element-wise: one float4 per thread,
-// fully coalesced, grid-stride over T*D/4; algorithmic bytes 8D + 8 per token.
+// so the gather reads en32 directly.  HBM-bound and purely element-wise, fully coalesced; algorithmic bytes
+// 8D + 8 per token.  When the step trains the codebook the same pass also accumulates the
+// codebook-gradient segment sums (they only need q - zn, which is in registers here).
 #include "vq_common.cuh"
 #include "vq_kernels.h"
 #include "../../include/vq_b200.h"
@@ -29,61 +30,80 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
     return t;   // valid in thread 0
 }
 
-// chunks = D/4 float4 per row.  Element e is float4 (e % chunks) of row e / chunks; a thread owns kUnroll
-// elements one grid-stride apart so that their loads are all in flight before the first use.
-template <int kUnroll>
-__global__ void __launch_bounds__(256) k_finish(const float4* __restrict__ zn, const int* __restrict__ cand,
-                                                const float4* __restrict__ en, int64_t T, int chunks, int K,
-                                                float4* __restrict__ zq, int64_t* __restrict__ idx_out,
-                                                int32_t* __restrict__ hist, int64_t* __restrict__ stats) {
+// A warp walks the (T x D) array in spans of 128 consecutive floats; lane l owns elements l, l + 32, l + 64, l + 96
+// of a span, so every load / store instruction of the warp is one coalesced 128-byte access and every segment-sum
+// RED instruction covers 256 contiguous bytes of int64 (whole 32-byte sectors).  kSpans spans are in flight per warp.
+template <int kSpans>
+__global__ void __launch_bounds__(256) k_finish(const float* __restrict__ zn, const int* __restrict__ cand,
+                                                const float* __restrict__ en, int64_t T, int D, int log2d, int K,
+                                                float* __restrict__ zq, int64_t* __restrict__ idx_out,
+                                                int32_t* __restrict__ hist, unsigned long long* __restrict__ seg,
+                                                int64_t* __restrict__ stats) {
     __shared__ unsigned long long red[8];
-    const int64_t total = T * chunks;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     long long loss_fx = 0;
     unsigned long long bad = 0;
-    for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += stride * kUnroll) {
-        int k[kUnroll], c[kUnroll];
-        int64_t t[kUnroll];
-        float4 a[kUnroll], q[kUnroll];
-#pragma unroll
-        for (int i = 0; i < kUnroll; ++i) {
-            const int64_t e = e0 + i * stride;
-            t[i] = e / chunks;
-            c[i] = (int)(e - t[i] * chunks);
-            k[i] = (e < total) ? (__ldg(cand + t[i]) & (kCandExactBit - 1)) : 0;
+    if (!zq) {   // indices only: one thread per row
+        for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
+            const int k = __ldg(cand + t) & (kCandExactBit - 1);
+            idx_out[t] = k;
+            if (hist) atomicAdd(hist + k, 1);
         }
-        if (zq) {
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t total = T << log2d;
+    const int64_t n_spans = (total + 127) >> 7;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t sp = warp; sp < n_spans; sp += n_warps * kSpans) {
+        int k[kSpans][4];
+        float a[kSpans][4], q[kSpans][4];
 #pragma unroll
-            for (int i = 0; i < kUnroll; ++i) {
-                const int64_t e = e0 + i * stride;
+        for (int j = 0; j < kSpans; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t e = ((sp + j * n_warps) << 7) + lane + 32 * i;
+                k[j][i] = (e < total) ? (__ldg(cand + (e >> log2d)) & (kCandExactBit - 1)) : 0;
+            }
+#pragma unroll
+        for (int j = 0; j < kSpans; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t e = ((sp + j * n_warps) << 7) + lane + 32 * i;
+                a[j][i] = 0.f; q[j][i] = 0.f;
                 if (e < total) {
-                    a[i] = __ldcs(zn + e);
-                    q[i] = __ldg(en + (int64_t)k[i] * chunks + c[i]);
+                    a[j][i] = __ldcs(zn + e);
+                    q[j][i] = __ldg(en + ((int64_t)k[j][i] << log2d) + (e & (D - 1)));
                 }
             }
-        }
 #pragma unroll
-        for (int i = 0; i < kUnroll; ++i) {
-            const int64_t e = e0 + i * stride;
-            if (e >= total) break;
-            if (c[i] == 0) {
-                idx_out[t[i]] = k[i];
-                if (hist) atomicAdd(hist + k[i], 1);
+        for (int j = 0; j < kSpans; ++j) {
+            float df[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t e = ((sp + j * n_warps) << 7) + lane + 32 * i;
+                df[i] = 0.f;
+                if (e < total) {
+                    const int c = (int)(e & (D - 1));
+                    if (c == 0) {
+                        idx_out[e >> log2d] = k[j][i];
+                        if (hist) atomicAdd(hist + k[j][i], 1);
+                    }
+                    df[i] = __fsub_rn(q[j][i], a[j][i]);
+                    __stcs(zq + e, __fadd_rn(a[j][i], df[i]));
+                    if (seg) {
+                        unsigned poison = 0;
+                        seg_add(seg + ((int64_t)k[j][i] << log2d) + c, df[i], poison);
+                        if (poison) atomicAdd(seg + ((int64_t)K << log2d) + k[j][i], 1ull);
+                    }
+                }
             }
-            if (zq) {
-                float4 df, o;
-                df.x = __fsub_rn(q[i].x, a[i].x); df.y = __fsub_rn(q[i].y, a[i].y);
-                df.z = __fsub_rn(q[i].z, a[i].z); df.w = __fsub_rn(q[i].w, a[i].w);
-                o.x = __fadd_rn(a[i].x, df.x); o.y = __fadd_rn(a[i].y, df.y);
-                o.z = __fadd_rn(a[i].z, df.z); o.w = __fadd_rn(a[i].w, df.w);
-                __stcs(zq + e, o);
-                const float p = (df.x * df.x + df.y * df.y) + (df.z * df.z + df.w * df.w);
-                if (is_finite(p)) loss_fx += to_fixed(p, VQ_LOSS_SHIFT);
-                else bad += 1;
-            }
+            const float p = (df[0] * df[0] + df[1] * df[1]) + (df[2] * df[2] + df[3] * df[3]);
+            if (is_finite(p)) loss_fx += to_fixed(p, VQ_LOSS_SHIFT);
+            else bad += 1;
         }
     }
-    if (zq && stats) {
+    if (stats) {
         const unsigned long long s1 = block_sum_u64((unsigned long long)loss_fx, red);
         __syncthreads();
         const unsigned long long s2 = block_sum_u64(bad, red);
@@ -95,27 +115,29 @@ __global__ void __launch_bounds__(256) k_finish(const float4* __restrict__ zn, c
 }
 
 cudaError_t launch_finish(const float* zn32, const int* cand, const CodebookView& cb, int64_t T, float* zq_tok,
-                          int64_t* idx_out, int32_t* hist, int64_t* stats, cudaStream_t s) {
+                          int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats, cudaStream_t s) {
     if (T == 0) return cudaSuccess;
-    const int chunks = zq_tok ? cb.D / 4 : 1;   // indices-only: one thread per row is enough
-    const int64_t total = T * chunks;
-    constexpr int kUnroll = 4;
-    int64_t blocks = (total + 256 * kUnroll - 1) / (256 * kUnroll);
+    constexpr int kSpans = 2;
+    int log2d = 0;
+    while ((1 << log2d) < cb.D) ++log2d;
+    // z_q pass: a warp per kSpans spans of 128 floats; indices only: one thread per row
+    const int64_t work = zq_tok ? ((T * cb.D + 127) / 128 + kSpans - 1) / kSpans : (T + 31) / 32;
+    int64_t blocks = (work + 7) / 8;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    k_finish<kUnroll><<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(zn32), cand,
-                                             reinterpret_cast<const float4*>(cb.en32), T, chunks, cb.K,
-                                             reinterpret_cast<float4*>(zq_tok), idx_out, hist, stats);
+    k_finish<kSpans><<<(unsigned)blocks, 256, 0, s>>>(zn32, cand, cb.en32, T, cb.D, log2d, cb.K, zq_tok, idx_out, hist,
+                                                      zq_tok ? reinterpret_cast<unsigned long long*>(seg_sums) : nullptr, stats);
     count_launch();
     return cudaGetLastError();
 }
 
 // One warp per listed row: same outputs as k_finish for rows [row_begin, *n_rows) of `rows`.
 __global__ void __launch_bounds__(256) k_finish_listed(const float4* __restrict__ zn, const int* __restrict__ cand,
-                                                       const float4* __restrict__ en, int chunks, const int* __restrict__ rows,
-                                                       const int* __restrict__ n_rows, int64_t row_begin,
-                                                       float4* __restrict__ zq, int64_t* __restrict__ idx_out,
-                                                       int32_t* __restrict__ hist, int64_t* __restrict__ stats) {
+                                                       const float4* __restrict__ en, int chunks, int K,
+                                                       const int* __restrict__ rows, const int* __restrict__ n_rows,
+                                                       int64_t row_begin, float4* __restrict__ zq,
+                                                       int64_t* __restrict__ idx_out, int32_t* __restrict__ hist,
+                                                       unsigned long long* __restrict__ seg, int64_t* __restrict__ stats) {
     const int lane = threadIdx.x & 31;
     const int64_t n = *n_rows;
     long long loss_fx = 0;
@@ -137,6 +159,13 @@ __global__ void __launch_bounds__(256) k_finish_listed(const float4* __restrict_
                 const float p = (df.x * df.x + df.y * df.y) + (df.z * df.z + df.w * df.w);
                 if (is_finite(p)) loss_fx += to_fixed(p, VQ_LOSS_SHIFT);
                 else bad += 1;
+                if (seg) {
+                    unsigned poison = 0;
+                    unsigned long long* slot = seg + ((int64_t)k * chunks + c) * 4;
+                    seg_add(slot + 0, df.x, poison); seg_add(slot + 1, df.y, poison);
+                    seg_add(slot + 2, df.z, poison); seg_add(slot + 3, df.w, poison);
+                    if (poison) atomicAdd(seg + (int64_t)K * chunks * 4 + k, 1ull);
+                }
             }
     }
     if (zq && stats && (loss_fx != 0 || bad != 0)) {
@@ -147,13 +176,14 @@ __global__ void __launch_bounds__(256) k_finish_listed(const float4* __restrict_
 
 cudaError_t launch_finish_listed(const float* zn32, const int* cand, const CodebookView& cb, int64_t T, const int* rows,
                                  const int* n_rows, int64_t row_begin, float* zq_tok, int64_t* idx_out, int32_t* hist,
-                                 int64_t* stats, cudaStream_t s) {
+                                 int64_t* seg_sums, int64_t* stats, cudaStream_t s) {
     if (T <= row_begin) return cudaSuccess;
     int64_t blocks = (T - row_begin + 7) / 8;
     if (blocks > sm_count() * 4) blocks = sm_count() * 4;
     k_finish_listed<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(zn32), cand,
-                                                    reinterpret_cast<const float4*>(cb.en32), cb.D / 4, rows, n_rows, row_begin,
-                                                    reinterpret_cast<float4*>(zq_tok), idx_out, hist, stats);
+                                                    reinterpret_cast<const float4*>(cb.en32), cb.D / 4, cb.K, rows, n_rows,
+                                                    row_begin, reinterpret_cast<float4*>(zq_tok), idx_out, hist,
+                                                    zq_tok ? reinterpret_cast<unsigned long long*>(seg_sums) : nullptr, stats);
     count_launch();
     return cudaGetLastError();
 }

@@ -60,7 +60,8 @@ constexpr int kFlaggedCap = 4096;     // listed rows that get the sliced per-row
 // exact rescoring of the filter's records + sliced search of the listed rows + the finish pass, one launch
 cudaError_t launch_exact_finish16(const void* records, const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
                                   const int* flagged, const int* n_flagged, int* done_counters, void* partial_ws, int* cand,
-                                  float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* stats, cudaStream_t s);
+                                  float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats,
+                                  cudaStream_t s);
 
 // ---- vq_dist_tc.cu ---------------------------------------------------------------------------
 // tcgen05 search: cand[row] = cell id (or exact index for rows resolved in-kernel); rows it cannot
@@ -72,13 +73,14 @@ cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* r
                            cudaStream_t s);
 
 // ---- vq_finish.cu ----------------------------------------------------------------------------
-// idx / hist / z_q (token-major) / loss partial from final indices in cand[].
+// idx / hist / z_q (token-major) / loss partial from final indices in cand[]; with seg_sums (K*D + K int64, not
+// zeroed here) also the codebook-gradient segment sums S_k += fixed(q_k - zn_t) as integer reductions.
 cudaError_t launch_finish(const float* zn32, const int* cand, const CodebookView& cb, int64_t T,
-                          float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* stats, cudaStream_t s);
+                          float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats, cudaStream_t s);
 // finish pass for the listed rows [row_begin, *n_rows) only (overflow of the D = 32 per-row fallback)
 cudaError_t launch_finish_listed(const float* zn32, const int* cand, const CodebookView& cb, int64_t T, const int* rows,
                                  const int* n_rows, int64_t row_begin, float* zq_tok, int64_t* idx_out, int32_t* hist,
-                                 int64_t* stats, cudaStream_t s);
+                                 int64_t* seg_sums, int64_t* stats, cudaStream_t s);
 cudaError_t launch_loss_finalize(const int64_t* stats, int64_t n_elem_total, int form, float beta, float* loss,
                                  cudaStream_t s);
 cudaError_t launch_gather(const int64_t* idx, int64_t T, int64_t hw, const float* table, int K, int D,
@@ -93,6 +95,17 @@ cudaError_t launch_segment_sums(const float* zn32, const int64_t* idx, const int
                                 int64_t T, int64_t* seg_sums, void* ws, size_t ws_bytes, cudaStream_t s);
 cudaError_t launch_codebook_grad(const int64_t* seg_sums, const CodebookView& cb, float coef, const float* g_loss,
                                  float* grad_weight, cudaStream_t s);
+
+// ---- vq_peer.cu ------------------------------------------------------------------------------
+// byte layout of one rank's exchange buffer (see vq_peer.cu); offsets of stats / hist are relative to the slot
+struct ExchangeLayout {
+    size_t seg_bytes, stats_off, hist_off, slot_bytes, slot0_off, total;
+};
+ExchangeLayout exchange_layout(int K, int D);
+cudaError_t launch_codebook_grad_sharded(const void* const* peer_bufs, int world, int rank, int slot, unsigned epoch,
+                                         const CodebookView& cb, float coef, const float* g_loss, int64_t n_elem_total,
+                                         int form, float beta, float* grad_weight, int64_t* hist_total, float* loss,
+                                         int64_t* stats_total, cudaStream_t s);
 
 // dispatch on the supported codebook dims (powers of two in [16, 512])
 inline bool has_cell_layout(int K, int D) { return D == 32 && K >= 512 && (K % 512) == 0; }

@@ -14,11 +14,13 @@ LIB_PATH = os.environ.get("VQ_B200_LIB") or os.path.join(_PKG_DIR, "lib", "libvq
 BUILD_SCRIPT = os.path.join(_PKG_DIR, "csrc", "build.py")
 
 # constants mirrored from include/vq_b200.h
-ABI_VERSION = 1
+ABI_VERSION = 2
 FORM_VIT, FORM_VQGAN = 0, 1
 LAYOUT_TOKEN_MAJOR, LAYOUT_NCHW = 0, 1
 FLAG_INDICES_ONLY, FLAG_EXACT_SCAN, FLAG_KEEP_STATS = 1, 2, 4
 STAT_NEAR_TIE_ROWS, STAT_AMBIGUOUS_ROWS, STAT_FALLBACK_ROWS, STAT_LOSS_FIXED, STAT_BAD_INDEX, STAT_NONFINITE = range(6)
+STAT_PEER_TIMEOUT = 6
+PEER_MAX_RANKS, IPC_HANDLE_BYTES = 16, 64
 STATS_LEN = 8
 SEG_SHIFT = 30
 
@@ -32,8 +34,8 @@ SIGNATURES = {
     "vq_codebook_prepare": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "vq_workspace_bytes": (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_size_t)]),
     "vq_forward": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int64,
-                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
-                           c_void_p]),
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_size_t, c_void_p]),
     "vq_loss_finalize": (c_int, [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]),
     "vq_backward_workspace_bytes": (c_int, [c_int64, c_int, c_int, POINTER(c_size_t)]),
     "vq_backward_tokens": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -41,6 +43,15 @@ SIGNATURES = {
                                    c_size_t, c_void_p]),
     "vq_backward_codebook": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_void_p,
                                      c_void_p]),
+    "vq_exchange_bytes": (c_int, [c_int, c_int, POINTER(c_size_t)]),
+    "vq_exchange_slot": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]),
+    "vq_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "vq_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "vq_peer_close": (c_int, [c_void_p]),
+    "vq_peer_free": (c_int, [c_void_p]),
+    "vq_backward_codebook_sharded": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, ctypes.c_uint32, c_void_p, c_int, c_int,
+                                             c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p]),
     "vq_gather": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                           c_void_p, c_void_p]),
     "vq_profile_begin": (c_int, []),

@@ -28,6 +28,8 @@ class _CodebookBase(nn.Module):
         self.beta = beta
         self.embedding = nn.Embedding(self.codebook_size, self.codebook_dim)
         self.exact_scan = False          # True forces the exhaustive fp32 search (no tensor cores)
+        self.sorted_segments = False     # True: codebook-gradient sums bucketed by code in the backward (skew-insensitive)
+                                         # instead of integer reductions from the forward's finish pass; same bits
         self.last_histogram: Optional[torch.Tensor] = None
         self.last_stats: Optional[torch.Tensor] = None
         self._prepared: Optional[F_vq.PreparedCodebook] = None
@@ -43,7 +45,8 @@ class _CodebookBase(nn.Module):
     def _quantise(self, z: torch.Tensor):
         z_q, flat_idx, loss, hist, stats = F_vq.quantise(z, self.embedding.weight, self.form, self.beta,
                                                          prepared=self._prepared_codebook(),
-                                                         exact_scan=self.exact_scan)
+                                                         exact_scan=self.exact_scan,
+                                                         sorted_segments=self.sorted_segments)
         self.last_histogram, self.last_stats = hist, stats
         return z_q, flat_idx, loss
 

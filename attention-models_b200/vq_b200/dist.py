@@ -1,21 +1,31 @@
 """Token-sharded quantiser step for N GPUs of one box (one process per GPU, torch.distributed).
 
 Rows (tokens) are independent, so each rank quantises its own shard against the replicated codebook and
-forward / encode / decode need no collective.  The backward has exactly one exchange: a single
-all-reduce(sum) of one packed **int64** buffer
+forward / encode / decode need no collective.  The backward has exactly one exchange: the sum over ranks of
 
     [ codebook-gradient segment sums (K*D, fixed point 2^-30) | non-finite counts per code (K)
     | code-usage histogram (K) | loss partial (fixed point 2^-24) | non-finite loss partials ]
 
-Integer sums are exact and order-free, so the all-reduced result -- and therefore grad_weight, the
+all of them **integers**: sums are exact and order-free, so the result -- and therefore grad_weight, the
 histogram and the loss -- is bit-identical to the single-GPU result on the concatenated batch, whatever
-the world size or NCCL algorithm.  This equals the reference's DDP semantics (mean over ranks of
+the world size or the order of the additions.  This equals the reference's DDP semantics (mean over ranks of
 per-rank mean-loss gradients, trainers/vitgqgan.py:184 + trainers/utils/base_trainer.py:29-33) when
 shards are equal, because every rank normalises by the global element count.
+
+Two implementations of the exchange:
+
+* ``exchange="peer"`` (default on CUDA): every rank's forward writes its partials into an exchange buffer that
+  all peers map through CUDA IPC; ONE kernel per rank (`vq_backward_codebook_sharded`) publishes a flag, waits
+  for the peers' flags, pulls their partials over NVLink, adds them and applies the codebook gradient.  The
+  partials depend on neither the upstream gradient nor d(loss), so the kernel is launched on a side stream
+  right after the forward and overlaps the token backward.
+* ``exchange="collective"``: one `all_reduce(SUM)` of the packed int64 buffer (NCCL on GPUs; gloo in the CPU
+  tests of the host logic), then the single-GPU codebook-gradient kernel.
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+import ctypes
+from typing import Dict, List, Optional
 
 import torch
 import torch.distributed as dist
@@ -46,7 +56,8 @@ class PackedReduce:
 
     def fill_side_channels(self, buf: torch.Tensor, hist_i32: torch.Tensor, stats: torch.Tensor) -> None:
         self.hist(buf).copy_(hist_i32)
-        self.loss_pair(buf).copy_(stats[[STAT_LOSS_FIXED, STAT_NONFINITE]])
+        assert STAT_NONFINITE == STAT_LOSS_FIXED + 2
+        self.loss_pair(buf).copy_(stats[STAT_LOSS_FIXED:STAT_NONFINITE + 1:2])
 
     def all_reduce(self, buf: torch.Tensor, group=None) -> torch.Tensor:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -55,8 +66,7 @@ class PackedReduce:
 
     def stats_from(self, buf: torch.Tensor) -> torch.Tensor:
         st = torch.zeros(STATS_LEN, dtype=torch.int64, device=buf.device)
-        st[STAT_LOSS_FIXED] = self.loss_pair(buf)[0]
-        st[STAT_NONFINITE] = self.loss_pair(buf)[1]
+        st[STAT_LOSS_FIXED:STAT_NONFINITE + 1:2] = self.loss_pair(buf)
         return st
 
 
@@ -69,26 +79,86 @@ def shard_batch(x: torch.Tensor, rank: int, world_size: int) -> torch.Tensor:
     return x[rank * per:(rank + 1) * per]
 
 
+class PeerExchange:
+    """Exchange buffers of all ranks of `group`, mapped into this process (CUDA IPC over NVLink).
+
+    `torch.distributed` only carries the 64-byte IPC handles at set-up; the data path is the library's own
+    kernel reading peer memory."""
+
+    def __init__(self, K: int, D: int, device: torch.device, group=None):
+        lib = _lib.load()
+        self.K, self.D, self.device, self.group = K, D, device, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > _lib.PEER_MAX_RANKS:
+            raise ValueError(f"peer exchange supports at most {_lib.PEER_MAX_RANKS} ranks")
+        self.nbytes = _lib.size_query("vq_exchange_bytes", K, D)
+        self.epoch = 0
+        own, handle = ctypes.c_void_p(), ctypes.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        with torch.cuda.device(device):
+            _lib.check(lib.vq_peer_alloc(self.nbytes, ctypes.byref(own), handle))
+            handles: List[Optional[bytes]] = [None] * self.world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            self.ptrs: List[int] = []
+            for r in range(self.world):
+                if r == self.rank:
+                    self.ptrs.append(own.value)
+                else:
+                    p = ctypes.c_void_p()
+                    _lib.check(lib.vq_peer_open(ctypes.create_string_buffer(handles[r], _lib.IPC_HANDLE_BYTES), ctypes.byref(p)))
+                    self.ptrs.append(p.value)
+        self.ptr_array = (ctypes.c_void_p * self.world)(*self.ptrs)
+        self._slots = [self._slot_pointers(s) for s in (0, 1)]
+        dist.barrier(group=group)          # every rank mapped every buffer before the first kernel publishes into it
+
+    def _slot_pointers(self, slot: int):
+        seg, stats, hist = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(_lib.load().vq_exchange_slot(self.ptrs[self.rank], self.K, self.D, slot, ctypes.byref(seg),
+                                                ctypes.byref(stats), ctypes.byref(hist)))
+        return seg.value, stats.value, hist.value
+
+    def next_step(self):
+        """-> (slot, epoch, seg_ptr, stats_ptr, hist_ptr) of the step about to run."""
+        self.epoch += 1
+        slot = (self.epoch - 1) & 1
+        return (slot, self.epoch) + self._slots[slot]
+
+    def close(self) -> None:
+        if not self.ptrs:
+            return
+        lib = _lib.load()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)     # nobody still reads a buffer that is about to be unmapped / freed
+        with torch.cuda.device(self.device):
+            for r, p in enumerate(self.ptrs):
+                if r != self.rank:
+                    _lib.check(lib.vq_peer_close(p))
+            dist.barrier(group=self.group)
+            _lib.check(lib.vq_peer_free(self.ptrs[self.rank]))
+        self.ptrs = []
+
+
 class ShardedQuantiser:
-    """fwd + bwd of one shard through the C ABI, with the packed all-reduce when world_size > 1.
+    """fwd + bwd of one shard through the C ABI, with the one exchange of the backward when world_size > 1.
 
     ``step(z_local, upstream_local, weight)`` returns a dict with z_q, indices, loss (global), grad_z,
-    grad_weight (global, identical on every rank), histogram (global, int64) and stats.
+    grad_weight (global, identical on every rank), histogram (global) and stats.
     """
 
     def __init__(self, form: str = "vit", beta: float = 0.25, world_size: Optional[int] = None,
-                 exact_scan: bool = False, group=None):
+                 exact_scan: bool = False, group=None, exchange: str = "peer"):
         self.form, self.beta, self.group, self.exact_scan = form, float(beta), group, exact_scan
         if world_size is None:
             world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-        self.world_size = world_size
-        self._plans: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        if exchange not in ("peer", "collective"):
+            raise ValueError("exchange must be 'peer' or 'collective'")
+        self.world_size, self.exchange = world_size, exchange
+        self._plans: Dict[tuple, Dict[str, object]] = {}
 
     @staticmethod
     def uses_tensor_cores(T: int, K: int, D: int) -> bool:
         return bool(_lib.load().vq_uses_tensor_cores(T, K, D))
 
-    def _plan(self, z: torch.Tensor, K: int, D: int, T: int, flags: int) -> Dict[str, torch.Tensor]:
+    def _plan(self, z: torch.Tensor, K: int, D: int, T: int, flags: int) -> Dict[str, object]:
         """Buffers of one (shape, device) are allocated once and reused by every later step: the step
         itself then costs a handful of ctypes calls and no allocator traffic.  Outputs of step() are
         views of these buffers and are overwritten by the next step() with the same shape."""
@@ -108,14 +178,26 @@ class ShardedQuantiser:
                 "idx": torch.empty(T, dtype=torch.int64, device=dev),
                 "loss": torch.empty(1, dtype=torch.float32, device=dev),
                 "hist": torch.empty(K, dtype=torch.int32, device=dev),
+                "hist_total": torch.empty(K, dtype=torch.int64, device=dev),
                 "stats": torch.empty(STATS_LEN, dtype=torch.int64, device=dev),
                 "zn": torch.empty(T, D, dtype=torch.float32, device=dev),
                 "denom": torch.empty(T, dtype=torch.float32, device=dev),
                 "grad_w": torch.empty(K, D, dtype=torch.float32, device=dev),
                 "buf": pack.allocate(dev),
             }
+            if self.world_size > 1 and self.exchange == "peer":
+                plan["peer"] = PeerExchange(K, D, dev, self.group)
+                plan["side"] = torch.cuda.Stream(dev)
+                plan["ev_fwd"], plan["ev_x"] = torch.cuda.Event(), torch.cuda.Event()
             self._plans[key] = plan
         return plan
+
+    def close(self) -> None:
+        """Unmap / free the peer exchange buffers (collective: every rank must call it)."""
+        for plan in self._plans.values():
+            if "peer" in plan:
+                plan["peer"].close()
+        self._plans.clear()
 
     def step(self, z: torch.Tensor, upstream: Optional[torch.Tensor], weight: torch.Tensor) -> Dict[str, torch.Tensor]:
         from .functional import FORMS, LAYOUT_NCHW, LAYOUT_TOKEN_MAJOR, _ptr, _require_cuda, _stream, _token_geometry
@@ -135,24 +217,43 @@ class ShardedQuantiser:
         if not w.is_contiguous():
             w = w.contiguous()
         up = None if upstream is None else upstream.contiguous()
-        cb, seg = _ptr(p["cb"]), _ptr(buf)          # the segment sums are the head of the packed buffer
+        cb = _ptr(p["cb"])
+        peer: Optional[PeerExchange] = p.get("peer")
         with torch.cuda.device(dev):
             s = _stream(dev)
+            if peer is not None:
+                slot, epoch, seg, stats_ptr, hist_ptr = peer.next_step()
+            else:
+                seg, stats_ptr, hist_ptr = _ptr(buf), _ptr(p["stats"]), _ptr(p["hist"])   # seg sums head the packed buffer
             _lib.check(lib.vq_codebook_prepare(_ptr(w), K, D, cb, p["cb_bytes"], s))
             _lib.check(lib.vq_forward(_ptr(z), layout, T, hw, cb, K, D, form_id, self.beta, flags, n_total,
-                                      _ptr(p["z_q"]), _ptr(p["idx"]), None, _ptr(p["hist"]), _ptr(p["stats"]),
-                                      _ptr(p["zn"]), _ptr(p["denom"]), _ptr(p["fws"]), p["fws_bytes"], s))
+                                      _ptr(p["z_q"]), _ptr(p["idx"]), None, hist_ptr, stats_ptr,
+                                      _ptr(p["zn"]), _ptr(p["denom"]), seg, _ptr(p["fws"]), p["fws_bytes"], s))
+            if peer is not None:
+                # the exchange needs nothing of the backward: it runs beside the token backward
+                side = p["side"]
+                p["ev_fwd"].record()
+                side.wait_event(p["ev_fwd"])
+                _lib.check(lib.vq_backward_codebook_sharded(peer.ptr_array, peer.world, peer.rank, slot, epoch, cb, K, D,
+                                                            form_id, self.beta, None, n_total, _ptr(p["grad_w"]),
+                                                            _ptr(p["hist_total"]), _ptr(p["loss"]), _ptr(p["stats"]),
+                                                            side.cuda_stream))
+                p["ev_x"].record(side)
             _lib.check(lib.vq_backward_tokens(_ptr(up), layout, T, hw, _ptr(p["zn"]), _ptr(p["denom"]), _ptr(p["idx"]),
-                                              _ptr(p["hist"]), cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_z"]), seg,
+                                              None, cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_z"]), None,
                                               _ptr(p["bws"]), p["bws_bytes"], s))
-            if self.world_size > 1:
-                pack.fill_side_channels(buf, p["hist"], p["stats"])
-                pack.all_reduce(buf, self.group)
-                red_stats = pack.stats_from(buf)
-                hist_out = pack.hist(buf)
+            if peer is not None:
+                torch.cuda.current_stream(dev).wait_event(p["ev_x"])
+                hist_out = p["hist_total"]
             else:
-                red_stats, hist_out = p["stats"], p["hist"]
-            _lib.check(lib.vq_loss_finalize(_ptr(red_stats), n_total, form_id, self.beta, _ptr(p["loss"]), s))
-            _lib.check(lib.vq_backward_codebook(seg, cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_w"]), s))
+                if self.world_size > 1:
+                    pack.fill_side_channels(buf, p["hist"], p["stats"])
+                    pack.all_reduce(buf, self.group)
+                    red_stats = pack.stats_from(buf)
+                    hist_out = pack.hist(buf)
+                else:
+                    red_stats, hist_out = p["stats"], p["hist"]
+                _lib.check(lib.vq_loss_finalize(_ptr(red_stats), n_total, form_id, self.beta, _ptr(p["loss"]), s))
+                _lib.check(lib.vq_backward_codebook(seg, cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_w"]), s))
         return {"z_q": p["z_q"], "indices": p["idx"], "loss": p["loss"].view(()), "grad_z": p["grad_z"],
                 "grad_weight": p["grad_w"], "histogram": hist_out, "stats": p["stats"]}

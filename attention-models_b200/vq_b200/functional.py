@@ -79,7 +79,7 @@ class _Quantise(torch.autograd.Function):
     """(z, weight) -> (z_q, flat indices, loss, histogram, stats) with the straight-through backward."""
 
     @staticmethod
-    def forward(ctx, z, weight, prepared, form, beta, layout, flags, n_elem_total):
+    def forward(ctx, z, weight, prepared, form, beta, layout, flags, n_elem_total, sorted_segments):
         lib = _lib.load()
         dev = z.device
         K, D = prepared.K, prepared.D
@@ -93,14 +93,19 @@ class _Quantise(torch.autograd.Function):
         stats = torch.empty(STATS_LEN, dtype=torch.int64, device=dev)
         saved_zn = torch.empty(T, D, dtype=torch.float32, device=dev) if need_grad else None
         saved_denom = torch.empty(T, dtype=torch.float32, device=dev) if need_grad else None
+        # codebook-gradient segment sums: accumulated by the forward's finish pass (it holds q - zn), unless the
+        # caller asks for the bucketed sum of the backward (sorted_segments; same integers, skew-insensitive)
+        seg = (torch.empty(K * D + K, dtype=torch.int64, device=dev)
+               if ctx.needs_input_grad[1] and not sorted_segments else None)
         ws_bytes = _lib.size_query("vq_workspace_bytes", T, K, D, flags)
         ws = _scratch(ws_bytes, dev)
         with torch.cuda.device(dev):
             _lib.check(lib.vq_forward(_ptr(z), layout, T, hw, _ptr(prepared.blob), K, D, form, float(beta), flags,
                                       n_total, _ptr(z_q), _ptr(idx), _ptr(loss), _ptr(hist), _ptr(stats),
-                                      _ptr(saved_zn), _ptr(saved_denom), _ptr(ws), ws_bytes, _stream(dev)))
+                                      _ptr(saved_zn), _ptr(saved_denom), _ptr(seg), _ptr(ws), ws_bytes, _stream(dev)))
         if need_grad:
             ctx.save_for_backward(saved_zn, saved_denom, idx, prepared.blob, hist)
+        ctx.seg = seg
         ctx.meta = (form, float(beta), layout, T, hw, K, D, n_total, tuple(z.shape))
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(idx, hist, stats)
@@ -118,7 +123,9 @@ class _Quantise(torch.autograd.Function):
             g_zq = g_zq.contiguous().float()
         g_loss = torch.zeros(1, dtype=torch.float32, device=dev) if g_loss is None else g_loss.reshape(1).float()
         grad_z = torch.empty(z_shape, dtype=torch.float32, device=dev) if want_z else None
-        seg = torch.empty(K * D + K, dtype=torch.int64, device=dev) if want_w else None
+        seg, from_forward = ctx.seg, ctx.seg is not None
+        if want_w and seg is None:
+            seg = torch.empty(K * D + K, dtype=torch.int64, device=dev)
         grad_w = torch.empty(K, D, dtype=torch.float32, device=dev) if want_w else None
         ws_bytes = _lib.size_query("vq_backward_workspace_bytes", T, K, D)
         ws = _scratch(ws_bytes, dev)
@@ -126,11 +133,11 @@ class _Quantise(torch.autograd.Function):
             s = _stream(dev)
             _lib.check(lib.vq_backward_tokens(_ptr(g_zq), layout, T, hw, _ptr(saved_zn), _ptr(saved_denom), _ptr(idx),
                                               _ptr(hist), _ptr(blob), K, D, form, beta, _ptr(g_loss), n_total, _ptr(grad_z),
-                                              _ptr(seg), _ptr(ws), ws_bytes, s))
+                                              None if from_forward or not want_w else _ptr(seg), _ptr(ws), ws_bytes, s))
             if want_w:
                 _lib.check(lib.vq_backward_codebook(_ptr(seg), _ptr(blob), K, D, form, beta, _ptr(g_loss), n_total,
                                                     _ptr(grad_w), s))
-        return grad_z, grad_w, None, None, None, None, None, None
+        return grad_z, grad_w, None, None, None, None, None, None, None
 
 
 def _as_fp32_input(z: torch.Tensor) -> torch.Tensor:
@@ -143,7 +150,7 @@ def _as_fp32_input(z: torch.Tensor) -> torch.Tensor:
 
 def quantise(z: torch.Tensor, weight: torch.Tensor, form: str = "vit", beta: float = 0.25,
              prepared: Optional[PreparedCodebook] = None, exact_scan: bool = False,
-             n_elem_total: Optional[int] = None):
+             n_elem_total: Optional[int] = None, sorted_segments: bool = False):
     """Full forward.  Returns ``(z_q, flat_indices, loss, histogram, stats)``.
 
     ``z``: (..., D) for ``form='vit'`` (token-major) or (b, D, h, w) for ``form='vqgan'``.
@@ -155,7 +162,8 @@ def quantise(z: torch.Tensor, weight: torch.Tensor, form: str = "vit", beta: flo
         prepared = prepare_codebook(weight)
     layout = LAYOUT_TOKEN_MAJOR if form == "vit" else LAYOUT_NCHW
     flags = FLAG_EXACT_SCAN if exact_scan else 0
-    return _Quantise.apply(_as_fp32_input(z), weight, prepared, FORMS[form], beta, layout, flags, n_elem_total)
+    return _Quantise.apply(_as_fp32_input(z), weight, prepared, FORMS[form], beta, layout, flags, n_elem_total,
+                           sorted_segments)
 
 
 @torch.no_grad()
@@ -179,7 +187,7 @@ def encode_indices(z: torch.Tensor, weight: torch.Tensor, form: str = "vit",
     ws = _scratch(ws_bytes, dev)
     with torch.cuda.device(dev):
         _lib.check(lib.vq_forward(_ptr(z), layout, T, hw, _ptr(prepared.blob), K, D, FORMS[form], 0.25, flags,
-                                  max(T * D, 1), None, _ptr(idx), None, _ptr(hist), None, None, None, _ptr(ws),
+                                  max(T * D, 1), None, _ptr(idx), None, _ptr(hist), None, None, None, None, _ptr(ws),
                                   ws_bytes, _stream(dev)))
     return (idx, hist) if want_hist else idx
 

@@ -188,7 +188,7 @@ def run_b200(args):
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     zs = [torch.randn(IMGS_PER_GPU, TOKENS_PER_IMG, DIM, device=dev, generator=g) for _ in range(n_sets)]
     ups = [torch.randn(IMGS_PER_GPU, TOKENS_PER_IMG, DIM, device=dev, generator=g) for _ in range(n_sets)]
-    stepper = vq_dist.ShardedQuantiser("vit", BETA, world_size=world, exact_scan=args.exact_scan)
+    stepper = vq_dist.ShardedQuantiser("vit", BETA, world_size=world, exact_scan=args.exact_scan, exchange=args.exchange)
 
     def one_step(i):
         z = zs[i % n_sets]
@@ -265,10 +265,13 @@ def run_b200(args):
                "ms_per_step": e_ms, "note": "vq_host_step: pinned host in/out, all outputs (z_q, idx, loss, grad_z, "
                                             "grad_weight) copied back every step"}
 
+    peer_timeouts = int(out["stats"][_lib.STAT_PEER_TIMEOUT].item()) if world > 1 and args.exchange == "peer" else 0
+    stepper.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    assert peer_timeouts == 0, "a peer never published its step (exchange kernel timed out)"
 
     # ---- roofline of the dominant kernel (nearest-code search) -------------------------------------
     flops_per_launch = 2.0 * K_CODES * DIM * T
@@ -313,7 +316,8 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "K": K_CODES, "D": DIM, "tokens_per_gpu": T, "global_tokens": T * world,
-                       "parallelism": f"tokens sharded over {world} GPU(s), codebook replicated",
+                       "parallelism": f"tokens sharded over {world} GPU(s), codebook replicated"
+                                      + (f"; backward exchange: {'fused peer-memory kernel over NVLink (CUDA IPC)' if args.exchange == 'peer' else 'NCCL all-reduce of the packed int64 buffer'}" if world > 1 else ""),
                        "l2": f"inputs rotate over {n_sets} resident sets ({n_sets * 2 * T * DIM * 4 >> 20} MiB) > 126 MB L2; "
                              "a step's own working set is 130 MB"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.value),
@@ -333,6 +337,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sets", type=int, default=4, help="resident input sets rotated between steps")
     ap.add_argument("--exact-scan", action="store_true", help="force the exhaustive fp32 SIMT search")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "collective"],
+                    help="N > 1: fused peer-memory exchange kernel (default) or one NCCL all-reduce")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()

@@ -10,7 +10,8 @@
  *
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in _host
- *   - all arrays are caller-allocated; the library owns no device memory
+ *   - all arrays are caller-allocated; the library owns no device memory (vq_peer_alloc allocates the
+ *     IPC-exportable exchange buffer on the caller's explicit request; the caller frees it)
  *   - every call is asynchronous on `stream` (a cudaStream_t) and re-entrant per stream
  *   - return value: 0 = OK, non-zero = error; vq_last_error() gives the message (thread-local)
  *   - nothing throws across the ABI; there is NO CPU fallback: without a CUDA device every compute
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 1
+#define VQ_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define VQ_API __attribute__((visibility("default")))
@@ -47,8 +48,8 @@ extern "C" {
 /* flags for vq_forward */
 #define VQ_FLAG_INDICES_ONLY 1    /* encode_imgs fast path: only idx (and hist) are produced   */
 #define VQ_FLAG_EXACT_SCAN   2    /* force the exhaustive fp32 SIMT search (no tensor cores)   */
-#define VQ_FLAG_KEEP_STATS   4    /* hist and stats accumulate (the caller zeroed them once): one
-                                     batch can be streamed through in token chunks               */
+#define VQ_FLAG_KEEP_STATS   4    /* hist, stats and seg_sums accumulate (the caller zeroed them once):
+                                     one batch can be streamed through in token chunks           */
 
 /* error codes */
 #define VQ_OK            0
@@ -64,6 +65,7 @@ extern "C" {
 #define VQ_STAT_LOSS_FIXED      3 /* sum over tokens of sum_j (q - zn)^2, fixed point 2^-24      */
 #define VQ_STAT_BAD_INDEX       4 /* vq_gather: count of out-of-range indices                    */
 #define VQ_STAT_NONFINITE       5 /* non-finite loss partials (NaN/Inf rows): the loss is NaN     */
+#define VQ_STAT_PEER_TIMEOUT    6 /* vq_backward_codebook_sharded: a peer never published its step  */
 #define VQ_STATS_LEN            8
 
 VQ_API int         vq_abi_version(void);
@@ -98,12 +100,18 @@ VQ_API int vq_codebook_prepare(const float* weight, int K, int D, void* cb, size
  * stats       : VQ_STATS_LEN int64 (overwritten), or NULL.
  * saved_zn    : T*D floats, token-major unit rows kept for vq_backward, or NULL.
  * saved_denom : T floats max(||z_t||, eps) kept for vq_backward, or NULL.
+ * seg_sums    : K*D + K int64, or NULL.  The codebook-gradient segment sums S_k = sum_{t: idx_t = k} (q_k - zn_t)
+ *               at fixed-point scale 2^30, followed by K per-code counts of non-finite terms -- what
+ *               vq_backward_codebook consumes.  They depend on neither the upstream gradient nor g_loss, so a
+ *               training step accumulates them here, in the pass that already holds q - zn (64-bit integer
+ *               reductions: exact, order-free, deterministic), and a token-sharded job can start their exchange
+ *               before the backward.  Overwritten unless VQ_FLAG_KEEP_STATS.
  * ws          : scratch of at least vq_workspace_bytes(T, K, D, flags).                            */
 VQ_API int vq_workspace_bytes(int64_t T, int K, int D, int flags, size_t* out);
 VQ_API int vq_forward(const float* z, int layout, int64_t T, int64_t hw,
                const void* cb, int K, int D, int form, float beta, int flags, int64_t n_elem_total,
                float* z_q, int64_t* idx, float* loss, int32_t* hist, int64_t* stats,
-               float* saved_zn, float* saved_denom,
+               float* saved_zn, float* saved_denom, int64_t* seg_sums,
                void* ws, size_t ws_bytes, void* stream);
 
 /* loss = the reference's two-term expression from the fixed-point sum (after an all-reduce). */
@@ -115,10 +123,12 @@ VQ_API int vq_loss_finalize(const int64_t* loss_fixed, int64_t n_elem_total, int
  *   g_zn = G + g_loss*c1*2(zn - q)/N ; grad_z = NB(z, g_zn)
  *   S_k  = sum_{t: idx_t = k} (q_k - zn_t)          (deterministic segmented sum, fixed point)
  *   grad_E[k] = NB(E_k, g_loss*c2*(2/N) S_k)        c1,c2 = (beta,1) ViT / (1,beta) VQGAN
- * vq_backward_tokens writes grad_z (layout of z) and the int64 fixed-point segment sums
- * `seg_sums` (K*D sums at scale 2^30 followed by K per-code counts of non-finite contributions;
- * K*D + K int64 in all, overwritten).  A token-sharded job all-reduces seg_sums (integer sum:
- * exact, order-free) before vq_backward_codebook; one GPU calls them back to back.
+ * vq_backward_tokens writes grad_z (layout of z) and, if asked (seg_sums != NULL; not needed when
+ * vq_forward already produced them), the int64 fixed-point segment sums from idx alone: tokens are
+ * bucketed by code and every bucket summed in a fixed order (K*D sums at scale 2^30 followed by K
+ * per-code counts of non-finite contributions; K*D + K int64 in all, overwritten; bit-identical to
+ * vq_forward's).  A token-sharded job adds the seg_sums of all ranks (integer sum: exact, order-free)
+ * before vq_backward_codebook; one GPU calls them back to back.
  * g_zq may be NULL (no upstream gradient through z_q); grad_z / seg_sums may be NULL (not wanted).
  * hist: the K int32 code-usage counts vq_forward wrote for the same idx (saves a recount), or NULL.
  * g_loss: DEVICE pointer to d(objective)/d(loss) (what autograd hands over), NULL means 1.0.       */
@@ -131,6 +141,36 @@ VQ_API int vq_backward_tokens(const float* g_zq, int layout, int64_t T, int64_t 
                        void* ws, size_t ws_bytes, void* stream);
 VQ_API int vq_backward_codebook(const int64_t* seg_sums, const void* cb, int K, int D, int form, float beta,
                          const float* g_loss, int64_t n_elem_total, float* grad_weight, void* stream);
+
+/* ---- token-sharded job: the backward's one exchange, fused with the codebook gradient -------------
+ * Replaces DDP's all-reduce of codebook.embedding.weight.grad (trainers/vitgqgan.py:184,
+ * trainers/utils/base_trainer.py:29-33) for one process per GPU on one NVSwitch box.  Every rank owns an
+ * exchange buffer of vq_exchange_bytes(K, D) bytes that all peers map (CUDA IPC):
+ *   vq_peer_alloc   cudaMalloc + zero + export: *dev_ptr and a 64-byte IPC handle to send to the peers
+ *   vq_peer_open    map a peer's handle (enables NVLink peer access); vq_peer_close unmaps it
+ *   vq_peer_free    free the own buffer (after every peer closed it)
+ * A buffer holds two slots (step parity); vq_exchange_slot gives, for `slot`, the device pointers to pass to
+ * vq_forward as seg_sums / stats / hist so that the forward writes its partials straight into the buffer.
+ * vq_backward_codebook_sharded then runs ONE kernel per rank that publishes "step `epoch` ready" to the
+ * peers, waits for theirs, reads every rank's integer partials over NVLink, adds them (exact, order-free:
+ * all ranks get bit-identical totals) and writes grad_weight (K*D), the global histogram (K int64, or
+ * NULL), the global loss (or NULL) and the summed stats (VQ_STATS_LEN int64, or NULL).
+ * peer_bufs: HOST array of `world` device pointers, peer_bufs[rank] the own buffer; world <=
+ * VQ_PEER_MAX_RANKS.  `epoch` must increase by one per call (same value on all ranks, first call 1) and
+ * `slot` = (epoch - 1) & 1.  n_elem_total is the GLOBAL element count.  world = 1 needs no peers.       */
+#define VQ_PEER_MAX_RANKS 16
+#define VQ_IPC_HANDLE_BYTES 64
+VQ_API int vq_exchange_bytes(int K, int D, size_t* out);
+VQ_API int vq_exchange_slot(void* exchange_buf, int K, int D, int slot, int64_t** seg_sums, int64_t** stats,
+                            int32_t** hist);
+VQ_API int vq_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out);
+VQ_API int vq_peer_open(const void* ipc_handle, void** dev_ptr);
+VQ_API int vq_peer_close(void* dev_ptr);
+VQ_API int vq_peer_free(void* dev_ptr);
+VQ_API int vq_backward_codebook_sharded(const void* const* peer_bufs, int world, int rank, int slot, uint32_t epoch,
+                                        const void* cb, int K, int D, int form, float beta, const float* g_loss,
+                                        int64_t n_elem_total, float* grad_weight, int64_t* hist_total, float* loss,
+                                        int64_t* stats_total, void* stream);
 
 /* ---- decode --------------------------------------------------------------------------------
  * Replaces Codebook.indices_to_embeddings: models/vitvqgan.py:173-176 (normalise=1, token-major)

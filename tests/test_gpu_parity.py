@@ -401,3 +401,80 @@ def test_host_buffer_step_equals_device_step(dev, T):
         assert torch.equal(o_gw, ref["grad_weight"].cpu())
         assert float(o_loss) == float(ref["loss"])
         o_zq.zero_(); o_gz.zero_(); o_idx.zero_(); o_gw.zero_(); o_loss.zero_()
+
+
+@pytest.mark.parametrize("form,K,D,shape", [("vit", 8192, 32, (40, 1000, 32)), ("vit", 1024, 32, (3, 100, 32)),
+                                            ("vit", 512, 64, (4, 300, 64)), ("vqgan", 1024, 256, (2, 256, 16, 16)),
+                                            ("vit", 256, 16, (5, 77, 16))])
+def test_segment_sums_from_forward_equal_bucketed_sums(dev, form, K, D, shape):
+    """The codebook-gradient segment sums accumulated by the forward's finish pass (64-bit integer reductions)
+    and the bucketed fixed-order sums of the backward are the same integers: grad_weight is bit-identical,
+    on random and on collapsed (3 hot codes) usage."""
+    w = vo.make_codebook(form, K, D, 60)
+    for collapsed in (False, True):
+        if collapsed:
+            g = torch.Generator().manual_seed(61)
+            n = int(torch.tensor(shape).prod()) // D
+            rows = vo.unit_rows(w)[torch.randint(0, 3, (n,), generator=g)] + 0.02 * torch.randn(n, D, generator=g)
+            z = rows.view(shape) if form == "vit" else rows.view(shape[0], shape[2], shape[3], D).permute(0, 3, 1, 2).contiguous()
+        else:
+            z = vo.make_latents(shape, 62)
+        grads = []
+        for sorted_segments in (False, True):
+            m = _module(form, K, D, 0.25, w.to(dev), dev, False)
+            m.sorted_segments = sorted_segments
+            zz = z.to(dev).requires_grad_(True)
+            z_q, idx, loss = m(zz)
+            (z_q.sum() + loss).backward()
+            grads.append((m.embedding.weight.grad.clone(), zz.grad.clone(), loss.detach().clone()))
+        for a, b in zip(*grads):
+            assert torch.equal(a, b)
+
+
+def test_sharded_codebook_kernel_world_1_equals_plain_path(dev):
+    """vq_backward_codebook_sharded with one rank (no peers): reads the exchange slot the forward wrote and must
+    reproduce vq_backward_codebook + vq_loss_finalize bit for bit; both slots, increasing epochs."""
+    import ctypes
+    from vq_b200 import _lib
+    from vq_b200 import dist as vq_dist
+    from vq_b200.functional import _scratch
+    lib = _lib.load()
+    K, D, beta, T = 1024, 32, 0.25, 4096
+    w = vo.make_codebook("vit", K, D, 70).to(dev)
+    own, handle = ctypes.c_void_p(), ctypes.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+    nbytes = _lib.size_query("vq_exchange_bytes", K, D)
+    _lib.check(lib.vq_peer_alloc(nbytes, ctypes.byref(own), handle))
+    try:
+        ptrs = (ctypes.c_void_p * 1)(own.value)
+        cb = _scratch(_lib.size_query("vq_codebook_bytes", K, D), dev)
+        fws_bytes = _lib.size_query("vq_workspace_bytes", T, K, D, 0)
+        fws = _scratch(fws_bytes, dev)
+        s = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.vq_codebook_prepare(w.data_ptr(), K, D, cb.data_ptr(), cb.numel(), s))
+        for epoch in (1, 2, 3):
+            z = vo.make_latents((T, D), 70 + epoch).to(dev)
+            ref = vq_dist.ShardedQuantiser("vit", beta, world_size=1).step(z, None, w)
+            slot = (epoch - 1) & 1
+            seg, st, hist = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+            _lib.check(lib.vq_exchange_slot(own.value, K, D, slot, ctypes.byref(seg), ctypes.byref(st), ctypes.byref(hist)))
+            z_q, idx = torch.empty_like(z), torch.empty(T, dtype=torch.int64, device=dev)
+            zn, dn = torch.empty_like(z), torch.empty(T, device=dev)
+            _lib.check(lib.vq_forward(z.data_ptr(), 0, T, 0, cb.data_ptr(), K, D, 0, beta, 0, T * D, z_q.data_ptr(),
+                                      idx.data_ptr(), None, hist.value, st.value, zn.data_ptr(), dn.data_ptr(), seg.value,
+                                      fws.data_ptr(), fws_bytes, s))
+            gw, loss = torch.empty(K, D, device=dev), torch.empty(1, device=dev)
+            hist_total = torch.empty(K, dtype=torch.int64, device=dev)
+            stats_total = torch.empty(_lib.STATS_LEN, dtype=torch.int64, device=dev)
+            _lib.check(lib.vq_backward_codebook_sharded(ptrs, 1, 0, slot, epoch, cb.data_ptr(), K, D, 0, beta, None, T * D,
+                                                        gw.data_ptr(), hist_total.data_ptr(), loss.data_ptr(),
+                                                        stats_total.data_ptr(), s))
+            torch.cuda.synchronize()
+            assert torch.equal(idx, ref["indices"]) and torch.equal(z_q, ref["z_q"])
+            assert torch.equal(gw, ref["grad_weight"])
+            assert float(loss) == float(ref["loss"])
+            assert torch.equal(hist_total, ref["histogram"].to(torch.int64))
+            assert int(stats_total[_lib.STAT_PEER_TIMEOUT]) == 0
+            assert int(stats_total[_lib.STAT_LOSS_FIXED]) == int(ref["stats"][_lib.STAT_LOSS_FIXED])
+    finally:
+        torch.cuda.synchronize()
+        _lib.check(lib.vq_peer_free(own.value))
