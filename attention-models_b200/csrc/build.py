@@ -37,21 +37,25 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False, instrument: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, instrument: bool = False, defines=(), suffix: str = "") -> str:
     """instrument=True builds lib/libvq_b200_instr.so with -DVQ_TC_INSTRUMENT (wait-cycle counters in the
     tensor-core kernel; diagnostic only, selected with VQ_B200_LIB=<path>)."""
     os.makedirs(LIB_DIR, exist_ok=True)
     global LIB
     lib_path = LIB.replace(".so", "_instr.so") if instrument else LIB
+    if suffix:      # experiment builds: extra -D flags, selected at run time with VQ_B200_LIB=<path>
+        lib_path = LIB.replace(".so", f"_{suffix}.so")
+    tag = "_instr" if instrument else (f"_{suffix}" if suffix else "")
+    extra = [f"-D{d}" for d in defines]
     stamp = lib_path.replace(".so", ".stamp")
-    digest = _digest()
+    digest = _digest() + "".join(extra)
     if not force and os.path.exists(lib_path) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return lib_path
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIB_DIR, src.replace(".cu", "_instr.o" if instrument else ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, *(["-DVQ_TC_INSTRUMENT"] if instrument else []), "-c", os.path.join(HERE, src), "-o", obj]
+        obj = os.path.join(LIB_DIR, src.replace(".cu", tag + ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, *(["-DVQ_TC_INSTRUMENT"] if instrument else []), *extra, "-c", os.path.join(HERE, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -75,4 +79,7 @@ def build(force: bool = False, verbose: bool = False, instrument: bool = False) 
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, instrument="--instrument" in sys.argv))
+    _defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    _suffix = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--suffix=")), "")
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, instrument="--instrument" in sys.argv,
+                defines=_defs, suffix=_suffix))

@@ -178,19 +178,26 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
     float* zn32 = saved_zn ? saved_zn : w.zn32;
     float* denom = saved_denom ? saved_denom : w.denom;
     int64_t* st = stats ? stats : w.stats;
-    if (!(flags & VQ_FLAG_KEEP_STATS)) {
-        VQ_CUDA(cudaMemsetAsync(st, 0, sizeof(int64_t) * VQ_STATS_LEN, s));
-        if (hist) VQ_CUDA(cudaMemsetAsync(hist, 0, sizeof(int32_t) * (size_t)K, s));
-        if (seg_sums) VQ_CUDA(cudaMemsetAsync(seg_sums, 0, sizeof(int64_t) * ((size_t)K * D + K), s));
-    }
-
     const bool use_tc = !(flags & VQ_FLAG_EXACT_SCAN) && vq::tc_supported(T, K, D);
     __half* zn16 = use_tc ? w.zn16 : nullptr;
+    const bool tc16 = use_tc && vq::tc16_supported(T, K, D);
+
+    // 0. buffers the call accumulates into, cleared by the first kernel (no memset nodes)
+    vq::ZeroList zl = {};
+    int nz = 0;
+    auto zero = [&](void* p, size_t bytes) { zl.ptr[nz] = p; zl.bytes[nz] = bytes; ++nz; };
+    if (use_tc) zero(w.n_flagged, sizeof(int) * (tc16 ? 64 + vq::kFlaggedCap : 64));
+    if (!(flags & VQ_FLAG_KEEP_STATS)) {
+        zero(st, sizeof(int64_t) * VQ_STATS_LEN);
+        if (hist) zero(hist, sizeof(int32_t) * (size_t)K);
+        if (seg_sums) zero(seg_sums, sizeof(int64_t) * ((size_t)K * D + K));
+    }
 
     // 1. unit rows (ATen-order norms), fp16 copy for the tensor cores
     if (layout == VQ_LAYOUT_TOKEN_MAJOR) {
-        VQ_CUDA(vq::launch_prep_tokens(z, T, D, zn32, w.row_sq, denom, zn16, s));
+        VQ_CUDA(vq::launch_prep_tokens(z, T, D, zn32, w.row_sq, denom, zn16, zl, s));
     } else {
+        if (nz) VQ_CUDA(vq::launch_zero_ranges(zl, s));
         VQ_CUDA(vq::launch_norm_nchw(z, T, hw, D, denom, s));
         VQ_CUDA(vq::launch_nchw_to_tok(z, T, hw, D, denom, zn32, zn16, s));
         VQ_CUDA(vq::launch_row_sumsq(zn32, T, D, w.row_sq, s));
@@ -199,11 +206,10 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
     // 2. nearest code per row, 3. idx, hist, z_q, loss partial
     float* zq_tok = indices_only ? nullptr : (layout == VQ_LAYOUT_NCHW ? w.zq_tok : z_q);
     SearchTimer timer(s);
-    if (use_tc && vq::tc16_supported(T, K, D)) {
+    if (tc16) {
         // D = 32: tensor-core filter -> records; one kernel then does the exact rescoring, the sliced search of
         // the undecided rows and the finish pass.  Undecided rows beyond kFlaggedCap (degenerate inputs) overflow
         // into the generic exhaustive kernel + a listed finish; both leave at once when there are none.
-        VQ_CUDA(cudaMemsetAsync(w.n_flagged, 0, sizeof(int) * (64 + vq::kFlaggedCap), s));
         VQ_CUDA(vq::launch_dist_tc(zn16, zn32, w.row_sq, cbv, T, w.cand, w.flagged, w.n_flagged, st, w.tc_ws, s));
         timer.stop();
         SearchTimer exact_timer(s, &g_exact_events);
@@ -211,13 +217,13 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
                                           nullptr, zq_tok, idx, hist, seg_sums, st, s));
         exact_timer.stop();
         if (T > vq::kFlaggedCap) {
-            VQ_CUDA(vq::launch_scan_listed_tail(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, vq::kFlaggedCap, w.cand, st, s));
-            VQ_CUDA(vq::launch_finish_listed(zn32, w.cand, cbv, T, w.flagged, w.n_flagged, vq::kFlaggedCap, zq_tok, idx, hist,
-                                             seg_sums, st, s));
+            vq::ListedFinish fin;
+            fin.zq = zq_tok; fin.idx = idx; fin.hist = hist;
+            fin.seg = zq_tok ? reinterpret_cast<unsigned long long*>(seg_sums) : nullptr;
+            VQ_CUDA(vq::launch_scan_listed_tail(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, vq::kFlaggedCap, w.cand, st, fin, s));
         }
     } else {
         if (use_tc) {
-            VQ_CUDA(cudaMemsetAsync(w.n_flagged, 0, sizeof(int) * 64, s));
             VQ_CUDA(vq::launch_dist_tc(zn16, zn32, w.row_sq, cbv, T, w.cand, w.flagged, w.n_flagged, st, w.tc_ws, s));
             VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, T, w.cand, st, w.scan_ws, s));
         } else {
@@ -287,13 +293,16 @@ int vq_backward_tokens(const float* g_zq, int layout, int64_t T, int64_t hw, con
 }
 
 int vq_backward_codebook(const int64_t* seg_sums, const void* cb, int K, int D, int form, float beta,
-                         const float* g_loss, int64_t n_elem_total, float* grad_weight, void* stream) {
+                         const float* g_loss, int64_t n_elem_total, float* grad_weight, const int64_t* stats, float* loss,
+                         void* stream) {
     if (int r = check_dims(0, K, D)) return r;
     if (!seg_sums || !cb || !grad_weight || n_elem_total <= 0) return fail(VQ_ERR_ARG, "bad argument to vq_backward_codebook");
     vq::CodebookView cbv = vq::codebook_view(const_cast<void*>(cb), K, D);
     const float c2 = (form == VQ_FORM_VIT) ? 1.f : beta;
     const float coef = (float)((double)c2 * 2.0 / (double)n_elem_total);
-    VQ_CUDA(vq::launch_codebook_grad(seg_sums, cbv, coef, g_loss, grad_weight, static_cast<cudaStream_t>(stream)));
+    if (loss && !stats) return fail(VQ_ERR_ARG, "loss needs stats");
+    VQ_CUDA(vq::launch_codebook_grad(seg_sums, cbv, coef, g_loss, grad_weight, stats, n_elem_total, form, beta, loss,
+                                     static_cast<cudaStream_t>(stream)));
     return VQ_OK;
 }
 
@@ -557,9 +566,12 @@ int vq_host_step(const float* z_host, const float* g_zq_host, int64_t T, const f
             VQ_CUDA(cudaMemcpyAsync(grad_z_host + t0 * D, a.gz + t0 * D, row_bytes * n, cudaMemcpyDeviceToHost, p.out));
     }
     // ---- whole-batch tail: loss and codebook gradient from the accumulated fixed-point sums ----
-    if (loss_host) VQ_CUDA(vq::launch_loss_finalize(a.stats, n_elem, form, beta, a.loss, s));
-    if (grad_weight_host)   // the chunks' forwards accumulated the integer segment sums of the whole batch
-        if (int r = vq_backward_codebook(a.seg, a.cb, K, D, form, beta, nullptr, n_elem, a.gw, s)) return r;
+    if (grad_weight_host) {   // the chunks' forwards accumulated the integer segment sums of the whole batch
+        if (int r = vq_backward_codebook(a.seg, a.cb, K, D, form, beta, nullptr, n_elem, a.gw, a.stats, loss_host ? a.loss : nullptr, s))
+            return r;
+    } else if (loss_host) {
+        VQ_CUDA(vq::launch_loss_finalize(a.stats, n_elem, form, beta, a.loss, s));
+    }
     VQ_CUDA(cudaEventRecord(p.tail, s));
     VQ_CUDA(cudaStreamWaitEvent(p.out, p.tail, 0));
     if (loss_host) VQ_CUDA(cudaMemcpyAsync(loss_host, a.loss, sizeof(float), cudaMemcpyDeviceToHost, p.out));

@@ -329,7 +329,10 @@ template <int D>
 __global__ void __launch_bounds__(256) k_codebook_grad(const long long* __restrict__ seg_sums,
                                                        const float* __restrict__ en, const float* __restrict__ code_denom,
                                                        int K, float coef_base, const float* __restrict__ g_loss,
-                                                       float* __restrict__ grad) {
+                                                       float* __restrict__ grad, const int64_t* __restrict__ stats,
+                                                       int64_t n_elem_total, int form, float beta, float* __restrict__ loss) {
+    if (loss && blockIdx.x == 0 && threadIdx.x == 0)
+        loss[0] = loss_from_fixed(stats[VQ_STAT_LOSS_FIXED], stats[VQ_STAT_NONFINITE], n_elem_total, form, beta);
     const float coef = coef_base * (g_loss ? __ldg(g_loss) : 1.f);
     constexpr int kPer = (D + 31) / 32;
     const int lane = threadIdx.x & 31;
@@ -361,12 +364,14 @@ __global__ void __launch_bounds__(256) k_codebook_grad(const long long* __restri
 }
 
 cudaError_t launch_codebook_grad(const int64_t* seg_sums, const CodebookView& cb, float coef, const float* g_loss,
-                                 float* grad_weight, cudaStream_t s) {
+                                 float* grad_weight, const int64_t* stats, int64_t n_elem_total, int form, float beta,
+                                 float* loss, cudaStream_t s) {
     int blocks = (cb.K + 7) / 8;
     const int cap = sm_count() * 8;
     if (blocks > cap) blocks = cap;
     VQ_DISPATCH_D(cb.D, (k_codebook_grad<kD><<<blocks, 256, 0, s>>>(reinterpret_cast<const long long*>(seg_sums),
-                                                                      cb.en32, cb.code_denom, cb.K, coef, g_loss, grad_weight)));
+                                                                      cb.en32, cb.code_denom, cb.K, coef, g_loss, grad_weight,
+                                                                      stats, n_elem_total, form, beta, stats ? loss : nullptr)));
     count_launch();
     return cudaGetLastError();
 }

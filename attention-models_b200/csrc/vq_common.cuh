@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "vq_kernels.h"
+
 #define VQ_NORM_EPS 1e-12f          // F.normalize eps (torch/nn/functional.py:5707-5708)
 #define VQ_SEG_SHIFT 30              // fixed-point scale of the codebook-gradient segment sums
 #define VQ_LOSS_SHIFT 24             // fixed-point scale of the per-row loss sums
@@ -145,6 +147,48 @@ __device__ __forceinline__ long long to_fixed(float v, int shift) {
 __device__ __forceinline__ void seg_add(unsigned long long* __restrict__ slot, float d, unsigned& poison) {
     if (is_finite(d)) atomicAdd(slot, (unsigned long long)to_fixed(d, VQ_SEG_SHIFT));
     else poison = 1;
+}
+
+// Buffers a forward zeroes before use (stats, histogram, segment sums, fallback-list counters), cleared by the
+// first kernel of the call instead of one memset node each.  Sizes in bytes, multiples of 4.
+__device__ __forceinline__ void zero_ranges(const ZeroList& zl) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n_thr = (size_t)gridDim.x * blockDim.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (!zl.ptr[i]) continue;
+        if (((reinterpret_cast<size_t>(zl.ptr[i]) | zl.bytes[i]) & 15) == 0) {
+            uint4* p = static_cast<uint4*>(zl.ptr[i]);
+            for (size_t j = tid; j < zl.bytes[i] / 16; j += n_thr) p[j] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            uint32_t* p = static_cast<uint32_t*>(zl.ptr[i]);
+            for (size_t j = tid; j < zl.bytes[i] / 4; j += n_thr) p[j] = 0u;
+        }
+    }
+}
+
+// cb.info: kInfoSlots per-block counts of codes whose |en|^2 is not ~1 (zero / non-finite rows), written by the
+// codebook preparation (every slot, no atomics, nothing to zero).  Any non-zero slot = degenerate codebook.
+constexpr int kInfoSlots = 64;
+__device__ __forceinline__ bool codebook_degenerate(const int* __restrict__ info) {
+    int any = 0;
+#pragma unroll
+    for (int i = 0; i < kInfoSlots / 4; ++i) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(info) + i);
+        any |= v.x | v.y | v.z | v.w;
+    }
+    return any != 0;
+}
+
+// loss = beta*m + m (ViT, models/vitvqgan.py:166) or m + beta*m (VQGAN, models/vqgan.py:169), m = mean((q - zn)^2)
+// from the fixed-point sum: both reference terms have the same value, only their gradients differ.  Non-finite
+// partials make the loss NaN.  `form`: 0 = ViT, 1 = VQGAN (VQ_FORM_*).
+__device__ __forceinline__ float loss_from_fixed(long long loss_fixed, long long nonfinite, long long n_elem_total, int form,
+                                                 float beta) {
+    const double sum = (double)loss_fixed / (double)(1ll << VQ_LOSS_SHIFT);
+    float m = (float)(sum / (double)n_elem_total);
+    if (nonfinite != 0) m = __int_as_float(0x7fc00000);
+    const float bm = __fmul_rn(beta, m);
+    return (form == 0) ? __fadd_rn(bm, m) : __fadd_rn(m, bm);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

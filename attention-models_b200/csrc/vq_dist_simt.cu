@@ -30,6 +30,31 @@ __device__ __forceinline__ void best_insert(Best& b, float d, int i) {
     else if (d < b.d2 || d != d) b.d2 = d;
 }
 
+// Finish pass of one listed row by one thread (the overflow rows of the D = 32 fallback list: degenerate inputs
+// only): idx / hist / z_q / loss partial / segment sums, same expressions as vq_finish.cu.
+__device__ __forceinline__ void finish_row_serial(const float* __restrict__ zn32, const float* __restrict__ en32, int D, int K,
+                                                  int row, int code, const ListedFinish& fin, long long& loss_fx,
+                                                  unsigned long long& bad) {
+    fin.idx[row] = code;
+    if (fin.hist) atomicAdd(fin.hist + code, 1);
+    if (!fin.zq) return;
+    unsigned poison = 0;
+    for (int d0 = 0; d0 < D; d0 += 4) {
+        float df[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float a = __ldg(zn32 + (int64_t)row * D + d0 + i), q = __ldg(en32 + (int64_t)code * D + d0 + i);
+            df[i] = __fsub_rn(q, a);
+            fin.zq[(int64_t)row * D + d0 + i] = __fadd_rn(a, df[i]);
+            if (fin.seg) seg_add(fin.seg + (int64_t)code * D + d0 + i, df[i], poison);
+        }
+        const float p = (df[0] * df[0] + df[1] * df[1]) + (df[2] * df[2] + df[3] * df[3]);
+        if (is_finite(p)) loss_fx += to_fixed(p, VQ_LOSS_SHIFT);
+        else bad += 1;
+    }
+    if (poison) atomicAdd(fin.seg + (int64_t)K * D + code, 1ull);
+}
+
 __device__ __forceinline__ void best_merge(Best& a, float d1, int i1, float d2) {
     if (argmin_better(d1, i1, a.d1, a.i1)) {
         const float loser = a.d1;
@@ -53,7 +78,8 @@ __global__ void __launch_bounds__(256) k_scan_exact(const float* __restrict__ zn
                                                     const int* __restrict__ n_rows_ptr, int64_t row_begin,
                                                     int64_t row_end, int* __restrict__ cand,
                                                     float4* __restrict__ partial, int partial_cap,
-                                                    int* __restrict__ tile_done, int64_t* __restrict__ stats) {
+                                                    int* __restrict__ tile_done, int64_t* __restrict__ stats,
+                                                    ListedFinish fin) {
     __shared__ __align__(16) float zs[kDK][kTM + 4];
     __shared__ __align__(16) float es[kDK][kTN + 4];
     __shared__ int row_id[kTM];
@@ -61,6 +87,8 @@ __global__ void __launch_bounds__(256) k_scan_exact(const float* __restrict__ zn
 
     int64_t n_rows = rows ? (int64_t)(*n_rows_ptr) : T;
     if (n_rows > row_end) n_rows = row_end;
+    long long loss_fx = 0;
+    unsigned long long bad = 0;
     const int tid = threadIdx.x;
     int k_lo = 0, k_hi = K;
     if (partial) {
@@ -154,6 +182,7 @@ __global__ void __launch_bounds__(256) k_scan_exact(const float* __restrict__ zn
                     const float gap = best[r].d2 - best[r].d1;
                     if (stats && gap < VQ_NEAR_TIE_REL * fabsf(best[r].d1))
                         atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), 1ull);
+                    if (fin.idx) finish_row_serial(zn32, en32, D, K, rid, best[r].i1, fin, loss_fx, bad);
                 }
             }
         }
@@ -194,6 +223,10 @@ __global__ void __launch_bounds__(256) k_scan_exact(const float* __restrict__ zn
             }
         }
     }
+    if (fin.idx && fin.zq && stats) {
+        if (loss_fx) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_LOSS_FIXED), (unsigned long long)loss_fx);
+        if (bad) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NONFINITE), bad);
+    }
 }
 
 // [tile-done counters (one int per 64-row tile, 1 KiB)] [partials: splits x cap float4]
@@ -214,7 +247,7 @@ cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const Code
         int64_t blocks = (n + kTM - 1) / kTM;
         if (blocks > cap_blocks) blocks = cap_blocks;
         k_scan_exact<<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, 0,
-                                                     n, cand, nullptr, 0, nullptr, stats);
+                                                     n, cand, nullptr, 0, nullptr, stats, ListedFinish{});
         count_launch();
         return cudaGetLastError();
     }
@@ -233,27 +266,28 @@ cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const Code
     if (tiles > 16) tiles = 16;
     dim3 grid((unsigned)tiles, (unsigned)splits);
     k_scan_exact<<<grid, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, 0, cap, cand,
-                                      partial, cap, tile_done, stats);
+                                      partial, cap, tile_done, stats, ListedFinish{});
     count_launch();
     if (n > cap) {
         int64_t blocks = (n - cap + kTM - 1) / kTM;
         if (blocks > sm_count()) blocks = sm_count();
         k_scan_exact<<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, cap,
-                                                     n, cand, nullptr, 0, nullptr, stats);
+                                                     n, cand, nullptr, 0, nullptr, stats, ListedFinish{});
         count_launch();
     }
     return cudaGetLastError();
 }
 
-// listed rows [row_begin, *n_rows) without the code split (used behind the D = 32 per-row fallback)
+// listed rows [row_begin, *n_rows) without the code split, finished in the same launch (behind the D = 32 per-row
+// fallback: its overflow beyond kFlaggedCap; the blocks read the device-side row count and leave when there is none)
 cudaError_t launch_scan_listed_tail(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
                                     const int* rows, const int* n_rows, int64_t row_begin, int* cand, int64_t* stats,
-                                    cudaStream_t s) {
+                                    const ListedFinish& fin, cudaStream_t s) {
     int64_t blocks = (T - row_begin + kTM - 1) / kTM;
     if (blocks <= 0) return cudaSuccess;
     if (blocks > sm_count()) blocks = sm_count();
     k_scan_exact<<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, row_begin, T,
-                                                 cand, nullptr, 0, nullptr, stats);
+                                                 cand, nullptr, 0, nullptr, stats, fin);
     count_launch();
     return cudaGetLastError();
 }

@@ -316,7 +316,7 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(r_sub * kTileN);
         const uint32_t snap0 = smem_base + L.snap + (uint32_t)row_in_cta * kSnapRow;
         constexpr uint32_t kSnapArea = kRowsPerCta * kSnapRow;
-        const bool force_exhaustive = (cb_info[0] != 0);
+        const bool force_exhaustive = codebook_degenerate(cb_info);
         uint32_t phase = 0;                          // parity of t_full: flips once per group (2 tiles, 2 stages)
         int it = 0;
 #ifdef VQ_TC_INSTRUMENT

@@ -131,72 +131,11 @@ cudaError_t launch_finish(const float* zn32, const int* cand, const CodebookView
     return cudaGetLastError();
 }
 
-// One warp per listed row: same outputs as k_finish for rows [row_begin, *n_rows) of `rows`.
-__global__ void __launch_bounds__(256) k_finish_listed(const float4* __restrict__ zn, const int* __restrict__ cand,
-                                                       const float4* __restrict__ en, int chunks, int K,
-                                                       const int* __restrict__ rows, const int* __restrict__ n_rows,
-                                                       int64_t row_begin, float4* __restrict__ zq,
-                                                       int64_t* __restrict__ idx_out, int32_t* __restrict__ hist,
-                                                       unsigned long long* __restrict__ seg, int64_t* __restrict__ stats) {
-    const int lane = threadIdx.x & 31;
-    const int64_t n = *n_rows;
-    long long loss_fx = 0;
-    unsigned long long bad = 0;
-    for (int64_t i = row_begin + (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * 8) {
-        const int64_t t = rows[i];
-        const int k = __ldg(cand + t) & (kCandExactBit - 1);
-        if (lane == 0) {
-            idx_out[t] = k;
-            if (hist) atomicAdd(hist + k, 1);
-        }
-        if (zq)
-            for (int c = lane; c < chunks; c += 32) {
-                const float4 a = __ldg(zn + t * chunks + c), q = __ldg(en + (int64_t)k * chunks + c);
-                float4 df, o;
-                df.x = __fsub_rn(q.x, a.x); df.y = __fsub_rn(q.y, a.y); df.z = __fsub_rn(q.z, a.z); df.w = __fsub_rn(q.w, a.w);
-                o.x = __fadd_rn(a.x, df.x); o.y = __fadd_rn(a.y, df.y); o.z = __fadd_rn(a.z, df.z); o.w = __fadd_rn(a.w, df.w);
-                zq[t * chunks + c] = o;
-                const float p = (df.x * df.x + df.y * df.y) + (df.z * df.z + df.w * df.w);
-                if (is_finite(p)) loss_fx += to_fixed(p, VQ_LOSS_SHIFT);
-                else bad += 1;
-                if (seg) {
-                    unsigned poison = 0;
-                    unsigned long long* slot = seg + ((int64_t)k * chunks + c) * 4;
-                    seg_add(slot + 0, df.x, poison); seg_add(slot + 1, df.y, poison);
-                    seg_add(slot + 2, df.z, poison); seg_add(slot + 3, df.w, poison);
-                    if (poison) atomicAdd(seg + (int64_t)K * chunks * 4 + k, 1ull);
-                }
-            }
-    }
-    if (zq && stats && (loss_fx != 0 || bad != 0)) {
-        atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_LOSS_FIXED), (unsigned long long)loss_fx);
-        if (bad) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NONFINITE), bad);
-    }
-}
-
-cudaError_t launch_finish_listed(const float* zn32, const int* cand, const CodebookView& cb, int64_t T, const int* rows,
-                                 const int* n_rows, int64_t row_begin, float* zq_tok, int64_t* idx_out, int32_t* hist,
-                                 int64_t* seg_sums, int64_t* stats, cudaStream_t s) {
-    if (T <= row_begin) return cudaSuccess;
-    int64_t blocks = (T - row_begin + 7) / 8;
-    if (blocks > sm_count() * 4) blocks = sm_count() * 4;
-    k_finish_listed<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(zn32), cand,
-                                                    reinterpret_cast<const float4*>(cb.en32), cb.D / 4, cb.K, rows, n_rows,
-                                                    row_begin, reinterpret_cast<float4*>(zq_tok), idx_out, hist,
-                                                    zq_tok ? reinterpret_cast<unsigned long long*>(seg_sums) : nullptr, stats);
-    count_launch();
-    return cudaGetLastError();
-}
-
 // loss = beta*m + m (ViT) or m + beta*m (VQGAN), m = mean((q - zn)^2): both reference terms have the
 // same value, only their gradients differ.  stats[NONFINITE] counts non-finite partials -> NaN.
 __global__ void k_loss_finalize(const int64_t* __restrict__ stats, int64_t n_elem_total, int form, float beta,
                                 float* __restrict__ loss) {
-    const double sum = (double)stats[VQ_STAT_LOSS_FIXED] / (double)(1ll << VQ_LOSS_SHIFT);
-    float m = (float)(sum / (double)n_elem_total);
-    if (stats[VQ_STAT_NONFINITE] != 0) m = __int_as_float(0x7fc00000);
-    const float bm = __fmul_rn(beta, m);
-    loss[0] = (form == VQ_FORM_VIT) ? __fadd_rn(bm, m) : __fadd_rn(m, bm);
+    loss[0] = loss_from_fixed(stats[VQ_STAT_LOSS_FIXED], stats[VQ_STAT_NONFINITE], n_elem_total, form, beta);
 }
 
 cudaError_t launch_loss_finalize(const int64_t* stats, int64_t n_elem_total, int form, float beta, float* loss,

@@ -14,7 +14,7 @@ struct CodebookView {
     float* code_sq;     // K    sum(en^2) in ATen order (~1, 0 for zero codes)
     float* code_denom;  // K    max(||E_k||, eps)
     __half* en16;       // K*D  fp16 copy of en32 (tensor-core operand, TMA source)
-    int* info;          // [0] = number of codes whose |en|^2 is not ~1 (zero / non-finite rows)
+    int* info;          // 64 per-block counts of codes whose |en|^2 is not ~1 (zero / non-finite rows); any != 0: degenerate
     // D = 32, K % 512 == 0 only (else null): "cell" copies for the fp16-accumulator search.  A cell is the 8 codes
     // g*512 + hs + 64*m (m = 0..7) that share one slot of group g; cell id ci = g*64 + hs.
     float* en32c;       // K*D  [ci][q][m][4]: 16-byte chunk q of code m -- 8 lanes, one per code, read whole lines
@@ -29,9 +29,14 @@ constexpr int kCandExactBit = 0x40000000;  // cand[t] holds a final index, not a
 
 // ---- vq_prep.cu ------------------------------------------------------------------------------
 cudaError_t launch_prep_codebook(const float* weight, const CodebookView& cb, cudaStream_t s);
-// token-major rows -> zn32, row_sq, denom, zn16 (any output may be null)
+// token-major rows -> zn32, row_sq, denom, zn16 (any output may be null); also clears the buffers of `zl`
+struct ZeroList {
+    void* ptr[4];
+    unsigned long long bytes[4];
+};
 cudaError_t launch_prep_tokens(const float* z, int64_t T, int D, float* zn32, float* row_sq, float* denom,
-                               __half* zn16, cudaStream_t s);
+                               __half* zn16, const ZeroList& zl, cudaStream_t s);
+cudaError_t launch_zero_ranges(const ZeroList& zl, cudaStream_t s);
 // NCHW (b, D, hw): denominators in ATen's channel-strided order (schedule chosen from T, hw, D)
 cudaError_t launch_norm_nchw(const float* z, int64_t T, int64_t hw, int D, float* denom, cudaStream_t s);
 // (b, D, hw) -> (T, D), optionally divided by denom[t]; optional fp16 copy
@@ -50,9 +55,13 @@ cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const Code
                               const int* rows, const int* n_rows, int64_t max_rows, int* cand, int64_t* stats,
                               void* partial_ws, cudaStream_t s);
 
+// outputs of the finish pass for rows a search kernel finishes itself (all null: search only)
+struct ListedFinish {
+    float* zq = nullptr; int64_t* idx = nullptr; int32_t* hist = nullptr; unsigned long long* seg = nullptr;
+};
 cudaError_t launch_scan_listed_tail(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
                                     const int* rows, const int* n_rows, int64_t row_begin, int* cand, int64_t* stats,
-                                    cudaStream_t s);
+                                    const ListedFinish& fin, cudaStream_t s);
 
 // ---- vq_dist_tc16.cu (D = 32: fp16 accumulators, packed 16-bit maxima) ------------------------
 bool tc16_supported(int64_t T, int K, int D);
@@ -77,10 +86,6 @@ cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* r
 // zeroed here) also the codebook-gradient segment sums S_k += fixed(q_k - zn_t) as integer reductions.
 cudaError_t launch_finish(const float* zn32, const int* cand, const CodebookView& cb, int64_t T,
                           float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats, cudaStream_t s);
-// finish pass for the listed rows [row_begin, *n_rows) only (overflow of the D = 32 per-row fallback)
-cudaError_t launch_finish_listed(const float* zn32, const int* cand, const CodebookView& cb, int64_t T, const int* rows,
-                                 const int* n_rows, int64_t row_begin, float* zq_tok, int64_t* idx_out, int32_t* hist,
-                                 int64_t* seg_sums, int64_t* stats, cudaStream_t s);
 cudaError_t launch_loss_finalize(const int64_t* stats, int64_t n_elem_total, int form, float beta, float* loss,
                                  cudaStream_t s);
 cudaError_t launch_gather(const int64_t* idx, int64_t T, int64_t hw, const float* table, int K, int D,
@@ -93,8 +98,10 @@ cudaError_t launch_backward_tokens(const float* g_tok, const float* zn32, const 
                                    float* grad_tok, cudaStream_t s);
 cudaError_t launch_segment_sums(const float* zn32, const int64_t* idx, const int32_t* hist, const CodebookView& cb,
                                 int64_t T, int64_t* seg_sums, void* ws, size_t ws_bytes, cudaStream_t s);
+// grad_E from the segment sums; with `loss` also the loss from stats (the former k_loss_finalize launch)
 cudaError_t launch_codebook_grad(const int64_t* seg_sums, const CodebookView& cb, float coef, const float* g_loss,
-                                 float* grad_weight, cudaStream_t s);
+                                 float* grad_weight, const int64_t* stats, int64_t n_elem_total, int form, float beta,
+                                 float* loss, cudaStream_t s);
 
 // ---- vq_peer.cu ------------------------------------------------------------------------------
 // byte layout of one rank's exchange buffer (see vq_peer.cu); offsets of stats / hist are relative to the slot

@@ -165,11 +165,7 @@ __global__ void __launch_bounds__(256) k_codebook_grad_sharded(PeerPtrs peers, i
         if (stats_total && threadIdx.x != VQ_STAT_PEER_TIMEOUT) stats_total[threadIdx.x] = t;
         __syncwarp((1u << VQ_STATS_LEN) - 1u);
         if (threadIdx.x == 0 && loss) {
-            const double sum = (double)tot[VQ_STAT_LOSS_FIXED] / (double)(1ll << VQ_LOSS_SHIFT);
-            float m = (float)(sum / (double)n_elem_total);
-            if (tot[VQ_STAT_NONFINITE] != 0) m = __int_as_float(0x7fc00000);
-            const float bm = __fmul_rn(beta, m);
-            loss[0] = (form == VQ_FORM_VIT) ? __fadd_rn(bm, m) : __fadd_rn(m, bm);
+            loss[0] = loss_from_fixed(tot[VQ_STAT_LOSS_FIXED], tot[VQ_STAT_NONFINITE], n_elem_total, form, beta);
         }
     }
 }

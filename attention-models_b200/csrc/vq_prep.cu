@@ -59,15 +59,26 @@ CodebookView codebook_view(void* cb, int K, int D) {
     return v;
 }
 
+// Codebook preparation: block b leaves its count of non-unit codes in info[b] (grid <= kInfoSlots; block 0 clears
+// the unused slots), so the count needs neither atomics nor a zeroed buffer.
+__device__ __forceinline__ void write_info(int* __restrict__ info, int n_bad) {
+    const int total = __syncthreads_count(n_bad != 0);
+    if (threadIdx.x == 0) info[blockIdx.x] = total;
+    if (blockIdx.x == 0)
+        for (int i = gridDim.x + threadIdx.x; i < kInfoSlots; i += blockDim.x) info[i] = 0;
+}
+
 // One warp per row, kRows rows in flight per warp for memory-level parallelism.
 template <int D, bool kIsCodebook>
 __global__ void __launch_bounds__(256) k_prep_rows(const float* __restrict__ in, int64_t rows,
                                                    float* __restrict__ unit32, float* __restrict__ sq,
                                                    float* __restrict__ denom, __half* __restrict__ unit16,
-                                                   int* __restrict__ info) {
+                                                   int* __restrict__ info, ZeroList zl) {
     using M = RowMap<D>;
     constexpr int kRows = (M::kPerLane <= 4) ? 4 : 2;
     const int lane = threadIdx.x & 31;
+    if (!kIsCodebook) zero_ranges(zl);
+    int n_bad = 0;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t r0 = warp * kRows; r0 < rows; r0 += n_warps * kRows) {
@@ -88,10 +99,11 @@ __global__ void __launch_bounds__(256) k_prep_rows(const float* __restrict__ in,
             if (lane == 0) {
                 if (sq) sq[r] = s2;
                 if (denom) denom[r] = den;
-                if (kIsCodebook && !(fabsf(s2 - 1.f) < 1e-4f)) atomicAdd(info, 1);
+                if (kIsCodebook && !(fabsf(s2 - 1.f) < 1e-4f)) ++n_bad;
             }
         }
     }
+    if (kIsCodebook) write_info(info, n_bad);
 }
 
 // D < 128 (ATen's non-vectorised schedule): D/4 lanes share a row, one float4 each, 32/(D/4) rows per
@@ -103,8 +115,11 @@ template <int D, bool kIsCodebook>
 __global__ void __launch_bounds__(256) k_prep_rows_small(const float4* __restrict__ in, int64_t rows,
                                                          float4* __restrict__ unit32, float* __restrict__ sq,
                                                          float* __restrict__ denom, uint2* __restrict__ unit16,
-                                                         int* __restrict__ info) {
+                                                         int* __restrict__ info, float4* __restrict__ en32c,
+                                                         float* __restrict__ csq_cell, ZeroList zl) {
     static_assert(D == 16 || D == 32 || D == 64, "small-row prep covers D < 128");
+    if (!kIsCodebook) zero_ranges(zl);
+    int n_bad = 0;
     constexpr int kLpr = D / 4;
     constexpr int kRpw = 32 / kLpr;
     constexpr int kUnroll = 4;
@@ -151,73 +166,74 @@ __global__ void __launch_bounds__(256) k_prep_rows_small(const float4* __restric
                 if (sub == 0) {
                     if (sq) sq[r] = s2;
                     if (denom) denom[r] = den;
-                    if (kIsCodebook && !(fabsf(s2 - 1.f) < 1e-4f)) atomicAdd(info, 1);
+                    if (kIsCodebook && !(fabsf(s2 - 1.f) < 1e-4f)) ++n_bad;
+                }
+                if (kIsCodebook && D == 32 && en32c) {
+                    // cell copies of the unit codes (see CodebookView): chunk `sub` of code r
+                    const int code = (int)r;
+                    const int g = code >> 9, w = code & 511, m = w >> 6, hs = w & 63;
+                    const int ci = g * 64 + hs;
+                    en32c[(ci * 8 + sub) * 8 + m] = v;
+                    if (sub == 0) csq_cell[ci * 8 + m] = s2;
                 }
             }
         }
     }
+    if (kIsCodebook) write_info(info, n_bad);
 }
 
 template <int D, bool kIsCodebook>
 static cudaError_t prep_rows(const float* in, int64_t rows, float* unit32, float* sq, float* denom, __half* unit16,
-                             int* info, cudaStream_t s) {
-    if (rows == 0) return cudaSuccess;
-    const int64_t cap = (int64_t)sm_count() * 8;
+                             int* info, float* en32c, float* csq_cell, const ZeroList& zl, cudaStream_t s) {
+    if (rows == 0 && kIsCodebook) return cudaSuccess;
+    const int64_t cap = kIsCodebook ? kInfoSlots : (int64_t)sm_count() * 8;
     if constexpr (D < 128) {
         constexpr int rows_per_block = 8 * (32 / (D / 4)) * 4;
         int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
         if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
         k_prep_rows_small<D, kIsCodebook><<<(unsigned)blocks, 256, 0, s>>>(
             reinterpret_cast<const float4*>(in), rows, reinterpret_cast<float4*>(unit32), sq, denom,
-            reinterpret_cast<uint2*>(unit16), info);
+            reinterpret_cast<uint2*>(unit16), info, reinterpret_cast<float4*>(en32c), csq_cell, zl);
     } else {
         constexpr int kRows = (RowMap<D>::kPerLane <= 4) ? 4 : 2;
         const int warps_per_block = 8;
         int64_t blocks = (rows + (int64_t)warps_per_block * kRows - 1) / (warps_per_block * kRows);
         if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
         k_prep_rows<D, kIsCodebook><<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(in, rows, unit32, sq, denom,
-                                                                                        unit16, info);
+                                                                                        unit16, info, zl);
     }
     count_launch();
     return cudaGetLastError();
 }
 
-// cell copies of the unit codes (see CodebookView): one thread per 16-byte chunk
-__global__ void __launch_bounds__(256) k_cell_layout32(const float4* __restrict__ en32, const float* __restrict__ code_sq,
-                                                       int K, float4* __restrict__ en32c, float* __restrict__ csq_cell) {
-    const int idx = blockIdx.x * 256 + threadIdx.x;
-    if (idx >= K * 8) return;
-    const int code = idx >> 3, q = idx & 7;
-    const int g = code >> 9, w = code & 511, m = w >> 6, hs = w & 63;
-    const int ci = g * 64 + hs;
-    en32c[(ci * 8 + q) * 8 + m] = en32[idx];
-    if (q == 0) csq_cell[ci * 8 + m] = code_sq[code];
-}
-
 static cudaError_t prep_codebook_rows(const float* weight, const CodebookView& cb, cudaStream_t s) {
+    const ZeroList none = {};
     VQ_DISPATCH_D(cb.D, return (prep_rows<kD, true>(weight, cb.K, cb.en32, cb.code_sq, cb.code_denom, cb.en16,
-                                                     cb.info, s)));
+                                                     cb.info, cb.en32c, cb.csq_cell, none, s)));
     return cudaSuccess;
 }
 
+// One launch: unit codes (fp32 + fp16), squared norms, row norms, the degenerate-code counts and, at D = 32, the
+// cell copies the exact rescoring reads.
 cudaError_t launch_prep_codebook(const float* weight, const CodebookView& cb, cudaStream_t s) {
-    cudaError_t e = cudaMemsetAsync(cb.info, 0, 256, s);
-    if (e != cudaSuccess) return e;
-    e = prep_codebook_rows(weight, cb, s);
-    if (e != cudaSuccess) return e;
-    if (cb.en32c) {
-        k_cell_layout32<<<(cb.K * 8 + 255) / 256, 256, 0, s>>>(reinterpret_cast<const float4*>(cb.en32), cb.code_sq, cb.K,
-                                                              reinterpret_cast<float4*>(cb.en32c), cb.csq_cell);
-        count_launch();
-        e = cudaGetLastError();
-    }
-    return e;
+    return prep_codebook_rows(weight, cb, s);
 }
 
 cudaError_t launch_prep_tokens(const float* z, int64_t T, int D, float* zn32, float* row_sq, float* denom,
-                               __half* zn16, cudaStream_t s) {
-    VQ_DISPATCH_D(D, return (prep_rows<kD, false>(z, T, zn32, row_sq, denom, zn16, nullptr, s)));
+                               __half* zn16, const ZeroList& zl, cudaStream_t s) {
+    VQ_DISPATCH_D(D, return (prep_rows<kD, false>(z, T, zn32, row_sq, denom, zn16, nullptr, nullptr, nullptr, zl, s)));
     return cudaSuccess;
+}
+
+__global__ void __launch_bounds__(256) k_zero_ranges(ZeroList zl) { zero_ranges(zl); }
+
+// the same zeroing as a launch of its own (layouts whose first kernel is not a token-major prep)
+cudaError_t launch_zero_ranges(const ZeroList& zl, cudaStream_t s) {
+    k_zero_ranges<<<sm_count() * 2, 256, 0, s>>>(zl);
+    count_launch();
+    return cudaGetLastError();
 }
 
 // row_sq only, from already-normalised contiguous rows

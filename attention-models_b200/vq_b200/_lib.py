@@ -42,7 +42,7 @@ SIGNATURES = {
                                    c_int, c_int, c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                    c_size_t, c_void_p]),
     "vq_backward_codebook": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_void_p,
-                                     c_void_p]),
+                                     c_void_p, c_void_p, c_void_p]),
     "vq_exchange_bytes": (c_int, [c_int, c_int, POINTER(c_size_t)]),
     "vq_exchange_slot": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]),
     "vq_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),

@@ -253,7 +253,7 @@ class ShardedQuantiser:
                     hist_out = pack.hist(buf)
                 else:
                     red_stats, hist_out = p["stats"], p["hist"]
-                _lib.check(lib.vq_loss_finalize(_ptr(red_stats), n_total, form_id, self.beta, _ptr(p["loss"]), s))
-                _lib.check(lib.vq_backward_codebook(seg, cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_w"]), s))
+                _lib.check(lib.vq_backward_codebook(seg, cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_w"]),
+                                                    _ptr(red_stats), _ptr(p["loss"]), s))
         return {"z_q": p["z_q"], "indices": p["idx"], "loss": p["loss"].view(()), "grad_z": p["grad_z"],
                 "grad_weight": p["grad_w"], "histogram": hist_out, "stats": p["stats"]}

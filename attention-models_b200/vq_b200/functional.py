@@ -136,7 +136,7 @@ class _Quantise(torch.autograd.Function):
                                               None if from_forward or not want_w else _ptr(seg), _ptr(ws), ws_bytes, s))
             if want_w:
                 _lib.check(lib.vq_backward_codebook(_ptr(seg), _ptr(blob), K, D, form, beta, _ptr(g_loss), n_total,
-                                                    _ptr(grad_w), s))
+                                                    _ptr(grad_w), None, None, s))
         return grad_z, grad_w, None, None, None, None, None, None, None
 
 

@@ -131,7 +131,9 @@ VQ_API int vq_loss_finalize(const int64_t* loss_fixed, int64_t n_elem_total, int
  * before vq_backward_codebook; one GPU calls them back to back.
  * g_zq may be NULL (no upstream gradient through z_q); grad_z / seg_sums may be NULL (not wanted).
  * hist: the K int32 code-usage counts vq_forward wrote for the same idx (saves a recount), or NULL.
- * g_loss: DEVICE pointer to d(objective)/d(loss) (what autograd hands over), NULL means 1.0.       */
+ * g_loss: DEVICE pointer to d(objective)/d(loss) (what autograd hands over), NULL means 1.0.
+ * vq_backward_codebook: with `loss` != NULL the same launch also writes the loss from `stats` (what
+ * vq_loss_finalize computes; for callers that did not ask vq_forward for it); both may be NULL.     */
 VQ_API int vq_backward_workspace_bytes(int64_t T, int K, int D, size_t* out);
 VQ_API int vq_backward_tokens(const float* g_zq, int layout, int64_t T, int64_t hw,
                        const float* saved_zn, const float* saved_denom, const int64_t* idx, const int32_t* hist,
@@ -140,7 +142,8 @@ VQ_API int vq_backward_tokens(const float* g_zq, int layout, int64_t T, int64_t 
                        float* grad_z, int64_t* seg_sums,
                        void* ws, size_t ws_bytes, void* stream);
 VQ_API int vq_backward_codebook(const int64_t* seg_sums, const void* cb, int K, int D, int form, float beta,
-                         const float* g_loss, int64_t n_elem_total, float* grad_weight, void* stream);
+                         const float* g_loss, int64_t n_elem_total, float* grad_weight,
+                         const int64_t* stats, float* loss, void* stream);
 
 /* ---- token-sharded job: the backward's one exchange, fused with the codebook gradient -------------
  * Replaces DDP's all-reduce of codebook.embedding.weight.grad (trainers/vitgqgan.py:184,
