@@ -36,22 +36,24 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// measurement hooks: event pairs around the search kernel while profiling is on
-bool g_profiling = false;
+// measurement hooks: CUDA-event pairs around the kernels of a step while profiling is on.  Event records between
+// kernels cost a few microseconds per step, so only every g_profile_every-th vq_forward (and the backward calls that
+// follow it) is bracketed; the other steps of the timed region run undisturbed.
+bool g_profiling = false, g_sampled = false;
+int g_profile_every = 1;
+long long g_profile_calls = 0;
 long long g_launches_at_begin = 0;
-// [0]: the search kernel proper (tensor-core filter, or the exhaustive scan); [1]: exact rescoring + finish behind it
-std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_search_events, g_exact_events;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_slot_events[VQ_PROFILE_SLOTS];
 
-struct SearchTimer {
+struct SlotTimer {
     cudaEvent_t a = nullptr, b = nullptr;
     cudaStream_t s;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* sink;
-    explicit SearchTimer(cudaStream_t stream, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* where = &g_search_events)
-        : s(stream), sink(where) {
-        if (g_profiling && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, s);
+    int slot;
+    SlotTimer(cudaStream_t stream, int which) : s(stream), slot(which) {
+        if (g_profiling && g_sampled && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, s);
     }
     void stop() {
-        if (a && b) { cudaEventRecord(b, s); sink->emplace_back(a, b); a = b = nullptr; }
+        if (a && b) { cudaEventRecord(b, s); g_slot_events[slot].emplace_back(a, b); a = b = nullptr; }
     }
 };
 
@@ -147,7 +149,10 @@ int vq_codebook_prepare(const float* weight, int K, int D, void* cb, size_t cb_b
     if (!weight || !cb) return fail(VQ_ERR_ARG, "weight/cb is NULL");
     if (cb_bytes < vq::codebook_bytes(K, D)) return fail(VQ_ERR_WORKSPACE, "codebook blob too small");
     vq::CodebookView v = vq::codebook_view(cb, K, D);
+    if (g_profiling) g_sampled = (g_profile_calls % g_profile_every) == 0;     // the step the next vq_forward opens
+    SlotTimer timer(static_cast<cudaStream_t>(stream), VQ_PROFILE_PREP_CODEBOOK);
     VQ_CUDA(vq::launch_prep_codebook(weight, v, static_cast<cudaStream_t>(stream)));
+    timer.stop();
     return VQ_OK;
 }
 
@@ -174,6 +179,7 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
     if (ws_bytes < w.bytes) return fail(VQ_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, w.bytes);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     vq::CodebookView cbv = vq::codebook_view(const_cast<void*>(cb), K, D);
+    if (g_profiling) g_sampled = (g_profile_calls++ % g_profile_every) == 0;
 
     float* zn32 = saved_zn ? saved_zn : w.zn32;
     float* denom = saved_denom ? saved_denom : w.denom;
@@ -194,6 +200,7 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
     }
 
     // 1. unit rows (ATen-order norms), fp16 copy for the tensor cores
+    SlotTimer prep_timer(s, VQ_PROFILE_PREP_TOKENS);
     if (layout == VQ_LAYOUT_TOKEN_MAJOR) {
         VQ_CUDA(vq::launch_prep_tokens(z, T, D, zn32, w.row_sq, denom, zn16, zl, s));
     } else {
@@ -202,17 +209,18 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
         VQ_CUDA(vq::launch_nchw_to_tok(z, T, hw, D, denom, zn32, zn16, s));
         VQ_CUDA(vq::launch_row_sumsq(zn32, T, D, w.row_sq, s));
     }
+    prep_timer.stop();
 
     // 2. nearest code per row, 3. idx, hist, z_q, loss partial
     float* zq_tok = indices_only ? nullptr : (layout == VQ_LAYOUT_NCHW ? w.zq_tok : z_q);
-    SearchTimer timer(s);
+    SlotTimer timer(s, VQ_PROFILE_SEARCH);
     if (tc16) {
         // D = 32: tensor-core filter -> records; one kernel then does the exact rescoring, the sliced search of
         // the undecided rows and the finish pass.  Undecided rows beyond kFlaggedCap (degenerate inputs) overflow
         // into the generic exhaustive kernel + a listed finish; both leave at once when there are none.
         VQ_CUDA(vq::launch_dist_tc(zn16, zn32, w.row_sq, cbv, T, w.cand, w.flagged, w.n_flagged, st, w.tc_ws, s));
         timer.stop();
-        SearchTimer exact_timer(s, &g_exact_events);
+        SlotTimer exact_timer(s, VQ_PROFILE_EXACT_FINISH);
         VQ_CUDA(vq::launch_exact_finish16(w.tc_ws, zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, w.n_flagged + 64, w.scan_ws,
                                           nullptr, zq_tok, idx, hist, seg_sums, st, s));
         exact_timer.stop();
@@ -220,7 +228,9 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
             vq::ListedFinish fin;
             fin.zq = zq_tok; fin.idx = idx; fin.hist = hist;
             fin.seg = zq_tok ? reinterpret_cast<unsigned long long*>(seg_sums) : nullptr;
+            SlotTimer tail_timer(s, VQ_PROFILE_TAIL);
             VQ_CUDA(vq::launch_scan_listed_tail(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, vq::kFlaggedCap, w.cand, st, fin, s));
+            tail_timer.stop();
         }
     } else {
         if (use_tc) {
@@ -230,7 +240,9 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
             VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, nullptr, nullptr, T, w.cand, st, nullptr, s));
         }
         timer.stop();
+        SlotTimer finish_timer(s, VQ_PROFILE_EXACT_FINISH);
         VQ_CUDA(vq::launch_finish(zn32, w.cand, cbv, T, zq_tok, idx, hist, seg_sums, st, s));
+        finish_timer.stop();
     }
     if (!indices_only && layout == VQ_LAYOUT_NCHW) VQ_CUDA(vq::launch_tok_to_nchw(zq_tok, T, hw, D, z_q, s));
     if (loss && !indices_only) {
@@ -276,6 +288,7 @@ int vq_backward_tokens(const float* g_zq, int layout, int64_t T, int64_t hw, con
     float* g_tok = reinterpret_cast<float*>(p); p += align_up(sizeof(float) * n * D, 256);
     float* grad_tok = reinterpret_cast<float*>(p);
 
+    SlotTimer bwd_timer(s, VQ_PROFILE_BACKWARD_TOKENS);
     if (grad_z) {
         const float c1 = (form == VQ_FORM_VIT) ? beta : 1.f;
         const float coef = (float)((double)c1 * 2.0 / (double)n_elem_total);
@@ -289,6 +302,7 @@ int vq_backward_tokens(const float* g_zq, int layout, int64_t T, int64_t hw, con
         }
     }
     if (seg_sums) VQ_CUDA(vq::launch_segment_sums(saved_zn, idx, hist, cbv, T, seg_sums, seg_ws, seg_bytes, s));
+    bwd_timer.stop();
     return VQ_OK;
 }
 
@@ -301,8 +315,10 @@ int vq_backward_codebook(const int64_t* seg_sums, const void* cb, int K, int D, 
     const float c2 = (form == VQ_FORM_VIT) ? 1.f : beta;
     const float coef = (float)((double)c2 * 2.0 / (double)n_elem_total);
     if (loss && !stats) return fail(VQ_ERR_ARG, "loss needs stats");
+    SlotTimer timer(static_cast<cudaStream_t>(stream), VQ_PROFILE_CODEBOOK_GRAD);
     VQ_CUDA(vq::launch_codebook_grad(seg_sums, cbv, coef, g_loss, grad_weight, stats, n_elem_total, form, beta, loss,
                                      static_cast<cudaStream_t>(stream)));
+    timer.stop();
     return VQ_OK;
 }
 
@@ -368,8 +384,10 @@ int vq_backward_codebook_sharded(const void* const* peer_bufs, int world, int ra
     vq::CodebookView cbv = vq::codebook_view(const_cast<void*>(cb), K, D);
     const float c2 = (form == VQ_FORM_VIT) ? 1.f : beta;
     const float coef = (float)((double)c2 * 2.0 / (double)n_elem_total);
+    SlotTimer timer(static_cast<cudaStream_t>(stream), VQ_PROFILE_CODEBOOK_GRAD);
     VQ_CUDA(vq::launch_codebook_grad_sharded(peer_bufs, world, rank, slot, epoch, cbv, coef, g_loss, n_elem_total, form, beta,
                                              grad_weight, hist_total, loss, stats_total, static_cast<cudaStream_t>(stream)));
+    timer.stop();
     return VQ_OK;
 }
 
@@ -392,46 +410,47 @@ int vq_gather(const int64_t* idx, int64_t T, int64_t hw, const float* weight, co
     return VQ_OK;
 }
 
-int vq_profile_begin(void) {
-    for (auto* v : {&g_search_events, &g_exact_events}) {
-        for (auto& p : *v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-        v->clear();
+namespace {
+int slot_total(int slot, double* ms_total, int64_t* launches) {
+    double total = 0.0;
+    auto& v = g_slot_events[slot];
+    for (auto& p : v) {
+        float ms = 0.f;
+        VQ_CUDA(cudaEventSynchronize(p.second));
+        VQ_CUDA(cudaEventElapsedTime(&ms, p.first, p.second));
+        total += ms;
+    }
+    if (ms_total) *ms_total = total;
+    if (launches) *launches = (int64_t)v.size();
+    for (auto& p : v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    v.clear();
+    return VQ_OK;
+}
+}  // namespace
+
+int vq_profile_begin(int sample_every) {
+    for (auto& v : g_slot_events) {
+        for (auto& p : v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+        v.clear();
     }
     g_launches_at_begin = vq::g_kernel_launches;
+    g_profile_every = sample_every > 0 ? sample_every : 1;
+    g_profile_calls = 0;
+    g_sampled = false;
     g_profiling = true;
     return VQ_OK;
 }
 
 int vq_profile_end(double* search_ms_total, int64_t* search_launches, int64_t* kernel_launches) {
     g_profiling = false;
-    double total = 0.0;
-    for (auto& p : g_search_events) {
-        float ms = 0.f;
-        VQ_CUDA(cudaEventSynchronize(p.second));
-        VQ_CUDA(cudaEventElapsedTime(&ms, p.first, p.second));
-        total += ms;
-    }
-    if (search_ms_total) *search_ms_total = total;
-    if (search_launches) *search_launches = (int64_t)g_search_events.size();
+    g_sampled = false;
     if (kernel_launches) *kernel_launches = vq::g_kernel_launches - g_launches_at_begin;
-    for (auto& p : g_search_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-    g_search_events.clear();
-    return VQ_OK;
+    return slot_total(VQ_PROFILE_SEARCH, search_ms_total, search_launches);
 }
 
-int vq_profile_exact(double* exact_ms_total, int64_t* exact_launches) {
-    double total = 0.0;
-    for (auto& p : g_exact_events) {
-        float ms = 0.f;
-        VQ_CUDA(cudaEventSynchronize(p.second));
-        VQ_CUDA(cudaEventElapsedTime(&ms, p.first, p.second));
-        total += ms;
-    }
-    if (exact_ms_total) *exact_ms_total = total;
-    if (exact_launches) *exact_launches = (int64_t)g_exact_events.size();
-    for (auto& p : g_exact_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-    g_exact_events.clear();
-    return VQ_OK;
+int vq_profile_slot(int slot, double* ms_total, int64_t* launches) {
+    if (slot < 0 || slot >= VQ_PROFILE_SLOTS) return fail(VQ_ERR_ARG, "profile slot %d out of range", slot);
+    return slot_total(slot, ms_total, launches);
 }
 
 // ---- host-buffer step ---------------------------------------------------------------------------

@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(256) k_backward_tokens(const float4* __restric
                                                          const int64_t* __restrict__ idx, const float4* __restrict__ en,
                                                          int64_t T, float coef_base, const float* __restrict__ g_loss,
                                                          float4* __restrict__ grad) {
+    pdl_trigger();
+    pdl_wait();
     const float coef = coef_base * (g_loss ? __ldg(g_loss) : 1.f);
     constexpr int kChunks = D / 4;
     constexpr int kLpr = (kChunks < 32) ? kChunks : 32;
@@ -122,12 +124,13 @@ cudaError_t launch_backward_tokens(const float* g_tok, const float* zn32, const 
     int64_t blocks = (T + rows_per_block - 1) / rows_per_block;
     const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    VQ_DISPATCH_D(cb.D, (k_backward_tokens<kD><<<(unsigned)blocks, 256, 0, s>>>(
-                            reinterpret_cast<const float4*>(g_tok), reinterpret_cast<const float4*>(zn32), denom, idx,
-                            reinterpret_cast<const float4*>(cb.en32), T, coef_commit, g_loss,
-                            reinterpret_cast<float4*>(grad_tok))));
+    cudaError_t e = cudaSuccess;
+    VQ_DISPATCH_D(cb.D, (e = launch_pdl(k_backward_tokens<kD>, dim3((unsigned)blocks), dim3(256), 0, s,
+                                        reinterpret_cast<const float4*>(g_tok), reinterpret_cast<const float4*>(zn32), denom,
+                                        idx, reinterpret_cast<const float4*>(cb.en32), T, coef_commit, g_loss,
+                                        reinterpret_cast<float4*>(grad_tok))));
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -331,6 +334,8 @@ __global__ void __launch_bounds__(256) k_codebook_grad(const long long* __restri
                                                        int K, float coef_base, const float* __restrict__ g_loss,
                                                        float* __restrict__ grad, const int64_t* __restrict__ stats,
                                                        int64_t n_elem_total, int form, float beta, float* __restrict__ loss) {
+    pdl_trigger();
+    pdl_wait();
     if (loss && blockIdx.x == 0 && threadIdx.x == 0)
         loss[0] = loss_from_fixed(stats[VQ_STAT_LOSS_FIXED], stats[VQ_STAT_NONFINITE], n_elem_total, form, beta);
     const float coef = coef_base * (g_loss ? __ldg(g_loss) : 1.f);
@@ -369,11 +374,12 @@ cudaError_t launch_codebook_grad(const int64_t* seg_sums, const CodebookView& cb
     int blocks = (cb.K + 7) / 8;
     const int cap = sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    VQ_DISPATCH_D(cb.D, (k_codebook_grad<kD><<<blocks, 256, 0, s>>>(reinterpret_cast<const long long*>(seg_sums),
-                                                                      cb.en32, cb.code_denom, cb.K, coef, g_loss, grad_weight,
-                                                                      stats, n_elem_total, form, beta, stats ? loss : nullptr)));
+    cudaError_t e = cudaSuccess;
+    VQ_DISPATCH_D(cb.D, (e = launch_pdl(k_codebook_grad<kD>, dim3(blocks), dim3(256), 0, s,
+                                        reinterpret_cast<const long long*>(seg_sums), cb.en32, cb.code_denom, cb.K, coef, g_loss,
+                                        grad_weight, stats, n_elem_total, form, beta, stats ? loss : nullptr)));
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace vq

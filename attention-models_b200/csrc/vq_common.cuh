@@ -22,6 +22,10 @@
 
 namespace vq {
 
+// programmatic dependent launch (see launch_pdl in vq_kernels.h); both are no-ops in a classic launch
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // Row <-> lane mapping.  One warp owns one row of D floats.
 //   D <  128 : lane l holds elements l + W*j           (W = min(D, 32); ATen: lanes stride the row)

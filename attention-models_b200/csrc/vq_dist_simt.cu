@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(256) k_scan_exact(const float* __restrict__ zn
     __shared__ int row_id[kTM];
     __shared__ int s_last;
 
+    pdl_trigger();
+    pdl_wait();
     int64_t n_rows = rows ? (int64_t)(*n_rows_ptr) : T;
     if (n_rows > row_end) n_rows = row_end;
     long long loss_fx = 0;
@@ -286,10 +288,10 @@ cudaError_t launch_scan_listed_tail(const float* zn32, const float* row_sq, cons
     int64_t blocks = (T - row_begin + kTM - 1) / kTM;
     if (blocks <= 0) return cudaSuccess;
     if (blocks > sm_count()) blocks = sm_count();
-    k_scan_exact<<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, row_begin, T,
-                                                 cand, nullptr, 0, nullptr, stats, fin);
+    cudaError_t e = launch_pdl(k_scan_exact, dim3((unsigned)blocks), dim3(256), 0, s, zn32, row_sq, cb.en32, cb.code_sq, T, cb.K,
+                               cb.D, rows, n_rows, row_begin, T, cand, nullptr, 0, nullptr, stats, fin);
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace vq

@@ -172,6 +172,10 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // barrier init and the TMEM allocation above overlap the tail of the token prep kernel (programmatic dependent
+    // launch); nothing before this line reads what that kernel writes
+    pdl_trigger();
+    pdl_wait();
     // every role reads the TMEM base address itself, after its setmaxnreg: a value kept live across the role
     // split ends up in a local-memory spill slot that the epilogue would reload once per tile
 
@@ -460,36 +464,58 @@ __device__ __forceinline__ float cell_distance(const float4* __restrict__ en32c,
     return ref_distance(a_sq, csq, dot);
 }
 
-// What vq_finish.cu does for one row, for lane m of the 8 lanes that just found its index (or one thread looping
-// over m): z_q = zn + (q - zn), loss partial in fixed point, and -- when the step trains the codebook -- the row's
-// terms of the segment sums S_code += fixed(q - zn).  Lane m owns elements m, m + 8, m + 16, m + 24 of the row, so
-// every load / store / RED instruction of the 8 lanes touches 8 consecutive elements: one 32-byte sector of
-// fp32, two of the int64 sums (4x fewer L2 reduction transactions than a float4-per-lane mapping; measured in
-// tools/ubench_red.cu: 8 us over the row stream for 262 144 rows against 35 us).
+// the same with the row staged in shared memory (zs: the row's 8 float4; the 8 lanes of a group read one address)
+__device__ __forceinline__ float cell_distance_staged(const float4* __restrict__ en32c, const float* __restrict__ csq_cell,
+                                                      int ci, int m, const float4* zs, float a_sq) {
+    const float4* e4 = en32c + (int64_t)ci * 64 + m;
+    float4 ev[kD / 4];
+#pragma unroll
+    for (int q = 0; q < kD / 4; ++q) ev[q] = __ldg(e4 + 8 * q);
+    const float csq = __ldg(csq_cell + ci * 8 + m);
+    float dot = 0.f;
+#pragma unroll
+    for (int q = 0; q < kD / 4; ++q) {
+        const float4 z = zs[q];
+        dot = __fmaf_rn(z.x, ev[q].x, dot);
+        dot = __fmaf_rn(z.y, ev[q].y, dot);
+        dot = __fmaf_rn(z.z, ev[q].z, dot);
+        dot = __fmaf_rn(z.w, ev[q].w, dot);
+    }
+    return ref_distance(a_sq, csq, dot);
+}
+
+// What vq_finish.cu does for one row: z_q = zn + (q - zn), loss partial in fixed point and -- when the step trains
+// the codebook -- the row's terms of the segment sums S_code += fixed(q - zn).
 struct FinishOut {
     float* zq; int64_t* idx; int32_t* hist; unsigned long long* seg;
 };
-__device__ __forceinline__ void finish_lane(const float* __restrict__ zn32, const float* __restrict__ en32, const FinishOut& out,
-                                            int K, int row, int code, int m, long long& loss_fx, unsigned& bad) {
-    const float* a_row = zn32 + (int64_t)row * kD + m;
-    const float* q_row = en32 + (int64_t)code * kD + m;
-    float a[4], q[4], df[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { a[i] = __ldg(a_row + 8 * i); q[i] = __ldg(q_row + 8 * i); }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        df[i] = __fsub_rn(q[i], a[i]);
-        __stcs(out.zq + (int64_t)row * kD + m + 8 * i, __fadd_rn(a[i], df[i]));
-    }
-    const float p = (df[0] * df[0] + df[1] * df[1]) + (df[2] * df[2] + df[3] * df[3]);
+// chunk `c` (4 elements) of one row: returns q - zn of the chunk
+__device__ __forceinline__ float4 finish_chunk(const float4 a, const float4* __restrict__ en4, const FinishOut& out, int row,
+                                               int code, int c, long long& loss_fx, unsigned& bad) {
+    const float4 q = __ldg(en4 + (int64_t)code * (kD / 4) + c);
+    float4 df, o;
+    df.x = __fsub_rn(q.x, a.x); df.y = __fsub_rn(q.y, a.y); df.z = __fsub_rn(q.z, a.z); df.w = __fsub_rn(q.w, a.w);
+    o.x = __fadd_rn(a.x, df.x); o.y = __fadd_rn(a.y, df.y); o.z = __fadd_rn(a.z, df.z); o.w = __fadd_rn(a.w, df.w);
+    __stcs(reinterpret_cast<float4*>(out.zq) + (int64_t)row * (kD / 4) + c, o);
+    const float p = (df.x * df.x + df.y * df.y) + (df.z * df.z + df.w * df.w);
     if (is_finite(p)) loss_fx += to_fixed(p, VQ_LOSS_SHIFT);
     else bad += 1;
-    if (out.seg) {
-        unsigned poison = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) seg_add(out.seg + (int64_t)code * kD + m + 8 * i, df[i], poison);
-        if (poison) atomicAdd(out.seg + (int64_t)K * kD + code, 1ull);
+    return df;
+}
+// a whole row by one thread (the few rows of phase B)
+__device__ __forceinline__ void finish_row_serial(const float4* __restrict__ zn4, const float4* __restrict__ en4,
+                                                  const FinishOut& out, int K, int row, int code, long long& loss_fx,
+                                                  unsigned& bad) {
+    unsigned poison = 0;
+    for (int c = 0; c < kD / 4; ++c) {
+        const float4 df = finish_chunk(__ldg(zn4 + (int64_t)row * (kD / 4) + c), en4, out, row, code, c, loss_fx, bad);
+        if (out.seg) {
+            unsigned long long* slot = out.seg + (int64_t)code * kD + 4 * c;
+            seg_add(slot + 0, df.x, poison); seg_add(slot + 1, df.y, poison);
+            seg_add(slot + 2, df.z, poison); seg_add(slot + 3, df.w, poison);
+        }
     }
+    if (poison) atomicAdd(out.seg + (int64_t)K * kD + code, 1ull);
 }
 
 // Everything behind the filter in one launch:
@@ -501,7 +527,7 @@ __device__ __forceinline__ void finish_lane(const float* __restrict__ zn32, cons
 //            Rows [0, min(*n_rows, cap)) of the list; `done` holds one zeroed counter per listed row.
 constexpr int kExactThreads = 128;
 #ifndef VQ_EXACT_MIN_BLOCKS
-#define VQ_EXACT_MIN_BLOCKS 6   // 80 registers; 8 (64 registers, 180 B of spills) measured 8% slower
+#define VQ_EXACT_MIN_BLOCKS 8   // 64 registers (24 B of spills): 2% faster than 6 blocks of 80 registers
 #endif
 constexpr int kFlaggedSlices = 32;
 struct __align__(16) FlaggedPartial {
@@ -515,17 +541,52 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
                  int64_t* __restrict__ stats) {
     __shared__ unsigned long long s_best[kExactThreads / 32];
     __shared__ float s_second[kExactThreads / 32];
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m = lane & 7;
     const float4* zn4 = reinterpret_cast<const float4*>(zn32);
     unsigned ties = 0, multi = 0, bad = 0;
     long long loss_fx = 0;
     // ---------------- phase A ----------------
+    // A warp owns 4 rows per iteration.  Their unit rows (512 contiguous bytes) arrive with ONE coalesced 16-byte load
+    // per lane and are staged in shared memory (the 8 lanes of a row then read them as broadcasts: 4 registers instead
+    // of 32 for the row); records and rows of the next iteration are prefetched while this one is rescored, so an
+    // iteration waits for two dependent round trips (cell codes, winner's code row) instead of four.
+    // Finish: lane m owns chunk m of the row (one 16-byte access per lane for zn, the code row and z_q); for the
+    // segment sums the differences are transposed through shared memory so that lane m adds elements m, m + 8, m + 16,
+    // m + 24: every RED instruction of a group then covers 8 consecutive int64 (two whole 32-byte sectors; 4x fewer
+    // L2 reduction transactions than 4 consecutive elements per lane, tools/ubench_red.cu).
+    // Row strides of 9 / 10 float4 put the 4 rows of a warp in different banks: the broadcast LDS.128 of the rescoring
+    // (one address per 8-lane group) and the strided LDS.32 of the segment-sum transposition are conflict-free.
+    __shared__ __align__(16) float4 s_z[kExactThreads / 32][4][kD / 4 + 1];
+    __shared__ __align__(16) float4 s_df[kExactThreads / 32][4][kD / 4 + 2];
+    const float4* en4 = reinterpret_cast<const float4*>(en32);
     const int groups = gridDim.x * (kExactThreads / 8);
-    for (int row0 = (blockIdx.x * kExactThreads + threadIdx.x - lane) >> 3; row0 < T; row0 += groups) {
-        const int row = row0 + (lane >> 3);
-        int4 h0 = make_int4(-1, 0, 0, 0), h1 = make_int4(0, 0, 0, 0), h2 = make_int4(0, 0, 0, 0);
-        if (row < T) { h0 = __ldg(rec + 3 * (int64_t)row); h1 = __ldg(rec + 3 * (int64_t)row + 1); h2 = __ldg(rec + 3 * (int64_t)row + 2); }
+    const int grp = lane >> 3;
+    int row0 = (blockIdx.x * kExactThreads + threadIdx.x - lane) >> 3;
+    int4 n0 = make_int4(-1, 0, 0, 0), n1 = make_int4(0, 0, 0, 0), n2 = make_int4(0, 0, 0, 0);
+    float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
+    float n_sq = 0.f;
+    auto fetch = [&](int r0) {
+        const int r = r0 + grp;
+        n0 = make_int4(-1, 0, 0, 0);
+        if (r < T) {
+            n0 = __ldg(rec + 3 * (int64_t)r); n1 = __ldg(rec + 3 * (int64_t)r + 1); n2 = __ldg(rec + 3 * (int64_t)r + 2);
+            nz = __ldg(zn4 + (int64_t)r0 * (kD / 4) + lane);      // row r0 + (lane >> 3), chunk lane & 7
+            n_sq = __ldg(row_sq + r);
+        }
+    };
+    if (row0 < T) fetch(row0);
+    for (; row0 < T; row0 += groups) {
+        const int row = row0 + grp;
+        const int4 h0 = n0, h1 = n1, h2 = n2;
+        const float a_sq = n_sq;
+        __syncwarp();                                   // the previous iteration's reads of s_z are done
+        s_z[warp][grp][m] = nz;
+        __syncwarp();
+        if (row0 + groups < T) fetch(row0 + groups);
+        const float4* zs = s_z[warp][grp];
         const bool valid = (row < T) && (h0.x >= 0);
         auto u64 = [](int lo, int hi) { return (unsigned long long)(uint32_t)lo | ((unsigned long long)(uint32_t)hi << 32); };
         unsigned long long cur = valid ? u64(h0.z, h0.w) : 0ull;
@@ -535,13 +596,6 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
         int a = 0, g = h0.x & 0xFFFF;
         const int n_cells = __popcll(cur) + __popcll(m1) + __popcll(m2) + __popcll(m3);
         const int n_iter = __reduce_max_sync(VQ_FULL, n_cells);
-        float4 z[kD / 4];
-        float a_sq = 0.f;
-        if (row < T) {      // not gated on the record: the row and its record are fetched in one round trip
-#pragma unroll
-            for (int q = 0; q < kD / 4; ++q) z[q] = __ldg(zn4 + (int64_t)row * (kD / 4) + q);
-            a_sq = __ldg(row_sq + row);
-        }
         Top2 top;
         top.init();
 #pragma unroll 1
@@ -552,7 +606,7 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
             if (cur != 0ull) {
                 const int hs = __ffsll((long long)cur) - 1;
                 cur &= cur - 1;
-                const float dist = cell_distance(en32c, csq_cell, g * 64 + hs, m, z, a_sq);
+                const float dist = cell_distance_staged(en32c, csq_cell, g * 64 + hs, m, zs, a_sq);
                 top.add(dist_key(dist, g * kGroupCols + hs + 64 * m));
             }
         }
@@ -572,7 +626,22 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
                 if (top.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) ++ties;
                 if (n_cells > 1) ++multi;
             }
-            if (out.zq) finish_lane(zn32, en32, out, K, row, code, m, loss_fx, bad);
+        }
+        if (out.zq) {                                   // uniform
+            const int code = (int)(uint32_t)top.best;
+            float4 df = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) df = finish_chunk(zs[m], en4, out, row, code, m, loss_fx, bad);
+            if (out.seg) {                              // uniform
+                s_df[warp][grp][m] = df;
+                __syncwarp();
+                if (valid) {
+                    const float* d = reinterpret_cast<const float*>(s_df[warp][grp]);
+                    unsigned poison = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) seg_add(out.seg + (int64_t)code * kD + m + 8 * i, d[m + 8 * i], poison);
+                    if (poison) atomicAdd(out.seg + (int64_t)K * kD + code, 1ull);
+                }
+            }
         }
     }
     // ---------------- phase B ----------------
@@ -585,15 +654,16 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
         for (int item = blockIdx.x; item < n * kFlaggedSlices; item += gridDim.x) {
             const int i = item / kFlaggedSlices, slice = item % kFlaggedSlices;
             const int row = flagged[i];
-            float4 z[kD / 4];
-#pragma unroll
-            for (int q = 0; q < kD / 4; ++q) z[q] = __ldg(zn4 + (int64_t)row * (kD / 4) + q);
+            __syncthreads();                       // the previous item's shared values are consumed
+            if (threadIdx.x < kD / 4) s_z[0][0][threadIdx.x] = __ldg(zn4 + (int64_t)row * (kD / 4) + threadIdx.x);
+            __syncthreads();
+            const float4* zs = s_z[0][0];
             const float a_sq = __ldg(row_sq + row);
             Top2 top;
             top.init();
             const int c_end = min(n_cells, (slice + 1) * per_slice);
             for (int ci = slice * per_slice + grp; ci < c_end; ci += kExactThreads / 8) {
-                const float dist = cell_distance(en32c, csq_cell, ci, m, z, a_sq);
+                const float dist = cell_distance_staged(en32c, csq_cell, ci, m, zs, a_sq);
                 top.add(dist_key(dist, (ci >> 6) * kGroupCols + (ci & 63) + 64 * m));
             }
 #pragma unroll
@@ -602,7 +672,6 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
                 const float os = __shfl_xor_sync(VQ_FULL, top.second, off);
                 top.merge(ob, os);
             }
-            __syncthreads();                       // the previous item's shared values are consumed
             if (lane == 0) { s_best[warp] = top.best; s_second[warp] = top.second; }
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -628,7 +697,7 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
                     if (out.hist) atomicAdd(out.hist + code, 1);
                     if (fin.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) ++ties;
                     if (out.zq)
-                        for (int mm = 0; mm < 8; ++mm) finish_lane(zn32, en32, out, K, row, code, mm, loss_fx, bad);
+                        finish_row_serial(zn4, reinterpret_cast<const float4*>(en32), out, K, row, code, loss_fx, bad);
                     done[i] = 0;                   // ready for the next call
                 }
             }
@@ -677,15 +746,16 @@ cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T
     int4* rec = static_cast<int4*>(records);
     const int n_row_tiles = (T + tc16::kRowsPerCta - 1) / tc16::kRowsPerCta;
     const int grid = n_row_tiles < sm_count() ? n_row_tiles : sm_count();
+    cudaError_t e;
     if (service_low)
-        tc16::k_dist_tc16<false><<<grid, tc16::kThreads, L.total + 1024, s>>>(ma, mb, T, cb.K, cb.info, rec, cand, flagged,
-                                                                             n_flagged, stats);
+        e = launch_pdl(tc16::k_dist_tc16<false>, dim3(grid), dim3(tc16::kThreads), L.total + 1024, s, ma, mb, T, cb.K, cb.info, rec,
+                       cand, flagged, n_flagged, stats);
     else
-        tc16::k_dist_tc16<true><<<grid, tc16::kThreads, L.total + 1024, s>>>(ma, mb, T, cb.K, cb.info, rec, cand, flagged,
-                                                                            n_flagged, stats);
+        e = launch_pdl(tc16::k_dist_tc16<true>, dim3(grid), dim3(tc16::kThreads), L.total + 1024, s, ma, mb, T, cb.K, cb.info, rec,
+                       cand, flagged, n_flagged, stats);
     count_launch();
     tc::instrument_report(s, grid);
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // Exact indices and the finish pass behind the filter (see k_exact_finish16).  zq_tok / hist may be null.
@@ -703,11 +773,12 @@ cudaError_t launch_exact_finish16(const void* records, const float* zn32, const 
     tc16::FinishOut out;
     out.zq = zq_tok; out.idx = idx_out; out.hist = hist;
     out.seg = zq_tok ? reinterpret_cast<unsigned long long*>(seg_sums) : nullptr;
-    tc16::k_exact_finish16<<<(unsigned)blocks, tc16::kExactThreads, 0, s>>>(
-        static_cast<const int4*>(records), zn32, row_sq, cb.en32, reinterpret_cast<const float4*>(cb.en32c), cb.csq_cell, (int)T,
-        cb.K, flagged, n_flagged, cap, static_cast<tc16::FlaggedPartial*>(partial_ws), done_counters, cand, out, stats);
+    cudaError_t e = launch_pdl(tc16::k_exact_finish16, dim3((unsigned)blocks), dim3(tc16::kExactThreads), 0, s,
+                               static_cast<const int4*>(records), zn32, row_sq, cb.en32, reinterpret_cast<const float4*>(cb.en32c),
+                               cb.csq_cell, (int)T, cb.K, flagged, n_flagged, cap, static_cast<tc16::FlaggedPartial*>(partial_ws),
+                               done_counters, cand, out, stats);
     count_launch();
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace vq

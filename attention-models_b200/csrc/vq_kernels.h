@@ -131,6 +131,23 @@ inline bool dim_supported(int D) { return D >= 16 && D <= 512 && (D & (D - 1)) =
 
 int sm_count();
 
+// Programmatic dependent launch (PDL) for the kernels of the step: a kernel launched with launch_pdl may be
+// scheduled while its predecessor in the stream drains (that predecessor calls pdl_trigger()), and must call
+// pdl_wait() before it touches anything an earlier kernel wrote -- the wait returns when the predecessor grid has
+// completed and flushed.  Every such kernel waits, so completion stays transitive along the stream; kernels launched
+// the classic way are unaffected.  VQ_PDL=0 in the environment turns the attribute off (debugging).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // kernel-launch counter (bench.py's gpu_launches); bumped by every launcher next to its <<<>>>
 extern long long g_kernel_launches;
 inline void count_launch(int n = 1) { g_kernel_launches += n; }

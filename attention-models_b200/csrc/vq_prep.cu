@@ -7,12 +7,18 @@
 //   models/vitvqgan.py:158  sum(embedd_norm**2, dim=1)            models/vqgan.py:158
 // All HBM-bound: one pass over the rows, coalesced 128 B (or float4) accesses, grid sized in
 // multiples of the SM count.
+#include <cstdlib>
+
 #include "vq_common.cuh"
 #include "vq_kernels.h"
 
 namespace vq {
 
 long long g_kernel_launches = 0;
+bool pdl_enabled() {
+    static const bool on = !(getenv("VQ_PDL") && atoi(getenv("VQ_PDL")) == 0);
+    return on;
+}
 static int g_sm_count = 0;
 int sm_count() {
     if (g_sm_count == 0) {
@@ -77,6 +83,8 @@ __global__ void __launch_bounds__(256) k_prep_rows(const float* __restrict__ in,
     using M = RowMap<D>;
     constexpr int kRows = (M::kPerLane <= 4) ? 4 : 2;
     const int lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();
     if (!kIsCodebook) zero_ranges(zl);
     int n_bad = 0;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -118,6 +126,8 @@ __global__ void __launch_bounds__(256) k_prep_rows_small(const float4* __restric
                                                          int* __restrict__ info, float4* __restrict__ en32c,
                                                          float* __restrict__ csq_cell, ZeroList zl) {
     static_assert(D == 16 || D == 32 || D == 64, "small-row prep covers D < 128");
+    pdl_trigger();
+    pdl_wait();
     if (!kIsCodebook) zero_ranges(zl);
     int n_bad = 0;
     constexpr int kLpr = D / 4;
@@ -192,17 +202,19 @@ static cudaError_t prep_rows(const float* in, int64_t rows, float* unit32, float
         int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        k_prep_rows_small<D, kIsCodebook><<<(unsigned)blocks, 256, 0, s>>>(
-            reinterpret_cast<const float4*>(in), rows, reinterpret_cast<float4*>(unit32), sq, denom,
-            reinterpret_cast<uint2*>(unit16), info, reinterpret_cast<float4*>(en32c), csq_cell, zl);
+        cudaError_t e = launch_pdl(k_prep_rows_small<D, kIsCodebook>, dim3((unsigned)blocks), dim3(256), 0, s,
+                                   reinterpret_cast<const float4*>(in), rows, reinterpret_cast<float4*>(unit32), sq, denom,
+                                   reinterpret_cast<uint2*>(unit16), info, reinterpret_cast<float4*>(en32c), csq_cell, zl);
+        if (e != cudaSuccess) return e;
     } else {
         constexpr int kRows = (RowMap<D>::kPerLane <= 4) ? 4 : 2;
         const int warps_per_block = 8;
         int64_t blocks = (rows + (int64_t)warps_per_block * kRows - 1) / (warps_per_block * kRows);
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        k_prep_rows<D, kIsCodebook><<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(in, rows, unit32, sq, denom,
-                                                                                        unit16, info, zl);
+        cudaError_t e = launch_pdl(k_prep_rows<D, kIsCodebook>, dim3((unsigned)blocks), dim3(warps_per_block * 32), 0, s, in,
+                                   rows, unit32, sq, denom, unit16, info, zl);
+        if (e != cudaSuccess) return e;
     }
     count_launch();
     return cudaGetLastError();

@@ -21,6 +21,8 @@ FLAG_INDICES_ONLY, FLAG_EXACT_SCAN, FLAG_KEEP_STATS = 1, 2, 4
 STAT_NEAR_TIE_ROWS, STAT_AMBIGUOUS_ROWS, STAT_FALLBACK_ROWS, STAT_LOSS_FIXED, STAT_BAD_INDEX, STAT_NONFINITE = range(6)
 STAT_PEER_TIMEOUT = 6
 PEER_MAX_RANKS, IPC_HANDLE_BYTES = 16, 64
+(PROFILE_PREP_CODEBOOK, PROFILE_PREP_TOKENS, PROFILE_SEARCH, PROFILE_EXACT_FINISH, PROFILE_TAIL, PROFILE_BACKWARD_TOKENS,
+ PROFILE_CODEBOOK_GRAD) = range(7)
 STATS_LEN = 8
 SEG_SHIFT = 30
 
@@ -54,9 +56,9 @@ SIGNATURES = {
                                              c_void_p]),
     "vq_gather": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                           c_void_p, c_void_p]),
-    "vq_profile_begin": (c_int, []),
+    "vq_profile_begin": (c_int, [c_int]),
     "vq_profile_end": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64), POINTER(c_int64)]),
-    "vq_profile_exact": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
+    "vq_profile_slot": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(c_int64)]),
     "vq_host_step_arena_bytes": (c_int, [c_int64, c_int, c_int, POINTER(c_size_t)]),
     "vq_host_step": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

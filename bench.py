@@ -204,7 +204,7 @@ def run_b200(args):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    _lib.check(lib.vq_profile_begin())
+    _lib.check(lib.vq_profile_begin(args.profile_every))
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record()
@@ -215,8 +215,14 @@ def run_b200(args):
     ms_total = start.elapsed_time(stop)
     search_ms, search_n, launches = ctypes.c_double(0), ctypes.c_int64(0), ctypes.c_int64(0)
     _lib.check(lib.vq_profile_end(ctypes.byref(search_ms), ctypes.byref(search_n), ctypes.byref(launches)))
-    exact_ms, exact_n = ctypes.c_double(0), ctypes.c_int64(0)
-    _lib.check(lib.vq_profile_exact(ctypes.byref(exact_ms), ctypes.byref(exact_n)))
+    slots = {}
+    for name, slot in (("prep_codebook", _lib.PROFILE_PREP_CODEBOOK), ("prep_tokens", _lib.PROFILE_PREP_TOKENS),
+                       ("exact_finish", _lib.PROFILE_EXACT_FINISH), ("tail", _lib.PROFILE_TAIL),
+                       ("backward_tokens", _lib.PROFILE_BACKWARD_TOKENS), ("codebook_grad", _lib.PROFILE_CODEBOOK_GRAD)):
+        ms_, n_ = ctypes.c_double(0), ctypes.c_int64(0)
+        _lib.check(lib.vq_profile_slot(slot, ctypes.byref(ms_), ctypes.byref(n_)))
+        slots[name] = ms_.value / max(1, n_.value)
+    exact_ms, exact_n = ctypes.c_double(slots["exact_finish"]), ctypes.c_int64(1 if slots["exact_finish"] > 0 else 0)
     clocks = sampler.stop()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -297,11 +303,27 @@ def run_b200(args):
                                      if exact_n.value else None}
     hbm_bytes_step = (20 * DIM + 16) * T + 4 * K_CODES * DIM
     non_search_ms = max(ms_step - search_avg_ms - exact_avg_ms, 1e-6)
-    hbm = {"algorithmic_bytes_per_step": hbm_bytes_step, "non_search_ms": non_search_ms,
-           "achieved_gbs": hbm_bytes_step / (non_search_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
-           "frac": hbm_bytes_step / (non_search_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-           "note": "all kernels of the step outside the search (filter + exact/finish) together: prep and backward, "
-                   "vs algorithmic 20D+16 B/token"}
+    peak_gbs = peaks["hbm_gbs"]
+
+    def hbm_kernel(ms, nbytes, what):
+        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        return {"avg_launch_ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": gbs, "frac": gbs / peak_gbs, "bytes": what}
+
+    hbm = {"peak_gbs": peak_gbs, "algorithmic_bytes_per_step": hbm_bytes_step,
+           "kernels": {
+               "k_prep_rows (tokens)": hbm_kernel(slots["prep_tokens"], (10 * DIM + 8) * T,
+                                                  "read z 4D, write zn32 4D + zn16 2D + row_sq, denom 8"),
+               "k_backward_tokens": hbm_kernel(slots["backward_tokens"], (16 * DIM + 12) * T,
+                                               "read G 4D, zn 4D, idx 8, denom 4, code row 4D (L2), write grad_z 4D"),
+               "k_prep_rows (codebook)": hbm_kernel(slots["prep_codebook"], 14 * DIM * K_CODES, "read E 4D, write en32, en32c 8D, en16 2D"),
+               "k_codebook_grad": hbm_kernel(slots["codebook_grad"], (16 * DIM + 8) * K_CODES, "read seg sums 8D + 8, en 4D, write grad_E 4D"),
+           },
+           "non_search_ms": non_search_ms,
+           "all_non_search_vs_20D+16": hbm_bytes_step / (non_search_ms * 1e-3) / 1e9 / peak_gbs,
+           "note": "per-kernel: actual bytes the kernel moves / its CUDA-event time (sampled steps); the z_q / idx / histogram / "
+                   "segment-sum writes of the forward are fused into k_exact_finish16 (reported under roofline.behind_the_filter); "
+                   "all_non_search_vs_20D+16 = SURVEY 8(d) bytes of the whole step over everything outside filter + exact/finish"}
+    kernel_ms = dict(slots, search=search_avg_ms)
 
     # ---- cpu_baseline: oracle port on this box's host cores, bounded sample -------------------------
     cpu = None
@@ -321,7 +343,9 @@ def run_b200(args):
                        "l2": f"inputs rotate over {n_sets} resident sets ({n_sets * 2 * T * DIM * 4 >> 20} MiB) > 126 MB L2; "
                              "a step's own working set is 130 MB"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.value),
-            "roofline": roofline, "hbm_side": hbm, "cpu_baseline": cpu,
+            "roofline": roofline, "hbm_side": hbm, "kernel_ms": kernel_ms,
+            "profile_sampling": f"CUDA-event pairs on every {args.profile_every}th step of the timed region",
+            "cpu_baseline": cpu,
             "parity": {"near_tie_rows_last_step": stats[_lib.STAT_NEAR_TIE_ROWS] if stats else None,
                        "fallback_rows_last_step": stats[_lib.STAT_FALLBACK_ROWS] if stats else None}}
     print(json.dumps(line), flush=True)
@@ -339,6 +363,8 @@ def main():
     ap.add_argument("--exact-scan", action="store_true", help="force the exhaustive fp32 SIMT search")
     ap.add_argument("--exchange", default="peer", choices=["peer", "collective"],
                     help="N > 1: fused peer-memory exchange kernel (default) or one NCCL all-reduce")
+    ap.add_argument("--profile-every", type=int, default=4,
+                    help="bracket the kernels with CUDA events on every n-th timed step (event records cost ~2%% of a step)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()

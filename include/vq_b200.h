@@ -184,15 +184,24 @@ VQ_API int vq_gather(const int64_t* idx, int64_t T, int64_t hw, const float* wei
               int K, int D, int normalise, int layout_out, float* out, int64_t* stats, void* stream);
 
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------
- * Between vq_profile_begin() and vq_profile_end() the library brackets every launch of its nearest-code
- * search (the dominant kernel) with CUDA events on the caller's stream and counts all kernel launches.
- * vq_profile_end synchronises those events and returns the summed search time, the number of search
- * launches and the number of kernel launches of all kinds.                                         */
-VQ_API int vq_profile_begin(void);
+ * Between vq_profile_begin() and vq_profile_end() the library counts all kernel launches and brackets the kernels
+ * of every `sample_every`-th step (a vq_forward and the calls that follow it) with CUDA events on the caller's
+ * stream, one slot per kernel family.  Event records between kernels cost a few microseconds per step, which is
+ * why a timed region samples (bench.py: every 4th step) instead of bracketing every launch.
+ * vq_profile_end synchronises and returns the summed time and launch count of the nearest-code search (the
+ * dominant kernel: the tensor-core filter, or the exhaustive scan) and the number of kernel launches of all kinds;
+ * vq_profile_slot then returns (and clears) any other slot.                                          */
+#define VQ_PROFILE_PREP_CODEBOOK   0
+#define VQ_PROFILE_PREP_TOKENS     1
+#define VQ_PROFILE_SEARCH          2
+#define VQ_PROFILE_EXACT_FINISH    3   /* exact rescoring + finish behind the filter (D = 32), else the finish pass */
+#define VQ_PROFILE_TAIL            4   /* overflow of the undecided-row list (normally an empty launch)            */
+#define VQ_PROFILE_BACKWARD_TOKENS 5
+#define VQ_PROFILE_CODEBOOK_GRAD   6   /* incl. the fused peer exchange of a token-sharded job                      */
+#define VQ_PROFILE_SLOTS           7
+VQ_API int vq_profile_begin(int sample_every);
 VQ_API int vq_profile_end(double* search_ms_total, int64_t* search_launches, int64_t* kernel_launches);
-/* Where the search is a tensor-core filter followed by an exact rescoring + finish kernel (D = 32), the filter is
- * what vq_profile_end times; this returns the summed time of the kernel behind it (call after vq_profile_end). */
-VQ_API int vq_profile_exact(double* exact_ms_total, int64_t* exact_launches);
+VQ_API int vq_profile_slot(int slot, double* ms_total, int64_t* launches);
 
 /* ---- host-buffer entry points (end-to-end path: host pointers in, host pointers out) --------
  * Same semantics as vq_forward + vq_backward_tokens + vq_backward_codebook for token-major fp32
