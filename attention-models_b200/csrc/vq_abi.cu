@@ -41,6 +41,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // follow it) is bracketed; the other steps of the timed region run undisturbed.
 bool g_profiling = false, g_sampled = false;
 int g_profile_every = 1;
+unsigned g_profile_mask = ~0u;
 long long g_profile_calls = 0;
 long long g_launches_at_begin = 0;
 std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_slot_events[VQ_PROFILE_SLOTS];
@@ -50,7 +51,7 @@ struct SlotTimer {
     cudaStream_t s;
     int slot;
     SlotTimer(cudaStream_t stream, int which) : s(stream), slot(which) {
-        if (g_profiling && g_sampled && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, s);
+        if (g_profiling && g_sampled && ((g_profile_mask >> which) & 1u) && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, s);
     }
     void stop() {
         if (a && b) { cudaEventRecord(b, s); g_slot_events[slot].emplace_back(a, b); a = b = nullptr; }
@@ -164,7 +165,7 @@ int vq_workspace_bytes(int64_t T, int K, int D, int flags, size_t* out) {
     return VQ_OK;
 }
 
-int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb, int K, int D, int form, float beta,
+int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* weight, void* cb, int K, int D, int form, float beta,
                int flags, int64_t n_elem_total, float* z_q, int64_t* idx, float* loss, int32_t* hist, int64_t* stats,
                float* saved_zn, float* saved_denom, int64_t* seg_sums, void* ws, size_t ws_bytes, void* stream) {
     if (int r = check_dims(T, K, D)) return r;
@@ -178,8 +179,15 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
     FwdWs w = carve_forward(ws, T, K, D);
     if (ws_bytes < w.bytes) return fail(VQ_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, w.bytes);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    vq::CodebookView cbv = vq::codebook_view(const_cast<void*>(cb), K, D);
+    vq::CodebookView cbv = vq::codebook_view(cb, K, D);
     if (g_profiling) g_sampled = (g_profile_calls++ % g_profile_every) == 0;
+    // `weight` given: the codebook is prepared by this call -- in the token prep launch when the shape allows it
+    const bool fuse_prep = weight && layout == VQ_LAYOUT_TOKEN_MAJOR && vq::prep_fusable(D);
+    if (weight && !fuse_prep) {
+        SlotTimer cb_timer(s, VQ_PROFILE_PREP_CODEBOOK);
+        VQ_CUDA(vq::launch_prep_codebook(weight, cbv, s));
+        cb_timer.stop();
+    }
 
     float* zn32 = saved_zn ? saved_zn : w.zn32;
     float* denom = saved_denom ? saved_denom : w.denom;
@@ -201,7 +209,9 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const void* cb
 
     // 1. unit rows (ATen-order norms), fp16 copy for the tensor cores
     SlotTimer prep_timer(s, VQ_PROFILE_PREP_TOKENS);
-    if (layout == VQ_LAYOUT_TOKEN_MAJOR) {
+    if (fuse_prep) {
+        VQ_CUDA(vq::launch_prep_fused(weight, cbv, z, T, zn32, w.row_sq, denom, zn16, zl, s));
+    } else if (layout == VQ_LAYOUT_TOKEN_MAJOR) {
         VQ_CUDA(vq::launch_prep_tokens(z, T, D, zn32, w.row_sq, denom, zn16, zl, s));
     } else {
         if (nz) VQ_CUDA(vq::launch_zero_ranges(zl, s));
@@ -322,6 +332,34 @@ int vq_backward_codebook(const int64_t* seg_sums, const void* cb, int K, int D, 
     return VQ_OK;
 }
 
+int vq_backward(const float* g_zq, int layout, int64_t T, int64_t hw, const float* saved_zn, const float* saved_denom,
+                const int64_t* idx, const void* cb, int K, int D, int form, float beta, const float* g_loss,
+                int64_t n_elem_total, const int64_t* seg_sums, const int64_t* stats, float* grad_z, float* grad_weight,
+                float* loss, void* ws, size_t ws_bytes, void* stream) {
+    if (!seg_sums || !grad_weight) return fail(VQ_ERR_ARG, "vq_backward needs seg_sums (from vq_forward) and grad_weight");
+    if (loss && !stats) return fail(VQ_ERR_ARG, "loss needs stats");
+    if (grad_z && layout == VQ_LAYOUT_TOKEN_MAJOR && T > 0) {
+        if (int r = check_dims(T, K, D)) return r;
+        if (!saved_zn || !saved_denom || !idx || !cb) return fail(VQ_ERR_ARG, "saved_zn/saved_denom/idx/cb is NULL");
+        if (n_elem_total <= 0) return fail(VQ_ERR_ARG, "n_elem_total must be positive");
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        vq::CodebookView cbv = vq::codebook_view(const_cast<void*>(cb), K, D);
+        const float c1 = (form == VQ_FORM_VIT) ? beta : 1.f, c2 = (form == VQ_FORM_VIT) ? 1.f : beta;
+        const float coef1 = (float)((double)c1 * 2.0 / (double)n_elem_total), coef2 = (float)((double)c2 * 2.0 / (double)n_elem_total);
+        SlotTimer timer(s, VQ_PROFILE_BACKWARD_TOKENS);
+        VQ_CUDA(vq::launch_backward_fused(g_zq, saved_zn, saved_denom, idx, cbv, T, coef1, g_loss, grad_z, seg_sums, coef2,
+                                          grad_weight, stats, n_elem_total, form, beta, loss, s));
+        timer.stop();
+        return VQ_OK;
+    }
+    // other layouts (or no grad_z wanted): the two calls back to back
+    if (grad_z)
+        if (int r = vq_backward_tokens(g_zq, layout, T, hw, saved_zn, saved_denom, idx, nullptr, cb, K, D, form, beta, g_loss,
+                                       n_elem_total, grad_z, nullptr, ws, ws_bytes, stream))
+            return r;
+    return vq_backward_codebook(seg_sums, cb, K, D, form, beta, g_loss, n_elem_total, grad_weight, stats, loss, stream);
+}
+
 int vq_exchange_bytes(int K, int D, size_t* out) {
     if (!out) return fail(VQ_ERR_ARG, "out is NULL");
     if (int r = check_dims(0, K, D)) return r;
@@ -428,13 +466,14 @@ int slot_total(int slot, double* ms_total, int64_t* launches) {
 }
 }  // namespace
 
-int vq_profile_begin(int sample_every) {
+int vq_profile_begin(int sample_every, unsigned slot_mask) {
     for (auto& v : g_slot_events) {
         for (auto& p : v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
         v.clear();
     }
     g_launches_at_begin = vq::g_kernel_launches;
     g_profile_every = sample_every > 0 ? sample_every : 1;
+    g_profile_mask = slot_mask ? slot_mask : ~0u;
     g_profile_calls = 0;
     g_sampled = false;
     g_profiling = true;
@@ -568,7 +607,7 @@ int vq_host_step(const float* z_host, const float* g_zq_host, int64_t T, const f
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t t0 = c * chunk, n = (T - t0 < chunk) ? T - t0 : chunk;
         VQ_CUDA(cudaStreamWaitEvent(s, p.loaded[c], 0));
-        if (int r = vq_forward(a.z + t0 * D, VQ_LAYOUT_TOKEN_MAJOR, n, 0, a.cb, K, D, form, beta, VQ_FLAG_KEEP_STATS, n_elem,
+        if (int r = vq_forward(a.z + t0 * D, VQ_LAYOUT_TOKEN_MAJOR, n, 0, nullptr, a.cb, K, D, form, beta, VQ_FLAG_KEEP_STATS, n_elem,
                                a.zq + t0 * D, a.idx + t0, nullptr, a.hist, a.stats, bwd ? a.zn + t0 * D : nullptr,
                                bwd ? a.denom + t0 : nullptr, grad_weight_host ? a.seg : nullptr, a.fws, a.fws_bytes, s))
             return r;

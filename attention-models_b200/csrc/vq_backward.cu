@@ -58,13 +58,11 @@ static BwdWs carve(void* ws, int64_t T, int K) {
 // product is an xor-shuffle tree inside the lane group.  Algorithmic bytes 12D + 8 per token.
 // ---------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(256) k_backward_tokens(const float4* __restrict__ g, const float4* __restrict__ zn,
-                                                         const float* __restrict__ denom,
-                                                         const int64_t* __restrict__ idx, const float4* __restrict__ en,
-                                                         int64_t T, float coef_base, const float* __restrict__ g_loss,
-                                                         float4* __restrict__ grad) {
-    pdl_trigger();
-    pdl_wait();
+__device__ __forceinline__ void backward_tokens_body(const float4* __restrict__ g, const float4* __restrict__ zn,
+                                                     const float* __restrict__ denom, const int64_t* __restrict__ idx,
+                                                     const float4* __restrict__ en, int64_t T, float coef_base,
+                                                     const float* __restrict__ g_loss, float4* __restrict__ grad, int vblock,
+                                                     int vgrid) {
     const float coef = coef_base * (g_loss ? __ldg(g_loss) : 1.f);
     constexpr int kChunks = D / 4;
     constexpr int kLpr = (kChunks < 32) ? kChunks : 32;
@@ -72,8 +70,8 @@ __global__ void __launch_bounds__(256) k_backward_tokens(const float4* __restric
     constexpr int kRowsPerWarp = 32 / kLpr;
     const int lane = threadIdx.x & 31;
     const int sub = lane % kLpr, grp = lane / kLpr;
-    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t warp = (int64_t)vblock * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)vgrid * (blockDim.x >> 5);
     for (int64_t t0 = warp * kRowsPerWarp; t0 < T; t0 += n_warps * kRowsPerWarp) {
         const int64_t t = t0 + grp;
         const bool live = t < T;
@@ -90,28 +88,42 @@ __global__ void __launch_bounds__(256) k_backward_tokens(const float4* __restric
                 const float4 q = __ldg(en + k * kChunks + c);
                 float4 up = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (g) up = __ldcs(g + t * kChunks + c);
-                gz[f].x = up.x + coef * (a[f].x - q.x);
-                gz[f].y = up.y + coef * (a[f].y - q.y);
-                gz[f].z = up.z + coef * (a[f].z - q.z);
-                gz[f].w = up.w + coef * (a[f].w - q.w);
-                dot += (a[f].x * gz[f].x + a[f].y * gz[f].y) + (a[f].z * gz[f].z + a[f].w * gz[f].w);
+                // explicit roundings: the same bits from every kernel this body is inlined into (grad_z is compared
+                // bit for bit between the fused, the stand-alone and the chunked host paths)
+                gz[f].x = __fmaf_rn(coef, __fsub_rn(a[f].x, q.x), up.x);
+                gz[f].y = __fmaf_rn(coef, __fsub_rn(a[f].y, q.y), up.y);
+                gz[f].z = __fmaf_rn(coef, __fsub_rn(a[f].z, q.z), up.z);
+                gz[f].w = __fmaf_rn(coef, __fsub_rn(a[f].w, q.w), up.w);
+                dot = __fadd_rn(dot, __fadd_rn(__fmaf_rn(a[f].x, gz[f].x, __fmul_rn(a[f].y, gz[f].y)),
+                                               __fmaf_rn(a[f].z, gz[f].z, __fmul_rn(a[f].w, gz[f].w))));
             }
         }
 #pragma unroll
-        for (int off = kLpr >> 1; off > 0; off >>= 1) dot += __shfl_xor_sync(VQ_FULL, dot, off);
+        for (int off = kLpr >> 1; off > 0; off >>= 1) dot = __fadd_rn(dot, __shfl_xor_sync(VQ_FULL, dot, off));
         if (live) {
-            const float inv = 1.f / dn;
+            const float inv = __fdiv_rn(1.f, dn);
 #pragma unroll
             for (int f = 0; f < kNf4; ++f) {
                 float4 o;
-                o.x = (gz[f].x - a[f].x * dot) * inv;
-                o.y = (gz[f].y - a[f].y * dot) * inv;
-                o.z = (gz[f].z - a[f].z * dot) * inv;
-                o.w = (gz[f].w - a[f].w * dot) * inv;
+                o.x = __fmul_rn(__fmaf_rn(-a[f].x, dot, gz[f].x), inv);
+                o.y = __fmul_rn(__fmaf_rn(-a[f].y, dot, gz[f].y), inv);
+                o.z = __fmul_rn(__fmaf_rn(-a[f].z, dot, gz[f].z), inv);
+                o.w = __fmul_rn(__fmaf_rn(-a[f].w, dot, gz[f].w), inv);
                 __stcs(grad + t * kChunks + sub + kLpr * f, o);
             }
         }
     }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) k_backward_tokens(const float4* __restrict__ g, const float4* __restrict__ zn,
+                                                         const float* __restrict__ denom,
+                                                         const int64_t* __restrict__ idx, const float4* __restrict__ en,
+                                                         int64_t T, float coef_base, const float* __restrict__ g_loss,
+                                                         float4* __restrict__ grad) {
+    pdl_trigger();
+    pdl_wait();
+    backward_tokens_body<D>(g, zn, denom, idx, en, T, coef_base, g_loss, grad, blockIdx.x, gridDim.x);
 }
 
 cudaError_t launch_backward_tokens(const float* g_tok, const float* zn32, const float* denom, const int64_t* idx,
@@ -328,21 +340,25 @@ cudaError_t launch_segment_sums(const float* zn32, const int64_t* idx, const int
 // ---------------------------------------------------------------------------------------------
 // grad_E[k] = NB(E_k, coef * S_k): one warp per code
 // ---------------------------------------------------------------------------------------------
+struct CodebookGradArgs {
+    const long long* seg_sums; const float* en; const float* code_denom; int K; float coef_base; float* grad;
+    const int64_t* stats; int64_t n_elem_total; int form; float beta; float* loss;
+};
 template <int D>
-__global__ void __launch_bounds__(256) k_codebook_grad(const long long* __restrict__ seg_sums,
-                                                       const float* __restrict__ en, const float* __restrict__ code_denom,
-                                                       int K, float coef_base, const float* __restrict__ g_loss,
-                                                       float* __restrict__ grad, const int64_t* __restrict__ stats,
-                                                       int64_t n_elem_total, int form, float beta, float* __restrict__ loss) {
-    pdl_trigger();
-    pdl_wait();
-    if (loss && blockIdx.x == 0 && threadIdx.x == 0)
-        loss[0] = loss_from_fixed(stats[VQ_STAT_LOSS_FIXED], stats[VQ_STAT_NONFINITE], n_elem_total, form, beta);
-    const float coef = coef_base * (g_loss ? __ldg(g_loss) : 1.f);
+__device__ __forceinline__ void codebook_grad_body(const CodebookGradArgs& a, const float* __restrict__ g_loss, int vblock,
+                                                   int vgrid) {
+    const long long* __restrict__ seg_sums = a.seg_sums;
+    const float* __restrict__ en = a.en;
+    const float* __restrict__ code_denom = a.code_denom;
+    float* __restrict__ grad = a.grad;
+    const int K = a.K;
+    if (a.loss && vblock == 0 && threadIdx.x == 0)
+        a.loss[0] = loss_from_fixed(a.stats[VQ_STAT_LOSS_FIXED], a.stats[VQ_STAT_NONFINITE], a.n_elem_total, a.form, a.beta);
+    const float coef = a.coef_base * (g_loss ? __ldg(g_loss) : 1.f);
     constexpr int kPer = (D + 31) / 32;
     const int lane = threadIdx.x & 31;
-    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int n_warps = gridDim.x * (blockDim.x >> 5);
+    const int warp = vblock * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int n_warps = vgrid * (blockDim.x >> 5);
     for (int k = warp; k < K; k += n_warps) {
         float g[kPer], y[kPer];
         float dot = 0.f;
@@ -351,21 +367,65 @@ __global__ void __launch_bounds__(256) k_codebook_grad(const long long* __restri
             const int d = lane + 32 * j;
             g[j] = 0.f; y[j] = 0.f;
             if (d < D) {
-                const double s = (double)__ldg(seg_sums + (int64_t)k * D + d) * (1.0 / (double)(1ll << VQ_SEG_SHIFT));
-                g[j] = coef * (float)s;
+                g[j] = seg_to_grad(__ldg(seg_sums + (int64_t)k * D + d), coef);
                 y[j] = __ldg(en + (int64_t)k * D + d);
-                dot += y[j] * g[j];
+                dot = __fmaf_rn(y[j], g[j], dot);
             }
         }
         dot = warp_sum(dot);
-        const float inv = 1.f / __ldg(code_denom + k);
+        const float inv = __fdiv_rn(1.f, __ldg(code_denom + k));
         const bool poisoned = __ldg(seg_sums + (int64_t)K * D + k) != 0;
 #pragma unroll
         for (int j = 0; j < kPer; ++j) {
             const int d = lane + 32 * j;
-            if (d < D) grad[(int64_t)k * D + d] = poisoned ? __int_as_float(0x7fc00000) : (g[j] - y[j] * dot) * inv;
+            if (d < D) grad[(int64_t)k * D + d] = poisoned ? __int_as_float(0x7fc00000) : grad_row_element(g[j], y[j], dot, inv);
         }
     }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) k_codebook_grad(CodebookGradArgs a, const float* __restrict__ g_loss) {
+    pdl_trigger();
+    pdl_wait();
+    codebook_grad_body<D>(a, g_loss, blockIdx.x, gridDim.x);
+}
+
+// grad_z on blocks [cbg_blocks, grid), grad_E (and the loss) on blocks [0, cbg_blocks): the backward of a step whose
+// segment sums came from the forward, in one launch
+template <int D>
+__global__ void __launch_bounds__(256) k_backward_fused(CodebookGradArgs a, int cbg_blocks, const float4* __restrict__ g,
+                                                        const float4* __restrict__ zn, const float* __restrict__ denom,
+                                                        const int64_t* __restrict__ idx, const float4* __restrict__ en4,
+                                                        int64_t T, float coef_commit, const float* __restrict__ g_loss,
+                                                        float4* __restrict__ grad_tok) {
+    pdl_trigger();
+    pdl_wait();
+    if ((int)blockIdx.x < cbg_blocks) codebook_grad_body<D>(a, g_loss, blockIdx.x, cbg_blocks);
+    else backward_tokens_body<D>(g, zn, denom, idx, en4, T, coef_commit, g_loss, grad_tok, blockIdx.x - cbg_blocks, gridDim.x - cbg_blocks);
+}
+
+cudaError_t launch_backward_fused(const float* g_tok, const float* zn32, const float* denom, const int64_t* idx,
+                                  const CodebookView& cb, int64_t T, float coef_commit, const float* g_loss, float* grad_tok,
+                                  const int64_t* seg_sums, float coef_codebook, float* grad_weight, const int64_t* stats,
+                                  int64_t n_elem_total, int form, float beta, float* loss, cudaStream_t s) {
+    const int chunks = cb.D / 4;
+    const int lpr = chunks < 32 ? chunks : 32;
+    const int rows_per_block = 8 * (32 / lpr);
+    int64_t tok_blocks = (T + rows_per_block - 1) / rows_per_block;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (tok_blocks > cap) tok_blocks = cap;
+    if (tok_blocks < 1) tok_blocks = 1;
+    int cbg_blocks = (cb.K + 7) / 8;
+    if (cbg_blocks > sm_count() * 2) cbg_blocks = sm_count() * 2;
+    CodebookGradArgs a{reinterpret_cast<const long long*>(seg_sums), cb.en32, cb.code_denom, cb.K, coef_codebook, grad_weight,
+                       stats, n_elem_total, form, beta, stats ? loss : nullptr};
+    cudaError_t e = cudaSuccess;
+    VQ_DISPATCH_D(cb.D, (e = launch_pdl(k_backward_fused<kD>, dim3((unsigned)(cbg_blocks + tok_blocks)), dim3(256), 0, s, a, cbg_blocks,
+                                        reinterpret_cast<const float4*>(g_tok), reinterpret_cast<const float4*>(zn32), denom, idx,
+                                        reinterpret_cast<const float4*>(cb.en32), T, coef_commit, g_loss,
+                                        reinterpret_cast<float4*>(grad_tok))));
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_codebook_grad(const int64_t* seg_sums, const CodebookView& cb, float coef, const float* g_loss,
@@ -375,9 +435,9 @@ cudaError_t launch_codebook_grad(const int64_t* seg_sums, const CodebookView& cb
     const int cap = sm_count() * 8;
     if (blocks > cap) blocks = cap;
     cudaError_t e = cudaSuccess;
-    VQ_DISPATCH_D(cb.D, (e = launch_pdl(k_codebook_grad<kD>, dim3(blocks), dim3(256), 0, s,
-                                        reinterpret_cast<const long long*>(seg_sums), cb.en32, cb.code_denom, cb.K, coef, g_loss,
-                                        grad_weight, stats, n_elem_total, form, beta, stats ? loss : nullptr)));
+    CodebookGradArgs a{reinterpret_cast<const long long*>(seg_sums), cb.en32, cb.code_denom, cb.K, coef, grad_weight,
+                       stats, n_elem_total, form, beta, stats ? loss : nullptr};
+    VQ_DISPATCH_D(cb.D, (e = launch_pdl(k_codebook_grad<kD>, dim3(blocks), dim3(256), 0, s, a, g_loss)));
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }

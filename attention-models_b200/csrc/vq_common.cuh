@@ -155,8 +155,8 @@ __device__ __forceinline__ void seg_add(unsigned long long* __restrict__ slot, f
 
 // Buffers a forward zeroes before use (stats, histogram, segment sums, fallback-list counters), cleared by the
 // first kernel of the call instead of one memset node each.  Sizes in bytes, multiples of 4.
-__device__ __forceinline__ void zero_ranges(const ZeroList& zl) {
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n_thr = (size_t)gridDim.x * blockDim.x;
+__device__ __forceinline__ void zero_ranges(const ZeroList& zl, int vblock, int vgrid) {
+    const size_t tid = (size_t)vblock * blockDim.x + threadIdx.x, n_thr = (size_t)vgrid * blockDim.x;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         if (!zl.ptr[i]) continue;
@@ -197,8 +197,17 @@ __device__ __forceinline__ float loss_from_fixed(long long loss_fixed, long long
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(VQ_FULL, v, off);
+    for (int off = 16; off > 0; off >>= 1) v = __fadd_rn(v, __shfl_xor_sync(VQ_FULL, v, off));
     return v;
+}
+
+// Pieces of grad_E[k] = (g - y (y . g)) / max(||E_k||, eps), g = coef * S_k, with every rounding explicit: the
+// single-GPU kernel, the fused backward and the sharded exchange kernel must give the same bits.
+__device__ __forceinline__ float seg_to_grad(long long seg_sum, float coef) {
+    return __fmul_rn(coef, (float)((double)seg_sum * (1.0 / (double)(1ll << VQ_SEG_SHIFT))));
+}
+__device__ __forceinline__ float grad_row_element(float g, float y, float dot, float inv) {
+    return __fmul_rn(__fmaf_rn(-y, dot, g), inv);
 }
 
 }  // namespace vq

@@ -37,6 +37,10 @@ struct ZeroList {
 cudaError_t launch_prep_tokens(const float* z, int64_t T, int D, float* zn32, float* row_sq, float* denom,
                                __half* zn16, const ZeroList& zl, cudaStream_t s);
 cudaError_t launch_zero_ranges(const ZeroList& zl, cudaStream_t s);
+// codebook + token preparation in one launch (training step; token-major rows, prep_fusable(D))
+bool prep_fusable(int D);
+cudaError_t launch_prep_fused(const float* weight, const CodebookView& cb, const float* z, int64_t T, float* zn32, float* row_sq,
+                              float* denom, __half* zn16, const ZeroList& zl, cudaStream_t s);
 // NCHW (b, D, hw): denominators in ATen's channel-strided order (schedule chosen from T, hw, D)
 cudaError_t launch_norm_nchw(const float* z, int64_t T, int64_t hw, int D, float* denom, cudaStream_t s);
 // (b, D, hw) -> (T, D), optionally divided by denom[t]; optional fp16 copy
@@ -96,6 +100,11 @@ size_t backward_workspace_bytes(int64_t T, int K, int D);
 cudaError_t launch_backward_tokens(const float* g_tok, const float* zn32, const float* denom, const int64_t* idx,
                                    const CodebookView& cb, int64_t T, float coef_commit, const float* g_loss,
                                    float* grad_tok, cudaStream_t s);
+// grad_z and grad_E (+ loss) in one launch, for segment sums that already exist (vq_forward's)
+cudaError_t launch_backward_fused(const float* g_tok, const float* zn32, const float* denom, const int64_t* idx,
+                                  const CodebookView& cb, int64_t T, float coef_commit, const float* g_loss, float* grad_tok,
+                                  const int64_t* seg_sums, float coef_codebook, float* grad_weight, const int64_t* stats,
+                                  int64_t n_elem_total, int form, float beta, float* loss, cudaStream_t s);
 cudaError_t launch_segment_sums(const float* zn32, const int64_t* idx, const int32_t* hist, const CodebookView& cb,
                                 int64_t T, int64_t* seg_sums, void* ws, size_t ws_bytes, cudaStream_t s);
 // grad_E from the segment sums; with `loss` also the loss from stats (the former k_loss_finalize launch)
@@ -107,6 +116,7 @@ cudaError_t launch_codebook_grad(const int64_t* seg_sums, const CodebookView& cb
 // byte layout of one rank's exchange buffer (see vq_peer.cu); offsets of stats / hist are relative to the slot
 struct ExchangeLayout {
     size_t seg_bytes, stats_off, hist_off, slot_bytes, slot0_off, total;
+    size_t results_off, results_hist_off;      // grad_E (K*D fp32) and, results_hist_off behind it, the histogram (K int64)
 };
 ExchangeLayout exchange_layout(int K, int D);
 cudaError_t launch_codebook_grad_sharded(const void* const* peer_bufs, int world, int rank, int slot, unsigned epoch,
@@ -135,7 +145,9 @@ int sm_count();
 // scheduled while its predecessor in the stream drains (that predecessor calls pdl_trigger()), and must call
 // pdl_wait() before it touches anything an earlier kernel wrote -- the wait returns when the predecessor grid has
 // completed and flushed.  Every such kernel waits, so completion stays transitive along the stream; kernels launched
-// the classic way are unaffected.  VQ_PDL=0 in the environment turns the attribute off (debugging).
+// the classic way are unaffected.  Off by default: with 5 launches per step the measured gain is < 1 us of 245 us
+// (the stream has no gaps to hide once the launches are queued ahead), and overlapping grids blur per-kernel
+// timings; VQ_PDL=1 in the environment turns the attribute on.
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {

@@ -7,16 +7,23 @@
 // models/vitvqgan.py:154,162-166 that autograd derives.
 //
 // Every rank owns one exchange buffer (cudaMalloc, exported with CUDA IPC, mapped by all peers):
-//     [ flags: 16 x 128 B ][ slot 0 ][ slot 1 ]      slot = [ seg_sums (K*D + K) int64 | stats 8 int64 | hist K int32 ]
-// vq_forward writes seg_sums / stats / hist of step n straight into slot n & 1.  The kernel then
-//   1. block 0 publishes "rank r finished step n" into every peer's flags[r] (st.release.sys after a system fence);
-//      every block waits until its own flags[] show all peers at step n (ld.acquire.sys; bounded spin);
-//   2. one warp per code pulls that code's int64 sums from every rank (256-byte coalesced NVLink reads, all ranks'
-//      loads in flight before the first add), adds them -- integer adds: exact, order-free, so every rank computes
-//      bit-identical totals without a broadcast -- and applies grad_E[k] = NB(E_k, coef * S_k);
-//   3. the histogram and the loss partial are summed the same way.
-// Two slots make a trailing barrier unnecessary: a rank overwrites slot s at step n + 2, after its step n + 1 kernel
-// saw every peer publish step n + 1, i.e. after every peer's step n kernel (which read slot s) had completed.
+//     [ control: ready flags 16 x 128 B | done flags 16 x 128 B | counters ][ results ][ slot 0 ][ slot 1 ]
+//     slot    = [ seg_sums (K*D + K) int64 | stats 8 int64 | hist K int32 ]      this rank's partials of a step
+//     results = [ grad_E K*D fp32 | histogram K int64 ]                            written by the slice owners
+// vq_forward writes seg_sums / stats / hist of step n straight into slot n & 1.  The kernel (one CTA per SM) is a
+// reduce-scatter + all-gather in two phases, W ranks, rank r owning the codes [r K/W, (r+1) K/W):
+//   1. block 0 publishes "rank r's partials of step n are ready" into every peer's ready[r] (st.release.sys after a
+//      system fence); every block waits until its own ready[] shows all peers at step n (ld.acquire.sys, bounded spin);
+//   2. one warp per owned code pulls that code's int64 sums from every rank (256-byte coalesced NVLink reads, all
+//      ranks' loads in flight before the first add), adds them -- integer adds: exact and order-free, so the totals
+//      are bit-identical to a single-GPU run on the concatenated batch -- applies grad_E[k] = NB(E_k, coef * S_k) and
+//      stores the fp32 row into EVERY rank's results (128-byte NVLink writes); same for the histogram slice;
+//   3. the last block of the rank to finish publishes done[r] to every peer; every block waits for all done[] flags and
+//      copies the complete results from its own buffer to the caller's grad_weight / histogram.
+// Per rank this moves (W-1)/W x (8D + 12) K bytes in and (W-1)/W x (4D + 8) K bytes out -- 2.8 MB at 8192 x 32 on 8
+// GPUs, against 15 MB for an all-gather of the partials -- and needs two flag round trips.  A rank reuses a slot or
+// the results only after its next kernel saw every peer's ready flag of the next step, i.e. after every peer's
+// previous kernel -- which read them -- had completed.
 #include <cstdio>
 
 #include "vq_common.cuh"
@@ -27,7 +34,8 @@ namespace vq {
 
 namespace {
 constexpr size_t kFlagStride = 128;
-constexpr size_t kFlagsBytes = VQ_PEER_MAX_RANKS * kFlagStride;
+constexpr size_t kReadyOff = 0, kDoneOff = VQ_PEER_MAX_RANKS * kFlagStride, kCounterOff = 2 * VQ_PEER_MAX_RANKS * kFlagStride;
+constexpr size_t kControlBytes = kCounterOff + 256;
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 }  // namespace
 
@@ -37,8 +45,10 @@ ExchangeLayout exchange_layout(int K, int D) {
     L.stats_off = align256(L.seg_bytes);
     L.hist_off = L.stats_off + align256(sizeof(int64_t) * VQ_STATS_LEN);
     L.slot_bytes = L.hist_off + align256(sizeof(int32_t) * (size_t)K);
-    L.slot0_off = kFlagsBytes;
-    L.total = kFlagsBytes + 2 * L.slot_bytes;
+    L.results_off = kControlBytes;
+    L.results_hist_off = align256(sizeof(float) * (size_t)K * D);
+    L.slot0_off = L.results_off + L.results_hist_off + align256(sizeof(int64_t) * (size_t)K);
+    L.total = L.slot0_off + 2 * L.slot_bytes;
     return L;
 }
 
@@ -57,117 +67,215 @@ __device__ __forceinline__ int ld_peer_s32(const int* p) {
     return v;
 }
 
+__device__ __forceinline__ void st_peer_f32(float* p, float v) {
+    asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_peer_s64(long long* p, long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// wait until flags[r] >= epoch for every peer r (warp 0 of the block; returns false on timeout)
+__device__ __forceinline__ bool wait_flags(const char* own_base, size_t flags_off, int world, int rank, unsigned epoch) {
+    const int lane = threadIdx.x & 31;
+    bool ok = true;
+    if (lane < world && lane != rank) {
+        const unsigned* f = reinterpret_cast<const unsigned*>(own_base + flags_off + (size_t)lane * kFlagStride);
+        const long long t0 = clock64();
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if ((int)(v - epoch) >= 0) break;
+            if (clock64() - t0 > 6000000000ll) { ok = false; break; }   // ~3 s: a peer died; do not hang the GPU
+            __nanosleep(32);
+        }
+    }
+    return __all_sync(VQ_FULL, ok);
+}
+__device__ __forceinline__ void publish_flags(const PeerPtrs& peers, size_t flags_off, int world, int rank, unsigned epoch) {
+    const int lane = threadIdx.x & 31;
+    if (lane < world && lane != rank) {
+        __threadfence_system();
+        unsigned* f = reinterpret_cast<unsigned*>(const_cast<char*>(peers.base[lane]) + flags_off + (size_t)rank * kFlagStride);
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+    }
+}
+
 template <int D>
-__global__ void __launch_bounds__(256) k_codebook_grad_sharded(PeerPtrs peers, int world, int rank, size_t slot_off,
-                                                               size_t stats_off, size_t hist_off, unsigned epoch,
-                                                               const float* __restrict__ en,
+__global__ void __launch_bounds__(512) k_codebook_grad_sharded(PeerPtrs peers, int world, int rank, ExchangeLayout L, int slot,
+                                                               unsigned epoch, const float* __restrict__ en,
                                                                const float* __restrict__ code_denom, int K, float coef_base,
                                                                const float* __restrict__ g_loss, int64_t n_elem_total,
                                                                int form, float beta, float* __restrict__ grad,
                                                                int64_t* __restrict__ hist_total, float* __restrict__ loss,
                                                                int64_t* __restrict__ stats_total) {
+    __shared__ int s_last;
     const int lane = threadIdx.x & 31;
-    // ---- 1. publish / wait ----
+#ifdef VQ_PEER_TRACE
+    auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    unsigned long long tr[5] = {now(), 0, 0, 0, 0};
+#endif
+    const size_t slot_off = L.slot0_off + (size_t)slot * L.slot_bytes;
+    char* own = const_cast<char*>(peers.base[rank]);
+    bool timed_out = false;
+    // ---- 1. partials ready everywhere ----
     if (world > 1) {
         if (threadIdx.x < 32) {
-            const bool is_peer = lane < world && lane != rank;
-            if (blockIdx.x == 0 && is_peer) {
-                __threadfence_system();
-                unsigned* theirs = reinterpret_cast<unsigned*>(const_cast<char*>(peers.base[lane]) + (size_t)rank * kFlagStride);
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
-            }
-            bool ok = true;
-            if (is_peer) {
-                const unsigned* mine = reinterpret_cast<const unsigned*>(peers.base[rank] + (size_t)lane * kFlagStride);
-                const long long t0 = clock64();
-                unsigned v;
-                for (;;) {
-                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-                    if ((int)(v - epoch) >= 0) break;
-                    if (clock64() - t0 > 6000000000ll) { ok = false; break; }   // ~3 s: a peer died; do not hang the GPU
-                    __nanosleep(64);
-                }
-            }
-            if (!__all_sync(VQ_FULL, ok) && lane == 0 && stats_total)
-                atomicAdd(reinterpret_cast<unsigned long long*>(stats_total + VQ_STAT_PEER_TIMEOUT), 1ull);
+            if (blockIdx.x == 0) publish_flags(peers, kReadyOff, world, rank, epoch);
+            timed_out = !wait_flags(own, kReadyOff, world, rank, epoch);
         }
         __syncthreads();
     }
-    // ---- 2. grad_E, one warp per code ----
+#ifdef VQ_PEER_TRACE
+    tr[1] = now();
+#endif
+    // ---- 2. owned slice: totals over ranks, grad_E rows and histogram to every rank's results ----
+    // A remote read is ~2 us away: a warp keeps kC codes x kR ranks of loads in flight and the grid is sized so that a
+    // warp has at most a couple of iterations.
     const float coef = coef_base * (g_loss ? __ldg(g_loss) : 1.f);
     constexpr int kPer = (D + 31) / 32;
+    constexpr int kC = (kPer <= 2) ? 2 : 1;
+    constexpr int kR = (16 / (kPer * kC)) > 8 ? 8 : (16 / (kPer * kC));
+    const int per_rank = (K + world - 1) / world;
+    const int k_lo = min(K, rank * per_rank), k_hi = min(K, k_lo + per_rank);
     const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int n_warps = gridDim.x * (blockDim.x >> 5);
-    for (int k = warp; k < K; k += n_warps) {
-        long long s[kPer], bad = 0;
+    for (int k0 = k_lo + warp * kC; k0 < k_hi; k0 += n_warps * kC) {
+        long long s[kC][kPer], bad[kC];
 #pragma unroll
-        for (int j = 0; j < kPer; ++j) s[j] = 0;
-        for (int r0 = 0; r0 < world; r0 += 4) {          // 4 ranks' loads in flight per batch
-            long long v[4][kPer], b[4];
+        for (int c = 0; c < kC; ++c) {
+            bad[c] = 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int j = 0; j < kPer; ++j) s[c][j] = 0;
+        }
+        for (int r0 = 0; r0 < world; r0 += kR) {
+            long long v[kR][kC][kPer], b[kR][kC];
+#pragma unroll
+            for (int u = 0; u < kR; ++u) {
                 const int r = r0 + u;
-                b[u] = 0;
+                const long long* seg = reinterpret_cast<const long long*>(peers.base[r < world ? r : rank] + slot_off);
 #pragma unroll
-                for (int j = 0; j < kPer; ++j) v[u][j] = 0;
-                if (r < world) {
-                    const long long* seg = reinterpret_cast<const long long*>(peers.base[r] + slot_off);
+                for (int c = 0; c < kC; ++c) {
+                    const int k = k0 + c;
+                    b[u][c] = 0;
 #pragma unroll
                     for (int j = 0; j < kPer; ++j) {
                         const int d = lane + 32 * j;
-                        if (d < D) v[u][j] = ld_peer_s64(seg + (int64_t)k * D + d);
+                        v[u][c][j] = 0;
+                        if (r < world && k < k_hi && d < D) v[u][c][j] = ld_peer_s64(seg + (int64_t)k * D + d);
                     }
-                    if (lane == 0) b[u] = ld_peer_s64(seg + (int64_t)K * D + k);
+                    if (r < world && k < k_hi && lane == 0) b[u][c] = ld_peer_s64(seg + (int64_t)K * D + k);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                bad += b[u];
+            for (int u = 0; u < kR; ++u)
 #pragma unroll
-                for (int j = 0; j < kPer; ++j) s[j] += v[u][j];
-            }
+                for (int c = 0; c < kC; ++c) {
+                    bad[c] += b[u][c];
+#pragma unroll
+                    for (int j = 0; j < kPer; ++j) s[c][j] += v[u][c][j];
+                }
         }
-        float g[kPer], y[kPer];
-        float dot = 0.f;
 #pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-            const int d = lane + 32 * j;
-            g[j] = 0.f; y[j] = 0.f;
-            if (d < D) {
-                g[j] = coef * (float)((double)s[j] * (1.0 / (double)(1ll << VQ_SEG_SHIFT)));
-                y[j] = __ldg(en + (int64_t)k * D + d);
-                dot += y[j] * g[j];
+        for (int c = 0; c < kC; ++c) {
+            const int k = k0 + c;
+            if (k >= k_hi) break;
+            float g[kPer], y[kPer];
+            float dot = 0.f;
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) {
+                const int d = lane + 32 * j;
+                g[j] = 0.f; y[j] = 0.f;
+                if (d < D) {
+                    g[j] = seg_to_grad(s[c][j], coef);
+                    y[j] = __ldg(en + (int64_t)k * D + d);
+                    dot = __fmaf_rn(y[j], g[j], dot);
+                }
             }
-        }
-        dot = warp_sum(dot);
-        const float inv = 1.f / __ldg(code_denom + k);
-        const bool poisoned = __shfl_sync(VQ_FULL, bad, 0) != 0;
+            dot = warp_sum(dot);
+            const float inv = __fdiv_rn(1.f, __ldg(code_denom + k));
+            const bool poisoned = __shfl_sync(VQ_FULL, bad[c], 0) != 0;
 #pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-            const int d = lane + 32 * j;
-            if (d < D) grad[(int64_t)k * D + d] = poisoned ? __int_as_float(0x7fc00000) : (g[j] - y[j] * dot) * inv;
+            for (int j = 0; j < kPer; ++j) {
+                const int d = lane + 32 * j;
+                if (d < D) {
+                    const float out = poisoned ? __int_as_float(0x7fc00000) : grad_row_element(g[j], y[j], dot, inv);
+                    if (world == 1) grad[(int64_t)k * D + d] = out;
+                    else
+                        for (int r = 0; r < world; ++r)
+                            st_peer_f32(reinterpret_cast<float*>(const_cast<char*>(peers.base[r]) + L.results_off) + (int64_t)k * D + d, out);
+                }
+            }
         }
     }
-    // ---- 3. histogram and loss ----
     if (hist_total)
-        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
-            int64_t h = 0;
-            for (int r = 0; r < world; ++r)
-                h += ld_peer_s32(reinterpret_cast<const int*>(peers.base[r] + slot_off + hist_off) + k);
-            hist_total[k] = h;
+        for (int k = k_lo + blockIdx.x * blockDim.x + threadIdx.x; k < k_hi; k += gridDim.x * blockDim.x) {
+            int hv[VQ_PEER_MAX_RANKS];
+#pragma unroll
+            for (int r = 0; r < VQ_PEER_MAX_RANKS; ++r)
+                hv[r] = r < world ? ld_peer_s32(reinterpret_cast<const int*>(peers.base[r] + slot_off + L.hist_off) + k) : 0;
+            long long h = 0;
+#pragma unroll
+            for (int r = 0; r < VQ_PEER_MAX_RANKS; ++r) h += hv[r];
+            if (world == 1) hist_total[k] = h;
+            else
+                for (int r = 0; r < world; ++r)
+                    st_peer_s64(reinterpret_cast<long long*>(const_cast<char*>(peers.base[r]) + L.results_off + L.results_hist_off) + k, h);
         }
-    if (blockIdx.x == 0 && threadIdx.x < VQ_STATS_LEN && (stats_total || loss)) {
+    // loss and summed statistics: 8 integers per rank, every rank adds them itself (the last warp of the last block,
+    // so that no block's slice waits behind them)
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x >= blockDim.x - 32 && (stats_total || loss)) {
         __shared__ long long tot[VQ_STATS_LEN];
-        long long t = 0;
-        for (int r = 0; r < world; ++r)
-            t += ld_peer_s64(reinterpret_cast<const long long*>(peers.base[r] + slot_off + stats_off) + threadIdx.x);
-        tot[threadIdx.x] = t;
-        if (stats_total && threadIdx.x != VQ_STAT_PEER_TIMEOUT) stats_total[threadIdx.x] = t;
-        __syncwarp((1u << VQ_STATS_LEN) - 1u);
-        if (threadIdx.x == 0 && loss) {
-            loss[0] = loss_from_fixed(tot[VQ_STAT_LOSS_FIXED], tot[VQ_STAT_NONFINITE], n_elem_total, form, beta);
+        if (lane < VQ_STATS_LEN) {
+            long long sv[VQ_PEER_MAX_RANKS];
+#pragma unroll
+            for (int r = 0; r < VQ_PEER_MAX_RANKS; ++r)
+                sv[r] = r < world ? ld_peer_s64(reinterpret_cast<const long long*>(peers.base[r] + slot_off + L.stats_off) + lane) : 0;
+            long long t = 0;
+#pragma unroll
+            for (int r = 0; r < VQ_PEER_MAX_RANKS; ++r) t += sv[r];
+            tot[lane] = t;
+            if (stats_total && lane != VQ_STAT_PEER_TIMEOUT) stats_total[lane] = t;
         }
+        __syncwarp();
+        if (lane == 0 && loss)
+            loss[0] = loss_from_fixed(tot[VQ_STAT_LOSS_FIXED], tot[VQ_STAT_NONFINITE], n_elem_total, form, beta);
     }
+    if (world == 1) return;
+    // ---- 3. slices complete everywhere, then results -> caller's tensors ----
+#ifdef VQ_PEER_TRACE
+    tr[2] = now();
+#endif
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned* counter = reinterpret_cast<unsigned*>(own + kCounterOff);
+        s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+        if (s_last) *counter = 0;                        // ready for the next launch
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        if (s_last) publish_flags(peers, kDoneOff, world, rank, epoch);
+        timed_out |= !wait_flags(own, kDoneOff, world, rank, epoch);
+        if (timed_out && lane == 0 && stats_total)
+            atomicAdd(reinterpret_cast<unsigned long long*>(stats_total + VQ_STAT_PEER_TIMEOUT), 1ull);
+    }
+    __syncthreads();
+#ifdef VQ_PEER_TRACE
+    tr[3] = now();
+#endif
+    const float4* res = reinterpret_cast<const float4*>(own + L.results_off);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * D / 4; i += gridDim.x * blockDim.x)
+        reinterpret_cast<float4*>(grad)[i] = __ldcg(res + i);
+    if (hist_total) {
+        const long long* rh = reinterpret_cast<const long long*>(own + L.results_off + L.results_hist_off);
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) hist_total[k] = __ldcg(rh + k);
+    }
+#ifdef VQ_PEER_TRACE
+    tr[4] = now();
+    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && epoch >= 10 && epoch < 14)
+        printf("rank %d epoch %u block %d: ready-wait %llu ns, slice %llu ns, done-wait %llu ns, copy %llu ns\n", rank, epoch,
+               blockIdx.x, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3]);
+#endif
 }
 
 cudaError_t launch_codebook_grad_sharded(const void* const* peer_bufs, int world, int rank, int slot, unsigned epoch,
@@ -177,17 +285,20 @@ cudaError_t launch_codebook_grad_sharded(const void* const* peer_bufs, int world
     const ExchangeLayout L = exchange_layout(cb.K, cb.D);
     PeerPtrs p;
     for (int r = 0; r < VQ_PEER_MAX_RANKS; ++r) p.base[r] = r < world ? static_cast<const char*>(peer_bufs[r]) : nullptr;
-    int blocks = (cb.K + 7) / 8;
-    const int cap = sm_count() * 8;
-    if (blocks > cap) blocks = cap;
+    // one CTA per SM: every block of the grid is resident, so the in-kernel waits of phase 3 cannot starve a block
+    // that still has phase-2 work (they only ever wait for kernels of other GPUs)
+    int blocks = sm_count();
+    if (world == 1) {
+        blocks = (cb.K + 7) / 8;
+        if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+    }
     if (stats_total) {
         cudaError_t e = cudaMemsetAsync(stats_total + VQ_STAT_PEER_TIMEOUT, 0, sizeof(int64_t), s);
         if (e != cudaSuccess) return e;
     }
-    VQ_DISPATCH_D(cb.D, (k_codebook_grad_sharded<kD><<<blocks, 256, 0, s>>>(
-                            p, world, rank, L.slot0_off + (size_t)slot * L.slot_bytes, L.stats_off, L.hist_off, epoch, cb.en32,
-                            cb.code_denom, cb.K, coef, g_loss, n_elem_total, form, beta, grad_weight, hist_total, loss,
-                            stats_total)));
+    VQ_DISPATCH_D(cb.D, (k_codebook_grad_sharded<kD><<<blocks, world == 1 ? 256 : 512, 0, s>>>(
+                            p, world, rank, L, slot, epoch, cb.en32, cb.code_denom, cb.K, coef, g_loss, n_elem_total, form, beta,
+                            grad_weight, hist_total, loss, stats_total)));
     count_launch();
     return cudaGetLastError();
 }

@@ -16,7 +16,7 @@ namespace vq {
 
 long long g_kernel_launches = 0;
 bool pdl_enabled() {
-    static const bool on = !(getenv("VQ_PDL") && atoi(getenv("VQ_PDL")) == 0);
+    static const bool on = getenv("VQ_PDL") && atoi(getenv("VQ_PDL")) != 0;
     return on;
 }
 static int g_sm_count = 0;
@@ -67,11 +67,11 @@ CodebookView codebook_view(void* cb, int K, int D) {
 
 // Codebook preparation: block b leaves its count of non-unit codes in info[b] (grid <= kInfoSlots; block 0 clears
 // the unused slots), so the count needs neither atomics nor a zeroed buffer.
-__device__ __forceinline__ void write_info(int* __restrict__ info, int n_bad) {
+__device__ __forceinline__ void write_info(int* __restrict__ info, int n_bad, int vblock, int vgrid) {
     const int total = __syncthreads_count(n_bad != 0);
-    if (threadIdx.x == 0) info[blockIdx.x] = total;
-    if (blockIdx.x == 0)
-        for (int i = gridDim.x + threadIdx.x; i < kInfoSlots; i += blockDim.x) info[i] = 0;
+    if (threadIdx.x == 0) info[vblock] = total;
+    if (vblock == 0)
+        for (int i = vgrid + threadIdx.x; i < kInfoSlots; i += blockDim.x) info[i] = 0;
 }
 
 // One warp per row, kRows rows in flight per warp for memory-level parallelism.
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) k_prep_rows(const float* __restrict__ in,
     const int lane = threadIdx.x & 31;
     pdl_trigger();
     pdl_wait();
-    if (!kIsCodebook) zero_ranges(zl);
+    if (!kIsCodebook) zero_ranges(zl, blockIdx.x, gridDim.x);
     int n_bad = 0;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) k_prep_rows(const float* __restrict__ in,
             }
         }
     }
-    if (kIsCodebook) write_info(info, n_bad);
+    if (kIsCodebook) write_info(info, n_bad, blockIdx.x, gridDim.x);
 }
 
 // D < 128 (ATen's non-vectorised schedule): D/4 lanes share a row, one float4 each, 32/(D/4) rows per
@@ -119,24 +119,23 @@ __global__ void __launch_bounds__(256) k_prep_rows(const float* __restrict__ in,
 // first and then runs the shuffle-down tree with element offsets W/2 ... 1.  With 4 consecutive elements
 // per thread those offsets become: thread offsets (D/4)/2 ... 1 (which include the per-lane fold when
 // D = 64), then the two in-thread steps (x0+x2, x1+x3) and their sum -- bit-identical to ATen.
+// The body works on a virtual (block, grid) so that one launch can prepare the codebook on its first blocks and the
+// token rows on the others (k_prep_rows_fused).
 template <int D, bool kIsCodebook>
-__global__ void __launch_bounds__(256) k_prep_rows_small(const float4* __restrict__ in, int64_t rows,
-                                                         float4* __restrict__ unit32, float* __restrict__ sq,
-                                                         float* __restrict__ denom, uint2* __restrict__ unit16,
-                                                         int* __restrict__ info, float4* __restrict__ en32c,
-                                                         float* __restrict__ csq_cell, ZeroList zl) {
+__device__ __forceinline__ void prep_rows_small_body(const float4* __restrict__ in, int64_t rows,
+                                                     float4* __restrict__ unit32, float* __restrict__ sq,
+                                                     float* __restrict__ denom, uint2* __restrict__ unit16,
+                                                     int* __restrict__ info, float4* __restrict__ en32c,
+                                                     float* __restrict__ csq_cell, int vblock, int vgrid) {
     static_assert(D == 16 || D == 32 || D == 64, "small-row prep covers D < 128");
-    pdl_trigger();
-    pdl_wait();
-    if (!kIsCodebook) zero_ranges(zl);
     int n_bad = 0;
     constexpr int kLpr = D / 4;
     constexpr int kRpw = 32 / kLpr;
     constexpr int kUnroll = 4;
     const int lane = threadIdx.x & 31;
     const int sub = lane % kLpr, grp = lane / kLpr;
-    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t warp = (int64_t)vblock * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)vgrid * (blockDim.x >> 5);
     auto tree = [&](float4 v) {
 #pragma unroll
         for (int off = kLpr >> 1; off > 0; off >>= 1) {
@@ -189,7 +188,40 @@ __global__ void __launch_bounds__(256) k_prep_rows_small(const float4* __restric
             }
         }
     }
-    if (kIsCodebook) write_info(info, n_bad);
+    if (kIsCodebook) write_info(info, n_bad, vblock, vgrid);
+}
+
+template <int D, bool kIsCodebook>
+__global__ void __launch_bounds__(256) k_prep_rows_small(const float4* __restrict__ in, int64_t rows,
+                                                         float4* __restrict__ unit32, float* __restrict__ sq,
+                                                         float* __restrict__ denom, uint2* __restrict__ unit16,
+                                                         int* __restrict__ info, float4* __restrict__ en32c,
+                                                         float* __restrict__ csq_cell, ZeroList zl) {
+    pdl_trigger();
+    pdl_wait();
+    if (!kIsCodebook) zero_ranges(zl, blockIdx.x, gridDim.x);
+    prep_rows_small_body<D, kIsCodebook>(in, rows, unit32, sq, denom, unit16, info, en32c, csq_cell, blockIdx.x, gridDim.x);
+}
+
+// codebook rows on blocks [0, cb_blocks), token rows on the rest: the two preparations of a training step in one launch
+struct PrepRowsArgs {
+    const float4* in; int64_t rows; float4* unit32; float* sq; float* denom; uint2* unit16;
+};
+template <int D>
+__global__ void __launch_bounds__(256) k_prep_rows_fused(PrepRowsArgs cbk, int* __restrict__ info, float4* __restrict__ en32c,
+                                                         float* __restrict__ csq_cell, int cb_blocks, PrepRowsArgs tok,
+                                                         ZeroList zl) {
+    pdl_trigger();
+    pdl_wait();
+    if ((int)blockIdx.x < cb_blocks) {
+        prep_rows_small_body<D, true>(cbk.in, cbk.rows, cbk.unit32, cbk.sq, cbk.denom, cbk.unit16, info, en32c, csq_cell,
+                                      blockIdx.x, cb_blocks);
+    } else {
+        const int vblock = blockIdx.x - cb_blocks, vgrid = gridDim.x - cb_blocks;
+        zero_ranges(zl, vblock, vgrid);
+        prep_rows_small_body<D, false>(tok.in, tok.rows, tok.unit32, tok.sq, tok.denom, tok.unit16, nullptr, nullptr, nullptr,
+                                       vblock, vgrid);
+    }
 }
 
 template <int D, bool kIsCodebook>
@@ -239,7 +271,37 @@ cudaError_t launch_prep_tokens(const float* z, int64_t T, int D, float* zn32, fl
     return cudaSuccess;
 }
 
-__global__ void __launch_bounds__(256) k_zero_ranges(ZeroList zl) { zero_ranges(zl); }
+// Codebook and token preparation in one launch (token-major rows, D < 128); false if the shape needs two launches.
+bool prep_fusable(int D) { return D < 128; }
+cudaError_t launch_prep_fused(const float* weight, const CodebookView& cb, const float* z, int64_t T, float* zn32, float* row_sq,
+                              float* denom, __half* zn16, const ZeroList& zl, cudaStream_t s) {
+    const int D = cb.D;
+    const int rows_per_block = 8 * (32 / (D / 4)) * 4;
+    int cb_blocks = (cb.K + rows_per_block - 1) / rows_per_block;
+    if (cb_blocks > kInfoSlots) cb_blocks = kInfoSlots;
+    int64_t tok_blocks = (T + rows_per_block - 1) / rows_per_block;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (tok_blocks > cap) tok_blocks = cap;
+    if (tok_blocks < 1) tok_blocks = 1;
+    PrepRowsArgs c{reinterpret_cast<const float4*>(weight), cb.K, reinterpret_cast<float4*>(cb.en32), cb.code_sq, cb.code_denom,
+                   reinterpret_cast<uint2*>(cb.en16)};
+    PrepRowsArgs t{reinterpret_cast<const float4*>(z), T, reinterpret_cast<float4*>(zn32), row_sq, denom,
+                   reinterpret_cast<uint2*>(zn16)};
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (D) {
+        case 16: e = launch_pdl(k_prep_rows_fused<16>, dim3((unsigned)(cb_blocks + tok_blocks)), dim3(256), 0, s, c, cb.info,
+                                reinterpret_cast<float4*>(cb.en32c), cb.csq_cell, cb_blocks, t, zl); break;
+        case 32: e = launch_pdl(k_prep_rows_fused<32>, dim3((unsigned)(cb_blocks + tok_blocks)), dim3(256), 0, s, c, cb.info,
+                                reinterpret_cast<float4*>(cb.en32c), cb.csq_cell, cb_blocks, t, zl); break;
+        case 64: e = launch_pdl(k_prep_rows_fused<64>, dim3((unsigned)(cb_blocks + tok_blocks)), dim3(256), 0, s, c, cb.info,
+                                reinterpret_cast<float4*>(cb.en32c), cb.csq_cell, cb_blocks, t, zl); break;
+        default: break;
+    }
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) k_zero_ranges(ZeroList zl) { zero_ranges(zl, blockIdx.x, gridDim.x); }
 
 // the same zeroing as a launch of its own (layouts whose first kernel is not a token-major prep)
 cudaError_t launch_zero_ranges(const ZeroList& zl, cudaStream_t s) {

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("VQ_B200_LIB") or os.path.join(_PKG_DIR, "lib", "libvq
 BUILD_SCRIPT = os.path.join(_PKG_DIR, "csrc", "build.py")
 
 # constants mirrored from include/vq_b200.h
-ABI_VERSION = 2
+ABI_VERSION = 3
 FORM_VIT, FORM_VQGAN = 0, 1
 LAYOUT_TOKEN_MAJOR, LAYOUT_NCHW = 0, 1
 FLAG_INDICES_ONLY, FLAG_EXACT_SCAN, FLAG_KEEP_STATS = 1, 2, 4
@@ -35,7 +35,7 @@ SIGNATURES = {
     "vq_codebook_bytes": (c_int, [c_int, c_int, POINTER(c_size_t)]),
     "vq_codebook_prepare": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "vq_workspace_bytes": (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_size_t)]),
-    "vq_forward": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int64,
+    "vq_forward": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int64,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_size_t, c_void_p]),
     "vq_loss_finalize": (c_int, [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]),
@@ -45,6 +45,8 @@ SIGNATURES = {
                                    c_size_t, c_void_p]),
     "vq_backward_codebook": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),
+    "vq_backward": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                            c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vq_exchange_bytes": (c_int, [c_int, c_int, POINTER(c_size_t)]),
     "vq_exchange_slot": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]),
     "vq_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
@@ -56,7 +58,7 @@ SIGNATURES = {
                                              c_void_p]),
     "vq_gather": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                           c_void_p, c_void_p]),
-    "vq_profile_begin": (c_int, [c_int]),
+    "vq_profile_begin": (c_int, [c_int, ctypes.c_uint32]),
     "vq_profile_end": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64), POINTER(c_int64)]),
     "vq_profile_slot": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(c_int64)]),
     "vq_host_step_arena_bytes": (c_int, [c_int64, c_int, c_int, POINTER(c_size_t)]),

@@ -225,8 +225,8 @@ class ShardedQuantiser:
                 slot, epoch, seg, stats_ptr, hist_ptr = peer.next_step()
             else:
                 seg, stats_ptr, hist_ptr = _ptr(buf), _ptr(p["stats"]), _ptr(p["hist"])   # seg sums head the packed buffer
-            _lib.check(lib.vq_codebook_prepare(_ptr(w), K, D, cb, p["cb_bytes"], s))
-            _lib.check(lib.vq_forward(_ptr(z), layout, T, hw, cb, K, D, form_id, self.beta, flags, n_total,
+            # the weights of a training step changed: the forward prepares the codebook itself (same launch as the rows)
+            _lib.check(lib.vq_forward(_ptr(z), layout, T, hw, _ptr(w), cb, K, D, form_id, self.beta, flags, n_total,
                                       _ptr(p["z_q"]), _ptr(p["idx"]), None, hist_ptr, stats_ptr,
                                       _ptr(p["zn"]), _ptr(p["denom"]), seg, _ptr(p["fws"]), p["fws_bytes"], s))
             if peer is not None:
@@ -239,21 +239,25 @@ class ShardedQuantiser:
                                                             _ptr(p["hist_total"]), _ptr(p["loss"]), _ptr(p["stats"]),
                                                             side.cuda_stream))
                 p["ev_x"].record(side)
-            _lib.check(lib.vq_backward_tokens(_ptr(up), layout, T, hw, _ptr(p["zn"]), _ptr(p["denom"]), _ptr(p["idx"]),
-                                              None, cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_z"]), None,
-                                              _ptr(p["bws"]), p["bws_bytes"], s))
-            if peer is not None:
-                torch.cuda.current_stream(dev).wait_event(p["ev_x"])
-                hist_out = p["hist_total"]
+            if self.world_size == 1:
+                # one launch: grad_z, grad_weight and the loss
+                _lib.check(lib.vq_backward(_ptr(up), layout, T, hw, _ptr(p["zn"]), _ptr(p["denom"]), _ptr(p["idx"]), cb, K, D,
+                                           form_id, self.beta, None, n_total, seg, stats_ptr, _ptr(p["grad_z"]), _ptr(p["grad_w"]),
+                                           _ptr(p["loss"]), _ptr(p["bws"]), p["bws_bytes"], s))
+                hist_out = p["hist"]
             else:
-                if self.world_size > 1:
+                _lib.check(lib.vq_backward_tokens(_ptr(up), layout, T, hw, _ptr(p["zn"]), _ptr(p["denom"]), _ptr(p["idx"]),
+                                                  None, cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_z"]), None,
+                                                  _ptr(p["bws"]), p["bws_bytes"], s))
+                if peer is not None:
+                    torch.cuda.current_stream(dev).wait_event(p["ev_x"])
+                    hist_out = p["hist_total"]
+                else:
                     pack.fill_side_channels(buf, p["hist"], p["stats"])
                     pack.all_reduce(buf, self.group)
                     red_stats = pack.stats_from(buf)
                     hist_out = pack.hist(buf)
-                else:
-                    red_stats, hist_out = p["stats"], p["hist"]
-                _lib.check(lib.vq_backward_codebook(seg, cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_w"]),
-                                                    _ptr(red_stats), _ptr(p["loss"]), s))
+                    _lib.check(lib.vq_backward_codebook(seg, cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_w"]),
+                                                        _ptr(red_stats), _ptr(p["loss"]), s))
         return {"z_q": p["z_q"], "indices": p["idx"], "loss": p["loss"].view(()), "grad_z": p["grad_z"],
                 "grad_weight": p["grad_w"], "histogram": hist_out, "stats": p["stats"]}

@@ -100,7 +100,7 @@ class _Quantise(torch.autograd.Function):
         ws_bytes = _lib.size_query("vq_workspace_bytes", T, K, D, flags)
         ws = _scratch(ws_bytes, dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.vq_forward(_ptr(z), layout, T, hw, _ptr(prepared.blob), K, D, form, float(beta), flags,
+            _lib.check(lib.vq_forward(_ptr(z), layout, T, hw, None, _ptr(prepared.blob), K, D, form, float(beta), flags,
                                       n_total, _ptr(z_q), _ptr(idx), _ptr(loss), _ptr(hist), _ptr(stats),
                                       _ptr(saved_zn), _ptr(saved_denom), _ptr(seg), _ptr(ws), ws_bytes, _stream(dev)))
         if need_grad:
@@ -131,6 +131,11 @@ class _Quantise(torch.autograd.Function):
         ws = _scratch(ws_bytes, dev)
         with torch.cuda.device(dev):
             s = _stream(dev)
+            if want_w and from_forward:        # one launch: grad_z + grad_weight from the forward's segment sums
+                _lib.check(lib.vq_backward(_ptr(g_zq), layout, T, hw, _ptr(saved_zn), _ptr(saved_denom), _ptr(idx), _ptr(blob),
+                                           K, D, form, beta, _ptr(g_loss), n_total, _ptr(seg), None, _ptr(grad_z), _ptr(grad_w),
+                                           None, _ptr(ws), ws_bytes, s))
+                return grad_z, grad_w, None, None, None, None, None, None, None
             _lib.check(lib.vq_backward_tokens(_ptr(g_zq), layout, T, hw, _ptr(saved_zn), _ptr(saved_denom), _ptr(idx),
                                               _ptr(hist), _ptr(blob), K, D, form, beta, _ptr(g_loss), n_total, _ptr(grad_z),
                                               None if from_forward or not want_w else _ptr(seg), _ptr(ws), ws_bytes, s))
@@ -186,7 +191,7 @@ def encode_indices(z: torch.Tensor, weight: torch.Tensor, form: str = "vit",
     ws_bytes = _lib.size_query("vq_workspace_bytes", T, K, D, flags)
     ws = _scratch(ws_bytes, dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.vq_forward(_ptr(z), layout, T, hw, _ptr(prepared.blob), K, D, FORMS[form], 0.25, flags,
+        _lib.check(lib.vq_forward(_ptr(z), layout, T, hw, None, _ptr(prepared.blob), K, D, FORMS[form], 0.25, flags,
                                   max(T * D, 1), None, _ptr(idx), None, _ptr(hist), None, None, None, None, _ptr(ws),
                                   ws_bytes, _stream(dev)))
     return (idx, hist) if want_hist else idx

@@ -204,7 +204,8 @@ def run_b200(args):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    _lib.check(lib.vq_profile_begin(args.profile_every))
+    search_mask = (1 << _lib.PROFILE_SEARCH) | (1 << _lib.PROFILE_EXACT_FINISH)
+    _lib.check(lib.vq_profile_begin(args.profile_every, search_mask))
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record()
@@ -215,13 +216,15 @@ def run_b200(args):
     ms_total = start.elapsed_time(stop)
     search_ms, search_n, launches = ctypes.c_double(0), ctypes.c_int64(0), ctypes.c_int64(0)
     _lib.check(lib.vq_profile_end(ctypes.byref(search_ms), ctypes.byref(search_n), ctypes.byref(launches)))
-    slots = {}
-    for name, slot in (("prep_codebook", _lib.PROFILE_PREP_CODEBOOK), ("prep_tokens", _lib.PROFILE_PREP_TOKENS),
-                       ("exact_finish", _lib.PROFILE_EXACT_FINISH), ("tail", _lib.PROFILE_TAIL),
-                       ("backward_tokens", _lib.PROFILE_BACKWARD_TOKENS), ("codebook_grad", _lib.PROFILE_CODEBOOK_GRAD)):
-        ms_, n_ = ctypes.c_double(0), ctypes.c_int64(0)
-        _lib.check(lib.vq_profile_slot(slot, ctypes.byref(ms_), ctypes.byref(n_)))
-        slots[name] = ms_.value / max(1, n_.value)
+    def read_slots(names):
+        res = {}
+        for name in names:
+            ms_, n_ = ctypes.c_double(0), ctypes.c_int64(0)
+            _lib.check(lib.vq_profile_slot(getattr(_lib, "PROFILE_" + name.upper()), ctypes.byref(ms_), ctypes.byref(n_)))
+            res[name] = ms_.value / max(1, n_.value)
+        return res
+
+    slots = read_slots(["exact_finish"])
     exact_ms, exact_n = ctypes.c_double(slots["exact_finish"]), ctypes.c_int64(1 if slots["exact_finish"] > 0 else 0)
     clocks = sampler.stop()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -229,6 +232,34 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     value = world * T / (ms_step * 1e-3)
+
+    # ---- the other kernel families: a short pass after the timed region, every kernel bracketed (an event pair adds
+    # ~5 us of idle time in front of its kernel, so these are upper bounds), and the same steps seen by CUPTI
+    # (torch.profiler: in-stream kernel durations without that idle time)
+    _lib.check(lib.vq_profile_begin(1, 0))
+    for i in range(5):
+        one_step(args.warmup + args.steps + i)
+    torch.cuda.synchronize()
+    _lib.check(lib.vq_profile_end(None, None, None))
+    slots.update(read_slots(["prep_codebook", "prep_tokens", "tail", "backward_tokens", "codebook_grad"]))
+    cupti_us = None
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(5):
+                one_step(args.warmup + args.steps + 5 + i)
+            torch.cuda.synchronize()
+        acc = {}
+        for e in prof.events():
+            if e.device_type == torch.autograd.DeviceType.CUDA and "vq::" in e.name:
+                key = e.name.split("(")[0].replace("void ", "")
+                a_ = acc.setdefault(key, [0, 0.0])
+                a_[0] += 1
+                a_[1] += e.time_range.end - e.time_range.start
+        cupti_us = {k: v[1] / v[0] for k, v in acc.items()}
+    except Exception as exc:      # CUPTI unavailable: the event-based numbers stand
+        cupti_us = {"unavailable": repr(exc)[:100]}
+    barrier()
 
     # ---- e2e: host buffers through the C ABI (vq_host_step), copies inside the timed region ------
     e2e = None
@@ -305,24 +336,35 @@ def run_b200(args):
     non_search_ms = max(ms_step - search_avg_ms - exact_avg_ms, 1e-6)
     peak_gbs = peaks["hbm_gbs"]
 
-    def hbm_kernel(ms, nbytes, what):
-        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        return {"avg_launch_ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": gbs, "frac": gbs / peak_gbs, "bytes": what}
+    def cupti(fragment):
+        if not cupti_us:
+            return None
+        hits = [v for k, v in cupti_us.items() if fragment in k and isinstance(v, float)]
+        return hits[0] * 1e-3 if hits else None
+
+    def hbm_kernel(ms_events, fragment, nbytes, what):
+        ms_cupti = cupti(fragment)
+        ms = ms_cupti if ms_cupti else ms_events
+        gbs = nbytes / (ms * 1e-3) / 1e9 if ms and ms > 0 else 0.0
+        return {"avg_launch_ms": ms, "timed_by": "cupti" if ms_cupti else "cuda events (incl. ~5 us idle before the kernel)",
+                "avg_launch_ms_events": ms_events, "dram_bytes": nbytes, "achieved_gbs": gbs, "frac": gbs / peak_gbs, "bytes": what}
 
     hbm = {"peak_gbs": peak_gbs, "algorithmic_bytes_per_step": hbm_bytes_step,
            "kernels": {
-               "k_prep_rows (tokens)": hbm_kernel(slots["prep_tokens"], (10 * DIM + 8) * T,
-                                                  "read z 4D, write zn32 4D + zn16 2D + row_sq, denom 8"),
-               "k_backward_tokens": hbm_kernel(slots["backward_tokens"], (16 * DIM + 12) * T,
-                                               "read G 4D, zn 4D, idx 8, denom 4, code row 4D (L2), write grad_z 4D"),
-               "k_prep_rows (codebook)": hbm_kernel(slots["prep_codebook"], 14 * DIM * K_CODES, "read E 4D, write en32, en32c 8D, en16 2D"),
-               "k_codebook_grad": hbm_kernel(slots["codebook_grad"], (16 * DIM + 8) * K_CODES, "read seg sums 8D + 8, en 4D, write grad_E 4D"),
+               "k_prep_rows_fused (token rows + codebook)": hbm_kernel(
+                   slots["prep_tokens"], "k_prep_rows_fused", (10 * DIM + 8) * T + 14 * DIM * K_CODES,
+                   "tokens: read z 4D; write zn32 4D, zn16 2D, row_sq + denom 8; codebook: read E 4D, write en32 + en32c 8D, en16 2D"),
+               "k_backward_fused (grad_z + grad_E)": hbm_kernel(
+                   slots["backward_tokens"], "k_backward_fused", (12 * DIM + 12) * T + (16 * DIM + 8) * K_CODES,
+                   "tokens: read G 4D, zn 4D, idx 8, denom 4; write grad_z 4D (code rows from L2); codebook: read seg sums "
+                   "8D + 8, en 4D, write grad_E 4D"),
            },
            "non_search_ms": non_search_ms,
            "all_non_search_vs_20D+16": hbm_bytes_step / (non_search_ms * 1e-3) / 1e9 / peak_gbs,
-           "note": "per-kernel: actual bytes the kernel moves / its CUDA-event time (sampled steps); the z_q / idx / histogram / "
-                   "segment-sum writes of the forward are fused into k_exact_finish16 (reported under roofline.behind_the_filter); "
-                   "all_non_search_vs_20D+16 = SURVEY 8(d) bytes of the whole step over everything outside filter + exact/finish"}
+           "note": "per kernel: DRAM bytes / in-stream duration of a separate 5-step pass after the timed region; the z_q / "
+                   "idx / histogram / segment-sum writes of the forward are fused into k_exact_finish16 (roofline."
+                   "behind_the_filter); all_non_search_vs_20D+16 = SURVEY 8(d) bytes of the step over all time outside the "
+                   "filter and exact/finish kernels"}
     kernel_ms = dict(slots, search=search_avg_ms)
 
     # ---- cpu_baseline: oracle port on this box's host cores, bounded sample -------------------------
@@ -343,8 +385,9 @@ def run_b200(args):
                        "l2": f"inputs rotate over {n_sets} resident sets ({n_sets * 2 * T * DIM * 4 >> 20} MiB) > 126 MB L2; "
                              "a step's own working set is 130 MB"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.value),
-            "roofline": roofline, "hbm_side": hbm, "kernel_ms": kernel_ms,
-            "profile_sampling": f"CUDA-event pairs on every {args.profile_every}th step of the timed region",
+            "roofline": roofline, "hbm_side": hbm, "kernel_ms_events": kernel_ms, "kernel_us_cupti": cupti_us,
+            "profile_sampling": f"timed region: CUDA-event pairs around the filter and exact/finish kernels on every "
+                                f"{args.profile_every}th step; other kernels: separate 5-step pass",
             "cpu_baseline": cpu,
             "parity": {"near_tie_rows_last_step": stats[_lib.STAT_NEAR_TIE_ROWS] if stats else None,
                        "fallback_rows_last_step": stats[_lib.STAT_FALLBACK_ROWS] if stats else None}}

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 2
+#define VQ_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define VQ_API __attribute__((visibility("default")))
@@ -91,6 +91,9 @@ VQ_API int vq_codebook_prepare(const float* weight, int K, int D, void* cb, size
  * Replaces Codebook.forward (models/vitvqgan.py:151-171, models/vqgan.py:148-176):
  *   zn = l2norm(z); idx = argmin_k ((|zn|^2 + |en_k|^2) - 2 zn.en_k); q = l2norm(E[idx]);
  *   loss; z_q = zn + (q - zn).
+ * weight      : NULL if `cb` is already prepared (a frozen tokeniser prepares once); else the K*D raw weights, and
+ *               this call prepares `cb` itself (a training step: the weights changed) -- in the same launch as the
+ *               token rows where the shape allows (token-major, D < 128), so the step has no separate prepare.
  * z, z_q      : `layout`, fp32.  z_q may be NULL with VQ_FLAG_INDICES_ONLY.
  * idx         : T int64, flat token order.
  * loss        : 1 float, the reference's loss with the mean taken over `n_elem_total` elements
@@ -109,7 +112,7 @@ VQ_API int vq_codebook_prepare(const float* weight, int K, int D, void* cb, size
  * ws          : scratch of at least vq_workspace_bytes(T, K, D, flags).                            */
 VQ_API int vq_workspace_bytes(int64_t T, int K, int D, int flags, size_t* out);
 VQ_API int vq_forward(const float* z, int layout, int64_t T, int64_t hw,
-               const void* cb, int K, int D, int form, float beta, int flags, int64_t n_elem_total,
+               const float* weight, void* cb, int K, int D, int form, float beta, int flags, int64_t n_elem_total,
                float* z_q, int64_t* idx, float* loss, int32_t* hist, int64_t* stats,
                float* saved_zn, float* saved_denom, int64_t* seg_sums,
                void* ws, size_t ws_bytes, void* stream);
@@ -144,6 +147,16 @@ VQ_API int vq_backward_tokens(const float* g_zq, int layout, int64_t T, int64_t 
 VQ_API int vq_backward_codebook(const int64_t* seg_sums, const void* cb, int K, int D, int form, float beta,
                          const float* g_loss, int64_t n_elem_total, float* grad_weight,
                          const int64_t* stats, float* loss, void* stream);
+
+/* The backward of a step whose seg_sums came from vq_forward, in ONE launch where the layout allows (token-major):
+ * grad_z as vq_backward_tokens, grad_weight (and, with `loss` != NULL, the loss from `stats`) as
+ * vq_backward_codebook.  grad_z may be NULL.  ws as for vq_backward_tokens (only used for the NCHW layout).        */
+VQ_API int vq_backward(const float* g_zq, int layout, int64_t T, int64_t hw,
+                const float* saved_zn, const float* saved_denom, const int64_t* idx,
+                const void* cb, int K, int D, int form, float beta, const float* g_loss, int64_t n_elem_total,
+                const int64_t* seg_sums, const int64_t* stats,
+                float* grad_z, float* grad_weight, float* loss,
+                void* ws, size_t ws_bytes, void* stream);
 
 /* ---- token-sharded job: the backward's one exchange, fused with the codebook gradient -------------
  * Replaces DDP's all-reduce of codebook.embedding.weight.grad (trainers/vitgqgan.py:184,
@@ -186,8 +199,9 @@ VQ_API int vq_gather(const int64_t* idx, int64_t T, int64_t hw, const float* wei
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------
  * Between vq_profile_begin() and vq_profile_end() the library counts all kernel launches and brackets the kernels
  * of every `sample_every`-th step (a vq_forward and the calls that follow it) with CUDA events on the caller's
- * stream, one slot per kernel family.  Event records between kernels cost a few microseconds per step, which is
- * why a timed region samples (bench.py: every 4th step) instead of bracketing every launch.
+ * stream, one slot per kernel family (those of `slot_mask`).  An event pair costs about 5 us of an otherwise
+ * gap-free step, which is why a timed region samples and brackets only the search kernels (bench.py), and times
+ * the other families in a separate pass.
  * vq_profile_end synchronises and returns the summed time and launch count of the nearest-code search (the
  * dominant kernel: the tensor-core filter, or the exhaustive scan) and the number of kernel launches of all kinds;
  * vq_profile_slot then returns (and clears) any other slot.                                          */
@@ -199,7 +213,7 @@ VQ_API int vq_gather(const int64_t* idx, int64_t T, int64_t hw, const float* wei
 #define VQ_PROFILE_BACKWARD_TOKENS 5
 #define VQ_PROFILE_CODEBOOK_GRAD   6   /* incl. the fused peer exchange of a token-sharded job                      */
 #define VQ_PROFILE_SLOTS           7
-VQ_API int vq_profile_begin(int sample_every);
+VQ_API int vq_profile_begin(int sample_every, unsigned slot_mask /* bit i = VQ_PROFILE_* slot i; 0 = all */);
 VQ_API int vq_profile_end(double* search_ms_total, int64_t* search_launches, int64_t* kernel_launches);
 VQ_API int vq_profile_slot(int slot, double* ms_total, int64_t* launches);
 

@@ -459,7 +459,7 @@ def test_sharded_codebook_kernel_world_1_equals_plain_path(dev):
             _lib.check(lib.vq_exchange_slot(own.value, K, D, slot, ctypes.byref(seg), ctypes.byref(st), ctypes.byref(hist)))
             z_q, idx = torch.empty_like(z), torch.empty(T, dtype=torch.int64, device=dev)
             zn, dn = torch.empty_like(z), torch.empty(T, device=dev)
-            _lib.check(lib.vq_forward(z.data_ptr(), 0, T, 0, cb.data_ptr(), K, D, 0, beta, 0, T * D, z_q.data_ptr(),
+            _lib.check(lib.vq_forward(z.data_ptr(), 0, T, 0, None, cb.data_ptr(), K, D, 0, beta, 0, T * D, z_q.data_ptr(),
                                       idx.data_ptr(), None, hist.value, st.value, zn.data_ptr(), dn.data_ptr(), seg.value,
                                       fws.data_ptr(), fws_bytes, s))
             gw, loss = torch.empty(K, D, device=dev), torch.empty(1, device=dev)

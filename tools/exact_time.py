@@ -17,14 +17,18 @@ for i in range(5):
 torch.cuda.synchronize()
 prof = os.environ.get("NOPROF", "0") == "0"
 if prof:
-    lib.vq_profile_begin(1)
+    lib.vq_profile_begin(1, 0)
 n = 20
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+import time
 a.record()
+t0 = time.perf_counter()
 for i in range(n):
     st.step(zs[i % 4], ups[i % 4], w)
+t_issue = (time.perf_counter() - t0) / n * 1e6
 b.record()
 torch.cuda.synchronize()
+print(f"host issue time {t_issue:.1f} us/step")
 if not prof:
     print(f"PDL={os.environ.get('VQ_PDL', '1')} no event hooks: step {a.elapsed_time(b) / n * 1e3:.1f} us")
     sys.exit(0)

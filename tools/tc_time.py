@@ -15,7 +15,7 @@ lib = _lib.load()
 for i in range(3):
     F_vq.encode_indices(zs[i % 4], w, "vit", prepared=prep)
 torch.cuda.synchronize()
-lib.vq_profile_begin(1)
+lib.vq_profile_begin(1, 0)
 n = 10
 for i in range(n):
     F_vq.encode_indices(zs[i % 4], w, "vit", prepared=prep)
