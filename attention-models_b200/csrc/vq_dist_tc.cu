@@ -1,6 +1,6 @@
 // Nearest-code search on the 5th-generation tensor cores (sm_100a): TMA -> shared memory ->
 // tcgen05.mma (fp16 in, fp32 accumulators in TMEM) -> tcgen05.ld -> running maxima in registers,
-// followed by exact fp32 rescoring of the few surviving candidates.
+// followed by exact fp32 rescoring of the few surviving candidates (k_rescore_g, a second launch).
 //
 // Replaces the dense part of the reference's search (paths relative to /root/reference):
 //   models/vitvqgan.py:157-161 / models/vqgan.py:157-161
@@ -44,11 +44,11 @@ constexpr int kGroupCols = kTileN * kGroupTiles;
 constexpr int kKBlock = 32;          // halfs per K block: 64-byte rows, SWIZZLE_64B
 constexpr int kABlockBytes = kRowsPerCta * kKBlock * 2;   // 16 KiB
 constexpr int kBStageBytes = kTileN * kKBlock * 2;        // 8 KiB
-constexpr int kThreads = 512;        // warps 0-3 service (TMA, MMA, TMEM alloc, idle), 4-7 rescoring, 8-15 epilogue
-constexpr int kRescoreThreads = 128;
+constexpr int kThreads = 512;        // warps 0-3 service (TMA, MMA, TMEM alloc, idle), 4-7 spare, 8-15 epilogue
+constexpr int kRecordBytes = 32;     // verdict record per row
 // register budget after setmaxnreg (the kernel launches with 128 per thread = the whole register file):
-constexpr int kRegsService = 40, kRegsRescore = 96, kRegsEpilogue = 184;
-static_assert(128 * kRegsService + 128 * kRegsRescore + 256 * kRegsEpilogue <= 65536, "register file overcommitted");
+constexpr int kRegsService = 40, kRegsEpilogue = 216;
+static_assert(256 * kRegsService + 256 * kRegsEpilogue <= 65536, "register file overcommitted");
 constexpr float kTwoEps = 2.2e-3f;   // 2 * eps, see header comment
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 // c_format = F32 (bit 4), a/b = F16 (0), K-major both, N = 128 (bits 17..22), M = 128 (bits 24..28)
@@ -70,7 +70,7 @@ __host__ __device__ inline SmemLayout smem_layout(int kb) {
     L.b = L.a + a_stages(kb) * kb * kABlockBytes;
     L.snap = L.b + b_stages(kb) * kBStageBytes;
     L.hand = L.snap + snap_areas(kb) * kRowsPerCta * snap_row_bytes(kb);
-    L.bars = L.hand + 2 * kHandBytes;
+    L.bars = L.hand;
     L.tmem_slot = L.bars + 8 * (2 * kMaxBStages + 2 * 2 + 4 + 4);
     L.total = L.tmem_slot + 16;
     return L;
@@ -83,54 +83,16 @@ __device__ __forceinline__ int cell_code(int g, int slot, int i) {
     return g * kGroupCols + 64 * (i >> 1) + ((slot & 16) << 1) + (slot & 15) + 16 * (i & 1);
 }
 
-// exact fp32 distance of one row to the 8 codes of cell (g, slot): same fma chain as the exhaustive search
-template <int D, bool kRowInRegs>
-__device__ __forceinline__ void rescore_cell(int g, int slot, const float4* __restrict__ z4, const float4 (&z)[kRowInRegs ? D / 4 : 1],
-                                             float a_sq, const float* __restrict__ en32, const float* __restrict__ code_sq,
-                                             float& best_d, int& best_i, float& second_d) {
-#pragma unroll 1
-    for (int i = 0; i < 8; ++i) {
-        const int code = cell_code(g, slot, i);
-        const float4* e4 = reinterpret_cast<const float4*>(en32 + (int64_t)code * D);
-        float dot = 0.f;
-        if constexpr (kRowInRegs) {
-            float4 ev[D / 4];
-#pragma unroll
-            for (int q = 0; q < D / 4; ++q) ev[q] = __ldg(e4 + q);
-#pragma unroll
-            for (int q = 0; q < D / 4; ++q) {
-                dot = __fmaf_rn(z[q].x, ev[q].x, dot);
-                dot = __fmaf_rn(z[q].y, ev[q].y, dot);
-                dot = __fmaf_rn(z[q].z, ev[q].z, dot);
-                dot = __fmaf_rn(z[q].w, ev[q].w, dot);
-            }
-        } else {
-#pragma unroll 8
-            for (int q = 0; q < D / 4; ++q) {
-                const float4 ev = __ldg(e4 + q);
-                const float4 zv = __ldg(z4 + q);
-                dot = __fmaf_rn(zv.x, ev.x, dot);
-                dot = __fmaf_rn(zv.y, ev.y, dot);
-                dot = __fmaf_rn(zv.z, ev.z, dot);
-                dot = __fmaf_rn(zv.w, ev.w, dot);
-            }
-        }
-        const float dist = ref_distance(a_sq, __ldg(code_sq + code), dot);
-        if (argmin_better(dist, code, best_d, best_i)) { second_d = best_d; best_d = dist; best_i = code; }
-        else if (dist < second_d) second_d = dist;
-    }
-}
-
 // One CTA per SM, persistent over row tiles.  KB = D / 32.
-// warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM alloc   warps 4-7: exact fp32 rescoring of the
-// previous row tile (one warp per scheduler, hidden under the ALU-bound main loop)
-// warps 8-15: epilogue, one thread per row.  Registers are redistributed with setmaxnreg.
+// warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM alloc   warps 8-15: epilogue, one thread per row, which
+// ends with the row's verdict record in global memory.  Registers are redistributed with setmaxnreg.
+// (Rescoring used to run on warps 4-7 of this kernel: at D = 256 its dependent 1 KB gathers held the tile hand-off
+// and the tensor pipe sat at 20 %; it is now k_rescore_g, which reads whole 128-byte lines of cell copies.)
 template <int KB>
 __global__ void __launch_bounds__(kThreads, 1)
 k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int T, int K,
-          const float* __restrict__ zn32, const float* __restrict__ row_sq, const float* __restrict__ en32,
-          const float* __restrict__ code_sq, const int* __restrict__ cb_info, int* __restrict__ cand,
-          int* __restrict__ flagged, int* __restrict__ n_flagged, int64_t* __restrict__ stats, int debug_flags) {
+          const int* __restrict__ cb_info, int4* __restrict__ records, int* __restrict__ cand,
+          int* __restrict__ flagged, int* __restrict__ n_flagged, int64_t* __restrict__ stats) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int D = KB * kKBlock;
     constexpr int AS = a_stages(KB);
@@ -150,8 +112,6 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     auto t_empty = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 2 + s); };
     auto a_full = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 4 + s); };
     auto a_empty = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 6 + s); };
-    auto h_full = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 8 + s); };
-    auto h_empty = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 10 + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_slot);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -163,7 +123,6 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         for (int s = 0; s < BS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), 256); }
         for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(h_full(s), 256); mbar_init(h_empty(s), kRescoreThreads); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -254,58 +213,8 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
 #endif
         }
     } else if (warp < 8) {
-        // ===================== rescoring: 128 threads, 2 rows each per row tile =====================
-        reg_dec<kRegsRescore>();
-        constexpr bool kRowInRegs = (D <= 32);
-        const int rtid = threadIdx.x - 128;
-        unsigned ties = 0, multi = 0;
-        int it = 0;
-        for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
-            const int hb = it & 1;
-            mbar_wait(h_full(hb), ((uint32_t)(it >> 1)) & 1u);
-            const int4* hand = reinterpret_cast<const int4*>(smem + L.hand + hb * kHandBytes);
-#pragma unroll 1
-            for (int rr = 0; rr < kRowsPerCta / kRescoreThreads; ++rr) {
-                const int r = rtid + kRescoreThreads * rr;
-                const int row = rt * kRowsPerCta + r;
-                const int4 h0 = hand[2 * r], h1 = hand[2 * r + 1];
-                if (row >= T || h0.x < 0) continue;                 // out of range, or left to the exhaustive search
-                if (debug_flags & 1) { cand[row] = kCandExactBit; continue; }   // timing experiment only
-                const int gs[3] = {h0.x & 0xFFFF, (h0.x >> 16) & 0x7FFF, h0.y};
-                const uint32_t ms[3] = {(uint32_t)h0.z, (uint32_t)h0.w, (uint32_t)h1.x};
-                float4 z[kRowInRegs ? D / 4 : 1];
-                const float4* z4 = reinterpret_cast<const float4*>(zn32 + (int64_t)row * D);
-                if (kRowInRegs) {
-#pragma unroll
-                    for (int q = 0; q < (kRowInRegs ? D / 4 : 1); ++q) z[q] = __ldg(z4 + q);
-                }
-                const float a_sq = __ldg(row_sq + row);
-                float best_d = INFINITY, second_d = INFINITY;
-                int best_i = 0x7fffffff, n_cells = 0;
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    uint32_t m = ms[a];
-                    while (m) {
-                        const int slot = __ffs(m) - 1;
-                        m &= m - 1;
-                        ++n_cells;
-                        rescore_cell<D, kRowInRegs>(gs[a], slot, z4, z, a_sq, en32, code_sq, best_d, best_i, second_d);
-                    }
-                }
-                cand[row] = best_i | kCandExactBit;
-                if (second_d - best_d < VQ_NEAR_TIE_REL * fabsf(best_d)) ++ties;
-                if (n_cells > 1) ++multi;
-            }
-            mbar_arrive(h_empty(hb));
-        }
-        if (stats) {
-            ties = __reduce_add_sync(VQ_FULL, ties);
-            multi = __reduce_add_sync(VQ_FULL, multi);
-            if (lane == 0) {
-                if (ties) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), (unsigned long long)ties);
-                if (multi) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_AMBIGUOUS_ROWS), (unsigned long long)multi);
-            }
-        }
+        // spare warps: hand their registers to the epilogue (setmaxnreg.inc waits for them) and leave
+        reg_dec<kRegsService>();
     } else {
         // ===================== epilogue: 8 warps, one thread per row =====================
         reg_inc<kRegsEpilogue>();
@@ -433,13 +342,12 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             const int row = rt * kRowsPerCta + row_in_cta;
             const bool in_range = row < T;
             const bool flag = in_range && !decided;
-            // hand the verdict to the rescoring warps (double-buffered)
-            const int hb = it & 1;
-            VQ_TIMED_WAIT(1, h_empty(hb), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
-            int4* hand = reinterpret_cast<int4*>(smem + L.hand + hb * kHandBytes);
-            hand[2 * row_in_cta] = make_int4(decided ? (g1 | (g2 << 16)) : -1, g3, (int)mask[0], (int)mask[1]);
-            hand[2 * row_in_cta + 1] = make_int4((int)mask[2], 0, 0, 0);
-            mbar_arrive(h_full(hb));
+            // the verdict record of the row, for the exact rescoring kernel: {g1 | g2 << 16 (or -1: undecided), g3,
+            // mask1, mask2} {mask3, -, -, -}
+            if (in_range) {
+                records[2 * (int64_t)row] = make_int4(decided ? (g1 | (g2 << 16)) : -1, g3, (int)mask[0], (int)mask[1]);
+                records[2 * (int64_t)row + 1] = make_int4((int)mask[2], 0, 0, 0);
+            }
             if (flag) cand[row] = -1;
             const uint32_t ballot = __ballot_sync(VQ_FULL, flag);
             if (ballot) {
@@ -465,6 +373,102 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Exact fp32 rescoring behind the filter, any D: cand[row] = argmin over the codes of the row's surviving cells.
+// Same shape as k_exact_finish16's phase A: a warp owns 4 rows per iteration, staged in shared memory; the 8 lanes of
+// a group each own one member of a cell and read whole 128-byte lines of the generic cell copies (CodebookView::en32c,
+// kind 2) in batches of 8 chunks; every lane runs the sequential fma chain over d = 0..D-1 of the exhaustive search,
+// so all paths return identical indices.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kRescoreThreads = 128;
+template <int D>
+__global__ void __launch_bounds__(kRescoreThreads)
+k_rescore_g(const int4* __restrict__ rec, const float* __restrict__ zn32, const float* __restrict__ row_sq,
+            const float4* __restrict__ en32c, const float* __restrict__ csq_cell, int T, int* __restrict__ cand,
+            int64_t* __restrict__ stats) {
+    constexpr int kChunks = D / 4;
+    __shared__ __align__(16) float4 s_z[kRescoreThreads / 32][4][kChunks + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = lane & 7, grp = lane >> 3;
+    const float4* zn4 = reinterpret_cast<const float4*>(zn32);
+    unsigned ties = 0, multi = 0;
+    const int groups = gridDim.x * (kRescoreThreads / 8);
+    for (int row0 = (blockIdx.x * kRescoreThreads + threadIdx.x - lane) >> 3; row0 < T; row0 += groups) {
+        const int row = row0 + grp;
+        int4 h0 = make_int4(-1, 0, 0, 0), h1 = make_int4(0, 0, 0, 0);
+        float a_sq = 0.f;
+        if (row < T) { h0 = __ldg(rec + 2 * (int64_t)row); h1 = __ldg(rec + 2 * (int64_t)row + 1); a_sq = __ldg(row_sq + row); }
+        __syncwarp();
+        // the warp's 4 rows are 4 * kChunks contiguous float4
+#pragma unroll
+        for (int j = 0; j < kChunks / 8; ++j) {
+            const int e = lane + 32 * j;                    // float4 index within the 4 rows
+            const int r = e / kChunks, c = e % kChunks;
+            if (row0 + r < T) s_z[warp][r][c] = __ldg(zn4 + (int64_t)row0 * kChunks + e);
+        }
+        __syncwarp();
+        const float4* zs = s_z[warp][grp];
+        const bool valid = (row < T) && (h0.x >= 0);
+        const int gs[3] = {h0.x & 0xFFFF, (h0.x >> 16) & 0x7FFF, h0.y};
+        uint32_t ms[3] = {valid ? (uint32_t)h0.z : 0u, valid ? (uint32_t)h0.w : 0u, valid ? (uint32_t)h1.x : 0u};
+        const int n_cells = __popc(ms[0]) + __popc(ms[1]) + __popc(ms[2]);
+        const int n_iter = __reduce_max_sync(VQ_FULL, n_cells);
+        Top2 top;
+        top.init();
+        int a = 0;
+#pragma unroll 1
+        for (int it = 0; it < n_iter; ++it) {
+            while (a < 3 && ms[a] == 0u) ++a;
+            if (a < 3) {
+                const int slot = __ffs(ms[a]) - 1;
+                ms[a] &= ms[a] - 1;
+                const int g = gs[a];
+                const int ci = g * 32 + slot;
+                const int code = g * kGroupCols + 64 * (m >> 1) + ((slot & 16) << 1) + (slot & 15) + 16 * (m & 1);
+                const float4* e4 = en32c + (int64_t)ci * kChunks * 8 + m;
+                const float csq = __ldg(csq_cell + ci * 8 + m);
+                float dot = 0.f;
+#pragma unroll 1
+                for (int q0 = 0; q0 < kChunks; q0 += 8) {
+                    float4 ev[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) ev[q] = __ldg(e4 + (q0 + q) * 8);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 z = zs[q0 + q];
+                        dot = __fmaf_rn(z.x, ev[q].x, dot);
+                        dot = __fmaf_rn(z.y, ev[q].y, dot);
+                        dot = __fmaf_rn(z.z, ev[q].z, dot);
+                        dot = __fmaf_rn(z.w, ev[q].w, dot);
+                    }
+                }
+                top.add(dist_key(ref_distance(a_sq, csq, dot), code));
+            }
+        }
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) {
+            const unsigned long long ob = __shfl_xor_sync(VQ_FULL, top.best, off);
+            const float os = __shfl_xor_sync(VQ_FULL, top.second, off);
+            top.merge(ob, os);
+        }
+        if (valid && m == 0) {
+            const float bd = key_dist(top.best);
+            cand[row] = (int)(uint32_t)top.best | kCandExactBit;
+            if (top.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) ++ties;
+            if (n_cells > 1) ++multi;
+        }
+    }
+    if (stats) {
+        ties = __reduce_add_sync(VQ_FULL, ties);
+        multi = __reduce_add_sync(VQ_FULL, multi);
+        if (lane == 0) {
+            if (ties) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), (unsigned long long)ties);
+            if (multi) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_AMBIGUOUS_ROWS), (unsigned long long)multi);
+        }
     }
 }
 
@@ -517,13 +521,14 @@ bool tc_supported(int64_t T, int K, int D) {
 }
 
 size_t tc_workspace_bytes(int64_t T, int K, int D) {
-    return tc16_supported(T, K, D) ? tc16_workspace_bytes(T) : 0;
+    if (tc16_supported(T, K, D)) return tc16_workspace_bytes(T);
+    return tc_supported(T, K, D) ? (size_t)(T > 0 ? T : 1) * tc::kRecordBytes : 0;
 }
 
 template <int KB>
 static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, int T, const float* zn32,
                                     const float* row_sq, const CodebookView& cb, int* cand, int* flagged,
-                                    int* n_flagged, int64_t* stats, cudaStream_t s) {
+                                    int* n_flagged, int64_t* stats, void* records, cudaStream_t s) {
     const tc::SmemLayout L = tc::smem_layout(KB);
     static bool configured = false;
     if (!configured) {
@@ -533,10 +538,20 @@ static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb
     }
     const int n_row_tiles = (T + tc::kRowsPerCta - 1) / tc::kRowsPerCta;
     const int grid = n_row_tiles < sm_count() ? n_row_tiles : sm_count();
-    static const int debug_flags = getenv("VQ_TC_DEBUG") ? atoi(getenv("VQ_TC_DEBUG")) : 0;
-    tc::k_dist_tc<KB><<<grid, tc::kThreads, L.total + 1024, s>>>(ma, mb, T, cb.K, zn32, row_sq, cb.en32, cb.code_sq, cb.info,
-                                                                 cand, flagged, n_flagged, stats, debug_flags);
+    tc::k_dist_tc<KB><<<grid, tc::kThreads, L.total + 1024, s>>>(ma, mb, T, cb.K, cb.info, static_cast<int4*>(records), cand,
+                                                                 flagged, n_flagged, stats);
     count_launch();
+    {
+        constexpr int D = KB * tc::kKBlock;
+        const int rows_per_block = tc::kRescoreThreads / 8;
+        int64_t blocks = ((int64_t)T + rows_per_block - 1) / rows_per_block;
+        const int64_t cap = (int64_t)sm_count() * 16 * 2;
+        if (blocks > cap) blocks = cap;
+        tc::k_rescore_g<D><<<(unsigned)blocks, tc::kRescoreThreads, 0, s>>>(static_cast<const int4*>(records), zn32, row_sq,
+                                                                             reinterpret_cast<const float4*>(cb.en32c), cb.csq_cell, T,
+                                                                             cand, stats);
+        count_launch();
+    }
 #ifdef VQ_TC_INSTRUMENT
     {
         cudaStreamSynchronize(s);
@@ -569,10 +584,10 @@ cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* r
         !tc::make_map(&mb, cb.en16, (uint64_t)cb.K, cb.D, tc::kTileN))
         return cudaErrorInvalidValue;
     switch (cb.D / tc::kKBlock) {
-        case 1: return launch_tc_kernel<1>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, s);
-        case 2: return launch_tc_kernel<2>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, s);
-        case 4: return launch_tc_kernel<4>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, s);
-        case 8: return launch_tc_kernel<8>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, s);
+        case 1: return launch_tc_kernel<1>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, s);
+        case 2: return launch_tc_kernel<2>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, s);
+        case 4: return launch_tc_kernel<4>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, s);
+        case 8: return launch_tc_kernel<8>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -414,36 +414,9 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 // identical indices.  (distance, index) pairs are compared as one 64-bit key: sign-corrected float bits, ties to
 // the lower index, NaN below everything (torch.argmin: NaN wins).
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long dist_key(float d, int code) {
-    const uint32_t b = __float_as_uint(d);
-    const uint32_t o = (d != d) ? 0u : (b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u));
-    return ((unsigned long long)o << 32) | (uint32_t)code;
-}
-__device__ __forceinline__ float key_dist(unsigned long long key) {
-    const uint32_t o = (uint32_t)(key >> 32);
-    return (o == 0u) ? __int_as_float(0x7fc00000) : __uint_as_float(o ^ ((o >> 31) ? 0x80000000u : 0xFFFFFFFFu));
-}
-struct Top2 {
-    unsigned long long best;   // key of the best (distance, index)
-    float second;              // second-smallest distance (NaN if a NaN lost)
-    __device__ __forceinline__ void init() { best = ~0ull; second = INFINITY; }
-    __device__ __forceinline__ void lose(unsigned long long key) {
-        if (key != ~0ull) {
-            const float d = key_dist(key);
-            second = (d != d || second != second) ? __int_as_float(0x7fc00000) : fminf(second, d);
-        }
-    }
-    __device__ __forceinline__ void add(unsigned long long key) {
-        const bool wins = key < best;
-        const unsigned long long loser = wins ? best : key;
-        best = wins ? key : best;
-        lose(loser);
-    }
-    __device__ __forceinline__ void merge(unsigned long long obest, float osecond) {
-        add(obest);
-        second = (osecond != osecond || second != second) ? __int_as_float(0x7fc00000) : fminf(second, osecond);
-    }
-};
+using tc::dist_key;
+using tc::key_dist;
+using tc::Top2;
 
 // distances of one row (z in registers) to the 8 codes of cell ci: this lane's code is m
 __device__ __forceinline__ float cell_distance(const float4* __restrict__ en32c, const float* __restrict__ csq_cell, int ci,

@@ -20,6 +20,7 @@ struct CodebookView {
     float* en32c;       // K*D  [ci][q][m][4]: 16-byte chunk q of code m -- 8 lanes, one per code, read whole lines
     float* csq_cell;    // K    [ci][m] = code_sq of that code
     int K, D;
+    int cell_kind;      // cell_layout_kind(K, D)
 };
 size_t codebook_bytes(int K, int D);
 CodebookView codebook_view(void* cb, int K, int D);
@@ -125,7 +126,23 @@ cudaError_t launch_codebook_grad_sharded(const void* const* peer_bufs, int world
                                          int64_t* stats_total, cudaStream_t s);
 
 // dispatch on the supported codebook dims (powers of two in [16, 512])
-inline bool has_cell_layout(int K, int D) { return D == 32 && K >= 512 && (K % 512) == 0; }
+// Cell copies of the unit codes for the exact rescoring behind a tensor-core filter (CodebookView::en32c):
+//   1  D = 32 filter (vq_dist_tc16.cu): cell = the 8 codes g*512 + hs + 64*m, ci = g*64 + hs
+//   2  generic filter (vq_dist_tc.cu):  cell = slot s of the 256-code group g, ci = g*32 + s, member i = code
+//      g*256 + 64*(i>>1) + 32*(s>>4) + (s&15) + 16*(i&1)
+//   0  none (shapes the tensor-core search does not take)
+inline int cell_layout_kind(int K, int D) {
+    if (D == 32 && K >= 512 && (K % 512) == 0 && K <= 65536) return 1;
+    if ((D == 32 || D == 64 || D == 128 || D == 256) && K >= 256 && (K % 256) == 0) return 2;
+    return 0;
+}
+inline bool has_cell_layout(int K, int D) { return cell_layout_kind(K, D) != 0; }
+// (cell, member) of a code in the generic layout
+__host__ __device__ inline void generic_cell_of(int code, int& ci, int& member) {
+    const int g = code >> 8, w = code & 255;
+    ci = g * 32 + (((w >> 5) & 1) << 4) + (w & 15);
+    member = ((w >> 6) << 1) | ((w >> 4) & 1);
+}
 inline bool dim_supported(int D) { return D >= 16 && D <= 512 && (D & (D - 1)) == 0; }
 
 #define VQ_DISPATCH_D(D, ...)                                       \

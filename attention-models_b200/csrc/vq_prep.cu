@@ -58,6 +58,7 @@ CodebookView codebook_view(void* cb, int K, int D) {
     v.en16 = reinterpret_cast<__half*>(p);       p += align_up(sizeof(__half) * (size_t)K * D, 256);
     v.info = reinterpret_cast<int*>(p);          p += 256;
     v.en32c = nullptr; v.csq_cell = nullptr;
+    v.cell_kind = cell_layout_kind(K, D);
     if (has_cell_layout(K, D)) {
         v.en32c = reinterpret_cast<float*>(p);   p += align_up(sizeof(float) * (size_t)K * D, 256);
         v.csq_cell = reinterpret_cast<float*>(p);
@@ -79,7 +80,8 @@ template <int D, bool kIsCodebook>
 __global__ void __launch_bounds__(256) k_prep_rows(const float* __restrict__ in, int64_t rows,
                                                    float* __restrict__ unit32, float* __restrict__ sq,
                                                    float* __restrict__ denom, __half* __restrict__ unit16,
-                                                   int* __restrict__ info, ZeroList zl) {
+                                                   int* __restrict__ info, float4* __restrict__ en32c,
+                                                   float* __restrict__ csq_cell, ZeroList zl) {
     using M = RowMap<D>;
     constexpr int kRows = (M::kPerLane <= 4) ? 4 : 2;
     const int lane = threadIdx.x & 31;
@@ -104,6 +106,18 @@ __global__ void __launch_bounds__(256) k_prep_rows(const float* __restrict__ in,
             const float s2 = M::template sumsq<false>(x[i]);
             if (unit32) M::store(unit32 + r * D, lane, x[i]);
             if (unit16) M::store_half(unit16 + r * D, lane, x[i]);
+            if (kIsCodebook && en32c) {
+                // generic cell copies (cell_layout_kind 2): RowMap's vector mapping holds float4 #(lane + 32 m) of the row
+                if constexpr (M::kVec) {
+                    int ci, mem;
+                    generic_cell_of((int)r, ci, mem);
+#pragma unroll
+                    for (int m = 0; m < M::kPerLane / 4; ++m)
+                        en32c[((int64_t)ci * (D / 4) + lane + 32 * m) * 8 + mem] =
+                            make_float4(x[i][4 * m], x[i][4 * m + 1], x[i][4 * m + 2], x[i][4 * m + 3]);
+                    if (lane == 0) csq_cell[ci * 8 + mem] = s2;
+                }
+            }
             if (lane == 0) {
                 if (sq) sq[r] = s2;
                 if (denom) denom[r] = den;
@@ -126,7 +140,7 @@ __device__ __forceinline__ void prep_rows_small_body(const float4* __restrict__ 
                                                      float4* __restrict__ unit32, float* __restrict__ sq,
                                                      float* __restrict__ denom, uint2* __restrict__ unit16,
                                                      int* __restrict__ info, float4* __restrict__ en32c,
-                                                     float* __restrict__ csq_cell, int vblock, int vgrid) {
+                                                     float* __restrict__ csq_cell, int cell_kind, int vblock, int vgrid) {
     static_assert(D == 16 || D == 32 || D == 64, "small-row prep covers D < 128");
     int n_bad = 0;
     constexpr int kLpr = D / 4;
@@ -177,12 +191,13 @@ __device__ __forceinline__ void prep_rows_small_body(const float4* __restrict__ 
                     if (denom) denom[r] = den;
                     if (kIsCodebook && !(fabsf(s2 - 1.f) < 1e-4f)) ++n_bad;
                 }
-                if (kIsCodebook && D == 32 && en32c) {
-                    // cell copies of the unit codes (see CodebookView): chunk `sub` of code r
+                if (kIsCodebook && en32c) {
+                    // cell copies of the unit codes (see cell_layout_kind): chunk `sub` of code r
                     const int code = (int)r;
-                    const int g = code >> 9, w = code & 511, m = w >> 6, hs = w & 63;
-                    const int ci = g * 64 + hs;
-                    en32c[(ci * 8 + sub) * 8 + m] = v;
+                    int ci, m;
+                    if (cell_kind == 1) { const int w = code & 511; ci = (code >> 9) * 64 + (w & 63); m = w >> 6; }
+                    else generic_cell_of(code, ci, m);
+                    en32c[((int64_t)ci * kLpr + sub) * 8 + m] = v;
                     if (sub == 0) csq_cell[ci * 8 + m] = s2;
                 }
             }
@@ -196,11 +211,12 @@ __global__ void __launch_bounds__(256) k_prep_rows_small(const float4* __restric
                                                          float4* __restrict__ unit32, float* __restrict__ sq,
                                                          float* __restrict__ denom, uint2* __restrict__ unit16,
                                                          int* __restrict__ info, float4* __restrict__ en32c,
-                                                         float* __restrict__ csq_cell, ZeroList zl) {
+                                                         float* __restrict__ csq_cell, int cell_kind, ZeroList zl) {
     pdl_trigger();
     pdl_wait();
     if (!kIsCodebook) zero_ranges(zl, blockIdx.x, gridDim.x);
-    prep_rows_small_body<D, kIsCodebook>(in, rows, unit32, sq, denom, unit16, info, en32c, csq_cell, blockIdx.x, gridDim.x);
+    prep_rows_small_body<D, kIsCodebook>(in, rows, unit32, sq, denom, unit16, info, en32c, csq_cell, cell_kind, blockIdx.x,
+                                         gridDim.x);
 }
 
 // codebook rows on blocks [0, cb_blocks), token rows on the rest: the two preparations of a training step in one launch
@@ -209,24 +225,24 @@ struct PrepRowsArgs {
 };
 template <int D>
 __global__ void __launch_bounds__(256) k_prep_rows_fused(PrepRowsArgs cbk, int* __restrict__ info, float4* __restrict__ en32c,
-                                                         float* __restrict__ csq_cell, int cb_blocks, PrepRowsArgs tok,
-                                                         ZeroList zl) {
+                                                         float* __restrict__ csq_cell, int cell_kind, int cb_blocks,
+                                                         PrepRowsArgs tok, ZeroList zl) {
     pdl_trigger();
     pdl_wait();
     if ((int)blockIdx.x < cb_blocks) {
         prep_rows_small_body<D, true>(cbk.in, cbk.rows, cbk.unit32, cbk.sq, cbk.denom, cbk.unit16, info, en32c, csq_cell,
-                                      blockIdx.x, cb_blocks);
+                                      cell_kind, blockIdx.x, cb_blocks);
     } else {
         const int vblock = blockIdx.x - cb_blocks, vgrid = gridDim.x - cb_blocks;
         zero_ranges(zl, vblock, vgrid);
-        prep_rows_small_body<D, false>(tok.in, tok.rows, tok.unit32, tok.sq, tok.denom, tok.unit16, nullptr, nullptr, nullptr,
+        prep_rows_small_body<D, false>(tok.in, tok.rows, tok.unit32, tok.sq, tok.denom, tok.unit16, nullptr, nullptr, nullptr, 0,
                                        vblock, vgrid);
     }
 }
 
 template <int D, bool kIsCodebook>
 static cudaError_t prep_rows(const float* in, int64_t rows, float* unit32, float* sq, float* denom, __half* unit16,
-                             int* info, float* en32c, float* csq_cell, const ZeroList& zl, cudaStream_t s) {
+                             int* info, float* en32c, float* csq_cell, int cell_kind, const ZeroList& zl, cudaStream_t s) {
     if (rows == 0 && kIsCodebook) return cudaSuccess;
     const int64_t cap = kIsCodebook ? kInfoSlots : (int64_t)sm_count() * 8;
     if constexpr (D < 128) {
@@ -236,7 +252,7 @@ static cudaError_t prep_rows(const float* in, int64_t rows, float* unit32, float
         if (blocks < 1) blocks = 1;
         cudaError_t e = launch_pdl(k_prep_rows_small<D, kIsCodebook>, dim3((unsigned)blocks), dim3(256), 0, s,
                                    reinterpret_cast<const float4*>(in), rows, reinterpret_cast<float4*>(unit32), sq, denom,
-                                   reinterpret_cast<uint2*>(unit16), info, reinterpret_cast<float4*>(en32c), csq_cell, zl);
+                                   reinterpret_cast<uint2*>(unit16), info, reinterpret_cast<float4*>(en32c), csq_cell, cell_kind, zl);
         if (e != cudaSuccess) return e;
     } else {
         constexpr int kRows = (RowMap<D>::kPerLane <= 4) ? 4 : 2;
@@ -245,7 +261,7 @@ static cudaError_t prep_rows(const float* in, int64_t rows, float* unit32, float
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
         cudaError_t e = launch_pdl(k_prep_rows<D, kIsCodebook>, dim3((unsigned)blocks), dim3(warps_per_block * 32), 0, s, in,
-                                   rows, unit32, sq, denom, unit16, info, zl);
+                                   rows, unit32, sq, denom, unit16, info, reinterpret_cast<float4*>(en32c), csq_cell, zl);
         if (e != cudaSuccess) return e;
     }
     count_launch();
@@ -255,7 +271,7 @@ static cudaError_t prep_rows(const float* in, int64_t rows, float* unit32, float
 static cudaError_t prep_codebook_rows(const float* weight, const CodebookView& cb, cudaStream_t s) {
     const ZeroList none = {};
     VQ_DISPATCH_D(cb.D, return (prep_rows<kD, true>(weight, cb.K, cb.en32, cb.code_sq, cb.code_denom, cb.en16,
-                                                     cb.info, cb.en32c, cb.csq_cell, none, s)));
+                                                     cb.info, cb.en32c, cb.csq_cell, cb.cell_kind, none, s)));
     return cudaSuccess;
 }
 
@@ -267,7 +283,7 @@ cudaError_t launch_prep_codebook(const float* weight, const CodebookView& cb, cu
 
 cudaError_t launch_prep_tokens(const float* z, int64_t T, int D, float* zn32, float* row_sq, float* denom,
                                __half* zn16, const ZeroList& zl, cudaStream_t s) {
-    VQ_DISPATCH_D(D, return (prep_rows<kD, false>(z, T, zn32, row_sq, denom, zn16, nullptr, nullptr, nullptr, zl, s)));
+    VQ_DISPATCH_D(D, return (prep_rows<kD, false>(z, T, zn32, row_sq, denom, zn16, nullptr, nullptr, nullptr, 0, zl, s)));
     return cudaSuccess;
 }
 
@@ -290,11 +306,11 @@ cudaError_t launch_prep_fused(const float* weight, const CodebookView& cb, const
     cudaError_t e = cudaErrorInvalidValue;
     switch (D) {
         case 16: e = launch_pdl(k_prep_rows_fused<16>, dim3((unsigned)(cb_blocks + tok_blocks)), dim3(256), 0, s, c, cb.info,
-                                reinterpret_cast<float4*>(cb.en32c), cb.csq_cell, cb_blocks, t, zl); break;
+                                reinterpret_cast<float4*>(cb.en32c), cb.csq_cell, cb.cell_kind, cb_blocks, t, zl); break;
         case 32: e = launch_pdl(k_prep_rows_fused<32>, dim3((unsigned)(cb_blocks + tok_blocks)), dim3(256), 0, s, c, cb.info,
-                                reinterpret_cast<float4*>(cb.en32c), cb.csq_cell, cb_blocks, t, zl); break;
+                                reinterpret_cast<float4*>(cb.en32c), cb.csq_cell, cb.cell_kind, cb_blocks, t, zl); break;
         case 64: e = launch_pdl(k_prep_rows_fused<64>, dim3((unsigned)(cb_blocks + tok_blocks)), dim3(256), 0, s, c, cb.info,
-                                reinterpret_cast<float4*>(cb.en32c), cb.csq_cell, cb_blocks, t, zl); break;
+                                reinterpret_cast<float4*>(cb.en32c), cb.csq_cell, cb.cell_kind, cb_blocks, t, zl); break;
         default: break;
     }
     count_launch();

