@@ -200,7 +200,7 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
     vq::ZeroList zl = {};
     int nz = 0;
     auto zero = [&](void* p, size_t bytes) { zl.ptr[nz] = p; zl.bytes[nz] = bytes; ++nz; };
-    if (use_tc) zero(w.n_flagged, sizeof(int) * (tc16 ? 64 + vq::kFlaggedCap : 64));
+    if (use_tc) zero(w.n_flagged, sizeof(int) * (tc16 ? 64 + vq::kFlaggedCap : 64 + vq::kFewFlagged));
     if (!(flags & VQ_FLAG_KEEP_STATS)) {
         zero(st, sizeof(int64_t) * VQ_STATS_LEN);
         if (hist) zero(hist, sizeof(int32_t) * (size_t)K);
@@ -228,7 +228,7 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
         // D = 32: tensor-core filter -> records; one kernel then does the exact rescoring, the sliced search of
         // the undecided rows and the finish pass.  Undecided rows beyond kFlaggedCap (degenerate inputs) overflow
         // into the generic exhaustive kernel + a listed finish; both leave at once when there are none.
-        VQ_CUDA(vq::launch_dist_tc(zn16, zn32, w.row_sq, cbv, T, w.cand, w.flagged, w.n_flagged, st, w.tc_ws, s));
+        VQ_CUDA(vq::launch_dist_tc(zn16, zn32, w.row_sq, cbv, T, w.cand, w.flagged, w.n_flagged, st, w.tc_ws, w.scan_ws, s));
         timer.stop();
         SlotTimer exact_timer(s, VQ_PROFILE_EXACT_FINISH);
         VQ_CUDA(vq::launch_exact_finish16(w.tc_ws, zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, w.n_flagged + 64, w.scan_ws,
@@ -244,8 +244,10 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
         }
     } else {
         if (use_tc) {
-            VQ_CUDA(vq::launch_dist_tc(zn16, zn32, w.row_sq, cbv, T, w.cand, w.flagged, w.n_flagged, st, w.tc_ws, s));
-            VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, T, w.cand, st, w.scan_ws, s));
+            // filter -> exact rescoring (+ the undecided rows when they are few) -> tiled exhaustive scan of a long list
+            VQ_CUDA(vq::launch_dist_tc(zn16, zn32, w.row_sq, cbv, T, w.cand, w.flagged, w.n_flagged, st, w.tc_ws, w.scan_ws, s));
+            VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, T, w.cand, st, w.scan_ws, s,
+                                          vq::kFewFlagged));
         } else {
             VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, nullptr, nullptr, T, w.cand, st, nullptr, s));
         }

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) k_scan_exact(const float* __restrict__ zn
                                                     int64_t row_end, int* __restrict__ cand,
                                                     float4* __restrict__ partial, int partial_cap,
                                                     int* __restrict__ tile_done, int64_t* __restrict__ stats,
-                                                    ListedFinish fin) {
+                                                    ListedFinish fin, int min_rows) {
     __shared__ __align__(16) float zs[kDK][kTM + 4];
     __shared__ __align__(16) float es[kDK][kTN + 4];
     __shared__ int row_id[kTM];
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256) k_scan_exact(const float* __restrict__ zn
     pdl_trigger();
     pdl_wait();
     int64_t n_rows = rows ? (int64_t)(*n_rows_ptr) : T;
+    if (rows && n_rows <= min_rows) return;         // a short list was handled by the rescoring kernel
     if (n_rows > row_end) n_rows = row_end;
     long long loss_fx = 0;
     unsigned long long bad = 0;
@@ -241,7 +242,7 @@ size_t scan_partial_bytes(int64_t T) {
 
 cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
                               const int* rows, const int* n_rows, int64_t max_rows, int* cand, int64_t* stats,
-                              void* partial_ws, cudaStream_t s) {
+                              void* partial_ws, cudaStream_t s, int min_rows) {
     const int64_t n = rows ? max_rows : T;
     if (n == 0) return cudaSuccess;
     const int64_t cap_blocks = (int64_t)sm_count() * 16;
@@ -249,7 +250,7 @@ cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const Code
         int64_t blocks = (n + kTM - 1) / kTM;
         if (blocks > cap_blocks) blocks = cap_blocks;
         k_scan_exact<<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, 0,
-                                                     n, cand, nullptr, 0, nullptr, stats, ListedFinish{});
+                                                     n, cand, nullptr, 0, nullptr, stats, ListedFinish{}, min_rows);
         count_launch();
         return cudaGetLastError();
     }
@@ -262,19 +263,20 @@ cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const Code
     float4* partial = reinterpret_cast<float4*>(static_cast<char*>(partial_ws) + kTileDoneBytes);
     cudaError_t e = cudaMemsetAsync(tile_done, 0, kTileDoneBytes, s);
     if (e != cudaSuccess) return e;
-    // few rows are expected: a small grid that strides over the row tiles keeps the empty-list cost at
-    // a couple of microseconds (each block reads the device-side row count and leaves)
+    // the list length is only known on the device: the grid covers up to 128 row tiles x the code splits (blocks
+    // beyond the list read the row count and leave; an empty list costs a few microseconds), enough parallelism for
+    // the ~0.5 % of rows the D = 256 filter leaves undecided
     int tiles = (cap + kTM - 1) / kTM;
-    if (tiles > 16) tiles = 16;
+    if (tiles > 128) tiles = 128;
     dim3 grid((unsigned)tiles, (unsigned)splits);
     k_scan_exact<<<grid, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, 0, cap, cand,
-                                      partial, cap, tile_done, stats, ListedFinish{});
+                                      partial, cap, tile_done, stats, ListedFinish{}, min_rows);
     count_launch();
     if (n > cap) {
         int64_t blocks = (n - cap + kTM - 1) / kTM;
         if (blocks > sm_count()) blocks = sm_count();
         k_scan_exact<<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, cap,
-                                                     n, cand, nullptr, 0, nullptr, stats, ListedFinish{});
+                                                     n, cand, nullptr, 0, nullptr, stats, ListedFinish{}, min_rows);
         count_launch();
     }
     return cudaGetLastError();
@@ -289,7 +291,7 @@ cudaError_t launch_scan_listed_tail(const float* zn32, const float* row_sq, cons
     if (blocks <= 0) return cudaSuccess;
     if (blocks > sm_count()) blocks = sm_count();
     cudaError_t e = launch_pdl(k_scan_exact, dim3((unsigned)blocks), dim3(256), 0, s, zn32, row_sq, cb.en32, cb.code_sq, T, cb.K,
-                               cb.D, rows, n_rows, row_begin, T, cand, nullptr, 0, nullptr, stats, fin);
+                               cb.D, rows, n_rows, row_begin, T, cand, nullptr, 0, nullptr, stats, fin, 0);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }

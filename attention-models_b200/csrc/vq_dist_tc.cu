@@ -59,10 +59,13 @@ struct SmemLayout {
 constexpr int kHandBytes = kRowsPerCta * 32;     // per row: {g1|g2<<16 or -1, g3, mask1, mask2} {mask3, -, -, -}
 __host__ __device__ constexpr int a_stages(int kb) { return kb <= 2 ? 2 : 1; }
 __host__ __device__ constexpr int b_stages(int kb) { return kb == 1 ? 8 : (kb <= 4 ? 4 : 2); }
-// slot-maxima snapshots of the best groups: kAreas x 256 rows x 32 floats; rows padded by 16 B
-// (conflict-free STS.128) except at D = 256 where shared memory is tight (2 areas, unpadded)
-__host__ __device__ constexpr int snap_areas(int kb) { return kb <= 4 ? 3 : 2; }
-__host__ __device__ constexpr int snap_row_bytes(int kb) { return kb <= 4 ? 144 : 128; }
+// slot-maxima snapshots of the best three groups: 3 areas x 256 rows x 32 slots; rows padded by 16 B (conflict-free
+// STS.128).  At D = 256 the A operand alone is 128 KB, so the snapshots are kept as fp16 (80-byte rows): the verdict
+// then compares against thr - kSnapSlack, which covers the rounding of the stored maxima (|score| <= 1).
+__host__ __device__ constexpr int snap_areas(int kb) { return 3; }
+__host__ __device__ constexpr bool snap_half(int kb) { return kb > 4; }
+__host__ __device__ constexpr int snap_row_bytes(int kb) { return kb <= 4 ? 144 : 80; }
+constexpr float kSnapSlack = 5.0e-4f;   // >= 2^-11: fp16 rounding of a slot maximum of magnitude <= 1
 constexpr int kMaxBStages = 8;
 __host__ __device__ inline SmemLayout smem_layout(int kb) {
     SmemLayout L;
@@ -99,6 +102,7 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     constexpr int BS = b_stages(KB);
     constexpr int kAreas = snap_areas(KB);
     constexpr int kSnapRow = snap_row_bytes(KB);
+    constexpr bool kSnapHalf = snap_half(KB);
     const SmemLayout L = smem_layout(KB);
     // swizzled TMA/UMMA tiles want a 1024-byte aligned base; the launch reserves 1 KiB of slack for this
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -287,11 +291,26 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                 if (is3) {
                     // whichever rank the group takes, the group that drops out is the current last one: reuse its area
                     const uint32_t dst = snap0 + a3 * kSnapArea;
+                    if constexpr (kSnapHalf) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16 * q), "f"(slot[4 * q]),
-                                     "f"(slot[4 * q + 1]), "f"(slot[4 * q + 2]), "f"(slot[4 * q + 3])
-                                     : "memory");
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t h[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const __half2 p = __floats2half2_rn(slot[8 * q + 2 * j], slot[8 * q + 2 * j + 1]);
+                                h[j] = *reinterpret_cast<const uint32_t*>(&p);
+                            }
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16 * q), "r"(h[0]), "r"(h[1]),
+                                         "r"(h[2]), "r"(h[3])
+                                         : "memory");
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16 * q), "f"(slot[4 * q]),
+                                         "f"(slot[4 * q + 1]), "f"(slot[4 * q + 2]), "f"(slot[4 * q + 3])
+                                         : "memory");
+                    }
                 }
                 // sorted insert of c1 into (m1 >= m2 >= m3 >= m4); identities and areas follow
                 const float lo1 = fminf(c1, m1);
@@ -327,13 +346,29 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             for (int a = 0; a < kAreas; ++a) {
                 if (a == 0 || mv[a] >= thr) {
                     const uint32_t src = snap0 + av[a] * kSnapArea;
+                    if constexpr (kSnapHalf) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                     : "=f"(kept[4 * q]), "=f"(kept[4 * q + 1]), "=f"(kept[4 * q + 2]), "=f"(kept[4 * q + 3])
-                                     : "r"(src + 16 * q));
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t h[4];
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3])
+                                         : "r"(src + 16 * q));
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) mask[a] |= (kept[j] >= thr) ? (1u << j) : 0u;
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+                                kept[8 * q + 2 * j] = f.x; kept[8 * q + 2 * j + 1] = f.y;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(kept[4 * q]), "=f"(kept[4 * q + 1]), "=f"(kept[4 * q + 2]), "=f"(kept[4 * q + 3])
+                                         : "r"(src + 16 * q));
+                    }
+                    const float thr_slot = kSnapHalf ? thr - kSnapSlack : thr;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mask[a] |= (kept[j] >= thr_slot) ? (1u << j) : 0u;
                 }
             }
             // decided iff no further group can hold the winner (NaN / -inf rows fail the comparisons)
@@ -385,13 +420,45 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
 // so all paths return identical indices.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kRescoreThreads = 128;
+constexpr int kFlaggedSlices = 32;
+struct __align__(16) FlaggedPartial {
+    unsigned long long best; float second; float pad;
+};
+// exact distance of the staged row zs to member m of generic cell ci: sequential fma chain over d = 0..D-1
+template <int D>
+__device__ __forceinline__ float cell_distance_g(const float4* __restrict__ en32c, const float* __restrict__ csq_cell, int ci,
+                                                 int m, const float4* zs, float a_sq) {
+    constexpr int kChunks = D / 4;
+    const float4* e4 = en32c + (int64_t)ci * kChunks * 8 + m;
+    const float csq = __ldg(csq_cell + ci * 8 + m);
+    float dot = 0.f;
+#pragma unroll 1
+    for (int q0 = 0; q0 < kChunks; q0 += 8) {
+        float4 ev[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ev[q] = __ldg(e4 + (q0 + q) * 8);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 z = zs[q0 + q];
+            dot = __fmaf_rn(z.x, ev[q].x, dot);
+            dot = __fmaf_rn(z.y, ev[q].y, dot);
+            dot = __fmaf_rn(z.z, ev[q].z, dot);
+            dot = __fmaf_rn(z.w, ev[q].w, dot);
+        }
+    }
+    return ref_distance(a_sq, csq, dot);
+}
+
 template <int D>
 __global__ void __launch_bounds__(kRescoreThreads)
 k_rescore_g(const int4* __restrict__ rec, const float* __restrict__ zn32, const float* __restrict__ row_sq,
-            const float4* __restrict__ en32c, const float* __restrict__ csq_cell, int T, int* __restrict__ cand,
-            int64_t* __restrict__ stats) {
+            const float4* __restrict__ en32c, const float* __restrict__ csq_cell, int T, int K,
+            const int* __restrict__ flagged, const int* __restrict__ n_flagged, FlaggedPartial* __restrict__ partial,
+            int* __restrict__ done, int* __restrict__ cand, int64_t* __restrict__ stats) {
     constexpr int kChunks = D / 4;
     __shared__ __align__(16) float4 s_z[kRescoreThreads / 32][4][kChunks + 1];
+    __shared__ unsigned long long s_best[kRescoreThreads / 32];
+    __shared__ float s_second[kRescoreThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m = lane & 7, grp = lane >> 3;
     const float4* zn4 = reinterpret_cast<const float4*>(zn32);
@@ -429,24 +496,7 @@ k_rescore_g(const int4* __restrict__ rec, const float* __restrict__ zn32, const 
                 const int g = gs[a];
                 const int ci = g * 32 + slot;
                 const int code = g * kGroupCols + 64 * (m >> 1) + ((slot & 16) << 1) + (slot & 15) + 16 * (m & 1);
-                const float4* e4 = en32c + (int64_t)ci * kChunks * 8 + m;
-                const float csq = __ldg(csq_cell + ci * 8 + m);
-                float dot = 0.f;
-#pragma unroll 1
-                for (int q0 = 0; q0 < kChunks; q0 += 8) {
-                    float4 ev[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) ev[q] = __ldg(e4 + (q0 + q) * 8);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 z = zs[q0 + q];
-                        dot = __fmaf_rn(z.x, ev[q].x, dot);
-                        dot = __fmaf_rn(z.y, ev[q].y, dot);
-                        dot = __fmaf_rn(z.z, ev[q].z, dot);
-                        dot = __fmaf_rn(z.w, ev[q].w, dot);
-                    }
-                }
-                top.add(dist_key(ref_distance(a_sq, csq, dot), code));
+                top.add(dist_key(cell_distance_g<D>(en32c, csq_cell, ci, m, zs, a_sq), code));
             }
         }
 #pragma unroll
@@ -460,6 +510,64 @@ k_rescore_g(const int4* __restrict__ rec, const float* __restrict__ zn32, const 
             cand[row] = (int)(uint32_t)top.best | kCandExactBit;
             if (top.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) ++ties;
             if (n_cells > 1) ++multi;
+        }
+    }
+    // ---- the rows the filter could not decide, when they are few (latency matters, not throughput): each listed row
+    // is split over kFlaggedSlices items that scan a slice of ALL cells; the last item of a row to finish folds the
+    // partial (best, second) pairs.  Longer lists are left to the tiled exhaustive kernel (k_scan_exact).
+    {
+        const int n = *n_flagged;
+        if (n > 0 && n <= kFewFlagged) {
+            const int bgrp = threadIdx.x >> 3;
+            const int n_cells = K / 8;
+            const int per_slice = (n_cells + kFlaggedSlices - 1) / kFlaggedSlices;
+            for (int item = blockIdx.x; item < n * kFlaggedSlices; item += gridDim.x) {
+                const int i = item / kFlaggedSlices, slice = item % kFlaggedSlices;
+                const int row = flagged[i];
+                __syncthreads();                       // the previous item's shared values are consumed
+                for (int c = threadIdx.x; c < kChunks; c += kRescoreThreads) s_z[0][0][c] = __ldg(zn4 + (int64_t)row * kChunks + c);
+                __syncthreads();
+                const float4* zs = s_z[0][0];
+                const float a_sq = __ldg(row_sq + row);
+                Top2 top;
+                top.init();
+                const int c_end = min(n_cells, (slice + 1) * per_slice);
+                for (int ci = slice * per_slice + bgrp; ci < c_end; ci += kRescoreThreads / 8) {
+                    const int g = ci >> 5, slot = ci & 31;
+                    const int code = g * kGroupCols + 64 * (m >> 1) + ((slot & 16) << 1) + (slot & 15) + 16 * (m & 1);
+                    top.add(dist_key(cell_distance_g<D>(en32c, csq_cell, ci, m, zs, a_sq), code));
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const unsigned long long ob = __shfl_xor_sync(VQ_FULL, top.best, off);
+                    const float os = __shfl_xor_sync(VQ_FULL, top.second, off);
+                    top.merge(ob, os);
+                }
+                if (lane == 0) { s_best[warp] = top.best; s_second[warp] = top.second; }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    Top2 all;
+                    all.init();
+                    for (int w = 0; w < kRescoreThreads / 32; ++w) all.merge(s_best[w], s_second[w]);
+                    FlaggedPartial pp;
+                    pp.best = all.best; pp.second = all.second; pp.pad = 0.f;
+                    partial[(int64_t)i * kFlaggedSlices + slice] = pp;
+                    __threadfence();
+                    if (atomicAdd(done + i, 1) == kFlaggedSlices - 1) {
+                        __threadfence();
+                        Top2 fin;
+                        fin.init();
+                        for (int w = 0; w < kFlaggedSlices; ++w) {
+                            const FlaggedPartial* q = partial + (int64_t)i * kFlaggedSlices + w;
+                            fin.merge(__ldcg(&q->best), __ldcg(&q->second));
+                        }
+                        const float bd = key_dist(fin.best);
+                        cand[row] = (int)(uint32_t)fin.best | kCandExactBit;
+                        if (fin.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) ++ties;
+                        done[i] = 0;                   // ready for the next call
+                    }
+                }
+            }
         }
     }
     if (stats) {
@@ -528,7 +636,7 @@ size_t tc_workspace_bytes(int64_t T, int K, int D) {
 template <int KB>
 static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, int T, const float* zn32,
                                     const float* row_sq, const CodebookView& cb, int* cand, int* flagged,
-                                    int* n_flagged, int64_t* stats, void* records, cudaStream_t s) {
+                                    int* n_flagged, int64_t* stats, void* records, void* partial_ws, cudaStream_t s) {
     const tc::SmemLayout L = tc::smem_layout(KB);
     static bool configured = false;
     if (!configured) {
@@ -549,7 +657,9 @@ static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb
         if (blocks > cap) blocks = cap;
         tc::k_rescore_g<D><<<(unsigned)blocks, tc::kRescoreThreads, 0, s>>>(static_cast<const int4*>(records), zn32, row_sq,
                                                                              reinterpret_cast<const float4*>(cb.en32c), cb.csq_cell, T,
-                                                                             cand, stats);
+                                                                             cb.K, flagged, n_flagged,
+                                                                             static_cast<tc::FlaggedPartial*>(partial_ws),
+                                                                             n_flagged + 64, cand, stats);
         count_launch();
     }
 #ifdef VQ_TC_INSTRUMENT
@@ -571,7 +681,7 @@ static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb
 
 cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* row_sq, const CodebookView& cb,
                            int64_t T, int* cand, int* flagged, int* n_flagged, int64_t* stats, void* tc_ws,
-                           cudaStream_t s) {
+                           void* partial_ws, cudaStream_t s) {
     if (T == 0) return cudaSuccess;
     CUtensorMap ma, mb;
     if (tc16_supported(T, cb.K, cb.D)) {
@@ -584,10 +694,10 @@ cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* r
         !tc::make_map(&mb, cb.en16, (uint64_t)cb.K, cb.D, tc::kTileN))
         return cudaErrorInvalidValue;
     switch (cb.D / tc::kKBlock) {
-        case 1: return launch_tc_kernel<1>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, s);
-        case 2: return launch_tc_kernel<2>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, s);
-        case 4: return launch_tc_kernel<4>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, s);
-        case 8: return launch_tc_kernel<8>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, s);
+        case 1: return launch_tc_kernel<1>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
+        case 2: return launch_tc_kernel<2>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
+        case 4: return launch_tc_kernel<4>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
+        case 8: return launch_tc_kernel<8>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
         default: return cudaErrorInvalidValue;
     }
 }

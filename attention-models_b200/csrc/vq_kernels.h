@@ -56,9 +56,10 @@ cudaError_t launch_row_sumsq(const float* zn32, int64_t T, int D, float* row_sq,
 // Writes cand[row] = index | kCandExactBit and counts near-tie rows into stats.
 // partial_ws (scan_partial_bytes) lets listed rows split the codebook over blocks; may be null.
 size_t scan_partial_bytes(int64_t T);
+// min_rows: a listed scan leaves at once when the list holds at most min_rows entries (someone else took them)
 cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
                               const int* rows, const int* n_rows, int64_t max_rows, int* cand, int64_t* stats,
-                              void* partial_ws, cudaStream_t s);
+                              void* partial_ws, cudaStream_t s, int min_rows = 0);
 
 // outputs of the finish pass for rows a search kernel finishes itself (all null: search only)
 struct ListedFinish {
@@ -82,9 +83,13 @@ cudaError_t launch_exact_finish16(const void* records, const float* zn32, const 
 // decide are appended to flagged[] (count in *n_flagged).
 bool tc_supported(int64_t T, int K, int D);
 size_t tc_workspace_bytes(int64_t T, int K, int D);
+// generic D: the filter launch is followed by k_rescore_g, which also searches the listed rows itself when there are at
+// most kFewFlagged of them (needs n_flagged[64 ..] zeroed: kFewFlagged done counters; partial_ws >= kFewFlagged * 512 B);
+// longer lists are for launch_scan_exact(..., min_rows = kFewFlagged)
+constexpr int kFewFlagged = 128;
 cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* row_sq, const CodebookView& cb,
                            int64_t T, int* cand, int* flagged, int* n_flagged, int64_t* stats, void* tc_ws,
-                           cudaStream_t s);
+                           void* partial_ws, cudaStream_t s);
 
 // ---- vq_finish.cu ----------------------------------------------------------------------------
 // idx / hist / z_q (token-major) / loss partial from final indices in cand[]; with seg_sums (K*D + K int64, not
