@@ -25,6 +25,7 @@
 // the results only after its next kernel saw every peer's ready flag of the next step, i.e. after every peer's
 // previous kernel -- which read them -- had completed.
 #include <cstdio>
+#include <cstdlib>
 
 #include "vq_common.cuh"
 #include "vq_kernels.h"
@@ -75,10 +76,12 @@ __device__ __forceinline__ void st_peer_s64(long long* p, long long v) {
 }
 
 // wait until flags[r] >= epoch for every peer r (warp 0 of the block; returns false on timeout)
-__device__ __forceinline__ bool wait_flags(const char* own_base, size_t flags_off, int world, int rank, unsigned epoch) {
+// (with_self: also this rank's own flag -- its last block to finish sets it)
+__device__ __forceinline__ bool wait_flags(const char* own_base, size_t flags_off, int world, int rank, unsigned epoch,
+                                           bool with_self = false) {
     const int lane = threadIdx.x & 31;
     bool ok = true;
-    if (lane < world && lane != rank) {
+    if (lane < world && (with_self || lane != rank)) {
         const unsigned* f = reinterpret_cast<const unsigned*>(own_base + flags_off + (size_t)lane * kFlagStride);
         const long long t0 = clock64();
         unsigned v;
@@ -91,9 +94,10 @@ __device__ __forceinline__ bool wait_flags(const char* own_base, size_t flags_of
     }
     return __all_sync(VQ_FULL, ok);
 }
-__device__ __forceinline__ void publish_flags(const PeerPtrs& peers, size_t flags_off, int world, int rank, unsigned epoch) {
+__device__ __forceinline__ void publish_flags(const PeerPtrs& peers, size_t flags_off, int world, int rank, unsigned epoch,
+                                              bool with_self = false) {
     const int lane = threadIdx.x & 31;
-    if (lane < world && lane != rank) {
+    if (lane < world && (with_self || lane != rank)) {
         __threadfence_system();
         unsigned* f = reinterpret_cast<unsigned*>(const_cast<char*>(peers.base[lane]) + flags_off + (size_t)rank * kFlagStride);
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
@@ -101,7 +105,14 @@ __device__ __forceinline__ void publish_flags(const PeerPtrs& peers, size_t flag
 }
 
 template <int D>
-__global__ void __launch_bounds__(512) k_codebook_grad_sharded(PeerPtrs peers, int world, int rank, ExchangeLayout L, int slot,
+// Small footprint on purpose (256 threads, <= 64 registers): the kernel spends most of its life waiting for other
+// GPUs while the token backward shares the SMs with it; with 512 threads x ~100 registers it left room for one
+// backward block per SM and the two kernels ran back to back in effect.
+#ifndef VQ_PEER_THREADS
+#define VQ_PEER_THREADS 256
+#endif
+__global__ void __launch_bounds__(VQ_PEER_THREADS, 1024 / VQ_PEER_THREADS) k_codebook_grad_sharded(PeerPtrs peers, int world, int rank, int one_shot,
+                                                                  ExchangeLayout L, int slot,
                                                                unsigned epoch, const float* __restrict__ en,
                                                                const float* __restrict__ code_denom, int K, float coef_base,
                                                                const float* __restrict__ g_loss, int64_t n_elem_total,
@@ -135,20 +146,31 @@ __global__ void __launch_bounds__(512) k_codebook_grad_sharded(PeerPtrs peers, i
     constexpr int kPer = (D + 31) / 32;
     constexpr int kC = (kPer <= 2) ? 2 : 1;
     constexpr int kR = (16 / (kPer * kC)) > 8 ? 8 : (16 / (kPer * kC));
-    const int per_rank = (K + world - 1) / world;
-    const int k_lo = min(K, rank * per_rank), k_hi = min(K, k_lo + per_rank);
+    // one_shot (small worlds): every rank reduces ALL codes itself and writes its own outputs -- (W-1) x the partials
+    // over NVLink but a single flag round trip; else the rank owns a slice and phase 3 gathers the slices
+    const bool local_out = (world == 1) || one_shot;
+    const int per_rank = local_out ? K : (K + world - 1) / world;
+    const int k_lo = local_out ? 0 : min(K, rank * per_rank), k_hi = min(K, k_lo + per_rank);
     const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int n_warps = gridDim.x * (blockDim.x >> 5);
     for (int k0 = k_lo + warp * kC; k0 < k_hi; k0 += n_warps * kC) {
-        long long s[kC][kPer], bad[kC];
+        long long s[kC][kPer];
+        int bad[kC];
+        float y[kC][kPer], dn[kC];                       // local operands, requested before the remote ones are awaited
 #pragma unroll
         for (int c = 0; c < kC; ++c) {
             bad[c] = 0;
+            dn[c] = (k0 + c < k_hi) ? __ldg(code_denom + k0 + c) : 1.f;
 #pragma unroll
-            for (int j = 0; j < kPer; ++j) s[c][j] = 0;
+            for (int j = 0; j < kPer; ++j) {
+                s[c][j] = 0;
+                const int d = lane + 32 * j;
+                y[c][j] = (k0 + c < k_hi && d < D) ? __ldg(en + (int64_t)(k0 + c) * D + d) : 0.f;
+            }
         }
         for (int r0 = 0; r0 < world; r0 += kR) {
-            long long v[kR][kC][kPer], b[kR][kC];
+            long long v[kR][kC][kPer];
+            int b[kR][kC];
 #pragma unroll
             for (int u = 0; u < kR; ++u) {
                 const int r = r0 + u;
@@ -163,14 +185,16 @@ __global__ void __launch_bounds__(512) k_codebook_grad_sharded(PeerPtrs peers, i
                         v[u][c][j] = 0;
                         if (r < world && k < k_hi && d < D) v[u][c][j] = ld_peer_s64(seg + (int64_t)k * D + d);
                     }
-                    if (r < world && k < k_hi && lane == 0) b[u][c] = ld_peer_s64(seg + (int64_t)K * D + k);
+                    if (r < world && k < k_hi && lane == 0)      // low word of the count: only zero / non-zero matters
+                        b[u][c] = ld_peer_s32(reinterpret_cast<const int*>(seg + (int64_t)K * D + k)) |
+                                  ld_peer_s32(reinterpret_cast<const int*>(seg + (int64_t)K * D + k) + 1);
                 }
             }
 #pragma unroll
             for (int u = 0; u < kR; ++u)
 #pragma unroll
                 for (int c = 0; c < kC; ++c) {
-                    bad[c] += b[u][c];
+                    bad[c] |= b[u][c];
 #pragma unroll
                     for (int j = 0; j < kPer; ++j) s[c][j] += v[u][c][j];
                 }
@@ -179,27 +203,26 @@ __global__ void __launch_bounds__(512) k_codebook_grad_sharded(PeerPtrs peers, i
         for (int c = 0; c < kC; ++c) {
             const int k = k0 + c;
             if (k >= k_hi) break;
-            float g[kPer], y[kPer];
+            float g[kPer];
             float dot = 0.f;
 #pragma unroll
             for (int j = 0; j < kPer; ++j) {
                 const int d = lane + 32 * j;
-                g[j] = 0.f; y[j] = 0.f;
+                g[j] = 0.f;
                 if (d < D) {
                     g[j] = seg_to_grad(s[c][j], coef);
-                    y[j] = __ldg(en + (int64_t)k * D + d);
-                    dot = __fmaf_rn(y[j], g[j], dot);
+                    dot = __fmaf_rn(y[c][j], g[j], dot);
                 }
             }
             dot = warp_sum(dot);
-            const float inv = __fdiv_rn(1.f, __ldg(code_denom + k));
+            const float inv = __fdiv_rn(1.f, dn[c]);
             const bool poisoned = __shfl_sync(VQ_FULL, bad[c], 0) != 0;
 #pragma unroll
             for (int j = 0; j < kPer; ++j) {
                 const int d = lane + 32 * j;
                 if (d < D) {
-                    const float out = poisoned ? __int_as_float(0x7fc00000) : grad_row_element(g[j], y[j], dot, inv);
-                    if (world == 1) grad[(int64_t)k * D + d] = out;
+                    const float out = poisoned ? __int_as_float(0x7fc00000) : grad_row_element(g[j], y[c][j], dot, inv);
+                    if (local_out) grad[(int64_t)k * D + d] = out;
                     else
                         for (int r = 0; r < world; ++r)
                             st_peer_f32(reinterpret_cast<float*>(const_cast<char*>(peers.base[r]) + L.results_off) + (int64_t)k * D + d, out);
@@ -208,7 +231,8 @@ __global__ void __launch_bounds__(512) k_codebook_grad_sharded(PeerPtrs peers, i
         }
     }
     if (hist_total)
-        for (int k = k_lo + blockIdx.x * blockDim.x + threadIdx.x; k < k_hi; k += gridDim.x * blockDim.x) {
+        // (trailing blocks first: they have no codes of the slice when K / W < warps of the grid)
+        for (int k = k_lo + (gridDim.x - 1 - blockIdx.x) * blockDim.x + threadIdx.x; k < k_hi; k += gridDim.x * blockDim.x) {
             int hv[VQ_PEER_MAX_RANKS];
 #pragma unroll
             for (int r = 0; r < VQ_PEER_MAX_RANKS; ++r)
@@ -216,7 +240,7 @@ __global__ void __launch_bounds__(512) k_codebook_grad_sharded(PeerPtrs peers, i
             long long h = 0;
 #pragma unroll
             for (int r = 0; r < VQ_PEER_MAX_RANKS; ++r) h += hv[r];
-            if (world == 1) hist_total[k] = h;
+            if (local_out) hist_total[k] = h;
             else
                 for (int r = 0; r < world; ++r)
                     st_peer_s64(reinterpret_cast<long long*>(const_cast<char*>(peers.base[r]) + L.results_off + L.results_hist_off) + k, h);
@@ -240,11 +264,17 @@ __global__ void __launch_bounds__(512) k_codebook_grad_sharded(PeerPtrs peers, i
         if (lane == 0 && loss)
             loss[0] = loss_from_fixed(tot[VQ_STAT_LOSS_FIXED], tot[VQ_STAT_NONFINITE], n_elem_total, form, beta);
     }
-    if (world == 1) return;
+    if (local_out) {
+        if (timed_out && threadIdx.x == 0 && stats_total)
+            atomicAdd(reinterpret_cast<unsigned long long*>(stats_total + VQ_STAT_PEER_TIMEOUT), 1ull);
+        return;
+    }
     // ---- 3. slices complete everywhere, then results -> caller's tensors ----
 #ifdef VQ_PEER_TRACE
     tr[2] = now();
 #endif
+    // every thread fences its own NVLink stores (one fence by thread 0 behind the barrier was tried: the peers then
+    // read stale rows now and then)
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -254,8 +284,10 @@ __global__ void __launch_bounds__(512) k_codebook_grad_sharded(PeerPtrs peers, i
     }
     __syncthreads();
     if (threadIdx.x < 32) {
-        if (s_last) publish_flags(peers, kDoneOff, world, rank, epoch);
-        timed_out |= !wait_flags(own, kDoneOff, world, rank, epoch);
+        // "done" includes this rank's own flag: a block whose peers finished early must still wait for the other blocks
+        // of its own rank, which write the rank's slice into the same results buffer
+        if (s_last) publish_flags(peers, kDoneOff, world, rank, epoch, true);
+        timed_out |= !wait_flags(own, kDoneOff, world, rank, epoch, true);
         if (timed_out && lane == 0 && stats_total)
             atomicAdd(reinterpret_cast<unsigned long long*>(stats_total + VQ_STAT_PEER_TIMEOUT), 1ull);
     }
@@ -273,8 +305,8 @@ __global__ void __launch_bounds__(512) k_codebook_grad_sharded(PeerPtrs peers, i
 #ifdef VQ_PEER_TRACE
     tr[4] = now();
     if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && epoch >= 10 && epoch < 14)
-        printf("rank %d epoch %u block %d: ready-wait %llu ns, slice %llu ns, done-wait %llu ns, copy %llu ns\n", rank, epoch,
-               blockIdx.x, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3]);
+        printf("rank %d epoch %u block %d: start %llu ready-wait %llu ns, slice %llu ns, done-wait %llu ns, copy %llu ns\n", rank, epoch,
+               blockIdx.x, tr[0] % 1000000000ull, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3]);
 #endif
 }
 
@@ -296,8 +328,12 @@ cudaError_t launch_codebook_grad_sharded(const void* const* peer_bufs, int world
         cudaError_t e = cudaMemsetAsync(stats_total + VQ_STAT_PEER_TIMEOUT, 0, sizeof(int64_t), s);
         if (e != cudaSuccess) return e;
     }
-    VQ_DISPATCH_D(cb.D, (k_codebook_grad_sharded<kD><<<blocks, world == 1 ? 256 : 512, 0, s>>>(
-                            p, world, rank, L, slot, epoch, cb.en32, cb.code_denom, cb.K, coef, g_loss, n_elem_total, form, beta,
+    // one flag round trip and (W-1) x 2.2 MB of reads, or two round trips and 2 (W-1)/W x as much: measured break-even
+    // between 4 and 8 GPUs (VQ_EXCHANGE_ONE_SHOT=0/1 forces a mode)
+    static const int forced = getenv("VQ_EXCHANGE_ONE_SHOT") ? atoi(getenv("VQ_EXCHANGE_ONE_SHOT")) : -1;
+    const int one_shot = forced >= 0 ? forced : (world <= 4 ? 1 : 0);
+    VQ_DISPATCH_D(cb.D, (k_codebook_grad_sharded<kD><<<blocks, world == 1 ? 256 : VQ_PEER_THREADS, 0, s>>>(
+                            p, world, rank, one_shot, L, slot, epoch, cb.en32, cb.code_denom, cb.K, coef, g_loss, n_elem_total, form, beta,
                             grad_weight, hist_total, loss, stats_total)));
     count_launch();
     return cudaGetLastError();

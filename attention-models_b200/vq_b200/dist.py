@@ -153,6 +153,8 @@ class ShardedQuantiser:
             raise ValueError("exchange must be 'peer' or 'collective'")
         self.world_size, self.exchange = world_size, exchange
         self._plans: Dict[tuple, Dict[str, object]] = {}
+        import os
+        self.trace = [] if os.environ.get("VQ_STEP_EVENTS") else None     # debugging: per-step CUDA events of the peer path
 
     @staticmethod
     def uses_tensor_cores(T: int, K: int, D: int) -> bool:
@@ -222,6 +224,8 @@ class ShardedQuantiser:
         with torch.cuda.device(dev):
             s = _stream(dev)
             if peer is not None:
+                if self.trace is not None and self.trace:
+                    pass
                 slot, epoch, seg, stats_ptr, hist_ptr = peer.next_step()
             else:
                 seg, stats_ptr, hist_ptr = _ptr(buf), _ptr(p["stats"]), _ptr(p["hist"])   # seg sums head the packed buffer
@@ -230,16 +234,32 @@ class ShardedQuantiser:
                                       _ptr(p["z_q"]), _ptr(p["idx"]), None, hist_ptr, stats_ptr,
                                       _ptr(p["zn"]), _ptr(p["denom"]), seg, _ptr(p["fws"]), p["fws_bytes"], s))
             if peer is not None:
-                # the exchange needs nothing of the backward: it runs beside the token backward
+                # The exchange needs nothing of the backward, so the two run side by side.  The exchange (two flag round
+                # trips over NVLink, ~25 us) is the longer one and stays on the caller's stream -- no cross-stream hand-off
+                # on the critical path -- while the token backward (~18 us of HBM streaming) goes to the side stream.
                 side = p["side"]
+                tr = None
+                if self.trace is not None:
+                    tr = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+                    self.trace.append(tr)
+                    p["ev_fwd"] = tr[1]
+                    p["ev_x"] = tr[3]
                 p["ev_fwd"].record()
-                side.wait_event(p["ev_fwd"])
                 _lib.check(lib.vq_backward_codebook_sharded(peer.ptr_array, peer.world, peer.rank, slot, epoch, cb, K, D,
                                                             form_id, self.beta, None, n_total, _ptr(p["grad_w"]),
-                                                            _ptr(p["hist_total"]), _ptr(p["loss"]), _ptr(p["stats"]),
-                                                            side.cuda_stream))
+                                                            _ptr(p["hist_total"]), _ptr(p["loss"]), _ptr(p["stats"]), s))
+                side.wait_event(p["ev_fwd"])
+                _lib.check(lib.vq_backward_tokens(_ptr(up), layout, T, hw, _ptr(p["zn"]), _ptr(p["denom"]), _ptr(p["idx"]),
+                                                  None, cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_z"]), None,
+                                                  _ptr(p["bws"]), p["bws_bytes"], side.cuda_stream))
+                if tr is not None:
+                    tr[2].record()
                 p["ev_x"].record(side)
-            if self.world_size == 1:
+                torch.cuda.current_stream(dev).wait_event(p["ev_x"])
+                if tr is not None:
+                    tr[4].record()
+                hist_out = p["hist_total"]
+            elif self.world_size == 1:
                 # one launch: grad_z, grad_weight and the loss
                 _lib.check(lib.vq_backward(_ptr(up), layout, T, hw, _ptr(p["zn"]), _ptr(p["denom"]), _ptr(p["idx"]), cb, K, D,
                                            form_id, self.beta, None, n_total, seg, stats_ptr, _ptr(p["grad_z"]), _ptr(p["grad_w"]),
@@ -249,15 +269,11 @@ class ShardedQuantiser:
                 _lib.check(lib.vq_backward_tokens(_ptr(up), layout, T, hw, _ptr(p["zn"]), _ptr(p["denom"]), _ptr(p["idx"]),
                                                   None, cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_z"]), None,
                                                   _ptr(p["bws"]), p["bws_bytes"], s))
-                if peer is not None:
-                    torch.cuda.current_stream(dev).wait_event(p["ev_x"])
-                    hist_out = p["hist_total"]
-                else:
-                    pack.fill_side_channels(buf, p["hist"], p["stats"])
-                    pack.all_reduce(buf, self.group)
-                    red_stats = pack.stats_from(buf)
-                    hist_out = pack.hist(buf)
-                    _lib.check(lib.vq_backward_codebook(seg, cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_w"]),
-                                                        _ptr(red_stats), _ptr(p["loss"]), s))
+                pack.fill_side_channels(buf, p["hist"], p["stats"])
+                pack.all_reduce(buf, self.group)
+                red_stats = pack.stats_from(buf)
+                hist_out = pack.hist(buf)
+                _lib.check(lib.vq_backward_codebook(seg, cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_w"]),
+                                                    _ptr(red_stats), _ptr(p["loss"]), s))
         return {"z_q": p["z_q"], "indices": p["idx"], "loss": p["loss"].view(()), "grad_z": p["grad_z"],
                 "grad_weight": p["grad_w"], "histogram": hist_out, "stats": p["stats"]}

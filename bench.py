@@ -302,6 +302,14 @@ def run_b200(args):
                "ms_per_step": e_ms, "note": "vq_host_step: pinned host in/out, all outputs (z_q, idx, loss, grad_z, "
                                             "grad_weight) copied back every step"}
 
+    if getattr(stepper, "trace", None):
+        torch.cuda.synchronize()
+        tr = stepper.trace[args.warmup + 2: args.warmup + args.steps]
+        n_ = len(tr) - 1
+        f = lambda a, b: sum(t[a].elapsed_time(t[b]) for t in tr[:-1]) / n_ * 1e3
+        nxt = sum(tr[i][4].elapsed_time(tr[i + 1][1]) for i in range(n_)) / n_ * 1e3
+        print(f"[rank {rank}] us: fwd_end->exchange_end {f(1, 2):.1f}  fwd_end->bwd_tokens_end {f(1, 3):.1f}  "
+              f"fwd_end->join {f(1, 4):.1f}  join->next fwd_end {nxt:.1f}", file=sys.stderr, flush=True)
     peer_timeouts = int(out["stats"][_lib.STAT_PEER_TIMEOUT].item()) if world > 1 and args.exchange == "peer" else 0
     stepper.close()
     if rank != 0:
