@@ -426,7 +426,29 @@ int vq_backward_codebook_sharded(const void* const* peer_bufs, int world, int ra
     const float coef = (float)((double)c2 * 2.0 / (double)n_elem_total);
     SlotTimer timer(static_cast<cudaStream_t>(stream), VQ_PROFILE_CODEBOOK_GRAD);
     VQ_CUDA(vq::launch_codebook_grad_sharded(peer_bufs, world, rank, slot, epoch, cbv, coef, g_loss, n_elem_total, form, beta,
-                                             grad_weight, hist_total, loss, stats_total, static_cast<cudaStream_t>(stream)));
+                                             grad_weight, hist_total, loss, stats_total, nullptr, static_cast<cudaStream_t>(stream)));
+    timer.stop();
+    return VQ_OK;
+}
+
+int vq_backward_sharded(const void* const* peer_bufs, int world, int rank, int slot, uint32_t epoch, const float* g_zq, int64_t T,
+                        const float* saved_zn, const float* saved_denom, const int64_t* idx, const void* cb, int K, int D, int form,
+                        float beta, const float* g_loss, int64_t n_elem_total, float* grad_z, float* grad_weight,
+                        int64_t* hist_total, float* loss, int64_t* stats_total, void* stream) {
+    if (int r = check_dims(T, K, D)) return r;
+    if (!peer_bufs || world < 1 || world > VQ_PEER_MAX_RANKS || rank < 0 || rank >= world || (slot != 0 && slot != 1))
+        return fail(VQ_ERR_ARG, "bad world / rank / slot for vq_backward_sharded");
+    for (int r = 0; r < world; ++r)
+        if (!peer_bufs[r]) return fail(VQ_ERR_ARG, "peer_bufs[%d] is NULL", r);
+    if (!cb || !grad_weight || !grad_z || !saved_zn || !saved_denom || !idx || n_elem_total <= 0)
+        return fail(VQ_ERR_ARG, "bad argument to vq_backward_sharded");
+    vq::CodebookView cbv = vq::codebook_view(const_cast<void*>(cb), K, D);
+    const float c1 = (form == VQ_FORM_VIT) ? beta : 1.f, c2 = (form == VQ_FORM_VIT) ? 1.f : beta;
+    const float coef1 = (float)((double)c1 * 2.0 / (double)n_elem_total), coef2 = (float)((double)c2 * 2.0 / (double)n_elem_total);
+    vq::TokenBackward tok{g_zq, saved_zn, saved_denom, idx, T, coef1, grad_z};
+    SlotTimer timer(static_cast<cudaStream_t>(stream), VQ_PROFILE_CODEBOOK_GRAD);
+    VQ_CUDA(vq::launch_codebook_grad_sharded(peer_bufs, world, rank, slot, epoch, cbv, coef2, g_loss, n_elem_total, form, beta,
+                                             grad_weight, hist_total, loss, stats_total, &tok, static_cast<cudaStream_t>(stream)));
     timer.stop();
     return VQ_OK;
 }

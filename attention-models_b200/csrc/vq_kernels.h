@@ -125,10 +125,14 @@ struct ExchangeLayout {
     size_t results_off, results_hist_off;      // grad_E (K*D fp32) and, results_hist_off behind it, the histogram (K int64)
 };
 ExchangeLayout exchange_layout(int K, int D);
+// token backward (token-major rows) to run in the same launch, behind the exchange's blocks; null: none
+struct TokenBackward {
+    const float* g_tok; const float* zn32; const float* denom; const int64_t* idx; int64_t T; float coef_commit; float* grad_tok;
+};
 cudaError_t launch_codebook_grad_sharded(const void* const* peer_bufs, int world, int rank, int slot, unsigned epoch,
                                          const CodebookView& cb, float coef, const float* g_loss, int64_t n_elem_total,
                                          int form, float beta, float* grad_weight, int64_t* hist_total, float* loss,
-                                         int64_t* stats_total, cudaStream_t s);
+                                         int64_t* stats_total, const TokenBackward* tokens, cudaStream_t s);
 
 // dispatch on the supported codebook dims (powers of two in [16, 512])
 // Cell copies of the unit codes for the exact rescoring behind a tensor-core filter (CodebookView::en32c):

@@ -29,6 +29,7 @@
 
 #include "vq_common.cuh"
 #include "vq_kernels.h"
+#include "vq_backward_body.cuh"
 #include "../../include/vq_b200.h"
 
 namespace vq {
@@ -104,6 +105,11 @@ __device__ __forceinline__ void publish_flags(const PeerPtrs& peers, size_t flag
     }
 }
 
+// token backward riding in the same launch (blocks [exchange_blocks, grid)); rows == 0: none
+struct TokenBackwardArgs {
+    const float4* g; const float4* zn; const float* denom; const int64_t* idx; const float4* en4; int64_t T; float coef_commit;
+    float4* grad; int exchange_blocks;
+};
 template <int D>
 // Small footprint on purpose (256 threads, <= 64 registers): the kernel spends most of its life waiting for other
 // GPUs while the token backward shares the SMs with it; with 512 threads x ~100 registers it left room for one
@@ -118,8 +124,17 @@ __global__ void __launch_bounds__(VQ_PEER_THREADS, 1024 / VQ_PEER_THREADS) k_cod
                                                                const float* __restrict__ g_loss, int64_t n_elem_total,
                                                                int form, float beta, float* __restrict__ grad,
                                                                int64_t* __restrict__ hist_total, float* __restrict__ loss,
-                                                               int64_t* __restrict__ stats_total) {
+                                                               int64_t* __restrict__ stats_total, TokenBackwardArgs tb) {
+    if (tb.exchange_blocks > 0 && (int)blockIdx.x >= tb.exchange_blocks) {
+        // grad_z on the blocks behind the exchange's (which are scheduled first and so all resident): no second
+        // stream, no cross-stream events -- the token backward simply fills the SMs the exchange leaves idle
+        if constexpr (VQ_PEER_THREADS == 256)
+            backward_tokens_body<D>(tb.g, tb.zn, tb.denom, tb.idx, tb.en4, tb.T, tb.coef_commit, g_loss, tb.grad,
+                                    blockIdx.x - tb.exchange_blocks, gridDim.x - tb.exchange_blocks);
+        return;
+    }
     __shared__ int s_last;
+    const int xgrid = tb.exchange_blocks > 0 ? tb.exchange_blocks : (int)gridDim.x;     // blocks of the exchange proper
     const int lane = threadIdx.x & 31;
 #ifdef VQ_PEER_TRACE
     auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
@@ -152,7 +167,7 @@ __global__ void __launch_bounds__(VQ_PEER_THREADS, 1024 / VQ_PEER_THREADS) k_cod
     const int per_rank = local_out ? K : (K + world - 1) / world;
     const int k_lo = local_out ? 0 : min(K, rank * per_rank), k_hi = min(K, k_lo + per_rank);
     const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int n_warps = gridDim.x * (blockDim.x >> 5);
+    const int n_warps = xgrid * (blockDim.x >> 5);
     for (int k0 = k_lo + warp * kC; k0 < k_hi; k0 += n_warps * kC) {
         long long s[kC][kPer];
         int bad[kC];
@@ -232,7 +247,7 @@ __global__ void __launch_bounds__(VQ_PEER_THREADS, 1024 / VQ_PEER_THREADS) k_cod
     }
     if (hist_total)
         // (trailing blocks first: they have no codes of the slice when K / W < warps of the grid)
-        for (int k = k_lo + (gridDim.x - 1 - blockIdx.x) * blockDim.x + threadIdx.x; k < k_hi; k += gridDim.x * blockDim.x) {
+        for (int k = k_lo + (xgrid - 1 - blockIdx.x) * blockDim.x + threadIdx.x; k < k_hi; k += xgrid * blockDim.x) {
             int hv[VQ_PEER_MAX_RANKS];
 #pragma unroll
             for (int r = 0; r < VQ_PEER_MAX_RANKS; ++r)
@@ -247,7 +262,7 @@ __global__ void __launch_bounds__(VQ_PEER_THREADS, 1024 / VQ_PEER_THREADS) k_cod
         }
     // loss and summed statistics: 8 integers per rank, every rank adds them itself (the last warp of the last block,
     // so that no block's slice waits behind them)
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x >= blockDim.x - 32 && (stats_total || loss)) {
+    if (blockIdx.x == xgrid - 1 && threadIdx.x >= blockDim.x - 32 && (stats_total || loss)) {
         __shared__ long long tot[VQ_STATS_LEN];
         if (lane < VQ_STATS_LEN) {
             long long sv[VQ_PEER_MAX_RANKS];
@@ -279,7 +294,7 @@ __global__ void __launch_bounds__(VQ_PEER_THREADS, 1024 / VQ_PEER_THREADS) k_cod
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned* counter = reinterpret_cast<unsigned*>(own + kCounterOff);
-        s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+        s_last = (atomicAdd(counter, 1u) == xgrid - 1);
         if (s_last) *counter = 0;                        // ready for the next launch
     }
     __syncthreads();
@@ -296,15 +311,15 @@ __global__ void __launch_bounds__(VQ_PEER_THREADS, 1024 / VQ_PEER_THREADS) k_cod
     tr[3] = now();
 #endif
     const float4* res = reinterpret_cast<const float4*>(own + L.results_off);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * D / 4; i += gridDim.x * blockDim.x)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * D / 4; i += xgrid * blockDim.x)
         reinterpret_cast<float4*>(grad)[i] = __ldcg(res + i);
     if (hist_total) {
         const long long* rh = reinterpret_cast<const long long*>(own + L.results_off + L.results_hist_off);
-        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) hist_total[k] = __ldcg(rh + k);
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += xgrid * blockDim.x) hist_total[k] = __ldcg(rh + k);
     }
 #ifdef VQ_PEER_TRACE
     tr[4] = now();
-    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && epoch >= 10 && epoch < 14)
+    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == xgrid - 1) && epoch >= 10 && epoch < 14)
         printf("rank %d epoch %u block %d: start %llu ready-wait %llu ns, slice %llu ns, done-wait %llu ns, copy %llu ns\n", rank, epoch,
                blockIdx.x, tr[0] % 1000000000ull, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3]);
 #endif
@@ -313,7 +328,7 @@ __global__ void __launch_bounds__(VQ_PEER_THREADS, 1024 / VQ_PEER_THREADS) k_cod
 cudaError_t launch_codebook_grad_sharded(const void* const* peer_bufs, int world, int rank, int slot, unsigned epoch,
                                          const CodebookView& cb, float coef, const float* g_loss, int64_t n_elem_total,
                                          int form, float beta, float* grad_weight, int64_t* hist_total, float* loss,
-                                         int64_t* stats_total, cudaStream_t s) {
+                                         int64_t* stats_total, const TokenBackward* tokens, cudaStream_t s) {
     const ExchangeLayout L = exchange_layout(cb.K, cb.D);
     PeerPtrs p;
     for (int r = 0; r < VQ_PEER_MAX_RANKS; ++r) p.base[r] = r < world ? static_cast<const char*>(peer_bufs[r]) : nullptr;
@@ -324,6 +339,19 @@ cudaError_t launch_codebook_grad_sharded(const void* const* peer_bufs, int world
         blocks = (cb.K + 7) / 8;
         if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     }
+    TokenBackwardArgs tb = {};
+    int64_t tok_blocks = 0;
+    if (tokens && tokens->T > 0 && VQ_PEER_THREADS == 256) {
+        const int chunks = cb.D / 4;
+        const int lpr = chunks < 32 ? chunks : 32;
+        const int rows_per_block = 8 * (32 / lpr);
+        tok_blocks = (tokens->T + rows_per_block - 1) / rows_per_block;
+        const int64_t cap = (int64_t)sm_count() * 16;
+        if (tok_blocks > cap) tok_blocks = cap;
+        tb = TokenBackwardArgs{reinterpret_cast<const float4*>(tokens->g_tok), reinterpret_cast<const float4*>(tokens->zn32),
+                               tokens->denom, tokens->idx, reinterpret_cast<const float4*>(cb.en32), tokens->T,
+                               tokens->coef_commit, reinterpret_cast<float4*>(tokens->grad_tok), blocks};
+    }
     if (stats_total) {
         cudaError_t e = cudaMemsetAsync(stats_total + VQ_STAT_PEER_TIMEOUT, 0, sizeof(int64_t), s);
         if (e != cudaSuccess) return e;
@@ -332,9 +360,9 @@ cudaError_t launch_codebook_grad_sharded(const void* const* peer_bufs, int world
     // between 4 and 8 GPUs (VQ_EXCHANGE_ONE_SHOT=0/1 forces a mode)
     static const int forced = getenv("VQ_EXCHANGE_ONE_SHOT") ? atoi(getenv("VQ_EXCHANGE_ONE_SHOT")) : -1;
     const int one_shot = forced >= 0 ? forced : (world <= 4 ? 1 : 0);
-    VQ_DISPATCH_D(cb.D, (k_codebook_grad_sharded<kD><<<blocks, world == 1 ? 256 : VQ_PEER_THREADS, 0, s>>>(
+    VQ_DISPATCH_D(cb.D, (k_codebook_grad_sharded<kD><<<(unsigned)(blocks + tok_blocks), world == 1 ? 256 : VQ_PEER_THREADS, 0, s>>>(
                             p, world, rank, one_shot, L, slot, epoch, cb.en32, cb.code_denom, cb.K, coef, g_loss, n_elem_total, form, beta,
-                            grad_weight, hist_total, loss, stats_total)));
+                            grad_weight, hist_total, loss, stats_total, tb)));
     count_launch();
     return cudaGetLastError();
 }

@@ -56,6 +56,9 @@ SIGNATURES = {
     "vq_backward_codebook_sharded": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, ctypes.c_uint32, c_void_p, c_int, c_int,
                                              c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p]),
+    "vq_backward_sharded": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, ctypes.c_uint32, c_void_p, c_int64, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "vq_gather": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                           c_void_p, c_void_p]),
     "vq_profile_begin": (c_int, [c_int, ctypes.c_uint32]),

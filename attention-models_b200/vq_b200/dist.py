@@ -234,30 +234,33 @@ class ShardedQuantiser:
                                       _ptr(p["z_q"]), _ptr(p["idx"]), None, hist_ptr, stats_ptr,
                                       _ptr(p["zn"]), _ptr(p["denom"]), seg, _ptr(p["fws"]), p["fws_bytes"], s))
             if peer is not None:
-                # The exchange needs nothing of the backward, so the two run side by side.  The exchange (two flag round
-                # trips over NVLink, ~25 us) is the longer one and stays on the caller's stream -- no cross-stream hand-off
-                # on the critical path -- while the token backward (~18 us of HBM streaming) goes to the side stream.
-                side = p["side"]
+                # The exchange needs nothing of the backward, so the two run side by side: in one launch for token-major
+                # rows, else the exchange on the caller's stream and the token backward on a side stream.
                 tr = None
                 if self.trace is not None:
                     tr = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
                     self.trace.append(tr)
-                    p["ev_fwd"] = tr[1]
-                    p["ev_x"] = tr[3]
-                p["ev_fwd"].record()
-                _lib.check(lib.vq_backward_codebook_sharded(peer.ptr_array, peer.world, peer.rank, slot, epoch, cb, K, D,
-                                                            form_id, self.beta, None, n_total, _ptr(p["grad_w"]),
-                                                            _ptr(p["hist_total"]), _ptr(p["loss"]), _ptr(p["stats"]), s))
-                side.wait_event(p["ev_fwd"])
-                _lib.check(lib.vq_backward_tokens(_ptr(up), layout, T, hw, _ptr(p["zn"]), _ptr(p["denom"]), _ptr(p["idx"]),
-                                                  None, cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_z"]), None,
-                                                  _ptr(p["bws"]), p["bws_bytes"], side.cuda_stream))
+                    tr[1].record()
+                if layout == LAYOUT_TOKEN_MAJOR:
+                    # one launch: the exchange + codebook gradient on the first blocks, grad_z on the others
+                    _lib.check(lib.vq_backward_sharded(peer.ptr_array, peer.world, peer.rank, slot, epoch, _ptr(up), T,
+                                                       _ptr(p["zn"]), _ptr(p["denom"]), _ptr(p["idx"]), cb, K, D, form_id,
+                                                       self.beta, None, n_total, _ptr(p["grad_z"]), _ptr(p["grad_w"]),
+                                                       _ptr(p["hist_total"]), _ptr(p["loss"]), _ptr(p["stats"]), s))
+                else:
+                    side = p["side"]
+                    p["ev_fwd"].record()
+                    _lib.check(lib.vq_backward_codebook_sharded(peer.ptr_array, peer.world, peer.rank, slot, epoch, cb, K, D,
+                                                                form_id, self.beta, None, n_total, _ptr(p["grad_w"]),
+                                                                _ptr(p["hist_total"]), _ptr(p["loss"]), _ptr(p["stats"]), s))
+                    side.wait_event(p["ev_fwd"])
+                    _lib.check(lib.vq_backward_tokens(_ptr(up), layout, T, hw, _ptr(p["zn"]), _ptr(p["denom"]), _ptr(p["idx"]),
+                                                      None, cb, K, D, form_id, self.beta, None, n_total, _ptr(p["grad_z"]), None,
+                                                      _ptr(p["bws"]), p["bws_bytes"], side.cuda_stream))
+                    p["ev_x"].record(side)
+                    torch.cuda.current_stream(dev).wait_event(p["ev_x"])
                 if tr is not None:
-                    tr[2].record()
-                p["ev_x"].record(side)
-                torch.cuda.current_stream(dev).wait_event(p["ev_x"])
-                if tr is not None:
-                    tr[4].record()
+                    tr[2].record(); tr[3].record(); tr[4].record()
                 hist_out = p["hist_total"]
             elif self.world_size == 1:
                 # one launch: grad_z, grad_weight and the loss

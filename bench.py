@@ -298,9 +298,24 @@ def run_b200(args):
         e_ms = float(te.item())
         h2d = T * DIM * 4 * 2 + K_CODES * DIM * 4
         d2h = T * DIM * 4 * 2 + T * 8 + K_CODES * DIM * 4 + 4 + _lib.STATS_LEN * 8
+        # the floor of this path: the same bytes as plain pinned copies, both directions at once, no kernels
+        d_in, d_out = torch.empty(2 * T * DIM, device=dev), torch.empty(2 * T * DIM + 2 * T, device=dev)
+        h_in, h_out = torch.empty(2 * T * DIM).pin_memory(), torch.empty(2 * T * DIM + 2 * T).pin_memory()
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            with torch.cuda.stream(s_in):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        pcie_ms = (time.perf_counter() - t0) / 5 * 1e3
+        del d_in, d_out, h_in, h_out
         e2e = {"value": world * T / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": e_ms, "note": "vq_host_step: pinned host in/out, all outputs (z_q, idx, loss, grad_z, "
-                                            "grad_weight) copied back every step"}
+               "ms_per_step": e_ms, "pcie_floor_ms": pcie_ms, "frac_of_pcie_floor": pcie_ms / e_ms,
+               "note": "vq_host_step: pinned host in/out, all outputs (z_q, idx, loss, grad_z, grad_weight) copied back every "
+                       "step; pcie_floor_ms = the same bytes as plain pinned copies in both directions at once, no kernels"}
 
     if getattr(stepper, "trace", None):
         torch.cuda.synchronize()

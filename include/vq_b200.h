@@ -188,6 +188,15 @@ VQ_API int vq_backward_codebook_sharded(const void* const* peer_bufs, int world,
                                         int64_t n_elem_total, float* grad_weight, int64_t* hist_total, float* loss,
                                         int64_t* stats_total, void* stream);
 
+/* The whole backward of a token-sharded step (token-major rows) in ONE launch: the first blocks run the exchange +
+ * codebook gradient above, the others grad_z as vq_backward_tokens -- no second stream, no cross-stream events; the
+ * token backward fills the SMs the exchange leaves idle while it waits for the other GPUs.                        */
+VQ_API int vq_backward_sharded(const void* const* peer_bufs, int world, int rank, int slot, uint32_t epoch,
+                               const float* g_zq, int64_t T, const float* saved_zn, const float* saved_denom,
+                               const int64_t* idx, const void* cb, int K, int D, int form, float beta, const float* g_loss,
+                               int64_t n_elem_total, float* grad_z, float* grad_weight, int64_t* hist_total, float* loss,
+                               int64_t* stats_total, void* stream);
+
 /* ---- decode --------------------------------------------------------------------------------
  * Replaces Codebook.indices_to_embeddings: models/vitvqgan.py:173-176 (normalise=1, token-major)
  * and models/vqgan.py:178-182 (normalise=0, NCHW out with hw = n).  normalise=1 reads the unit

@@ -28,6 +28,9 @@ def _worker(rank, world, port, exchange, q):
         if p not in sys.path:
             sys.path.insert(0, p)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if exchange.startswith("peer-"):       # the library reads the mode once, when it is loaded (fresh process here)
+        os.environ["VQ_EXCHANGE_ONE_SHOT"] = "1" if exchange == "peer-one-shot" else "0"
+        exchange = "peer"
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -69,7 +72,7 @@ def _worker(rank, world, port, exchange, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("exchange", ["peer", "collective"])
+@pytest.mark.parametrize("exchange", ["peer-one-shot", "peer-two-shot", "collective"])
 def test_two_gpu_sharded_step_equals_single_gpu_on_global_batch(exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
