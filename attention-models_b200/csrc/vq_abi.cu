@@ -83,7 +83,7 @@ FwdWs carve_forward(void* ws, int64_t T, int K, int D) {
     w.row_sq = b.take<float>(n);
     w.zn16 = b.take<__half>(n * D);
     w.cand = b.take<int>(n);
-    w.flagged = b.take<int>(n);
+    w.flagged = b.take<int>(n * (size_t)vq::tc_flag_multiplier(T, K, D));
     w.n_flagged = b.take<int>(64 + vq::kFlaggedCap);   // [0]: count, [64..]: done counters of the sliced fallback
     w.stats = b.take<int64_t>(VQ_STATS_LEN);
     w.zq_tok = b.take<float>(n * D);
@@ -246,8 +246,8 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
         if (use_tc) {
             // filter -> exact rescoring (+ the undecided rows when they are few) -> tiled exhaustive scan of a long list
             VQ_CUDA(vq::launch_dist_tc(zn16, zn32, w.row_sq, cbv, T, w.cand, w.flagged, w.n_flagged, st, w.tc_ws, w.scan_ws, s));
-            VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, T, w.cand, st, w.scan_ws, s,
-                                          vq::kFewFlagged));
+            VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, T * vq::tc_flag_multiplier(T, K, D),
+                                          w.cand, st, w.scan_ws, s, vq::kFewFlagged));
         } else {
             VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, nullptr, nullptr, T, w.cand, st, nullptr, s));
         }

@@ -95,7 +95,7 @@ template <int KB>
 __global__ void __launch_bounds__(kThreads, 1)
 k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int T, int K,
           const int* __restrict__ cb_info, int4* __restrict__ records, int* __restrict__ cand,
-          int* __restrict__ flagged, int* __restrict__ n_flagged, int64_t* __restrict__ stats) {
+          int* __restrict__ flagged, int* __restrict__ n_flagged, int64_t* __restrict__ stats, int splits) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int D = KB * kKBlock;
     constexpr int AS = a_stages(KB);
@@ -119,9 +119,14 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_slot);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // A work item is (row tile, code split): with few row tiles (a 16 384-token encode is 64 of them for 148 SMs) the
+    // codebook is cut into `splits` ranges of whole groups and every range gets its own CTA, record and verdict.  A
+    // verdict taken against the split's own best score keeps a superset of what the global best would keep, so the
+    // union of the splits' surviving cells contains the winner whenever every split is decided.
     const int n_row_tiles = (T + kRowsPerCta - 1) / kRowsPerCta;
-    const int n_tiles = K / kTileN;
-    const int n_groups = n_tiles / kGroupTiles;
+    const int n_items = n_row_tiles * splits;
+    const int n_tiles = K / kTileN / splits;            // per item
+    const int n_groups = n_tiles / kGroupTiles;         // per item
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < BS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
@@ -150,7 +155,8 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             long long wait_acc[4] = {0, 0, 0, 0};
             const long long t_begin = clock64();
 #endif
-            for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int rt = item / splits, tile0 = (item % splits) * n_tiles;
                 const int as = it % AS;
                 VQ_TIMED_WAIT(0, a_empty(as), (((uint32_t)(it / AS)) & 1u) ^ 1u);
                 mbar_expect_tx(a_full(as), KB * kABlockBytes);
@@ -164,7 +170,7 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                         const int s = b_cnt % BS;
                         VQ_TIMED_WAIT(1, b_empty(s), ((b_cnt / BS) & 1u) ^ 1u);
                         mbar_expect_tx(b_full(s), kBStageBytes);
-                        tma_load_2d(smem_base + L.b + s * kBStageBytes, &tm_b, b_full(s), kb * kKBlock, n * kTileN);
+                        tma_load_2d(smem_base + L.b + s * kBStageBytes, &tm_b, b_full(s), kb * kKBlock, (tile0 + n) * kTileN);
                     }
                 }
             }
@@ -181,7 +187,7 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             long long wait_acc[4] = {0, 0, 0, 0};
             const long long t_begin = clock64();
 #endif
-            for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int as = it % AS;
                 VQ_TIMED_WAIT(0, a_full(as), ((uint32_t)(it / AS)) & 1u);
                 tc_fence_after();
@@ -244,7 +250,9 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             tmem_ld16(ta + 32, v + 32);
             tmem_ld16(ta + 48, v + 48);
         };
-        for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int rt = item / splits, split = item % splits;
+            const int group0 = split * n_groups;        // global id of the item's first group
             float slot[32];
             float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY, m4 = -INFINITY;
             int g1 = 0, g2 = 0, g3 = 0;
@@ -380,8 +388,9 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             // the verdict record of the row, for the exact rescoring kernel: {g1 | g2 << 16 (or -1: undecided), g3,
             // mask1, mask2} {mask3, -, -, -}
             if (in_range) {
-                records[2 * (int64_t)row] = make_int4(decided ? (g1 | (g2 << 16)) : -1, g3, (int)mask[0], (int)mask[1]);
-                records[2 * (int64_t)row + 1] = make_int4((int)mask[2], 0, 0, 0);
+                int4* rec = records + 2 * ((int64_t)split * T + row);
+                rec[0] = make_int4(decided ? ((group0 + g1) | ((group0 + g2) << 16)) : -1, group0 + g3, (int)mask[0], (int)mask[1]);
+                rec[1] = make_int4((int)mask[2], __float_as_int(m1), 0, 0);     // m1: the split's best approximate score
             }
             if (flag) cand[row] = -1;
             const uint32_t ballot = __ballot_sync(VQ_FULL, flag);
@@ -420,6 +429,7 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
 // so all paths return identical indices.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kRescoreThreads = 128;
+constexpr int kMaxSplits = 4;
 constexpr int kFlaggedSlices = 32;
 struct __align__(16) FlaggedPartial {
     unsigned long long best; float second; float pad;
@@ -452,7 +462,7 @@ __device__ __forceinline__ float cell_distance_g(const float4* __restrict__ en32
 template <int D>
 __global__ void __launch_bounds__(kRescoreThreads)
 k_rescore_g(const int4* __restrict__ rec, const float* __restrict__ zn32, const float* __restrict__ row_sq,
-            const float4* __restrict__ en32c, const float* __restrict__ csq_cell, int T, int K,
+            const float4* __restrict__ en32c, const float* __restrict__ csq_cell, int T, int K, int splits,
             const int* __restrict__ flagged, const int* __restrict__ n_flagged, FlaggedPartial* __restrict__ partial,
             int* __restrict__ done, int* __restrict__ cand, int64_t* __restrict__ stats) {
     constexpr int kChunks = D / 4;
@@ -466,9 +476,28 @@ k_rescore_g(const int4* __restrict__ rec, const float* __restrict__ zn32, const 
     const int groups = gridDim.x * (kRescoreThreads / 8);
     for (int row0 = (blockIdx.x * kRescoreThreads + threadIdx.x - lane) >> 3; row0 < T; row0 += groups) {
         const int row = row0 + grp;
-        int4 h0 = make_int4(-1, 0, 0, 0), h1 = make_int4(0, 0, 0, 0);
+        // the row's verdict records, one per code split (splits <= kMaxSplits); undecided in any split: not ours
+        int gs[3 * kMaxSplits];
+        uint32_t ms[3 * kMaxSplits];
+        float best_of[kMaxSplits], gmax = -INFINITY;
+        bool valid = row < T;
         float a_sq = 0.f;
-        if (row < T) { h0 = __ldg(rec + 2 * (int64_t)row); h1 = __ldg(rec + 2 * (int64_t)row + 1); a_sq = __ldg(row_sq + row); }
+        if (row < T) a_sq = __ldg(row_sq + row);
+#pragma unroll
+        for (int sp = 0; sp < kMaxSplits; ++sp) {
+            int4 h0 = make_int4(-1, 0, 0, 0), h1 = make_int4(0, 0, 0, 0);
+            if (sp < splits && row < T) {
+                h0 = __ldg(rec + 2 * ((int64_t)sp * T + row));
+                h1 = __ldg(rec + 2 * ((int64_t)sp * T + row) + 1);
+            }
+            if (sp < splits) valid = valid && (h0.x >= 0);
+            best_of[sp] = (sp < splits) ? __int_as_float(h1.y) : -INFINITY;
+            gmax = fmaxf(gmax, best_of[sp]);
+            gs[3 * sp] = h0.x & 0xFFFF; gs[3 * sp + 1] = (h0.x >> 16) & 0x7FFF; gs[3 * sp + 2] = h0.y;
+            ms[3 * sp] = (sp < splits) ? (uint32_t)h0.z : 0u;
+            ms[3 * sp + 1] = (sp < splits) ? (uint32_t)h0.w : 0u;
+            ms[3 * sp + 2] = (sp < splits) ? (uint32_t)h1.x : 0u;
+        }
         __syncwarp();
         // the warp's 4 rows are 4 * kChunks contiguous float4
 #pragma unroll
@@ -479,21 +508,28 @@ k_rescore_g(const int4* __restrict__ rec, const float* __restrict__ zn32, const 
         }
         __syncwarp();
         const float4* zs = s_z[warp][grp];
-        const bool valid = (row < T) && (h0.x >= 0);
-        const int gs[3] = {h0.x & 0xFFFF, (h0.x >> 16) & 0x7FFF, h0.y};
-        uint32_t ms[3] = {valid ? (uint32_t)h0.z : 0u, valid ? (uint32_t)h0.w : 0u, valid ? (uint32_t)h1.x : 0u};
-        const int n_cells = __popc(ms[0]) + __popc(ms[1]) + __popc(ms[2]);
+        // a split whose best approximate score is more than 2 eps below the best of all splits cannot hold the winner
+        int n_cells = 0;
+#pragma unroll
+        for (int i = 0; i < 3 * kMaxSplits; ++i) {
+            if (!valid || best_of[i / 3] < gmax - kTwoEps) ms[i] = 0u;
+            n_cells += __popc(ms[i]);
+        }
         const int n_iter = __reduce_max_sync(VQ_FULL, n_cells);
         Top2 top;
         top.init();
-        int a = 0;
 #pragma unroll 1
         for (int it = 0; it < n_iter; ++it) {
-            while (a < 3 && ms[a] == 0u) ++a;
-            if (a < 3) {
-                const int slot = __ffs(ms[a]) - 1;
-                ms[a] &= ms[a] - 1;
-                const int g = gs[a];
+            // first non-empty mask (static indexing keeps gs / ms in registers)
+            int g = -1, slot = 0;
+#pragma unroll
+            for (int i = 0; i < 3 * kMaxSplits; ++i)
+                if (g < 0 && ms[i] != 0u) {
+                    slot = __ffs(ms[i]) - 1;
+                    ms[i] &= ms[i] - 1;
+                    g = gs[i];
+                }
+            if (g >= 0) {
                 const int ci = g * 32 + slot;
                 const int code = g * kGroupCols + 64 * (m >> 1) + ((slot & 16) << 1) + (slot & 15) + 16 * (m & 1);
                 top.add(dist_key(cell_distance_g<D>(en32c, csq_cell, ci, m, zs, a_sq), code));
@@ -628,9 +664,23 @@ bool tc_supported(int64_t T, int K, int D) {
     return d_ok && K >= tc::kGroupCols && (K % tc::kGroupCols) == 0 && K / tc::kGroupCols <= 32767 && T >= 256;
 }
 
+// code splits of the generic filter: as many as keep (row tiles x splits) within one wave of CTAs
+static int tc_splits(int64_t T, int K) {
+    const int64_t n_row_tiles = (T + tc::kRowsPerCta - 1) / tc::kRowsPerCta;
+    const int n_groups = K / tc::kGroupCols;
+    int s = tc::kMaxSplits;
+    while (s > 1 && (n_groups % s != 0 || n_row_tiles * s > sm_count())) s >>= 1;
+    return s;
+}
+
+// a row can be listed once per split
+int tc_flag_multiplier(int64_t T, int K, int D) {
+    return (tc_supported(T, K, D) && !tc16_supported(T, K, D)) ? tc_splits(T, K) : 1;
+}
+
 size_t tc_workspace_bytes(int64_t T, int K, int D) {
     if (tc16_supported(T, K, D)) return tc16_workspace_bytes(T);
-    return tc_supported(T, K, D) ? (size_t)(T > 0 ? T : 1) * tc::kRecordBytes : 0;
+    return tc_supported(T, K, D) ? (size_t)(T > 0 ? T : 1) * tc::kRecordBytes * tc_splits(T, K) : 0;
 }
 
 template <int KB>
@@ -645,9 +695,11 @@ static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb
         configured = true;
     }
     const int n_row_tiles = (T + tc::kRowsPerCta - 1) / tc::kRowsPerCta;
-    const int grid = n_row_tiles < sm_count() ? n_row_tiles : sm_count();
+    const int splits = tc_splits(T, cb.K);
+    const int n_items = n_row_tiles * splits;
+    const int grid = n_items < sm_count() ? n_items : sm_count();
     tc::k_dist_tc<KB><<<grid, tc::kThreads, L.total + 1024, s>>>(ma, mb, T, cb.K, cb.info, static_cast<int4*>(records), cand,
-                                                                 flagged, n_flagged, stats);
+                                                                 flagged, n_flagged, stats, splits);
     count_launch();
     {
         constexpr int D = KB * tc::kKBlock;
@@ -657,7 +709,7 @@ static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb
         if (blocks > cap) blocks = cap;
         tc::k_rescore_g<D><<<(unsigned)blocks, tc::kRescoreThreads, 0, s>>>(static_cast<const int4*>(records), zn32, row_sq,
                                                                              reinterpret_cast<const float4*>(cb.en32c), cb.csq_cell, T,
-                                                                             cb.K, flagged, n_flagged,
+                                                                             cb.K, splits, flagged, n_flagged,
                                                                              static_cast<tc::FlaggedPartial*>(partial_ws),
                                                                              n_flagged + 64, cand, stats);
         count_launch();

@@ -83,6 +83,7 @@ cudaError_t launch_exact_finish16(const void* records, const float* zn32, const 
 // decide are appended to flagged[] (count in *n_flagged).
 bool tc_supported(int64_t T, int K, int D);
 size_t tc_workspace_bytes(int64_t T, int K, int D);
+int tc_flag_multiplier(int64_t T, int K, int D);   // entries the undecided-row list may need per token row
 // generic D: the filter launch is followed by k_rescore_g, which also searches the listed rows itself when there are at
 // most kFewFlagged of them (needs n_flagged[64 ..] zeroed: kFewFlagged done counters; partial_ws >= kFewFlagged * 512 B);
 // longer lists are for launch_scan_exact(..., min_rows = kFewFlagged)
