@@ -356,10 +356,12 @@ cudaError_t launch_codebook_grad_sharded(const void* const* peer_bufs, int world
         cudaError_t e = cudaMemsetAsync(stats_total + VQ_STAT_PEER_TIMEOUT, 0, sizeof(int64_t), s);
         if (e != cudaSuccess) return e;
     }
-    // one flag round trip and (W-1) x 2.2 MB of reads, or two round trips and 2 (W-1)/W x as much: measured break-even
-    // between 4 and 8 GPUs (VQ_EXCHANGE_ONE_SHOT=0/1 forces a mode)
+    // one flag round trip and (W-1) x 2.2 MB of reads (one-shot), or two round trips and 2 (W-1)/W x as much
+    // (two-shot).  Measured per step at 8192 x 32: 2 GPUs 266 us either way, 4 GPUs 289 us one-shot / 269 us
+    // two-shot -- the reads contend with the token backward that shares the launch -- so two-shot is the default;
+    // VQ_EXCHANGE_ONE_SHOT=1 selects the other.
     static const int forced = getenv("VQ_EXCHANGE_ONE_SHOT") ? atoi(getenv("VQ_EXCHANGE_ONE_SHOT")) : -1;
-    const int one_shot = forced >= 0 ? forced : (world <= 4 ? 1 : 0);
+    const int one_shot = forced >= 0 ? forced : 0;
     VQ_DISPATCH_D(cb.D, (k_codebook_grad_sharded<kD><<<(unsigned)(blocks + tok_blocks), world == 1 ? 256 : VQ_PEER_THREADS, 0, s>>>(
                             p, world, rank, one_shot, L, slot, epoch, cb.en32, cb.code_denom, cb.K, coef, g_loss, n_elem_total, form, beta,
                             grad_weight, hist_total, loss, stats_total, tb)));
