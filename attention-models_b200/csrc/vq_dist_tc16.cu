@@ -519,13 +519,15 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m = lane & 7;
     const float4* zn4 = reinterpret_cast<const float4*>(zn32);
-    unsigned ties = 0, multi = 0, bad = 0;
+    // per-thread counters share one register (a thread sees at most a few dozen rows): ties in bits 0-9, rows
+    // rescored over several cells in bits 10-19, non-finite loss partials above
+    unsigned counts = 0, bad = 0;
+    constexpr unsigned kTie = 1u, kMulti = 1u << 10;
     long long loss_fx = 0;
     // ---------------- phase A ----------------
     // A warp owns 4 rows per iteration.  Their unit rows (512 contiguous bytes) arrive with ONE coalesced 16-byte load
     // per lane and are staged in shared memory (the 8 lanes of a row then read them as broadcasts: 4 registers instead
-    // of 32 for the row); records and rows of the next iteration are prefetched while this one is rescored, so an
-    // iteration waits for two dependent round trips (cell codes, winner's code row) instead of four.
+    // of 32 for the row), in the same round trip as the row's record.
     // Finish: lane m owns chunk m of the row (one 16-byte access per lane for zn, the code row and z_q); for the
     // segment sums the differences are transposed through shared memory so that lane m adds elements m, m + 8, m + 16,
     // m + 24: every RED instruction of a group then covers 8 consecutive int64 (two whole 32-byte sectors; 4x fewer
@@ -550,15 +552,19 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
             n_sq = __ldg(row_sq + r);
         }
     };
-    if (row0 < T) fetch(row0);
+#ifndef VQ_EXACT_PREFETCH
+#define VQ_EXACT_PREFETCH 0     // 1: records / rows of the next iteration prefetched into registers -- measured 3 us slower
+#endif                          // (17 more live registers spill under the 64-register cap; the data sits in L2 anyway)
+    if (VQ_EXACT_PREFETCH && row0 < T) fetch(row0);
     for (; row0 < T; row0 += groups) {
         const int row = row0 + grp;
+        if (!VQ_EXACT_PREFETCH) fetch(row0);
         const int4 h0 = n0, h1 = n1, h2 = n2;
         const float a_sq = n_sq;
         __syncwarp();                                   // the previous iteration's reads of s_z are done
         s_z[warp][grp][m] = nz;
         __syncwarp();
-        if (row0 + groups < T) fetch(row0 + groups);
+        if (VQ_EXACT_PREFETCH && row0 + groups < T) fetch(row0 + groups);
         const float4* zs = s_z[warp][grp];
         const bool valid = (row < T) && (h0.x >= 0);
         auto u64 = [](int lo, int hi) { return (unsigned long long)(uint32_t)lo | ((unsigned long long)(uint32_t)hi << 32); };
@@ -596,8 +602,8 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
                 if (cand) cand[row] = code | kCandExactBit;
                 out.idx[row] = code;
                 if (out.hist) atomicAdd(out.hist + code, 1);
-                if (top.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) ++ties;
-                if (n_cells > 1) ++multi;
+                if (top.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) counts += kTie;
+                if (n_cells > 1) counts += kMulti;
             }
         }
         if (out.zq) {                                   // uniform
@@ -668,7 +674,7 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
                     if (cand) cand[row] = code | kCandExactBit;
                     out.idx[row] = code;
                     if (out.hist) atomicAdd(out.hist + code, 1);
-                    if (fin.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) ++ties;
+                    if (fin.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) counts += kTie;
                     if (out.zq)
                         finish_row_serial(zn4, reinterpret_cast<const float4*>(en32), out, K, row, code, loss_fx, bad);
                     done[i] = 0;                   // ready for the next call
@@ -678,8 +684,8 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
     }
     // ---------------- statistics ----------------
     if (stats) {
-        ties = __reduce_add_sync(VQ_FULL, ties);
-        multi = __reduce_add_sync(VQ_FULL, multi);
+        const unsigned ties = __reduce_add_sync(VQ_FULL, counts & 1023u);
+        const unsigned multi = __reduce_add_sync(VQ_FULL, (counts >> 10) & 1023u);
         bad = __reduce_add_sync(VQ_FULL, bad);
         unsigned long long lf = (unsigned long long)loss_fx;
 #pragma unroll
