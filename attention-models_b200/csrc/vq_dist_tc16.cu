@@ -595,29 +595,44 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
             const float os = __shfl_xor_sync(VQ_FULL, top.second, off);
             top.merge(ob, os);
         }
+        const int code = (int)(uint32_t)top.best;
+        // rows of the warp that chose the same code (collapsed codebooks): their histogram count and segment-sum terms
+        // are added once, by the first of them -- the L2 serialises reductions per address
+        const unsigned same = __match_any_sync(VQ_FULL, valid ? code : -1 - grp);
+        const bool lead = valid && ((__ffs(same) - 1) >> 3) == grp;
         if (valid) {
-            const int code = (int)(uint32_t)top.best;
             if (m == 0) {
                 const float bd = key_dist(top.best);
                 if (cand) cand[row] = code | kCandExactBit;
                 out.idx[row] = code;
-                if (out.hist) atomicAdd(out.hist + code, 1);
+                if (out.hist && lead) atomicAdd(out.hist + code, __popc(same & 0x01010101u));
                 if (top.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) counts += kTie;
                 if (n_cells > 1) counts += kMulti;
             }
         }
         if (out.zq) {                                   // uniform
-            const int code = (int)(uint32_t)top.best;
             float4 df = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) df = finish_chunk(zs[m], en4, out, row, code, m, loss_fx, bad);
             if (out.seg) {                              // uniform
                 s_df[warp][grp][m] = df;
                 __syncwarp();
-                if (valid) {
-                    const float* d = reinterpret_cast<const float*>(s_df[warp][grp]);
+                if (lead) {
+                    long long acc[4] = {0, 0, 0, 0};
                     unsigned poison = 0;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) seg_add(out.seg + (int64_t)code * kD + m + 8 * i, d[m + 8 * i], poison);
+                    for (int p = 0; p < 4; ++p)
+                        if ((same >> (8 * p)) & 1u) {       // group p chose this code too (its lane 0 is in `same`)
+                            const float* d = reinterpret_cast<const float*>(s_df[warp][p]);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float v = d[m + 8 * i];
+                                if (is_finite(v)) acc[i] += to_fixed(v, VQ_SEG_SHIFT);   // per term, as every other path
+                                else poison = 1;
+                            }
+                        }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        atomicAdd(out.seg + (int64_t)code * kD + m + 8 * i, (unsigned long long)acc[i]);
                     if (poison) atomicAdd(out.seg + (int64_t)K * kD + code, 1ull);
                 }
             }
