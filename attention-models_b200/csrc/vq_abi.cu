@@ -253,10 +253,15 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
         }
         timer.stop();
         SlotTimer finish_timer(s, VQ_PROFILE_EXACT_FINISH);
-        VQ_CUDA(vq::launch_finish(zn32, w.cand, cbv, T, zq_tok, idx, hist, seg_sums, st, s));
+        if (!indices_only && layout == VQ_LAYOUT_NCHW) {
+            VQ_CUDA(vq::launch_finish_nchw(zn32, w.cand, cbv, T, hw, z_q, idx, hist, seg_sums, st, s));
+            zq_tok = nullptr;      // written in place: no layout kernel behind
+        } else {
+            VQ_CUDA(vq::launch_finish(zn32, w.cand, cbv, T, zq_tok, idx, hist, seg_sums, st, s));
+        }
         finish_timer.stop();
     }
-    if (!indices_only && layout == VQ_LAYOUT_NCHW) VQ_CUDA(vq::launch_tok_to_nchw(zq_tok, T, hw, D, z_q, s));
+    if (!indices_only && layout == VQ_LAYOUT_NCHW && zq_tok) VQ_CUDA(vq::launch_tok_to_nchw(zq_tok, T, hw, D, z_q, s));
     if (loss && !indices_only) {
         if (n_elem_total <= 0) return fail(VQ_ERR_ARG, "n_elem_total must be positive");
         VQ_CUDA(vq::launch_loss_finalize(st, n_elem_total, form, beta, loss, s));
@@ -307,10 +312,8 @@ int vq_backward_tokens(const float* g_zq, int layout, int64_t T, int64_t hw, con
         if (layout == VQ_LAYOUT_TOKEN_MAJOR) {
             VQ_CUDA(vq::launch_backward_tokens(g_zq, saved_zn, saved_denom, idx, cbv, T, coef, g_loss, grad_z, s));
         } else {
-            if (g_zq) VQ_CUDA(vq::launch_nchw_to_tok(g_zq, T, hw, D, nullptr, g_tok, nullptr, s));
-            VQ_CUDA(vq::launch_backward_tokens(g_zq ? g_tok : nullptr, saved_zn, saved_denom, idx, cbv, T, coef,
-                                               g_loss, grad_tok, s));
-            VQ_CUDA(vq::launch_tok_to_nchw(grad_tok, T, hw, D, grad_z, s));
+            (void)g_tok; (void)grad_tok;
+            VQ_CUDA(vq::launch_backward_tokens_nchw(g_zq, saved_zn, saved_denom, idx, cbv, T, hw, coef, g_loss, grad_z, s));
         }
     }
     if (seg_sums) VQ_CUDA(vq::launch_segment_sums(saved_zn, idx, hist, cbv, T, seg_sums, seg_ws, seg_bytes, s));

@@ -89,6 +89,87 @@ cudaError_t launch_backward_tokens(const float* g_tok, const float* zn32, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// grad_z for the VQGAN form's (b, D, hw) tensors, without token-major staging: a block owns 32 consecutive tokens; the
+// upstream gradient tile is read coalesced along the pixels into shared memory, one warp per token row then computes
+// g_zn = G + coef (zn - q), the row dot product and grad_z = (g_zn - zn (zn . g_zn)) / max(||z||, eps) in place, and the
+// tile goes back out coalesced along the pixels.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) k_backward_tokens_nchw(const float* __restrict__ g, const float* __restrict__ zn,
+                                                              const float* __restrict__ denom,
+                                                              const int64_t* __restrict__ idx, const float* __restrict__ en,
+                                                              int64_t T, int64_t hw, float coef_base,
+                                                              const float* __restrict__ g_loss, float* __restrict__ grad) {
+    extern __shared__ float tile[];                   // [32][D + 1]
+    constexpr int kStride = D + 1;
+    const float coef = coef_base * (g_loss ? __ldg(g_loss) : 1.f);
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    {
+        const int64_t t = t0 + x;
+        if (t < T) {
+            const int64_t b = t / hw, pix = t % hw;
+            for (int c = y; c < D; c += 8) tile[x * kStride + c] = g ? __ldcs(g + (b * D + c) * hw + pix) : 0.f;
+        }
+    }
+    __syncthreads();
+    for (int tt = y; tt < 32; tt += 8) {
+        const int64_t t = t0 + tt;
+        if (t >= T) break;
+        const int64_t k = __ldg(idx + t);
+        const float inv = __fdiv_rn(1.f, __ldg(denom + t));
+        float a[(D + 31) / 32], gz[(D + 31) / 32];
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < (D + 31) / 32; ++j) {
+            const int c = x + 32 * j;
+            a[j] = 0.f; gz[j] = 0.f;
+            if (c < D) {
+                a[j] = __ldg(zn + t * D + c);
+                gz[j] = __fmaf_rn(coef, __fsub_rn(a[j], __ldg(en + k * D + c)), tile[tt * kStride + c]);
+                dot = __fmaf_rn(a[j], gz[j], dot);
+            }
+        }
+        dot = warp_sum(dot);
+#pragma unroll
+        for (int j = 0; j < (D + 31) / 32; ++j) {
+            const int c = x + 32 * j;
+            if (c < D) tile[tt * kStride + c] = __fmul_rn(__fmaf_rn(-a[j], dot, gz[j]), inv);
+        }
+    }
+    __syncthreads();
+    {
+        const int64_t t = t0 + x;
+        if (t < T) {
+            const int64_t b = t / hw, pix = t % hw;
+            for (int c = y; c < D; c += 8) __stcs(grad + (b * D + c) * hw + pix, tile[x * kStride + c]);
+        }
+    }
+}
+
+cudaError_t launch_backward_tokens_nchw(const float* g_nchw, const float* zn32, const float* denom, const int64_t* idx,
+                                        const CodebookView& cb, int64_t T, int64_t hw, float coef_commit, const float* g_loss,
+                                        float* grad_nchw, cudaStream_t s) {
+    if (T == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((T + 31) / 32);
+    const size_t smem = sizeof(float) * 32 * (size_t)(cb.D + 1);
+    cudaError_t e = cudaSuccess;
+    VQ_DISPATCH_D(cb.D, {
+        if (smem > 48 * 1024) {
+            static bool configured = false;
+            if (!configured) {
+                e = cudaFuncSetAttribute(k_backward_tokens_nchw<kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                configured = true;
+            }
+        }
+        if (e == cudaSuccess) k_backward_tokens_nchw<kD><<<blocks, 256, smem, s>>>(g_nchw, zn32, denom, idx, cb.en32, T, hw,
+                                                                                   coef_commit, g_loss, grad_nchw);
+    });
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // bucket tokens by code
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_count(const int64_t* __restrict__ idx, int64_t T, int* __restrict__ counts) {

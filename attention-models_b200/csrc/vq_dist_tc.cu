@@ -58,7 +58,7 @@ struct SmemLayout {
 };
 constexpr int kHandBytes = kRowsPerCta * 32;     // per row: {g1|g2<<16 or -1, g3, mask1, mask2} {mask3, -, -, -}
 __host__ __device__ constexpr int a_stages(int kb) { return kb <= 2 ? 2 : 1; }
-__host__ __device__ constexpr int b_stages(int kb) { return kb == 1 ? 8 : (kb <= 4 ? 4 : 2); }
+__host__ __device__ constexpr int b_stages(int kb) { return kb == 1 ? 8 : (kb <= 4 ? 4 : 2); }   // (4 at D = 256 fits but measured no faster)
 // slot-maxima snapshots of the best three groups: 3 areas x 256 rows x 32 slots; rows padded by 16 B (conflict-free
 // STS.128).  At D = 256 the A operand alone is 128 KB, so the snapshots are kept as fp16 (80-byte rows): the verdict
 // then compares against thr - kSnapSlack, which covers the rounding of the stored maxima (|score| <= 1).

@@ -114,6 +114,80 @@ __global__ void __launch_bounds__(256) k_finish(const float* __restrict__ zn, co
     }
 }
 
+// The same pass with z_q written straight into the reference's (b, D, h, w) output (models/vqgan.py:174): 32-token x
+// 32-channel tiles, reads coalesced along the channels, z_q transposed through shared memory and stored coalesced along
+// the pixels -- no token-major staging buffer and no separate layout kernel.  Segment-sum REDs cover 256 contiguous bytes.
+__global__ void __launch_bounds__(256) k_finish_nchw(const float* __restrict__ zn, const int* __restrict__ cand,
+                                                     const float* __restrict__ en, int64_t T, int64_t hw, int D, int K,
+                                                     float* __restrict__ zq_nchw, int64_t* __restrict__ idx_out,
+                                                     int32_t* __restrict__ hist, unsigned long long* __restrict__ seg,
+                                                     int64_t* __restrict__ stats) {
+    __shared__ float tile[32][33];
+    __shared__ unsigned long long red[8];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int c = c0 + x;
+    float df[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int tt = y + 8 * i;
+        const int64_t t = t0 + tt;
+        if (t < T && c < D) {
+            const int k = __ldg(cand + t) & (kCandExactBit - 1);
+            const float a = __ldcs(zn + t * D + c), q = __ldg(en + (int64_t)k * D + c);
+            df[i] = __fsub_rn(q, a);
+            tile[tt][x] = __fadd_rn(a, df[i]);
+            if (c == 0) {
+                idx_out[t] = k;
+                if (hist) atomicAdd(hist + k, 1);
+            }
+            if (seg) {
+                unsigned poison = 0;
+                seg_add(seg + (int64_t)k * D + c, df[i], poison);
+                if (poison) atomicAdd(seg + (int64_t)K * D + k, 1ull);
+            }
+        }
+    }
+    long long loss_fx = 0;
+    unsigned long long bad = 0;
+    const float p = (df[0] * df[0] + df[1] * df[1]) + (df[2] * df[2] + df[3] * df[3]);
+    if (is_finite(p)) loss_fx = to_fixed(p, VQ_LOSS_SHIFT);
+    else bad = 1;
+    __syncthreads();
+    {
+        const int64_t t = t0 + x;
+        if (t < T) {
+            const int64_t b = t / hw, pix = t % hw;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cc = c0 + y + 8 * i;
+                if (cc < D) __stcs(zq_nchw + (b * D + cc) * hw + pix, tile[x][y + 8 * i]);
+            }
+        }
+    }
+    if (stats) {
+        const unsigned long long s1 = block_sum_u64((unsigned long long)loss_fx, red);
+        __syncthreads();
+        const unsigned long long s2 = block_sum_u64(bad, red);
+        if (threadIdx.x == 0) {
+            if (s1) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_LOSS_FIXED), s1);
+            if (s2) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NONFINITE), s2);
+        }
+    }
+}
+
+cudaError_t launch_finish_nchw(const float* zn32, const int* cand, const CodebookView& cb, int64_t T, int64_t hw,
+                               float* zq_nchw, int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats,
+                               cudaStream_t s) {
+    if (T == 0) return cudaSuccess;
+    dim3 grid((unsigned)((T + 31) / 32), (unsigned)((cb.D + 31) / 32));
+    k_finish_nchw<<<grid, 256, 0, s>>>(zn32, cand, cb.en32, T, hw, cb.D, cb.K, zq_nchw, idx_out, hist,
+                                       reinterpret_cast<unsigned long long*>(seg_sums), stats);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_finish(const float* zn32, const int* cand, const CodebookView& cb, int64_t T, float* zq_tok,
                           int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats, cudaStream_t s) {
     if (T == 0) return cudaSuccess;

@@ -97,6 +97,10 @@ cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* r
 // zeroed here) also the codebook-gradient segment sums S_k += fixed(q_k - zn_t) as integer reductions.
 cudaError_t launch_finish(const float* zn32, const int* cand, const CodebookView& cb, int64_t T,
                           float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats, cudaStream_t s);
+// the same with z_q written straight into the (b, D, hw) output
+cudaError_t launch_finish_nchw(const float* zn32, const int* cand, const CodebookView& cb, int64_t T, int64_t hw,
+                               float* zq_nchw, int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats,
+                               cudaStream_t s);
 cudaError_t launch_loss_finalize(const int64_t* stats, int64_t n_elem_total, int form, float beta, float* loss,
                                  cudaStream_t s);
 cudaError_t launch_gather(const int64_t* idx, int64_t T, int64_t hw, const float* table, int K, int D,
@@ -112,6 +116,10 @@ cudaError_t launch_backward_fused(const float* g_tok, const float* zn32, const f
                                   const CodebookView& cb, int64_t T, float coef_commit, const float* g_loss, float* grad_tok,
                                   const int64_t* seg_sums, float coef_codebook, float* grad_weight, const int64_t* stats,
                                   int64_t n_elem_total, int form, float beta, float* loss, cudaStream_t s);
+// grad_z for the (b, D, hw) layout: upstream gradient read and grad_z written in place of the two layout kernels
+cudaError_t launch_backward_tokens_nchw(const float* g_nchw, const float* zn32, const float* denom, const int64_t* idx,
+                                        const CodebookView& cb, int64_t T, int64_t hw, float coef_commit, const float* g_loss,
+                                        float* grad_nchw, cudaStream_t s);
 cudaError_t launch_segment_sums(const float* zn32, const int64_t* idx, const int32_t* hist, const CodebookView& cb,
                                 int64_t T, int64_t* seg_sums, void* ws, size_t ws_bytes, cudaStream_t s);
 // grad_E from the segment sums; with `loss` also the loss from stats (the former k_loss_finalize launch)
