@@ -214,8 +214,8 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
     } else if (layout == VQ_LAYOUT_TOKEN_MAJOR) {
         VQ_CUDA(vq::launch_prep_tokens(z, T, D, zn32, w.row_sq, denom, zn16, zl, s));
     } else {
-        if (nz) VQ_CUDA(vq::launch_zero_ranges(zl, s));
-        VQ_CUDA(vq::launch_norm_nchw(z, T, hw, D, denom, s));
+        if (T == 0 && nz) VQ_CUDA(vq::launch_zero_ranges(zl, s));
+        VQ_CUDA(vq::launch_norm_nchw(z, T, hw, D, denom, zl, s));
         VQ_CUDA(vq::launch_nchw_to_tok(z, T, hw, D, denom, zn32, zn16, s));
         VQ_CUDA(vq::launch_row_sumsq(zn32, T, D, w.row_sq, s));
     }

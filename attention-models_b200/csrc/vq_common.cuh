@@ -156,7 +156,8 @@ __device__ __forceinline__ void seg_add(unsigned long long* __restrict__ slot, f
 // Buffers a forward zeroes before use (stats, histogram, segment sums, fallback-list counters), cleared by the
 // first kernel of the call instead of one memset node each.  Sizes in bytes, multiples of 4.
 __device__ __forceinline__ void zero_ranges(const ZeroList& zl, int vblock, int vgrid) {
-    const size_t tid = (size_t)vblock * blockDim.x + threadIdx.x, n_thr = (size_t)vgrid * blockDim.x;
+    const size_t per_block = (size_t)blockDim.x * blockDim.y;
+    const size_t tid = (size_t)vblock * per_block + threadIdx.y * blockDim.x + threadIdx.x, n_thr = (size_t)vgrid * per_block;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         if (!zl.ptr[i]) continue;

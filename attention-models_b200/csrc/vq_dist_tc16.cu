@@ -599,13 +599,14 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
         // rows of the warp that chose the same code (collapsed codebooks): their histogram count and segment-sum terms
         // are added once, by the first of them -- the L2 serialises reductions per address
         const unsigned same = __match_any_sync(VQ_FULL, valid ? code : -1 - grp);
-        const bool lead = valid && ((__ffs(same) - 1) >> 3) == grp;
+        const bool dup = __any_sync(VQ_FULL, __popc(same) > 8);        // uniform; false on all but collapsed usage
+        const bool lead = valid && (!dup || ((__ffs(same) - 1) >> 3) == grp);
         if (valid) {
             if (m == 0) {
                 const float bd = key_dist(top.best);
                 if (cand) cand[row] = code | kCandExactBit;
                 out.idx[row] = code;
-                if (out.hist && lead) atomicAdd(out.hist + code, __popc(same & 0x01010101u));
+                if (out.hist && lead) atomicAdd(out.hist + code, dup ? __popc(same & 0x01010101u) : 1);
                 if (top.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) counts += kTie;
                 if (n_cells > 1) counts += kMulti;
             }
@@ -616,7 +617,15 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
             if (out.seg) {                              // uniform
                 s_df[warp][grp][m] = df;
                 __syncwarp();
-                if (lead) {
+                if (!dup) {
+                    if (valid) {
+                        const float* d = reinterpret_cast<const float*>(s_df[warp][grp]);
+                        unsigned poison = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) seg_add(out.seg + (int64_t)code * kD + m + 8 * i, d[m + 8 * i], poison);
+                        if (poison) atomicAdd(out.seg + (int64_t)K * kD + code, 1ull);
+                    }
+                } else if (lead) {
                     long long acc[4] = {0, 0, 0, 0};
                     unsigned poison = 0;
 #pragma unroll

@@ -43,7 +43,7 @@ bool prep_fusable(int D);
 cudaError_t launch_prep_fused(const float* weight, const CodebookView& cb, const float* z, int64_t T, float* zn32, float* row_sq,
                               float* denom, __half* zn16, const ZeroList& zl, cudaStream_t s);
 // NCHW (b, D, hw): denominators in ATen's channel-strided order (schedule chosen from T, hw, D)
-cudaError_t launch_norm_nchw(const float* z, int64_t T, int64_t hw, int D, float* denom, cudaStream_t s);
+cudaError_t launch_norm_nchw(const float* z, int64_t T, int64_t hw, int D, float* denom, const ZeroList& zl, cudaStream_t s);
 // (b, D, hw) -> (T, D), optionally divided by denom[t]; optional fp16 copy
 cudaError_t launch_nchw_to_tok(const float* in, int64_t T, int64_t hw, int D, const float* denom,
                                float* out32, __half* out16, cudaStream_t s);

@@ -360,7 +360,8 @@ cudaError_t launch_row_sumsq(const float* zn32, int64_t T, int D, float* row_sq,
 // ---------------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(128) k_norm_nchw(const float* __restrict__ z, int64_t T, int64_t hw,
-                                                   float* __restrict__ denom) {
+                                                   float* __restrict__ denom, ZeroList zl) {
+    zero_ranges(zl, blockIdx.x, gridDim.x);           // first kernel of an NCHW forward: clears what the call accumulates into
     constexpr int kSplit = (D >= 64) ? 4 : 1;
     __shared__ float4 part[4][32];
     const int x = threadIdx.x, y = threadIdx.y;
@@ -418,7 +419,8 @@ __global__ void __launch_bounds__(128) k_norm_nchw(const float* __restrict__ z, 
 // stripes in turn (stripe y: accumulator i <- channels y + S*(i + 4m)) and folds them with the same
 // tree (offsets S/2 ... 1).  Only small or odd-shaped inputs come here, so simplicity wins.
 __global__ void __launch_bounds__(128) k_norm_nchw_generic(const float* __restrict__ z, int64_t T, int64_t hw, int D,
-                                                           int S, float* __restrict__ denom) {
+                                                           int S, float* __restrict__ denom, ZeroList zl) {
+    zero_ranges(zl, blockIdx.x, gridDim.x);
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     const int64_t b = t / hw, p = t % hw;
@@ -459,16 +461,16 @@ static int aten_strided_stripes(int64_t T, int64_t hw, int D) {
     return (D >= thresh) ? (int)bh : 1;
 }
 
-cudaError_t launch_norm_nchw(const float* z, int64_t T, int64_t hw, int D, float* denom, cudaStream_t s) {
+cudaError_t launch_norm_nchw(const float* z, int64_t T, int64_t hw, int D, float* denom, const ZeroList& zl, cudaStream_t s) {
     if (T == 0) return cudaSuccess;
     const int S = aten_strided_stripes(T, hw, D);
     const bool fast = (hw % 4 == 0) && ((D >= 64 && S == 4) || (D < 64 && S == 1));
     if (fast) {
         const int64_t blocks = (T / 4 + 31) / 32;
-        VQ_DISPATCH_D(D, (k_norm_nchw<kD><<<(unsigned)blocks, dim3(32, 4), 0, s>>>(z, T, hw, denom)));
+        VQ_DISPATCH_D(D, (k_norm_nchw<kD><<<(unsigned)blocks, dim3(32, 4), 0, s>>>(z, T, hw, denom, zl)));
     } else {
         if (S > 128) return cudaErrorInvalidValue;
-        k_norm_nchw_generic<<<(unsigned)((T + 127) / 128), 128, 0, s>>>(z, T, hw, D, S, denom);
+        k_norm_nchw_generic<<<(unsigned)((T + 127) / 128), 128, 0, s>>>(z, T, hw, D, S, denom, zl);
     }
     count_launch();
     return cudaGetLastError();

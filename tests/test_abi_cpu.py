@@ -112,3 +112,42 @@ def test_module_surface_matches_reference():
     q = Vqgan(64, 32)
     assert float(q.embedding.weight.abs().max()) <= 1.0 / 64          # uniform_(-1/K, 1/K), vqgan.py:146
     assert hasattr(m, "indices_to_embeddings") and hasattr(m, "forward")
+
+
+def test_exchange_layout_queries_and_argument_errors(lib):
+    """Host-side logic of the token-sharded entry points: sizes, slot pointers, argument checks (no device needed)."""
+    cdll = lib.load()
+    K, D = 8192, 32
+    n = lib.size_query("vq_exchange_bytes", K, D)
+    seg_bytes = (K * D + K) * 8
+    assert n >= 2 * (seg_bytes + K * 4 + 64) + K * D * 4 + K * 8          # two slots + results + control
+    base = 1 << 20                                                         # any aligned fake address: only arithmetic happens
+    ptrs = []
+    for slot in (0, 1):
+        seg, st, hist = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        assert cdll.vq_exchange_slot(base, K, D, slot, ctypes.byref(seg), ctypes.byref(st), ctypes.byref(hist)) == 0
+        assert base < seg.value < st.value < hist.value < base + n
+        assert st.value - seg.value >= seg_bytes and seg.value % 256 == 0
+        ptrs.append(seg.value)
+    assert ptrs[1] - ptrs[0] >= seg_bytes + K * 4 + 64
+    assert cdll.vq_exchange_slot(base, K, D, 2, None, None, None) != 0      # slot out of range
+    one = (ctypes.c_void_p * 1)(base)
+    # world / rank / slot validation happens before anything touches the device
+    assert cdll.vq_backward_codebook_sharded(one, 0, 0, 0, 1, base, K, D, 0, 0.25, None, K * D, base, None, None, None, None) != 0
+    assert cdll.vq_backward_codebook_sharded(one, 1, 1, 0, 1, base, K, D, 0, 0.25, None, K * D, base, None, None, None, None) != 0
+    assert cdll.vq_backward_codebook_sharded(one, 17, 0, 0, 1, base, K, D, 0, 0.25, None, K * D, base, None, None, None, None) != 0
+    assert b"world" in cdll.vq_last_error()
+    assert cdll.vq_backward_sharded(one, 1, 0, 3, 1, None, 1024, base, base, base, base, K, D, 0, 0.25, None, 1024 * D, base, base,
+                                    None, None, None, None) != 0
+    # the one-GPU fused backward needs the forward's segment sums
+    assert cdll.vq_backward(None, 0, 1024, 0, base, base, base, base, K, D, 0, 0.25, None, 1024 * D, None, None, base, base, None,
+                            base, 1 << 20, None) != 0
+    assert b"seg_sums" in cdll.vq_last_error()
+    assert lib.PEER_MAX_RANKS == 16 and lib.IPC_HANDLE_BYTES == 64
+
+
+def test_workspace_grows_with_code_splits(lib):
+    """Few row tiles: the generic filter cuts the codebook into ranges, one record per (row, range)."""
+    small = lib.size_query("vq_workspace_bytes", 16384, 8192, 256, 0)      # 64 row tiles -> 2 ranges
+    large = lib.size_query("vq_workspace_bytes", 16384 * 64, 8192, 256, 0)
+    assert small / 16384 > large / (16384 * 64)                            # more record bytes per row when split
