@@ -56,7 +56,6 @@ constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint
 struct SmemLayout {
     uint32_t a, b, snap, hand, bars, tmem_slot, total;
 };
-constexpr int kHandBytes = kRowsPerCta * 32;     // per row: {g1|g2<<16 or -1, g3, mask1, mask2} {mask3, -, -, -}
 __host__ __device__ constexpr int a_stages(int kb) { return kb <= 2 ? 2 : 1; }
 __host__ __device__ constexpr int b_stages(int kb) { return kb == 1 ? 8 : (kb <= 4 ? 4 : 2); }   // (4 at D = 256 fits but measured no faster)
 // slot-maxima snapshots of the best three groups: 3 areas x 256 rows x 32 slots; rows padded by 16 B (conflict-free
@@ -442,7 +441,11 @@ __device__ __forceinline__ float cell_distance_g(const float4* __restrict__ en32
     const float4* e4 = en32c + (int64_t)ci * kChunks * 8 + m;
     const float csq = __ldg(csq_cell + ci * 8 + m);
     float dot = 0.f;
-#pragma unroll 1
+#ifndef VQ_RESCORE_UNROLL
+#define VQ_RESCORE_UNROLL 4   // 1: 64 us, 2: 60 us, 4: 50 us for the rescoring of a 16 384-token 8192 x 256 encode
+#endif
+    constexpr int kBatchUnroll = VQ_RESCORE_UNROLL;    // batches of 8 chunks the compiler may overlap
+#pragma unroll kBatchUnroll
     for (int q0 = 0; q0 < kChunks; q0 += 8) {
         float4 ev[8];
 #pragma unroll
@@ -459,7 +462,7 @@ __device__ __forceinline__ float cell_distance_g(const float4* __restrict__ en32
     return ref_distance(a_sq, csq, dot);
 }
 
-template <int D>
+template <int D, int kS>      // kS: code splits the records may come from (1, or kMaxSplits)
 __global__ void __launch_bounds__(kRescoreThreads)
 k_rescore_g(const int4* __restrict__ rec, const float* __restrict__ zn32, const float* __restrict__ row_sq,
             const float4* __restrict__ en32c, const float* __restrict__ csq_cell, int T, int K, int splits,
@@ -477,14 +480,14 @@ k_rescore_g(const int4* __restrict__ rec, const float* __restrict__ zn32, const 
     for (int row0 = (blockIdx.x * kRescoreThreads + threadIdx.x - lane) >> 3; row0 < T; row0 += groups) {
         const int row = row0 + grp;
         // the row's verdict records, one per code split (splits <= kMaxSplits); undecided in any split: not ours
-        int gs[3 * kMaxSplits];
-        uint32_t ms[3 * kMaxSplits];
-        float best_of[kMaxSplits], gmax = -INFINITY;
+        int gs[3 * kS];
+        uint32_t ms[3 * kS];
+        float best_of[kS], gmax = -INFINITY;
         bool valid = row < T;
         float a_sq = 0.f;
         if (row < T) a_sq = __ldg(row_sq + row);
 #pragma unroll
-        for (int sp = 0; sp < kMaxSplits; ++sp) {
+        for (int sp = 0; sp < kS; ++sp) {
             int4 h0 = make_int4(-1, 0, 0, 0), h1 = make_int4(0, 0, 0, 0);
             if (sp < splits && row < T) {
                 h0 = __ldg(rec + 2 * ((int64_t)sp * T + row));
@@ -511,7 +514,7 @@ k_rescore_g(const int4* __restrict__ rec, const float* __restrict__ zn32, const 
         // a split whose best approximate score is more than 2 eps below the best of all splits cannot hold the winner
         int n_cells = 0;
 #pragma unroll
-        for (int i = 0; i < 3 * kMaxSplits; ++i) {
+        for (int i = 0; i < 3 * kS; ++i) {
             if (!valid || best_of[i / 3] < gmax - kTwoEps) ms[i] = 0u;
             n_cells += __popc(ms[i]);
         }
@@ -523,7 +526,7 @@ k_rescore_g(const int4* __restrict__ rec, const float* __restrict__ zn32, const 
             // first non-empty mask (static indexing keeps gs / ms in registers)
             int g = -1, slot = 0;
 #pragma unroll
-            for (int i = 0; i < 3 * kMaxSplits; ++i)
+            for (int i = 0; i < 3 * kS; ++i)
                 if (g < 0 && ms[i] != 0u) {
                     slot = __ffs(ms[i]) - 1;
                     ms[i] &= ms[i] - 1;
@@ -707,11 +710,14 @@ static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb
         int64_t blocks = ((int64_t)T + rows_per_block - 1) / rows_per_block;
         const int64_t cap = (int64_t)sm_count() * 16 * 2;
         if (blocks > cap) blocks = cap;
-        tc::k_rescore_g<D><<<(unsigned)blocks, tc::kRescoreThreads, 0, s>>>(static_cast<const int4*>(records), zn32, row_sq,
-                                                                             reinterpret_cast<const float4*>(cb.en32c), cb.csq_cell, T,
-                                                                             cb.K, splits, flagged, n_flagged,
-                                                                             static_cast<tc::FlaggedPartial*>(partial_ws),
-                                                                             n_flagged + 64, cand, stats);
+        if (splits == 1)
+            tc::k_rescore_g<D, 1><<<(unsigned)blocks, tc::kRescoreThreads, 0, s>>>(
+                static_cast<const int4*>(records), zn32, row_sq, reinterpret_cast<const float4*>(cb.en32c), cb.csq_cell, T, cb.K,
+                splits, flagged, n_flagged, static_cast<tc::FlaggedPartial*>(partial_ws), n_flagged + 64, cand, stats);
+        else
+            tc::k_rescore_g<D, tc::kMaxSplits><<<(unsigned)blocks, tc::kRescoreThreads, 0, s>>>(
+                static_cast<const int4*>(records), zn32, row_sq, reinterpret_cast<const float4*>(cb.en32c), cb.csq_cell, T, cb.K,
+                splits, flagged, n_flagged, static_cast<tc::FlaggedPartial*>(partial_ws), n_flagged + 64, cand, stats);
         count_launch();
     }
 #ifdef VQ_TC_INSTRUMENT

@@ -104,7 +104,14 @@ class PeerExchange:
                     self.ptrs.append(own.value)
                 else:
                     p = ctypes.c_void_p()
-                    _lib.check(lib.vq_peer_open(ctypes.create_string_buffer(handles[r], _lib.IPC_HANDLE_BYTES), ctypes.byref(p)))
+                    try:
+                        _lib.check(lib.vq_peer_open(ctypes.create_string_buffer(handles[r], _lib.IPC_HANDLE_BYTES),
+                                                    ctypes.byref(p)))
+                    except _lib.VQLibraryError as exc:
+                        raise RuntimeError(
+                            f"rank {self.rank} cannot map rank {r}'s exchange buffer ({exc}). The peer exchange needs CUDA "
+                            "IPC and NVLink / PCIe peer access between all ranks of the group (one box); pass "
+                            "exchange='collective' to use one NCCL all-reduce instead") from exc
                     self.ptrs.append(p.value)
         self.ptr_array = (ctypes.c_void_p * self.world)(*self.ptrs)
         self._slots = [self._slot_pointers(s) for s in (0, 1)]

@@ -61,7 +61,8 @@ extern "C" {
 /* slots of the int64 `stats` array written by vq_forward (device memory, VQ_STATS_LEN entries) */
 #define VQ_STAT_NEAR_TIE_ROWS   0 /* rows whose two best fp32 distances differ by < 1e-6 relative */
 #define VQ_STAT_AMBIGUOUS_ROWS  1 /* rows the tensor-core pass could not decide alone (rescored over >1 cell) */
-#define VQ_STAT_FALLBACK_ROWS   2 /* rows sent to the exhaustive fp32 search                     */
+#define VQ_STAT_FALLBACK_ROWS   2 /* rows sent to the exhaustive fp32 search (a row the split filter
+                                     leaves undecided in two code ranges is counted twice)        */
 #define VQ_STAT_LOSS_FIXED      3 /* sum over tokens of sum_j (q - zn)^2, fixed point 2^-24      */
 #define VQ_STAT_BAD_INDEX       4 /* vq_gather: count of out-of-range indices                    */
 #define VQ_STAT_NONFINITE       5 /* non-finite loss partials (NaN/Inf rows): the loss is NaN     */
