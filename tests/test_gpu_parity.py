@@ -542,3 +542,30 @@ def test_sweep_points_tensor_core_search_equals_exhaustive(dev, T, K, D):
     rep = vo.classify_index_mismatches(a.reshape(-1)[:8 * 1024], ref.indices.reshape(-1), vo.unit_rows(z[:8].reshape(-1, D)),
                                        vo.unit_rows(w))
     assert rep["hard_rows"] == 0, rep
+
+
+@pytest.mark.parametrize("D", [32, 64, 256])
+@pytest.mark.parametrize("K", [256, 768, 1024, 8192])
+def test_boundary_token_counts_all_paths_agree(dev, K, D):
+    """Token counts around every dispatch boundary -- below the tensor-core minimum (256), ragged row tiles, the point
+    where the generic filter stops splitting the codebook (row tiles x splits > SMs), a little above kFlaggedCap -- :
+    the automatic path and the exhaustive fp32 search give identical indices, z_q and gradients (loss to 1e-6)."""
+    w = vo.make_codebook("vit", K, D, 90).to(dev)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    counts = [1, 31, 255, 256, 257, 1000, 4097, 256 * (sms // 4), 256 * (sms // 2) + 1, 256 * sms + 77]
+    for T in counts:
+        z = vo.make_latents((1, T, D), 91 + T % 7).to(dev)
+        up = vo.make_latents((1, T, D), 92).to(dev)
+        outs = []
+        for exact in (False, True):
+            m = _module("vit", K, D, 0.25, w, dev, exact)
+            zz = z.clone().requires_grad_(True)
+            z_q, idx, loss = m(zz)
+            ((z_q * up).sum() + loss).backward()
+            assert int(m.last_histogram.sum()) == T
+            outs.append((idx, z_q.detach(), loss.detach(), zz.grad, m.embedding.weight.grad))
+        for name, a, b in zip(("idx", "z_q", "loss", "grad_z", "grad_weight"), *outs):
+            if name == "loss":     # fixed-point partials are grouped differently by the two finish kernels
+                assert abs(float(a) - float(b)) <= 1e-6 * abs(float(b)), (T, K, D)
+            else:
+                assert torch.equal(a, b), (name, T, K, D)
