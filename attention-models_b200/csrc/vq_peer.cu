@@ -105,26 +105,24 @@ __device__ __forceinline__ void publish_flags(const PeerPtrs& peers, size_t flag
     }
 }
 
-// token backward riding in the same launch (blocks [exchange_blocks, grid)); rows == 0: none
+// token backward riding in the same launch (blocks [exchange_blocks, grid)); exchange_blocks == 0: none
 struct TokenBackwardArgs {
     const float4* g; const float4* zn; const float* denom; const int64_t* idx; const float4* en4; int64_t T; float coef_commit;
     float4* grad; int exchange_blocks;
 };
-template <int D>
 // Small footprint on purpose (256 threads, <= 64 registers): the kernel spends most of its life waiting for other
 // GPUs while the token backward shares the SMs with it; with 512 threads x ~100 registers it left room for one
 // backward block per SM and the two kernels ran back to back in effect.
 #ifndef VQ_PEER_THREADS
 #define VQ_PEER_THREADS 256
 #endif
-__global__ void __launch_bounds__(VQ_PEER_THREADS, 1024 / VQ_PEER_THREADS) k_codebook_grad_sharded(PeerPtrs peers, int world, int rank, int one_shot,
-                                                                  ExchangeLayout L, int slot,
-                                                               unsigned epoch, const float* __restrict__ en,
-                                                               const float* __restrict__ code_denom, int K, float coef_base,
-                                                               const float* __restrict__ g_loss, int64_t n_elem_total,
-                                                               int form, float beta, float* __restrict__ grad,
-                                                               int64_t* __restrict__ hist_total, float* __restrict__ loss,
-                                                               int64_t* __restrict__ stats_total, TokenBackwardArgs tb) {
+template <int D>
+__global__ void __launch_bounds__(VQ_PEER_THREADS, 1024 / VQ_PEER_THREADS)
+k_codebook_grad_sharded(PeerPtrs peers, int world, int rank, int one_shot, ExchangeLayout L, int slot, unsigned epoch,
+                        const float* __restrict__ en, const float* __restrict__ code_denom, int K, float coef_base,
+                        const float* __restrict__ g_loss, int64_t n_elem_total, int form, float beta, float* __restrict__ grad,
+                        int64_t* __restrict__ hist_total, float* __restrict__ loss, int64_t* __restrict__ stats_total,
+                        TokenBackwardArgs tb) {
     if (tb.exchange_blocks > 0 && (int)blockIdx.x >= tb.exchange_blocks) {
         // grad_z on the blocks behind the exchange's (which are scheduled first and so all resident): no second
         // stream, no cross-stream events -- the token backward simply fills the SMs the exchange leaves idle

@@ -231,8 +231,6 @@ class ShardedQuantiser:
         with torch.cuda.device(dev):
             s = _stream(dev)
             if peer is not None:
-                if self.trace is not None and self.trace:
-                    pass
                 slot, epoch, seg, stats_ptr, hist_ptr = peer.next_step()
             else:
                 seg, stats_ptr, hist_ptr = _ptr(buf), _ptr(p["stats"]), _ptr(p["hist"])   # seg sums head the packed buffer
