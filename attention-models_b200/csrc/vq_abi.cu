@@ -493,6 +493,22 @@ int slot_total(int slot, double* ms_total, int64_t* launches) {
 }
 }  // namespace
 
+int vq_token_embed(const int64_t* tokens, const uint8_t* mask, int64_t T, int64_t n_per_seq, int64_t mask_token_id,
+                   int64_t ignore_index, const float* table, int64_t vocab, int dim, const float* pos, float* embeds,
+                   int64_t* input_ids, int64_t* labels, int64_t* stats, void* stream) {
+    if (T < 0 || T >= (1ll << 40)) return fail(VQ_ERR_ARG, "token count %lld out of range", (long long)T);
+    if (!tokens && T > 0) return fail(VQ_ERR_ARG, "tokens is NULL");
+    if (embeds && (!table || vocab <= 0 || dim <= 0 || dim % 4 != 0))
+        return fail(VQ_ERR_ARG, "embeds needs a (vocab, dim) table with dim a multiple of 4 (dim=%d)", dim);
+    if (pos && n_per_seq <= 0) return fail(VQ_ERR_ARG, "pos needs n_per_seq > 0");
+    if (!embeds && !input_ids && !labels) return fail(VQ_ERR_ARG, "nothing to produce");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (stats) VQ_CUDA(cudaMemsetAsync(stats + VQ_STAT_BAD_INDEX, 0, sizeof(int64_t), s));
+    VQ_CUDA(vq::launch_token_embed(tokens, mask, T, n_per_seq > 0 ? n_per_seq : 1, mask_token_id, ignore_index, table, vocab, dim,
+                                   pos, embeds, input_ids, labels, stats, s));
+    return VQ_OK;
+}
+
 int vq_profile_begin(int sample_every, unsigned slot_mask) {
     for (auto& v : g_slot_events) {
         for (auto& p : v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }

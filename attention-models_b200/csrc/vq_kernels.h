@@ -127,6 +127,11 @@ cudaError_t launch_codebook_grad(const int64_t* seg_sums, const CodebookView& cb
                                  float* grad_weight, const int64_t* stats, int64_t n_elem_total, int form, float beta,
                                  float* loss, cudaStream_t s);
 
+// ---- vq_tokens.cu ---------------------------------------------------------------------------
+cudaError_t launch_token_embed(const int64_t* tokens, const uint8_t* mask, int64_t T, int64_t n_per_seq, int64_t mask_token_id,
+                               int64_t ignore_index, const float* table, int64_t V, int dim, const float* pos, float* embeds,
+                               int64_t* input_ids, int64_t* labels, int64_t* stats, cudaStream_t s);
+
 // ---- vq_peer.cu ------------------------------------------------------------------------------
 // byte layout of one rank's exchange buffer (see vq_peer.cu); offsets of stats / hist are relative to the slot
 struct ExchangeLayout {

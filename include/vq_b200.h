@@ -206,6 +206,19 @@ VQ_API int vq_backward_sharded(const void* const* peer_bufs, int world, int rank
 VQ_API int vq_gather(const int64_t* idx, int64_t T, int64_t hw, const float* weight, const void* cb,
               int K, int D, int normalise, int layout_out, float* out, int64_t* stats, void* stream);
 
+/* ---- first consumer of the tokens ------------------------------------------
+ * The mask-fill + token-embedding lookup the generative models do right behind encode_imgs, in one pass:
+ *   input_ids = tokens.masked_fill(mask, mask_token_id)        models/muse.py:149, models/maskgit.py:132
+ *   labels    = tokens.masked_fill(~mask, ignore_index)        models/muse.py:150, models/maskgit.py:131
+ *   embeds[t] = table[input_ids[t]] + pos[t mod n_per_seq]     models/muse.py:90-91, models/maskgit.py:80-81
+ * tokens: T int64; mask: T bytes (0 / non-zero) or NULL (nothing masked); table: (vocab, dim) fp32 with dim % 4 == 0;
+ * pos: (n_per_seq, dim) fp32 or NULL; embeds (T, dim), input_ids, labels: any may be NULL.  Forward only (inference /
+ * frozen embeddings).  Out-of-range ids are counted in stats[VQ_STAT_BAD_INDEX] and embed to 0.                     */
+VQ_API int vq_token_embed(const int64_t* tokens, const uint8_t* mask, int64_t T, int64_t n_per_seq,
+                          int64_t mask_token_id, int64_t ignore_index, const float* table, int64_t vocab, int dim,
+                          const float* pos, float* embeds, int64_t* input_ids, int64_t* labels, int64_t* stats,
+                          void* stream);
+
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------
  * Between vq_profile_begin() and vq_profile_end() the library counts all kernel launches and brackets the kernels
  * of every `sample_every`-th step (a vq_forward and the calls that follow it) with CUDA events on the caller's

@@ -83,6 +83,27 @@ def decode_case(name, form, K, D, b, n, w_seed, i_seed):
     print(name, tuple(e.shape))
 
 
+def token_embed_case(name, vocab, dim, b, n, seed):
+    """MaskGIT's token consumer on the reference's own modules: `fill_mask`'s two masked_fill lines
+    (/root/reference/models/maskgit.py:131-132) on a seeded mask, then `input_proj(x)`; `x += pos_enc`
+    (models/maskgit.py:80-81) of an unmodified BiDirectionalTransformer."""
+    from models.maskgit import BiDirectionalTransformer
+    g = torch.Generator().manual_seed(seed)
+    m = BiDirectionalTransformer(dim=dim, vocab_size=vocab, num_patches=n, n_heads=2, d_head=16, dec_depth=1)
+    with torch.no_grad():
+        m.input_proj.weight.copy_(torch.randn(vocab + 1, dim, generator=g))
+        m.pos_enc.copy_(0.02 * torch.randn(1, n, dim, generator=g))
+        tokens = torch.randint(0, vocab, (b, n), generator=g)
+        mask = torch.rand(b, n, generator=g) < 0.4
+        tgt = tokens.masked_fill(~mask, -1)                       # maskgit.py:131
+        x = tokens.masked_fill(mask, m.mask_token_id)             # maskgit.py:132
+        e = m.input_proj(x)                                       # maskgit.py:80
+        e += m.pos_enc                                            # maskgit.py:81
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), vocab=vocab, dim=dim, b=b, n=n, seed=seed,
+                        input_ids=x.numpy(), labels=tgt.numpy(), embeds=e.numpy())
+    print(name, "masked", int(mask.sum()), "of", b * n)
+
+
 def degenerate_rows(z, w):
     """zero row, NaN row, a row equal to a code, a zero code (SURVEY.md section 7 'Degenerate rows')."""
     z[0, 0] = 0.0
@@ -107,3 +128,5 @@ if __name__ == "__main__":
     decode_case("vqgan_decode", vo.VQGAN, 1024, 256, 2, 64, 31, 32)
     # edge rows
     forward_case("vit_degenerate_fwd", vo.VIT, 64, 32, (2, 8, 32), 40, 41, edit=degenerate_rows)
+    # first consumer of the tokens
+    token_embed_case("maskgit_token_embed", 512, 64, 3, 16, 50)

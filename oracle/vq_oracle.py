@@ -269,3 +269,31 @@ def make_trained_like(weight: torch.Tensor, tokens: int, seed: int, sigma: float
     en = unit_rows(weight)
     pick = torch.randint(0, weight.shape[0], (tokens,), generator=g)
     return en[pick] + sigma * torch.randn(tokens, weight.shape[1], generator=g)
+
+
+# ---------------------------------------------------------------------------------------------------
+# first consumer of the tokens
+# ---------------------------------------------------------------------------------------------------
+def token_embed_inputs(vocab: int, dim: int, b: int, n: int, seed: int):
+    """Seeded (table (vocab + 1, dim), pos_enc (1, n, dim), tokens (b, n), mask (b, n)) of the token-consumer fixture;
+    the same draws, in the same order, as oracle/make_golden.py::token_embed_case."""
+    g = torch.Generator().manual_seed(seed)
+    table = torch.randn(vocab + 1, dim, generator=g)
+    pos = 0.02 * torch.randn(1, n, dim, generator=g)
+    tokens = torch.randint(0, vocab, (b, n), generator=g)
+    mask = torch.rand(b, n, generator=g) < 0.4
+    return table, pos, tokens, mask
+
+
+def masked_token_embeddings(tokens: torch.Tensor, mask, mask_token_id: int, table: torch.Tensor, pos_enc=None,
+                            ignore_index: int = -1):
+    """/root/reference/models/muse.py:149-150 (= models/maskgit.py:131-132): the two masked_fill lines;
+    /root/reference/models/muse.py:90-91 (= models/maskgit.py:80-81): embedding lookup, ``+= pos_enc``."""
+    if mask is None:
+        mask = torch.zeros_like(tokens, dtype=torch.bool)
+    input_ids = tokens.masked_fill(mask, mask_token_id)
+    labels = tokens.masked_fill(~mask, ignore_index)
+    embeds = torch.nn.functional.embedding(input_ids, table)
+    if pos_enc is not None:
+        embeds = embeds + pos_enc
+    return embeds, input_ids, labels

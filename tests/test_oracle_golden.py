@@ -164,3 +164,14 @@ def test_near_tie_classifier():
     assert r == {"mismatch_rows": 1, "near_tie_rows": 0, "hard_rows": 1}
     assert torch.equal(vo.argmin_fp64(zn, en), idx)
     assert (vo.top2_relative_gap(zn, en) >= 0).all()
+
+
+def test_token_consumer_oracle_matches_reference_fixture():
+    """the masked-fill + embedding + pos_enc restatement against what the reference's own
+    BiDirectionalTransformer modules produced (tests/golden/maskgit_token_embed.npz)."""
+    g = load_golden("maskgit_token_embed")
+    vocab, dim, b, n, seed = (int(g[k]) for k in ("vocab", "dim", "b", "n", "seed"))
+    table, pos, tokens, mask = vo.token_embed_inputs(vocab, dim, b, n, seed)
+    embeds, ids, labels = vo.masked_token_embeddings(tokens, mask, vocab, table, pos, -1)
+    assert np.array_equal(ids.numpy(), g["input_ids"]) and np.array_equal(labels.numpy(), g["labels"])
+    assert np.array_equal(embeds.numpy(), g["embeds"])          # a gather and one fp32 add: bit-exact
