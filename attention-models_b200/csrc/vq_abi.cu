@@ -278,9 +278,8 @@ int vq_loss_finalize(const int64_t* stats, int64_t n_elem_total, int form, float
 int vq_backward_workspace_bytes(int64_t T, int K, int D, size_t* out) {
     if (!out) return fail(VQ_ERR_ARG, "out is NULL");
     if (int r = check_dims(T, K, D)) return r;
-    const size_t n = (size_t)(T > 0 ? T : 1);
-    // segment bucketing + two token-major staging buffers for the NCHW layout
-    *out = align_up(vq::backward_workspace_bytes(T, K, D), 256) + 2 * align_up(sizeof(float) * n * D, 256);
+    // segment bucketing only (the NCHW layout needs no token-major staging any more)
+    *out = align_up(vq::backward_workspace_bytes(T, K, D), 256);
     return VQ_OK;
 }
 
@@ -300,10 +299,6 @@ int vq_backward_tokens(const float* g_zq, int layout, int64_t T, int64_t hw, con
     char* p = static_cast<char*>(ws);
     void* seg_ws = p;
     const size_t seg_bytes = align_up(vq::backward_workspace_bytes(T, K, D), 256);
-    p += seg_bytes;
-    const size_t n = (size_t)(T > 0 ? T : 1);
-    float* g_tok = reinterpret_cast<float*>(p); p += align_up(sizeof(float) * n * D, 256);
-    float* grad_tok = reinterpret_cast<float*>(p);
 
     SlotTimer bwd_timer(s, VQ_PROFILE_BACKWARD_TOKENS);
     if (grad_z) {
@@ -312,7 +307,6 @@ int vq_backward_tokens(const float* g_zq, int layout, int64_t T, int64_t hw, con
         if (layout == VQ_LAYOUT_TOKEN_MAJOR) {
             VQ_CUDA(vq::launch_backward_tokens(g_zq, saved_zn, saved_denom, idx, cbv, T, coef, g_loss, grad_z, s));
         } else {
-            (void)g_tok; (void)grad_tok;
             VQ_CUDA(vq::launch_backward_tokens_nchw(g_zq, saved_zn, saved_denom, idx, cbv, T, hw, coef, g_loss, grad_z, s));
         }
     }
