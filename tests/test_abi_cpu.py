@@ -151,3 +151,34 @@ def test_workspace_grows_with_code_splits(lib):
     small = lib.size_query("vq_workspace_bytes", 16384, 8192, 256, 0)      # 64 row tiles -> 2 ranges
     large = lib.size_query("vq_workspace_bytes", 16384 * 64, 8192, 256, 0)
     assert small / 16384 > large / (16384 * 64)                            # more record bytes per row when split
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="the reference is only mounted in the build container")
+def test_patch_reference_model_swaps_the_quantiser_in_place():
+    """INTEGRATION.md route 1 on the unmodified reference classes: same attributes, same state_dict keys and weights,
+    and the swapped module refuses CPU tensors (there is no CPU path)."""
+    import importlib
+    import torch.nn as nn
+    sys.path.insert(0, "/root/reference")
+    sys.dont_write_bytecode = True
+    from vq_b200.integration import patch_reference_model
+    from vq_b200 import vitvqgan as b_vit, vqgan as b_vqgan
+    for mod_name, ours in (("models.vitvqgan", b_vit.Codebook), ("models.vqgan", b_vqgan.Codebook)):
+        ref_cls = importlib.import_module(mod_name).Codebook
+
+        class Holder(nn.Module):                     # stands in for VQGAN / ViTVQGAN: only `.codebook` matters here
+            def __init__(self):
+                super().__init__()
+                self.codebook = ref_cls(512, 32, 0.4)
+
+        model = Holder()
+        before = {k: v.clone() for k, v in model.state_dict().items()}
+        patch_reference_model(model)
+        assert type(model.codebook) is ours
+        assert (model.codebook.codebook_size, model.codebook.codebook_dim, model.codebook.beta) == (512, 32, 0.4)
+        after = model.state_dict()
+        assert list(after) == list(before) == ["codebook.embedding.weight"]
+        assert torch.equal(after["codebook.embedding.weight"], before["codebook.embedding.weight"])
+        z = torch.randn(1, 4, 32) if ours is b_vit.Codebook else torch.randn(1, 32, 2, 2)
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            model.codebook(z)
