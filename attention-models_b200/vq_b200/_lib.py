@@ -103,7 +103,16 @@ def check(status: int) -> None:
         raise VQLibraryError(f"libvq_b200 error {status}: {load().vq_last_error().decode(errors='replace')}")
 
 
+_size_cache = {}
+
+
 def size_query(fn_name: str, *args) -> int:
+    """Byte-size queries of the ABI (pure host arithmetic), memoised: they sit on the per-step path of the modules."""
+    key = (fn_name, args)
+    hit = _size_cache.get(key)
+    if hit is not None:
+        return hit
     out = c_size_t(0)
     check(getattr(load(), fn_name)(*args, ctypes.byref(out)))
-    return int(out.value)
+    _size_cache[key] = int(out.value)
+    return _size_cache[key]

@@ -43,8 +43,12 @@ class _CodebookBase(nn.Module):
         return self._prepared
 
     def _quantise(self, z: torch.Tensor):
+        # a stale prepared codebook of the right size is refilled by the forward itself (training: the weights changed)
+        w = self.embedding.weight
+        if self._prepared is None or not self._prepared.fits(w):
+            self._prepared = F_vq.prepare_codebook(w)
         z_q, flat_idx, loss, hist, stats = F_vq.quantise(z, self.embedding.weight, self.form, self.beta,
-                                                         prepared=self._prepared_codebook(),
+                                                         prepared=self._prepared,
                                                          exact_scan=self.exact_scan,
                                                          sorted_segments=self.sorted_segments)
         self.last_histogram, self.last_stats = hist, stats

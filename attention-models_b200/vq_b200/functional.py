@@ -49,6 +49,13 @@ class PreparedCodebook:
         return (self.weight_ptr == weight.data_ptr() and self.weight_version == weight._version
                 and self.blob.device == weight.device)
 
+    def fits(self, weight: torch.Tensor) -> bool:
+        """Same shape and device: the blob can be re-filled in place (by vq_forward itself, see quantise)."""
+        return self.blob.device == weight.device and tuple(weight.shape) == (self.K, self.D)
+
+    def mark_current(self, weight: torch.Tensor) -> None:
+        self.weight_ptr, self.weight_version = weight.data_ptr(), weight._version
+
 
 def prepare_codebook(weight: torch.Tensor) -> PreparedCodebook:
     """``l2_norm(embedding.weight)`` and ``sum(embedd_norm**2, 1)`` (reference vitvqgan.py:154,158)."""
@@ -79,7 +86,7 @@ class _Quantise(torch.autograd.Function):
     """(z, weight) -> (z_q, flat indices, loss, histogram, stats) with the straight-through backward."""
 
     @staticmethod
-    def forward(ctx, z, weight, prepared, form, beta, layout, flags, n_elem_total, sorted_segments):
+    def forward(ctx, z, weight, prepared, form, beta, layout, flags, n_elem_total, sorted_segments, refresh):
         lib = _lib.load()
         dev = z.device
         K, D = prepared.K, prepared.D
@@ -100,9 +107,15 @@ class _Quantise(torch.autograd.Function):
         ws_bytes = _lib.size_query("vq_workspace_bytes", T, K, D, flags)
         ws = _scratch(ws_bytes, dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.vq_forward(_ptr(z), layout, T, hw, None, _ptr(prepared.blob), K, D, form, float(beta), flags,
+            # refresh: the weights changed since `prepared` was filled -- the forward re-prepares the codebook itself
+            # (in the launch that normalises the token rows where the shape allows)
+            w_c = weight.detach().contiguous() if refresh else None      # kept alive until the launch is queued
+            w_ptr = _ptr(w_c)
+            _lib.check(lib.vq_forward(_ptr(z), layout, T, hw, w_ptr, _ptr(prepared.blob), K, D, form, float(beta), flags,
                                       n_total, _ptr(z_q), _ptr(idx), _ptr(loss), _ptr(hist), _ptr(stats),
                                       _ptr(saved_zn), _ptr(saved_denom), _ptr(seg), _ptr(ws), ws_bytes, _stream(dev)))
+        if refresh:
+            prepared.mark_current(weight)
         if need_grad:
             ctx.save_for_backward(saved_zn, saved_denom, idx, prepared.blob, hist)
         ctx.seg = seg
@@ -135,14 +148,14 @@ class _Quantise(torch.autograd.Function):
                 _lib.check(lib.vq_backward(_ptr(g_zq), layout, T, hw, _ptr(saved_zn), _ptr(saved_denom), _ptr(idx), _ptr(blob),
                                            K, D, form, beta, _ptr(g_loss), n_total, _ptr(seg), None, _ptr(grad_z), _ptr(grad_w),
                                            None, _ptr(ws), ws_bytes, s))
-                return grad_z, grad_w, None, None, None, None, None, None, None
+                return grad_z, grad_w, None, None, None, None, None, None, None, None
             _lib.check(lib.vq_backward_tokens(_ptr(g_zq), layout, T, hw, _ptr(saved_zn), _ptr(saved_denom), _ptr(idx),
                                               _ptr(hist), _ptr(blob), K, D, form, beta, _ptr(g_loss), n_total, _ptr(grad_z),
                                               None if from_forward or not want_w else _ptr(seg), _ptr(ws), ws_bytes, s))
             if want_w:
                 _lib.check(lib.vq_backward_codebook(_ptr(seg), _ptr(blob), K, D, form, beta, _ptr(g_loss), n_total,
                                                     _ptr(grad_w), None, None, s))
-        return grad_z, grad_w, None, None, None, None, None, None, None
+        return grad_z, grad_w, None, None, None, None, None, None, None, None
 
 
 def _as_fp32_input(z: torch.Tensor) -> torch.Tensor:
@@ -163,12 +176,15 @@ def quantise(z: torch.Tensor, weight: torch.Tensor, form: str = "vit", beta: flo
     """
     _require_cuda(z, "z")
     _require_cuda(weight, "the codebook weight")
-    if prepared is None or not prepared.matches(weight):
+    refresh = False
+    if prepared is None or not prepared.fits(weight):
         prepared = prepare_codebook(weight)
+    elif not prepared.matches(weight):
+        refresh = True                      # stale contents, right size: vq_forward refills the blob (no extra launch)
     layout = LAYOUT_TOKEN_MAJOR if form == "vit" else LAYOUT_NCHW
     flags = FLAG_EXACT_SCAN if exact_scan else 0
     return _Quantise.apply(_as_fp32_input(z), weight, prepared, FORMS[form], beta, layout, flags, n_elem_total,
-                           sorted_segments)
+                           sorted_segments, refresh)
 
 
 @torch.no_grad()
