@@ -51,6 +51,10 @@ struct SlotTimer {
     cudaStream_t s;
     int slot;
     SlotTimer(cudaStream_t stream, int which) : s(stream), slot(which) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (g_profiling && g_sampled && cudaStreamIsCapturing(stream, &cap) == cudaSuccess &&
+            cap != cudaStreamCaptureStatusNone)
+            return;                                    // events recorded into a graph cannot be read back: no hooks
         if (g_profiling && g_sampled && ((g_profile_mask >> which) & 1u) && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, s);
     }
     void stop() {
@@ -502,6 +506,8 @@ int vq_token_embed(const int64_t* tokens, const uint8_t* mask, int64_t T, int64_
                                    pos, embeds, input_ids, labels, stats, s));
     return VQ_OK;
 }
+
+int64_t vq_kernel_launches(void) { return (int64_t)vq::g_kernel_launches; }
 
 int vq_profile_begin(int sample_every, unsigned slot_mask) {
     for (auto& v : g_slot_events) {

@@ -37,6 +37,7 @@ namespace vq {
 namespace {
 constexpr size_t kFlagStride = 128;
 constexpr size_t kReadyOff = 0, kDoneOff = VQ_PEER_MAX_RANKS * kFlagStride, kCounterOff = 2 * VQ_PEER_MAX_RANKS * kFlagStride;
+constexpr size_t kStepOff = kCounterOff + 128;      // device-resident count of completed exchanges of this rank
 constexpr size_t kControlBytes = kCounterOff + 256;
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 }  // namespace
@@ -138,14 +139,21 @@ k_codebook_grad_sharded(PeerPtrs peers, int world, int rank, int one_shot, Excha
     auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
     unsigned long long tr[5] = {now(), 0, 0, 0, 0};
 #endif
-    const size_t slot_off = L.slot0_off + (size_t)slot * L.slot_bytes;
     char* own = const_cast<char*>(peers.base[rank]);
     bool timed_out = false;
+    // The step number lives on the device (the last block of a launch bumps it), so a launch carries no per-step host
+    // state and can sit in a CUDA graph; a host-side epoch, when given, must agree with it.
+    if (world > 1) {
+        const unsigned dev_epoch = *reinterpret_cast<volatile unsigned*>(own + kStepOff) + 1u;
+        if ((epoch != 0u && epoch != dev_epoch) || (int)((dev_epoch - 1u) & 1u) != slot) timed_out = true;   // out of step
+        epoch = dev_epoch;
+    }
+    const size_t slot_off = L.slot0_off + (size_t)slot * L.slot_bytes;
     // ---- 1. partials ready everywhere ----
     if (world > 1) {
         if (threadIdx.x < 32) {
             if (blockIdx.x == 0) publish_flags(peers, kReadyOff, world, rank, epoch);
-            timed_out = !wait_flags(own, kReadyOff, world, rank, epoch);
+            timed_out |= !wait_flags(own, kReadyOff, world, rank, epoch);
         }
         __syncthreads();
     }
@@ -280,6 +288,16 @@ k_codebook_grad_sharded(PeerPtrs peers, int world, int rank, int one_shot, Excha
     if (local_out) {
         if (timed_out && threadIdx.x == 0 && stats_total)
             atomicAdd(reinterpret_cast<unsigned long long*>(stats_total + VQ_STAT_PEER_TIMEOUT), 1ull);
+        if (world > 1) {                                 // the last block to get here closes the step
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned* counter = reinterpret_cast<unsigned*>(own + kCounterOff);
+                if (atomicAdd(counter, 1u) == (unsigned)xgrid - 1u) {
+                    *counter = 0;
+                    *reinterpret_cast<volatile unsigned*>(own + kStepOff) = epoch;
+                }
+            }
+        }
         return;
     }
     // ---- 3. slices complete everywhere, then results -> caller's tensors ----
@@ -293,7 +311,10 @@ k_codebook_grad_sharded(PeerPtrs peers, int world, int rank, int one_shot, Excha
     if (threadIdx.x == 0) {
         unsigned* counter = reinterpret_cast<unsigned*>(own + kCounterOff);
         s_last = (atomicAdd(counter, 1u) == xgrid - 1);
-        if (s_last) *counter = 0;                        // ready for the next launch
+        if (s_last) {
+            *counter = 0;                                // ready for the next launch
+            *reinterpret_cast<volatile unsigned*>(own + kStepOff) = epoch;   // every block has read the step number by now
+        }
     }
     __syncthreads();
     if (threadIdx.x < 32) {

@@ -63,6 +63,7 @@ SIGNATURES = {
                           c_void_p, c_void_p]),
     "vq_token_embed": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vq_kernel_launches": (c_int64, []),
     "vq_profile_begin": (c_int, [c_int, ctypes.c_uint32]),
     "vq_profile_end": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64), POINTER(c_int64)]),
     "vq_profile_slot": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(c_int64)]),

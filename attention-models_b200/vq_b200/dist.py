@@ -152,13 +152,20 @@ class ShardedQuantiser:
     """
 
     def __init__(self, form: str = "vit", beta: float = 0.25, world_size: Optional[int] = None,
-                 exact_scan: bool = False, group=None, exchange: str = "peer"):
+                 exact_scan: bool = False, group=None, exchange: str = "peer", graphs: bool = False):
         self.form, self.beta, self.group, self.exact_scan = form, float(beta), group, exact_scan
         if world_size is None:
             world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         if exchange not in ("peer", "collective"):
             raise ValueError("exchange must be 'peer' or 'collective'")
         self.world_size, self.exchange = world_size, exchange
+        # graphs: the launches of a step are captured once per (input buffers, weight buffer) in a CUDA graph and
+        # replayed afterwards (one graph launch instead of five kernel launches; the step is capture-safe: no
+        # allocation, no host synchronisation, device-side counters only).  `step(..., eager=True)` bypasses it.
+        self.graphs = graphs
+        self._graphs: Dict[tuple, tuple] = {}
+        self._warmed = set()
+        self.graph_kernel_launches = 0        # kernels run through graph replays (the library only counts eager launches)
         self._plans: Dict[tuple, Dict[str, object]] = {}
         import os
         self.trace = [] if os.environ.get("VQ_STEP_EVENTS") else None     # debugging: per-step CUDA events of the peer path
@@ -203,12 +210,66 @@ class ShardedQuantiser:
 
     def close(self) -> None:
         """Unmap / free the peer exchange buffers (collective: every rank must call it)."""
+        self._graphs.clear()
         for plan in self._plans.values():
             if "peer" in plan:
                 plan["peer"].close()
         self._plans.clear()
 
-    def step(self, z: torch.Tensor, upstream: Optional[torch.Tensor], weight: torch.Tensor) -> Dict[str, torch.Tensor]:
+    def step(self, z: torch.Tensor, upstream: Optional[torch.Tensor], weight: torch.Tensor,
+             eager: bool = False) -> Dict[str, torch.Tensor]:
+        if not self.graphs or eager or not self._graph_capable():
+            return self._step(z, upstream, weight)
+        z = z.contiguous()
+        upstream = None if upstream is None else upstream.contiguous()
+        key = (z.data_ptr(), tuple(z.shape), None if upstream is None else upstream.data_ptr(), weight.data_ptr(),
+               tuple(weight.shape), self._graph_phase(z, weight))
+        hit = self._graphs.get(key)
+        if hit is None:
+            if key not in self._warmed:                   # first use: a real eager step (allocations, kernel attributes)
+                self._warmed.add(key)
+                return self._step(z, upstream, weight)
+            torch.cuda.synchronize(z.device)
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.load().vq_kernel_launches()
+            with torch.cuda.graph(g):
+                out = self._step(z, upstream, weight)
+            n_kernels = _lib.load().vq_kernel_launches() - n0
+            self._graph_rewind(z, weight)                 # the capture advanced the host-side step count, nothing ran
+            hit = (g, out, (z, upstream, weight), n_kernels)   # the graph reads these buffers: keep them alive
+            self._graphs[key] = hit
+        hit[0].replay()
+        self.graph_kernel_launches += hit[3]
+        self._graph_advance(z, weight)
+        return hit[1]
+
+    # Graphs are offered where a step has no per-step host state in its kernel arguments: always on one GPU; with the
+    # peer exchange for token-major rows (one launch for the backward, step number on the device, two graphs per input
+    # buffer: one per exchange slot).  The NCCL exchange and the two-stream NCHW backward stay eager.
+    def _graph_capable(self) -> bool:
+        return self.world_size == 1 or (self.exchange == "peer" and self.form == "vit")
+
+    def _peer_of(self, z, weight) -> Optional[PeerExchange]:
+        for key, plan in self._plans.items():
+            if key[1] == tuple(z.shape) and key[2:4] == tuple(weight.shape) and "peer" in plan:
+                return plan["peer"]
+        return None
+
+    def _graph_phase(self, z, weight) -> int:
+        peer = self._peer_of(z, weight) if self.world_size > 1 else None
+        return 0 if peer is None else peer.epoch & 1
+
+    def _graph_rewind(self, z, weight) -> None:
+        peer = self._peer_of(z, weight) if self.world_size > 1 else None
+        if peer is not None:
+            peer.epoch -= 1
+
+    def _graph_advance(self, z, weight) -> None:
+        peer = self._peer_of(z, weight) if self.world_size > 1 else None
+        if peer is not None:
+            peer.epoch += 1
+
+    def _step(self, z: torch.Tensor, upstream: Optional[torch.Tensor], weight: torch.Tensor) -> Dict[str, torch.Tensor]:
         from .functional import FORMS, LAYOUT_NCHW, LAYOUT_TOKEN_MAJOR, _ptr, _require_cuda, _stream, _token_geometry
         _require_cuda(z, "z")
         lib = _lib.load()
@@ -248,7 +309,9 @@ class ShardedQuantiser:
                     tr[1].record()
                 if layout == LAYOUT_TOKEN_MAJOR:
                     # one launch: the exchange + codebook gradient on the first blocks, grad_z on the others
-                    _lib.check(lib.vq_backward_sharded(peer.ptr_array, peer.world, peer.rank, slot, epoch, _ptr(up), T,
+                    # (a captured launch carries no host-side step number: the kernel reads the device's)
+                    _lib.check(lib.vq_backward_sharded(peer.ptr_array, peer.world, peer.rank, slot,
+                                                       0 if torch.cuda.is_current_stream_capturing() else epoch, _ptr(up), T,
                                                        _ptr(p["zn"]), _ptr(p["denom"]), _ptr(p["idx"]), cb, K, D, form_id,
                                                        self.beta, None, n_total, _ptr(p["grad_z"]), _ptr(p["grad_w"]),
                                                        _ptr(p["hist_total"]), _ptr(p["loss"]), _ptr(p["stats"]), s))

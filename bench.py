@@ -188,31 +188,41 @@ def run_b200(args):
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     zs = [torch.randn(IMGS_PER_GPU, TOKENS_PER_IMG, DIM, device=dev, generator=g) for _ in range(n_sets)]
     ups = [torch.randn(IMGS_PER_GPU, TOKENS_PER_IMG, DIM, device=dev, generator=g) for _ in range(n_sets)]
-    stepper = vq_dist.ShardedQuantiser("vit", BETA, world_size=world, exact_scan=args.exact_scan, exchange=args.exchange)
+    stepper = vq_dist.ShardedQuantiser("vit", BETA, world_size=world, exact_scan=args.exact_scan, exchange=args.exchange,
+                                       graphs=not args.no_graphs)
 
-    def one_step(i):
-        z = zs[i % n_sets]
-        return stepper.step(z, ups[i % n_sets], weight)
+    counter = [0]                                     # steps so far: input sets rotate without a break between phases
+
+    def one_step(_unused=None, eager=False):
+        i = counter[0]
+        counter[0] += 1
+        return stepper.step(zs[i % n_sets], ups[i % n_sets], weight, eager=eager)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
+    # with graphs, every input set is seen twice before timing: one eager step, one capture
+    for i in range(max(args.warmup, 2 * n_sets if stepper.graphs else 0)):
         one_step(i)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # the step runs as a replayed CUDA graph; every profile_every-th step of the timed region runs eagerly instead, with
+    # CUDA-event pairs around the filter and exact/finish kernels (events cannot be read out of a graph replay)
     search_mask = (1 << _lib.PROFILE_SEARCH) | (1 << _lib.PROFILE_EXACT_FINISH)
-    _lib.check(lib.vq_profile_begin(args.profile_every, search_mask))
+    graphed = stepper.graphs and stepper._graph_capable()
+    _lib.check(lib.vq_profile_begin(1 if graphed else args.profile_every, search_mask))
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    replayed0 = stepper.graph_kernel_launches
     start.record()
     for i in range(args.steps):
-        out = one_step(args.warmup + i)
+        out = one_step(args.warmup + i, eager=graphed and (i % args.profile_every == 0))
     stop.record()
     barrier()
+    replayed_launches = stepper.graph_kernel_launches - replayed0      # kernels run by the graph replays of the timed region
     ms_total = start.elapsed_time(stop)
     search_ms, search_n, launches = ctypes.c_double(0), ctypes.c_int64(0), ctypes.c_int64(0)
     _lib.check(lib.vq_profile_end(ctypes.byref(search_ms), ctypes.byref(search_n), ctypes.byref(launches)))
@@ -238,7 +248,7 @@ def run_b200(args):
     # (torch.profiler: in-stream kernel durations without that idle time)
     _lib.check(lib.vq_profile_begin(1, 0))
     for i in range(5):
-        one_step(args.warmup + args.steps + i)
+        one_step(args.warmup + args.steps + i, eager=True)
     torch.cuda.synchronize()
     _lib.check(lib.vq_profile_end(None, None, None))
     slots.update(read_slots(["prep_codebook", "prep_tokens", "tail", "backward_tokens", "codebook_grad"]))
@@ -247,7 +257,7 @@ def run_b200(args):
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             for i in range(5):
-                one_step(args.warmup + args.steps + 5 + i)
+                one_step(args.warmup + args.steps + 5 + i, eager=True)
             torch.cuda.synchronize()
         acc = {}
         for e in prof.events():
@@ -407,10 +417,12 @@ def run_b200(args):
                                       + (f"; backward exchange: {'fused peer-memory kernel over NVLink (CUDA IPC)' if args.exchange == 'peer' else 'NCCL all-reduce of the packed int64 buffer'}" if world > 1 else ""),
                        "l2": f"inputs rotate over {n_sets} resident sets ({n_sets * 2 * T * DIM * 4 >> 20} MiB) > 126 MB L2; "
                              "a step's own working set is 130 MB"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.value),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.value) + int(replayed_launches),
             "roofline": roofline, "hbm_side": hbm, "kernel_ms_events": kernel_ms, "kernel_us_cupti": cupti_us,
             "profile_sampling": f"timed region: CUDA-event pairs around the filter and exact/finish kernels on every "
-                                f"{args.profile_every}th step; other kernels: separate 5-step pass",
+                                f"{args.profile_every}th step" + (" (those steps run eagerly, the others replay a CUDA graph "
+                                "of the same five launches)" if graphed else "") + "; other kernels: separate 5-step pass",
+            "cuda_graph": bool(graphed),
             "cpu_baseline": cpu,
             "parity": {"near_tie_rows_last_step": stats[_lib.STAT_NEAR_TIE_ROWS] if stats else None,
                        "fallback_rows_last_step": stats[_lib.STAT_FALLBACK_ROWS] if stats else None}}
@@ -429,8 +441,9 @@ def main():
     ap.add_argument("--exact-scan", action="store_true", help="force the exhaustive fp32 SIMT search")
     ap.add_argument("--exchange", default="peer", choices=["peer", "collective"],
                     help="N > 1: fused peer-memory exchange kernel (default) or one NCCL all-reduce")
-    ap.add_argument("--profile-every", type=int, default=4,
+    ap.add_argument("--profile-every", type=int, default=10,
                     help="bracket the kernels with CUDA events on every n-th timed step (event records cost ~2%% of a step)")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every step eagerly (no CUDA-graph replay)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()

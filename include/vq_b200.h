@@ -173,8 +173,11 @@ VQ_API int vq_backward(const float* g_zq, int layout, int64_t T, int64_t hw,
  * all ranks get bit-identical totals) and writes grad_weight (K*D), the global histogram (K int64, or
  * NULL), the global loss (or NULL) and the summed stats (VQ_STATS_LEN int64, or NULL).
  * peer_bufs: HOST array of `world` device pointers, peer_bufs[rank] the own buffer; world <=
- * VQ_PEER_MAX_RANKS.  `epoch` must increase by one per call (same value on all ranks, first call 1) and
- * `slot` = (epoch - 1) & 1.  n_elem_total is the GLOBAL element count.  world = 1 needs no peers.       */
+ * VQ_PEER_MAX_RANKS.  The step number lives in the exchange buffer (the kernel bumps it), so a launch carries no
+ * per-step host state and can be captured in a CUDA graph: `slot` must alternate 0, 1, 0, ... from the first
+ * call on; `epoch` is the caller's own count of the calls (1, 2, ...) for a consistency check, or 0 to skip it
+ * (graph capture).  A mismatch is reported like a peer time-out.  n_elem_total is the GLOBAL element count.
+ * world = 1 needs no peers.                                                                              */
 #define VQ_PEER_MAX_RANKS 16
 #define VQ_IPC_HANDLE_BYTES 64
 VQ_API int vq_exchange_bytes(int K, int D, size_t* out);
@@ -236,6 +239,9 @@ VQ_API int vq_token_embed(const int64_t* tokens, const uint8_t* mask, int64_t T,
 #define VQ_PROFILE_BACKWARD_TOKENS 5
 #define VQ_PROFILE_CODEBOOK_GRAD   6   /* incl. the fused peer exchange of a token-sharded job                      */
 #define VQ_PROFILE_SLOTS           7
+/* Kernels this library has launched so far in this process (a launch recorded into a CUDA graph counts once, at
+ * capture; its replays are the caller's to count).                                                    */
+VQ_API int64_t vq_kernel_launches(void);
 VQ_API int vq_profile_begin(int sample_every, unsigned slot_mask /* bit i = VQ_PROFILE_* slot i; 0 = all */);
 VQ_API int vq_profile_end(double* search_ms_total, int64_t* search_launches, int64_t* kernel_launches);
 VQ_API int vq_profile_slot(int slot, double* ms_total, int64_t* launches);

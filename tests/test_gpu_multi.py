@@ -28,6 +28,7 @@ def _worker(rank, world, port, exchange, q):
         if p not in sys.path:
             sys.path.insert(0, p)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    graphs = exchange == "peer-graphs"
     if exchange.startswith("peer-"):       # the library reads the mode once, when it is loaded (fresh process here)
         os.environ["VQ_EXCHANGE_ONE_SHOT"] = "1" if exchange == "peer-one-shot" else "0"
         exchange = "peer"
@@ -39,14 +40,18 @@ def _worker(rank, world, port, exchange, q):
         from vq_b200 import _lib
         from vq_b200 import dist as vq_dist
         w = vo.make_codebook("vit", K, D, 0).to(dev)
-        sharded = vq_dist.ShardedQuantiser("vit", BETA, world_size=world, exchange=exchange)
+        sharded = vq_dist.ShardedQuantiser("vit", BETA, world_size=world, exchange=exchange, graphs=graphs)
         single = vq_dist.ShardedQuantiser("vit", BETA, world_size=1)
         ok = True
         msgs = []
-        for step in range(4):          # both slots twice
+        zbuf = [torch.empty(B // world, N_TOK, D, device=dev) for _ in range(2)]       # fixed buffers: graphs replay on them
+        ubuf = [torch.empty(B // world, N_TOK, D, device=dev) for _ in range(2)]
+        for step in range(8 if graphs else 4):          # both slots twice (graphs: eager, capture, then replays)
             zg = vo.make_latents((B, N_TOK, D), 100 + step).to(dev)
             ug = vo.make_latents((B, N_TOK, D), 200 + step).to(dev)
-            out = sharded.step(vq_dist.shard_batch(zg, rank, world), vq_dist.shard_batch(ug, rank, world), w)
+            zbuf[step & 1].copy_(vq_dist.shard_batch(zg, rank, world))
+            ubuf[step & 1].copy_(vq_dist.shard_batch(ug, rank, world))
+            out = sharded.step(zbuf[step & 1], ubuf[step & 1], w)
             out = {k: v.clone() for k, v in out.items()}
             ref = single.step(zg, ug, w)
             per = B // world * N_TOK
@@ -72,7 +77,7 @@ def _worker(rank, world, port, exchange, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("exchange", ["peer-one-shot", "peer-two-shot", "collective"])
+@pytest.mark.parametrize("exchange", ["peer-one-shot", "peer-two-shot", "peer-graphs", "collective"])
 def test_two_gpu_sharded_step_equals_single_gpu_on_global_batch(exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
