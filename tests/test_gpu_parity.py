@@ -569,3 +569,25 @@ def test_boundary_token_counts_all_paths_agree(dev, K, D):
                 assert abs(float(a) - float(b)) <= 1e-6 * abs(float(b)), (T, K, D)
             else:
                 assert torch.equal(a, b), (name, T, K, D)
+
+
+@pytest.mark.parametrize("K,D,T", [(8192, 32, 8192), (1024, 256, 4096), (1000, 32, 300)])
+def test_cuda_graph_replay_equals_eager(dev, K, D, T):
+    """ShardedQuantiser(graphs=True): first use of a buffer set runs eagerly, the second is captured, later ones replay --
+    every output bit-identical to the eager step, also after the buffers' CONTENTS change (a graph is keyed on
+    addresses, not values)."""
+    from vq_b200 import dist as vq_dist
+    w = vo.make_codebook("vit", K, D, 80).to(dev)
+    z = torch.empty(T // 100 if T % 100 == 0 else 1, 100 if T % 100 == 0 else T, D, device=dev)
+    up = torch.empty_like(z)
+    eager = vq_dist.ShardedQuantiser("vit", 0.25, world_size=1)
+    graphed = vq_dist.ShardedQuantiser("vit", 0.25, world_size=1, graphs=True)
+    for i in range(5):
+        z.copy_(vo.make_latents(tuple(z.shape), 81 + i))
+        up.copy_(vo.make_latents(tuple(z.shape), 91 + i))
+        ref = {k: v.clone() for k, v in eager.step(z, up, w).items()}
+        out = graphed.step(z, up, w)
+        torch.cuda.synchronize()
+        for k in ("z_q", "indices", "loss", "grad_z", "grad_weight", "histogram"):
+            assert torch.equal(out[k], ref[k]), (k, i)
+    assert len(graphed._graphs) == 1 and graphed.graph_kernel_launches > 0
