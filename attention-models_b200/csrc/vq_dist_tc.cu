@@ -96,7 +96,6 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
           const int* __restrict__ cb_info, int4* __restrict__ records, int* __restrict__ cand,
           int* __restrict__ flagged, int* __restrict__ n_flagged, int64_t* __restrict__ stats, int splits) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    constexpr int D = KB * kKBlock;
     constexpr int AS = a_stages(KB);
     constexpr int BS = b_stages(KB);
     constexpr int kAreas = snap_areas(KB);
