@@ -191,5 +191,3 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
                         "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    text = open(HEADER).read()
-    assert "torch" not in text.replace("torch.argmin", "").replace("no torch types", "").lower().replace("pytorch", "") or True
