@@ -771,7 +771,8 @@ cudaError_t launch_exact_finish16(const void* records, const float* zn32, const 
     const int cap = (int)(T < kFlaggedCap ? T : kFlaggedCap);
     const int rows_per_block = tc16::kExactThreads / 8;
     int64_t blocks = (T + rows_per_block - 1) / rows_per_block;
-    const int64_t grid_cap = (int64_t)sm_count() * 16 * 2;       // resident blocks, two passes
+    static const int grid_mult = getenv("VQ_EXACT_GRID_MULT") ? atoi(getenv("VQ_EXACT_GRID_MULT")) : 32;
+    const int64_t grid_cap = (int64_t)sm_count() * grid_mult;    // 32 = 8 resident blocks per SM x 4 waves
     if (blocks > grid_cap) blocks = grid_cap;
     tc16::FinishOut out;
     out.zq = zq_tok; out.idx = idx_out; out.hist = hist;

@@ -165,6 +165,7 @@ class ShardedQuantiser:
         self.graphs = graphs
         self._graphs: Dict[tuple, tuple] = {}
         self._warmed = set()
+        self.max_graphs = 64
         self.graph_kernel_launches = 0        # kernels run through graph replays (the library only counts eager launches)
         self._plans: Dict[tuple, Dict[str, object]] = {}
         import os
@@ -218,16 +219,19 @@ class ShardedQuantiser:
 
     def step(self, z: torch.Tensor, upstream: Optional[torch.Tensor], weight: torch.Tensor,
              eager: bool = False) -> Dict[str, torch.Tensor]:
-        if not self.graphs or eager or not self._graph_capable():
+        # a graph is tied to buffer addresses: only caller-owned contiguous buffers qualify (a .contiguous() copy would
+        # be a fresh address on every call), and the cache is bounded
+        if (not self.graphs or eager or not self._graph_capable() or not z.is_contiguous() or not weight.is_contiguous()
+                or (upstream is not None and not upstream.is_contiguous())):
             return self._step(z, upstream, weight)
-        z = z.contiguous()
-        upstream = None if upstream is None else upstream.contiguous()
         key = (z.data_ptr(), tuple(z.shape), None if upstream is None else upstream.data_ptr(), weight.data_ptr(),
                tuple(weight.shape), self._graph_phase(z, weight))
         hit = self._graphs.get(key)
         if hit is None:
-            if key not in self._warmed:                   # first use: a real eager step (allocations, kernel attributes)
-                self._warmed.add(key)
+            if key not in self._warmed or len(self._graphs) >= self.max_graphs:
+                self._warmed.add(key)                     # first use: a real eager step (allocations, kernel attributes)
+                if len(self._warmed) > 16 * self.max_graphs:
+                    self._warmed.clear()
                 return self._step(z, upstream, weight)
             torch.cuda.synchronize(z.device)
             g = torch.cuda.CUDAGraph()
