@@ -77,11 +77,14 @@ def _worker(rank, world, port, exchange, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("exchange", ["peer-one-shot", "peer-two-shot", "peer-graphs", "collective"])
-def test_two_gpu_sharded_step_equals_single_gpu_on_global_batch(exchange):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    world, port = 2, _free_port()
+def test_sharded_step_equals_single_gpu_on_global_batch(exchange, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    if world > 2 and exchange in ("peer-one-shot", "collective"):
+        pytest.skip("covered at world 2")
+    port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, exchange, q)) for r in range(world)]
