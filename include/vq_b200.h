@@ -66,7 +66,8 @@ extern "C" {
 #define VQ_STAT_LOSS_FIXED      3 /* sum over tokens of sum_j (q - zn)^2, fixed point 2^-24      */
 #define VQ_STAT_BAD_INDEX       4 /* vq_gather: count of out-of-range indices                    */
 #define VQ_STAT_NONFINITE       5 /* non-finite loss partials (NaN/Inf rows): the loss is NaN     */
-#define VQ_STAT_PEER_TIMEOUT    6 /* vq_backward_codebook_sharded: a peer never published its step  */
+#define VQ_STAT_PEER_TIMEOUT    6 /* sharded backward: a peer never published its step, or the caller's
+                                     slot / epoch is out of step with the device's count            */
 #define VQ_STATS_LEN            8
 
 VQ_API int         vq_abi_version(void);
