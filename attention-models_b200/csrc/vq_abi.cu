@@ -229,23 +229,14 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
     float* zq_tok = indices_only ? nullptr : (layout == VQ_LAYOUT_NCHW ? w.zq_tok : z_q);
     SlotTimer timer(s, VQ_PROFILE_SEARCH);
     if (tc16) {
-        // D = 32: tensor-core filter -> records; one kernel then does the exact rescoring, the sliced search of
-        // the undecided rows and the finish pass.  Undecided rows beyond kFlaggedCap (degenerate inputs) overflow
-        // into the generic exhaustive kernel + a listed finish; both leave at once when there are none.
+        // D = 32: tensor-core filter -> records; one kernel then does the exact rescoring, the search of the undecided
+        // rows (sliced over blocks for the first kFlaggedCap of them, one block per row beyond) and the finish pass.
         VQ_CUDA(vq::launch_dist_tc(zn16, zn32, w.row_sq, cbv, T, w.cand, w.flagged, w.n_flagged, st, w.tc_ws, w.scan_ws, s));
         timer.stop();
         SlotTimer exact_timer(s, VQ_PROFILE_EXACT_FINISH);
         VQ_CUDA(vq::launch_exact_finish16(w.tc_ws, zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, w.n_flagged + 64, w.scan_ws,
-                                          nullptr, zq_tok, idx, hist, seg_sums, st, s));
+                                          zq_tok, idx, hist, seg_sums, st, s));
         exact_timer.stop();
-        if (T > vq::kFlaggedCap) {
-            vq::ListedFinish fin;
-            fin.zq = zq_tok; fin.idx = idx; fin.hist = hist;
-            fin.seg = zq_tok ? reinterpret_cast<unsigned long long*>(seg_sums) : nullptr;
-            SlotTimer tail_timer(s, VQ_PROFILE_TAIL);
-            VQ_CUDA(vq::launch_scan_listed_tail(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, vq::kFlaggedCap, w.cand, st, fin, s));
-            tail_timer.stop();
-        }
     } else {
         if (use_tc) {
             // filter -> exact rescoring (+ the undecided rows when they are few) -> tiled exhaustive scan of a long list

@@ -655,8 +655,8 @@ static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, int D, u
 
 // vq_dist_tc16.cu: D = 32 with fp16 accumulators and packed 16-bit maxima
 bool tc16_supported(int64_t T, int K, int D);
-cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T, const float* zn32, const float* row_sq,
-                             const CodebookView& cb, int* cand, int* flagged, int* n_flagged, int64_t* stats,
+cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T, const __half* zn16, const float* zn32,
+                             const float* row_sq, const CodebookView& cb, int* cand, int* flagged, int* n_flagged, int64_t* stats,
                              void* records, cudaStream_t s);
 size_t tc16_workspace_bytes(int64_t T);
 
@@ -745,7 +745,7 @@ cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* r
         // one 256-row box per row tile, one 128-code box per n-tile
         if (!tc::make_map(&ma, zn16, (uint64_t)T, cb.D, 256) || !tc::make_map(&mb, cb.en16, (uint64_t)cb.K, cb.D, 128))
             return cudaErrorInvalidValue;
-        return launch_dist_tc16(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, s);
+        return launch_dist_tc16(ma, mb, (int)T, zn16, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, s);
     }
     if (!tc::make_map(&ma, zn16, (uint64_t)T, cb.D, tc::kRowsPerCta) ||
         !tc::make_map(&mb, cb.en16, (uint64_t)cb.K, cb.D, tc::kTileN))

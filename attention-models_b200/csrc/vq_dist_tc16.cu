@@ -18,20 +18,25 @@
 // exhaustive search.  eps covers fp16 rounding of both operands plus the two fp16 roundings of the
 // accumulator (one per K = 16 MMA).
 //
-// Two kernels.  k_dist_tc16 is the filter: it writes one 32-byte verdict record per row (the best three groups
-// and, per group, a 64-bit mask of the cells that can still win).  k_rescore16 turns records into indices with
-// the exact fp32 formula.  Rescoring inside the tensor-core kernel was tried first and cost more than it hid: four
-// rescoring warps per SM are instruction-latency bound (~300 dependent instructions per item at IPC 0.2) and
-// their scattered 16-byte loads saturate the L1 wavefront pipe under the epilogue; as its own kernel the same
-// work runs at full occupancy.  Rescoring is warp-cooperative: 8 lanes share one row, each load instruction
-// fetches whole 128-byte code rows (the cell's 8 rows are transposed through shared memory), so the L1 sees one
-// wavefront per code row instead of eight.
+// Two kernels.  k_dist_tc16 is the filter: it writes one 16-byte verdict record per row -- the ids of the up to 8
+// cells (8 codes each) that can still hold the winner.  k_exact_finish16 turns records into indices with the exact
+// fp32 formula and does everything behind the search in the same pass (idx, histogram, z_q, loss partial, segment
+// sums), plus the exhaustive search of the few rows the filter could not decide.  Rescoring inside the tensor-core
+// kernel was tried first and cost more than it hid: four rescoring warps per SM are instruction-latency bound and
+// their scattered loads saturate the L1 wavefront pipe under the epilogue; as its own kernel the same work runs at
+// full occupancy.  Rescoring is warp-cooperative: 8 lanes share one row, lane m owns member m of every cell and each
+// load instruction fetches whole 128-byte lines of the cell-interleaved codebook copy.
 //
 // Shape of the computation: one persistent CTA per SM, 256 token rows per CTA (two M = 128 MMA row tiles),
-// codebook streamed by TMA in 256-code stages (two n-tiles of 128 codes), 2 x 2 accumulator tiles in TMEM.
+// codebook streamed by TMA in 128-code stages, 2 x 2 accumulator tiles of 128 columns in TMEM.
 // A "group" is 4 n-tiles = 512 codes; a row keeps 64 slot maxima per group (32 packed registers; slot hs
-// covers codes g*512 + hs + 64*m, m = 0..7 -- a "cell"), the maxima of the best three groups are parked in
-// shared memory, and at the end of the row tile every cell within 2*eps of the row's best score is rescored.
+// covers codes g*512 + hs + 64*m, m = 0..7 -- a "cell"), the slot maxima of the best four groups are parked in
+// shared memory, and at the end of the row tile every cell within 2*eps of the row's best score goes into the record.
+//
+// What bounds the filter (tools/ubench_mma.cu, profiles/r02_ubench_mma.txt): an M = 128, K = 16 tcgen05.mma with both
+// operands in shared memory costs ~60 cycles + 0.42 cycles per column -- 107 cycles at N = 128 against the nominal 64
+// -- and a D = 32 tile is just two of them: 2 x 107 cycles per 128 x 128 tile is exactly the ~58 % tensor-pipe
+// activity ncu reports.  k_dist_tc16_ts below keeps the token rows in tensor memory instead (83 cycles per MMA).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cstdio>
@@ -70,9 +75,10 @@ constexpr uint32_t kIdesc = ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(128 >>
 
 constexpr int kSnapRow = 144;                       // 32 packed slot registers + 16 B pad (conflict-free STS.128)
 constexpr int kSnapArea = kRowsPerCta * kSnapRow;
-// verdict record, 48 bytes per row: {g1 | g2 << 16 or -1 (undecided), g3 | g4 << 16, mask0 lo, hi}
-// {mask1 lo, hi, mask2 lo, hi} {mask3 lo, hi, -, -}: the best four groups and, per group, the cells that can still win
-constexpr int kRecordBytes = 48;
+// verdict record, 16 bytes per row: up to 8 surviving cells as 16-bit ids (group * 64 + slot), 0xFFFF = none, filled
+// from the low end; all-ones = the filter could not decide the row (it is on the list for the exhaustive search)
+constexpr int kRecordBytes = 16;
+constexpr int kRecCells = 8;
 constexpr int kAreas = 4;
 
 struct SmemLayout {
@@ -266,41 +272,7 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
             int m1 = -32768, m2 = -32768, m3 = -32768, m4 = -32768, m5 = -32768;
             int g1 = 0, g2 = 0, g3 = 0, g4 = 0;
             uint32_t a1 = 0, a2 = 1, a3 = 2, a4 = 3;  // snapshot areas of the best four groups
-            VQ_TIMED_WAIT(0, t_full(r_sub), (t_cnt >> 1) & 1u);
-            tc_fence_after();
-            tmem_ld_tile(tbase, bufA);
-            for (int g = 0; g < n_groups; ++g) {
-#pragma unroll
-                for (int b = 0; b < kGroupTiles; ++b) {
-                    uint32_t (&cur)[64] = (b & 1) ? bufB : bufA;
-                    uint32_t (&nxt)[64] = (b & 1) ? bufA : bufB;
-                    VQ_TIMED_BEGIN();
-                    tmem_ld_wait();                                   // tile b is in registers: its TMEM stage is free
-                    VQ_TIMED_END(2);
-#ifdef VQ_TC_INSTRUMENT
-                    if (e == 0 && lane == 0) { asm volatile("" ::"r"(cur[0]), "r"(cur[63])); VQ_TRACE(1, (int)t_cnt, 1); }
-#endif
-                    tc_fence_before();
-                    if (lane == 0) mbar_arrive(t_empty(2 * (b & 1) + r_sub));
-                    if (e == 0 && lane == 0) VQ_TRACE(1, (int)t_cnt, 2);
-                    ++t_cnt;
-                    if (b < kGroupTiles - 1 || g + 1 < n_groups) {
-                        VQ_TIMED_WAIT(0, t_full(2 * ((b + 1) & 1) + r_sub), (t_cnt >> 1) & 1u);
-                        if (e == 0 && lane == 0) VQ_TRACE(1, (int)t_cnt, 0);
-                        tc_fence_after();
-                        tmem_ld_tile(tbase + (uint32_t)(((b + 1) & 1) * 2 * kTileN), nxt);
-                    }
-                    if (b == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) slot[j] = __vmaxs2(cur[j], cur[j + 32]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) slot[j] = __vimax3_s16x2(slot[j], cur[j], cur[j + 32]);
-                    }
-#ifdef VQ_TC_INSTRUMENT
-                    if (e == 0 && lane == 0) { asm volatile("" ::"r"(slot[0]), "r"(slot[31])); VQ_TRACE(1, (int)t_cnt - 1, 3); }
-#endif
-                }
+            auto group_end = [&](const int g) {
                 // group maximum: 3-input tree over the 32 packed registers, then the two halves
                 uint32_t t[11];
 #pragma unroll
@@ -339,7 +311,47 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                 const uint32_t na1 = is1 ? a4 : a1;
                 g1 = is1 ? g : g1; g2 = ng2; g3 = ng3; g4 = ng4;
                 a1 = na1; a2 = na2; a3 = na3; a4 = na4;
+            };
+            VQ_TIMED_WAIT(0, t_full(r_sub), (t_cnt >> 1) & 1u);
+            tc_fence_after();
+            tmem_ld_tile(tbase, bufA);
+            for (int g = 0; g < n_groups; ++g) {
+#pragma unroll
+                for (int b = 0; b < kGroupTiles; ++b) {
+                    uint32_t (&cur)[64] = (b & 1) ? bufB : bufA;
+                    uint32_t (&nxt)[64] = (b & 1) ? bufA : bufB;
+                    VQ_TIMED_BEGIN();
+                    tmem_ld_wait();                                   // tile b is in registers: its TMEM stage is free
+                    VQ_TIMED_END(2);
+#ifdef VQ_TC_INSTRUMENT
+                    if (e == 0 && lane == 0) { asm volatile("" ::"r"(cur[0]), "r"(cur[63])); VQ_TRACE(1, (int)t_cnt, 1); }
+#endif
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(t_empty(2 * (b & 1) + r_sub));
+                    if (e == 0 && lane == 0) VQ_TRACE(1, (int)t_cnt, 2);
+                    ++t_cnt;
+                    if (b < kGroupTiles - 1 || g + 1 < n_groups) {
+                        VQ_TIMED_WAIT(0, t_full(2 * ((b + 1) & 1) + r_sub), (t_cnt >> 1) & 1u);
+                        if (e == 0 && lane == 0) VQ_TRACE(1, (int)t_cnt, 0);
+                        tc_fence_after();
+                        tmem_ld_tile(tbase + (uint32_t)(((b + 1) & 1) * 2 * kTileN), nxt);
+                    }
+                    if (b == 0) {
+                        // the previous group's bookkeeping runs here, behind the hand-off of this tile's TMEM stage: the
+                        // tensor pipe refills that stage meanwhile instead of idling with both stages full
+                        if (g > 0) group_end(g - 1);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) slot[j] = __vmaxs2(cur[j], cur[j + 32]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) slot[j] = __vimax3_s16x2(slot[j], cur[j], cur[j + 32]);
+                    }
+#ifdef VQ_TC_INSTRUMENT
+                    if (e == 0 && lane == 0) { asm volatile("" ::"r"(slot[0]), "r"(slot[31])); VQ_TRACE(1, (int)t_cnt - 1, 3); }
+#endif
+                }
             }
+            group_end(n_groups - 1);
             // ---- row verdict ----
             // m1 is a non-negative finite fp16 pattern for every row the filter may decide; NaN / Inf patterns,
             // negative best scores and thresholds near zero leave the row to the exhaustive search
@@ -372,19 +384,32 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                     }
                 }
             }
-            // decided iff no further group can hold the winner
+            // decided iff no further group can hold the winner and the survivors fit a record
             const int n_cand = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]) + __popc(mask[4]) + __popc(mask[5]) +
                                __popc(mask[6]) + __popc(mask[7]);
-            const bool decided = thr_ok && (m5 < thr) && ((mask[0] | mask[1]) != 0) && (n_cand <= 16) && !force_exhaustive;
+            const bool decided = thr_ok && (m5 < thr) && ((mask[0] | mask[1]) != 0) && (n_cand <= kRecCells) && !force_exhaustive;
             const int row = rt * kRowsPerCta + row_in_cta;
             const bool in_range = row < T;
             const bool flag = in_range && !decided;
-            if (in_range) {
-                rec[3 * (int64_t)row] = make_int4(decided ? (g1 | (g2 << 16)) : -1, g3 | (g4 << 16), (int)mask[0], (int)mask[1]);
-                rec[3 * (int64_t)row + 1] = make_int4((int)mask[2], (int)mask[3], (int)mask[4], (int)mask[5]);
-                rec[3 * (int64_t)row + 2] = make_int4((int)mask[6], (int)mask[7], 0, 0);
+            // verdict record: the surviving cells as 16-bit cell ids (group * 64 + slot), pushed into a 128-bit shift register
+            // from the low end; 0xFFFF = none.  An undecided row keeps all-ones (its first field says "listed").
+            unsigned long long lo = ~0ull, hi = ~0ull;
+            if (decided) {
+                const int gv[4] = {g1, g2, g3, g4};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t w = mask[2 * a + h];
+                        while (w) {
+                            const uint32_t id = (uint32_t)gv[a] * 64u + 32u * h + (uint32_t)(__ffs((int)w) - 1);
+                            w &= w - 1;
+                            hi = (hi << 16) | (lo >> 48);
+                            lo = (lo << 16) | id;
+                        }
+                    }
             }
-            if (flag) cand[row] = -1;
+            if (in_range) rec[row] = make_int4((int)(uint32_t)lo, (int)(uint32_t)(lo >> 32), (int)(uint32_t)hi, (int)(uint32_t)(hi >> 32));
             const uint32_t ballot = __ballot_sync(VQ_FULL, flag);
             if (ballot) {
                 int base = 0;
@@ -395,6 +420,381 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                     atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_FALLBACK_ROWS),
                               (unsigned long long)__popc(ballot));
             }
+        }
+        if (threadIdx.x == kEpiWarp0 * 32) { VQ_INSTR_END(8, 3); }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kAllocWarp) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(512u) : "memory");
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// The filter with the token rows in TENSOR MEMORY (tcgen05.mma "TS" form: A from TMEM, B from shared memory).
+//
+// Why: an M = 128, K = 16 MMA costs a fixed ~60 cycles on top of ~0.42 cycles per column when A comes from shared
+// memory and ~30 when it comes from tensor memory (tools/ubench_mma.cu, profiles/r02_ubench_mma.txt: N = 128 takes
+// 107 / 83 cycles against the nominal 64).  At codebook_dim = 32 a 128 x 128 tile is just two such instructions, so
+// the SS kernel above is bound by that fixed cost (2 x 107 cycles per tile = the 58 % tensor-pipe activity ncu
+// shows), not by its accumulator ring.  Here the row tile's fp16 unit rows are written once per row tile into 16
+// TMEM columns per row half by the epilogue threads themselves (tcgen05.st; thread = row = TMEM lane) -- no A tile in
+// shared memory, no TMA for it -- and every MMA reads them from there.
+// TMEM: 3 accumulator stages of 128 columns shared by BOTH row halves (stage of the c-th (n-tile, half) pair:
+// c mod 3), A at columns 384 + 32 * (row-tile parity) + 16 * half, three MMA issuer warps (one per stage: a wait on
+// an mbarrier costs ~90 cycles even when its phase completed long ago, so one issuer walking every pair is too slow).
+// MEASURED (B200, 262 144 x 8192): 142 us against 124 us for the SS kernel -- the A columns leave room for only three
+// accumulator stages, and three stages cannot cover the issue -> commit -> tcgen05.ld -> release chain (~420 cycles
+// before the next MMA of a stage can start): the epilogue waits for finished tiles 35 % of its time.  Kept behind
+// VQ_TC16_TS=1 as the measured alternative; the default stays the SS kernel above.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kAccStages = 3;
+constexpr int kACol = kAccStages * kTileN;
+constexpr int kBStagesTs = 8;
+// setmaxnreg moves registers inside the pool the block was launched with (384 threads x 168): the epilogue's increase
+// blocks forever if the two budgets add up to more than that
+constexpr int kRegsServiceTs = 56, kRegsEpilogueTs = 224;
+static_assert(128 * kRegsServiceTs + 256 * kRegsEpilogueTs <= 384 * 168, "register pool overcommitted");
+struct SmemLayoutTs {
+    uint32_t b, snap, bars, tmem_slot, total;
+};
+__host__ __device__ inline SmemLayoutTs smem_layout_ts() {
+    SmemLayoutTs L;
+    L.b = 0;
+    L.snap = L.b + kBStagesTs * kBStageBytes;
+    L.bars = L.snap + kAreas * kSnapArea;
+    L.tmem_slot = L.bars + 8 * 32;
+    L.total = L.tmem_slot + 16;
+    return L;
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 16 columns: thread i writes its 16 registers to columns [col, col + 16) of TMEM lane (lane_base + i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint4 (&v)[4]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0].x), "r"(v[0].y), "r"(v[0].z), "r"(v[0].w), "r"(v[1].x), "r"(v[1].y), "r"(v[1].z), "r"(v[1].w),
+          "r"(v[2].x), "r"(v[2].y), "r"(v[2].z), "r"(v[2].w), "r"(v[3].x), "r"(v[3].y), "r"(v[3].z), "r"(v[3].w)
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_dist_tc16_ts(const __grid_constant__ CUtensorMap tm_b, const uint4* __restrict__ zn16, int T, int K,
+               const int* __restrict__ cb_info, int4* __restrict__ rec, int* __restrict__ flagged, int* __restrict__ n_flagged,
+               int64_t* __restrict__ stats) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const SmemLayoutTs L = smem_layout_ts();
+    const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + L.bars;
+    auto b_full = [&](int s) { return bar_base + 8 * s; };
+    auto b_empty = [&](int s) { return bar_base + 8 * (8 + s); };
+    // "stage q holds a finished tile of row half h": one barrier per (stage, half).  A stage serves the two halves in turn
+    // (3 is odd), and a parity wait is only sound when the waiter also consumed the barrier's previous phase -- a half
+    // that ran ahead would otherwise see the other half's still-pending phase as "mine, completed"
+    auto t_full = [&](int q, int h) { return bar_base + 8 * (16 + 2 * q + h); };
+    auto t_empty = [&](int q) { return bar_base + 8 * (24 + q); };
+    auto a_full = [&](int s) { return bar_base + 8 * (27 + s); };
+    auto a_empty = [&](int s) { return bar_base + 8 * (29 + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_slot);
+
+    const int warp = __shfl_sync(VQ_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    constexpr int kEpiWarp0 = 0, kTmaWarp = 8, kMmaWarp = 9, kAllocWarp = 10;
+    const int n_row_tiles = (T + kRowsPerCta - 1) / kRowsPerCta;
+    const int n_tiles = K / kTileN;
+    const int n_groups = n_tiles / kGroupTiles;
+
+    if (warp == kMmaWarp && lane == 0) {
+        for (int s = 0; s < kBStagesTs; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 2); }       // both halves' MMAs done
+        for (int q = 0; q < kAccStages; ++q) { mbar_init(t_full(q, 0), 1); mbar_init(t_full(q, 1), 1); mbar_init(t_empty(q), 4); }   // 4 warps drain
+        for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 8); mbar_init(a_empty(s), kAccStages); } // 8 epilogue warps wrote / 3 issuers done
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kAllocWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + L.tmem_slot),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    pdl_trigger();
+    pdl_wait();
+
+    if (warp >= kTmaWarp) {
+        reg_dec<kRegsServiceTs>();
+        if (warp == kTmaWarp) {
+            // ===================== TMA producer: codebook tiles only =====================
+            uint32_t b_cnt = 0;
+            VQ_INSTR_BEGIN();
+            for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
+                for (int n = 0; n < n_tiles; ++n, ++b_cnt) {
+                    const int s = b_cnt % kBStagesTs;
+                    VQ_TIMED_WAIT(1, b_empty(s), ((b_cnt / kBStagesTs) & 1u) ^ 1u);
+                    if (elect_one()) {
+                        mbar_expect_tx(b_full(s), kBStageBytes);
+                        tma_load_2d(smem_base + L.b + s * kBStageBytes, &tm_b, b_full(s), 0, n * kTileN);
+                    }
+                    __syncwarp();
+                }
+            }
+            VQ_INSTR_END(0, 2);
+        } else {
+            // ===================== MMA issuers: one warp per accumulator stage =====================
+            // A wait on an mbarrier costs ~90 cycles even when its phase is long complete, so one thread walking
+            // t_empty / b_full / issue / commit for every (n-tile, half) pair needs ~350 cycles per pair against the
+            // 167 the tensor pipe takes; three issuers (pairs c = q, q + 3, ...; stage q) have 500 each.
+            const int q = warp - kMmaWarp;                         // accumulator stage served by this warp
+            const uint32_t tmem_base = *tmem_slot;
+            const int pairs_per_rt = 2 * n_tiles;
+            const int my_row_tiles = ((int)blockIdx.x < n_row_tiles) ? (n_row_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+            int it = 0, c_in = q;                                  // row-tile count and pair index inside the row tile
+            uint32_t tile_cnt = (uint32_t)(q >> 1);                // n-tiles of this CTA so far (b ring position)
+            uint32_t ph = 0;
+            VQ_INSTR_BEGIN();
+            if (my_row_tiles > 0) {
+                VQ_TIMED_WAIT(0, a_full(0), 0u);
+                tc_fence_after();
+            }
+            while (it < my_row_tiles) {
+                const int h = c_in & 1;
+                const int sb = tile_cnt % kBStagesTs;
+                VQ_TIMED_WAIT(2, b_full(sb), (tile_cnt / kBStagesTs) & 1u);
+                VQ_TIMED_WAIT(1, t_empty(q), ph ^ 1u);
+                tc_fence_after();
+                const uint32_t b_addr = smem_base + L.b + sb * kBStageBytes;
+                const uint32_t a_col = tmem_base + (uint32_t)(kACol + (it & 1) * 32 + h * 16);
+                VQ_TIMED_BEGIN();
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        umma_f16_ts(tmem_base + (uint32_t)(q * kTileN), a_col + (uint32_t)(k * 8), umma_desc(b_addr + k * 32), kIdesc,
+                                    (uint32_t)k);
+                    umma_commit(t_full(q, h));
+                    umma_commit(b_empty(sb));
+                }
+                __syncwarp();
+                VQ_TIMED_END(3);
+                ph ^= 1u;
+                // next pair of this issuer: c + 3
+                const int c_next = c_in + kAccStages;
+                tile_cnt += (uint32_t)((c_next >> 1) - (c_in >> 1));
+                c_in = c_next;
+                if (c_in >= pairs_per_rt) {
+                    c_in -= pairs_per_rt;
+                    if (elect_one()) umma_commit(a_empty(it & 1));      // this issuer's MMAs of the row tile are all queued
+                    __syncwarp();
+                    ++it;
+                    if (it < my_row_tiles) {
+                        VQ_TIMED_WAIT(0, a_full(it & 1), ((uint32_t)(it >> 1)) & 1u);
+                        tc_fence_after();
+                    }
+                }
+            }
+            if (q == 0) { VQ_INSTR_END(3, 4); }
+        }
+    } else {
+        // ===================== epilogue: 8 warps, one thread per row =====================
+        reg_inc<kRegsEpilogueTs>();
+        VQ_INSTR_BEGIN();
+        const int e = warp - kEpiWarp0;
+        const int r_sub = e >> 2;                    // which 128-row half
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may access (warp id mod 4)
+        const int row_in_cta = r_sub * 128 + quarter * 32 + lane;
+        const uint32_t tlane = *tmem_slot + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t snap0 = smem_base + L.snap + (uint32_t)row_in_cta * kSnapRow;
+        const bool force_exhaustive = codebook_degenerate(cb_info);
+        // this half's (n-tile, half) pairs are c = 2 j + r_sub: stage c mod 3; the half meets each stage every third tile,
+        // so the phase parity of its barriers flips every three tiles
+        uint32_t st = (uint32_t)r_sub, ph = 0, t3 = 0;
+        auto advance = [&]() {
+            st += 2;
+            if (st >= (uint32_t)kAccStages) st -= (uint32_t)kAccStages;
+            if (++t3 == 3u) { t3 = 0; ph ^= 1u; }
+        };
+        // the thread's own fp16 unit row of a row tile (64 bytes; rows past the end read as zero)
+        auto load_row = [&](int rt, uint4 (&v)[4]) {
+            const int64_t row = (int64_t)rt * kRowsPerCta + row_in_cta;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = (row < T) ? __ldg(zn16 + row * 4 + i) : make_uint4(0u, 0u, 0u, 0u);
+        };
+        // ... into the A columns of buffer `buf` (its w-th use): wait until the MMAs of the row tile that used it completed
+        auto store_row = [&](int buf, int w, const uint4 (&v)[4]) {
+            VQ_TIMED_WAIT(1, a_empty(buf), ((uint32_t)w & 1u) ^ 1u);
+            tc_fence_after();
+            tmem_st16(tlane + (uint32_t)(kACol + buf * 32 + r_sub * 16), v);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full(buf));
+        };
+        int it = 0;
+        uint32_t bufA[64], bufB[64];
+        {
+            uint4 first[4];
+            if ((int)blockIdx.x < n_row_tiles) { load_row(blockIdx.x, first); store_row(0, 0, first); }
+        }
+        for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
+            uint32_t slot[32];
+            int m1 = -32768, m2 = -32768, m3 = -32768, m4 = -32768, m5 = -32768;
+            int g1 = 0, g2 = 0, g3 = 0, g4 = 0;
+            uint32_t a1 = 0, a2 = 1, a3 = 2, a4 = 3;  // snapshot areas of the best four groups
+            const bool has_next = rt + (int)gridDim.x < n_row_tiles;
+            uint4 a_next[4];
+            if (has_next) load_row(rt + gridDim.x, a_next);     // lands while the first group is folded
+            auto group_end = [&](const int g) {
+                // group maximum: 3-input tree over the 32 packed registers, then the two halves
+                uint32_t t[11];
+#pragma unroll
+                for (int j = 0; j < 10; ++j) t[j] = __vimax3_s16x2(slot[3 * j], slot[3 * j + 1], slot[3 * j + 2]);
+                t[10] = __vmaxs2(slot[30], slot[31]);
+                const uint32_t u0 = __vimax3_s16x2(t[0], t[1], t[2]), u1 = __vimax3_s16x2(t[3], t[4], t[5]),
+                               u2 = __vimax3_s16x2(t[6], t[7], t[8]);
+                const uint32_t pk = __vimax3_s16x2(__vimax3_s16x2(u0, u1, u2), t[9], t[10]);
+                const int c1 = max(lo16(pk), hi16(pk));
+                const bool is1 = c1 > m1, is2 = c1 > m2, is3 = c1 > m3, is4 = c1 > m4;
+                if (is4) {
+                    // whichever rank the group takes, the group that drops out is the current last one: reuse its area
+                    const uint32_t dst = snap0 + a4 * kSnapArea;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16 * q), "r"(slot[4 * q]),
+                                     "r"(slot[4 * q + 1]), "r"(slot[4 * q + 2]), "r"(slot[4 * q + 3])
+                                     : "memory");
+                }
+                // sorted insert of c1 into (m1 >= m2 >= m3 >= m4 >= m5); identities and areas follow
+                const int lo1 = min(c1, m1);
+                m1 = max(c1, m1);
+                const int lo2 = min(lo1, m2);
+                m2 = max(lo1, m2);
+                const int lo3 = min(lo2, m3);
+                m3 = max(lo2, m3);
+                const int lo4 = min(lo3, m4);
+                m4 = max(lo3, m4);
+                m5 = max(lo4, m5);
+                const int ng4 = is3 ? g3 : (is4 ? g : g4);
+                const uint32_t na4 = is3 ? a3 : a4;
+                const int ng3 = is2 ? g2 : (is3 ? g : g3);
+                const uint32_t na3 = is2 ? a2 : (is3 ? a4 : a3);
+                const int ng2 = is1 ? g1 : (is2 ? g : g2);
+                const uint32_t na2 = is1 ? a1 : (is2 ? a4 : a2);
+                const uint32_t na1 = is1 ? a4 : a1;
+                g1 = is1 ? g : g1; g2 = ng2; g3 = ng3; g4 = ng4;
+                a1 = na1; a2 = na2; a3 = na3; a4 = na4;
+            };
+
+            VQ_TIMED_WAIT(0, t_full(st, r_sub), ph);
+            tc_fence_after();
+            tmem_ld_tile(tlane + st * (uint32_t)kTileN, bufA);
+            for (int g = 0; g < n_groups; ++g) {
+#pragma unroll
+                for (int b = 0; b < kGroupTiles; ++b) {
+                    uint32_t (&cur)[64] = (b & 1) ? bufB : bufA;
+                    uint32_t (&nxt)[64] = (b & 1) ? bufA : bufB;
+                    VQ_TIMED_BEGIN();
+                    tmem_ld_wait();                                   // tile b is in registers: its TMEM stage is free
+                    VQ_TIMED_END(2);
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(t_empty(st));
+                    advance();
+                    if (b < kGroupTiles - 1 || g + 1 < n_groups) {
+                        VQ_TIMED_WAIT(0, t_full(st, r_sub), ph);
+                        tc_fence_after();
+                        tmem_ld_tile(tlane + st * (uint32_t)kTileN, nxt);
+                    }
+                    if (b == 0) {
+                        if (g > 0) group_end(g - 1);      // behind the hand-off of this tile's stage
+                        if (g == 1 && has_next) store_row((it + 1) & 1, (it + 1) >> 1, a_next);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) slot[j] = __vmaxs2(cur[j], cur[j + 32]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) slot[j] = __vimax3_s16x2(slot[j], cur[j], cur[j + 32]);
+                    }
+                }
+            }
+            group_end(n_groups - 1);
+            if (n_groups == 1 && has_next) store_row((it + 1) & 1, (it + 1) >> 1, a_next);
+            // ---- row verdict ----
+            // m1 is a non-negative finite fp16 pattern for every row the filter may decide; NaN / Inf patterns,
+            // negative best scores and thresholds near zero leave the row to the exhaustive search
+            const float m1f = __half2float(__ushort_as_half((unsigned short)(m1 & 0xFFFF)));
+            // a code whose K = 16 partial sum reaches 1 has a final score >= 0.95, so below 0.9 both accumulator
+            // roundings are at most one ulp of [0.5, 1)
+            const float thr_f = m1f - (m1f < 0.9f ? kTwoEps : kTwoEpsNearOne);
+            const bool thr_ok = (m1 >= 0) && (m1 < 0x7C00) && (thr_f >= kMinThreshold);
+            const int thr = thr_ok ? (int)__half_as_ushort(__float2half_rd(thr_f)) : 0x7BFF;
+            const uint32_t thr2 = (uint32_t)thr * 0x10001u;
+            uint32_t mask[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            const int mv[4] = {m1, m2, m3, m4};
+            const uint32_t av[4] = {a1, a2, a3, a4};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                if (a == 0 || mv[a] >= thr) {
+                    const uint32_t src = snap0 + av[a] * kSnapArea;
+                    uint32_t kept[32];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(kept[4 * q]), "=r"(kept[4 * q + 1]), "=r"(kept[4 * q + 2]), "=r"(kept[4 * q + 3])
+                                     : "r"(src + 16 * q));
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        bool ph, pl;
+                        (void)__vibmax_s16x2(kept[j], thr2, &ph, &pl);      // per half: kept >= thr
+                        const uint32_t bits = (pl ? (1u << ((2 * j) & 31)) : 0u) | (ph ? (1u << ((2 * j + 1) & 31)) : 0u);
+                        mask[2 * a + (j >> 4)] |= bits;
+                    }
+                }
+            }
+            // decided iff no further group can hold the winner and the survivors fit a record
+            const int n_cand = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]) + __popc(mask[4]) + __popc(mask[5]) +
+                               __popc(mask[6]) + __popc(mask[7]);
+            const bool decided = thr_ok && (m5 < thr) && ((mask[0] | mask[1]) != 0) && (n_cand <= kRecCells) && !force_exhaustive;
+            const int row = rt * kRowsPerCta + row_in_cta;
+            const bool in_range = row < T;
+            const bool flag = in_range && !decided;
+            // verdict record: the surviving cells as 16-bit cell ids (group * 64 + slot), pushed into a 128-bit shift register
+            // from the low end; 0xFFFF = none.  An undecided row keeps all-ones (its first field says "listed").
+            unsigned long long lo = ~0ull, hi = ~0ull;
+            if (decided) {
+                const int gv[4] = {g1, g2, g3, g4};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t w = mask[2 * a + h];
+                        while (w) {
+                            const uint32_t id = (uint32_t)gv[a] * 64u + 32u * h + (uint32_t)(__ffs((int)w) - 1);
+                            w &= w - 1;
+                            hi = (hi << 16) | (lo >> 48);
+                            lo = (lo << 16) | id;
+                        }
+                    }
+            }
+            if (in_range) rec[row] = make_int4((int)(uint32_t)lo, (int)(uint32_t)(lo >> 32), (int)(uint32_t)hi, (int)(uint32_t)(hi >> 32));
+            const uint32_t ballot = __ballot_sync(VQ_FULL, flag);
+            if (ballot) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(n_flagged, __popc(ballot));
+                base = __shfl_sync(VQ_FULL, base, 0);
+                if (flag) flagged[base + __popc(ballot & ((1u << lane) - 1))] = row;
+                if (lane == 0 && stats)
+                    atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_FALLBACK_ROWS),
+                              (unsigned long long)__popc(ballot));
+            }
+
         }
         if (threadIdx.x == kEpiWarp0 * 32) { VQ_INSTR_END(8, 3); }
     }
@@ -495,121 +895,115 @@ __device__ __forceinline__ void finish_row_serial(const float4* __restrict__ zn4
 //   phase A  rescoring of the verdict records, one 8-lane group per row: index = argmin over the row's surviving
 //            cells; the same lanes then write idx / hist / z_q / loss partial (the former k_finish pass);
 //   phase B  exhaustive search of the rows the filter could not decide (a few dozen per 262 144).  Latency
-//            matters there, not throughput: a listed row is split over kFlaggedSlices items, an item leaves its
-//            (best, second) in `partial`, the last item of a row to finish folds them and finishes the row.
-//            Rows [0, min(*n_rows, cap)) of the list; `done` holds one zeroed counter per listed row.
+//            matters there, not throughput: each of the first `flagged_cap` listed rows is split over kFlaggedSlices
+//            items, an item leaves its (best, second) in `partial`, the last item of a row to finish folds them and
+//            finishes the row (`done` holds one zeroed counter per such row); listed rows beyond the cap (degenerate
+//            inputs only) are searched by one block each.
+// The instruction stream of phase A is what bounds the kernel (the loads are L2 hits and 32 warps per SM hide them), so
+// it is kept lean: 16-byte records holding cell ids, 32-bit ordered distance keys, one pass of 8-lane minimum shuffles.
 constexpr int kExactThreads = 128;
 #ifndef VQ_EXACT_MIN_BLOCKS
-#define VQ_EXACT_MIN_BLOCKS 8   // 64 registers (24 B of spills): 2% faster than 6 blocks of 80 registers
+#define VQ_EXACT_MIN_BLOCKS 8
 #endif
 constexpr int kFlaggedSlices = 32;
 struct __align__(16) FlaggedPartial {
     unsigned long long best; float second; float pad;
 };
+// distance -> unsigned key with torch.argmin's order: NaN (wins) -> 0, else sign-corrected float bits
+__device__ __forceinline__ uint32_t dist_ord(float d) {
+    const uint32_t b = __float_as_uint(d);
+    return (d != d) ? 0u : (b ^ ((uint32_t)((int)b >> 31) | 0x80000000u));
+}
+__device__ __forceinline__ float ord_dist(uint32_t o) {
+    return (o == 0u) ? __int_as_float(0x7fc00000) : __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+}
+
 __global__ void __launch_bounds__(kExactThreads, VQ_EXACT_MIN_BLOCKS)
 k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, const float* __restrict__ row_sq,
                  const float* __restrict__ en32, const float4* __restrict__ en32c, const float* __restrict__ csq_cell, int T,
                  int K, const int* __restrict__ flagged, const int* __restrict__ n_flagged, int flagged_cap,
-                 FlaggedPartial* __restrict__ partial, int* __restrict__ done, int* __restrict__ cand, FinishOut out,
-                 int64_t* __restrict__ stats) {
+                 FlaggedPartial* __restrict__ partial, int* __restrict__ done, FinishOut out, int64_t* __restrict__ stats) {
     __shared__ unsigned long long s_best[kExactThreads / 32];
     __shared__ float s_second[kExactThreads / 32];
-    pdl_trigger();
-    pdl_wait();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int m = lane & 7;
-    const float4* zn4 = reinterpret_cast<const float4*>(zn32);
-    // per-thread counters share one register (a thread sees at most a few dozen rows): ties in bits 0-9, rows
-    // rescored over several cells in bits 10-19, non-finite loss partials above
-    unsigned counts = 0, bad = 0;
-    constexpr unsigned kTie = 1u, kMulti = 1u << 10;
-    long long loss_fx = 0;
-    // ---------------- phase A ----------------
-    // A warp owns 4 rows per iteration.  Their unit rows (512 contiguous bytes) arrive with ONE coalesced 16-byte load
-    // per lane and are staged in shared memory (the 8 lanes of a row then read them as broadcasts: 4 registers instead
-    // of 32 for the row), in the same round trip as the row's record.
-    // Finish: lane m owns chunk m of the row (one 16-byte access per lane for zn, the code row and z_q); for the
-    // segment sums the differences are transposed through shared memory so that lane m adds elements m, m + 8, m + 16,
-    // m + 24: every RED instruction of a group then covers 8 consecutive int64 (two whole 32-byte sectors; 4x fewer
-    // L2 reduction transactions than 4 consecutive elements per lane, tools/ubench_red.cu).
     // Row strides of 9 / 10 float4 put the 4 rows of a warp in different banks: the broadcast LDS.128 of the rescoring
     // (one address per 8-lane group) and the strided LDS.32 of the segment-sum transposition are conflict-free.
     __shared__ __align__(16) float4 s_z[kExactThreads / 32][4][kD / 4 + 1];
     __shared__ __align__(16) float4 s_df[kExactThreads / 32][4][kD / 4 + 2];
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = lane & 7, grp = lane >> 3;
+    const float4* zn4 = reinterpret_cast<const float4*>(zn32);
     const float4* en4 = reinterpret_cast<const float4*>(en32);
+    // per-thread counters share one register (a thread sees at most a few dozen rows): ties in bits 0-9, rows
+    // rescored over several cells in bits 10-19
+    unsigned counts = 0, bad = 0;
+    constexpr unsigned kTie = 1u, kMulti = 1u << 10;
+    long long loss_fx = 0;
+    // ---------------- phase A ----------------
+    // A warp owns 4 rows per iteration; lane m of a row's 8-lane group owns member m of every cell (whole 128-byte lines
+    // of the cell copies) and chunk m of the row in the finish.  The unit rows (512 contiguous bytes) arrive with ONE
+    // coalesced 16-byte load per lane and are staged in shared memory for the broadcast reads of the dot products.
     const int groups = gridDim.x * (kExactThreads / 8);
-    const int grp = lane >> 3;
-    int row0 = (blockIdx.x * kExactThreads + threadIdx.x - lane) >> 3;
-    int4 n0 = make_int4(-1, 0, 0, 0), n1 = make_int4(0, 0, 0, 0), n2 = make_int4(0, 0, 0, 0);
-    float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
-    float n_sq = 0.f;
-    auto fetch = [&](int r0) {
-        const int r = r0 + grp;
-        n0 = make_int4(-1, 0, 0, 0);
-        if (r < T) {
-            n0 = __ldg(rec + 3 * (int64_t)r); n1 = __ldg(rec + 3 * (int64_t)r + 1); n2 = __ldg(rec + 3 * (int64_t)r + 2);
-            nz = __ldg(zn4 + (int64_t)r0 * (kD / 4) + lane);      // row r0 + (lane >> 3), chunk lane & 7
-            n_sq = __ldg(row_sq + r);
-        }
-    };
-#ifndef VQ_EXACT_PREFETCH
-#define VQ_EXACT_PREFETCH 0     // 1: records / rows of the next iteration prefetched into registers -- measured 3 us slower
-#endif                          // (17 more live registers spill under the 64-register cap; the data sits in L2 anyway)
-    if (VQ_EXACT_PREFETCH && row0 < T) fetch(row0);
-    for (; row0 < T; row0 += groups) {
+    const uint32_t gmask = 0xFFu << (8 * grp);
+    for (int row0 = (blockIdx.x * kExactThreads + threadIdx.x - lane) >> 3; row0 < T; row0 += groups) {
         const int row = row0 + grp;
-        if (!VQ_EXACT_PREFETCH) fetch(row0);
-        const int4 h0 = n0, h1 = n1, h2 = n2;
-        const float a_sq = n_sq;
-        __syncwarp();                                   // the previous iteration's reads of s_z are done
+        const bool in_range = row < T;
+        int4 r = make_int4(-1, -1, -1, -1);
+        float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
+        float a_sq = 0.f;
+        if (in_range) {
+            r = __ldg(rec + row);
+            nz = __ldg(zn4 + (int64_t)row0 * (kD / 4) + lane);      // row row0 + (lane >> 3), chunk lane & 7
+            a_sq = __ldg(row_sq + row);
+        }
+        // (fetching the next iteration's record / row with cp.async into a second buffer was measured: no gain, the kernel
+        // is bound by L1 wavefronts -- 70 % of peak in ncu -- not by the latency of these first loads)
+        __syncwarp();                                   // the previous iteration's reads of s_z / s_df are done
         s_z[warp][grp][m] = nz;
         __syncwarp();
-        if (VQ_EXACT_PREFETCH && row0 + groups < T) fetch(row0 + groups);
         const float4* zs = s_z[warp][grp];
-        const bool valid = (row < T) && (h0.x >= 0);
-        auto u64 = [](int lo, int hi) { return (unsigned long long)(uint32_t)lo | ((unsigned long long)(uint32_t)hi << 32); };
-        unsigned long long cur = valid ? u64(h0.z, h0.w) : 0ull;
-        const unsigned long long m1 = valid ? u64(h1.x, h1.y) : 0ull, m2 = valid ? u64(h1.z, h1.w) : 0ull,
-                                 m3 = valid ? u64(h2.x, h2.y) : 0ull;
-        const int gs1 = (h0.x >> 16) & 0x7FFF, gs2 = h0.y & 0xFFFF, gs3 = (h0.y >> 16) & 0x7FFF;
-        int a = 0, g = h0.x & 0xFFFF;
-        const int n_cells = __popcll(cur) + __popcll(m1) + __popcll(m2) + __popcll(m3);
-        const int n_iter = __reduce_max_sync(VQ_FULL, n_cells);
-        Top2 top;
-        top.init();
-#pragma unroll 1
-        for (int c = 0; c < n_iter; ++c) {
-#pragma unroll
-            for (int skip = 0; skip < 3; ++skip)
-                if (cur == 0ull && a < 3) { ++a; cur = (a == 1) ? m1 : (a == 2 ? m2 : m3); g = (a == 1) ? gs1 : (a == 2 ? gs2 : gs3); }
-            if (cur != 0ull) {
-                const int hs = __ffsll((long long)cur) - 1;
-                cur &= cur - 1;
-                const float dist = cell_distance_staged(en32c, csq_cell, g * 64 + hs, m, zs, a_sq);
-                top.add(dist_key(dist, g * kGroupCols + hs + 64 * m));
-            }
+        const bool valid = in_range && ((uint32_t)r.x & 0xFFFFu) != 0xFFFFu;
+        // this lane's best over the row's cells: (ordered distance, code), and the ordered distance of its runner-up
+        uint32_t bo = 0xFFFFFFFFu, so = 0xFFFFFFFFu;
+        int bc = 0x7FFFFFFF;
+        uint32_t w0 = (uint32_t)r.x, w1 = (uint32_t)r.y, w2 = (uint32_t)r.z, w3 = (uint32_t)r.w;
+        int n_cells = 0;
+        while ((w0 & 0xFFFFu) != 0xFFFFu) {             // per group: its own cell count (1 for ~7 rows of 8)
+            const int ci = (int)(w0 & 0xFFFFu);
+            w0 = __funnelshift_r(w0, w1, 16); w1 = __funnelshift_r(w1, w2, 16); w2 = __funnelshift_r(w2, w3, 16);
+            w3 = (w3 >> 16) | 0xFFFF0000u;
+            ++n_cells;
+            const float dist = cell_distance_staged(en32c, csq_cell, ci, m, zs, a_sq);
+            const uint32_t o = dist_ord(dist);
+            const int code = (ci >> 6) * kGroupCols + (ci & 63) + 64 * m;
+            const bool wins = (o < bo) || (o == bo && code < bc);
+            so = wins ? bo : min(so, o);
+            bc = wins ? code : bc;
+            bo = wins ? o : bo;
         }
+        // minimum over the 8 lanes of the group, ties to the lowest code
+        uint32_t omin = bo;
 #pragma unroll
-        for (int off = 4; off > 0; off >>= 1) {
-            const unsigned long long ob = __shfl_xor_sync(VQ_FULL, top.best, off);
-            const float os = __shfl_xor_sync(VQ_FULL, top.second, off);
-            top.merge(ob, os);
-        }
-        const int code = (int)(uint32_t)top.best;
+        for (int off = 4; off > 0; off >>= 1) omin = min(omin, __shfl_xor_sync(VQ_FULL, omin, off));
+        int code = (bo == omin) ? bc : 0x7FFFFFFF;
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) code = min(code, __shfl_xor_sync(VQ_FULL, code, off));
+        // near tie: some other candidate of the row within 1e-6 relative of the best distance
+        const float bd = ord_dist(omin);
+        const float runner = ord_dist((bc == code) ? so : bo);
+        const bool close = valid && (runner - bd < VQ_NEAR_TIE_REL * fabsf(bd));
+        const uint32_t close_ballot = __ballot_sync(VQ_FULL, close);
         // rows of the warp that chose the same code (collapsed codebooks): their histogram count and segment-sum terms
         // are added once, by the first of them -- the L2 serialises reductions per address
         const unsigned same = __match_any_sync(VQ_FULL, valid ? code : -1 - grp);
         const bool dup = __any_sync(VQ_FULL, __popc(same) > 8);        // uniform; false on all but collapsed usage
         const bool lead = valid && (!dup || ((__ffs(same) - 1) >> 3) == grp);
-        if (valid) {
-            if (m == 0) {
-                const float bd = key_dist(top.best);
-                if (cand) cand[row] = code | kCandExactBit;
-                out.idx[row] = code;
-                if (out.hist && lead) atomicAdd(out.hist + code, dup ? __popc(same & 0x01010101u) : 1);
-                if (top.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) counts += kTie;
-                if (n_cells > 1) counts += kMulti;
-            }
+        if (valid && m == 0) {
+            out.idx[row] = code;
+            if (out.hist && lead) atomicAdd(out.hist + code, dup ? __popc(same & 0x01010101u) : 1);
+            if (close_ballot & gmask) counts += kTie;
+            if (n_cells > 1) counts += kMulti;
         }
         if (out.zq) {                                   // uniform
             float4 df = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -649,13 +1043,16 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
     }
     // ---------------- phase B ----------------
     {
-        const int grp = threadIdx.x >> 3;
-        int n = *n_flagged;
-        if (n > flagged_cap) n = flagged_cap;
+        const int grp16 = threadIdx.x >> 3;
+        const int n = *n_flagged;
+        const int n_sliced = min(n, flagged_cap);
         const int n_cells = K / kCellCodes;
         const int per_slice = (n_cells + kFlaggedSlices - 1) / kFlaggedSlices;
-        for (int item = blockIdx.x; item < n * kFlaggedSlices; item += gridDim.x) {
-            const int i = item / kFlaggedSlices, slice = item % kFlaggedSlices;
+        const int n_items = n_sliced * kFlaggedSlices + (n - n_sliced);
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const bool sliced = item < n_sliced * kFlaggedSlices;
+            const int i = sliced ? item / kFlaggedSlices : n_sliced + (item - n_sliced * kFlaggedSlices);
+            const int slice = sliced ? item % kFlaggedSlices : 0;
             const int row = flagged[i];
             __syncthreads();                       // the previous item's shared values are consumed
             if (threadIdx.x < kD / 4) s_z[0][0][threadIdx.x] = __ldg(zn4 + (int64_t)row * (kD / 4) + threadIdx.x);
@@ -664,8 +1061,9 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
             const float a_sq = __ldg(row_sq + row);
             Top2 top;
             top.init();
-            const int c_end = min(n_cells, (slice + 1) * per_slice);
-            for (int ci = slice * per_slice + grp; ci < c_end; ci += kExactThreads / 8) {
+            const int c_begin = sliced ? slice * per_slice : 0;
+            const int c_end = sliced ? min(n_cells, (slice + 1) * per_slice) : n_cells;
+            for (int ci = c_begin + grp16; ci < c_end; ci += kExactThreads / 8) {
                 const float dist = cell_distance_staged(en32c, csq_cell, ci, m, zs, a_sq);
                 top.add(dist_key(dist, (ci >> 6) * kGroupCols + (ci & 63) + 64 * m));
             }
@@ -678,30 +1076,33 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
             if (lane == 0) { s_best[warp] = top.best; s_second[warp] = top.second; }
             __syncthreads();
             if (threadIdx.x == 0) {
-                Top2 all;
-                all.init();
-                for (int w = 0; w < kExactThreads / 32; ++w) all.merge(s_best[w], s_second[w]);
-                FlaggedPartial pp;
-                pp.best = all.best; pp.second = all.second; pp.pad = 0.f;
-                partial[(int64_t)i * kFlaggedSlices + slice] = pp;
-                __threadfence();
-                if (atomicAdd(done + i, 1) == kFlaggedSlices - 1) {
+                Top2 fin;
+                fin.init();
+                for (int w = 0; w < kExactThreads / 32; ++w) fin.merge(s_best[w], s_second[w]);
+                bool last = true;
+                if (sliced) {
+                    FlaggedPartial pp;
+                    pp.best = fin.best; pp.second = fin.second; pp.pad = 0.f;
+                    partial[(int64_t)i * kFlaggedSlices + slice] = pp;
                     __threadfence();
-                    Top2 fin;
-                    fin.init();
-                    for (int w = 0; w < kFlaggedSlices; ++w) {
-                        const FlaggedPartial* q = partial + (int64_t)i * kFlaggedSlices + w;
-                        fin.merge(__ldcg(&q->best), __ldcg(&q->second));
+                    last = atomicAdd(done + i, 1) == kFlaggedSlices - 1;
+                    if (last) {
+                        __threadfence();
+                        fin.init();
+                        for (int w = 0; w < kFlaggedSlices; ++w) {
+                            const FlaggedPartial* q = partial + (int64_t)i * kFlaggedSlices + w;
+                            fin.merge(__ldcg(&q->best), __ldcg(&q->second));
+                        }
+                        done[i] = 0;               // ready for the next call
                     }
+                }
+                if (last) {
                     const float bd = key_dist(fin.best);
                     const int code = (int)(uint32_t)fin.best;
-                    if (cand) cand[row] = code | kCandExactBit;
                     out.idx[row] = code;
                     if (out.hist) atomicAdd(out.hist + code, 1);
                     if (fin.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) counts += kTie;
-                    if (out.zq)
-                        finish_row_serial(zn4, reinterpret_cast<const float4*>(en32), out, K, row, code, loss_fx, bad);
-                    done[i] = 0;                   // ready for the next call
+                    if (out.zq) finish_row_serial(zn4, en4, out, K, row, code, loss_fx, bad);
                 }
             }
         }
@@ -733,29 +1134,29 @@ bool tc16_supported(int64_t T, int K, int D) {
 
 size_t tc16_workspace_bytes(int64_t T) { return (size_t)(T > 0 ? T : 1) * tc16::kRecordBytes; }
 
-cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T, const float* zn32, const float* row_sq,
-                             const CodebookView& cb, int* cand, int* flagged, int* n_flagged, int64_t* stats,
+cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T, const __half* zn16, const float* zn32,
+                             const float* row_sq, const CodebookView& cb, int* cand, int* flagged, int* n_flagged, int64_t* stats,
                              void* records, cudaStream_t s) {
-    const tc16::SmemLayout L = tc16::smem_layout();
-    static const bool service_low = getenv("VQ_TC16_SERVICE_LOW") && atoi(getenv("VQ_TC16_SERVICE_LOW")) != 0;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc16::k_dist_tc16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(tc16::k_dist_tc16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    // VQ_TC16_TS=1: the variant with the token rows in tensor memory (measured slower, see k_dist_tc16_ts)
+    static const bool ss_form = !(getenv("VQ_TC16_TS") && atoi(getenv("VQ_TC16_TS")) != 0);
     int4* rec = static_cast<int4*>(records);
     const int n_row_tiles = (T + tc16::kRowsPerCta - 1) / tc16::kRowsPerCta;
     const int grid = n_row_tiles < sm_count() ? n_row_tiles : sm_count();
     cudaError_t e;
-    if (service_low)
-        e = launch_pdl(tc16::k_dist_tc16<false>, dim3(grid), dim3(tc16::kThreads), L.total + 1024, s, ma, mb, T, cb.K, cb.info, rec,
-                       cand, flagged, n_flagged, stats);
-    else
+    if (ss_form) {
+        const tc16::SmemLayout L = tc16::smem_layout();
+        e = cudaFuncSetAttribute(tc16::k_dist_tc16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
+        if (e != cudaSuccess) return e;
         e = launch_pdl(tc16::k_dist_tc16<true>, dim3(grid), dim3(tc16::kThreads), L.total + 1024, s, ma, mb, T, cb.K, cb.info, rec,
                        cand, flagged, n_flagged, stats);
+    } else {
+        const tc16::SmemLayoutTs L = tc16::smem_layout_ts();
+        // (the attribute is per device: set on every launch, it is a cheap host-side call)
+        e = cudaFuncSetAttribute(tc16::k_dist_tc16_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
+        if (e != cudaSuccess) return e;
+        e = launch_pdl(tc16::k_dist_tc16_ts, dim3(grid), dim3(tc16::kThreads), L.total + 1024, s, mb,
+                       reinterpret_cast<const uint4*>(zn16), T, cb.K, cb.info, rec, flagged, n_flagged, stats);
+    }
     count_launch();
     tc::instrument_report(s, grid);
     return e != cudaSuccess ? e : cudaGetLastError();
@@ -765,7 +1166,7 @@ cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T
 // done_counters: kFlaggedCap zeroed ints; partial_ws: kFlaggedCap * 32 * 16 bytes.  Listed rows beyond kFlaggedCap
 // (degenerate inputs only) are left in cand[] = -1 for the caller's overflow path.
 cudaError_t launch_exact_finish16(const void* records, const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
-                                  const int* flagged, const int* n_flagged, int* done_counters, void* partial_ws, int* cand,
+                                  const int* flagged, const int* n_flagged, int* done_counters, void* partial_ws,
                                   float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats,
                                   cudaStream_t s) {
     const int cap = (int)(T < kFlaggedCap ? T : kFlaggedCap);
@@ -780,7 +1181,7 @@ cudaError_t launch_exact_finish16(const void* records, const float* zn32, const 
     cudaError_t e = launch_pdl(tc16::k_exact_finish16, dim3((unsigned)blocks), dim3(tc16::kExactThreads), 0, s,
                                static_cast<const int4*>(records), zn32, row_sq, cb.en32, reinterpret_cast<const float4*>(cb.en32c),
                                cb.csq_cell, (int)T, cb.K, flagged, n_flagged, cap, static_cast<tc16::FlaggedPartial*>(partial_ws),
-                               done_counters, cand, out, stats);
+                               done_counters, out, stats);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }

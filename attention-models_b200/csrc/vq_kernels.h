@@ -74,7 +74,7 @@ bool tc16_supported(int64_t T, int K, int D);
 constexpr int kFlaggedCap = 4096;     // listed rows that get the sliced per-row search (and a done counter each)
 // exact rescoring of the filter's records + sliced search of the listed rows + the finish pass, one launch
 cudaError_t launch_exact_finish16(const void* records, const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
-                                  const int* flagged, const int* n_flagged, int* done_counters, void* partial_ws, int* cand,
+                                  const int* flagged, const int* n_flagged, int* done_counters, void* partial_ws,
                                   float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats,
                                   cudaStream_t s);
 

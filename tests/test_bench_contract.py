@@ -37,7 +37,7 @@ def test_b200_arm_line_on_gpu():
     d = _run("--steps", "4", "--warmup", "3", "--profile-every", "2")
     assert BASE_KEYS | {"roofline", "cpu_baseline", "clocks", "hbm_side"} <= set(d)
     assert d["metric"] == "vq_tokens_per_sec_fwd_bwd_K8192_D32" and d["n_gpus"] == 1 and d["dtype"] == "f32"
-    assert d["gpu_launches"] >= 4 * 5 and d["value"] > 1e8
+    assert d["gpu_launches"] >= 4 * 4 and d["value"] > 1e8
     r = d["roofline"]
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert r["traffic"] and 0.2 < r["frac"] < 1.0
