@@ -399,6 +399,18 @@ int vq_peer_close(void* dev_ptr) {
     return VQ_OK;
 }
 
+int vq_peer_configure(void* own_buf, int64_t timeout_ms, void* abort_flag, void* stream) {
+    if (!own_buf || timeout_ms < 0) return fail(VQ_ERR_ARG, "bad argument to vq_peer_configure");
+    VQ_CUDA(vq::peer_configure(own_buf, (unsigned long long)timeout_ms * 1000000ull, abort_flag, static_cast<cudaStream_t>(stream)));
+    return VQ_OK;
+}
+
+int vq_peer_resync(void* own_buf, void* stream) {
+    if (!own_buf) return fail(VQ_ERR_ARG, "bad argument to vq_peer_resync");
+    VQ_CUDA(vq::peer_resync(own_buf, static_cast<cudaStream_t>(stream)));
+    return VQ_OK;
+}
+
 int vq_peer_free(void* dev_ptr) {
     if (dev_ptr) VQ_CUDA(cudaFree(dev_ptr));
     return VQ_OK;
@@ -579,8 +591,16 @@ struct HostPipe {
     cudaEvent_t loaded[kMaxChunks], done[kMaxChunks];
     bool ready = false;
 };
-HostPipe g_pipe;
-cudaError_t pipe_init() {
+// one pipe per device (streams and events belong to a device); the host-buffer step of one device is not re-entrant
+// from several host threads at once -- it is a whole-batch call that owns the device for its duration
+constexpr int kMaxDevices = 64;
+HostPipe g_pipes[kMaxDevices];
+HostPipe* current_pipe() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    return &g_pipes[dev];
+}
+cudaError_t pipe_init(HostPipe& g_pipe) {
     if (g_pipe.ready) return cudaSuccess;
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&g_pipe.in, cudaStreamNonBlocking)) != cudaSuccess) return e;
@@ -605,8 +625,10 @@ int vq_host_step(const float* z_host, const float* g_zq_host, int64_t T, const f
     HostArena a = carve_host(dev_arena, T, K, D);
     if (arena_bytes < a.bytes) return fail(VQ_ERR_WORKSPACE, "arena too small: %zu < %zu", arena_bytes, a.bytes);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    VQ_CUDA(pipe_init());
-    HostPipe& p = g_pipe;
+    HostPipe* pipe = current_pipe();
+    if (!pipe) return fail(VQ_ERR_CUDA, "no current CUDA device for vq_host_step");
+    VQ_CUDA(pipe_init(*pipe));
+    HostPipe& p = *pipe;
     const size_t row_bytes = sizeof(float) * (size_t)D;
     const int64_t n_elem = T * D > 0 ? T * D : 1;
     const bool bwd = grad_z_host || grad_weight_host;

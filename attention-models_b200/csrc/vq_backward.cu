@@ -156,11 +156,9 @@ cudaError_t launch_backward_tokens_nchw(const float* g_nchw, const float* zn32, 
     cudaError_t e = cudaSuccess;
     VQ_DISPATCH_D(cb.D, {
         if (smem > 48 * 1024) {
-            static bool configured = false;
-            if (!configured) {
+            static PerDeviceOnce once;
+            if (once.need())
                 e = cudaFuncSetAttribute(k_backward_tokens_nchw<kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                configured = true;
-            }
         }
         if (e == cudaSuccess) k_backward_tokens_nchw<kD><<<blocks, 256, smem, s>>>(g_nchw, zn32, denom, idx, cb.en32, T, hw,
                                                                                    coef_commit, g_loss, grad_nchw);

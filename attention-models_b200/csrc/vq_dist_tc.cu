@@ -690,11 +690,10 @@ static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb
                                     const float* row_sq, const CodebookView& cb, int* cand, int* flagged,
                                     int* n_flagged, int64_t* stats, void* records, void* partial_ws, cudaStream_t s) {
     const tc::SmemLayout L = tc::smem_layout(KB);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(tc::k_dist_tc<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     const int n_row_tiles = (T + tc::kRowsPerCta - 1) / tc::kRowsPerCta;
     const int splits = tc_splits(T, cb.K);

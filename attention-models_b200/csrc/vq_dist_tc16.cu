@@ -1145,15 +1145,20 @@ cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T
     cudaError_t e;
     if (ss_form) {
         const tc16::SmemLayout L = tc16::smem_layout();
-        e = cudaFuncSetAttribute(tc16::k_dist_tc16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
-        if (e != cudaSuccess) return e;
+        static PerDeviceOnce once;
+        if (once.need()) {
+            e = cudaFuncSetAttribute(tc16::k_dist_tc16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
+            if (e != cudaSuccess) return e;
+        }
         e = launch_pdl(tc16::k_dist_tc16<true>, dim3(grid), dim3(tc16::kThreads), L.total + 1024, s, ma, mb, T, cb.K, cb.info, rec,
                        cand, flagged, n_flagged, stats);
     } else {
         const tc16::SmemLayoutTs L = tc16::smem_layout_ts();
-        // (the attribute is per device: set on every launch, it is a cheap host-side call)
-        e = cudaFuncSetAttribute(tc16::k_dist_tc16_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
-        if (e != cudaSuccess) return e;
+        static PerDeviceOnce once;
+        if (once.need()) {
+            e = cudaFuncSetAttribute(tc16::k_dist_tc16_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
+            if (e != cudaSuccess) return e;
+        }
         e = launch_pdl(tc16::k_dist_tc16_ts, dim3(grid), dim3(tc16::kThreads), L.total + 1024, s, mb,
                        reinterpret_cast<const uint4*>(zn16), T, cb.K, cb.info, rec, flagged, n_flagged, stats);
     }

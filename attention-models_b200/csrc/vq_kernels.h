@@ -139,6 +139,8 @@ struct ExchangeLayout {
     size_t results_off, results_hist_off;      // grad_E (K*D fp32) and, results_hist_off behind it, the histogram (K int64)
 };
 ExchangeLayout exchange_layout(int K, int D);
+cudaError_t peer_configure(void* own_buf, unsigned long long timeout_ns, void* abort_flag, cudaStream_t s);
+cudaError_t peer_resync(void* own_buf, cudaStream_t s);
 // token backward (token-major rows) to run in the same launch, behind the exchange's blocks; null: none
 struct TokenBackward {
     const float* g_tok; const float* zn32; const float* denom; const int64_t* idx; int64_t T; float coef_commit; float* grad_tok;
@@ -179,7 +181,20 @@ inline bool dim_supported(int D) { return D >= 16 && D <= 512 && (D & (D - 1)) =
         default: return cudaErrorInvalidValue;                      \
     }
 
-int sm_count();
+int sm_count();          // of the CURRENT device (cached per device)
+
+// Function attributes (opt-in shared memory sizes) are per device: a process that uses several GPUs has to set them on
+// each.  `need()` returns true the first time it is called on the current device.
+struct PerDeviceOnce {
+    unsigned long long done = 0;                 // bit d: configured on device d (d < 64; beyond that: set every time)
+    bool need() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        const unsigned long long bit = 1ull << dev;
+        const unsigned long long before = __atomic_fetch_or(&done, bit, __ATOMIC_RELAXED);
+        return (before & bit) == 0;
+    }
+};
 
 // Programmatic dependent launch (PDL) for the kernels of the step: a kernel launched with launch_pdl may be
 // scheduled while its predecessor in the stream drains (that predecessor calls pdl_trigger()), and must call
@@ -202,6 +217,6 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 // kernel-launch counter (bench.py's gpu_launches); bumped by every launcher next to its <<<>>>
 extern long long g_kernel_launches;
-inline void count_launch(int n = 1) { g_kernel_launches += n; }
+inline void count_launch(int n = 1) { __atomic_fetch_add(&g_kernel_launches, (long long)n, __ATOMIC_RELAXED); }
 
 }  // namespace vq

@@ -38,7 +38,9 @@ namespace {
 constexpr size_t kFlagStride = 128;
 constexpr size_t kReadyOff = 0, kDoneOff = VQ_PEER_MAX_RANKS * kFlagStride, kCounterOff = 2 * VQ_PEER_MAX_RANKS * kFlagStride;
 constexpr size_t kStepOff = kCounterOff + 128;      // device-resident count of completed exchanges of this rank
-constexpr size_t kControlBytes = kCounterOff + 256;
+constexpr size_t kConfigOff = kCounterOff + 256;    // {timeout in ns (0 = default), device-visible address of the host abort flag}
+constexpr size_t kControlBytes = kCounterOff + 512;      // (a multiple of 256: the slots behind it stay 256-byte aligned)
+constexpr unsigned long long kDefaultTimeoutNs = 600ull * 1000ull * 1000ull * 1000ull;   // 10 minutes, the order of NCCL's watchdog
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 }  // namespace
 
@@ -59,6 +61,18 @@ struct PeerPtrs {
     const char* base[VQ_PEER_MAX_RANKS];
 };
 
+// time-out (0 = default) and the device-visible address of a host flag the kernel raises when it gives up
+cudaError_t peer_configure(void* own_buf, unsigned long long timeout_ns, void* abort_flag, cudaStream_t s) {
+    const unsigned long long cfg[2] = {timeout_ns, reinterpret_cast<unsigned long long>(abort_flag)};
+    cudaError_t e = cudaMemcpyAsync(static_cast<char*>(own_buf) + kConfigOff, cfg, sizeof(cfg), cudaMemcpyHostToDevice, s);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(s);      // cfg lives on this stack frame
+}
+// flags, block counter and step count back to zero (the configuration stays); every rank does this between two
+// barriers of the job, with no exchange kernel in flight anywhere
+cudaError_t peer_resync(void* own_buf, cudaStream_t s) {
+    return cudaMemsetAsync(own_buf, 0, kConfigOff, s);
+}
+
 __device__ __forceinline__ long long ld_peer_s64(const long long* p) {
     long long v;
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -77,20 +91,27 @@ __device__ __forceinline__ void st_peer_s64(long long* p, long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 // wait until flags[r] >= epoch for every peer r (warp 0 of the block; returns false on timeout)
 // (with_self: also this rank's own flag -- its last block to finish sets it)
 __device__ __forceinline__ bool wait_flags(const char* own_base, size_t flags_off, int world, int rank, unsigned epoch,
-                                           bool with_self = false) {
+                                           unsigned long long timeout_ns, bool with_self = false) {
     const int lane = threadIdx.x & 31;
     bool ok = true;
     if (lane < world && (with_self || lane != rank)) {
         const unsigned* f = reinterpret_cast<const unsigned*>(own_base + flags_off + (size_t)lane * kFlagStride);
-        const long long t0 = clock64();
+        const unsigned long long t0 = global_ns();
         unsigned v;
+        unsigned spins = 0;
         for (;;) {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
             if ((int)(v - epoch) >= 0) break;
-            if (clock64() - t0 > 6000000000ll) { ok = false; break; }   // ~3 s: a peer died; do not hang the GPU
+            // the wall clock is read every 1024 polls; a peer that never shows up must not hang the GPU for ever
+            if ((++spins & 1023u) == 0 && global_ns() - t0 > timeout_ns) { ok = false; break; }
             __nanosleep(32);
         }
     }
@@ -149,13 +170,39 @@ k_codebook_grad_sharded(PeerPtrs peers, int world, int rank, int one_shot, Excha
         epoch = dev_epoch;
     }
     const size_t slot_off = L.slot0_off + (size_t)slot * L.slot_bytes;
+    unsigned long long timeout_ns = kDefaultTimeoutNs;
+    int* abort_flag = nullptr;
+    if (world > 1) {
+        const unsigned long long* cfg = reinterpret_cast<const unsigned long long*>(own + kConfigOff);
+        if (cfg[0] != 0ull) timeout_ns = cfg[0];
+        abort_flag = reinterpret_cast<int*>(cfg[1]);
+    }
+    // A peer that never publishes its step (it died, or it is further behind than the time-out allows), or a launch that
+    // is out of step with the device-side count, is FATAL for the exchange: the results are poisoned with NaN, the step
+    // count is not advanced (every later launch fails the same way until vq_peer_resync), and the host abort flag is
+    // raised so that the caller finds out without synchronising with the device.
+    auto give_up = [&]() {
+        const float nan = __int_as_float(0x7fc00000);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * D; i += xgrid * blockDim.x) grad[i] = nan;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (loss) loss[0] = nan;
+            if (stats_total) atomicAdd(reinterpret_cast<unsigned long long*>(stats_total + VQ_STAT_PEER_TIMEOUT), 1ull);
+            if (abort_flag) {
+                *reinterpret_cast<volatile int*>(abort_flag) = 1;
+                __threadfence_system();
+            }
+        }
+    };
     // ---- 1. partials ready everywhere ----
     if (world > 1) {
+        __shared__ int s_timed_out;
         if (threadIdx.x < 32) {
-            if (blockIdx.x == 0) publish_flags(peers, kReadyOff, world, rank, epoch);
-            timed_out |= !wait_flags(own, kReadyOff, world, rank, epoch);
+            if (blockIdx.x == 0 && !timed_out) publish_flags(peers, kReadyOff, world, rank, epoch);
+            if (!timed_out) timed_out = !wait_flags(own, kReadyOff, world, rank, epoch, timeout_ns);
+            if (threadIdx.x == 0) s_timed_out = timed_out;
         }
         __syncthreads();
+        if (s_timed_out) { give_up(); return; }
     }
 #ifdef VQ_PEER_TRACE
     tr[1] = now();
@@ -286,8 +333,6 @@ k_codebook_grad_sharded(PeerPtrs peers, int world, int rank, int one_shot, Excha
             loss[0] = loss_from_fixed(tot[VQ_STAT_LOSS_FIXED], tot[VQ_STAT_NONFINITE], n_elem_total, form, beta);
     }
     if (local_out) {
-        if (timed_out && threadIdx.x == 0 && stats_total)
-            atomicAdd(reinterpret_cast<unsigned long long*>(stats_total + VQ_STAT_PEER_TIMEOUT), 1ull);
         if (world > 1) {                                 // the last block to get here closes the step
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -321,11 +366,11 @@ k_codebook_grad_sharded(PeerPtrs peers, int world, int rank, int one_shot, Excha
         // "done" includes this rank's own flag: a block whose peers finished early must still wait for the other blocks
         // of its own rank, which write the rank's slice into the same results buffer
         if (s_last) publish_flags(peers, kDoneOff, world, rank, epoch, true);
-        timed_out |= !wait_flags(own, kDoneOff, world, rank, epoch, true);
-        if (timed_out && lane == 0 && stats_total)
-            atomicAdd(reinterpret_cast<unsigned long long*>(stats_total + VQ_STAT_PEER_TIMEOUT), 1ull);
+        timed_out = !wait_flags(own, kDoneOff, world, rank, epoch, timeout_ns, true);
+        if (threadIdx.x == 0) s_last = timed_out;            // (reused: "this block gave up")
     }
     __syncthreads();
+    if (s_last) { give_up(); return; }
 #ifdef VQ_PEER_TRACE
     tr[3] = now();
 #endif

@@ -19,17 +19,14 @@ bool pdl_enabled() {
     static const bool on = getenv("VQ_PDL") && atoi(getenv("VQ_PDL")) != 0;
     return on;
 }
-static int g_sm_count = 0;
+static int g_sm_count[64] = {0};
 int sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            g_sm_count = n;
-        else
-            return 148;
-    }
-    return g_sm_count;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64 && g_sm_count[dev] > 0) return g_sm_count[dev];
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    if (dev >= 0 && dev < 64) g_sm_count[dev] = n;
+    return n;
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

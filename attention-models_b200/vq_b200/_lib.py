@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("VQ_B200_LIB") or os.path.join(_PKG_DIR, "lib", "libvq
 BUILD_SCRIPT = os.path.join(_PKG_DIR, "csrc", "build.py")
 
 # constants mirrored from include/vq_b200.h
-ABI_VERSION = 3
+ABI_VERSION = 4
 FORM_VIT, FORM_VQGAN = 0, 1
 LAYOUT_TOKEN_MAJOR, LAYOUT_NCHW = 0, 1
 FLAG_INDICES_ONLY, FLAG_EXACT_SCAN, FLAG_KEEP_STATS = 1, 2, 4
@@ -53,6 +53,8 @@ SIGNATURES = {
     "vq_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
     "vq_peer_close": (c_int, [c_void_p]),
     "vq_peer_free": (c_int, [c_void_p]),
+    "vq_peer_configure": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "vq_peer_resync": (c_int, [c_void_p, c_void_p]),
     "vq_backward_codebook_sharded": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, ctypes.c_uint32, c_void_p, c_int, c_int,
                                              c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p]),

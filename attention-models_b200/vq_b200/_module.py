@@ -34,8 +34,23 @@ class _CodebookBase(nn.Module):
         self.last_stats: Optional[torch.Tensor] = None
         self._prepared: Optional[F_vq.PreparedCodebook] = None
 
-    # the prepared codebook is a cache keyed on the weight's storage and version counter: a frozen
-    # tokeniser (MaskGIT / Muse / Parti) prepares once, a training step re-prepares after each update
+    # The prepared codebook (unit codes, fp16 copy, ...) is a cache keyed on the weight's storage and version counter: a
+    # frozen tokeniser (MaskGIT / Muse / Parti) prepares once.  A forward that can train the codebook never trusts the
+    # cache (the refill rides in its first launch for free).  What the version counter cannot see is an edit through
+    # `embedding.weight.data` (the reference's own init idiom, `weights_init`, codebook restarts) made while the module
+    # is used for inference only: call invalidate_codebook() after such an edit.  load_state_dict() and .to() / .cuda()
+    # invalidate by themselves.
+    def invalidate_codebook(self) -> None:
+        self._prepared = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._prepared = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._prepared = None
+        return super()._apply(fn, *args, **kwargs)
+
     def _prepared_codebook(self) -> F_vq.PreparedCodebook:
         w = self.embedding.weight
         if self._prepared is None or not self._prepared.matches(w):
@@ -47,10 +62,12 @@ class _CodebookBase(nn.Module):
         w = self.embedding.weight
         if self._prepared is None or not self._prepared.fits(w):
             self._prepared = F_vq.prepare_codebook(w)
+        trainable = torch.is_grad_enabled() and w.requires_grad
         z_q, flat_idx, loss, hist, stats = F_vq.quantise(z, self.embedding.weight, self.form, self.beta,
                                                          prepared=self._prepared,
                                                          exact_scan=self.exact_scan,
-                                                         sorted_segments=self.sorted_segments)
+                                                         sorted_segments=self.sorted_segments,
+                                                         always_refresh=trainable)
         self.last_histogram, self.last_stats = hist, stats
         return z_q, flat_idx, loss
 

@@ -79,13 +79,39 @@ def shard_batch(x: torch.Tensor, rank: int, world_size: int) -> torch.Tensor:
     return x[rank * per:(rank + 1) * per]
 
 
+class PeerTimeoutError(RuntimeError):
+    """The fused exchange gave up waiting for a peer (or was launched out of step): the codebook gradient and loss of
+    that step are NaN on this rank and the exchange stays dead until every rank calls ``resync()``."""
+
+
+def _unmap_exchange(ptrs, rank, device_index):
+    """Best-effort clean-up when a PeerExchange is dropped without the collective close(): unmap the peers' buffers and
+    free the own one, no barriers (a peer that still reads this rank's buffer has a bug of its own by then)."""
+    try:
+        lib = _lib.load()
+        with torch.cuda.device(device_index):
+            torch.cuda.synchronize()
+            for r, p in enumerate(ptrs):
+                if p and r != rank:
+                    lib.vq_peer_close(p)
+            if ptrs and ptrs[rank]:
+                lib.vq_peer_free(ptrs[rank])
+    except Exception:       # interpreter shutdown: the driver reclaims everything anyway
+        pass
+
+
 class PeerExchange:
     """Exchange buffers of all ranks of `group`, mapped into this process (CUDA IPC over NVLink).
 
     `torch.distributed` only carries the 64-byte IPC handles at set-up; the data path is the library's own
-    kernel reading peer memory."""
+    kernel reading peer memory.
 
-    def __init__(self, K: int, D: int, device: torch.device, group=None):
+    ``timeout_s``: how long the exchange kernel waits for a peer's step before it gives up (None: the library default
+    of 10 minutes).  Giving up is fatal and loud: NaN results, ``abort_flag`` raised (a pinned host int the kernel
+    writes; ``raise_if_aborted()`` reads it without a device synchronisation), every later step fails until the
+    collective ``resync()``."""
+
+    def __init__(self, K: int, D: int, device: torch.device, group=None, timeout_s: Optional[float] = None):
         lib = _lib.load()
         self.K, self.D, self.device, self.group = K, D, device, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -115,7 +141,39 @@ class PeerExchange:
                     self.ptrs.append(p.value)
         self.ptr_array = (ctypes.c_void_p * self.world)(*self.ptrs)
         self._slots = [self._slot_pointers(s) for s in (0, 1)]
+        # pinned host memory is device-visible at the same address (unified addressing): the kernel raises this flag
+        self.abort_flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+        timeout_ms = 0 if timeout_s is None else max(1, int(timeout_s * 1000))
+        with torch.cuda.device(device):
+            _lib.check(lib.vq_peer_configure(self.ptrs[self.rank], timeout_ms, self.abort_flag.data_ptr(),
+                                             torch.cuda.current_stream(device).cuda_stream))
+        import weakref
+        self._ptr_holder = list(self.ptrs)          # what the finalizer unmaps if close() never ran
+        self._finalizer = weakref.finalize(self, _unmap_exchange, self._ptr_holder, self.rank,
+                                           device.index if device.index is not None else torch.cuda.current_device())
         dist.barrier(group=group)          # every rank mapped every buffer before the first kernel publishes into it
+
+    def aborted(self) -> bool:
+        return bool(self.abort_flag[0].item())      # a host read of pinned memory: no device synchronisation
+
+    def raise_if_aborted(self) -> None:
+        if self.aborted():
+            raise PeerTimeoutError(
+                f"rank {self.rank}: the peer exchange of step {self.epoch} gave up (a peer did not publish its partials in "
+                "time, or the launches went out of step); grad_weight / loss of that step are NaN.  Call resync() on "
+                "every rank (collective) to restart the exchange, or fall back to exchange='collective'.")
+
+    def resync(self) -> None:
+        """Collective: restart the exchange after a time-out (every rank, no step in flight)."""
+        lib = _lib.load()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.vq_peer_resync(self.ptrs[self.rank], torch.cuda.current_stream(self.device).cuda_stream))
+            torch.cuda.synchronize(self.device)
+        self.abort_flag.zero_()
+        self.epoch = 0
+        dist.barrier(group=self.group)
 
     def _slot_pointers(self, slot: int):
         seg, stats, hist = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
@@ -142,6 +200,8 @@ class PeerExchange:
             dist.barrier(group=self.group)
             _lib.check(lib.vq_peer_free(self.ptrs[self.rank]))
         self.ptrs = []
+        self._ptr_holder.clear()           # nothing left for the finalizer
+        self._finalizer.detach()
 
 
 class ShardedQuantiser:
@@ -152,8 +212,10 @@ class ShardedQuantiser:
     """
 
     def __init__(self, form: str = "vit", beta: float = 0.25, world_size: Optional[int] = None,
-                 exact_scan: bool = False, group=None, exchange: str = "peer", graphs: bool = False):
+                 exact_scan: bool = False, group=None, exchange: str = "peer", graphs: bool = False,
+                 peer_timeout_s: Optional[float] = None):
         self.form, self.beta, self.group, self.exact_scan = form, float(beta), group, exact_scan
+        self.peer_timeout_s = peer_timeout_s      # None: the library default (10 minutes); see PeerExchange
         if world_size is None:
             world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         if exchange not in ("peer", "collective"):
@@ -203,7 +265,7 @@ class ShardedQuantiser:
                 "buf": pack.allocate(dev),
             }
             if self.world_size > 1 and self.exchange == "peer":
-                plan["peer"] = PeerExchange(K, D, dev, self.group)
+                plan["peer"] = PeerExchange(K, D, dev, self.group, timeout_s=self.peer_timeout_s)
                 plan["side"] = torch.cuda.Stream(dev)
                 plan["ev_fwd"], plan["ev_x"] = torch.cuda.Event(), torch.cuda.Event()
             self._plans[key] = plan
@@ -217,8 +279,22 @@ class ShardedQuantiser:
                 plan["peer"].close()
         self._plans.clear()
 
+    def resync(self) -> None:
+        """Collective: restart the peer exchange of every plan after a PeerTimeoutError."""
+        self._graphs.clear()
+        self._warmed.clear()
+        for plan in self._plans.values():
+            if "peer" in plan:
+                plan["peer"].resync()
+
     def step(self, z: torch.Tensor, upstream: Optional[torch.Tensor], weight: torch.Tensor,
              eager: bool = False) -> Dict[str, torch.Tensor]:
+        # a time-out of an earlier step's exchange is reported here, at the latest one step later (the kernel raises a
+        # pinned host flag; reading it does not synchronise with the device)
+        for plan in self._plans.values():
+            peer = plan.get("peer")
+            if peer is not None:
+                peer.raise_if_aborted()
         # a graph is tied to buffer addresses: only caller-owned contiguous buffers qualify (a .contiguous() copy would
         # be a fresh address on every call), and the cache is bounded
         if (not self.graphs or eager or not self._graph_capable() or not z.is_contiguous() or not weight.is_contiguous()

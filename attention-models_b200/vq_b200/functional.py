@@ -106,6 +106,10 @@ class _Quantise(torch.autograd.Function):
                if ctx.needs_input_grad[1] and not sorted_segments else None)
         ws_bytes = _lib.size_query("vq_workspace_bytes", T, K, D, flags)
         ws = _scratch(ws_bytes, dev)
+        if refresh and need_grad:
+            # an earlier forward whose backward has not run yet saved the old blob: refill a fresh one instead of
+            # rewriting that one in place (autograd's version counters cannot see a write made by the library)
+            prepared.blob = torch.empty_like(prepared.blob)
         with torch.cuda.device(dev):
             # refresh: the weights changed since `prepared` was filled -- the forward re-prepares the codebook itself
             # (in the launch that normalises the token rows where the shape allows)
@@ -117,8 +121,9 @@ class _Quantise(torch.autograd.Function):
         if refresh:
             prepared.mark_current(weight)
         if need_grad:
-            ctx.save_for_backward(saved_zn, saved_denom, idx, prepared.blob, hist)
-        ctx.seg = seg
+            ctx.save_for_backward(saved_zn, saved_denom, idx, prepared.blob, hist,
+                                  seg if seg is not None else saved_denom.new_empty(0))
+        ctx.has_seg = seg is not None
         ctx.meta = (form, float(beta), layout, T, hw, K, D, n_total, tuple(z.shape))
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(idx, hist, stats)
@@ -128,7 +133,7 @@ class _Quantise(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g_zq, g_idx, g_loss, g_hist, g_stats):
         lib = _lib.load()
-        saved_zn, saved_denom, idx, blob, hist = ctx.saved_tensors
+        saved_zn, saved_denom, idx, blob, hist, seg_saved = ctx.saved_tensors
         form, beta, layout, T, hw, K, D, n_total, z_shape = ctx.meta
         dev = saved_zn.device
         want_z, want_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
@@ -136,7 +141,7 @@ class _Quantise(torch.autograd.Function):
             g_zq = g_zq.contiguous().float()
         g_loss = torch.zeros(1, dtype=torch.float32, device=dev) if g_loss is None else g_loss.reshape(1).float()
         grad_z = torch.empty(z_shape, dtype=torch.float32, device=dev) if want_z else None
-        seg, from_forward = ctx.seg, ctx.seg is not None
+        seg, from_forward = (seg_saved if ctx.has_seg else None), ctx.has_seg
         if want_w and seg is None:
             seg = torch.empty(K * D + K, dtype=torch.int64, device=dev)
         grad_w = torch.empty(K, D, dtype=torch.float32, device=dev) if want_w else None
@@ -168,7 +173,7 @@ def _as_fp32_input(z: torch.Tensor) -> torch.Tensor:
 
 def quantise(z: torch.Tensor, weight: torch.Tensor, form: str = "vit", beta: float = 0.25,
              prepared: Optional[PreparedCodebook] = None, exact_scan: bool = False,
-             n_elem_total: Optional[int] = None, sorted_segments: bool = False):
+             n_elem_total: Optional[int] = None, sorted_segments: bool = False, always_refresh: bool = False):
     """Full forward.  Returns ``(z_q, flat_indices, loss, histogram, stats)``.
 
     ``z``: (..., D) for ``form='vit'`` (token-major) or (b, D, h, w) for ``form='vqgan'``.
@@ -179,8 +184,10 @@ def quantise(z: torch.Tensor, weight: torch.Tensor, form: str = "vit", beta: flo
     refresh = False
     if prepared is None or not prepared.fits(weight):
         prepared = prepare_codebook(weight)
-    elif not prepared.matches(weight):
-        refresh = True                      # stale contents, right size: vq_forward refills the blob (no extra launch)
+    elif always_refresh or not prepared.matches(weight):
+        # stale (or not provably current: an edit through `weight.data` leaves the version counter alone) contents of the
+        # right size: vq_forward refills the blob in the launch that normalises the rows (no extra launch)
+        refresh = True
     layout = LAYOUT_TOKEN_MAJOR if form == "vit" else LAYOUT_NCHW
     flags = FLAG_EXACT_SCAN if exact_scan else 0
     return _Quantise.apply(_as_fp32_input(z), weight, prepared, FORMS[form], beta, layout, flags, n_elem_total,

@@ -12,7 +12,9 @@
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in _host
  *   - all arrays are caller-allocated; the library owns no device memory (vq_peer_alloc allocates the
  *     IPC-exportable exchange buffer on the caller's explicit request; the caller frees it)
- *   - every call is asynchronous on `stream` (a cudaStream_t) and re-entrant per stream
+ *   - every call is asynchronous on `stream` (a cudaStream_t) and re-entrant per stream and per device; the two
+ *     exceptions keep per-device state inside the library and are single-caller: vq_host_step (its copy streams and
+ *     events) and the vq_profile_* measurement hooks (process-global event lists)
  *   - return value: 0 = OK, non-zero = error; vq_last_error() gives the message (thread-local)
  *   - nothing throws across the ABI; there is NO CPU fallback: without a CUDA device every compute
  *     call returns VQ_ERR_CUDA
@@ -30,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 3
+#define VQ_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define VQ_API __attribute__((visibility("default")))
@@ -66,8 +68,9 @@ extern "C" {
 #define VQ_STAT_LOSS_FIXED      3 /* sum over tokens of sum_j (q - zn)^2, fixed point 2^-24      */
 #define VQ_STAT_BAD_INDEX       4 /* vq_gather: count of out-of-range indices                    */
 #define VQ_STAT_NONFINITE       5 /* non-finite loss partials (NaN/Inf rows): the loss is NaN     */
-#define VQ_STAT_PEER_TIMEOUT    6 /* sharded backward: a peer never published its step, or the caller's
-                                     slot / epoch is out of step with the device's count            */
+#define VQ_STAT_PEER_TIMEOUT    6 /* sharded backward gave up: a peer never published its step within the time-out, or
+                                     the caller's slot / epoch is out of step with the device's count; grad_weight
+                                     and loss of that call are NaN (see vq_peer_configure)            */
 #define VQ_STATS_LEN            8
 
 VQ_API int         vq_abi_version(void);
@@ -188,6 +191,16 @@ VQ_API int vq_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out);
 VQ_API int vq_peer_open(const void* ipc_handle, void** dev_ptr);
 VQ_API int vq_peer_close(void* dev_ptr);
 VQ_API int vq_peer_free(void* dev_ptr);
+/* Time-out and failure reporting of the exchange.  A rank waits at most `timeout_ms` (0 = the default, 10 minutes --
+ * the order of a collective library's watchdog) for a peer to publish its step.  Giving up is FATAL for the exchange,
+ * never silent: the launch writes NaN into grad_weight and loss, bumps stats_total[VQ_STAT_PEER_TIMEOUT], does not
+ * advance the device-side step count (every later launch on this buffer fails the same way) and stores 1 into
+ * `*abort_flag` -- an int in pinned, device-visible HOST memory that the caller polls without synchronising (NULL: none).
+ * A launch whose slot / epoch disagrees with the device-side count is treated the same way.  Recovery is collective:
+ * with no exchange kernel in flight on any rank, every rank calls vq_peer_resync on its own buffer between two
+ * barriers of the job (flags, counters and the step count return to zero; the next call is step 1, slot 0).     */
+VQ_API int vq_peer_configure(void* own_exchange_buf, int64_t timeout_ms, void* abort_flag, void* stream);
+VQ_API int vq_peer_resync(void* own_exchange_buf, void* stream);
 VQ_API int vq_backward_codebook_sharded(const void* const* peer_bufs, int world, int rank, int slot, uint32_t epoch,
                                         const void* cb, int K, int D, int form, float beta, const float* g_loss,
                                         int64_t n_elem_total, float* grad_weight, int64_t* hist_total, float* loss,
