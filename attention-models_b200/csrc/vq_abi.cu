@@ -510,6 +510,42 @@ int vq_token_embed(const int64_t* tokens, const uint8_t* mask, int64_t T, int64_
     return VQ_OK;
 }
 
+int vq_token_embed_causal(const int64_t* tokens, int64_t T, int64_t n_per_seq, const float* table, int64_t vocab, int dim,
+                          const float* pos, const float* start, float* embeds, int64_t* stats, void* stream) {
+    if (T < 0 || T >= (1ll << 40) || n_per_seq <= 0 || T % n_per_seq != 0)
+        return fail(VQ_ERR_ARG, "vq_token_embed_causal needs T a multiple of n_per_seq > 0 (T=%lld)", (long long)T);
+    if (!tokens || !table || !start || !embeds || vocab <= 0 || dim <= 0 || dim % 4 != 0)
+        return fail(VQ_ERR_ARG, "vq_token_embed_causal needs tokens, a (vocab, dim) table with dim %% 4 == 0, start and embeds");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (stats) VQ_CUDA(cudaMemsetAsync(stats + VQ_STAT_BAD_INDEX, 0, sizeof(int64_t), s));
+    VQ_CUDA(vq::launch_token_embed(tokens, nullptr, T, n_per_seq, 0, 0, table, vocab, dim, pos, embeds, nullptr, nullptr, stats, s, start));
+    return VQ_OK;
+}
+
+int vq_embedding_backward_bytes(int64_t vocab, int dim, size_t* out) {
+    if (!out || vocab <= 0 || dim <= 0) return fail(VQ_ERR_ARG, "bad argument to vq_embedding_backward_bytes");
+    *out = vq::embedding_backward_bytes(vocab, dim);
+    return VQ_OK;
+}
+
+int vq_embedding_backward(const int64_t* ids, int64_t n_ids, int64_t ids_per_seq, int64_t rows_per_seq, int64_t row_shift,
+                          const float* grad_out, int64_t n_rows, int64_t hw, int64_t vocab, int dim, const void* cb,
+                          float* grad_table, void* ws, size_t ws_bytes, void* stream) {
+    if (n_ids < 0 || n_rows < 0 || vocab <= 0 || dim <= 0 || dim % 4 != 0)
+        return fail(VQ_ERR_ARG, "bad sizes for vq_embedding_backward (dim must be a multiple of 4)");
+    if ((n_ids > 0 && !ids) || (n_rows > 0 && !grad_out) || !grad_table) return fail(VQ_ERR_ARG, "ids / grad_out / grad_table is NULL");
+    if (hw < 0 || (hw > 0 && n_ids % hw != 0)) return fail(VQ_ERR_ARG, "NCHW gradient needs hw dividing the id count");
+    if (!ws || ws_bytes < vq::embedding_backward_bytes(vocab, dim)) return fail(VQ_ERR_WORKSPACE, "embedding backward workspace too small");
+    vq::CodebookView cbv;
+    if (cb) {
+        if (int r = check_dims(0, (int)vocab, dim)) return r;
+        cbv = vq::codebook_view(const_cast<void*>(cb), (int)vocab, dim);
+    }
+    VQ_CUDA(vq::launch_embedding_backward(ids, n_ids, ids_per_seq, rows_per_seq, row_shift, grad_out, n_rows, hw, vocab, dim,
+                                          cb ? &cbv : nullptr, grad_table, ws, static_cast<cudaStream_t>(stream)));
+    return VQ_OK;
+}
+
 int64_t vq_kernel_launches(void) { return (int64_t)vq::g_kernel_launches; }
 
 int vq_profile_begin(int sample_every, unsigned slot_mask) {

@@ -130,7 +130,13 @@ cudaError_t launch_codebook_grad(const int64_t* seg_sums, const CodebookView& cb
 // ---- vq_tokens.cu ---------------------------------------------------------------------------
 cudaError_t launch_token_embed(const int64_t* tokens, const uint8_t* mask, int64_t T, int64_t n_per_seq, int64_t mask_token_id,
                                int64_t ignore_index, const float* table, int64_t V, int dim, const float* pos, float* embeds,
-                               int64_t* input_ids, int64_t* labels, int64_t* stats, cudaStream_t s);
+                               int64_t* input_ids, int64_t* labels, int64_t* stats, cudaStream_t s, const float* start = nullptr);
+// grad_table[id] += grad_out[row]: integer-accumulated (deterministic) embedding backward; `normalised` != null applies the
+// backward of l2norm(E[k]) on top (grad_table is then the codebook gradient, V == K, dim == D)
+size_t embedding_backward_bytes(int64_t V, int dim);
+cudaError_t launch_embedding_backward(const int64_t* ids, int64_t n_ids, int64_t ids_per_seq, int64_t rows_per_seq,
+                                      int64_t row_shift, const float* grad_out, int64_t n_rows, int64_t hw, int64_t V, int dim,
+                                      const CodebookView* normalised, float* grad_table, void* ws, cudaStream_t s);
 
 // ---- vq_peer.cu ------------------------------------------------------------------------------
 // byte layout of one rank's exchange buffer (see vq_peer.cu); offsets of stats / hist are relative to the slot

@@ -65,6 +65,11 @@ SIGNATURES = {
                           c_void_p, c_void_p]),
     "vq_token_embed": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vq_token_embed_causal": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
+    "vq_embedding_backward_bytes": (c_int, [c_int64, c_int, POINTER(c_size_t)]),
+    "vq_embedding_backward": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vq_kernel_launches": (c_int64, []),
     "vq_profile_begin": (c_int, [c_int, ctypes.c_uint32]),
     "vq_profile_end": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64), POINTER(c_int64)]),

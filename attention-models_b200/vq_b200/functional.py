@@ -220,39 +220,90 @@ def encode_indices(z: torch.Tensor, weight: torch.Tensor, form: str = "vit",
     return (idx, hist) if want_hist else idx
 
 
-@torch.no_grad()
+def _embedding_backward(ids: torch.Tensor, grad_out: torch.Tensor, vocab: int, dim: int, *, ids_per_seq: int = 0,
+                        rows_per_seq: int = 0, row_shift: int = 0, hw: int = 0,
+                        prepared: Optional[PreparedCodebook] = None) -> torch.Tensor:
+    """grad_table (vocab, dim) of a lookup, through vq_embedding_backward (integer-accumulated: deterministic)."""
+    dev = grad_out.device
+    g = grad_out.contiguous().float()
+    ids = ids.contiguous()
+    n_rows = g.numel() // dim
+    out = torch.empty(vocab, dim, dtype=torch.float32, device=dev)
+    ws_bytes = _lib.size_query("vq_embedding_backward_bytes", vocab, dim)
+    ws = _scratch(ws_bytes, dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().vq_embedding_backward(_ptr(ids), ids.numel(), ids_per_seq, rows_per_seq, row_shift, _ptr(g), n_rows,
+                                                     hw, vocab, dim, None if prepared is None else _ptr(prepared.blob), _ptr(out),
+                                                     _ptr(ws), ws_bytes, _stream(dev)))
+    return out
+
+
+class _Decode(torch.autograd.Function):
+    """indices -> embeddings, differentiable w.r.t. the codebook weights like the reference's nn.Embedding lookup
+    (models/vitvqgan.py:173-176: the gradient also passes through the l2 normalisation; models/vqgan.py:178-182)."""
+
+    @staticmethod
+    def forward(ctx, weight, idx, form, prepared, stats):
+        lib = _lib.load()
+        dev = idx.device
+        K, D = weight.shape
+        T = idx.numel()
+        w = weight.detach().contiguous()
+        if form == "vit":
+            out = torch.empty(*idx.shape, D, dtype=torch.float32, device=dev)
+            args = (_ptr(idx), T, 0, None, _ptr(prepared.blob), K, D, 1, LAYOUT_TOKEN_MAJOR)
+        else:
+            b, n = idx.shape
+            side = int(n ** 0.5)
+            out = torch.empty(b, D, side, side, dtype=torch.float32, device=dev)
+            args = (_ptr(idx), T, n, _ptr(w), None, K, D, 0, LAYOUT_NCHW)
+        with torch.cuda.device(dev):
+            _lib.check(lib.vq_gather(*args, _ptr(out), _ptr(stats), _stream(dev)))
+        ctx.form, ctx.prepared, ctx.shape = form, prepared, (K, D)
+        ctx.save_for_backward(idx)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        K, D = ctx.shape
+        if ctx.form == "vit":
+            gw = _embedding_backward(idx, g, K, D, prepared=ctx.prepared)
+        else:
+            gw = _embedding_backward(idx, g, K, D, hw=idx.shape[1])
+        return gw, None, None, None, None
+
+
 def indices_to_embeddings(indices: torch.Tensor, weight: torch.Tensor, form: str = "vit",
                           prepared: Optional[PreparedCodebook] = None, check_indices: bool = True) -> torch.Tensor:
     """Decode gather (reference vitvqgan.py:173-176: l2norm(E[i]); vqgan.py:178-182: E[i] as (b, D, h, w)).
 
     ``indices``: (b, n) integer tensor.  Out-of-range indices raise IndexError like the reference's CPU
-    path (one host sync for the check; pass ``check_indices=False`` to skip it).  Not differentiable.
+    path (one host sync for the check; pass ``check_indices=False`` to skip it).  Differentiable with respect to
+    ``weight`` (as the reference's ``nn.Embedding`` lookup is) when gradients are enabled and it requires them.
     """
     _require_cuda(indices, "indices")
     _require_cuda(weight, "the codebook weight")
-    lib = _lib.load()
     dev = indices.device
     idx = indices.to(torch.int64).contiguous()
-    K, D = weight.shape
-    T = idx.numel()
-    stats = torch.zeros(STATS_LEN, dtype=torch.int64, device=dev)
-    w = weight.detach().contiguous()
     if form == "vit":
         if prepared is None or not prepared.matches(weight):
             prepared = prepare_codebook(weight)
-        out = torch.empty(*idx.shape, D, dtype=torch.float32, device=dev)
-        args = (_ptr(idx), T, 0, None, _ptr(prepared.blob), K, D, 1, LAYOUT_TOKEN_MAJOR)
     else:
         if idx.dim() != 2:
             raise ValueError("vqgan indices_to_embeddings expects (b, n) indices")
-        b, n = idx.shape
+        n = idx.shape[1]
         side = int(n ** 0.5)
         if side * side != n:   # einops.rearrange in the reference fails the same way
             raise ValueError(f"n={n} is not a perfect square")
-        out = torch.empty(b, D, side, side, dtype=torch.float32, device=dev)
-        args = (_ptr(idx), T, n, _ptr(w), None, K, D, 0, LAYOUT_NCHW)
-    with torch.cuda.device(dev):
-        _lib.check(lib.vq_gather(*args, _ptr(out), _ptr(stats), _stream(dev)))
+        prepared = None
+    stats = torch.zeros(STATS_LEN, dtype=torch.int64, device=dev)
+    if torch.is_grad_enabled() and weight.requires_grad:
+        out = _Decode.apply(weight, idx, form, prepared, stats)
+    else:
+        with torch.no_grad():
+            out = _Decode.apply(weight, idx, form, prepared, stats)
     if check_indices and int(stats[_lib.STAT_BAD_INDEX].item()) != 0:
         raise IndexError("index out of range in self")
     return out

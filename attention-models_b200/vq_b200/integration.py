@@ -1,23 +1,50 @@
 """Swap the reference's quantiser for this one inside an already-built reference model."""
 from __future__ import annotations
 
+import types
+from typing import Optional
+
 import torch.nn as nn
 
 
-def patch_reference_model(model: nn.Module) -> nn.Module:
+def _encode_imgs_vit(self, imgs):
+    """models/vitvqgan.py:204-210 with the quantiser's indices-only path: encoder -> pre_quant -> indices (b, n)."""
+    enc_imgs = self.pre_quant(self.encoder(imgs))
+    return self.codebook.encode(enc_imgs)
+
+
+def _encode_imgs_vqgan(self, imgs):
+    """models/vqgan.py:245-251 with the quantiser's indices-only path; ``rearrange(indices, '(b i) -> b i', b=b)``."""
+    b = imgs.shape[0]
+    enc_imgs = self.pre_quant(self.encoder(imgs))
+    return self.codebook.encode(enc_imgs).view(b, -1)
+
+
+def patch_reference_model(model: nn.Module, form: Optional[str] = None, fast_encode: bool = True) -> nn.Module:
     """Replace ``model.codebook`` (a reference ``Codebook`` from models/vitvqgan.py or models/vqgan.py)
     by the B200 drop-in carrying the same weights, ``beta`` and sizes.  The wrappers' call sites
     (vitvqgan.py:193,200,208; vqgan.py:234,241,249) keep working unchanged.  Returns ``model``.
+
+    ``form``: "vit" or "vqgan"; by default taken from the module the old codebook's class lives in.
+    ``fast_encode``: also rebind ``model.encode_imgs`` so that tokenisation (what MaskGIT / Muse / Parti call) takes the
+    indices-only path of the quantiser (VQ_FLAG_INDICES_ONLY: no z_q, no loss, nothing saved) instead of running the
+    whole forward and dropping two of its three results; same indices, same shape.
     """
     from . import vitvqgan, vqgan
 
     old = model.codebook
-    ref_module = type(old).__module__
-    cls = vqgan.Codebook if ref_module.endswith("vqgan") and not ref_module.endswith("vitvqgan") else vitvqgan.Codebook
+    if form is None:
+        ref_module = type(old).__module__
+        form = "vqgan" if ref_module.endswith("vqgan") and not ref_module.endswith("vitvqgan") else "vit"
+    if form not in ("vit", "vqgan"):
+        raise ValueError("form must be 'vit' or 'vqgan'")
+    cls = vqgan.Codebook if form == "vqgan" else vitvqgan.Codebook
     new = cls(old.codebook_size, old.codebook_dim, getattr(old, "beta", 0.25))
     new.embedding.load_state_dict(old.embedding.state_dict())
     new.to(old.embedding.weight.device)
     new.embedding.weight.requires_grad_(old.embedding.weight.requires_grad)
     new.train(old.training)
     model.codebook = new
+    if fast_encode and all(hasattr(model, a) for a in ("encoder", "pre_quant", "encode_imgs")):
+        model.encode_imgs = types.MethodType(_encode_imgs_vqgan if form == "vqgan" else _encode_imgs_vit, model)
     return model

@@ -229,12 +229,35 @@ VQ_API int vq_gather(const int64_t* idx, int64_t T, int64_t hw, const float* wei
  *   labels    = tokens.masked_fill(~mask, ignore_index)        models/muse.py:150, models/maskgit.py:131
  *   embeds[t] = table[input_ids[t]] + pos[t mod n_per_seq]     models/muse.py:90-91, models/maskgit.py:80-81
  * tokens: T int64; mask: T bytes (0 / non-zero) or NULL (nothing masked); table: (vocab, dim) fp32 with dim % 4 == 0;
- * pos: (n_per_seq, dim) fp32 or NULL; embeds (T, dim), input_ids, labels: any may be NULL.  Forward only (inference /
- * frozen embeddings).  Out-of-range ids are counted in stats[VQ_STAT_BAD_INDEX] and embed to 0.                     */
+  * pos: (n_per_seq, dim) fp32 or NULL; embeds (T, dim), input_ids, labels: any may be NULL.  The backward with respect
+ * to the table is vq_embedding_backward over input_ids.  Out-of-range ids are counted in stats[VQ_STAT_BAD_INDEX] and embed to 0.                     */
 VQ_API int vq_token_embed(const int64_t* tokens, const uint8_t* mask, int64_t T, int64_t n_per_seq,
                           int64_t mask_token_id, int64_t ignore_index, const float* table, int64_t vocab, int dim,
                           const float* pos, float* embeds, int64_t* input_ids, int64_t* labels, int64_t* stats,
                           void* stream);
+
+/* The autoregressive consumer (Parti, models/parti.py:98-106): the decoder input of a (b, n) token batch is
+ *   embeds[b, 0] = start_token ;  embeds[b, i] = table[tokens[b, i - 1]] + pos[i - 1]   (i = 1 .. n - 1)
+ * i.e. `token_emb(tokens[:, :-1])`, `+ pe[:n-1]` (models/positional_encoding.py:40-41; the dropout behind it is the
+ * caller's) and `cat(start_token, ...)` in one pass; the labels are the tokens themselves.  T = b * n_per_seq.      */
+VQ_API int vq_token_embed_causal(const int64_t* tokens, int64_t T, int64_t n_per_seq, const float* table, int64_t vocab,
+                                 int dim, const float* pos, const float* start, float* embeds, int64_t* stats, void* stream);
+
+/* Backward of an embedding lookup, deterministic: grad_table[ids[j]] += grad_out[row(j)], accumulated as 64-bit
+ * integers at a per-call fixed-point scale derived from max |grad_out| (exact, order-free sums), converted once.
+ * Replaces what autograd derives for nn.Embedding behind the tokens (models/muse.py:90, models/maskgit.py:80,
+ * models/parti.py:100) and for Codebook.indices_to_embeddings (models/vitvqgan.py:173-176, models/vqgan.py:178-182).
+ *   row(j) = (j / ids_per_seq) * rows_per_seq + j % ids_per_seq + row_shift     (0, 0, 0: row(j) = j; Parti's shifted
+ *            input: ids_per_seq = n - 1 over tokens[:, :-1] made contiguous, rows_per_seq = n, row_shift = 1)
+ *   hw > 0 : grad_out is (b, dim, hw) (the VQGAN decode layout), id j = b * hw + p pairs with grad_out[b, :, p]
+ *   ids outside [0, vocab) take no gradient;  grad_out holds n_rows rows of `dim` floats (dim % 4 == 0)
+ *   cb != NULL (the prepared codebook, vocab = K, dim = D): the lookup was l2norm(E[i]) -- grad_table is then the
+ *            codebook gradient NB(E_k, sum of the upstream rows)
+ * grad_table (vocab, dim) is overwritten.  ws: vq_embedding_backward_bytes(vocab, dim) of device scratch.          */
+VQ_API int vq_embedding_backward_bytes(int64_t vocab, int dim, size_t* out);
+VQ_API int vq_embedding_backward(const int64_t* ids, int64_t n_ids, int64_t ids_per_seq, int64_t rows_per_seq,
+                                 int64_t row_shift, const float* grad_out, int64_t n_rows, int64_t hw, int64_t vocab, int dim,
+                                 const void* cb, float* grad_table, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------
  * Between vq_profile_begin() and vq_profile_end() the library counts all kernel launches and brackets the kernels

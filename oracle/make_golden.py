@@ -104,6 +104,62 @@ def token_embed_case(name, vocab, dim, b, n, seed):
     print(name, "masked", int(mask.sum()), "of", b * n)
 
 
+def token_grad_case(name, vocab, dim, b, n, seed):
+    """Backward of the two token consumers through the reference's own modules and autograd:
+    MaskGIT (models/maskgit.py:80-81: input_proj lookup, `+= pos_enc` with pos_enc an nn.Parameter) and Parti's shifted
+    decoder input (models/parti.py:98-106: token_emb(tokens[:, :-1]), PositionalEncoding, start token; eval mode so the
+    dropout of models/positional_encoding.py:42 is the identity)."""
+    from einops import repeat
+    from models.maskgit import BiDirectionalTransformer
+    from models.positional_encoding import PositionalEncoding
+    g = torch.Generator().manual_seed(seed)
+    m = BiDirectionalTransformer(dim=dim, vocab_size=vocab, num_patches=n, n_heads=2, d_head=16, dec_depth=1)
+    with torch.no_grad():
+        m.input_proj.weight.copy_(torch.randn(vocab + 1, dim, generator=g))
+        m.pos_enc.copy_(0.02 * torch.randn(1, n, dim, generator=g))
+    tokens = torch.randint(0, vocab, (b, n), generator=g)
+    mask = torch.rand(b, n, generator=g) < 0.4
+    up = torch.randn(b, n, dim, generator=g) * 1e-3
+    x = tokens.masked_fill(mask, m.mask_token_id)
+    e = m.input_proj(x)
+    e = e + m.pos_enc            # (out-of-place form of maskgit.py:81 so that autograd can run on the leaf)
+    (e * up).sum().backward()
+    # Parti
+    token_emb = torch.nn.Embedding(vocab, dim)
+    pos = PositionalEncoding(dim).eval()
+    start = torch.nn.Parameter(torch.randn(dim, generator=g))
+    with torch.no_grad():
+        token_emb.weight.copy_(torch.randn(vocab, dim, generator=g))
+    inp, labels = tokens[:, :-1], tokens                                   # parti.py:98
+    pe = token_emb(inp)                                                    # parti.py:100
+    pe = pos(pe)                                                           # parti.py:102
+    pe = torch.cat((repeat(start, 'd -> b 1 d', b=b), pe), dim=1)          # parti.py:104-105
+    (pe * up).sum().backward()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), vocab=vocab, dim=dim, b=b, n=n, seed=seed, tokens=tokens.numpy(),
+                        mask=mask.numpy(), upstream=up.numpy(), maskgit_table=m.input_proj.weight.detach().numpy(),
+                        maskgit_pos=m.pos_enc.detach().numpy(), maskgit_embeds=e.detach().numpy(),
+                        maskgit_grad_table=m.input_proj.weight.grad.numpy(), maskgit_grad_pos=m.pos_enc.grad.numpy(),
+                        parti_table=token_emb.weight.detach().numpy(), parti_pe=pos.pe[:n].numpy(), parti_start=start.detach().numpy(),
+                        parti_embeds=pe.detach().numpy(), parti_labels=labels.numpy(),
+                        parti_grad_table=token_emb.weight.grad.numpy(), parti_grad_start=start.grad.numpy())
+    print(name, "ok")
+
+
+def decode_grad_case(name, form, K, D, b, n, seed):
+    """indices_to_embeddings is differentiable w.r.t. the codebook in the reference (nn.Embedding lookup; the ViT form
+    normalises behind it): gradients of the unmodified Codebook classes through autograd."""
+    cb = _module(form, K, D, 0.25, vo.make_codebook(form, K, D, seed))
+    g = torch.Generator().manual_seed(seed + 1)
+    idx = torch.randint(0, K, (b, n), generator=g)
+    out = cb.indices_to_embeddings(idx)
+    up = torch.randn(out.shape, generator=g)
+    (out * up).sum().backward()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), form=form, K=K, D=D, weight=cb.embedding.weight.detach().numpy(),
+                        indices=idx.numpy(), upstream=up.numpy(), out=out.detach().numpy(),
+                        grad_weight=cb.embedding.weight.grad.numpy())
+    print(name, "ok")
+
+
 def degenerate_rows(z, w):
     """zero row, NaN row, a row equal to a code, a zero code (SURVEY.md section 7 'Degenerate rows')."""
     z[0, 0] = 0.0
@@ -112,8 +168,18 @@ def degenerate_rows(z, w):
     z[1, 0] = -w[7]
 
 
+def _selected(fn):
+    """`python oracle/make_golden.py name ...` regenerates only the named fixtures."""
+    def run(name, *a, **k):
+        if len(sys.argv) == 1 or name in sys.argv[1:]:
+            fn(name, *a, **k)
+    return run
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    forward_case, step_case, decode_case = _selected(forward_case), _selected(step_case), _selected(decode_case)
+    token_embed_case, token_grad_case, decode_grad_case = _selected(token_embed_case), _selected(token_grad_case), _selected(decode_grad_case)
     # BASELINE.json configs[0]: ViT form K=8192 D=32, 2 x 1024 tokens
     forward_case("vit_cfg1_fwd", vo.VIT, 8192, 32, (2, 1024, 32), 0, 1)
     # a slice of configs[1]: VQGAN form K=8192 D=256, NCHW 16x16 latents
@@ -130,3 +196,6 @@ if __name__ == "__main__":
     forward_case("vit_degenerate_fwd", vo.VIT, 64, 32, (2, 8, 32), 40, 41, edit=degenerate_rows)
     # first consumer of the tokens
     token_embed_case("maskgit_token_embed", 512, 64, 3, 16, 50)
+    token_grad_case("token_consumers_grad", 512, 64, 3, 16, 51)
+    decode_grad_case("vit_decode_grad", "vit", 512, 32, 3, 16, 52)
+    decode_grad_case("vqgan_decode_grad", "vqgan", 256, 64, 2, 16, 53)

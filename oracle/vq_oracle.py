@@ -297,3 +297,15 @@ def masked_token_embeddings(tokens: torch.Tensor, mask, mask_token_id: int, tabl
     if pos_enc is not None:
         embeds = embeds + pos_enc
     return embeds, input_ids, labels
+
+
+def causal_token_embeddings(tokens: torch.Tensor, table: torch.Tensor, pe, start_token: torch.Tensor):
+    """/root/reference/models/parti.py:98-106: the decoder input of the autoregressive model --
+    ``token_emb(tokens[:, :-1])`` (``:100``), ``+ pe[:seq_len]`` (``:102`` via models/positional_encoding.py:40-41; its
+    dropout is the identity in eval mode), start token in front (``:104-105``); the labels are the tokens (``:98``)."""
+    inp, labels = tokens[:, :-1], tokens
+    e = torch.nn.functional.embedding(inp, table)
+    if pe is not None:
+        e = e + pe[: e.size(1)]
+    start = start_token.reshape(1, 1, -1).expand(tokens.shape[0], 1, -1)
+    return torch.cat((start, e), dim=1), labels

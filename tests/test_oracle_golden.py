@@ -175,3 +175,35 @@ def test_token_consumer_oracle_matches_reference_fixture():
     embeds, ids, labels = vo.masked_token_embeddings(tokens, mask, vocab, table, pos, -1)
     assert np.array_equal(ids.numpy(), g["input_ids"]) and np.array_equal(labels.numpy(), g["labels"])
     assert np.array_equal(embeds.numpy(), g["embeds"])          # a gather and one fp32 add: bit-exact
+
+
+def test_token_consumer_gradients_and_causal_form_match_reference_fixture():
+    """The oracle's two token consumers, forward and autograd backward, against what the reference's own modules gave
+    (tests/golden/token_consumers_grad.npz: MaskGIT's BiDirectionalTransformer lookup and Parti's shifted decoder input)."""
+    g = load_golden("token_consumers_grad")
+    vocab = int(g["vocab"])
+    tokens, mask, up = torch.from_numpy(g["tokens"]), torch.from_numpy(g["mask"]), torch.from_numpy(g["upstream"])
+    table = torch.from_numpy(g["maskgit_table"]).requires_grad_(True)
+    pos = torch.from_numpy(g["maskgit_pos"]).requires_grad_(True)
+    e, _, _ = vo.masked_token_embeddings(tokens, mask, vocab, table, pos, -1)
+    (e * up).sum().backward()
+    assert np.array_equal(e.detach().numpy(), g["maskgit_embeds"])
+    assert rel_err(table.grad.numpy(), g["maskgit_grad_table"]) < 1e-6 and rel_err(pos.grad.numpy(), g["maskgit_grad_pos"]) < 1e-6
+    ptable = torch.from_numpy(g["parti_table"]).requires_grad_(True)
+    start = torch.from_numpy(g["parti_start"]).requires_grad_(True)
+    pe, labels = vo.causal_token_embeddings(tokens, ptable, torch.from_numpy(g["parti_pe"]), start)
+    (pe * up).sum().backward()
+    assert np.array_equal(pe.detach().numpy(), g["parti_embeds"]) and np.array_equal(labels.numpy(), g["parti_labels"])
+    assert rel_err(ptable.grad.numpy(), g["parti_grad_table"]) < 1e-6 and rel_err(start.grad.numpy(), g["parti_grad_start"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["vit_decode_grad", "vqgan_decode_grad"])
+def test_decode_is_differentiable_like_the_reference(name):
+    """indices_to_embeddings carries a gradient to the codebook in the reference (nn.Embedding lookup, normalised in the
+    ViT form): the oracle's restatement gives the fixture's gradient."""
+    g = load_golden(name)
+    w = torch.from_numpy(g["weight"]).requires_grad_(True)
+    out = vo.indices_to_embeddings(str(g["form"]), torch.from_numpy(g["indices"]), w)
+    (out * torch.from_numpy(g["upstream"])).sum().backward()
+    assert np.array_equal(out.detach().numpy(), g["out"])
+    assert rel_err(w.grad.numpy(), g["grad_weight"]) < 1e-6
