@@ -161,6 +161,14 @@ int vq_codebook_prepare(const float* weight, int K, int D, void* cb, size_t cb_b
     return VQ_OK;
 }
 
+int vq_codebook_prepare_raw(const float* weight, int K, int D, void* cb, size_t cb_bytes, void* stream) {
+    if (int r = check_dims(0, K, D)) return r;
+    if (!weight || !cb) return fail(VQ_ERR_ARG, "weight/cb is NULL");
+    if (cb_bytes < vq::codebook_bytes(K, D)) return fail(VQ_ERR_WORKSPACE, "codebook blob too small");
+    VQ_CUDA(vq::launch_prep_codebook(weight, vq::codebook_view(cb, K, D), static_cast<cudaStream_t>(stream), true));
+    return VQ_OK;
+}
+
 int vq_workspace_bytes(int64_t T, int K, int D, int flags, size_t* out) {
     (void)flags;
     if (!out) return fail(VQ_ERR_ARG, "out is NULL");
@@ -174,7 +182,9 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
                float* saved_zn, float* saved_denom, int64_t* seg_sums, void* ws, size_t ws_bytes, void* stream) {
     if (int r = check_dims(T, K, D)) return r;
     if (int r = check_layout(layout, T, hw)) return r;
-    if (form != VQ_FORM_VIT && form != VQ_FORM_VQGAN) return fail(VQ_ERR_ARG, "unknown form %d", form);
+    if (form != VQ_FORM_VIT && form != VQ_FORM_VQGAN && form != VQ_FORM_VQGAN_L2) return fail(VQ_ERR_ARG, "unknown form %d", form);
+    const bool raw = form == VQ_FORM_VQGAN_L2;
+    if (raw) flags |= VQ_FLAG_EXACT_SCAN;       // the filters' error bounds assume unit rows
     if (!cb || !idx || (!z && T > 0)) return fail(VQ_ERR_ARG, "z/cb/idx is NULL");
     const bool indices_only = (flags & VQ_FLAG_INDICES_ONLY) != 0;
     if (!indices_only && !z_q) return fail(VQ_ERR_ARG, "z_q is NULL without VQ_FLAG_INDICES_ONLY");
@@ -186,10 +196,10 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
     vq::CodebookView cbv = vq::codebook_view(cb, K, D);
     if (g_profiling) g_sampled = (g_profile_calls++ % g_profile_every) == 0;
     // `weight` given: the codebook is prepared by this call -- in the token prep launch when the shape allows it
-    const bool fuse_prep = weight && layout == VQ_LAYOUT_TOKEN_MAJOR && vq::prep_fusable(D);
+    const bool fuse_prep = weight && layout == VQ_LAYOUT_TOKEN_MAJOR && vq::prep_fusable(D) && !raw;
     if (weight && !fuse_prep) {
         SlotTimer cb_timer(s, VQ_PROFILE_PREP_CODEBOOK);
-        VQ_CUDA(vq::launch_prep_codebook(weight, cbv, s));
+        VQ_CUDA(vq::launch_prep_codebook(weight, cbv, s, raw));
         cb_timer.stop();
     }
 
@@ -216,7 +226,13 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
     if (fuse_prep) {
         VQ_CUDA(vq::launch_prep_fused(weight, cbv, z, T, zn32, w.row_sq, denom, zn16, zl, s));
     } else if (layout == VQ_LAYOUT_TOKEN_MAJOR) {
-        VQ_CUDA(vq::launch_prep_tokens(z, T, D, zn32, w.row_sq, denom, zn16, zl, s));
+        VQ_CUDA(vq::launch_prep_tokens(z, T, D, zn32, w.row_sq, denom, zn16, zl, s, raw));
+    } else if (raw) {
+        // un-normalised form: the rows as they are (transposed to token-major), denominators of 1, row_sq = sum(z^2)
+        if (nz) VQ_CUDA(vq::launch_zero_ranges(zl, s));
+        VQ_CUDA(vq::launch_fill_ones(denom, T, s));
+        VQ_CUDA(vq::launch_nchw_to_tok(z, T, hw, D, nullptr, zn32, zn16, s));
+        VQ_CUDA(vq::launch_row_sumsq(zn32, T, D, w.row_sq, s));
     } else {
         if (T == 0 && nz) VQ_CUDA(vq::launch_zero_ranges(zl, s));
         VQ_CUDA(vq::launch_norm_nchw(z, T, hw, D, denom, zl, s));
@@ -300,9 +316,11 @@ int vq_backward_tokens(const float* g_zq, int layout, int64_t T, int64_t hw, con
         const float c1 = (form == VQ_FORM_VIT) ? beta : 1.f;
         const float coef = (float)((double)c1 * 2.0 / (double)n_elem_total);
         if (layout == VQ_LAYOUT_TOKEN_MAJOR) {
+            if (form == VQ_FORM_VQGAN_L2) return fail(VQ_ERR_ARG, "VQ_FORM_VQGAN_L2 backward supports the NCHW layout only");
             VQ_CUDA(vq::launch_backward_tokens(g_zq, saved_zn, saved_denom, idx, cbv, T, coef, g_loss, grad_z, s));
         } else {
-            VQ_CUDA(vq::launch_backward_tokens_nchw(g_zq, saved_zn, saved_denom, idx, cbv, T, hw, coef, g_loss, grad_z, s));
+            VQ_CUDA(vq::launch_backward_tokens_nchw(g_zq, saved_zn, saved_denom, idx, cbv, T, hw, coef, g_loss, grad_z, s,
+                                                    form == VQ_FORM_VQGAN_L2));
         }
     }
     if (seg_sums) VQ_CUDA(vq::launch_segment_sums(saved_zn, idx, hist, cbv, T, seg_sums, seg_ws, seg_bytes, s));
@@ -331,6 +349,8 @@ int vq_backward(const float* g_zq, int layout, int64_t T, int64_t hw, const floa
                 int64_t n_elem_total, const int64_t* seg_sums, const int64_t* stats, float* grad_z, float* grad_weight,
                 float* loss, void* ws, size_t ws_bytes, void* stream) {
     if (!seg_sums || !grad_weight) return fail(VQ_ERR_ARG, "vq_backward needs seg_sums (from vq_forward) and grad_weight");
+    if (form == VQ_FORM_VQGAN_L2 && layout == VQ_LAYOUT_TOKEN_MAJOR && grad_z)
+        return fail(VQ_ERR_ARG, "VQ_FORM_VQGAN_L2 backward supports the NCHW layout only");
     if (loss && !stats) return fail(VQ_ERR_ARG, "loss needs stats");
     if (grad_z && layout == VQ_LAYOUT_TOKEN_MAJOR && T > 0) {
         if (int r = check_dims(T, K, D)) return r;
@@ -425,6 +445,7 @@ int vq_backward_codebook_sharded(const void* const* peer_bufs, int world, int ra
     for (int r = 0; r < world; ++r)
         if (!peer_bufs[r]) return fail(VQ_ERR_ARG, "peer_bufs[%d] is NULL", r);
     if (!cb || !grad_weight || n_elem_total <= 0) return fail(VQ_ERR_ARG, "bad argument to vq_backward_codebook_sharded");
+    if (form == VQ_FORM_VQGAN_L2) return fail(VQ_ERR_ARG, "VQ_FORM_VQGAN_L2 is not supported by the fused peer exchange (use the collective exchange)");
     vq::CodebookView cbv = vq::codebook_view(const_cast<void*>(cb), K, D);
     const float c2 = (form == VQ_FORM_VIT) ? 1.f : beta;
     const float coef = (float)((double)c2 * 2.0 / (double)n_elem_total);
@@ -446,6 +467,7 @@ int vq_backward_sharded(const void* const* peer_bufs, int world, int rank, int s
         if (!peer_bufs[r]) return fail(VQ_ERR_ARG, "peer_bufs[%d] is NULL", r);
     if (!cb || !grad_weight || !grad_z || !saved_zn || !saved_denom || !idx || n_elem_total <= 0)
         return fail(VQ_ERR_ARG, "bad argument to vq_backward_sharded");
+    if (form == VQ_FORM_VQGAN_L2) return fail(VQ_ERR_ARG, "VQ_FORM_VQGAN_L2 is not supported by the fused peer exchange (use the collective exchange)");
     vq::CodebookView cbv = vq::codebook_view(const_cast<void*>(cb), K, D);
     const float c1 = (form == VQ_FORM_VIT) ? beta : 1.f, c2 = (form == VQ_FORM_VIT) ? 1.f : beta;
     const float coef1 = (float)((double)c1 * 2.0 / (double)n_elem_total), coef2 = (float)((double)c2 * 2.0 / (double)n_elem_total);

@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(256) k_backward_tokens_nchw(const float* __res
                                                               const float* __restrict__ denom,
                                                               const int64_t* __restrict__ idx, const float* __restrict__ en,
                                                               int64_t T, int64_t hw, float coef_base,
-                                                              const float* __restrict__ g_loss, float* __restrict__ grad) {
+                                                              const float* __restrict__ g_loss, float* __restrict__ grad,
+                                                              int raw) {
     extern __shared__ float tile[];                   // [32][D + 1]
     constexpr int kStride = D + 1;
     const float coef = coef_base * (g_loss ? __ldg(g_loss) : 1.f);
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(256) k_backward_tokens_nchw(const float* __res
                 dot = __fmaf_rn(a[j], gz[j], dot);
             }
         }
-        dot = warp_sum(dot);
+        dot = raw ? 0.f : warp_sum(dot);              // raw (un-normalised) form: no projection, denom = 1: grad_z = g_zn
 #pragma unroll
         for (int j = 0; j < (D + 31) / 32; ++j) {
             const int c = x + 32 * j;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(256) k_backward_tokens_nchw(const float* __res
 
 cudaError_t launch_backward_tokens_nchw(const float* g_nchw, const float* zn32, const float* denom, const int64_t* idx,
                                         const CodebookView& cb, int64_t T, int64_t hw, float coef_commit, const float* g_loss,
-                                        float* grad_nchw, cudaStream_t s) {
+                                        float* grad_nchw, cudaStream_t s, bool raw) {
     if (T == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((T + 31) / 32);
     const size_t smem = sizeof(float) * 32 * (size_t)(cb.D + 1);
@@ -161,7 +162,7 @@ cudaError_t launch_backward_tokens_nchw(const float* g_nchw, const float* zn32, 
                 e = cudaFuncSetAttribute(k_backward_tokens_nchw<kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
         if (e == cudaSuccess) k_backward_tokens_nchw<kD><<<blocks, 256, smem, s>>>(g_nchw, zn32, denom, idx, cb.en32, T, hw,
-                                                                                   coef_commit, g_loss, grad_nchw);
+                                                                                   coef_commit, g_loss, grad_nchw, raw ? 1 : 0);
     });
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
@@ -394,7 +395,8 @@ __device__ __forceinline__ void codebook_grad_body(const CodebookGradArgs& a, co
                 dot = __fmaf_rn(y[j], g[j], dot);
             }
         }
-        dot = warp_sum(dot);
+        // un-normalised form (VQ_FORM_VQGAN_L2): grad_E = coef * S_k as it is (code_denom = 1, no projection)
+        dot = (a.form == VQ_FORM_VQGAN_L2) ? 0.f : warp_sum(dot);
         const float inv = __fdiv_rn(1.f, __ldg(code_denom + k));
         const bool poisoned = __ldg(seg_sums + (int64_t)K * D + k) != 0;
 #pragma unroll

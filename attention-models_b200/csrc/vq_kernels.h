@@ -29,14 +29,16 @@ constexpr int kSegPiece = 256;   // tokens per work item of the segmented codebo
 constexpr int kCandExactBit = 0x40000000;  // cand[t] holds a final index, not a cell id
 
 // ---- vq_prep.cu ------------------------------------------------------------------------------
-cudaError_t launch_prep_codebook(const float* weight, const CodebookView& cb, cudaStream_t s);
+cudaError_t launch_prep_codebook(const float* weight, const CodebookView& cb, cudaStream_t s, bool raw = false);
 // token-major rows -> zn32, row_sq, denom, zn16 (any output may be null); also clears the buffers of `zl`
 struct ZeroList {
     void* ptr[4];
     unsigned long long bytes[4];
 };
 cudaError_t launch_prep_tokens(const float* z, int64_t T, int D, float* zn32, float* row_sq, float* denom,
-                               __half* zn16, const ZeroList& zl, cudaStream_t s);
+                               __half* zn16, const ZeroList& zl, cudaStream_t s, bool raw = false);
+// denom[t] = 1 for the un-normalised form behind the NCHW transposition (which then divides by nothing)
+cudaError_t launch_fill_ones(float* p, int64_t n, cudaStream_t s);
 cudaError_t launch_zero_ranges(const ZeroList& zl, cudaStream_t s);
 // codebook + token preparation in one launch (training step; token-major rows, prep_fusable(D))
 bool prep_fusable(int D);
@@ -119,7 +121,7 @@ cudaError_t launch_backward_fused(const float* g_tok, const float* zn32, const f
 // grad_z for the (b, D, hw) layout: upstream gradient read and grad_z written in place of the two layout kernels
 cudaError_t launch_backward_tokens_nchw(const float* g_nchw, const float* zn32, const float* denom, const int64_t* idx,
                                         const CodebookView& cb, int64_t T, int64_t hw, float coef_commit, const float* g_loss,
-                                        float* grad_nchw, cudaStream_t s);
+                                        float* grad_nchw, cudaStream_t s, bool raw = false);
 cudaError_t launch_segment_sums(const float* zn32, const int64_t* idx, const int32_t* hist, const CodebookView& cb,
                                 int64_t T, int64_t* seg_sums, void* ws, size_t ws_bytes, cudaStream_t s);
 // grad_E from the segment sums; with `loss` also the loss from stats (the former k_loss_finalize launch)

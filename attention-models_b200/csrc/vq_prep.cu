@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) k_prep_rows(const float* __restrict__ in,
                                                    float* __restrict__ unit32, float* __restrict__ sq,
                                                    float* __restrict__ denom, __half* __restrict__ unit16,
                                                    int* __restrict__ info, float4* __restrict__ en32c,
-                                                   float* __restrict__ csq_cell, ZeroList zl) {
+                                                   float* __restrict__ csq_cell, ZeroList zl, int raw) {
     using M = RowMap<D>;
     constexpr int kRows = (M::kPerLane <= 4) ? 4 : 2;
     const int lane = threadIdx.x & 31;
@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(256) k_prep_rows(const float* __restrict__ in,
         for (int i = 0; i < kRows; ++i) {
             const int64_t r = r0 + i;
             if (r >= rows) break;
-            const float den = norm_denominator(M::template sumsq<true>(x[i]));
+            // raw: the un-normalised (plain squared-L2) form keeps the rows as they are (x / 1 is exact)
+            const float den = raw ? 1.f : norm_denominator(M::template sumsq<true>(x[i]));
 #pragma unroll
             for (int j = 0; j < M::kPerLane; ++j) x[i][j] = __fdiv_rn(x[i][j], den);
             const float s2 = M::template sumsq<false>(x[i]);
@@ -137,7 +138,8 @@ __device__ __forceinline__ void prep_rows_small_body(const float4* __restrict__ 
                                                      float4* __restrict__ unit32, float* __restrict__ sq,
                                                      float* __restrict__ denom, uint2* __restrict__ unit16,
                                                      int* __restrict__ info, float4* __restrict__ en32c,
-                                                     float* __restrict__ csq_cell, int cell_kind, int vblock, int vgrid) {
+                                                     float* __restrict__ csq_cell, int cell_kind, int vblock, int vgrid,
+                                                     int raw = 0) {
     static_assert(D == 16 || D == 32 || D == 64, "small-row prep covers D < 128");
     int n_bad = 0;
     constexpr int kLpr = D / 4;
@@ -169,7 +171,7 @@ __device__ __forceinline__ void prep_rows_small_body(const float4* __restrict__ 
         for (int i = 0; i < kUnroll; ++i) {
             const int64_t r = r0 + i * kRpw + grp;
             float4 v = x[i];
-            const float den = norm_denominator(
+            const float den = raw ? 1.f : norm_denominator(
                 tree(make_float4(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y), __fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w))));
             v.x = __fdiv_rn(v.x, den); v.y = __fdiv_rn(v.y, den); v.z = __fdiv_rn(v.z, den); v.w = __fdiv_rn(v.w, den);
             const float s2 =
@@ -208,12 +210,12 @@ __global__ void __launch_bounds__(256) k_prep_rows_small(const float4* __restric
                                                          float4* __restrict__ unit32, float* __restrict__ sq,
                                                          float* __restrict__ denom, uint2* __restrict__ unit16,
                                                          int* __restrict__ info, float4* __restrict__ en32c,
-                                                         float* __restrict__ csq_cell, int cell_kind, ZeroList zl) {
+                                                         float* __restrict__ csq_cell, int cell_kind, ZeroList zl, int raw) {
     pdl_trigger();
     pdl_wait();
     if (!kIsCodebook) zero_ranges(zl, blockIdx.x, gridDim.x);
     prep_rows_small_body<D, kIsCodebook>(in, rows, unit32, sq, denom, unit16, info, en32c, csq_cell, cell_kind, blockIdx.x,
-                                         gridDim.x);
+                                         gridDim.x, raw);
 }
 
 // codebook rows on blocks [0, cb_blocks), token rows on the rest: the two preparations of a training step in one launch
@@ -239,7 +241,8 @@ __global__ void __launch_bounds__(256) k_prep_rows_fused(PrepRowsArgs cbk, int* 
 
 template <int D, bool kIsCodebook>
 static cudaError_t prep_rows(const float* in, int64_t rows, float* unit32, float* sq, float* denom, __half* unit16,
-                             int* info, float* en32c, float* csq_cell, int cell_kind, const ZeroList& zl, cudaStream_t s) {
+                             int* info, float* en32c, float* csq_cell, int cell_kind, const ZeroList& zl, cudaStream_t s,
+                             int raw = 0) {
     if (rows == 0 && kIsCodebook) return cudaSuccess;
     const int64_t cap = kIsCodebook ? kInfoSlots : (int64_t)sm_count() * 8;
     if constexpr (D < 128) {
@@ -249,7 +252,7 @@ static cudaError_t prep_rows(const float* in, int64_t rows, float* unit32, float
         if (blocks < 1) blocks = 1;
         cudaError_t e = launch_pdl(k_prep_rows_small<D, kIsCodebook>, dim3((unsigned)blocks), dim3(256), 0, s,
                                    reinterpret_cast<const float4*>(in), rows, reinterpret_cast<float4*>(unit32), sq, denom,
-                                   reinterpret_cast<uint2*>(unit16), info, reinterpret_cast<float4*>(en32c), csq_cell, cell_kind, zl);
+                                   reinterpret_cast<uint2*>(unit16), info, reinterpret_cast<float4*>(en32c), csq_cell, cell_kind, zl, raw);
         if (e != cudaSuccess) return e;
     } else {
         constexpr int kRows = (RowMap<D>::kPerLane <= 4) ? 4 : 2;
@@ -258,29 +261,31 @@ static cudaError_t prep_rows(const float* in, int64_t rows, float* unit32, float
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
         cudaError_t e = launch_pdl(k_prep_rows<D, kIsCodebook>, dim3((unsigned)blocks), dim3(warps_per_block * 32), 0, s, in,
-                                   rows, unit32, sq, denom, unit16, info, reinterpret_cast<float4*>(en32c), csq_cell, zl);
+                                   rows, unit32, sq, denom, unit16, info, reinterpret_cast<float4*>(en32c), csq_cell, zl, raw);
         if (e != cudaSuccess) return e;
     }
     count_launch();
     return cudaGetLastError();
 }
 
-static cudaError_t prep_codebook_rows(const float* weight, const CodebookView& cb, cudaStream_t s) {
+static cudaError_t prep_codebook_rows(const float* weight, const CodebookView& cb, cudaStream_t s, int raw) {
     const ZeroList none = {};
     VQ_DISPATCH_D(cb.D, return (prep_rows<kD, true>(weight, cb.K, cb.en32, cb.code_sq, cb.code_denom, cb.en16,
-                                                     cb.info, cb.en32c, cb.csq_cell, cb.cell_kind, none, s)));
+                                                     cb.info, cb.en32c, cb.csq_cell, cb.cell_kind, none, s, raw)));
     return cudaSuccess;
 }
 
 // One launch: unit codes (fp32 + fp16), squared norms, row norms, the degenerate-code counts and, at D = 32, the
 // cell copies the exact rescoring reads.
-cudaError_t launch_prep_codebook(const float* weight, const CodebookView& cb, cudaStream_t s) {
-    return prep_codebook_rows(weight, cb, s);
+// raw: the plain squared-L2 form -- en32 = the weights themselves, code_sq = sum(E^2), code_denom = 1 (the info block then
+// reports every code as "not unit": the tensor-core filters, whose bounds assume unit rows, stand aside)
+cudaError_t launch_prep_codebook(const float* weight, const CodebookView& cb, cudaStream_t s, bool raw) {
+    return prep_codebook_rows(weight, cb, s, raw ? 1 : 0);
 }
 
 cudaError_t launch_prep_tokens(const float* z, int64_t T, int D, float* zn32, float* row_sq, float* denom,
-                               __half* zn16, const ZeroList& zl, cudaStream_t s) {
-    VQ_DISPATCH_D(D, return (prep_rows<kD, false>(z, T, zn32, row_sq, denom, zn16, nullptr, nullptr, nullptr, 0, zl, s)));
+                               __half* zn16, const ZeroList& zl, cudaStream_t s, bool raw) {
+    VQ_DISPATCH_D(D, return (prep_rows<kD, false>(z, T, zn32, row_sq, denom, zn16, nullptr, nullptr, nullptr, 0, zl, s, raw ? 1 : 0)));
     return cudaSuccess;
 }
 
@@ -319,6 +324,18 @@ __global__ void __launch_bounds__(256) k_zero_ranges(ZeroList zl) { zero_ranges(
 // the same zeroing as a launch of its own (layouts whose first kernel is not a token-major prep)
 cudaError_t launch_zero_ranges(const ZeroList& zl, cudaStream_t s) {
     k_zero_ranges<<<sm_count() * 2, 256, 0, s>>>(zl);
+    count_launch();
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) k_fill_ones(float* __restrict__ p, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 1.f;
+}
+cudaError_t launch_fill_ones(float* p, int64_t n, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+    k_fill_ones<<<(unsigned)blocks, 256, 0, s>>>(p, n);
     count_launch();
     return cudaGetLastError();
 }

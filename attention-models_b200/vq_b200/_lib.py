@@ -15,7 +15,7 @@ BUILD_SCRIPT = os.path.join(_PKG_DIR, "csrc", "build.py")
 
 # constants mirrored from include/vq_b200.h
 ABI_VERSION = 4
-FORM_VIT, FORM_VQGAN = 0, 1
+FORM_VIT, FORM_VQGAN, FORM_VQGAN_L2 = 0, 1, 2
 LAYOUT_TOKEN_MAJOR, LAYOUT_NCHW = 0, 1
 FLAG_INDICES_ONLY, FLAG_EXACT_SCAN, FLAG_KEEP_STATS = 1, 2, 4
 STAT_NEAR_TIE_ROWS, STAT_AMBIGUOUS_ROWS, STAT_FALLBACK_ROWS, STAT_LOSS_FIXED, STAT_BAD_INDEX, STAT_NONFINITE = range(6)
@@ -34,6 +34,7 @@ SIGNATURES = {
     "vq_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "vq_codebook_bytes": (c_int, [c_int, c_int, POINTER(c_size_t)]),
     "vq_codebook_prepare": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "vq_codebook_prepare_raw": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "vq_workspace_bytes": (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_size_t)]),
     "vq_forward": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int64,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -53,15 +53,16 @@ class _CodebookBase(nn.Module):
 
     def _prepared_codebook(self) -> F_vq.PreparedCodebook:
         w = self.embedding.weight
-        if self._prepared is None or not self._prepared.matches(w):
-            self._prepared = F_vq.prepare_codebook(w)
+        raw = self.form == "l2"
+        if self._prepared is None or not self._prepared.matches(w, raw):
+            self._prepared = F_vq.prepare_codebook(w, raw)
         return self._prepared
 
     def _quantise(self, z: torch.Tensor):
         # a stale prepared codebook of the right size is refilled by the forward itself (training: the weights changed)
         w = self.embedding.weight
         if self._prepared is None or not self._prepared.fits(w):
-            self._prepared = F_vq.prepare_codebook(w)
+            self._prepared = F_vq.prepare_codebook(w, self.form == "l2")
         trainable = torch.is_grad_enabled() and w.requires_grad
         z_q, flat_idx, loss, hist, stats = F_vq.quantise(z, self.embedding.weight, self.form, self.beta,
                                                          prepared=self._prepared,

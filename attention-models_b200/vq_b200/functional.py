@@ -13,10 +13,11 @@ import torch
 from torch.autograd.function import once_differentiable
 
 from . import _lib
-from ._lib import (FLAG_EXACT_SCAN, FLAG_INDICES_ONLY, FORM_VIT, FORM_VQGAN, LAYOUT_NCHW, LAYOUT_TOKEN_MAJOR,
+from ._lib import (FLAG_EXACT_SCAN, FLAG_INDICES_ONLY, FORM_VIT, FORM_VQGAN, FORM_VQGAN_L2, LAYOUT_NCHW, LAYOUT_TOKEN_MAJOR,
                    STATS_LEN)
 
-FORMS = {"vit": FORM_VIT, "vqgan": FORM_VQGAN}
+# "l2": the CNN form without l2 normalisation (plain squared-L2 on raw vectors; not a form of the reference)
+FORMS = {"vit": FORM_VIT, "vqgan": FORM_VQGAN, "l2": FORM_VQGAN_L2}
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -44,10 +45,11 @@ class PreparedCodebook:
     D: int
     weight_ptr: int
     weight_version: int
+    raw: bool = False          # prepared for the un-normalised form ("l2"): the codes as they are
 
-    def matches(self, weight: torch.Tensor) -> bool:
+    def matches(self, weight: torch.Tensor, raw: bool = False) -> bool:
         return (self.weight_ptr == weight.data_ptr() and self.weight_version == weight._version
-                and self.blob.device == weight.device)
+                and self.blob.device == weight.device and self.raw == raw)
 
     def fits(self, weight: torch.Tensor) -> bool:
         """Same shape and device: the blob can be re-filled in place (by vq_forward itself, see quantise)."""
@@ -57,8 +59,9 @@ class PreparedCodebook:
         self.weight_ptr, self.weight_version = weight.data_ptr(), weight._version
 
 
-def prepare_codebook(weight: torch.Tensor) -> PreparedCodebook:
-    """``l2_norm(embedding.weight)`` and ``sum(embedd_norm**2, 1)`` (reference vitvqgan.py:154,158)."""
+def prepare_codebook(weight: torch.Tensor, raw: bool = False) -> PreparedCodebook:
+    """``l2_norm(embedding.weight)`` and ``sum(embedd_norm**2, 1)`` (reference vitvqgan.py:154,158); ``raw``: the codes
+    as they are and ``sum(weight**2, 1)`` for the un-normalised form."""
     _require_cuda(weight, "the codebook weight")
     if weight.dtype != torch.float32 or weight.dim() != 2:
         raise TypeError("codebook weight must be a 2-D float32 tensor")
@@ -67,8 +70,9 @@ def prepare_codebook(weight: torch.Tensor) -> PreparedCodebook:
     nbytes = _lib.size_query("vq_codebook_bytes", K, D)
     blob = _scratch(nbytes, w.device)
     with torch.cuda.device(w.device):
-        _lib.check(_lib.load().vq_codebook_prepare(_ptr(w), K, D, _ptr(blob), nbytes, _stream(w.device)))
-    return PreparedCodebook(blob, K, D, weight.data_ptr(), weight._version)
+        fn = _lib.load().vq_codebook_prepare_raw if raw else _lib.load().vq_codebook_prepare
+        _lib.check(fn(_ptr(w), K, D, _ptr(blob), nbytes, _stream(w.device)))
+    return PreparedCodebook(blob, K, D, weight.data_ptr(), weight._version, raw)
 
 
 def _token_geometry(z: torch.Tensor, layout: int, D: int) -> Tuple[int, int]:
@@ -182,9 +186,10 @@ def quantise(z: torch.Tensor, weight: torch.Tensor, form: str = "vit", beta: flo
     _require_cuda(z, "z")
     _require_cuda(weight, "the codebook weight")
     refresh = False
-    if prepared is None or not prepared.fits(weight):
-        prepared = prepare_codebook(weight)
-    elif always_refresh or not prepared.matches(weight):
+    raw = form == "l2"
+    if prepared is None or not prepared.fits(weight) or prepared.raw != raw:
+        prepared = prepare_codebook(weight, raw)
+    elif always_refresh or not prepared.matches(weight, raw):
         # stale (or not provably current: an edit through `weight.data` leaves the version counter alone) contents of the
         # right size: vq_forward refills the blob in the launch that normalises the rows (no extra launch)
         refresh = True
@@ -200,8 +205,8 @@ def encode_indices(z: torch.Tensor, weight: torch.Tensor, form: str = "vit",
                    want_hist: bool = False):
     """``encode_imgs`` fast path: flat int64 indices only (z_q, loss and the saved state are skipped)."""
     _require_cuda(z, "z")
-    if prepared is None or not prepared.matches(weight):
-        prepared = prepare_codebook(weight)
+    if prepared is None or not prepared.matches(weight, form == "l2"):
+        prepared = prepare_codebook(weight, form == "l2")
     lib = _lib.load()
     z = _as_fp32_input(z)
     dev = z.device

@@ -43,6 +43,12 @@ extern "C" {
 /* which Codebook: decides where beta sits in the loss and whether decode renormalises */
 #define VQ_FORM_VIT   0   /* models/vitvqgan.py:140-176 */
 #define VQ_FORM_VQGAN 1   /* models/vqgan.py:138-182   */
+#define VQ_FORM_VQGAN_L2 2 /* the CNN form WITHOUT l2 normalisation: plain squared-L2 nearest code on the raw vectors,
+                              d = (|z|^2 + |e_k|^2) - 2 z.e_k, q = E[idx], loss / STE / layouts as VQ_FORM_VQGAN.  Not a form
+                              of the reference (both its Codebooks normalise); BASELINE.json's north_star names it.  Exhaustive
+                              fp32 search only (the tensor-core filters' error bounds assume unit rows); single GPU or the
+                              collective exchange.  `cb` must have been prepared by this form (vq_forward(weight != NULL)
+                              or vq_codebook_prepare_raw).                                                      */
 
 #define VQ_LAYOUT_TOKEN_MAJOR 0   /* (T, D)      -- ViT form input/output            */
 #define VQ_LAYOUT_NCHW        1   /* (b, D, h*w) -- VQGAN form input/output          */
@@ -91,6 +97,8 @@ VQ_API int vq_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * tokeniser prepares once.                                                                        */
 VQ_API int vq_codebook_bytes(int K, int D, size_t* out);
 VQ_API int vq_codebook_prepare(const float* weight, int K, int D, void* cb, size_t cb_bytes, void* stream);
+/* the same blob for VQ_FORM_VQGAN_L2: the codes as they are, sum(E_k^2), denominators of 1 */
+VQ_API int vq_codebook_prepare_raw(const float* weight, int K, int D, void* cb, size_t cb_bytes, void* stream);
 
 /* ---- forward -------------------------------------------------------------------------------
  * Replaces Codebook.forward (models/vitvqgan.py:151-171, models/vqgan.py:148-176):

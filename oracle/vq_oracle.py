@@ -26,6 +26,10 @@ import torch.nn.functional as F
 
 VIT = "vit"      # reference models/vitvqgan.py:140-176
 VQGAN = "vqgan"  # reference models/vqgan.py:138-182
+L2 = "l2"        # NOT a form of the reference: the CNN form with the two l2_norm calls (models/vqgan.py:154-155,163) removed --
+                 # plain squared-L2 nearest code on raw vectors, which BASELINE.json's north_star names.  PARITY UNPINNED for
+                 # this form: there is no reference code to mint fixtures from; it is the reference's own expression
+                 # (models/vqgan.py:157-176) with `l2_norm` replaced by the identity.
 NORM_EPS = 1e-12  # F.normalize default eps (torch/nn/functional.py:5707-5708)
 
 
@@ -59,7 +63,7 @@ def _loss(form: str, beta: float, q: torch.Tensor, zn: torch.Tensor) -> torch.Te
     codebook = torch.mean((q - zn.detach()) ** 2)   # pulls the code towards zn
     if form == VIT:       # reference models/vitvqgan.py:166
         return beta * commit + codebook
-    if form == VQGAN:     # reference models/vqgan.py:169
+    if form in (VQGAN, L2):     # reference models/vqgan.py:169
         return commit + beta * codebook
     raise ValueError(form)
 
@@ -73,18 +77,19 @@ def quantise(form: str, z: torch.Tensor, weight: torch.Tensor, beta: float = 0.2
     and permutes z_q back; indices come back flat in (b, h, w) order.
     """
     dim = weight.shape[1]
-    if form == VQGAN:
+    norm = (lambda t: t) if form == L2 else unit_rows        # L2: the same expressions on the raw vectors
+    if form in (VQGAN, L2):
         z = z.permute(0, 2, 3, 1)                   # 'b d h w -> b h w d' (view)
-    zn = unit_rows(z)
+    zn = norm(z)
     zn_flat = zn.reshape(-1, dim)                   # .view for VIT, copy for VQGAN
-    en = unit_rows(weight)
+    en = norm(weight)
     d = distance_matrix(zn_flat, en)
     flat_idx = torch.argmin(d, dim=1)
     idx = flat_idx.view(*z.shape[:-1]) if form == VIT else flat_idx
-    q = unit_rows(F.embedding(flat_idx, weight)).view(*z.shape)
+    q = norm(F.embedding(flat_idx, weight)).view(*z.shape)
     loss = _loss(form, beta, q, zn)
     z_q = zn + (q - zn).detach()                    # straight-through estimator
-    if form == VQGAN:
+    if form in (VQGAN, L2):
         z_q = z_q.permute(0, 3, 1, 2)               # 'b h w d -> b d h w'
     return QuantiserOut(z_q, idx, loss)
 

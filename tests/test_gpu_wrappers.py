@@ -48,13 +48,18 @@ def test_wrapper_call_sites_around_the_patched_codebook(form, fast):
 
     # forward + backward through the whole wrapper (vitvqgan.py:190-196 / vqgan.py:231-237)
     target = torch.randn_like(imgs)
-    outs = []
+    outs, seen = [], []
     for m in (ref, new):
         m.zero_grad(set_to_none=True)
+        hook = m.codebook.register_forward_hook(lambda _m, _i, o: seen.append((o[0].detach().contiguous(), o[1].detach())))
         out, loss = m(imgs)
+        hook.remove()
         ((out - target).square().mean() + loss).backward()
         outs.append((out.detach(), loss.detach()))
-    assert torch.equal(outs[0][0], outs[1][0]), "wrapper output differs (z_q must be bit-exact)"
+    # at the quantiser's boundary: bit-exact z_q, equal indices; behind post_quant / the decoder the two wrappers run the
+    # same torch modules on the same values (cuDNN may still pick another algorithm for another memory format)
+    assert torch.equal(seen[0][0], seen[1][0]) and torch.equal(seen[0][1].reshape(-1), seen[1][1].reshape(-1))
+    assert rel_err(outs[1][0].cpu().numpy(), outs[0][0].cpu().numpy()) < 1e-5
     assert rel_err(outs[1][1].cpu().numpy(), outs[0][1].cpu().numpy()) < 1e-5
     for (name, p_ref), (_, p_new) in zip(ref.named_parameters(), new.named_parameters()):
         assert p_new.grad is not None, name
@@ -66,4 +71,5 @@ def test_wrapper_call_sites_around_the_patched_codebook(form, fast):
         assert t_new.dtype == torch.int64 and t_new.shape == t_ref.shape and t_new.dim() == 2
         assert torch.equal(t_ref, t_new)
         # decode_indices (vitvqgan.py:198-202 / vqgan.py:239-243)
-        assert torch.equal(ref.decode_indices(t_ref), new.decode_indices(t_new))
+        assert torch.equal(ref.codebook.indices_to_embeddings(t_ref).contiguous(), new.codebook.indices_to_embeddings(t_new))
+        assert rel_err(new.decode_indices(t_new).cpu().numpy(), ref.decode_indices(t_ref).cpu().numpy()) < 1e-5
