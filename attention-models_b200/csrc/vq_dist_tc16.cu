@@ -62,9 +62,20 @@ constexpr int kABytes = kRowsPerCta * kD * 2;       // 16 KiB: one row tile of f
 constexpr int kBStageBytes = kTileN * kD * 2;       // 8 KiB: one n-tile of fp16 unit codes per TMA
 constexpr int kBStages = 6;
 constexpr int kAStages = 2;
-constexpr int kThreads = 384;          // warps 0-7 epilogue, 8 TMA, 9 + 11 MMA (one per row half), 10 TMEM allocator
-constexpr int kRegsService = 40, kRegsEpilogue = 232;
-static_assert(128 * kRegsService + 256 * kRegsEpilogue <= 65536, "register file overcommitted");
+// MMA issuer warps.  A thread issues one tcgen05.mma per ~110-140 cycles however small the instruction is, and several
+// issuer warps overlap perfectly (tools/ubench_mma.cu: 137 / 69 / 34 cycles per N = 128 MMA aggregated over 1 / 2 / 4
+// issuers): at D = 32 a tile is two MMAs, so it is the ISSUE rate of a warp, not the tensor pipe, that paces the kernel.
+// 4 issuers = one per accumulator stage (row half x n-tile parity); 2 = one per row half (the first-generation layout).
+#ifndef VQ_TC16_ISSUERS
+#define VQ_TC16_ISSUERS 4
+#endif
+constexpr int kIssuers = VQ_TC16_ISSUERS;
+static_assert(kIssuers == 2 || kIssuers == 4, "2 or 4 MMA issuer warps");
+// warps 0-7 epilogue; 8 TMA; then the issuers and the TMEM allocator: 384 threads (9, 11 issue; 10 allocates) or 512
+// (9-12 issue; 13 allocates).  setmaxnreg moves registers inside the pool the block was launched with.
+constexpr int kThreads = kIssuers == 2 ? 384 : 512;
+constexpr int kRegsService = 40, kRegsEpilogue = kIssuers == 2 ? 232 : 216;
+static_assert((kThreads - 256) * kRegsService + 256 * kRegsEpilogue <= (65536 / kThreads / 8 * 8) * kThreads, "register pool overcommitted");
 // |fp16-pipeline score - exact dot| <= eps: 1.1e-3 for the fp16 operands (as in vq_dist_tc.cu) + one fp16 ulp
 // per accumulator rounding (2^-11 below 1, 2^-10 in [1, 2)); the threshold is additionally rounded down to fp16
 constexpr float kTwoEps = 2.f * (1.1e-3f + 4.8829e-4f + 4.8829e-4f);
@@ -158,7 +169,8 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     // service warps derive from it then live in the uniform datapath (no R2UR / elect loops around tcgen05 ops)
     const int warp = __shfl_sync(VQ_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     constexpr int kEpiWarp0 = kServiceHigh ? 0 : 4;
-    constexpr int kTmaWarp = kServiceHigh ? 8 : 0, kMmaWarp = kTmaWarp + 1, kAllocWarp = kTmaWarp + 2;   // second MMA warp: kTmaWarp + 3
+    constexpr int kTmaWarp = kServiceHigh ? 8 : 0, kMmaWarp = kTmaWarp + 1;
+    constexpr int kAllocWarp = kIssuers == 2 ? kTmaWarp + 2 : kTmaWarp + 5;     // (2 issuers: warps kMmaWarp and kMmaWarp + 2)
     const int n_row_tiles = (T + kRowsPerCta - 1) / kRowsPerCta;
     const int n_tiles = K / kTileN;
     const int n_groups = n_tiles / kGroupTiles;
@@ -166,7 +178,7 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     if (warp == kMmaWarp && lane == 0) {
         for (int s = 0; s < kBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 2); }   // both MMA warps commit
         for (int q = 0; q < 4; ++q) { mbar_init(t_full(q), 1); mbar_init(t_empty(q), 4); }     // one arrive per epilogue warp of the half
-        for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 2); }
+        for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), kIssuers); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kAllocWarp) {
@@ -185,7 +197,7 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     // every role reads the TMEM base address itself, after its setmaxnreg: a value kept live across the role
     // split ends up in a local-memory spill slot that the epilogue would reload once per tile
 
-    if (warp >= kTmaWarp && warp < kTmaWarp + 4) {
+    if (warp >= kTmaWarp && warp < kTmaWarp + (kThreads - 256) / 32) {
         reg_dec<kRegsService>();
         if (warp == kTmaWarp) {
             // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
@@ -211,13 +223,15 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                 }
             }
             VQ_INSTR_END(0, 2);
-        } else if (warp == kMmaWarp || warp == kMmaWarp + 2) {
-            // ===================== MMA issuers: one warp per row half (whole warp loops, one elected lane issues) ==========
-            // At D = 32 a 128 x 128 x 32 unit is only 128 tensor cycles, so the issue path (barrier wait, descriptors,
-            // 2 x tcgen05.mma, commit) of a single thread would be the bottleneck; the two halves are independent.
-            const int r = (warp == kMmaWarp) ? 0 : 1;
+        } else if (kIssuers == 2 ? (warp == kMmaWarp || warp == kMmaWarp + 2) : (warp >= kMmaWarp && warp < kMmaWarp + 4)) {
+            // ===================== MMA issuers (whole warp loops, one elected lane issues) ==========
+            // r: row half; with 4 issuers also p0: the n-tile parity (= accumulator stage 2 p0 + r) this warp serves
+            const int iw = warp - kMmaWarp;
+            const int r = kIssuers == 2 ? (iw >> 1) : (iw & 1);
+            const int p0 = kIssuers == 2 ? 0 : (iw >> 1);
+            constexpr int kStep = kIssuers == 2 ? 1 : 2;               // n-tiles between two tiles of this issuer
             const uint32_t tmem_base = *tmem_slot;
-            uint32_t b_cnt = 0, t_cnt = 0;
+            uint32_t t_cnt = 0;                                        // tiles issued by this warp
             int it = 0;
             VQ_INSTR_BEGIN();
             for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
@@ -225,33 +239,36 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                 VQ_TIMED_WAIT(0, a_full(as), ((uint32_t)(it >> 1)) & 1u);
                 tc_fence_after();
                 const uint32_t a_addr = smem_base + L.a + as * kABytes + r * (128 * 64);
-                for (int n = 0; n < n_tiles; n += 2) {
+                for (int n = p0; n < n_tiles; n += kStep, ++t_cnt) {
+                    const int p = n & 1;                               // accumulator stage 2p + r
+                    const uint32_t b_cnt = (uint32_t)it * (uint32_t)n_tiles + (uint32_t)n;
+                    const int s = b_cnt % kBStages;
+                    VQ_TIMED_WAIT(2, b_full(s), (b_cnt / kBStages) & 1u);
+                    // uses of stage 2p + r so far: every tile of this half with parity p
+                    const uint32_t use = kIssuers == 2 ? (t_cnt >> 1) : t_cnt;
+                    VQ_TIMED_WAIT(1, t_empty(2 * p + r), (use & 1u) ^ 1u);
+                    tc_fence_after();
+                    if (iw == 0 && lane == 0) VQ_TRACE(0, (int)t_cnt, 0);
+                    const uint32_t b_addr = smem_base + L.b + s * kBStageBytes;
+                    VQ_TIMED_BEGIN();
+                    if (elect_one()) {
 #pragma unroll
-                    for (int p = 0; p < 2; ++p, ++t_cnt, ++b_cnt) {      // n-tile n + p -> accumulator stage 2p + r
-                        const int s = b_cnt % kBStages;
-                        VQ_TIMED_WAIT(2, b_full(s), (b_cnt / kBStages) & 1u);
-                        VQ_TIMED_WAIT(1, t_empty(2 * p + r), ((t_cnt >> 1) & 1u) ^ 1u);
-                        tc_fence_after();
-                        if (r == 0 && lane == 0) VQ_TRACE(0, (int)t_cnt, 0);
-                        const uint32_t b_addr = smem_base + L.b + s * kBStageBytes;
-                        VQ_TIMED_BEGIN();
-                        if (elect_one()) {
-#pragma unroll
-                            for (int k = 0; k < 2; ++k)
-                                umma_f16(tmem_base + (uint32_t)((p * 2 + r) * kTileN), umma_desc(a_addr + k * 32),
-                                         umma_desc(b_addr + k * 32), kIdesc, (uint32_t)k);
-                            umma_commit(t_full(2 * p + r));
-                            umma_commit(b_empty(s));
-                        }
-                        __syncwarp();
-                        if (r == 0 && lane == 0) VQ_TRACE(0, (int)t_cnt, 1);
-                        VQ_TIMED_END(3);
+                        for (int k = 0; k < 2; ++k)
+                            umma_f16(tmem_base + (uint32_t)((p * 2 + r) * kTileN), umma_desc(a_addr + k * 32),
+                                     umma_desc(b_addr + k * 32), kIdesc, (uint32_t)k);
+                        umma_commit(t_full(2 * p + r));
+                        umma_commit(b_empty(s));
                     }
+                    __syncwarp();
+                    if (iw == 0 && lane == 0) VQ_TRACE(0, (int)t_cnt, 1);
+                    VQ_TIMED_END(3);
                 }
                 if (elect_one()) umma_commit(a_empty(as));
                 __syncwarp();
             }
-            if (r == 0) { VQ_INSTR_END(3, 4); }
+            const int r_report = iw;
+            (void)r_report;
+            if (iw == 0) { VQ_INSTR_END(3, 4); }
         }
     } else {
         // ===================== epilogue: 8 warps, one thread per row =====================
@@ -320,6 +337,10 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                 for (int b = 0; b < kGroupTiles; ++b) {
                     uint32_t (&cur)[64] = (b & 1) ? bufB : bufA;
                     uint32_t (&nxt)[64] = (b & 1) ? bufA : bufB;
+                    const bool has_next = b < kGroupTiles - 1 || g + 1 < n_groups;
+                    // probe "next tile finished?" while this tile's tcgen05.ld is still in flight: a blocking wait costs
+                    // ~90 cycles even on a completed phase, and here it would sit between "stage released" and the next load
+                    const uint32_t next_ready = has_next ? mbar_test(t_full(2 * ((b + 1) & 1) + r_sub), ((t_cnt + 1) >> 1) & 1u) : 0u;
                     VQ_TIMED_BEGIN();
                     tmem_ld_wait();                                   // tile b is in registers: its TMEM stage is free
                     VQ_TIMED_END(2);
@@ -330,7 +351,8 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                     if (lane == 0) mbar_arrive(t_empty(2 * (b & 1) + r_sub));
                     if (e == 0 && lane == 0) VQ_TRACE(1, (int)t_cnt, 2);
                     ++t_cnt;
-                    if (b < kGroupTiles - 1 || g + 1 < n_groups) {
+                    if (has_next) {
+                        if (!next_ready)
                         VQ_TIMED_WAIT(0, t_full(2 * ((b + 1) & 1) + r_sub), (t_cnt >> 1) & 1u);
                         if (e == 0 && lane == 0) VQ_TRACE(1, (int)t_cnt, 0);
                         tc_fence_after();
@@ -453,6 +475,7 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 constexpr int kAccStages = 3;
 constexpr int kACol = kAccStages * kTileN;
 constexpr int kBStagesTs = 8;
+constexpr int kThreadsTs = 384;        // warps 0-7 epilogue, 8 TMA, 9-11 MMA issuers (10 also allocates TMEM)
 // setmaxnreg moves registers inside the pool the block was launched with (384 threads x 168): the epilogue's increase
 // blocks forever if the two budgets add up to more than that
 constexpr int kRegsServiceTs = 56, kRegsEpilogueTs = 224;
@@ -488,7 +511,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint4 (&v)[4]) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsTs, 1)
 k_dist_tc16_ts(const __grid_constant__ CUtensorMap tm_b, const uint4* __restrict__ zn16, int T, int K,
                const int* __restrict__ cb_info, int4* __restrict__ rec, int* __restrict__ flagged, int* __restrict__ n_flagged,
                int64_t* __restrict__ stats) {
@@ -1159,7 +1182,7 @@ cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T
             e = cudaFuncSetAttribute(tc16::k_dist_tc16_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
             if (e != cudaSuccess) return e;
         }
-        e = launch_pdl(tc16::k_dist_tc16_ts, dim3(grid), dim3(tc16::kThreads), L.total + 1024, s, mb,
+        e = launch_pdl(tc16::k_dist_tc16_ts, dim3(grid), dim3(tc16::kThreadsTs), L.total + 1024, s, mb,
                        reinterpret_cast<const uint4*>(zn16), T, cb.K, cb.info, rec, flagged, n_flagged, stats);
     }
     count_launch();

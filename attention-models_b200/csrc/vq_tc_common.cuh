@@ -36,6 +36,19 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
         : "memory");
     return done;
 }
+// non-blocking probe of a phase (mbarrier.test_wait): issued early, its result is consumed later, so its latency hides
+// behind whatever the thread waits for in between
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done;
+}
 // Bounded wait: a broken pipeline traps (launch failure) instead of hanging the GPU.  try_wait itself
 // suspends the thread for a hardware-defined window, so the retry loop is just try_wait + counter:
 // no clock reads, (almost) no issue slots stolen from the epilogue warps sharing the scheduler.

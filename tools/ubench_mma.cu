@@ -103,6 +103,61 @@ __global__ void __launch_bounds__(128, 1) k_mma(long long* out, int mode, int n,
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+// `issuers` warps issue `iters` MMAs each (own accumulator columns, shared operands); block time / total MMAs
+__global__ void __launch_bounds__(128, 1) k_mma_multi(long long* out, int n, int iters, int issuers) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(8) uint64_t bar[4];
+    __shared__ long long t_end[4];
+    const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+    for (int i = threadIdx.x; i < (8192 + 4 * 16384) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[i])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    const uint32_t a_smem = smem_u32(smem), b_smem = a_smem + 8192;
+    const uint32_t idesc = ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const int uwarp = __shfl_sync(0xffffffffu, warp, 0);
+    const long long t0 = clock64();
+    if (uwarp < issuers) {
+        const uint32_t d = tmem + (uint32_t)uwarp * 128;
+        for (int i = 0; i < iters; i += 8) {
+            uint32_t pred = 0;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+            if (pred) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    mma_ss(d, umma_desc(a_smem + (u & 1) * 32), umma_desc(b_smem + ((u >> 1) & 3) * 16384 + (u & 1) * 32), idesc, u & 1);
+            }
+            __syncwarp();
+        }
+        if ((threadIdx.x & 31) == 0) {
+            commit(smem_u32(&bar[uwarp]));
+            mbar_wait(smem_u32(&bar[uwarp]), 0);
+            t_end[uwarp] = clock64();
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long m = 0;
+        for (int i = 0; i < issuers; ++i) m = t_end[i] > m ? t_end[i] : m;
+        out[0] = m - t0;
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 // latencies: (a) one N-wide stage (2 MMAs, K = 32) issue -> commit -> mbarrier visible; (b) tcgen05.ld of that stage
 __global__ void __launch_bounds__(128, 1) k_lat(long long* out, int n, int reps) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -185,6 +240,16 @@ int main() {
                     printf("%s acc=%s N=%3d %s: %7.1f cycles / MMA (M=128, K=16)   nominal %d   (%s)\n", mode ? "TS" : "SS",
                            c_f32 ? "f32" : "f16", n, lds ? "+LDS traffic" : "            ", (double)c / iters, n / 2, cudaGetErrorString(e));
                 }
+    // several issuer warps, each on its own accumulator columns: does the fixed per-MMA cost overlap between threads?
+    for (int issuers : {1, 2, 4})
+        for (int n : {64, 128}) {
+            k_mma_multi<<<148, 128, smem>>>(out, n, iters, issuers);
+            cudaError_t e = cudaDeviceSynchronize();
+            long long c = 0;
+            cudaMemcpy(&c, out, 8, cudaMemcpyDeviceToHost);
+            printf("SS acc=f16 N=%3d, %d issuer warp(s): %7.1f cycles / MMA aggregated (%s)\n", n, issuers,
+                   (double)c / (iters * issuers), cudaGetErrorString(e));
+        }
     for (int n : {64, 128}) {
         k_lat<<<1, 128, smem>>>(out, n, 64);
         cudaError_t e = cudaDeviceSynchronize();
