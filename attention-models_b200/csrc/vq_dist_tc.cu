@@ -127,9 +127,10 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     const int n_groups = n_tiles / kGroupTiles;         // per item
 
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < BS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), 256); }
-        for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        // two MMA issuers (one per row half) commit to the stage / tile / row-tile barriers
+        for (int s = 0; s < BS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 2); }
+        for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 2); mbar_init(t_empty(s), 256); }
+        for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -177,8 +178,12 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             atomicAdd((unsigned long long*)&g_tc_wait[1], (unsigned long long)wait_acc[1]);
             atomicAdd((unsigned long long*)&g_tc_wait[2], (unsigned long long)(clock64() - t_begin));
 #endif
-        } else if (warp == 1 && lane == 0) {
-            // ===================== MMA issuer (one thread) =====================
+        } else if ((warp == 1 || warp == 3) && lane == 0) {
+            // ===================== MMA issuers: one thread per row half =====================
+            // A thread gets one tcgen05.mma out per ~110-140 cycles whatever its size, and issuers overlap perfectly
+            // (tools/ubench_mma.cu): with a single issuer an M = N = 128, K = 16 MMA "retired" at half rate here.  The two
+            // halves write different accumulators, so each issuer keeps its own MMAs in order and nothing else is shared.
+            const int r = warp == 3 ? 1 : 0;
             uint32_t b_cnt = 0, t_cnt = 0;
             int it = 0;
 #ifdef VQ_TC_INSTRUMENT
@@ -201,23 +206,23 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                         const uint32_t a_addr = smem_base + L.a + (as * KB + kb) * kABlockBytes;
                         const uint32_t b_addr = smem_base + L.b + s * kBStageBytes;
 #pragma unroll
-                        for (int r = 0; r < 2; ++r)
-#pragma unroll
-                            for (int k = 0; k < 2; ++k)
-                                umma_f16(tmem_base + (uint32_t)((acc * 2 + r) * kTileN),
-                                         umma_desc(a_addr + r * (128 * 64) + k * 32), umma_desc(b_addr + k * 32), kIdesc,
-                                         (uint32_t)((kb | k) != 0));
-                        umma_commit(b_empty(s));     // smem stage free once these MMAs retire
+                        for (int k = 0; k < 2; ++k)
+                            umma_f16(tmem_base + (uint32_t)((acc * 2 + r) * kTileN),
+                                     umma_desc(a_addr + r * (128 * 64) + k * 32), umma_desc(b_addr + k * 32), kIdesc,
+                                     (uint32_t)((kb | k) != 0));
+                        umma_commit(b_empty(s));     // smem stage free once these MMAs (and the other half's) retire
                     }
-                    umma_commit(t_full(acc));        // accumulators of this tile complete
+                    umma_commit(t_full(acc));        // this half's accumulator of the tile complete
                 }
-                umma_commit(a_empty(as));            // row tile's A operand no longer needed
+                umma_commit(a_empty(as));            // row tile's A operand no longer needed by this half
             }
 #ifdef VQ_TC_INSTRUMENT
-            atomicAdd((unsigned long long*)&g_tc_wait[4], (unsigned long long)wait_acc[0]);
-            atomicAdd((unsigned long long*)&g_tc_wait[5], (unsigned long long)wait_acc[1]);
-            atomicAdd((unsigned long long*)&g_tc_wait[6], (unsigned long long)wait_acc[2]);
-            atomicAdd((unsigned long long*)&g_tc_wait[7], (unsigned long long)(clock64() - t_begin));
+            if (r == 0) {
+                atomicAdd((unsigned long long*)&g_tc_wait[4], (unsigned long long)wait_acc[0]);
+                atomicAdd((unsigned long long*)&g_tc_wait[5], (unsigned long long)wait_acc[1]);
+                atomicAdd((unsigned long long*)&g_tc_wait[6], (unsigned long long)wait_acc[2]);
+                atomicAdd((unsigned long long*)&g_tc_wait[7], (unsigned long long)(clock64() - t_begin));
+            }
 #endif
         }
     } else if (warp < 8) {

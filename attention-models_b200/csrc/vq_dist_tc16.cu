@@ -338,9 +338,6 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                     uint32_t (&cur)[64] = (b & 1) ? bufB : bufA;
                     uint32_t (&nxt)[64] = (b & 1) ? bufA : bufB;
                     const bool has_next = b < kGroupTiles - 1 || g + 1 < n_groups;
-                    // probe "next tile finished?" while this tile's tcgen05.ld is still in flight: a blocking wait costs
-                    // ~90 cycles even on a completed phase, and here it would sit between "stage released" and the next load
-                    const uint32_t next_ready = has_next ? mbar_test(t_full(2 * ((b + 1) & 1) + r_sub), ((t_cnt + 1) >> 1) & 1u) : 0u;
                     VQ_TIMED_BEGIN();
                     tmem_ld_wait();                                   // tile b is in registers: its TMEM stage is free
                     VQ_TIMED_END(2);
@@ -352,7 +349,7 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                     if (e == 0 && lane == 0) VQ_TRACE(1, (int)t_cnt, 2);
                     ++t_cnt;
                     if (has_next) {
-                        if (!next_ready)
+                        // (probing this barrier with mbarrier.test_wait ahead of the tcgen05.wait::ld above was measured: no gain)
                         VQ_TIMED_WAIT(0, t_full(2 * ((b + 1) & 1) + r_sub), (t_cnt >> 1) & 1u);
                         if (e == 0 && lane == 0) VQ_TRACE(1, (int)t_cnt, 0);
                         tc_fence_after();
