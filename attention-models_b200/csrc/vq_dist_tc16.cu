@@ -979,40 +979,104 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
         }
         // (fetching the next iteration's record / row with cp.async into a second buffer was measured: no gain, the kernel
         // is bound by L1 wavefronts -- 70 % of peak in ncu -- not by the latency of these first loads)
-        __syncwarp();                                   // the previous iteration's reads of s_z / s_df are done
-        s_z[warp][grp][m] = nz;
-        __syncwarp();
-        const float4* zs = s_z[warp][grp];
         const bool valid = in_range && ((uint32_t)r.x & 0xFFFFu) != 0xFFFFu;
+        const uint32_t w0i = (uint32_t)r.x, w1i = (uint32_t)r.y, w2i = (uint32_t)r.z, w3i = (uint32_t)r.w;
         // this lane's best over the row's cells: (ordered distance, code), and the ordered distance of its runner-up
-        uint32_t bo = 0xFFFFFFFFu, so = 0xFFFFFFFFu;
-        int bc = 0x7FFFFFFF;
-        uint32_t w0 = (uint32_t)r.x, w1 = (uint32_t)r.y, w2 = (uint32_t)r.z, w3 = (uint32_t)r.w;
-        int n_cells = 0;
-        while ((w0 & 0xFFFFu) != 0xFFFFu) {             // per group: its own cell count (1 for ~7 rows of 8)
-            const int ci = (int)(w0 & 0xFFFFu);
-            w0 = __funnelshift_r(w0, w1, 16); w1 = __funnelshift_r(w1, w2, 16); w2 = __funnelshift_r(w2, w3, 16);
-            w3 = (w3 >> 16) | 0xFFFF0000u;
-            ++n_cells;
-            const float dist = cell_distance_staged(en32c, csq_cell, ci, m, zs, a_sq);
+        uint32_t bo, so;
+        int bc, n_cells;
+        auto take = [&](float dist, int code) {
             const uint32_t o = dist_ord(dist);
-            const int code = (ci >> 6) * kGroupCols + (ci & 63) + 64 * m;
             const bool wins = (o < bo) || (o == bo && code < bc);
             so = wins ? bo : min(so, o);
             bc = wins ? code : bc;
             bo = wins ? o : bo;
+        };
+        // Fast pass.  Lane m keeps chunk m of its row in registers and reads chunk m of each of the cell's 8 members (one
+        // whole 128-byte line of the row-major unit codes per member and row); the 8 x 8 partial sums are transposed and
+        // added with 7 shuffles, after which lane m holds the dot product of member m.  No shared-memory staging, no
+        // broadcast reads of the row: a third fewer L1 wavefronts than a full dot product per lane.  The summation
+        // order differs from the library's reference chain (one sequential fma chain over d = 0..31, vq_dist_simt.cu), by
+        // at most ~1.5e-6 in the distance of unit vectors: rows whose two best candidates are closer than kSafeGap fall
+        // through to the chain below, everything else is decided here with the same index the chain would give.
+        constexpr float kSafeGapAbs = 1e-5f, kSafeGapRel = 2e-5f;
+        {
+            bo = so = 0xFFFFFFFFu; bc = 0x7FFFFFFF; n_cells = 0;
+            uint32_t w0 = w0i, w1 = w1i, w2 = w2i, w3 = w3i;
+            // cells of this group; the loop is warp-uniform (shuffles inside): groups with fewer cells idle
+            int mine = 0;
+            { uint32_t t0 = w0i, t1 = w1i, t2 = w2i, t3 = w3i;
+              while ((t0 & 0xFFFFu) != 0xFFFFu) { ++mine; t0 = __funnelshift_r(t0, t1, 16); t1 = __funnelshift_r(t1, t2, 16); t2 = __funnelshift_r(t2, t3, 16); t3 = (t3 >> 16) | 0xFFFF0000u; } }
+            if (!valid) mine = 0;
+            const int trips = __reduce_max_sync(VQ_FULL, mine);
+            n_cells = mine;
+            for (int c = 0; c < trips; ++c) {
+                const bool on = c < mine;
+                const int ci = on ? (int)(w0 & 0xFFFFu) : 0;
+                w0 = __funnelshift_r(w0, w1, 16); w1 = __funnelshift_r(w1, w2, 16); w2 = __funnelshift_r(w2, w3, 16);
+                w3 = (w3 >> 16) | 0xFFFF0000u;
+                const int code0 = (ci >> 6) * kGroupCols + (ci & 63);
+                float p[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (on) e = __ldg(en4 + (int64_t)(code0 + 64 * j) * (kD / 4) + m);
+                    p[j] = __fmaf_rn(nz.w, e.w, __fmaf_rn(nz.z, e.z, __fmaf_rn(nz.y, e.y, __fmul_rn(nz.x, e.x))));
+                }
+                const float csq = on ? __ldg(csq_cell + ci * 8 + m) : 0.f;
+                float q4[4], q2[2];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float recv = __shfl_xor_sync(VQ_FULL, (m & 4) ? p[i] : p[i + 4], 4);
+                    q4[i] = ((m & 4) ? p[i + 4] : p[i]) + recv;
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float recv = __shfl_xor_sync(VQ_FULL, (m & 2) ? q4[i] : q4[i + 2], 2);
+                    q2[i] = ((m & 2) ? q4[i + 2] : q4[i]) + recv;
+                }
+                const float recv = __shfl_xor_sync(VQ_FULL, (m & 1) ? q2[0] : q2[1], 1);
+                const float dot = ((m & 1) ? q2[1] : q2[0]) + recv;
+                if (on) take(ref_distance(a_sq, csq, dot), code0 + 64 * m);
+            }
         }
-        // minimum over the 8 lanes of the group, ties to the lowest code
-        uint32_t omin = bo;
+        uint32_t omin;
+        int code;
+        float bd, runner;
+        auto group_argmin = [&]() {
+            // minimum over the 8 lanes of the group, ties to the lowest code
+            omin = bo;
 #pragma unroll
-        for (int off = 4; off > 0; off >>= 1) omin = min(omin, __shfl_xor_sync(VQ_FULL, omin, off));
-        int code = (bo == omin) ? bc : 0x7FFFFFFF;
+            for (int off = 4; off > 0; off >>= 1) omin = min(omin, __shfl_xor_sync(VQ_FULL, omin, off));
+            code = (bo == omin) ? bc : 0x7FFFFFFF;
 #pragma unroll
-        for (int off = 4; off > 0; off >>= 1) code = min(code, __shfl_xor_sync(VQ_FULL, code, off));
-        // near tie: some other candidate of the row within 1e-6 relative of the best distance
-        const float bd = ord_dist(omin);
-        const float runner = ord_dist((bc == code) ? so : bo);
-        const bool close = valid && (runner - bd < VQ_NEAR_TIE_REL * fabsf(bd));
+            for (int off = 4; off > 0; off >>= 1) code = min(code, __shfl_xor_sync(VQ_FULL, code, off));
+            bd = ord_dist(omin);
+            runner = ord_dist((bc == code) ? so : bo);      // (a lane without a second candidate reports NaN: no candidate)
+        };
+        group_argmin();
+        // a lane vetoes the fast verdict if one of ITS other candidates is not safely behind the best (NaN anywhere: veto)
+        const bool has_runner = ((bc == code) ? so : bo) != 0xFFFFFFFFu;
+        const bool unsafe = valid && ((bd != bd) || (has_runner && !(runner - bd > kSafeGapAbs + kSafeGapRel * fabsf(bd))));
+        bool close = false;
+        if (__any_sync(VQ_FULL, unsafe)) {
+            // the library's reference chain for the whole warp iteration (a few rows per 10 000 get here): rows staged
+            // in shared memory, lane m owns member m of every cell and runs the sequential fma chain over d = 0..31
+            __syncwarp();                               // the previous iteration's reads of s_z / s_df are done
+            s_z[warp][grp][m] = nz;
+            __syncwarp();
+            const float4* zs = s_z[warp][grp];
+            bo = so = 0xFFFFFFFFu; bc = 0x7FFFFFFF;
+            uint32_t w0 = w0i, w1 = w1i, w2 = w2i, w3 = w3i;
+            while (valid && (w0 & 0xFFFFu) != 0xFFFFu) {
+                const int ci = (int)(w0 & 0xFFFFu);
+                w0 = __funnelshift_r(w0, w1, 16); w1 = __funnelshift_r(w1, w2, 16); w2 = __funnelshift_r(w2, w3, 16);
+                w3 = (w3 >> 16) | 0xFFFF0000u;
+                take(cell_distance_staged(en32c, csq_cell, ci, m, zs, a_sq), (ci >> 6) * kGroupCols + (ci & 63) + 64 * m);
+            }
+            group_argmin();
+            // near tie: some other candidate of the row within 1e-6 relative of the best distance
+            close = valid && (runner - bd < VQ_NEAR_TIE_REL * fabsf(bd));
+        }
         const uint32_t close_ballot = __ballot_sync(VQ_FULL, close);
         // rows of the warp that chose the same code (collapsed codebooks): their histogram count and segment-sum terms
         // are added once, by the first of them -- the L2 serialises reductions per address
@@ -1027,8 +1091,9 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
         }
         if (out.zq) {                                   // uniform
             float4 df = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) df = finish_chunk(zs[m], en4, out, row, code, m, loss_fx, bad);
+            if (valid) df = finish_chunk(nz, en4, out, row, code, m, loss_fx, bad);
             if (out.seg) {                              // uniform
+                __syncwarp();                           // the previous iteration's reads of s_df are done
                 s_df[warp][grp][m] = df;
                 __syncwarp();
                 if (!dup) {
