@@ -50,7 +50,7 @@ def main():
             agg.setdefault(name, []).append(float(r["Metric Value"]))
         skip = ("distribution_elementwise", "vectorized_elementwise", "unrolled_elementwise")
         agg = collections.OrderedDict((k, v) for k, v in agg.items() if not any(s in k for s in skip))
-        steps = min(len(v) for v in agg.values())
+        steps = len(max(agg.values(), key=sum))      # launches of the heaviest kernel: one per step
         tot = sum(sum(v) / steps for v in agg.values())
         print(f"## launch list (`{sys.argv[2].split('/')[-1]}`, gpu__time_duration.sum, {steps} steps)\n")
         print("| kernel | launches | mean us | us/step | share |\n|---|---:|---:|---:|---:|")
