@@ -452,6 +452,329 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 
 
 // ---------------------------------------------------------------------------------------------------------------
+// The filter with a WIDE DRAIN: 16 epilogue warps instead of 8.
+//
+// The idea: with four MMA issuers the first kernel above looked bound by the serial latency of an epilogue warp's
+// per-tile loop (wait for the finished tile -> tcgen05.ld -> release -> fold, ~500 cycles) with only two such warps per
+// scheduler.  MEASURED: no faster (see tc16_wide_drain below); kept as the measured alternative.  Here every 128 x 128 accumulator tile is drained by EIGHT warps -- two per TMEM lane
+// quarter, each taking one 64-column half (tcgen05.ld.x32.pack::16b: 32 registers) -- so four epilogue warps per scheduler
+// hide each other's hand-off waits, and a thread needs 16 slot registers + one 32-register load buffer (96-register
+// budget, 768 threads).  A thread folds column c with c + 32 of its half over the 4 tiles of a group: a slot is again a
+// cell of 8 codes (cell layout 3 in vq_kernels.h), 32 cells per thread and group, 64-byte snapshots (swizzled chunks
+// instead of row padding: 4 areas x 512 threads x 64 B = 128 KB).  A row's verdict is taken by its TWO threads: they
+// exchange their best scores through shared memory, each marks the cells of its half within 2 eps of the row's best
+// and fills its own half of the 16-byte record (up to 4 cell ids each); the row is decided iff both halves are.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kThreadsW = 768;         // warps 0-15 epilogue, 16 TMA, 17-20 MMA issuers (one per accumulator stage), 21 TMEM allocator
+constexpr int kRegsServiceW = 40, kRegsEpilogueW = 96;
+static_assert(256 * kRegsServiceW + 512 * kRegsEpilogueW <= (65536 / kThreadsW / 8 * 8) * kThreadsW, "register pool overcommitted");
+constexpr int kSnapRowW = 64;                              // 16 packed slot registers, chunk order swizzled by the lane
+constexpr int kSnapAreaW = 2 * kRowsPerCta * kSnapRowW;    // 32 KB: both column halves of 256 rows
+struct SmemLayoutW {
+    uint32_t a, b, snap, xch, bars, tmem_slot, total;
+};
+__host__ __device__ inline SmemLayoutW smem_layout_w() {
+    SmemLayoutW L;
+    L.a = 0;
+    L.b = L.a + kAStages * kABytes;
+    L.snap = L.b + kBStages * kBStageBytes;
+    L.xch = L.snap + kAreas * kSnapAreaW;                  // [2 rounds][256 rows][2 halves] ints: best score / decided
+    L.bars = L.xch + 2 * kRowsPerCta * 2 * 4;
+    L.tmem_slot = L.bars + 8 * 32;
+    L.total = L.tmem_slot + 16;
+    return L;
+}
+// 32 lanes x 64 columns of fp16 accumulators, two adjacent columns per register
+__device__ __forceinline__ void tmem_ld_half_tile(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void pair_barrier(int id) {      // the two warps that own the same 32 rows (64 threads)
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreadsW, 1)
+k_dist_tc16_w16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int T, int K,
+                const int* __restrict__ cb_info, uint2* __restrict__ rec, int* __restrict__ flagged, int* __restrict__ n_flagged,
+                int64_t* __restrict__ stats) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const SmemLayoutW L = smem_layout_w();
+    const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + L.bars;
+    auto b_full = [&](int s) { return bar_base + 8 * s; };
+    auto b_empty = [&](int s) { return bar_base + 8 * (8 + s); };
+    // accumulator stage q = 2 * (n-tile parity) + (row half): 128 rows x 128 codes, i.e. 128 TMEM columns
+    auto t_full = [&](int q) { return bar_base + 8 * (16 + q); };
+    auto t_empty = [&](int q) { return bar_base + 8 * (20 + q); };
+    auto a_full = [&](int s) { return bar_base + 8 * (24 + s); };
+    auto a_empty = [&](int s) { return bar_base + 8 * (26 + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_slot);
+
+    const int warp = __shfl_sync(VQ_FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    constexpr int kTmaWarp = 16, kMmaWarp = 17, kAllocWarp = 21;
+    const int n_row_tiles = (T + kRowsPerCta - 1) / kRowsPerCta;
+    const int n_tiles = K / kTileN;
+    const int n_groups = n_tiles / kGroupTiles;
+
+    if (warp == kMmaWarp && lane == 0) {
+        for (int s = 0; s < kBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 2); }   // both halves' issuers commit
+        for (int q = 0; q < 4; ++q) { mbar_init(t_full(q), 1); mbar_init(t_empty(q), 8); }          // 8 warps drain a stage
+        for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 4); }          // 4 issuers
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kAllocWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + L.tmem_slot),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    pdl_trigger();
+    pdl_wait();
+
+    if (warp >= kTmaWarp) {
+        reg_dec<kRegsServiceW>();
+        if (warp == kTmaWarp) {
+            // ===================== TMA producer =====================
+            uint32_t b_cnt = 0;
+            int it = 0;
+            VQ_INSTR_BEGIN();
+            for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
+                const int as = it & 1;
+                VQ_TIMED_WAIT(0, a_empty(as), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+                if (elect_one()) {
+                    mbar_expect_tx(a_full(as), kABytes);
+                    tma_load_2d(smem_base + L.a + as * kABytes, &tm_a, a_full(as), 0, rt * kRowsPerCta);
+                }
+                __syncwarp();
+                for (int n = 0; n < n_tiles; ++n, ++b_cnt) {
+                    const int s = b_cnt % kBStages;
+                    VQ_TIMED_WAIT(1, b_empty(s), ((b_cnt / kBStages) & 1u) ^ 1u);
+                    if (elect_one()) {
+                        mbar_expect_tx(b_full(s), kBStageBytes);
+                        tma_load_2d(smem_base + L.b + s * kBStageBytes, &tm_b, b_full(s), 0, n * kTileN);
+                    }
+                    __syncwarp();
+                }
+            }
+            VQ_INSTR_END(0, 2);
+        } else if (warp >= kMmaWarp && warp < kMmaWarp + 4) {
+            // ===================== MMA issuers: one warp per accumulator stage (row half r, n-tile parity p0) =====================
+            const int iw = warp - kMmaWarp;
+            const int r = iw & 1, p0 = iw >> 1;
+            const uint32_t tmem_base = *tmem_slot;
+            uint32_t t_cnt = 0;
+            int it = 0;
+            VQ_INSTR_BEGIN();
+            for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
+                const int as = it & 1;
+                VQ_TIMED_WAIT(0, a_full(as), ((uint32_t)(it >> 1)) & 1u);
+                tc_fence_after();
+                const uint32_t a_addr = smem_base + L.a + as * kABytes + r * (128 * 64);
+                for (int n = p0; n < n_tiles; n += 2, ++t_cnt) {
+                    const uint32_t b_cnt = (uint32_t)it * (uint32_t)n_tiles + (uint32_t)n;
+                    const int s = b_cnt % kBStages;
+                    VQ_TIMED_WAIT(2, b_full(s), (b_cnt / kBStages) & 1u);
+                    VQ_TIMED_WAIT(1, t_empty(2 * p0 + r), (t_cnt & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_base + L.b + s * kBStageBytes;
+                    VQ_TIMED_BEGIN();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
+                            umma_f16(tmem_base + (uint32_t)((p0 * 2 + r) * kTileN), umma_desc(a_addr + k * 32),
+                                     umma_desc(b_addr + k * 32), kIdesc, (uint32_t)k);
+                        umma_commit(t_full(2 * p0 + r));
+                        umma_commit(b_empty(s));
+                    }
+                    __syncwarp();
+                    VQ_TIMED_END(3);
+                }
+                if (elect_one()) umma_commit(a_empty(as));
+                __syncwarp();
+            }
+            if (iw == 0) { VQ_INSTR_END(3, 4); }
+        }
+    } else {
+        // ===================== epilogue: 16 warps; thread = (row, column half) =====================
+        reg_inc<kRegsEpilogueW>();
+        VQ_INSTR_BEGIN();
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may read (warp id mod 4)
+        const int r_sub = (warp >> 2) & 1;           // which 128-row MMA tile
+        const int h2 = warp >> 3;                    // which 64-column half of every tile
+        const int row_in_cta = r_sub * 128 + quarter * 32 + lane;
+        const uint32_t tbase = *tmem_slot + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(r_sub * kTileN + h2 * 64);
+        const uint32_t snap0 = smem_base + L.snap + (uint32_t)(h2 * kRowsPerCta + row_in_cta) * kSnapRowW;
+        const uint32_t swz = (uint32_t)((lane >> 1) & 3);          // chunk swizzle: conflict-free 16-byte accesses at a 64-byte stride
+        volatile int* xch = reinterpret_cast<volatile int*>(smem + L.xch);
+        const int pair_id = 1 + r_sub * 4 + quarter;               // named barrier of the two warps that share these 32 rows
+        const bool force_exhaustive = codebook_degenerate(cb_info);
+        uint32_t t_cnt = 0;                          // n-tiles drained so far (same sequence as the issuers)
+        uint32_t bufA[32], bufB[32];
+        for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
+            uint32_t slot[16];
+            // the best four groups of this thread's column half as sorted keys (score << 16 | group << 2 | snapshot area):
+            // one register each, and the sorted insert is 9 min / max
+            // (k4 is always the smallest KEY, low bits included: it is the entry a better group pushes out)
+            int k1 = (int)0x80000000 | 3, k2 = (int)0x80000000 | 2, k3 = (int)0x80000000 | 1, k4 = (int)0x80000000 | 0;
+            int m5 = -32768;
+            auto group_end = [&](const int g) {
+                uint32_t t[6];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) t[j] = __vimax3_s16x2(slot[3 * j], slot[3 * j + 1], slot[3 * j + 2]);
+                t[5] = slot[15];
+                const uint32_t pk = __vimax3_s16x2(__vimax3_s16x2(t[0], t[1], t[2]), __vimax3_s16x2(t[3], t[4], t[5]), t[5]);
+                const int c1 = max(lo16(pk), hi16(pk));
+                const uint32_t area = (uint32_t)k4 & 3u;            // the entry that drops out frees its area
+                const int nk = (c1 << 16) | (g << 2) | (int)area;
+                if (nk > k4) {
+                    const uint32_t dst = snap0 + area * kSnapAreaW;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16 * ((uint32_t)q ^ swz)), "r"(slot[4 * q]),
+                                     "r"(slot[4 * q + 1]), "r"(slot[4 * q + 2]), "r"(slot[4 * q + 3])
+                                     : "memory");
+                }
+                const int lo1 = min(nk, k1);
+                k1 = max(nk, k1);
+                const int lo2 = min(lo1, k2);
+                k2 = max(lo1, k2);
+                const int lo3 = min(lo2, k3);
+                k3 = max(lo2, k3);
+                const int lo4 = min(lo3, k4);
+                k4 = max(lo3, k4);
+                m5 = max(m5, lo4 >> 16);
+            };
+            {
+                VQ_TIMED_WAIT(0, t_full(r_sub), (t_cnt >> 1) & 1u);
+                tc_fence_after();
+                tmem_ld_half_tile(tbase, bufA);
+            }
+            for (int g = 0; g < n_groups; ++g) {
+#pragma unroll
+                for (int b = 0; b < kGroupTiles; ++b) {
+                    uint32_t (&cur)[32] = (b & 1) ? bufB : bufA;
+                    uint32_t (&nxt)[32] = (b & 1) ? bufA : bufB;
+                    VQ_TIMED_BEGIN();
+                    tmem_ld_wait();                                   // this half of tile b is in registers
+                    VQ_TIMED_END(2);
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(t_empty(2 * (b & 1) + r_sub));
+                    ++t_cnt;
+                    if (b < kGroupTiles - 1 || g + 1 < n_groups) {
+                        VQ_TIMED_WAIT(0, t_full(2 * ((b + 1) & 1) + r_sub), (t_cnt >> 1) & 1u);
+                        tc_fence_after();
+#if !defined(VQ_EXP) || VQ_EXP < 2
+                        tmem_ld_half_tile(tbase + (uint32_t)(((b + 1) & 1) * 2 * kTileN), nxt);
+#endif
+                    }
+#if defined(VQ_EXP) && VQ_EXP >= 1
+                    // timing experiment only (results are garbage): no fold / bookkeeping
+                    if (b == 0 && g == 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) slot[j] = cur[j] ^ cur[j + 16];
+                    } else { slot[0] ^= cur[0] ^ cur[31]; }
+#else
+                    if (b == 0) {
+                        if (g > 0) group_end(g - 1);                  // behind the hand-off of this tile's stage
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) slot[j] = __vmaxs2(cur[j], cur[j + 16]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) slot[j] = __vimax3_s16x2(slot[j], cur[j], cur[j + 16]);
+                    }
+#endif
+                }
+            }
+            group_end(n_groups - 1);
+            const int m1 = k1 >> 16;
+            // ---- row verdict, taken by the row's two threads ----
+            xch[row_in_cta * 2 + h2] = m1;
+            pair_barrier(pair_id);
+            const int m1_row = max(m1, xch[row_in_cta * 2 + (h2 ^ 1)]);
+            const float m1f = __half2float(__ushort_as_half((unsigned short)(m1_row & 0xFFFF)));
+            const float thr_f = m1f - (m1f < 0.9f ? kTwoEps : kTwoEpsNearOne);
+            const bool thr_ok = (m1_row >= 0) && (m1_row < 0x7C00) && (thr_f >= kMinThreshold);
+            const int thr = thr_ok ? (int)__half_as_ushort(__float2half_rd(thr_f)) : 0x7BFF;
+            const uint32_t thr2 = (uint32_t)thr * 0x10001u;
+            uint32_t mask[4] = {0u, 0u, 0u, 0u};
+            const int kv[4] = {k1, k2, k3, k4};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                if ((kv[a] >> 16) >= thr) {
+                    const uint32_t src = snap0 + ((uint32_t)kv[a] & 3u) * kSnapAreaW;
+                    uint32_t kept[16];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(kept[4 * q]), "=r"(kept[4 * q + 1]), "=r"(kept[4 * q + 2]), "=r"(kept[4 * q + 3])
+                                     : "r"(src + 16 * ((uint32_t)q ^ swz)));
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        bool ph, pl;
+                        (void)__vibmax_s16x2(kept[j], thr2, &ph, &pl);      // per half: kept >= thr
+                        mask[a] |= (pl ? (1u << (2 * j)) : 0u) | (ph ? (1u << (2 * j + 1)) : 0u);
+                    }
+                }
+            }
+            const int n_cand = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
+            const bool mine_ok = thr_ok && (m5 < thr) && (n_cand <= kRecCells / 2) && !force_exhaustive;
+            xch[2 * kRowsPerCta + row_in_cta * 2 + h2] = mine_ok ? 1 : 0;
+            pair_barrier(pair_id);
+            const bool decided = mine_ok && (xch[2 * kRowsPerCta + row_in_cta * 2 + (h2 ^ 1)] != 0);
+            const int row = rt * kRowsPerCta + row_in_cta;
+            const bool in_range = row < T;
+            // this thread's half of the record: its surviving cells as 16-bit ids (group * 64 + half * 32 + slot), 0xFFFF = none
+            unsigned long long half_rec = ~0ull;
+            if (decided) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    uint32_t w = mask[a];
+                    while (w) {
+                        const uint32_t id = (uint32_t)((kv[a] >> 2) & 0x3FFF) * 64u + 32u * (uint32_t)h2 + (uint32_t)(__ffs((int)w) - 1);
+                        w &= w - 1;
+                        half_rec = (half_rec << 16) | id;
+                    }
+                }
+            }
+            if (in_range) rec[2 * (int64_t)row + h2] = make_uint2((uint32_t)half_rec, (uint32_t)(half_rec >> 32));
+            if (h2 == 0) {                           // warp-uniform: one of the two warps lists the undecided rows
+                const bool flag = in_range && !decided;
+                const uint32_t ballot = __ballot_sync(VQ_FULL, flag);
+                if (ballot) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(n_flagged, __popc(ballot));
+                    base = __shfl_sync(VQ_FULL, base, 0);
+                    if (flag) flagged[base + __popc(ballot & ((1u << lane) - 1))] = row;
+                    if (lane == 0 && stats)
+                        atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_FALLBACK_ROWS),
+                                  (unsigned long long)__popc(ballot));
+                }
+            }
+            pair_barrier(pair_id);                   // the exchange words are free for the next row tile
+        }
+        if (threadIdx.x == 0) { VQ_INSTR_END(8, 3); }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kAllocWarp) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // The filter with the token rows in TENSOR MEMORY (tcgen05.mma "TS" form: A from TMEM, B from shared memory).
 //
 // Why: an M = 128, K = 16 MMA costs a fixed ~60 cycles on top of ~0.42 cycles per column when A comes from shared
@@ -942,7 +1265,8 @@ __global__ void __launch_bounds__(kExactThreads, VQ_EXACT_MIN_BLOCKS)
 k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, const float* __restrict__ row_sq,
                  const float* __restrict__ en32, const float4* __restrict__ en32c, const float* __restrict__ csq_cell, int T,
                  int K, const int* __restrict__ flagged, const int* __restrict__ n_flagged, int flagged_cap,
-                 FlaggedPartial* __restrict__ partial, int* __restrict__ done, FinishOut out, int64_t* __restrict__ stats) {
+                 FlaggedPartial* __restrict__ partial, int* __restrict__ done, FinishOut out, int64_t* __restrict__ stats,
+                 int cell_kind) {
     __shared__ unsigned long long s_best[kExactThreads / 32];
     __shared__ float s_second[kExactThreads / 32];
     // Row strides of 9 / 10 float4 put the 4 rows of a warp in different banks: the broadcast LDS.128 of the rescoring
@@ -979,7 +1303,7 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
         }
         // (fetching the next iteration's record / row with cp.async into a second buffer was measured: no gain, the kernel
         // is bound by L1 wavefronts -- 70 % of peak in ncu -- not by the latency of these first loads)
-        const bool valid = in_range && ((uint32_t)r.x & 0xFFFFu) != 0xFFFFu;
+        const bool valid = in_range && ((r.x & r.y & r.z & r.w) != -1);      // all-ones: the filter left the row undecided
         const uint32_t w0i = (uint32_t)r.x, w1i = (uint32_t)r.y, w2i = (uint32_t)r.z, w3i = (uint32_t)r.w;
         // this lane's best over the row's cells: (ordered distance, code), and the ordered distance of its runner-up
         uint32_t bo, so;
@@ -1002,24 +1326,33 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
         {
             bo = so = 0xFFFFFFFFu; bc = 0x7FFFFFFF; n_cells = 0;
             uint32_t w0 = w0i, w1 = w1i, w2 = w2i, w3 = w3i;
-            // cells of this group; the loop is warp-uniform (shuffles inside): groups with fewer cells idle
+            // cells of this group (record fields that are not 0xFFFF; the wide-drain filter fills the two halves of a
+            // record separately); the loop is warp-uniform (shuffles inside): groups with fewer cells idle
             int mine = 0;
-            { uint32_t t0 = w0i, t1 = w1i, t2 = w2i, t3 = w3i;
-              while ((t0 & 0xFFFFu) != 0xFFFFu) { ++mine; t0 = __funnelshift_r(t0, t1, 16); t1 = __funnelshift_r(t1, t2, 16); t2 = __funnelshift_r(t2, t3, 16); t3 = (t3 >> 16) | 0xFFFF0000u; } }
-            if (!valid) mine = 0;
+            if (valid) {
+#pragma unroll
+                for (int f = 0; f < 8; ++f) {
+                    const uint32_t wsel = f < 2 ? w0i : (f < 4 ? w1i : (f < 6 ? w2i : w3i));
+                    mine += (((wsel >> (16 * (f & 1))) & 0xFFFFu) != 0xFFFFu) ? 1 : 0;
+                }
+            }
             const int trips = __reduce_max_sync(VQ_FULL, mine);
             n_cells = mine;
             for (int c = 0; c < trips; ++c) {
                 const bool on = c < mine;
+                // next non-empty field
+                while (on && (w0 & 0xFFFFu) == 0xFFFFu) {
+                    w0 = __funnelshift_r(w0, w1, 16); w1 = __funnelshift_r(w1, w2, 16); w2 = __funnelshift_r(w2, w3, 16);
+                    w3 = (w3 >> 16) | 0xFFFF0000u;
+                }
                 const int ci = on ? (int)(w0 & 0xFFFFu) : 0;
                 w0 = __funnelshift_r(w0, w1, 16); w1 = __funnelshift_r(w1, w2, 16); w2 = __funnelshift_r(w2, w3, 16);
                 w3 = (w3 >> 16) | 0xFFFF0000u;
-                const int code0 = (ci >> 6) * kGroupCols + (ci & 63);
                 float p[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (on) e = __ldg(en4 + (int64_t)(code0 + 64 * j) * (kD / 4) + m);
+                    if (on) e = __ldg(en4 + (int64_t)tc16_code_of(ci, j, cell_kind) * (kD / 4) + m);
                     p[j] = __fmaf_rn(nz.w, e.w, __fmaf_rn(nz.z, e.z, __fmaf_rn(nz.y, e.y, __fmul_rn(nz.x, e.x))));
                 }
                 const float csq = on ? __ldg(csq_cell + ci * 8 + m) : 0.f;
@@ -1036,7 +1369,7 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
                 }
                 const float recv = __shfl_xor_sync(VQ_FULL, (m & 1) ? q2[0] : q2[1], 1);
                 const float dot = ((m & 1) ? q2[1] : q2[0]) + recv;
-                if (on) take(ref_distance(a_sq, csq, dot), code0 + 64 * m);
+                if (on) take(ref_distance(a_sq, csq, dot), tc16_code_of(ci, m, cell_kind));
             }
         }
         uint32_t omin;
@@ -1067,11 +1400,11 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
             const float4* zs = s_z[warp][grp];
             bo = so = 0xFFFFFFFFu; bc = 0x7FFFFFFF;
             uint32_t w0 = w0i, w1 = w1i, w2 = w2i, w3 = w3i;
-            while (valid && (w0 & 0xFFFFu) != 0xFFFFu) {
+            for (int f = 0; valid && f < 8; ++f) {
                 const int ci = (int)(w0 & 0xFFFFu);
                 w0 = __funnelshift_r(w0, w1, 16); w1 = __funnelshift_r(w1, w2, 16); w2 = __funnelshift_r(w2, w3, 16);
                 w3 = (w3 >> 16) | 0xFFFF0000u;
-                take(cell_distance_staged(en32c, csq_cell, ci, m, zs, a_sq), (ci >> 6) * kGroupCols + (ci & 63) + 64 * m);
+                if (ci != 0xFFFF) take(cell_distance_staged(en32c, csq_cell, ci, m, zs, a_sq), tc16_code_of(ci, m, cell_kind));
             }
             group_argmin();
             // near tie: some other candidate of the row within 1e-6 relative of the best distance
@@ -1150,7 +1483,7 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
             const int c_end = sliced ? min(n_cells, (slice + 1) * per_slice) : n_cells;
             for (int ci = c_begin + grp16; ci < c_end; ci += kExactThreads / 8) {
                 const float dist = cell_distance_staged(en32c, csq_cell, ci, m, zs, a_sq);
-                top.add(dist_key(dist, (ci >> 6) * kGroupCols + (ci & 63) + 64 * m));
+                top.add(dist_key(dist, tc16_code_of(ci, m, cell_kind)));
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
@@ -1211,8 +1544,21 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
 
 }  // namespace tc16
 
-bool tc16_supported(int64_t T, int K, int D) {
+// VQ_TC16_W16=1 selects the 16-epilogue-warp kernel (k_dist_tc16_w16, cell layout 3).  Measured equal to the 8-warp
+// kernel (123.0 vs 122.3 us, same box): with the epilogue's work removed altogether the kernel still takes 96 us (the
+// MMA / hand-off side), so neither drain is what bounds it; the default stays the kernel with fewer moving parts.
+bool tc16_wide_drain() {
+    static const bool on = getenv("VQ_TC16_W16") && atoi(getenv("VQ_TC16_W16")) != 0;
+    return on;
+}
+
+bool tc16_disabled() {
     static const bool disabled = getenv("VQ_TC16_DISABLE") && atoi(getenv("VQ_TC16_DISABLE")) != 0;
+    return disabled;
+}
+
+bool tc16_supported(int64_t T, int K, int D) {
+    const bool disabled = tc16_disabled();
     // code ids travel as 16-bit fields of the rescoring items; the threshold logic needs whole 512-code groups
     return !disabled && D == tc16::kD && K >= tc16::kGroupCols && (K % tc16::kGroupCols) == 0 && K <= 65536 && T >= 256;
 }
@@ -1228,7 +1574,16 @@ cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T
     const int n_row_tiles = (T + tc16::kRowsPerCta - 1) / tc16::kRowsPerCta;
     const int grid = n_row_tiles < sm_count() ? n_row_tiles : sm_count();
     cudaError_t e;
-    if (ss_form) {
+    if (cb.cell_kind == 3) {
+        const tc16::SmemLayoutW L = tc16::smem_layout_w();
+        static PerDeviceOnce once;
+        if (once.need()) {
+            e = cudaFuncSetAttribute(tc16::k_dist_tc16_w16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
+            if (e != cudaSuccess) return e;
+        }
+        e = launch_pdl(tc16::k_dist_tc16_w16, dim3(grid), dim3(tc16::kThreadsW), L.total + 1024, s, ma, mb, T, cb.K, cb.info,
+                       reinterpret_cast<uint2*>(rec), flagged, n_flagged, stats);
+    } else if (ss_form) {
         const tc16::SmemLayout L = tc16::smem_layout();
         static PerDeviceOnce once;
         if (once.need()) {
@@ -1271,7 +1626,7 @@ cudaError_t launch_exact_finish16(const void* records, const float* zn32, const 
     cudaError_t e = launch_pdl(tc16::k_exact_finish16, dim3((unsigned)blocks), dim3(tc16::kExactThreads), 0, s,
                                static_cast<const int4*>(records), zn32, row_sq, cb.en32, reinterpret_cast<const float4*>(cb.en32c),
                                cb.csq_cell, (int)T, cb.K, flagged, n_flagged, cap, static_cast<tc16::FlaggedPartial*>(partial_ws),
-                               done_counters, out, stats);
+                               done_counters, out, stats, cb.cell_kind);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }

@@ -164,10 +164,28 @@ cudaError_t launch_codebook_grad_sharded(const void* const* peer_bufs, int world
 //   2  generic filter (vq_dist_tc.cu):  cell = slot s of the 256-code group g, ci = g*32 + s, member i = code
 //      g*256 + 64*(i>>1) + 32*(s>>4) + (s&15) + 16*(i&1)
 //   0  none (shapes the tensor-core search does not take)
+bool tc16_wide_drain();     // vq_dist_tc16.cu: VQ_TC16_W16=1 selects the 16-epilogue-warp kernel (cell layout 3)
+bool tc16_disabled();       // VQ_TC16_DISABLE=1: D = 32 goes through the generic filter (cell layout 2) like every other D
 inline int cell_layout_kind(int K, int D) {
-    if (D == 32 && K >= 512 && (K % 512) == 0 && K <= 65536) return 1;
+    if (D == 32 && K >= 512 && (K % 512) == 0 && K <= 65536 && !tc16_disabled()) return tc16_wide_drain() ? 3 : 1;
     if ((D == 32 || D == 64 || D == 128 || D == 256) && K >= 256 && (K % 256) == 0) return 2;
     return 0;
+}
+// D = 32 filter cells (kinds 1 and 3): cell id ci = group * 64 + cell-in-group, member m = 0..7.
+//   kind 1 (8 epilogue warps, a thread folds column c with c + 64):  code = g*512 + (ci & 63) + 64*m
+//   kind 3 (16 epilogue warps, a thread owns a 64-column half h2 of every tile and folds column c with c + 32):
+//           ci & 63 = h2*32 + s,  code = g*512 + 128*(m >> 1) + 64*h2 + 32*(m & 1) + s
+__host__ __device__ inline int tc16_code_of(int ci, int m, int kind) {
+    const int g = ci >> 6, c = ci & 63;
+    if (kind == 1) return g * 512 + c + 64 * m;
+    return g * 512 + 128 * (m >> 1) + 64 * (c >> 5) + 32 * (m & 1) + (c & 31);
+}
+__host__ __device__ inline void tc16_cell_of(int code, int kind, int& ci, int& m) {
+    const int g = code >> 9, w = code & 511;
+    if (kind == 1) { ci = g * 64 + (w & 63); m = w >> 6; return; }
+    const int t = w >> 7, c = w & 127;
+    ci = g * 64 + (c >> 6) * 32 + (c & 31);
+    m = 2 * t + ((c >> 5) & 1);
 }
 inline bool has_cell_layout(int K, int D) { return cell_layout_kind(K, D) != 0; }
 // (cell, member) of a code in the generic layout

@@ -194,7 +194,7 @@ __device__ __forceinline__ void prep_rows_small_body(const float4* __restrict__ 
                     // cell copies of the unit codes (see cell_layout_kind): chunk `sub` of code r
                     const int code = (int)r;
                     int ci, m;
-                    if (cell_kind == 1) { const int w = code & 511; ci = (code >> 9) * 64 + (w & 63); m = w >> 6; }
+                    if (cell_kind == 1 || cell_kind == 3) tc16_cell_of(code, cell_kind, ci, m);
                     else generic_cell_of(code, ci, m);
                     en32c[((int64_t)ci * kLpr + sub) * 8 + m] = v;
                     if (sub == 0) csq_cell[ci * 8 + m] = s2;

@@ -7,11 +7,13 @@ fixtures written by the unmodified reference on CPU, and a float64 closed form f
 Bars (north_star): indices and z_q bit-exact except near-tie rows (top-2 fp32 distances < 1e-6 relative
 apart), which are counted and reported; loss and gradients within 1e-5 relative.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, rel_err, ulp_distance
+from conftest import ROOT, load_golden, rel_err, ulp_distance
 from oracle import vq_oracle as vo
 
 pytestmark = pytest.mark.gpu
@@ -681,3 +683,31 @@ def test_plain_l2_form_matches_its_oracle(dev, K, D, shape, scale):
     dec = m.indices_to_embeddings(idx.view(shape[0], -1))
     assert torch.equal(dec.detach(), vo.indices_to_embeddings("l2", idx.view(shape[0], -1), w).contiguous())
     assert torch.equal(m.encode(z), idx)
+
+
+@pytest.mark.parametrize("env", [{"VQ_TC16_W16": "1"}, {"VQ_TC16_TS": "1"}, {"VQ_TC16_DISABLE": "1"}],
+                         ids=["wide-drain", "rows-in-tmem", "generic-filter"])
+def test_alternative_filter_kernels_equal_exhaustive_search(env):
+    """The measured alternatives of the D = 32 filter that stay in the library behind environment switches (16 epilogue
+    warps / token rows in tensor memory / the generic fp32-accumulator filter) return the exhaustive search's indices on
+    every row; the library reads the switches when it is loaded, hence a fresh process."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path[:0] = [%r, %r]\n"
+        "import torch\n"
+        "from oracle import vq_oracle as vo\n"
+        "from vq_b200 import functional as F\n"
+        "dev = torch.device('cuda:0')\n"
+        "w = vo.make_codebook('vit', 8192, 32, 0).to(dev)\n"
+        "for shape, seed in (((2, 1024, 32), 1), ((41, 1000, 32), 2)):\n"
+        "    z = vo.make_latents(shape, seed).to(dev)\n"
+        "    p = F.prepare_codebook(w)\n"
+        "    a = F.encode_indices(z, w, 'vit', prepared=p)\n"
+        "    b = F.encode_indices(z, w, 'vit', prepared=p, exact_scan=True)\n"
+        "    assert torch.equal(a, b), int((a != b).sum())\n"
+        "    zq, idx, loss, hist, stats = F.quantise(z, w, 'vit', prepared=p)\n"
+        "    assert torch.equal(idx, b.reshape(-1)) and int(hist.sum()) == idx.numel()\n"
+        "print('ok')\n") % (ROOT, os.path.join(ROOT, "attention-models_b200"))
+    out = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]

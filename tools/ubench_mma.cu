@@ -104,14 +104,14 @@ __global__ void __launch_bounds__(128, 1) k_mma(long long* out, int mode, int n,
 }
 
 // `issuers` warps issue `iters` MMAs each (own accumulator columns, shared operands); block time / total MMAs
-__global__ void __launch_bounds__(128, 1) k_mma_multi(long long* out, int n, int iters, int issuers) {
+__global__ void __launch_bounds__(256, 1) k_mma_multi(long long* out, int n, int iters, int issuers, int mode, int distinct, int ldtm) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t bar[4];
     __shared__ long long t_end[4];
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
     uint8_t* smem = smem_raw + pad;
-    for (int i = threadIdx.x; i < (8192 + 4 * 16384) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u;
+    for (int i = threadIdx.x; i < (4 * 8192 + 16 * 8192) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u;
     const int warp = threadIdx.x >> 5;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
@@ -126,19 +126,24 @@ __global__ void __launch_bounds__(128, 1) k_mma_multi(long long* out, int n, int
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
-    const uint32_t a_smem = smem_u32(smem), b_smem = a_smem + 8192;
-    const uint32_t idesc = ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int uwarp = __shfl_sync(0xffffffffu, warp, 0);
+    // distinct: every issuer has its own A tile (8 KB) and four own B tiles (8 KB each), as in the filter kernel where the
+    // operands of consecutive MMAs never coincide; else all issuers read the same bytes
+    const uint32_t a_smem = smem_u32(smem) + (distinct ? uwarp : 0) * 8192, b_smem = smem_u32(smem) + 4 * 8192 + (distinct ? uwarp : 0) * 4 * 8192;
+    const uint32_t idesc = ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const long long t0 = clock64();
     if (uwarp < issuers) {
-        const uint32_t d = tmem + (uint32_t)uwarp * 128;
+        const uint32_t d = tmem + (uint32_t)uwarp * (mode ? 96 : 128);      // TS: columns 448.. hold A
         for (int i = 0; i < iters; i += 8) {
             uint32_t pred = 0;
             asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
             if (pred) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    mma_ss(d, umma_desc(a_smem + (u & 1) * 32), umma_desc(b_smem + ((u >> 1) & 3) * 16384 + (u & 1) * 32), idesc, u & 1);
+                for (int u = 0; u < 8; ++u) {
+                    const uint64_t b = umma_desc(b_smem + ((u >> 1) & 3) * 8192 + (u & 1) * 32);
+                    if (mode == 0) mma_ss(d, umma_desc(a_smem + (u & 1) * 32), b, idesc, u & 1);
+                    else mma_ts(d, tmem + 448 + (uint32_t)uwarp * 16 + (u & 1) * 8, b, idesc, u & 1);
+                }
             }
             __syncwarp();
         }
@@ -147,6 +152,32 @@ __global__ void __launch_bounds__(128, 1) k_mma_multi(long long* out, int n, int
             mbar_wait(smem_u32(&bar[uwarp]), 0);
             t_end[uwarp] = clock64();
         }
+    } else if (ldtm && uwarp >= 4) {
+        // the epilogue's traffic next to the MMAs: warps 4-7 keep reading accumulator tiles out of tensor memory
+        // (x64.pack::16b, the filter kernel's load), about one 128-column tile per MMA pair
+        const uint32_t taddr = tmem + ((uint32_t)((uwarp & 3) * 32) << 16);
+        uint32_t acc = 0;
+        for (int i = 0; i < iters / 2 * issuers; ++i) {
+            uint32_t v[64];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x64.pack::16b.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+                "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+                "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                  "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]),
+                  "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]),
+                  "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]),
+                  "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]),
+                  "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+                : "r"(taddr + (uint32_t)((i & 3) * 128)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            acc += v[0] ^ v[63];
+        }
+        if (acc == 0x12345) out[2] = acc;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -241,15 +272,23 @@ int main() {
                            c_f32 ? "f32" : "f16", n, lds ? "+LDS traffic" : "            ", (double)c / iters, n / 2, cudaGetErrorString(e));
                 }
     // several issuer warps, each on its own accumulator columns: does the fixed per-MMA cost overlap between threads?
-    for (int issuers : {1, 2, 4})
-        for (int n : {64, 128}) {
-            k_mma_multi<<<148, 128, smem>>>(out, n, iters, issuers);
-            cudaError_t e = cudaDeviceSynchronize();
-            long long c = 0;
-            cudaMemcpy(&c, out, 8, cudaMemcpyDeviceToHost);
-            printf("SS acc=f16 N=%3d, %d issuer warp(s): %7.1f cycles / MMA aggregated (%s)\n", n, issuers,
-                   (double)c / (iters * issuers), cudaGetErrorString(e));
-        }
+    cudaFuncSetAttribute(k_mma_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 20 * 8192 + 1024);
+    for (int mode = 0; mode < 2; ++mode)
+        for (int distinct = 0; distinct < 2; ++distinct)
+            for (int issuers : {1, 2, 4})
+                for (int n : {64, 96, 128}) {
+                    if (mode == 1 && n == 128) continue;        // (TS leaves 448 accumulator columns: 4 x 96)
+                    if (mode == 0 && n == 96) continue;
+                  for (int ldtm = 0; ldtm < 2; ++ldtm) {
+                    if (ldtm && (distinct == 0 || issuers != 4)) continue;
+                    k_mma_multi<<<148, 256, 20 * 8192 + 1024>>>(out, n, iters, issuers, mode, distinct, ldtm);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    long long c = 0;
+                    cudaMemcpy(&c, out, 8, cudaMemcpyDeviceToHost);
+                    printf("%s acc=f16 N=%3d, %d issuer warp(s), %s operands%s: %7.1f cycles / MMA aggregated (%s)\n", mode ? "TS" : "SS", n,
+                           issuers, distinct ? "distinct" : "shared  ", ldtm ? " + tcgen05.ld traffic" : "", (double)c / (iters * issuers), cudaGetErrorString(e));
+                  }
+                }
     for (int n : {64, 128}) {
         k_lat<<<1, 128, smem>>>(out, n, 64);
         cudaError_t e = cudaDeviceSynchronize();
