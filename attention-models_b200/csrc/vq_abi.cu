@@ -227,6 +227,8 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
         VQ_CUDA(vq::launch_prep_fused(weight, cbv, z, T, zn32, w.row_sq, denom, zn16, zl, s));
     } else if (layout == VQ_LAYOUT_TOKEN_MAJOR) {
         VQ_CUDA(vq::launch_prep_tokens(z, T, D, zn32, w.row_sq, denom, zn16, zl, s, raw));
+    } else if (vq::prep_nchw_fused_supported(T, hw, D)) {
+        VQ_CUDA(vq::launch_prep_nchw_fused(z, T, hw, D, denom, zn32, zn16, w.row_sq, zl, raw, s));
     } else if (raw) {
         // un-normalised form: the rows as they are (transposed to token-major), denominators of 1, row_sq = sum(z^2)
         if (nz) VQ_CUDA(vq::launch_zero_ranges(zl, s));

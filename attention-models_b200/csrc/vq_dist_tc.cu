@@ -42,13 +42,14 @@ constexpr int kTileN = 128;          // codes per accumulator stage
 constexpr int kGroupTiles = 2;       // tiles per group (256 columns)
 constexpr int kGroupCols = kTileN * kGroupTiles;
 constexpr int kKBlock = 32;          // halfs per K block: 64-byte rows, SWIZZLE_64B
-constexpr int kABlockBytes = kRowsPerCta * kKBlock * 2;   // 16 KiB
+constexpr int kABlockBytes = kRowsPerCta * kKBlock * 2;   // 16 KiB (two row halves; one half: 8 KiB)
+__host__ __device__ constexpr int a_block_bytes(int halves) { return halves * 128 * kKBlock * 2; }
 constexpr int kBStageBytes = kTileN * kKBlock * 2;        // 8 KiB
 constexpr int kThreads = 512;        // warps 0-3 service (TMA, MMA, TMEM alloc, idle), 4-7 spare, 8-15 epilogue
 constexpr int kRecordBytes = 32;     // verdict record per row
 // register budget after setmaxnreg (the kernel launches with 128 per thread = the whole register file):
-constexpr int kRegsService = 40, kRegsEpilogue = 216;
-static_assert(256 * kRegsService + 256 * kRegsEpilogue <= 65536, "register file overcommitted");
+constexpr int kRegsService = 56, kRegsSpare = 24, kRegsEpilogue = 216;    // warps 0-3, 4-7 (and idle epilogue warps), 8-15
+static_assert(128 * kRegsService + 128 * kRegsSpare + 256 * kRegsEpilogue <= 65536, "register file overcommitted");
 constexpr float kTwoEps = 2.2e-3f;   // 2 * eps, see header comment
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 // c_format = F32 (bit 4), a/b = F16 (0), K-major both, N = 128 (bits 17..22), M = 128 (bits 24..28)
@@ -57,7 +58,19 @@ struct SmemLayout {
     uint32_t a, b, snap, hand, bars, tmem_slot, total;
 };
 __host__ __device__ constexpr int a_stages(int kb) { return kb <= 2 ? 2 : 1; }
-__host__ __device__ constexpr int b_stages(int kb) { return kb == 1 ? 8 : (kb <= 4 ? 4 : 2); }   // (4 at D = 256 fits but measured no faster)
+// codebook ring.  At D = 256 the A operand of 256 rows takes 128 KB and leaves four 8 KB stages: each is consumed by 4 MMAs
+// (~400 cycles) against a TMA round trip of ~700, so the issuers starve for tiles (2 -> 4 stages: 147 -> 126 us for cfg 2's
+// search).  128-row CTAs (A = 64 KB, 16 stages) on their own are no way out: every CTA then streams the whole codebook
+// for half the rows, 512 MB of L2 -> SM traffic for cfg 2, and the kernel sits at the ~6.2 TB/s the L2 delivers (82.8 vs
+// 66.3 us, same box).  `halves` = 1 therefore runs as CLUSTERS OF TWO CTAs that share the codebook stream: each CTA
+// fetches one 64-code half of every stage and TMA-multicasts it into both, a stage is released by both CTAs' issuers
+// (multicast tcgen05.commit).  There are 16 stages: two rings of 8, one per issuer (the issuers take alternate code
+// tiles; a ring of its own lets each issuer see every phase of its barriers - a parity wait by a thread that skipped
+// the previous phase returns early).
+#ifndef VQ_TC_BS256
+#define VQ_TC_BS256 4      // 2 -> 4: 147 -> 126 us (cfg 2), 5.38 -> 4.31 ms (1 M tokens), same-box A/B with two issuers
+#endif
+__host__ __device__ constexpr int b_stages(int kb, int halves = 2) { return kb == 1 ? 8 : (kb <= 4 ? 4 : (halves == 1 ? 16 : VQ_TC_BS256)); }
 // slot-maxima snapshots of the best three groups: 3 areas x 256 rows x 32 slots; rows padded by 16 B (conflict-free
 // STS.128).  At D = 256 the A operand alone is 128 KB, so the snapshots are kept as fp16 (80-byte rows): the verdict
 // then compares against thr - kSnapSlack, which covers the rounding of the stored maxima (|score| <= 1).
@@ -65,13 +78,13 @@ __host__ __device__ constexpr int snap_areas(int kb) { return 3; }
 __host__ __device__ constexpr bool snap_half(int kb) { return kb > 4; }
 __host__ __device__ constexpr int snap_row_bytes(int kb) { return kb <= 4 ? 144 : 80; }
 constexpr float kSnapSlack = 5.0e-4f;   // >= 2^-11: fp16 rounding of a slot maximum of magnitude <= 1
-constexpr int kMaxBStages = 8;
-__host__ __device__ inline SmemLayout smem_layout(int kb) {
+constexpr int kMaxBStages = 16;
+__host__ __device__ inline SmemLayout smem_layout(int kb, int halves = 2) {
     SmemLayout L;
     L.a = 0;
-    L.b = L.a + a_stages(kb) * kb * kABlockBytes;
-    L.snap = L.b + b_stages(kb) * kBStageBytes;
-    L.hand = L.snap + snap_areas(kb) * kRowsPerCta * snap_row_bytes(kb);
+    L.b = L.a + a_stages(kb) * kb * a_block_bytes(halves);
+    L.snap = L.b + b_stages(kb, halves) * kBStageBytes;
+    L.hand = L.snap + snap_areas(kb) * (128 * halves) * snap_row_bytes(kb);
     L.bars = L.hand;
     L.tmem_slot = L.bars + 8 * (2 * kMaxBStages + 2 * 2 + 4 + 4);
     L.total = L.tmem_slot + 16;
@@ -90,18 +103,30 @@ __device__ __forceinline__ int cell_code(int g, int slot, int i) {
 // ends with the row's verdict record in global memory.  Registers are redistributed with setmaxnreg.
 // (Rescoring used to run on warps 4-7 of this kernel: at D = 256 its dependent 1 KB gathers held the tile hand-off
 // and the tensor pipe sat at 20 %; it is now k_rescore_g, which reads whole 128-byte lines of cell copies.)
-template <int KB>
+template <int KB, int HALVES>
 __global__ void __launch_bounds__(kThreads, 1)
 k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int T, int K,
           const int* __restrict__ cb_info, int4* __restrict__ records, int* __restrict__ cand,
           int* __restrict__ flagged, int* __restrict__ n_flagged, int64_t* __restrict__ stats, int splits) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int AS = a_stages(KB);
-    constexpr int BS = b_stages(KB);
+    constexpr int BS = b_stages(KB, HALVES);
+    constexpr int kRows = 128 * HALVES;               // token rows per CTA: two MMA row halves, or one
+    constexpr int CL = HALVES == 1 ? 2 : 1;           // CTAs per cluster (launch attribute): they share the codebook stream
+    // HALVES = 1 (see b_stages): two issuers on alternate code tiles, each with its own producer thread, ring of RING
+    // stages and pair of accumulator stages; a full / empty barrier covers KS consecutive stages (k blocks) - a wait on
+    // an mbarrier costs ~90 cycles even when its phase completed long ago, and at one wait per stage the producer and
+    // the issuers spent more time on barriers than the two MMAs of a stage take (first cluster version: 91.5 us for cfg 2
+    // against 66.4 with 256-row CTAs; tensor pipe 43 % busy, L2 18 %).
+    constexpr int KS = HALVES == 1 ? 2 : 1;
+    constexpr int RING = HALVES == 1 ? BS / 2 : BS;
+    constexpr int NACC = HALVES == 1 ? 4 : 2;         // accumulator stages of HALVES x 128 columns
+    static_assert(KB % KS == 0 && RING % KS == 0 && NACC * HALVES * kTileN <= 512, "stage geometry");
+    constexpr int kABlock = a_block_bytes(HALVES);
     constexpr int kAreas = snap_areas(KB);
     constexpr int kSnapRow = snap_row_bytes(KB);
     constexpr bool kSnapHalf = snap_half(KB);
-    const SmemLayout L = smem_layout(KB);
+    const SmemLayout L = smem_layout(KB, HALVES);
     // swizzled TMA/UMMA tiles want a 1024-byte aligned base; the launch reserves 1 KiB of slack for this
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
     uint8_t* smem = smem_raw + pad;
@@ -111,9 +136,9 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     auto b_full = [&](int s) { return bar_base + 8 * s; };
     auto b_empty = [&](int s) { return bar_base + 8 * (kMaxBStages + s); };
     auto t_full = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + s); };
-    auto t_empty = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 2 + s); };
-    auto a_full = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 4 + s); };
-    auto a_empty = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 6 + s); };
+    auto t_empty = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 4 + s); };
+    auto a_full = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 8 + s); };
+    auto a_empty = [&](int s) { return bar_base + 8 * (2 * kMaxBStages + 10 + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_slot);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,15 +146,20 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     // codebook is cut into `splits` ranges of whole groups and every range gets its own CTA, record and verdict.  A
     // verdict taken against the split's own best score keeps a superset of what the global best would keep, so the
     // union of the splits' surviving cells contains the winner whenever every split is decided.
-    const int n_row_tiles = (T + kRowsPerCta - 1) / kRowsPerCta;
+    // With clusters a work item is taken by a cluster: its CTAs own consecutive row tiles (a tile past the end reads
+    // zeros and writes nothing) and walk the same code tiles in step.
+    const uint32_t cta_rank = CL == 2 ? cluster_cta_rank() : 0u;
+    const int unit0 = blockIdx.x / CL, n_units = gridDim.x / CL;
+    const int n_row_tiles = ((T + kRows - 1) / kRows + CL - 1) / CL;
     const int n_items = n_row_tiles * splits;
     const int n_tiles = K / kTileN / splits;            // per item
     const int n_groups = n_tiles / kGroupTiles;         // per item
 
     if (warp == 1 && lane == 0) {
         // two MMA issuers (one per row half) commit to the stage / tile / row-tile barriers
+        // a stage is read by both row halves, or by its ring's issuer in either CTA of the cluster
         for (int s = 0; s < BS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 2); }
-        for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 2); mbar_init(t_empty(s), 256); }
+        for (int s = 0; s < NACC; ++s) { mbar_init(t_full(s), HALVES); mbar_init(t_empty(s), 128 * HALVES); }
         for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -141,83 +171,111 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL == 2) cluster_sync_all();        // the peer's barriers are initialised before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        reg_dec<kRegsService>();
-        if (warp == 0 && lane == 0) {
-            // ===================== TMA producer =====================
-            uint32_t b_cnt = 0;
+        // (with one row half only four epilogue warps take registers, so the service warps can keep more)
+        reg_dec<HALVES == 1 ? 80 : kRegsService>();
+        if ((warp == 0 || (HALVES == 1 && warp == 2)) && lane == 0) {
+            // ===================== TMA producers: one, or one per issuer ring =====================
+            const int pw = warp == 2 ? 1 : 0;
+            const int n0 = HALVES == 2 ? 0 : pw, n_step = HALVES == 2 ? 1 : 2;
             int it = 0;
 #ifdef VQ_TC_INSTRUMENT
             long long wait_acc[4] = {0, 0, 0, 0};
             const long long t_begin = clock64();
 #endif
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const int rt = item / splits, tile0 = (item % splits) * n_tiles;
-                const int as = it % AS;
-                VQ_TIMED_WAIT(0, a_empty(as), (((uint32_t)(it / AS)) & 1u) ^ 1u);
-                mbar_expect_tx(a_full(as), KB * kABlockBytes);
+            for (int item = unit0; item < n_items; item += n_units, ++it) {
+                const int rt = (item / splits) * CL + (int)cta_rank, tile0 = (item % splits) * n_tiles;
+                if (pw == 0) {
+                    const int as = it % AS;
+                    VQ_TIMED_WAIT(0, a_empty(as), (((uint32_t)(it / AS)) & 1u) ^ 1u);
+                    mbar_expect_tx(a_full(as), KB * kABlock);
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb)
-                    tma_load_2d(smem_base + L.a + (as * KB + kb) * kABlockBytes, &tm_a, a_full(as), kb * kKBlock,
-                                rt * kRowsPerCta);
-                for (int n = 0; n < n_tiles; ++n) {
+                    for (int kb = 0; kb < KB; ++kb)
+                        tma_load_2d(smem_base + L.a + (as * KB + kb) * kABlock, &tm_a, a_full(as), kb * kKBlock,
+                                    rt * kRows);
+                }
+                for (int n = n0; n < n_tiles; n += n_step) {
+                    const uint32_t t_cnt = (uint32_t)(it * n_tiles + n);          // n_tiles is even: ring = n & 1
+                    uint32_t ring_cnt = (HALVES == 2 ? t_cnt : (t_cnt >> 1)) * KB;  // stages this ring has carried so far
 #pragma unroll
-                    for (int kb = 0; kb < KB; ++kb, ++b_cnt) {
-                        const int s = b_cnt % BS;
-                        VQ_TIMED_WAIT(1, b_empty(s), ((b_cnt / BS) & 1u) ^ 1u);
-                        mbar_expect_tx(b_full(s), kBStageBytes);
-                        tma_load_2d(smem_base + L.b + s * kBStageBytes, &tm_b, b_full(s), kb * kKBlock, (tile0 + n) * kTileN);
+                    for (int kb = 0; kb < KB; ++kb, ++ring_cnt) {
+                        const int s = pw * RING + (int)(ring_cnt % RING);          // stage; its barrier is that of stage s - s % KS
+                        const int sb = s - (kb % KS);
+                        if (kb % KS == 0) {
+                            VQ_TIMED_WAIT(1, b_empty(sb), ((ring_cnt / RING) & 1u) ^ 1u);
+                            mbar_expect_tx(b_full(sb), KS * kBStageBytes);
+                        }
+                        if constexpr (CL == 2)      // this CTA's half of the stage (tm_b boxes are 64 codes), into both CTAs
+                            tma_load_2d_multicast(smem_base + L.b + s * kBStageBytes + cta_rank * (kBStageBytes / 2), &tm_b, b_full(sb),
+                                                  kb * kKBlock, (tile0 + n) * kTileN + (int)cta_rank * (kTileN / 2), (uint16_t)3);
+                        else
+                            tma_load_2d(smem_base + L.b + s * kBStageBytes, &tm_b, b_full(sb), kb * kKBlock, (tile0 + n) * kTileN);
                     }
                 }
             }
 #ifdef VQ_TC_INSTRUMENT
-            atomicAdd((unsigned long long*)&g_tc_wait[0], (unsigned long long)wait_acc[0]);
-            atomicAdd((unsigned long long*)&g_tc_wait[1], (unsigned long long)wait_acc[1]);
-            atomicAdd((unsigned long long*)&g_tc_wait[2], (unsigned long long)(clock64() - t_begin));
+            if (pw == 0) {
+                atomicAdd((unsigned long long*)&g_tc_wait[0], (unsigned long long)wait_acc[0]);
+                atomicAdd((unsigned long long*)&g_tc_wait[1], (unsigned long long)wait_acc[1]);
+                atomicAdd((unsigned long long*)&g_tc_wait[2], (unsigned long long)(clock64() - t_begin));
+            }
 #endif
         } else if ((warp == 1 || warp == 3) && lane == 0) {
-            // ===================== MMA issuers: one thread per row half =====================
-            // A thread gets one tcgen05.mma out per ~110-140 cycles whatever its size, and issuers overlap perfectly
-            // (tools/ubench_mma.cu): with a single issuer an M = N = 128, K = 16 MMA "retired" at half rate here.  The two
-            // halves write different accumulators, so each issuer keeps its own MMAs in order and nothing else is shared.
-            const int r = warp == 3 ? 1 : 0;
-            uint32_t b_cnt = 0, t_cnt = 0;
+            // ===================== MMA issuers: two threads =====================
+            // A thread gets one tcgen05.mma out per ~105 cycles whatever its size, and issuers overlap
+            // (tools/ubench_mma.cu): with a single issuer an M = N = 128, K = 16 MMA "retired" at half rate here.
+            // HALVES = 2: one issuer per row half - the halves write different accumulators, both read every stage.
+            // HALVES = 1: the issuers take alternate code tiles (= alternate accumulator stages) of the one row half.
+            const int w = warp == 3 ? 1 : 0;
+            const int r = HALVES == 2 ? w : 0;
+            const int n0 = HALVES == 2 ? 0 : w, n_step = HALVES == 2 ? 1 : 2;
             int it = 0;
 #ifdef VQ_TC_INSTRUMENT
             long long wait_acc[4] = {0, 0, 0, 0};
             const long long t_begin = clock64();
 #endif
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            for (int item = unit0; item < n_items; item += n_units, ++it) {
                 const int as = it % AS;
                 VQ_TIMED_WAIT(0, a_full(as), ((uint32_t)(it / AS)) & 1u);
                 tc_fence_after();
-                for (int n = 0; n < n_tiles; ++n, ++t_cnt) {
-                    const int acc = t_cnt & 1;
-                    VQ_TIMED_WAIT(1, t_empty(acc), ((t_cnt >> 1) & 1u) ^ 1u);
+                for (int n = n0; n < n_tiles; n += n_step) {
+                    const uint32_t t_cnt = (uint32_t)(it * n_tiles + n);      // n_tiles is even: t_cnt & 1 = n & 1
+                    const int acc = (int)(t_cnt % NACC);                       // HALVES = 1: issuer w owns stages w, w + 2
+                    VQ_TIMED_WAIT(1, t_empty(acc), ((t_cnt / NACC) & 1u) ^ 1u);
                     tc_fence_after();
+                    // ring position of the tile's first stage: HALVES = 2 - one ring, every tile; 1 - own ring, own tiles
+                    uint32_t b_cnt = (HALVES == 2 ? t_cnt : (t_cnt >> 1)) * KB;
 #pragma unroll
                     for (int kb = 0; kb < KB; ++kb, ++b_cnt) {
-                        const int s = b_cnt % BS;
-                        VQ_TIMED_WAIT(2, b_full(s), (b_cnt / BS) & 1u);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_base + L.a + (as * KB + kb) * kABlockBytes;
+                        const int s = (HALVES == 2 ? 0 : w * RING) + (int)(b_cnt % RING);
+                        const int sb = s - (kb % KS);
+                        if (kb % KS == 0) {
+                            VQ_TIMED_WAIT(2, b_full(sb), (b_cnt / RING) & 1u);
+                            tc_fence_after();
+                        }
+                        const uint32_t a_addr = smem_base + L.a + (as * KB + kb) * kABlock;
                         const uint32_t b_addr = smem_base + L.b + s * kBStageBytes;
 #pragma unroll
                         for (int k = 0; k < 2; ++k)
-                            umma_f16(tmem_base + (uint32_t)((acc * 2 + r) * kTileN),
+                            umma_f16(tmem_base + (uint32_t)((acc * HALVES + r) * kTileN),
                                      umma_desc(a_addr + r * (128 * 64) + k * 32), umma_desc(b_addr + k * 32), kIdesc,
                                      (uint32_t)((kb | k) != 0));
-                        umma_commit(b_empty(s));     // smem stage free once these MMAs (and the other half's) retire
+                        // smem stages free once their readers' MMAs retire
+                        if (kb % KS == KS - 1) {
+                            if constexpr (CL == 2) umma_commit_multicast(b_empty(sb), (uint16_t)3);
+                            else umma_commit(b_empty(sb));
+                        }
                     }
-                    umma_commit(t_full(acc));        // this half's accumulator of the tile complete
+                    umma_commit(t_full(acc));        // this issuer's accumulator of the tile complete
                 }
-                umma_commit(a_empty(as));            // row tile's A operand no longer needed by this half
+                umma_commit(a_empty(as));            // row tile's A operand no longer needed by this issuer
             }
 #ifdef VQ_TC_INSTRUMENT
-            if (r == 0) {
+            if (w == 0) {
                 atomicAdd((unsigned long long*)&g_tc_wait[4], (unsigned long long)wait_acc[0]);
                 atomicAdd((unsigned long long*)&g_tc_wait[5], (unsigned long long)wait_acc[1]);
                 atomicAdd((unsigned long long*)&g_tc_wait[6], (unsigned long long)wait_acc[2]);
@@ -225,9 +283,9 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             }
 #endif
         }
-    } else if (warp < 8) {
+    } else if (warp < 8 || (HALVES == 1 && warp >= 12)) {
         // spare warps: hand their registers to the epilogue (setmaxnreg.inc waits for them) and leave
-        reg_dec<kRegsService>();
+        reg_dec<kRegsSpare>();
     } else {
         // ===================== epilogue: 8 warps, one thread per row =====================
         reg_inc<kRegsEpilogue>();
@@ -236,10 +294,14 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         const int quarter = warp & 3;                // TMEM lane quarter this warp may read
         const int row_in_cta = r_sub * 128 + quarter * 32 + lane;
         const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(r_sub * kTileN);
+        constexpr uint32_t kStage = HALVES * kTileN;     // TMEM columns of an accumulator stage
         const uint32_t snap0 = smem_base + L.snap + (uint32_t)row_in_cta * kSnapRow;
-        constexpr uint32_t kSnapArea = kRowsPerCta * kSnapRow;
+        constexpr uint32_t kSnapArea = kRows * kSnapRow;
         const bool force_exhaustive = codebook_degenerate(cb_info);
-        uint32_t phase = 0;                          // parity of t_full: flips once per group (2 tiles, 2 stages)
+        // a group (2 tiles) drains accumulator stages sp, sp + 1: group count gc -> sp = 2 gc mod NACC, parity of its use
+        uint32_t gc = 0;
+        auto sp_of = [&](uint32_t c) { return (int)((2u * c) % NACC); };
+        auto ph_of = [&](uint32_t c) { return ((2u * c) / NACC) & 1u; };
         int it = 0;
 #ifdef VQ_TC_INSTRUMENT
         long long wait_acc[4] = {0, 0, 0, 0};
@@ -253,30 +315,32 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             tmem_ld16(ta + 32, v + 32);
             tmem_ld16(ta + 48, v + 48);
         };
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-            const int rt = item / splits, split = item % splits;
+        for (int item = unit0; item < n_items; item += n_units, ++it) {
+            const int rt = (item / splits) * CL + (int)cta_rank, split = item % splits;
             const int group0 = split * n_groups;        // global id of the item's first group
             float slot[32];
             float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY, m4 = -INFINITY;
             int g1 = 0, g2 = 0, g3 = 0;
             uint32_t a1 = 0, a2 = 1, a3 = (kAreas == 3) ? 2 : 1;   // snapshot areas of the best / second / third group
             float buf[2][64];
-            VQ_TIMED_WAIT(0, t_full(0), phase);
+            VQ_TIMED_WAIT(0, t_full(sp_of(gc)), ph_of(gc));
             tc_fence_after();
-            load_batch(tbase, buf[0]);
-            for (int g = 0; g < n_groups; ++g) {
+            load_batch(tbase + (uint32_t)sp_of(gc) * kStage, buf[0]);
+            for (int g = 0; g < n_groups; ++g, ++gc) {
+                const int sp = sp_of(gc);
+                const uint32_t phase = ph_of(gc);
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     tmem_ld_wait();                                   // batch b has landed in buf[b & 1]
-                    if (b == 1) { tc_fence_before(); mbar_arrive(t_empty(0)); }   // tile 0 fully in registers
-                    if (b == 3) { tc_fence_before(); mbar_arrive(t_empty(1)); }
+                    if (b == 1) { tc_fence_before(); mbar_arrive(t_empty(sp)); }   // tile 0 fully in registers
+                    if (b == 3) { tc_fence_before(); mbar_arrive(t_empty(sp + 1)); }
                     if (b < 3) {
-                        if (b == 1) { VQ_TIMED_WAIT(0, t_full(1), phase); tc_fence_after(); }
-                        load_batch(tbase + (uint32_t)(((b + 1) >> 1) * 2 * kTileN + ((b + 1) & 1) * 64), buf[(b + 1) & 1]);
+                        if (b == 1) { VQ_TIMED_WAIT(0, t_full(sp + 1), phase); tc_fence_after(); }
+                        load_batch(tbase + (uint32_t)((sp + ((b + 1) >> 1)) * kStage + ((b + 1) & 1) * 64), buf[(b + 1) & 1]);
                     } else if (g + 1 < n_groups) {
-                        VQ_TIMED_WAIT(0, t_full(0), phase ^ 1u);
+                        VQ_TIMED_WAIT(0, t_full(sp_of(gc + 1)), ph_of(gc + 1));
                         tc_fence_after();
-                        load_batch(tbase, buf[0]);
+                        load_batch(tbase + (uint32_t)sp_of(gc + 1) * kStage, buf[0]);
                     }
                     const float* v = buf[b & 1];
                     if (b == 0) {
@@ -290,7 +354,6 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                         }
                     }
                 }
-                phase ^= 1u;
                 // group maximum: 3-input tree over the 32 slots
                 float t[11];
 #pragma unroll
@@ -385,7 +448,7 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             // decided iff no further group can hold the winner (NaN / -inf rows fail the comparisons)
             const float bound = (kAreas == 3) ? m4 : m3;
             const bool decided = (bound < thr) && (mask[0] != 0) && !force_exhaustive;
-            const int row = rt * kRowsPerCta + row_in_cta;
+            const int row = rt * kRows + row_in_cta;
             const bool in_range = row < T;
             const bool flag = in_range && !decided;
             // the verdict record of the row, for the exact rescoring kernel: {g1 | g2 << 16 (or -1: undecided), g3,
@@ -417,6 +480,7 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL == 2) cluster_sync_all();        // nothing of the peer's (multicast tiles, stage releases) is still on its way
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -671,41 +735,96 @@ bool tc_supported(int64_t T, int K, int D) {
     return d_ok && K >= tc::kGroupCols && (K % tc::kGroupCols) == 0 && K / tc::kGroupCols <= 32767 && T >= 256;
 }
 
-// code splits of the generic filter: as many as keep (row tiles x splits) within one wave of CTAs
-static int tc_splits(int64_t T, int K) {
-    const int64_t n_row_tiles = (T + tc::kRowsPerCta - 1) / tc::kRowsPerCta;
-    const int n_groups = K / tc::kGroupCols;
-    int s = tc::kMaxSplits;
-    while (s > 1 && (n_groups % s != 0 || n_row_tiles * s > sm_count())) s >>= 1;
-    return s;
+// D = 256: clusters of two 128-row CTAs sharing the codebook stream (k_dist_tc<8, 1>), when the device can co-schedule
+// them.  Returns how many such clusters fit the device at once (0: use the 256-row kernel).  VQ_TC_CLUSTER=0 disables.
+static int tc_max_clusters() {
+    static PerDeviceOnce once;
+    static int n_of[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (once.need()) {
+        const char* e = getenv("VQ_TC_CLUSTER");
+        int n = 0;
+        if (!(e && e[0] == '0')) {
+            const tc::SmemLayout L = tc::smem_layout(8, 1);
+            if (cudaFuncSetAttribute(tc::k_dist_tc<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024) == cudaSuccess) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(2 * sm_count());
+                cfg.blockDim = dim3(tc::kThreads);
+                cfg.dynamicSmemBytes = L.total + 1024;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                if (cudaOccupancyMaxActiveClusters(&n, tc::k_dist_tc<8, 1>, &cfg) != cudaSuccess) n = 0;
+            }
+            cudaGetLastError();
+        }
+        n_of[dev & 63] = n;
+    }
+    return n_of[dev & 63];
 }
+
+// geometry of a generic-filter call: rows per CTA, CTAs per cluster, code splits (as many as keep row units x splits
+// within one wave), grid
+struct TcGeom {
+    int rows, cl, splits, grid;
+};
+static TcGeom tc_geom(int64_t T, int K, int D) {
+    TcGeom g;
+    const int clusters = (D == 256) ? tc_max_clusters() : 0;
+    g.cl = clusters > 0 ? 2 : 1;
+    g.rows = g.cl == 2 ? 128 : tc::kRowsPerCta;
+    const int64_t units = ((T + g.rows - 1) / g.rows + g.cl - 1) / g.cl;
+    const int wave = g.cl == 2 ? clusters : sm_count();
+    const int n_groups = K / tc::kGroupCols;
+    g.splits = tc::kMaxSplits;
+    while (g.splits > 1 && (n_groups % g.splits != 0 || units * g.splits > wave)) g.splits >>= 1;
+    const int64_t items = units * g.splits;
+    g.grid = (int)(items < wave ? items : wave) * g.cl;
+    return g;
+}
+static int tc_splits(int64_t T, int K, int D) { return tc_geom(T, K, D).splits; }
 
 // a row can be listed once per split
 int tc_flag_multiplier(int64_t T, int K, int D) {
-    return (tc_supported(T, K, D) && !tc16_supported(T, K, D)) ? tc_splits(T, K) : 1;
+    return (tc_supported(T, K, D) && !tc16_supported(T, K, D)) ? tc_splits(T, K, D) : 1;
 }
 
 size_t tc_workspace_bytes(int64_t T, int K, int D) {
     if (tc16_supported(T, K, D)) return tc16_workspace_bytes(T);
-    return tc_supported(T, K, D) ? (size_t)(T > 0 ? T : 1) * tc::kRecordBytes * tc_splits(T, K) : 0;
+    return tc_supported(T, K, D) ? (size_t)(T > 0 ? T : 1) * tc::kRecordBytes * tc_splits(T, K, D) : 0;
 }
 
-template <int KB>
+template <int KB, int HALVES>
 static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, int T, const float* zn32,
                                     const float* row_sq, const CodebookView& cb, int* cand, int* flagged,
                                     int* n_flagged, int64_t* stats, void* records, void* partial_ws, cudaStream_t s) {
-    const tc::SmemLayout L = tc::smem_layout(KB);
+    const tc::SmemLayout L = tc::smem_layout(KB, HALVES);
     static PerDeviceOnce once;
     if (once.need()) {
-        cudaError_t e = cudaFuncSetAttribute(tc::k_dist_tc<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
+        cudaError_t e = cudaFuncSetAttribute(tc::k_dist_tc<KB, HALVES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
         if (e != cudaSuccess) return e;
     }
-    const int n_row_tiles = (T + tc::kRowsPerCta - 1) / tc::kRowsPerCta;
-    const int splits = tc_splits(T, cb.K);
-    const int n_items = n_row_tiles * splits;
-    const int grid = n_items < sm_count() ? n_items : sm_count();
-    tc::k_dist_tc<KB><<<grid, tc::kThreads, L.total + 1024, s>>>(ma, mb, T, cb.K, cb.info, static_cast<int4*>(records), cand,
-                                                                 flagged, n_flagged, stats, splits);
+    const TcGeom geom = tc_geom(T, cb.K, KB * tc::kKBlock);
+    const int splits = geom.splits, grid = geom.grid;
+    if (geom.cl != (HALVES == 1 ? 2 : 1)) return cudaErrorInvalidValue;
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(tc::kThreads);
+        cfg.dynamicSmemBytes = L.total + 1024;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)geom.cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, tc::k_dist_tc<KB, HALVES>, ma, mb, T, cb.K, (const int*)cb.info,
+                                           static_cast<int4*>(records), cand, flagged, n_flagged, stats, splits);
+        if (e != cudaSuccess) return e;
+    }
     count_launch();
     {
         constexpr int D = KB * tc::kKBlock;
@@ -751,14 +870,20 @@ cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* r
             return cudaErrorInvalidValue;
         return launch_dist_tc16(ma, mb, (int)T, zn16, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, s);
     }
-    if (!tc::make_map(&ma, zn16, (uint64_t)T, cb.D, tc::kRowsPerCta) ||
-        !tc::make_map(&mb, cb.en16, (uint64_t)cb.K, cb.D, tc::kTileN))
+    // clusters: a CTA fetches (and multicasts) one 64-code half of every codebook stage
+    const TcGeom geom = tc_geom(T, cb.K, cb.D);
+    const int rows = geom.rows;
+    if (!tc::make_map(&ma, zn16, (uint64_t)T, cb.D, rows) ||
+        !tc::make_map(&mb, cb.en16, (uint64_t)cb.K, cb.D, geom.cl == 2 ? tc::kTileN / 2 : tc::kTileN))
         return cudaErrorInvalidValue;
     switch (cb.D / tc::kKBlock) {
-        case 1: return launch_tc_kernel<1>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
-        case 2: return launch_tc_kernel<2>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
-        case 4: return launch_tc_kernel<4>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
-        case 8: return launch_tc_kernel<8>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
+        case 1: return launch_tc_kernel<1, 2>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
+        case 2: return launch_tc_kernel<2, 2>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
+        case 4: return launch_tc_kernel<4, 2>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
+        case 8:
+            if (rows == 128)
+                return launch_tc_kernel<8, 1>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
+            return launch_tc_kernel<8, 2>(ma, mb, (int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -52,6 +52,10 @@ cudaError_t launch_nchw_to_tok(const float* in, int64_t T, int64_t hw, int D, co
 cudaError_t launch_tok_to_nchw(const float* in, int64_t T, int64_t hw, int D, float* out, cudaStream_t s);
 // row_sq[t] = sum(zn^2) over contiguous rows, ATen order (used after the NCHW path)
 cudaError_t launch_row_sumsq(const float* zn32, int64_t T, int D, float* row_sq, cudaStream_t s);
+// the three NCHW prep launches above in one (hw % 4 == 0, D in {64, 128, 256}, ATen's 4-stripe reduction shape)
+bool prep_nchw_fused_supported(int64_t T, int64_t hw, int D);
+cudaError_t launch_prep_nchw_fused(const float* z, int64_t T, int64_t hw, int D, float* denom, float* zn32, __half* zn16,
+                                   float* row_sq, const ZeroList& zl, bool raw, cudaStream_t s);
 
 // ---- vq_dist_simt.cu -------------------------------------------------------------------------
 // Exhaustive fp32 search.  rows == nullptr: all T rows; else the first *n_rows entries of `rows`.

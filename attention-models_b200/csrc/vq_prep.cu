@@ -491,6 +491,142 @@ cudaError_t launch_norm_nchw(const float* z, int64_t T, int64_t hw, int D, float
 }
 
 // ---------------------------------------------------------------------------------------------
+// The NCHW prep in ONE launch (it was three: k_norm_nchw, k_nchw_to_tok, k_row_sumsq = 29 us of a 190 us cfg 2 encode,
+// the input read twice and the unit rows written and read back).  A CTA of 128 threads owns 32 tokens x D channels:
+// thread (y = warp, i = lane >> 3, tq = lane & 7) is k_norm_nchw's accumulator i of channel stripe y for token quad tq -
+// the same fma chain over channels y + 4i + 16m, the same ((a0+a1)+a2)+a3 and (s0+s2)+(s1+s3) - and keeps the D/16
+// float4 it loaded in registers.  It then divides them by the denominators, transposes through shared memory, and each
+// warp writes 8 token rows: unit rows fp32 + fp16 and, from the row as RowMap holds it, row_sq exactly as k_row_sumsq.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) k_prep_nchw_fused(const float* __restrict__ z, int64_t T, int64_t hw,
+                                                         float* __restrict__ denom, float* __restrict__ zn32,
+                                                         __half* __restrict__ zn16, float* __restrict__ row_sq, ZeroList zl,
+                                                         int raw) {
+    using M = RowMap<D>;
+    constexpr int kM = D / 16;                  // channels per accumulator chain
+    constexpr int kStride = D + 4;              // floats per staged token row (16-byte aligned rows)
+    extern __shared__ __align__(16) float s_tile[];          // [32][kStride]
+    __shared__ float4 part[4][8];
+    zero_ranges(zl, blockIdx.x, gridDim.x);
+    const int lane = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int tq = lane & 7, i = lane >> 3;
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    const int64_t t = t0 + 4 * tq;                           // first of this thread's 4 tokens (hw % 4 == 0: same image)
+    float4 v[kM];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < T) {
+        const int64_t b = t / hw, p = t % hw;
+        const float* base = z + (b * D) * hw + p;
+#pragma unroll
+        for (int m = 0; m < kM; ++m) v[m] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(y + 4 * i + 16 * m) * hw));
+#pragma unroll
+        for (int m = 0; m < kM; ++m) {
+            acc.x = __fmaf_rn(v[m].x, v[m].x, acc.x);
+            acc.y = __fmaf_rn(v[m].y, v[m].y, acc.y);
+            acc.z = __fmaf_rn(v[m].z, v[m].z, acc.z);
+            acc.w = __fmaf_rn(v[m].w, v[m].w, acc.w);
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < kM; ++m) v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 dn = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (!raw) {
+        // stripe sum ((a0 + a1) + a2) + a3 on every lane of the token quad
+        float4 sy;
+        {
+            float4 a[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                a[k].x = __shfl_sync(VQ_FULL, acc.x, tq + 8 * k);
+                a[k].y = __shfl_sync(VQ_FULL, acc.y, tq + 8 * k);
+                a[k].z = __shfl_sync(VQ_FULL, acc.z, tq + 8 * k);
+                a[k].w = __shfl_sync(VQ_FULL, acc.w, tq + 8 * k);
+            }
+            sy.x = __fadd_rn(__fadd_rn(__fadd_rn(a[0].x, a[1].x), a[2].x), a[3].x);
+            sy.y = __fadd_rn(__fadd_rn(__fadd_rn(a[0].y, a[1].y), a[2].y), a[3].y);
+            sy.z = __fadd_rn(__fadd_rn(__fadd_rn(a[0].z, a[1].z), a[2].z), a[3].z);
+            sy.w = __fadd_rn(__fadd_rn(__fadd_rn(a[0].w, a[1].w), a[2].w), a[3].w);
+        }
+        if (i == 0) part[y][tq] = sy;
+        __syncthreads();
+        const float4 s0 = part[0][tq], s1 = part[1][tq], s2 = part[2][tq], s3 = part[3][tq];
+        float4 tot;
+        tot.x = __fadd_rn(__fadd_rn(s0.x, s2.x), __fadd_rn(s1.x, s3.x));
+        tot.y = __fadd_rn(__fadd_rn(s0.y, s2.y), __fadd_rn(s1.y, s3.y));
+        tot.z = __fadd_rn(__fadd_rn(s0.z, s2.z), __fadd_rn(s1.z, s3.z));
+        tot.w = __fadd_rn(__fadd_rn(s0.w, s2.w), __fadd_rn(s1.w, s3.w));
+        dn.x = norm_denominator(tot.x); dn.y = norm_denominator(tot.y);
+        dn.z = norm_denominator(tot.z); dn.w = norm_denominator(tot.w);
+    }
+    if (y == 0 && i == 0 && t < T) *reinterpret_cast<float4*>(denom + t) = dn;
+    // transpose: token 4 tq + c, channel y + 4 i + 16 m
+    {
+        float* col = s_tile + (4 * tq) * kStride + y + 4 * i;
+#pragma unroll
+        for (int m = 0; m < kM; ++m) {
+            col[0 * kStride + 16 * m] = raw ? v[m].x : __fdiv_rn(v[m].x, dn.x);
+            col[1 * kStride + 16 * m] = raw ? v[m].y : __fdiv_rn(v[m].y, dn.y);
+            col[2 * kStride + 16 * m] = raw ? v[m].z : __fdiv_rn(v[m].z, dn.z);
+            col[3 * kStride + 16 * m] = raw ? v[m].w : __fdiv_rn(v[m].w, dn.w);
+        }
+    }
+    __syncthreads();
+    for (int rr = 0; rr < 8; ++rr) {
+        const int r = 8 * y + rr;
+        const int64_t row = t0 + r;
+        if (row >= T) break;
+        const float* src = s_tile + r * kStride;
+        float x[M::kPerLane];
+        if constexpr (M::kVec) {
+#pragma unroll
+            for (int m = 0; m < M::kPerLane / 4; ++m) {
+                const float4 q = *reinterpret_cast<const float4*>(src + (lane + 32 * m) * 4);
+                x[4 * m + 0] = q.x; x[4 * m + 1] = q.y; x[4 * m + 2] = q.z; x[4 * m + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < M::kPerLane; ++j) x[j] = src[lane + M::kWidth * j];
+        }
+        M::store(zn32 + row * D, lane, x);
+        if (zn16) M::store_half(zn16 + row * D, lane, x);
+        const float s2 = M::template sumsq<false>(x);
+        if (lane == 0) row_sq[row] = s2;
+    }
+}
+
+bool prep_nchw_fused_supported(int64_t T, int64_t hw, int D) {
+    static const bool off = [] { const char* e = getenv("VQ_PREP_NCHW_FUSED"); return e && e[0] == '0'; }();
+    return !off && T > 0 && hw % 4 == 0 && (D == 64 || D == 128 || D == 256) && aten_strided_stripes(T, hw, D) == 4;
+}
+
+cudaError_t launch_prep_nchw_fused(const float* z, int64_t T, int64_t hw, int D, float* denom, float* zn32, __half* zn16,
+                                   float* row_sq, const ZeroList& zl, bool raw, cudaStream_t s) {
+    const unsigned blocks = (unsigned)((T + 31) / 32);
+    const size_t smem = (size_t)32 * (D + 4) * sizeof(float);
+#define VQ_PREP_NCHW_CASE(kD)                                                                                           \
+    case kD: {                                                                                                          \
+        static PerDeviceOnce once;                                                                                      \
+        if (once.need()) {                                                                                              \
+            cudaError_t e = cudaFuncSetAttribute(k_prep_nchw_fused<kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                             \
+        }                                                                                                               \
+        k_prep_nchw_fused<kD><<<blocks, 128, smem, s>>>(z, T, hw, denom, zn32, zn16, row_sq, zl, raw ? 1 : 0);           \
+        break;                                                                                                          \
+    }
+    switch (D) {
+        VQ_PREP_NCHW_CASE(64)
+        VQ_PREP_NCHW_CASE(128)
+        VQ_PREP_NCHW_CASE(256)
+        default: return cudaErrorInvalidValue;
+    }
+#undef VQ_PREP_NCHW_CASE
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Layout changes between (b, D, hw) and (T, D): 32 x 32 tiles through padded shared memory, both
 // sides coalesced.  nchw_to_tok optionally divides by denom[t] (true division, as F.normalize).
 // ---------------------------------------------------------------------------------------------

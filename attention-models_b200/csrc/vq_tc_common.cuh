@@ -98,6 +98,24 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+// the same box into every CTA of `mask` (same CTA-relative destination and barrier offsets in each)
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                      uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// all threads of all CTAs of the cluster
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -124,6 +142,12 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint6
 
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// ... arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
 }
 
 // 32 lanes x 32 columns of fp32: thread i gets columns [col, col + 32) of TMEM lane (lane_base + i)
