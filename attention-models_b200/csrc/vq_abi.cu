@@ -214,7 +214,8 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
     vq::ZeroList zl = {};
     int nz = 0;
     auto zero = [&](void* p, size_t bytes) { zl.ptr[nz] = p; zl.bytes[nz] = bytes; ++nz; };
-    if (use_tc) zero(w.n_flagged, sizeof(int) * (tc16 ? 64 + vq::kFlaggedCap : 64 + vq::kFewFlagged));
+    // [0]: listed rows, [64 ..]: done counters of the listed-row searches, then (generic filter) the tiled scan's tile counters
+    if (use_tc) zero(w.n_flagged, sizeof(int) * (tc16 ? 64 + vq::kFlaggedCap : 64 + vq::kFewFlagged + vq::kScanTileCounters));
     if (!(flags & VQ_FLAG_KEEP_STATS)) {
         zero(st, sizeof(int64_t) * VQ_STATS_LEN);
         if (hist) zero(hist, sizeof(int32_t) * (size_t)K);
@@ -256,16 +257,22 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
                                           zq_tok, idx, hist, seg_sums, st, s));
         exact_timer.stop();
     } else {
+        // (profile slots: SEARCH = the tensor-core filter alone, as at D = 32; EXACT_FINISH = everything behind it.
+        //  Without the filter the exhaustive scan is the search.)
         if (use_tc) {
             // filter -> exact rescoring (+ the undecided rows when they are few) -> tiled exhaustive scan of a long list
             VQ_CUDA(vq::launch_dist_tc(zn16, zn32, w.row_sq, cbv, T, w.cand, w.flagged, w.n_flagged, st, w.tc_ws, w.scan_ws, s));
-            VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, T * vq::tc_flag_multiplier(T, K, D),
-                                          w.cand, st, w.scan_ws, s, vq::kFewFlagged));
+            timer.stop();
         } else {
             VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, nullptr, nullptr, T, w.cand, st, nullptr, s));
+            timer.stop();
         }
-        timer.stop();
         SlotTimer finish_timer(s, VQ_PROFILE_EXACT_FINISH);
+        if (use_tc) {
+            VQ_CUDA(vq::launch_rescore_generic(zn32, w.row_sq, cbv, T, w.cand, w.flagged, w.n_flagged, st, w.tc_ws, w.scan_ws, s));
+            VQ_CUDA(vq::launch_scan_exact(zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, T * vq::tc_flag_multiplier(T, K, D),
+                                          w.cand, st, w.scan_ws, s, vq::kFewFlagged, w.n_flagged + 64 + vq::kFewFlagged));
+        }
         if (!indices_only && layout == VQ_LAYOUT_NCHW) {
             VQ_CUDA(vq::launch_finish_nchw(zn32, w.cand, cbv, T, hw, z_q, idx, hist, seg_sums, st, s));
             zq_tok = nullptr;      // written in place: no layout kernel behind

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) k_scan_exact(const float* __restrict__ zn
                                                     int64_t row_end, int* __restrict__ cand,
                                                     float4* __restrict__ partial, int partial_cap,
                                                     int* __restrict__ tile_done, int64_t* __restrict__ stats,
-                                                    ListedFinish fin, int min_rows) {
+                                                    ListedFinish fin, int min_rows, int64_t tail_end) {
     __shared__ __align__(16) float zs[kDK][kTM + 4];
     __shared__ __align__(16) float es[kDK][kTN + 4];
     __shared__ int row_id[kTM];
@@ -87,142 +87,150 @@ __global__ void __launch_bounds__(256) k_scan_exact(const float* __restrict__ zn
 
     pdl_trigger();
     pdl_wait();
-    int64_t n_rows = rows ? (int64_t)(*n_rows_ptr) : T;
-    if (rows && n_rows <= min_rows) return;         // a short list was handled by the rescoring kernel
-    if (n_rows > row_end) n_rows = row_end;
+    const int64_t n_listed = rows ? (int64_t)(*n_rows_ptr) : T;
+    if (rows && n_listed <= min_rows) return;       // a short list was handled by the rescoring kernel
     long long loss_fx = 0;
     unsigned long long bad = 0;
     const int tid = threadIdx.x;
-    int k_lo = 0, k_hi = K;
-    if (partial) {
-        const int per = ((K + (int)gridDim.y - 1) / (int)gridDim.y + kTN - 1) / kTN * kTN;
-        k_lo = min(K, (int)blockIdx.y * per);
-        k_hi = min(K, k_lo + per);
-    }
     const int ty = tid >> 4, tx = tid & 15;     // rows ty*4..+3 ; codes tx*4..+3 and 64+tx*4..+3
-
-    for (int64_t tile0 = row_begin + (int64_t)blockIdx.x * kTM; tile0 < n_rows; tile0 += (int64_t)gridDim.x * kTM) {
-        __syncthreads();
-        if (tid < kTM) {
-            const int64_t i = tile0 + tid;
-            row_id[tid] = (i < n_rows) ? (rows ? rows[i] : (int)i) : -1;
+    // pass 0: rows [row_begin, row_end), split over blockIdx.y when `partial` is given.  pass 1 (tail_end > row_end):
+    // the listed rows beyond the split treatment, [row_end, tail_end), unsplit, over all blocks of the grid.
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1 && (tail_end <= row_end || n_listed <= row_end)) break;
+        float4* part = pass == 0 ? partial : nullptr;
+        const int64_t n_rows = pass == 0 ? (n_listed < row_end ? n_listed : row_end) : (n_listed < tail_end ? n_listed : tail_end);
+        const int64_t first = pass == 0 ? row_begin : row_end;
+        const int64_t blk = pass == 0 ? (int64_t)blockIdx.x : (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+        const int64_t n_blk = pass == 0 ? (int64_t)gridDim.x : (int64_t)gridDim.x * gridDim.y;
+        int k_lo = 0, k_hi = K;
+        if (part) {
+            const int per = ((K + (int)gridDim.y - 1) / (int)gridDim.y + kTN - 1) / kTN * kTN;
+            k_lo = min(K, (int)blockIdx.y * per);
+            k_hi = min(K, k_lo + per);
         }
-        __syncthreads();
-
-        Best best[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) { best[r].d1 = INFINITY; best[r].i1 = 0x7fffffff; best[r].d2 = INFINITY; }
-        float a_sq[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int rid = row_id[ty * 4 + r];
-            a_sq[r] = (rid >= 0) ? row_sq[rid] : 0.f;
-        }
-
-        for (int k0 = k_lo; k0 < k_hi; k0 += kTN) {
-            float acc[4][8];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
-
-            for (int d0 = 0; d0 < D; d0 += kDK) {
-                __syncthreads();
-                // stage zs[d][row] and es[d][code] (global reads coalesced along d)
-                for (int e = tid; e < kTM * kDK; e += 256) {
-                    const int r = e / kDK, d = e % kDK;
-                    const int rid = row_id[r];
-                    zs[d][r] = (rid >= 0 && d0 + d < D) ? __ldg(zn32 + (int64_t)rid * D + d0 + d) : 0.f;
-                }
-                for (int e = tid; e < kTN * kDK; e += 256) {
-                    const int c = e / kDK, d = e % kDK;
-                    const int k = k0 + c;
-                    es[d][c] = (k < K && d0 + d < D) ? __ldg(en32 + (int64_t)k * D + d0 + d) : 0.f;
-                }
-                __syncthreads();
-#pragma unroll 8
-                for (int d = 0; d < kDK; ++d) {
-                    const float4 zv = *reinterpret_cast<const float4*>(&zs[d][ty * 4]);
-                    const float4 e0 = *reinterpret_cast<const float4*>(&es[d][tx * 4]);
-                    const float4 e1 = *reinterpret_cast<const float4*>(&es[d][64 + tx * 4]);
-                    const float zr[4] = {zv.x, zv.y, zv.z, zv.w};
-                    const float ec[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) acc[r][c] = __fmaf_rn(zr[r], ec[c], acc[r][c]);
-                }
-            }
-            // distances of this code tile, in increasing code order per thread
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int k = k0 + ((c < 4) ? (tx * 4 + c) : (64 + tx * 4 + c - 4));
-                if (k < K) {
-                    const float b_sq = __ldg(code_sq + k);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) best_insert(best[r], ref_distance(a_sq[r], b_sq, acc[r][c]), k);
-                }
-            }
-        }
-        // merge the 16 threads (tx) that share each row: xor-shuffles stay inside 16-lane groups
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-#pragma unroll
-            for (int off = 8; off > 0; off >>= 1) {
-                const float od1 = __shfl_xor_sync(VQ_FULL, best[r].d1, off);
-                const int oi1 = __shfl_xor_sync(VQ_FULL, best[r].i1, off);
-                const float od2 = __shfl_xor_sync(VQ_FULL, best[r].d2, off);
-                best_merge(best[r], od1, oi1, od2);
-            }
-            const int rid = row_id[ty * 4 + r];
-            if (tx == 0 && rid >= 0) {
-                if (partial) {
-                    const int64_t slot = tile0 + ty * 4 + r;
-                    partial[(int64_t)blockIdx.y * partial_cap + slot] =
-                        make_float4(best[r].d1, __int_as_float(best[r].i1), best[r].d2, 0.f);
-                } else {
-                    cand[rid] = best[r].i1 | kCandExactBit;
-                    const float gap = best[r].d2 - best[r].d1;
-                    if (stats && gap < VQ_NEAR_TIE_REL * fabsf(best[r].d1))
-                        atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), 1ull);
-                    if (fin.idx) finish_row_serial(zn32, en32, D, K, rid, best[r].i1, fin, loss_fx, bad);
-                }
-            }
-        }
-        if (partial) {
-            // the last code range to finish a row tile folds all ranges: lane = range, shuffle tree.
-            // argmin with index tie-break and "second smallest" do not depend on the fold order.
-            __threadfence();
+        for (int64_t tile0 = first + blk * kTM; tile0 < n_rows; tile0 += n_blk * kTM) {
             __syncthreads();
-            const int tile_idx = (int)(tile0 / kTM);
-            if (tid == 0) s_last = (atomicAdd(tile_done + tile_idx, 1) == (int)gridDim.y - 1);
+            if (tid < kTM) {
+                const int64_t i = tile0 + tid;
+                row_id[tid] = (i < n_rows) ? (rows ? rows[i] : (int)i) : -1;
+            }
             __syncthreads();
-            if (s_last) {
-                __threadfence();
-                const int lane = tid & 31, w = tid >> 5;
-                for (int rr = w * 8; rr < w * 8 + 8; ++rr) {
-                    const int64_t slot = tile0 + rr;
-                    if (slot >= n_rows) break;
-                    Best b;
-                    b.d1 = INFINITY; b.i1 = 0x7fffffff; b.d2 = INFINITY;
-                    if (lane < (int)gridDim.y) {
-                        const float4 p = __ldcg(partial + (int64_t)lane * partial_cap + slot);
-                        b.d1 = p.x; b.i1 = __float_as_int(p.y); b.d2 = p.z;
+
+            Best best[4];
+    #pragma unroll
+            for (int r = 0; r < 4; ++r) { best[r].d1 = INFINITY; best[r].i1 = 0x7fffffff; best[r].d2 = INFINITY; }
+            float a_sq[4];
+    #pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int rid = row_id[ty * 4 + r];
+                a_sq[r] = (rid >= 0) ? row_sq[rid] : 0.f;
+            }
+
+            for (int k0 = k_lo; k0 < k_hi; k0 += kTN) {
+                float acc[4][8];
+    #pragma unroll
+                for (int r = 0; r < 4; ++r)
+    #pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+
+                for (int d0 = 0; d0 < D; d0 += kDK) {
+                    __syncthreads();
+                    // stage zs[d][row] and es[d][code] (global reads coalesced along d)
+                    for (int e = tid; e < kTM * kDK; e += 256) {
+                        const int r = e / kDK, d = e % kDK;
+                        const int rid = row_id[r];
+                        zs[d][r] = (rid >= 0 && d0 + d < D) ? __ldg(zn32 + (int64_t)rid * D + d0 + d) : 0.f;
                     }
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) {
-                        const float od1 = __shfl_xor_sync(VQ_FULL, b.d1, off);
-                        const int oi1 = __shfl_xor_sync(VQ_FULL, b.i1, off);
-                        const float od2 = __shfl_xor_sync(VQ_FULL, b.d2, off);
-                        best_merge(b, od1, oi1, od2);
+                    for (int e = tid; e < kTN * kDK; e += 256) {
+                        const int c = e / kDK, d = e % kDK;
+                        const int k = k0 + c;
+                        es[d][c] = (k < K && d0 + d < D) ? __ldg(en32 + (int64_t)k * D + d0 + d) : 0.f;
                     }
-                    if (lane == 0) {
-                        cand[row_id[rr]] = b.i1 | kCandExactBit;
-                        if (stats && (b.d2 - b.d1) < VQ_NEAR_TIE_REL * fabsf(b.d1))
+                    __syncthreads();
+    #pragma unroll 8
+                    for (int d = 0; d < kDK; ++d) {
+                        const float4 zv = *reinterpret_cast<const float4*>(&zs[d][ty * 4]);
+                        const float4 e0 = *reinterpret_cast<const float4*>(&es[d][tx * 4]);
+                        const float4 e1 = *reinterpret_cast<const float4*>(&es[d][64 + tx * 4]);
+                        const float zr[4] = {zv.x, zv.y, zv.z, zv.w};
+                        const float ec[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+    #pragma unroll
+                        for (int r = 0; r < 4; ++r)
+    #pragma unroll
+                            for (int c = 0; c < 8; ++c) acc[r][c] = __fmaf_rn(zr[r], ec[c], acc[r][c]);
+                    }
+                }
+                // distances of this code tile, in increasing code order per thread
+    #pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int k = k0 + ((c < 4) ? (tx * 4 + c) : (64 + tx * 4 + c - 4));
+                    if (k < K) {
+                        const float b_sq = __ldg(code_sq + k);
+    #pragma unroll
+                        for (int r = 0; r < 4; ++r) best_insert(best[r], ref_distance(a_sq[r], b_sq, acc[r][c]), k);
+                    }
+                }
+            }
+            // merge the 16 threads (tx) that share each row: xor-shuffles stay inside 16-lane groups
+    #pragma unroll
+            for (int r = 0; r < 4; ++r) {
+    #pragma unroll
+                for (int off = 8; off > 0; off >>= 1) {
+                    const float od1 = __shfl_xor_sync(VQ_FULL, best[r].d1, off);
+                    const int oi1 = __shfl_xor_sync(VQ_FULL, best[r].i1, off);
+                    const float od2 = __shfl_xor_sync(VQ_FULL, best[r].d2, off);
+                    best_merge(best[r], od1, oi1, od2);
+                }
+                const int rid = row_id[ty * 4 + r];
+                if (tx == 0 && rid >= 0) {
+                    if (part) {
+                        const int64_t slot = tile0 + ty * 4 + r;
+                        part[(int64_t)blockIdx.y * partial_cap + slot] =
+                            make_float4(best[r].d1, __int_as_float(best[r].i1), best[r].d2, 0.f);
+                    } else {
+                        cand[rid] = best[r].i1 | kCandExactBit;
+                        const float gap = best[r].d2 - best[r].d1;
+                        if (stats && gap < VQ_NEAR_TIE_REL * fabsf(best[r].d1))
                             atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), 1ull);
+                        if (fin.idx) finish_row_serial(zn32, en32, D, K, rid, best[r].i1, fin, loss_fx, bad);
                     }
                 }
-                if (tid == 0) tile_done[tile_idx] = 0;      // ready for the next call
+            }
+            if (part) {
+                // the last code range to finish a row tile folds all ranges: lane = range, shuffle tree.
+                // argmin with index tie-break and "second smallest" do not depend on the fold order.
+                __threadfence();
+                __syncthreads();
+                const int tile_idx = (int)(tile0 / kTM);
+                if (tid == 0) s_last = (atomicAdd(tile_done + tile_idx, 1) == (int)gridDim.y - 1);
+                __syncthreads();
+                if (s_last) {
+                    __threadfence();
+                    const int lane = tid & 31, w = tid >> 5;
+                    for (int rr = w * 8; rr < w * 8 + 8; ++rr) {
+                        const int64_t slot = tile0 + rr;
+                        if (slot >= n_rows) break;
+                        Best b;
+                        b.d1 = INFINITY; b.i1 = 0x7fffffff; b.d2 = INFINITY;
+                        if (lane < (int)gridDim.y) {
+                            const float4 p = __ldcg(part + (int64_t)lane * partial_cap + slot);
+                            b.d1 = p.x; b.i1 = __float_as_int(p.y); b.d2 = p.z;
+                        }
+    #pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) {
+                            const float od1 = __shfl_xor_sync(VQ_FULL, b.d1, off);
+                            const int oi1 = __shfl_xor_sync(VQ_FULL, b.i1, off);
+                            const float od2 = __shfl_xor_sync(VQ_FULL, b.d2, off);
+                            best_merge(b, od1, oi1, od2);
+                        }
+                        if (lane == 0) {
+                            cand[row_id[rr]] = b.i1 | kCandExactBit;
+                            if (stats && (b.d2 - b.d1) < VQ_NEAR_TIE_REL * fabsf(b.d1))
+                                atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_NEAR_TIE_ROWS), 1ull);
+                        }
+                    }
+                    if (tid == 0) tile_done[tile_idx] = 0;      // ready for the next call
+                }
             }
         }
     }
@@ -234,15 +242,18 @@ __global__ void __launch_bounds__(256) k_scan_exact(const float* __restrict__ zn
 
 // [tile-done counters (one int per 64-row tile, 1 KiB)] [partials: splits x cap float4]
 constexpr size_t kTileDoneBytes = 1024;
-static_assert(kScanSplitCap / kTM * sizeof(int) <= kTileDoneBytes, "tile counters do not fit");
+static_assert(kScanSplitCap / kTM * sizeof(int) <= kTileDoneBytes && kScanTileCounters * sizeof(int) == kTileDoneBytes,
+              "tile counters do not fit");
 size_t scan_partial_bytes(int64_t T) {
     const int64_t cap = T < kScanSplitCap ? T : kScanSplitCap;
-    return kTileDoneBytes + sizeof(float4) * (size_t)kScanSplits * (size_t)(cap > 0 ? cap : 1);
+    const size_t tiled = kTileDoneBytes + sizeof(float4) * (size_t)kScanSplits * (size_t)(cap > 0 ? cap : 1);
+    const size_t few = (size_t)kFewFlagged * kFewFlaggedSlices * 16;      // k_rescore_g's partials: rows x slices
+    return tiled > few ? tiled : few;
 }
 
 cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
                               const int* rows, const int* n_rows, int64_t max_rows, int* cand, int64_t* stats,
-                              void* partial_ws, cudaStream_t s, int min_rows) {
+                              void* partial_ws, cudaStream_t s, int min_rows, int* tile_done_zeroed) {
     const int64_t n = rows ? max_rows : T;
     if (n == 0) return cudaSuccess;
     const int64_t cap_blocks = (int64_t)sm_count() * 16;
@@ -250,7 +261,7 @@ cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const Code
         int64_t blocks = (n + kTM - 1) / kTM;
         if (blocks > cap_blocks) blocks = cap_blocks;
         k_scan_exact<<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, 0,
-                                                     n, cand, nullptr, 0, nullptr, stats, ListedFinish{}, min_rows);
+                                                     n, cand, nullptr, 0, nullptr, stats, ListedFinish{}, min_rows, (int64_t)0);
         count_launch();
         return cudaGetLastError();
     }
@@ -259,26 +270,28 @@ cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const Code
     int splits = cb.K / kTN;
     if (splits > kScanSplits) splits = kScanSplits;
     if (splits < 1) splits = 1;
-    int* tile_done = static_cast<int*>(partial_ws);
+    // tile-done counters: the caller's (cleared with the other per-call counters by the forward's first kernel), else
+    // the head of partial_ws, cleared here
+    int* tile_done = tile_done_zeroed;
     float4* partial = reinterpret_cast<float4*>(static_cast<char*>(partial_ws) + kTileDoneBytes);
-    cudaError_t e = cudaMemsetAsync(tile_done, 0, kTileDoneBytes, s);
-    if (e != cudaSuccess) return e;
-    // the list length is only known on the device: the grid covers up to 128 row tiles x the code splits (blocks
-    // beyond the list read the row count and leave; an empty list costs a few microseconds), enough parallelism for
-    // the ~0.5 % of rows the D = 256 filter leaves undecided
+    if (!tile_done) {
+        tile_done = static_cast<int*>(partial_ws);
+        cudaError_t e = cudaMemsetAsync(tile_done, 0, kTileDoneBytes, s);
+        if (e != cudaSuccess) return e;
+    }
+    // the list length is only known on the device: the grid is one wave of (row tiles x code splits) blocks, which
+    // read the row count and leave when the list is short - enough parallelism for the ~0.5 % of rows the D = 256
+    // filter leaves undecided.  Listed rows beyond `cap` are scanned unsplit by the same
+    // blocks afterwards (pass 1 of the kernel).
+    // (two resident blocks per SM is all the kernel's registers allow: more blocks than that only make the usual
+    // case - nothing listed, every block reads the count and leaves - cost 6 us instead of 2.5; blocks stride over tiles)
     int tiles = (cap + kTM - 1) / kTM;
-    if (tiles > 128) tiles = 128;
+    const int resident = (2 * sm_count() + splits - 1) / splits;
+    if (tiles > resident) tiles = resident;
     dim3 grid((unsigned)tiles, (unsigned)splits);
     k_scan_exact<<<grid, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, 0, cap, cand,
-                                      partial, cap, tile_done, stats, ListedFinish{}, min_rows);
+                                      partial, cap, tile_done, stats, ListedFinish{}, min_rows, (int64_t)n);
     count_launch();
-    if (n > cap) {
-        int64_t blocks = (n - cap + kTM - 1) / kTM;
-        if (blocks > sm_count()) blocks = sm_count();
-        k_scan_exact<<<(unsigned)blocks, 256, 0, s>>>(zn32, row_sq, cb.en32, cb.code_sq, T, cb.K, cb.D, rows, n_rows, cap,
-                                                     n, cand, nullptr, 0, nullptr, stats, ListedFinish{}, min_rows);
-        count_launch();
-    }
     return cudaGetLastError();
 }
 
@@ -291,7 +304,7 @@ cudaError_t launch_scan_listed_tail(const float* zn32, const float* row_sq, cons
     if (blocks <= 0) return cudaSuccess;
     if (blocks > sm_count()) blocks = sm_count();
     cudaError_t e = launch_pdl(k_scan_exact, dim3((unsigned)blocks), dim3(256), 0, s, zn32, row_sq, cb.en32, cb.code_sq, T, cb.K,
-                               cb.D, rows, n_rows, row_begin, T, cand, nullptr, 0, nullptr, stats, fin, 0);
+                               cb.D, rows, n_rows, row_begin, T, cand, nullptr, 0, nullptr, stats, fin, 0, (int64_t)0);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }

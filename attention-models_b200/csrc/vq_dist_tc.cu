@@ -42,7 +42,6 @@ constexpr int kTileN = 128;          // codes per accumulator stage
 constexpr int kGroupTiles = 2;       // tiles per group (256 columns)
 constexpr int kGroupCols = kTileN * kGroupTiles;
 constexpr int kKBlock = 32;          // halfs per K block: 64-byte rows, SWIZZLE_64B
-constexpr int kABlockBytes = kRowsPerCta * kKBlock * 2;   // 16 KiB (two row halves; one half: 8 KiB)
 __host__ __device__ constexpr int a_block_bytes(int halves) { return halves * 128 * kKBlock * 2; }
 constexpr int kBStageBytes = kTileN * kKBlock * 2;        // 8 KiB
 constexpr int kThreads = 512;        // warps 0-3 service (TMA, MMA, TMEM alloc, idle), 4-7 spare, 8-15 epilogue
@@ -497,7 +496,7 @@ k_dist_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kRescoreThreads = 128;
 constexpr int kMaxSplits = 4;
-constexpr int kFlaggedSlices = 32;
+constexpr int kFlaggedSlices = kFewFlaggedSlices;
 struct __align__(16) FlaggedPartial {
     unsigned long long best; float second; float pad;
 };
@@ -530,16 +529,19 @@ __device__ __forceinline__ float cell_distance_g(const float4* __restrict__ en32
     return ref_distance(a_sq, csq, dot);
 }
 
+// Without a minimum-blocks bound ptxas settles on 48-64 registers for this kernel and serialises the 32 loads a batch
+// wants in flight; 4 blocks per SM = up to 128 registers keeps them all outstanding.
+#ifndef VQ_RESCORE_MINBLOCKS
+#define VQ_RESCORE_MINBLOCKS 4
+#endif
 template <int D, int kS>      // kS: code splits the records may come from (1, or kMaxSplits)
-__global__ void __launch_bounds__(kRescoreThreads)
+__global__ void __launch_bounds__(kRescoreThreads, VQ_RESCORE_MINBLOCKS)
 k_rescore_g(const int4* __restrict__ rec, const float* __restrict__ zn32, const float* __restrict__ row_sq,
             const float4* __restrict__ en32c, const float* __restrict__ csq_cell, int T, int K, int splits,
             const int* __restrict__ flagged, const int* __restrict__ n_flagged, FlaggedPartial* __restrict__ partial,
             int* __restrict__ done, int* __restrict__ cand, int64_t* __restrict__ stats) {
     constexpr int kChunks = D / 4;
     __shared__ __align__(16) float4 s_z[kRescoreThreads / 32][4][kChunks + 1];
-    __shared__ unsigned long long s_best[kRescoreThreads / 32];
-    __shared__ float s_second[kRescoreThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m = lane & 7, grp = lane >> 3;
     const float4* zn4 = reinterpret_cast<const float4*>(zn32);
@@ -619,60 +621,84 @@ k_rescore_g(const int4* __restrict__ rec, const float* __restrict__ zn32, const 
             if (n_cells > 1) ++multi;
         }
     }
-    // ---- the rows the filter could not decide, when they are few (latency matters, not throughput): each listed row
-    // is split over kFlaggedSlices items that scan a slice of ALL cells; the last item of a row to finish folds the
-    // partial (best, second) pairs.  Longer lists are left to the tiled exhaustive kernel (k_scan_exact).
+    // ---- the rows the filter could not decide, when they are few (latency matters, not throughput).  A work item is
+    // (batch of 16 listed rows, slice of ALL cells): the block stages the 16 rows, group gi of 8 lanes scores row gi
+    // against every cell of the slice - the 16 groups walk the same cells together, so a cell comes out of L2 once per
+    // batch (one row per item, as it was, read the whole 8 MB of cell copies per listed row: 224 MB for the 28 rows a
+    // cfg 2 encode leaves undecided, 60 % of this kernel's L2 traffic).  The last item of a batch to finish folds the
+    // partial (best, second) pairs of its rows.  Longer lists are left to the tiled exhaustive kernel (k_scan_exact).
     {
         const int n = *n_flagged;
         if (n > 0 && n <= kFewFlagged) {
+            constexpr int kBatchRows = kRescoreThreads / 8;
+            __shared__ int s_last;
+            float4 (*zrow)[kChunks + 1] = reinterpret_cast<float4 (*)[kChunks + 1]>(&s_z[0][0][0]);
             const int bgrp = threadIdx.x >> 3;
+            const int n_batches = (n + kBatchRows - 1) / kBatchRows;
             const int n_cells = K / 8;
             const int per_slice = (n_cells + kFlaggedSlices - 1) / kFlaggedSlices;
-            for (int item = blockIdx.x; item < n * kFlaggedSlices; item += gridDim.x) {
-                const int i = item / kFlaggedSlices, slice = item % kFlaggedSlices;
-                const int row = flagged[i];
+            for (int item = blockIdx.x; item < n_batches * kFlaggedSlices; item += gridDim.x) {
+                const int batch = item / kFlaggedSlices, slice = item % kFlaggedSlices;
                 __syncthreads();                       // the previous item's shared values are consumed
-                for (int c = threadIdx.x; c < kChunks; c += kRescoreThreads) s_z[0][0][c] = __ldg(zn4 + (int64_t)row * kChunks + c);
+                for (int e = threadIdx.x; e < kBatchRows * kChunks; e += kRescoreThreads) {
+                    const int r = e / kChunks, c = e % kChunks;
+                    const int i = batch * kBatchRows + r;
+                    if (i < n) zrow[r][c] = __ldg(zn4 + (int64_t)flagged[i] * kChunks + c);
+                }
                 __syncthreads();
-                const float4* zs = s_z[0][0];
-                const float a_sq = __ldg(row_sq + row);
+                const int i = batch * kBatchRows + bgrp;
+                const bool have = i < n;
                 Top2 top;
                 top.init();
-                const int c_end = min(n_cells, (slice + 1) * per_slice);
-                for (int ci = slice * per_slice + bgrp; ci < c_end; ci += kRescoreThreads / 8) {
-                    const int g = ci >> 5, slot = ci & 31;
-                    const int code = g * kGroupCols + 64 * (m >> 1) + ((slot & 16) << 1) + (slot & 15) + 16 * (m & 1);
-                    top.add(dist_key(cell_distance_g<D>(en32c, csq_cell, ci, m, zs, a_sq), code));
+                if (have) {
+                    const float a_sq = __ldg(row_sq + flagged[i]);
+                    const int c_end = min(n_cells, (slice + 1) * per_slice);
+                    for (int ci = slice * per_slice; ci < c_end; ++ci) {
+                        const int g = ci >> 5, slot = ci & 31;
+                        const int code = g * kGroupCols + 64 * (m >> 1) + ((slot & 16) << 1) + (slot & 15) + 16 * (m & 1);
+                        top.add(dist_key(cell_distance_g<D>(en32c, csq_cell, ci, m, zrow[bgrp], a_sq), code));
+                    }
                 }
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
+                for (int off = 4; off > 0; off >>= 1) {
                     const unsigned long long ob = __shfl_xor_sync(VQ_FULL, top.best, off);
                     const float os = __shfl_xor_sync(VQ_FULL, top.second, off);
                     top.merge(ob, os);
                 }
-                if (lane == 0) { s_best[warp] = top.best; s_second[warp] = top.second; }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    Top2 all;
-                    all.init();
-                    for (int w = 0; w < kRescoreThreads / 32; ++w) all.merge(s_best[w], s_second[w]);
+                if (have && m == 0) {
                     FlaggedPartial pp;
-                    pp.best = all.best; pp.second = all.second; pp.pad = 0.f;
+                    pp.best = top.best; pp.second = top.second; pp.pad = 0.f;
                     partial[(int64_t)i * kFlaggedSlices + slice] = pp;
+                }
+                __threadfence();
+                __syncthreads();
+                if (threadIdx.x == 0) s_last = (atomicAdd(done + batch, 1) == kFlaggedSlices - 1);
+                __syncthreads();
+                if (s_last) {
                     __threadfence();
-                    if (atomicAdd(done + i, 1) == kFlaggedSlices - 1) {
-                        __threadfence();
+                    // warp w folds rows 4w .. 4w + 3 of the batch: lane = slices lane, lane + 32, ...
+                    for (int rr = 0; rr < kBatchRows / (kRescoreThreads / 32); ++rr) {
+                        const int fi = batch * kBatchRows + warp * (kBatchRows / (kRescoreThreads / 32)) + rr;
+                        if (fi >= n) break;
                         Top2 fin;
                         fin.init();
-                        for (int w = 0; w < kFlaggedSlices; ++w) {
-                            const FlaggedPartial* q = partial + (int64_t)i * kFlaggedSlices + w;
-                            fin.merge(__ldcg(&q->best), __ldcg(&q->second));
+                        for (int q = lane; q < kFlaggedSlices; q += 32) {
+                            const FlaggedPartial* pq = partial + (int64_t)fi * kFlaggedSlices + q;
+                            fin.merge(__ldcg(&pq->best), __ldcg(&pq->second));
                         }
-                        const float bd = key_dist(fin.best);
-                        cand[row] = (int)(uint32_t)fin.best | kCandExactBit;
-                        if (fin.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) ++ties;
-                        done[i] = 0;                   // ready for the next call
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) {
+                            const unsigned long long ob = __shfl_xor_sync(VQ_FULL, fin.best, off);
+                            const float os = __shfl_xor_sync(VQ_FULL, fin.second, off);
+                            fin.merge(ob, os);
+                        }
+                        if (lane == 0) {
+                            const float bd = key_dist(fin.best);
+                            cand[flagged[fi]] = (int)(uint32_t)fin.best | kCandExactBit;
+                            if (fin.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) ++ties;
+                        }
                     }
+                    if (threadIdx.x == 0) done[batch] = 0;     // ready for the next call
                 }
             }
         }
@@ -797,6 +823,42 @@ size_t tc_workspace_bytes(int64_t T, int K, int D) {
     return tc_supported(T, K, D) ? (size_t)(T > 0 ? T : 1) * tc::kRecordBytes * tc_splits(T, K, D) : 0;
 }
 
+template <int D>
+static cudaError_t launch_rescore_d(int T, const float* zn32, const float* row_sq, const CodebookView& cb, int* cand,
+                                    const int* flagged, int* n_flagged, int64_t* stats, const void* records, void* partial_ws,
+                                    cudaStream_t s) {
+    const int splits = tc_splits(T, cb.K, D);
+    const int rows_per_block = tc::kRescoreThreads / 8;
+    int64_t blocks = ((int64_t)T + rows_per_block - 1) / rows_per_block;
+    const int64_t cap = (int64_t)sm_count() * 16 * 2;
+    if (blocks > cap) blocks = cap;
+    if (splits == 1)
+        tc::k_rescore_g<D, 1><<<(unsigned)blocks, tc::kRescoreThreads, 0, s>>>(
+            static_cast<const int4*>(records), zn32, row_sq, reinterpret_cast<const float4*>(cb.en32c), cb.csq_cell, T, cb.K,
+            splits, flagged, n_flagged, static_cast<tc::FlaggedPartial*>(partial_ws), n_flagged + 64, cand, stats);
+    else
+        tc::k_rescore_g<D, tc::kMaxSplits><<<(unsigned)blocks, tc::kRescoreThreads, 0, s>>>(
+            static_cast<const int4*>(records), zn32, row_sq, reinterpret_cast<const float4*>(cb.en32c), cb.csq_cell, T, cb.K,
+            splits, flagged, n_flagged, static_cast<tc::FlaggedPartial*>(partial_ws), n_flagged + 64, cand, stats);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// the exact rescoring behind the generic filter (launch_dist_tc with !tc16_supported): cand[] for every decided row,
+// and for the undecided ones when at most kFewFlagged are listed
+cudaError_t launch_rescore_generic(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T, int* cand,
+                                   const int* flagged, int* n_flagged, int64_t* stats, const void* tc_ws, void* partial_ws,
+                                   cudaStream_t s) {
+    if (T == 0) return cudaSuccess;
+    switch (cb.D) {
+        case 32: return launch_rescore_d<32>((int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
+        case 64: return launch_rescore_d<64>((int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
+        case 128: return launch_rescore_d<128>((int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
+        case 256: return launch_rescore_d<256>((int)T, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, partial_ws, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 template <int KB, int HALVES>
 static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb, int T, const float* zn32,
                                     const float* row_sq, const CodebookView& cb, int* cand, int* flagged,
@@ -826,22 +888,6 @@ static cudaError_t launch_tc_kernel(const CUtensorMap& ma, const CUtensorMap& mb
         if (e != cudaSuccess) return e;
     }
     count_launch();
-    {
-        constexpr int D = KB * tc::kKBlock;
-        const int rows_per_block = tc::kRescoreThreads / 8;
-        int64_t blocks = ((int64_t)T + rows_per_block - 1) / rows_per_block;
-        const int64_t cap = (int64_t)sm_count() * 16 * 2;
-        if (blocks > cap) blocks = cap;
-        if (splits == 1)
-            tc::k_rescore_g<D, 1><<<(unsigned)blocks, tc::kRescoreThreads, 0, s>>>(
-                static_cast<const int4*>(records), zn32, row_sq, reinterpret_cast<const float4*>(cb.en32c), cb.csq_cell, T, cb.K,
-                splits, flagged, n_flagged, static_cast<tc::FlaggedPartial*>(partial_ws), n_flagged + 64, cand, stats);
-        else
-            tc::k_rescore_g<D, tc::kMaxSplits><<<(unsigned)blocks, tc::kRescoreThreads, 0, s>>>(
-                static_cast<const int4*>(records), zn32, row_sq, reinterpret_cast<const float4*>(cb.en32c), cb.csq_cell, T, cb.K,
-                splits, flagged, n_flagged, static_cast<tc::FlaggedPartial*>(partial_ws), n_flagged + 64, cand, stats);
-        count_launch();
-    }
 #ifdef VQ_TC_INSTRUMENT
     {
         cudaStreamSynchronize(s);

@@ -63,9 +63,11 @@ cudaError_t launch_prep_nchw_fused(const float* z, int64_t T, int64_t hw, int D,
 // partial_ws (scan_partial_bytes) lets listed rows split the codebook over blocks; may be null.
 size_t scan_partial_bytes(int64_t T);
 // min_rows: a listed scan leaves at once when the list holds at most min_rows entries (someone else took them)
+// tile_done_zeroed: kScanTileCounters ints the caller has already cleared on the stream (else cleared here, by a memset)
+constexpr int kScanTileCounters = 256;
 cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
                               const int* rows, const int* n_rows, int64_t max_rows, int* cand, int64_t* stats,
-                              void* partial_ws, cudaStream_t s, int min_rows = 0);
+                              void* partial_ws, cudaStream_t s, int min_rows = 0, int* tile_done_zeroed = nullptr);
 
 // outputs of the finish pass for rows a search kernel finishes itself (all null: search only)
 struct ListedFinish {
@@ -90,13 +92,18 @@ cudaError_t launch_exact_finish16(const void* records, const float* zn32, const 
 bool tc_supported(int64_t T, int K, int D);
 size_t tc_workspace_bytes(int64_t T, int K, int D);
 int tc_flag_multiplier(int64_t T, int K, int D);   // entries the undecided-row list may need per token row
-// generic D: the filter launch is followed by k_rescore_g, which also searches the listed rows itself when there are at
-// most kFewFlagged of them (needs n_flagged[64 ..] zeroed: kFewFlagged done counters; partial_ws >= kFewFlagged * 512 B);
-// longer lists are for launch_scan_exact(..., min_rows = kFewFlagged)
+// generic D: launch_dist_tc is the filter alone; launch_rescore_generic (k_rescore_g) then rescores the decided rows and
+// searches the listed rows itself when there are at most kFewFlagged of them (needs n_flagged[64 ..] zeroed: kFewFlagged
+// done counters; partial_ws >= kFewFlagged * kFewFlaggedSlices * 16 B); longer lists are for
+// launch_scan_exact(..., min_rows = kFewFlagged)
 constexpr int kFewFlagged = 128;
+constexpr int kFewFlaggedSlices = 256;   // cell slices a listed row's search is cut into there
 cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* row_sq, const CodebookView& cb,
                            int64_t T, int* cand, int* flagged, int* n_flagged, int64_t* stats, void* tc_ws,
                            void* partial_ws, cudaStream_t s);
+cudaError_t launch_rescore_generic(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T, int* cand,
+                                   const int* flagged, int* n_flagged, int64_t* stats, const void* tc_ws, void* partial_ws,
+                                   cudaStream_t s);
 
 // ---- vq_finish.cu ----------------------------------------------------------------------------
 // idx / hist / z_q (token-major) / loss partial from final indices in cand[]; with seg_sums (K*D + K int64, not

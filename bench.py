@@ -559,7 +559,8 @@ def run_b200(args, cfg):
     peak_tf = peaks["tf_burst"] if burst else peaks["tf_sustained"]
     search_total_ms = search_avg_ms + (exact_avg_ms if tc_path else 0.0)
     roofline = {"kernel": ("k_dist_tc16: tcgen05 distance + running-maximum filter (z.C^T for every token x code)" if tc16 else
-                           "k_dist_tc: tcgen05 distance filter (fp32 accumulators)" if tc_path else
+                           "k_dist_tc: tcgen05 distance filter, fp32 accumulators (D = 256: clusters of two 128-row CTAs sharing the "
+                           "codebook stream by TMA multicast)" if tc_path else
                            "k_scan_exact: exhaustive fp32 distance + argmin"),
                 "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf,
@@ -575,8 +576,8 @@ def run_b200(args, cfg):
                          "tcgen05 filter (fp32 accumulators) -> exact fp32 rescoring -> finish kernel" if tc_path else
                          "exact fp32 SIMT scan"),
                 "distance_plus_argmin": {
-                    "what": "filter + exact rescoring (the second half of distance+argmin; at D = 32 the same launch also does the "
-                            "finish pass: idx / z_q / loss / histogram / segment sums)",
+                    "what": "filter + everything behind it: exact rescoring, the rows the filter left undecided, and the finish "
+                            "pass (idx / z_q / loss / histogram / segment sums; one launch at D = 32, 2-3 launches otherwise)",
                     "ms": search_total_ms,
                     "tflops": flops_per_launch / (search_total_ms * 1e-3) / 1e12 if search_total_ms > 0 else 0.0,
                     "frac_vs_burst_peak": flops_per_launch / (search_total_ms * 1e-3) / 1e12 / peaks["tf_burst"] if search_total_ms > 0 else 0.0,
@@ -621,6 +622,11 @@ def run_b200(args, cfg):
             "SURVEY 8(d) backward: read G 4D, zn 4D, idx 8, write grad_z 4D; write grad_E 4KD once",
             "tokens: read G 4D, zn 4D, idx 8, denom 4; write grad_z 4D (code rows from L2); codebook: read seg sums 8D + 8, en 4D, "
             "write grad_E 4D")
+    if tc_path and not tc16 and not tok_major:
+        kernels["k_prep_nchw_fused (NCHW latents -> unit token rows fp32 + fp16, row norms: one launch)"] = hbm_kernel(
+            slots["prep_tokens"], "k_prep_nchw_fused", 4 * D * T, (10 * D + 8) * T,
+            "read z 4D per token (the unit rows it writes are an intermediate of this implementation)",
+            "read z 4D; write zn32 4D, zn16 2D, row_sq + denom 8")
     iface_total = sum(k["interface_bytes"] for k in kernels.values() if k) + (2 * D * T + 16 * T if tc16 and mode == "step" else 0)
     non_filter_ms = max(ms_step - search_avg_ms, 1e-6)
     hbm = {"peak_gbs": peak_gbs, "algorithmic_bytes_per_step": alg_bytes,

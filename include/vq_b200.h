@@ -278,8 +278,8 @@ VQ_API int vq_embedding_backward(const int64_t* ids, int64_t n_ids, int64_t ids_
  * vq_profile_slot then returns (and clears) any other slot.                                          */
 #define VQ_PROFILE_PREP_CODEBOOK   0
 #define VQ_PROFILE_PREP_TOKENS     1
-#define VQ_PROFILE_SEARCH          2
-#define VQ_PROFILE_EXACT_FINISH    3   /* exact rescoring + finish behind the filter (D = 32), else the finish pass */
+#define VQ_PROFILE_SEARCH          2   /* the tensor-core filter (without it: the exhaustive scan)                   */
+#define VQ_PROFILE_EXACT_FINISH    3   /* everything behind the filter: exact rescoring, undecided rows, finish pass  */
 #define VQ_PROFILE_TAIL            4   /* overflow of the undecided-row list (normally an empty launch)            */
 #define VQ_PROFILE_BACKWARD_TOKENS 5
 #define VQ_PROFILE_CODEBOOK_GRAD   6   /* incl. the fused peer exchange of a token-sharded job                      */

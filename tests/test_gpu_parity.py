@@ -685,6 +685,38 @@ def test_plain_l2_form_matches_its_oracle(dev, K, D, shape, scale):
     assert torch.equal(m.encode(z), idx)
 
 
+@pytest.mark.parametrize("D,T,few", [(256, 9000, False), (256, 600, False), (64, 9000, False), (256, 1000, True),
+                                     (128, 1000, True)])
+def test_generic_filter_undecided_rows_take_the_exhaustive_paths(dev, D, T, few):
+    """A codebook whose codes repeat eight times, 256 codes apart (= in eight different groups of the filter): every row
+    has more near-best groups than a verdict record holds, so the filter decides nothing and the rows go to the
+    fallbacks - the batched search inside the rescoring kernel (<= 128 listed rows), the tiled scan with the codebook
+    split over blocks (<= 8192) and its unsplit tail (beyond).  Ties must resolve to the lowest index like argmin."""
+    from vq_b200 import functional as F_vq
+    K = 2048
+    z = vo.make_latents((T, D), 61)
+    if few:     # one code in eight copies, 50 rows next to it: a short list of undecided rows
+        w = vo.make_codebook("vit", K, D, 60)
+        w[5::256] = w[5]
+        z[100:150] = w[5] * 2.0 + 0.01 * vo.make_latents((50, D), 62)
+    else:
+        w = vo.make_codebook("vit", 256, D, 60).repeat(K // 256, 1)
+    w, z = w.to(dev), z.to(dev)
+    prep = F_vq.prepare_codebook(w)
+    want = F_vq.encode_indices(z, w, "vit", prepared=prep, exact_scan=True)
+    got = F_vq.encode_indices(z, w, "vit", prepared=prep)
+    ref = vo.quantise("vit", z.view(1, T, D), w, 0.25).indices.view(-1)
+    assert torch.equal(got.view(-1), want.view(-1))
+    assert torch.equal(got.view(-1), ref)
+    if few:
+        assert bool((got.view(-1)[100:150] == 5).all())
+    else:
+        assert int(got.max()) < 256     # the first copy of every code wins its ties
+    # and a second call on the same workspace state (counters the kernels reset themselves)
+    again = F_vq.encode_indices(z, w, "vit", prepared=prep)
+    assert torch.equal(again, got)
+
+
 @pytest.mark.parametrize("env", [{"VQ_TC16_W16": "1"}, {"VQ_TC16_TS": "1"}, {"VQ_TC16_DISABLE": "1"}],
                          ids=["wide-drain", "rows-in-tmem", "generic-filter"])
 def test_alternative_filter_kernels_equal_exhaustive_search(env):
