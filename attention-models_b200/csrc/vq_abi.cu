@@ -178,7 +178,7 @@ int vq_workspace_bytes(int64_t T, int K, int D, int flags, size_t* out) {
 }
 
 int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* weight, void* cb, int K, int D, int form, float beta,
-               int flags, int64_t n_elem_total, float* z_q, int64_t* idx, float* loss, int32_t* hist, int64_t* stats,
+               int flags, int64_t n_elem_total, float* z_q, void* idx, float* loss, int32_t* hist, int64_t* stats,
                float* saved_zn, float* saved_denom, int64_t* seg_sums, void* ws, size_t ws_bytes, void* stream) {
     if (int r = check_dims(T, K, D)) return r;
     if (int r = check_layout(layout, T, hw)) return r;
@@ -189,6 +189,11 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
     const bool indices_only = (flags & VQ_FLAG_INDICES_ONLY) != 0;
     if (!indices_only && !z_q) return fail(VQ_ERR_ARG, "z_q is NULL without VQ_FLAG_INDICES_ONLY");
     if (indices_only && seg_sums) return fail(VQ_ERR_ARG, "seg_sums needs the full forward (no VQ_FLAG_INDICES_ONLY)");
+    // narrow token formats: encode-only calls (the backward reads the int64 indices of a full forward)
+    if ((flags & VQ_FLAG_IDX32) && (flags & VQ_FLAG_IDX16)) return fail(VQ_ERR_ARG, "VQ_FLAG_IDX32 and VQ_FLAG_IDX16 exclude each other");
+    const int idx_bits = (flags & VQ_FLAG_IDX16) ? 16 : ((flags & VQ_FLAG_IDX32) ? 32 : 64);
+    if (idx_bits != 64 && !indices_only) return fail(VQ_ERR_ARG, "narrow indices need VQ_FLAG_INDICES_ONLY");
+    if (idx_bits == 16 && K > 65536) return fail(VQ_ERR_ARG, "VQ_FLAG_IDX16 needs codebook_size <= 65536 (K=%d)", K);
     if (!ws) return fail(VQ_ERR_WORKSPACE, "workspace is NULL");
     FwdWs w = carve_forward(ws, T, K, D);
     if (ws_bytes < w.bytes) return fail(VQ_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, w.bytes);
@@ -254,7 +259,7 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
         timer.stop();
         SlotTimer exact_timer(s, VQ_PROFILE_EXACT_FINISH);
         VQ_CUDA(vq::launch_exact_finish16(w.tc_ws, zn32, w.row_sq, cbv, T, w.flagged, w.n_flagged, w.n_flagged + 64, w.scan_ws,
-                                          zq_tok, idx, hist, seg_sums, st, s));
+                                          zq_tok, idx, hist, seg_sums, st, s, idx_bits));
         exact_timer.stop();
     } else {
         // (profile slots: SEARCH = the tensor-core filter alone, as at D = 32; EXACT_FINISH = everything behind it.
@@ -274,10 +279,10 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
                                           w.cand, st, w.scan_ws, s, vq::kFewFlagged, w.n_flagged + 64 + vq::kFewFlagged));
         }
         if (!indices_only && layout == VQ_LAYOUT_NCHW) {
-            VQ_CUDA(vq::launch_finish_nchw(zn32, w.cand, cbv, T, hw, z_q, idx, hist, seg_sums, st, s));
+            VQ_CUDA(vq::launch_finish_nchw(zn32, w.cand, cbv, T, hw, z_q, idx, hist, seg_sums, st, s, idx_bits));
             zq_tok = nullptr;      // written in place: no layout kernel behind
         } else {
-            VQ_CUDA(vq::launch_finish(zn32, w.cand, cbv, T, zq_tok, idx, hist, seg_sums, st, s));
+            VQ_CUDA(vq::launch_finish(zn32, w.cand, cbv, T, zq_tok, idx, hist, seg_sums, st, s, idx_bits));
         }
         finish_timer.stop();
     }
@@ -488,10 +493,11 @@ int vq_backward_sharded(const void* const* peer_bufs, int world, int rank, int s
     return VQ_OK;
 }
 
-int vq_gather(const int64_t* idx, int64_t T, int64_t hw, const float* weight, const void* cb, int K, int D,
+int vq_gather_tokens(const void* idx, int token_bits, int64_t T, int64_t hw, const float* weight, const void* cb, int K, int D,
               int normalise, int layout_out, float* out, int64_t* stats, void* stream) {
     if (int r = check_dims(T, K, D)) return r;
     if (int r = check_layout(layout_out, T, hw)) return r;
+    if (token_bits != 16 && token_bits != 32 && token_bits != 64) return fail(VQ_ERR_ARG, "token_bits %d: 16, 32 or 64", token_bits);
     if (!idx || !out) return fail(VQ_ERR_ARG, "idx/out is NULL");
     const float* table = nullptr;
     if (normalise) {
@@ -503,8 +509,13 @@ int vq_gather(const int64_t* idx, int64_t T, int64_t hw, const float* weight, co
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (stats) VQ_CUDA(cudaMemsetAsync(stats + VQ_STAT_BAD_INDEX, 0, sizeof(int64_t), s));
-    VQ_CUDA(vq::launch_gather(idx, T, hw, table, K, D, layout_out, out, stats, s));
+    VQ_CUDA(vq::launch_gather(idx, T, hw, table, K, D, layout_out, out, stats, s, token_bits));
     return VQ_OK;
+}
+
+int vq_gather(const int64_t* idx, int64_t T, int64_t hw, const float* weight, const void* cb, int K, int D,
+              int normalise, int layout_out, float* out, int64_t* stats, void* stream) {
+    return vq_gather_tokens(idx, 64, T, hw, weight, cb, K, D, normalise, layout_out, out, stats, stream);
 }
 
 namespace {
@@ -525,10 +536,11 @@ int slot_total(int slot, double* ms_total, int64_t* launches) {
 }
 }  // namespace
 
-int vq_token_embed(const int64_t* tokens, const uint8_t* mask, int64_t T, int64_t n_per_seq, int64_t mask_token_id,
-                   int64_t ignore_index, const float* table, int64_t vocab, int dim, const float* pos, float* embeds,
-                   int64_t* input_ids, int64_t* labels, int64_t* stats, void* stream) {
+int vq_token_embed_tokens(const void* tokens, int token_bits, const uint8_t* mask, int64_t T, int64_t n_per_seq,
+                          int64_t mask_token_id, int64_t ignore_index, const float* table, int64_t vocab, int dim,
+                          const float* pos, float* embeds, int64_t* input_ids, int64_t* labels, int64_t* stats, void* stream) {
     if (T < 0 || T >= (1ll << 40)) return fail(VQ_ERR_ARG, "token count %lld out of range", (long long)T);
+    if (token_bits != 16 && token_bits != 32 && token_bits != 64) return fail(VQ_ERR_ARG, "token_bits %d: 16, 32 or 64", token_bits);
     if (!tokens && T > 0) return fail(VQ_ERR_ARG, "tokens is NULL");
     if (embeds && (!table || vocab <= 0 || dim <= 0 || dim % 4 != 0))
         return fail(VQ_ERR_ARG, "embeds needs a (vocab, dim) table with dim a multiple of 4 (dim=%d)", dim);
@@ -537,19 +549,42 @@ int vq_token_embed(const int64_t* tokens, const uint8_t* mask, int64_t T, int64_
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (stats) VQ_CUDA(cudaMemsetAsync(stats + VQ_STAT_BAD_INDEX, 0, sizeof(int64_t), s));
     VQ_CUDA(vq::launch_token_embed(tokens, mask, T, n_per_seq > 0 ? n_per_seq : 1, mask_token_id, ignore_index, table, vocab, dim,
-                                   pos, embeds, input_ids, labels, stats, s));
+                                   pos, embeds, input_ids, labels, stats, s, nullptr, token_bits));
+    return VQ_OK;
+}
+
+int vq_token_embed(const int64_t* tokens, const uint8_t* mask, int64_t T, int64_t n_per_seq, int64_t mask_token_id,
+                   int64_t ignore_index, const float* table, int64_t vocab, int dim, const float* pos, float* embeds,
+                   int64_t* input_ids, int64_t* labels, int64_t* stats, void* stream) {
+    return vq_token_embed_tokens(tokens, 64, mask, T, n_per_seq, mask_token_id, ignore_index, table, vocab, dim, pos, embeds,
+                                 input_ids, labels, stats, stream);
+}
+
+int vq_token_embed_causal_tokens(const void* tokens, int token_bits, int64_t T, int64_t n_per_seq, const float* table,
+                                 int64_t vocab, int dim, const float* pos, const float* start, float* embeds, int64_t* stats,
+                                 void* stream) {
+    if (T < 0 || T >= (1ll << 40) || n_per_seq <= 0 || T % n_per_seq != 0)
+        return fail(VQ_ERR_ARG, "vq_token_embed_causal needs T a multiple of n_per_seq > 0 (T=%lld)", (long long)T);
+    if (token_bits != 16 && token_bits != 32 && token_bits != 64) return fail(VQ_ERR_ARG, "token_bits %d: 16, 32 or 64", token_bits);
+    if (!tokens || !table || !start || !embeds || vocab <= 0 || dim <= 0 || dim % 4 != 0)
+        return fail(VQ_ERR_ARG, "vq_token_embed_causal needs tokens, a (vocab, dim) table with dim %% 4 == 0, start and embeds");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (stats) VQ_CUDA(cudaMemsetAsync(stats + VQ_STAT_BAD_INDEX, 0, sizeof(int64_t), s));
+    VQ_CUDA(vq::launch_token_embed(tokens, nullptr, T, n_per_seq, 0, 0, table, vocab, dim, pos, embeds, nullptr, nullptr, stats, s,
+                                   start, token_bits));
     return VQ_OK;
 }
 
 int vq_token_embed_causal(const int64_t* tokens, int64_t T, int64_t n_per_seq, const float* table, int64_t vocab, int dim,
                           const float* pos, const float* start, float* embeds, int64_t* stats, void* stream) {
-    if (T < 0 || T >= (1ll << 40) || n_per_seq <= 0 || T % n_per_seq != 0)
-        return fail(VQ_ERR_ARG, "vq_token_embed_causal needs T a multiple of n_per_seq > 0 (T=%lld)", (long long)T);
-    if (!tokens || !table || !start || !embeds || vocab <= 0 || dim <= 0 || dim % 4 != 0)
-        return fail(VQ_ERR_ARG, "vq_token_embed_causal needs tokens, a (vocab, dim) table with dim %% 4 == 0, start and embeds");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (stats) VQ_CUDA(cudaMemsetAsync(stats + VQ_STAT_BAD_INDEX, 0, sizeof(int64_t), s));
-    VQ_CUDA(vq::launch_token_embed(tokens, nullptr, T, n_per_seq, 0, 0, table, vocab, dim, pos, embeds, nullptr, nullptr, stats, s, start));
+    return vq_token_embed_causal_tokens(tokens, 64, T, n_per_seq, table, vocab, dim, pos, start, embeds, stats, stream);
+}
+
+int vq_tokens_convert(const void* in, int in_bits, void* out, int out_bits, int64_t T, void* stream) {
+    auto ok = [](int b) { return b == 16 || b == 32 || b == 64; };
+    if (!ok(in_bits) || !ok(out_bits)) return fail(VQ_ERR_ARG, "token bits %d -> %d: 16, 32 or 64", in_bits, out_bits);
+    if (T < 0 || ((!in || !out) && T > 0)) return fail(VQ_ERR_ARG, "bad argument to vq_tokens_convert");
+    VQ_CUDA(vq::launch_tokens_convert(in, in_bits, out, out_bits, T, static_cast<cudaStream_t>(stream)));
     return VQ_OK;
 }
 

@@ -116,6 +116,19 @@ struct RowMap {
     }
 };
 
+// Token indices on the wire: int64 (what the reference returns), or int32 / uint16 where the caller asked for a narrow
+// format (encode-only calls and the consumers behind them; K <= 65536 for 16 bits).  `bits` is warp-uniform.
+__device__ __forceinline__ void store_token(void* base, int64_t t, int code, int bits) {
+    if (bits == 64) static_cast<int64_t*>(base)[t] = code;
+    else if (bits == 32) static_cast<int32_t*>(base)[t] = code;
+    else static_cast<uint16_t*>(base)[t] = (uint16_t)code;
+}
+__device__ __forceinline__ int64_t load_token(const void* base, int64_t t, int bits) {
+    if (bits == 64) return __ldg(static_cast<const int64_t*>(base) + t);
+    if (bits == 32) return (int64_t)__ldg(static_cast<const int32_t*>(base) + t);
+    return (int64_t)__ldg(static_cast<const uint16_t*>(base) + t);
+}
+
 // clamp_min(eps) keeps NaN (ATen semantics); fmaxf would drop it.
 __device__ __forceinline__ float clamp_min_keep_nan(float v, float lo) { return (v < lo) ? lo : v; }
 

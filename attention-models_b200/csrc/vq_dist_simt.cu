@@ -35,7 +35,7 @@ __device__ __forceinline__ void best_insert(Best& b, float d, int i) {
 __device__ __forceinline__ void finish_row_serial(const float* __restrict__ zn32, const float* __restrict__ en32, int D, int K,
                                                   int row, int code, const ListedFinish& fin, long long& loss_fx,
                                                   unsigned long long& bad) {
-    fin.idx[row] = code;
+    store_token(fin.idx, row, code, fin.idx_bits);
     if (fin.hist) atomicAdd(fin.hist + code, 1);
     if (!fin.zq) return;
     unsigned poison = 0;

@@ -1203,7 +1203,7 @@ __device__ __forceinline__ float cell_distance_staged(const float4* __restrict__
 // What vq_finish.cu does for one row: z_q = zn + (q - zn), loss partial in fixed point and -- when the step trains
 // the codebook -- the row's terms of the segment sums S_code += fixed(q - zn).
 struct FinishOut {
-    float* zq; int64_t* idx; int32_t* hist; unsigned long long* seg;
+    float* zq; void* idx; int32_t* hist; unsigned long long* seg; int idx_bits;
 };
 // chunk `c` (4 elements) of one row: returns q - zn of the chunk
 __device__ __forceinline__ float4 finish_chunk(const float4 a, const float4* __restrict__ en4, const FinishOut& out, int row,
@@ -1417,7 +1417,7 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
         const bool dup = __any_sync(VQ_FULL, __popc(same) > 8);        // uniform; false on all but collapsed usage
         const bool lead = valid && (!dup || ((__ffs(same) - 1) >> 3) == grp);
         if (valid && m == 0) {
-            out.idx[row] = code;
+            store_token(out.idx, row, code, out.idx_bits);
             if (out.hist && lead) atomicAdd(out.hist + code, dup ? __popc(same & 0x01010101u) : 1);
             if (close_ballot & gmask) counts += kTie;
             if (n_cells > 1) counts += kMulti;
@@ -1517,7 +1517,7 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
                 if (last) {
                     const float bd = key_dist(fin.best);
                     const int code = (int)(uint32_t)fin.best;
-                    out.idx[row] = code;
+                    store_token(out.idx, row, code, out.idx_bits);
                     if (out.hist) atomicAdd(out.hist + code, 1);
                     if (fin.second - bd < VQ_NEAR_TIE_REL * fabsf(bd)) counts += kTie;
                     if (out.zq) finish_row_serial(zn4, en4, out, K, row, code, loss_fx, bad);
@@ -1612,8 +1612,8 @@ cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T
 // (degenerate inputs only) are left in cand[] = -1 for the caller's overflow path.
 cudaError_t launch_exact_finish16(const void* records, const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
                                   const int* flagged, const int* n_flagged, int* done_counters, void* partial_ws,
-                                  float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats,
-                                  cudaStream_t s) {
+                                  float* zq_tok, void* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats,
+                                  cudaStream_t s, int idx_bits) {
     const int cap = (int)(T < kFlaggedCap ? T : kFlaggedCap);
     const int rows_per_block = tc16::kExactThreads / 8;
     int64_t blocks = (T + rows_per_block - 1) / rows_per_block;
@@ -1621,7 +1621,7 @@ cudaError_t launch_exact_finish16(const void* records, const float* zn32, const 
     const int64_t grid_cap = (int64_t)sm_count() * grid_mult;    // 32 = 8 resident blocks per SM x 4 waves
     if (blocks > grid_cap) blocks = grid_cap;
     tc16::FinishOut out;
-    out.zq = zq_tok; out.idx = idx_out; out.hist = hist;
+    out.zq = zq_tok; out.idx = idx_out; out.idx_bits = idx_bits; out.hist = hist;
     out.seg = zq_tok ? reinterpret_cast<unsigned long long*>(seg_sums) : nullptr;
     cudaError_t e = launch_pdl(tc16::k_exact_finish16, dim3((unsigned)blocks), dim3(tc16::kExactThreads), 0, s,
                                static_cast<const int4*>(records), zn32, row_sq, cb.en32, reinterpret_cast<const float4*>(cb.en32c),

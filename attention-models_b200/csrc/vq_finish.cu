@@ -36,7 +36,7 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 template <int kSpans>
 __global__ void __launch_bounds__(256) k_finish(const float* __restrict__ zn, const int* __restrict__ cand,
                                                 const float* __restrict__ en, int64_t T, int D, int log2d, int K,
-                                                float* __restrict__ zq, int64_t* __restrict__ idx_out,
+                                                float* __restrict__ zq, void* __restrict__ idx_out, int idx_bits,
                                                 int32_t* __restrict__ hist, unsigned long long* __restrict__ seg,
                                                 int64_t* __restrict__ stats) {
     __shared__ unsigned long long red[8];
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) k_finish(const float* __restrict__ zn, co
     if (!zq) {   // indices only: one thread per row
         for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
             const int k = __ldg(cand + t) & (kCandExactBit - 1);
-            idx_out[t] = k;
+            store_token(idx_out, t, k, idx_bits);
             if (hist) atomicAdd(hist + k, 1);
         }
         return;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) k_finish(const float* __restrict__ zn, co
                 if (e < total) {
                     const int c = (int)(e & (D - 1));
                     if (c == 0) {
-                        idx_out[e >> log2d] = k[j][i];
+                        store_token(idx_out, e >> log2d, k[j][i], idx_bits);
                         if (hist) atomicAdd(hist + k[j][i], 1);
                     }
                     df[i] = __fsub_rn(q[j][i], a[j][i]);
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) k_finish(const float* __restrict__ zn, co
 // the pixels -- no token-major staging buffer and no separate layout kernel.  Segment-sum REDs cover 256 contiguous bytes.
 __global__ void __launch_bounds__(256) k_finish_nchw(const float* __restrict__ zn, const int* __restrict__ cand,
                                                      const float* __restrict__ en, int64_t T, int64_t hw, int D, int K,
-                                                     float* __restrict__ zq_nchw, int64_t* __restrict__ idx_out,
+                                                     float* __restrict__ zq_nchw, void* __restrict__ idx_out, int idx_bits,
                                                      int32_t* __restrict__ hist, unsigned long long* __restrict__ seg,
                                                      int64_t* __restrict__ stats) {
     __shared__ float tile[32][33];
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) k_finish_nchw(const float* __restrict__ z
             df[i] = __fsub_rn(q, a);
             tile[tt][x] = __fadd_rn(a, df[i]);
             if (c == 0) {
-                idx_out[t] = k;
+                store_token(idx_out, t, k, idx_bits);
                 if (hist) atomicAdd(hist + k, 1);
             }
             if (seg) {
@@ -178,18 +178,18 @@ __global__ void __launch_bounds__(256) k_finish_nchw(const float* __restrict__ z
 }
 
 cudaError_t launch_finish_nchw(const float* zn32, const int* cand, const CodebookView& cb, int64_t T, int64_t hw,
-                               float* zq_nchw, int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats,
-                               cudaStream_t s) {
+                               float* zq_nchw, void* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats,
+                               cudaStream_t s, int idx_bits) {
     if (T == 0) return cudaSuccess;
     dim3 grid((unsigned)((T + 31) / 32), (unsigned)((cb.D + 31) / 32));
-    k_finish_nchw<<<grid, 256, 0, s>>>(zn32, cand, cb.en32, T, hw, cb.D, cb.K, zq_nchw, idx_out, hist,
+    k_finish_nchw<<<grid, 256, 0, s>>>(zn32, cand, cb.en32, T, hw, cb.D, cb.K, zq_nchw, idx_out, idx_bits, hist,
                                        reinterpret_cast<unsigned long long*>(seg_sums), stats);
     count_launch();
     return cudaGetLastError();
 }
 
 cudaError_t launch_finish(const float* zn32, const int* cand, const CodebookView& cb, int64_t T, float* zq_tok,
-                          int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats, cudaStream_t s) {
+                          void* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats, cudaStream_t s, int idx_bits) {
     if (T == 0) return cudaSuccess;
     constexpr int kSpans = 2;
     int log2d = 0;
@@ -199,7 +199,7 @@ cudaError_t launch_finish(const float* zn32, const int* cand, const CodebookView
     int64_t blocks = (work + 7) / 8;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    k_finish<kSpans><<<(unsigned)blocks, 256, 0, s>>>(zn32, cand, cb.en32, T, cb.D, log2d, cb.K, zq_tok, idx_out, hist,
+    k_finish<kSpans><<<(unsigned)blocks, 256, 0, s>>>(zn32, cand, cb.en32, T, cb.D, log2d, cb.K, zq_tok, idx_out, idx_bits, hist,
                                                       zq_tok ? reinterpret_cast<unsigned long long*>(seg_sums) : nullptr, stats);
     count_launch();
     return cudaGetLastError();
@@ -223,14 +223,14 @@ cudaError_t launch_loss_finalize(const int64_t* stats, int64_t n_elem_total, int
 // decode gather.  Token-major out: element-wise float4.  NCHW out: 32-token x 32-channel tiles
 // through shared memory so both the row reads and the (b, D, hw) writes are coalesced.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_gather_tok(const int64_t* __restrict__ idx, int64_t T, int chunks, int K,
+__global__ void __launch_bounds__(256) k_gather_tok(const void* __restrict__ idx, int idx_bits, int64_t T, int chunks, int K,
                                                     const float4* __restrict__ table, float4* __restrict__ out,
                                                     int64_t* __restrict__ stats) {
     const int64_t total = T * chunks;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t t = e / chunks;
         const int c = (int)(e - t * chunks);
-        const int64_t k = __ldg(idx + t);
+        const int64_t k = load_token(idx, t, idx_bits);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (k >= 0 && k < K) v = __ldg(table + k * chunks + c);
         else if (c == 0 && stats) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_BAD_INDEX), 1ull);
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) k_gather_tok(const int64_t* __restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(256) k_gather_nchw(const int64_t* __restrict__ idx, int64_t T, int64_t hw, int D,
+__global__ void __launch_bounds__(256) k_gather_nchw(const void* __restrict__ idx, int idx_bits, int64_t T, int64_t hw, int D,
                                                      int K, const float* __restrict__ table, float* __restrict__ out,
                                                      int64_t* __restrict__ stats) {
     __shared__ float tile[32][33];
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) k_gather_nchw(const int64_t* __restrict__
     const int c0 = blockIdx.y * 32;
     if (y == 0) {
         const int64_t t = t0 + x;
-        int64_t k = (t < T) ? __ldg(idx + t) : 0;
+        int64_t k = (t < T) ? load_token(idx, t, idx_bits) : 0;
         if (k < 0 || k >= K) {
             if (blockIdx.y == 0 && stats) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_BAD_INDEX), 1ull);
             k = -1;
@@ -272,19 +272,19 @@ __global__ void __launch_bounds__(256) k_gather_nchw(const int64_t* __restrict__
     }
 }
 
-cudaError_t launch_gather(const int64_t* idx, int64_t T, int64_t hw, const float* table, int K, int D,
-                          int layout_out, float* out, int64_t* stats, cudaStream_t s) {
+cudaError_t launch_gather(const void* idx, int64_t T, int64_t hw, const float* table, int K, int D,
+                          int layout_out, float* out, int64_t* stats, cudaStream_t s, int idx_bits) {
     if (T == 0) return cudaSuccess;
     if (layout_out == VQ_LAYOUT_TOKEN_MAJOR) {
         const int chunks = D / 4;
         int64_t blocks = (T * chunks + 255) / 256;
         const int64_t cap = (int64_t)sm_count() * 16;
         if (blocks > cap) blocks = cap;
-        k_gather_tok<<<(unsigned)blocks, 256, 0, s>>>(idx, T, chunks, K, reinterpret_cast<const float4*>(table),
+        k_gather_tok<<<(unsigned)blocks, 256, 0, s>>>(idx, idx_bits, T, chunks, K, reinterpret_cast<const float4*>(table),
                                                      reinterpret_cast<float4*>(out), stats);
     } else {
         dim3 grid((unsigned)((T + 31) / 32), (unsigned)((D + 31) / 32));
-        k_gather_nchw<<<grid, dim3(32, 8), 0, s>>>(idx, T, hw, D, K, table, out, stats);
+        k_gather_nchw<<<grid, dim3(32, 8), 0, s>>>(idx, idx_bits, T, hw, D, K, table, out, stats);
     }
     count_launch();
     return cudaGetLastError();

@@ -71,7 +71,8 @@ cudaError_t launch_scan_exact(const float* zn32, const float* row_sq, const Code
 
 // outputs of the finish pass for rows a search kernel finishes itself (all null: search only)
 struct ListedFinish {
-    float* zq = nullptr; int64_t* idx = nullptr; int32_t* hist = nullptr; unsigned long long* seg = nullptr;
+    float* zq = nullptr; void* idx = nullptr; int32_t* hist = nullptr; unsigned long long* seg = nullptr;
+    int idx_bits = 64;
 };
 cudaError_t launch_scan_listed_tail(const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
                                     const int* rows, const int* n_rows, int64_t row_begin, int* cand, int64_t* stats,
@@ -83,8 +84,8 @@ constexpr int kFlaggedCap = 4096;     // listed rows that get the sliced per-row
 // exact rescoring of the filter's records + sliced search of the listed rows + the finish pass, one launch
 cudaError_t launch_exact_finish16(const void* records, const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
                                   const int* flagged, const int* n_flagged, int* done_counters, void* partial_ws,
-                                  float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats,
-                                  cudaStream_t s);
+                                  float* zq_tok, void* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats,
+                                  cudaStream_t s, int idx_bits = 64);
 
 // ---- vq_dist_tc.cu ---------------------------------------------------------------------------
 // tcgen05 search: cand[row] = cell id (or exact index for rows resolved in-kernel); rows it cannot
@@ -109,15 +110,16 @@ cudaError_t launch_rescore_generic(const float* zn32, const float* row_sq, const
 // idx / hist / z_q (token-major) / loss partial from final indices in cand[]; with seg_sums (K*D + K int64, not
 // zeroed here) also the codebook-gradient segment sums S_k += fixed(q_k - zn_t) as integer reductions.
 cudaError_t launch_finish(const float* zn32, const int* cand, const CodebookView& cb, int64_t T,
-                          float* zq_tok, int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats, cudaStream_t s);
+                          float* zq_tok, void* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats, cudaStream_t s,
+                          int idx_bits = 64);      // idx_out: int64, or int32 / uint16 (store_token, vq_common.cuh)
 // the same with z_q written straight into the (b, D, hw) output
 cudaError_t launch_finish_nchw(const float* zn32, const int* cand, const CodebookView& cb, int64_t T, int64_t hw,
-                               float* zq_nchw, int64_t* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats,
-                               cudaStream_t s);
+                               float* zq_nchw, void* idx_out, int32_t* hist, int64_t* seg_sums, int64_t* stats,
+                               cudaStream_t s, int idx_bits = 64);
 cudaError_t launch_loss_finalize(const int64_t* stats, int64_t n_elem_total, int form, float beta, float* loss,
                                  cudaStream_t s);
-cudaError_t launch_gather(const int64_t* idx, int64_t T, int64_t hw, const float* table, int K, int D,
-                          int layout_out, float* out, int64_t* stats, cudaStream_t s);
+cudaError_t launch_gather(const void* idx, int64_t T, int64_t hw, const float* table, int K, int D,
+                          int layout_out, float* out, int64_t* stats, cudaStream_t s, int idx_bits = 64);
 
 // ---- vq_backward.cu --------------------------------------------------------------------------
 size_t backward_workspace_bytes(int64_t T, int K, int D);
@@ -141,9 +143,12 @@ cudaError_t launch_codebook_grad(const int64_t* seg_sums, const CodebookView& cb
                                  float* loss, cudaStream_t s);
 
 // ---- vq_tokens.cu ---------------------------------------------------------------------------
-cudaError_t launch_token_embed(const int64_t* tokens, const uint8_t* mask, int64_t T, int64_t n_per_seq, int64_t mask_token_id,
+cudaError_t launch_token_embed(const void* tokens, const uint8_t* mask, int64_t T, int64_t n_per_seq, int64_t mask_token_id,
                                int64_t ignore_index, const float* table, int64_t V, int dim, const float* pos, float* embeds,
-                               int64_t* input_ids, int64_t* labels, int64_t* stats, cudaStream_t s, const float* start = nullptr);
+                               int64_t* input_ids, int64_t* labels, int64_t* stats, cudaStream_t s, const float* start = nullptr,
+                               int token_bits = 64);
+// token indices between the wire formats (bits in {16, 32, 64}; values that do not fit the target are the caller's error)
+cudaError_t launch_tokens_convert(const void* in, int in_bits, void* out, int out_bits, int64_t T, cudaStream_t s);
 // grad_table[id] += grad_out[row]: integer-accumulated (deterministic) embedding backward; `normalised` != null applies the
 // backward of l2norm(E[k]) on top (grad_table is then the codebook gradient, V == K, dim == D)
 size_t embedding_backward_bytes(int64_t V, int dim);

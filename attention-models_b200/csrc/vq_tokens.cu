@@ -18,7 +18,7 @@
 
 namespace vq {
 
-__global__ void __launch_bounds__(256) k_token_embed(const int64_t* __restrict__ tokens, const uint8_t* __restrict__ mask,
+__global__ void __launch_bounds__(256) k_token_embed(const void* __restrict__ tokens, int token_bits, const uint8_t* __restrict__ mask,
                                                      int64_t T, int64_t n_per_seq, int64_t mask_token_id,
                                                      int64_t ignore_index, const float4* __restrict__ table, int64_t V,
                                                      int chunks, const float4* __restrict__ pos, float4* __restrict__ embeds,
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) k_token_embed(const int64_t* __restrict__
                 for (int c = lane; c < chunks; c += 32) __stcs(embeds + t * chunks + c, __ldg(start + c));
                 continue;
             }
-            const int64_t id = __ldg(tokens + t - 1);
+            const int64_t id = load_token(tokens, t - 1, token_bits);
             const bool ok = id >= 0 && id < V;
             if (!ok && lane == 0 && stats) atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_BAD_INDEX), 1ull);
             const float4* row = table + id * chunks;
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) k_token_embed(const int64_t* __restrict__
             }
             continue;
         }
-        const int64_t tok = __ldg(tokens + t);
+        const int64_t tok = load_token(tokens, t, token_bits);
         const bool masked = mask ? (__ldg(mask + t) != 0) : false;
         const int64_t id = masked ? mask_token_id : tok;
         if (lane == 0) {
@@ -74,17 +74,35 @@ __global__ void __launch_bounds__(256) k_token_embed(const int64_t* __restrict__
     }
 }
 
-cudaError_t launch_token_embed(const int64_t* tokens, const uint8_t* mask, int64_t T, int64_t n_per_seq, int64_t mask_token_id,
+cudaError_t launch_token_embed(const void* tokens, const uint8_t* mask, int64_t T, int64_t n_per_seq, int64_t mask_token_id,
                                int64_t ignore_index, const float* table, int64_t V, int dim, const float* pos, float* embeds,
-                               int64_t* input_ids, int64_t* labels, int64_t* stats, cudaStream_t s, const float* start) {
+                               int64_t* input_ids, int64_t* labels, int64_t* stats, cudaStream_t s, const float* start,
+                               int token_bits) {
     if (T == 0) return cudaSuccess;
     int64_t blocks = (T + 7) / 8;
     const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    k_token_embed<<<(unsigned)blocks, 256, 0, s>>>(tokens, mask, T, n_per_seq, mask_token_id, ignore_index,
+    k_token_embed<<<(unsigned)blocks, 256, 0, s>>>(tokens, token_bits, mask, T, n_per_seq, mask_token_id, ignore_index,
                                                    reinterpret_cast<const float4*>(table), V, dim / 4,
                                                    reinterpret_cast<const float4*>(pos), reinterpret_cast<float4*>(embeds),
                                                    input_ids, labels, stats, reinterpret_cast<const float4*>(start));
+    count_launch();
+    return cudaGetLastError();
+}
+
+// token indices between the wire formats
+__global__ void __launch_bounds__(256) k_tokens_convert(const void* __restrict__ in, int in_bits, void* __restrict__ out,
+                                                        int out_bits, int64_t T) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x)
+        store_token(out, t, (int)load_token(in, t, in_bits), out_bits);
+}
+
+cudaError_t launch_tokens_convert(const void* in, int in_bits, void* out, int out_bits, int64_t T, cudaStream_t s) {
+    if (T == 0) return cudaSuccess;
+    int64_t blocks = (T + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    k_tokens_convert<<<(unsigned)blocks, 256, 0, s>>>(in, in_bits, out, out_bits, T);
     count_launch();
     return cudaGetLastError();
 }

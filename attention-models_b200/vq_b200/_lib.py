@@ -14,10 +14,10 @@ LIB_PATH = os.environ.get("VQ_B200_LIB") or os.path.join(_PKG_DIR, "lib", "libvq
 BUILD_SCRIPT = os.path.join(_PKG_DIR, "csrc", "build.py")
 
 # constants mirrored from include/vq_b200.h
-ABI_VERSION = 4
+ABI_VERSION = 5
 FORM_VIT, FORM_VQGAN, FORM_VQGAN_L2 = 0, 1, 2
 LAYOUT_TOKEN_MAJOR, LAYOUT_NCHW = 0, 1
-FLAG_INDICES_ONLY, FLAG_EXACT_SCAN, FLAG_KEEP_STATS = 1, 2, 4
+FLAG_INDICES_ONLY, FLAG_EXACT_SCAN, FLAG_KEEP_STATS, FLAG_IDX32, FLAG_IDX16 = 1, 2, 4, 8, 16
 STAT_NEAR_TIE_ROWS, STAT_AMBIGUOUS_ROWS, STAT_FALLBACK_ROWS, STAT_LOSS_FIXED, STAT_BAD_INDEX, STAT_NONFINITE = range(6)
 STAT_PEER_TIMEOUT = 6
 PEER_MAX_RANKS, IPC_HANDLE_BYTES = 16, 64
@@ -64,6 +64,13 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "vq_gather": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                           c_void_p, c_void_p]),
+    "vq_gather_tokens": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                 c_void_p, c_void_p]),
+    "vq_tokens_convert": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p]),
+    "vq_token_embed_tokens": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vq_token_embed_causal_tokens": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p]),
     "vq_token_embed": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vq_token_embed_causal": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,

@@ -72,10 +72,11 @@ class _CodebookBase(nn.Module):
         self.last_histogram, self.last_stats = hist, stats
         return z_q, flat_idx, loss
 
-    def encode(self, z: torch.Tensor) -> torch.Tensor:
-        """Flat int64 indices only (what ``encode_imgs`` keeps; reference vitvqgan.py:204-210)."""
+    def encode(self, z: torch.Tensor, index_dtype: torch.dtype = torch.int64) -> torch.Tensor:
+        """Flat indices only (what ``encode_imgs`` keeps; reference vitvqgan.py:204-210): int64 like the reference, or
+        the narrow wire formats torch.int32 / torch.uint16 that ``indices_to_embeddings`` and the token consumers read."""
         return F_vq.encode_indices(z, self.embedding.weight, self.form, prepared=self._prepared_codebook(),
-                                   exact_scan=self.exact_scan)
+                                   exact_scan=self.exact_scan, index_dtype=index_dtype)
 
     def indices_to_embeddings(self, indices: torch.Tensor) -> torch.Tensor:
         prepared = self._prepared_codebook() if self.form == "vit" else None

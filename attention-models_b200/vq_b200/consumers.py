@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from .functional import _ptr, _require_cuda, _stream
+from .functional import _ptr, _require_cuda, _stream, as_tokens, token_bits
 
 
 class _TokenEmbed(torch.autograd.Function):
@@ -32,14 +32,15 @@ class _TokenEmbed(torch.autograd.Function):
         with torch.cuda.device(dev):
             if causal:
                 st = start.detach().reshape(dim).float().contiguous()
-                _lib.check(lib.vq_token_embed_causal(_ptr(tok), b * n, n, _ptr(w), V, dim, _ptr(p), _ptr(st), _ptr(embeds),
-                                                     _ptr(stats), _stream(dev)))
+                _lib.check(lib.vq_token_embed_causal_tokens(_ptr(tok), token_bits(tok.dtype), b * n, n, _ptr(w), V, dim, _ptr(p),
+                                                            _ptr(st), _ptr(embeds), _ptr(stats), _stream(dev)))
                 ids = labels = tok.new_empty(0)        # the labels of the causal form are the tokens themselves (the caller has them)
             else:
                 ids = torch.empty(b, n, dtype=torch.int64, device=dev)
                 labels = torch.empty(b, n, dtype=torch.int64, device=dev)
-                _lib.check(lib.vq_token_embed(_ptr(tok), _ptr(m), b * n, n, int(mask_token_id), int(ignore_index), _ptr(w), V, dim,
-                                              _ptr(p), _ptr(embeds), _ptr(ids), _ptr(labels), _ptr(stats), _stream(dev)))
+                _lib.check(lib.vq_token_embed_tokens(_ptr(tok), token_bits(tok.dtype), _ptr(m), b * n, n, int(mask_token_id),
+                                                     int(ignore_index), _ptr(w), V, dim, _ptr(p), _ptr(embeds), _ptr(ids),
+                                                     _ptr(labels), _ptr(stats), _stream(dev)))
         ctx.causal, ctx.shape = causal, (V, dim, b, n)
         ctx.pos_shape = None if pos is None else tuple(pos.shape)
         ctx.save_for_backward(tok if causal else ids)
@@ -49,8 +50,9 @@ class _TokenEmbed(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g, _g_ids, _g_labels):
-        from .functional import _embedding_backward
+        from .functional import _embedding_backward, convert_tokens
         (ids,) = ctx.saved_tensors
+        ids = convert_tokens(ids, torch.int64)
         V, dim, b, n = ctx.shape
         g = g.contiguous().float()
         g_table = g_pos = g_start = None
@@ -83,7 +85,7 @@ def masked_token_embeddings(tokens: torch.Tensor, mask: Optional[torch.Tensor], 
                             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """-> (embeds (b, n, dim) fp32, input_ids (b, n) int64, labels (b, n) int64).
 
-    ``tokens``: (b, n) integer; ``mask``: (b, n) bool or None; ``table``: (vocab, dim) fp32 embedding weight;
+    ``tokens``: (b, n) integer (int64, or the narrow wire formats int32 / uint16 of ``encode_indices``); ``mask``: (b, n) bool or None; ``table``: (vocab, dim) fp32 embedding weight;
     ``pos_enc``: (1, n, dim) or (n, dim) fp32 or None.  Differentiable with respect to ``table`` and ``pos_enc`` (a
     training step of MaskGIT / Muse).  Out-of-range ids raise IndexError like ``nn.Embedding`` on the CPU (one host
     sync; ``check_indices=False`` skips it)."""
@@ -91,7 +93,7 @@ def masked_token_embeddings(tokens: torch.Tensor, mask: Optional[torch.Tensor], 
     dev = tokens.device
     b, n = tokens.shape
     dim = table.shape[1]
-    tok = tokens.to(torch.int64).contiguous()
+    tok = as_tokens(tokens)
     m = None
     if mask is not None:
         if mask.shape != tokens.shape:
@@ -118,7 +120,7 @@ def causal_token_embeddings(tokens: torch.Tensor, table: torch.Tensor, pos_enc: 
     dev = tokens.device
     b, n = tokens.shape
     dim = table.shape[1]
-    tok = tokens.to(torch.int64).contiguous()
+    tok = as_tokens(tokens)
     pos = None
     if pos_enc is not None:
         pos = pos_enc.reshape(-1, dim)

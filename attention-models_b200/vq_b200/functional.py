@@ -199,11 +199,41 @@ def quantise(z: torch.Tensor, weight: torch.Tensor, form: str = "vit", beta: flo
                            sorted_segments, refresh)
 
 
+_TOKEN_BITS = {torch.int64: 64, torch.int32: 32, torch.uint16: 16}
+
+
+def token_bits(dtype: torch.dtype) -> int:
+    """Wire formats of token indices the library reads and writes: int64 (the reference's), int32, uint16."""
+    try:
+        return _TOKEN_BITS[dtype]
+    except KeyError:
+        raise TypeError(f"token dtype {dtype}: torch.int64, torch.int32 or torch.uint16") from None
+
+
+def as_tokens(t: torch.Tensor) -> torch.Tensor:
+    """A contiguous tensor in one of the wire formats (other integer dtypes are widened to int64)."""
+    return (t if t.dtype in _TOKEN_BITS else t.to(torch.int64)).contiguous()
+
+
+def convert_tokens(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Tokens in another wire format (vq_tokens_convert; values must fit the target)."""
+    t = as_tokens(t)
+    if t.dtype == dtype:
+        return t
+    out = torch.empty(t.shape, dtype=dtype, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.load().vq_tokens_convert(_ptr(t), token_bits(t.dtype), _ptr(out), token_bits(dtype), t.numel(),
+                                                 _stream(t.device)))
+    return out
+
+
 @torch.no_grad()
 def encode_indices(z: torch.Tensor, weight: torch.Tensor, form: str = "vit",
                    prepared: Optional[PreparedCodebook] = None, exact_scan: bool = False,
-                   want_hist: bool = False):
-    """``encode_imgs`` fast path: flat int64 indices only (z_q, loss and the saved state are skipped)."""
+                   want_hist: bool = False, index_dtype: torch.dtype = torch.int64):
+    """``encode_imgs`` fast path: flat indices only (z_q, loss and the saved state are skipped).  ``index_dtype``:
+    torch.int64 as the reference returns them, or the narrow wire formats torch.int32 / torch.uint16 (K <= 65536) that
+    ``indices_to_embeddings`` and the token consumers read directly."""
     _require_cuda(z, "z")
     if prepared is None or not prepared.matches(weight, form == "l2"):
         prepared = prepare_codebook(weight, form == "l2")
@@ -213,8 +243,9 @@ def encode_indices(z: torch.Tensor, weight: torch.Tensor, form: str = "vit",
     layout = LAYOUT_TOKEN_MAJOR if form == "vit" else LAYOUT_NCHW
     K, D = prepared.K, prepared.D
     T, hw = _token_geometry(z, layout, D)
-    flags = FLAG_INDICES_ONLY | (FLAG_EXACT_SCAN if exact_scan else 0)
-    idx = torch.empty(T, dtype=torch.int64, device=dev)
+    bits = token_bits(index_dtype)
+    flags = FLAG_INDICES_ONLY | (FLAG_EXACT_SCAN if exact_scan else 0) | {64: 0, 32: _lib.FLAG_IDX32, 16: _lib.FLAG_IDX16}[bits]
+    idx = torch.empty(T, dtype=index_dtype, device=dev)
     hist = torch.empty(K, dtype=torch.int32, device=dev) if want_hist else None
     ws_bytes = _lib.size_query("vq_workspace_bytes", T, K, D, flags)
     ws = _scratch(ws_bytes, dev)
@@ -254,16 +285,17 @@ class _Decode(torch.autograd.Function):
         K, D = weight.shape
         T = idx.numel()
         w = weight.detach().contiguous()
+        bits = token_bits(idx.dtype)
         if form == "vit":
             out = torch.empty(*idx.shape, D, dtype=torch.float32, device=dev)
-            args = (_ptr(idx), T, 0, None, _ptr(prepared.blob), K, D, 1, LAYOUT_TOKEN_MAJOR)
+            args = (_ptr(idx), bits, T, 0, None, _ptr(prepared.blob), K, D, 1, LAYOUT_TOKEN_MAJOR)
         else:
             b, n = idx.shape
             side = int(n ** 0.5)
             out = torch.empty(b, D, side, side, dtype=torch.float32, device=dev)
-            args = (_ptr(idx), T, n, _ptr(w), None, K, D, 0, LAYOUT_NCHW)
+            args = (_ptr(idx), bits, T, n, _ptr(w), None, K, D, 0, LAYOUT_NCHW)
         with torch.cuda.device(dev):
-            _lib.check(lib.vq_gather(*args, _ptr(out), _ptr(stats), _stream(dev)))
+            _lib.check(lib.vq_gather_tokens(*args, _ptr(out), _ptr(stats), _stream(dev)))
         ctx.form, ctx.prepared, ctx.shape = form, prepared, (K, D)
         ctx.save_for_backward(idx)
         return out
@@ -272,6 +304,7 @@ class _Decode(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g):
         (idx,) = ctx.saved_tensors
+        idx = convert_tokens(idx, torch.int64)
         K, D = ctx.shape
         if ctx.form == "vit":
             gw = _embedding_backward(idx, g, K, D, prepared=ctx.prepared)
@@ -284,14 +317,14 @@ def indices_to_embeddings(indices: torch.Tensor, weight: torch.Tensor, form: str
                           prepared: Optional[PreparedCodebook] = None, check_indices: bool = True) -> torch.Tensor:
     """Decode gather (reference vitvqgan.py:173-176: l2norm(E[i]); vqgan.py:178-182: E[i] as (b, D, h, w)).
 
-    ``indices``: (b, n) integer tensor.  Out-of-range indices raise IndexError like the reference's CPU
+    ``indices``: (b, n) integer tensor (int64, or the narrow wire formats int32 / uint16).  Out-of-range indices raise IndexError like the reference's CPU
     path (one host sync for the check; pass ``check_indices=False`` to skip it).  Differentiable with respect to
     ``weight`` (as the reference's ``nn.Embedding`` lookup is) when gradients are enabled and it requires them.
     """
     _require_cuda(indices, "indices")
     _require_cuda(weight, "the codebook weight")
     dev = indices.device
-    idx = indices.to(torch.int64).contiguous()
+    idx = as_tokens(indices)
     if form == "vit":
         if prepared is None or not prepared.matches(weight):
             prepared = prepare_codebook(weight)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 4
+#define VQ_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define VQ_API __attribute__((visibility("default")))
@@ -58,6 +58,10 @@ extern "C" {
 #define VQ_FLAG_EXACT_SCAN   2    /* force the exhaustive fp32 SIMT search (no tensor cores)   */
 #define VQ_FLAG_KEEP_STATS   4    /* hist, stats and seg_sums accumulate (the caller zeroed them once):
                                      one batch can be streamed through in token chunks           */
+#define VQ_FLAG_IDX32        8    /* with VQ_FLAG_INDICES_ONLY: `idx` is T int32 ...                            */
+#define VQ_FLAG_IDX16        16   /* ... or T uint16 (codebook_size <= 65536): the token wire format for the
+                                     consumers below (vq_gather_tokens, vq_token_embed_tokens), 2 or 4 instead
+                                     of 8 bytes per token on every copy behind encode_imgs                       */
 
 /* error codes */
 #define VQ_OK            0
@@ -126,7 +130,7 @@ VQ_API int vq_codebook_prepare_raw(const float* weight, int K, int D, void* cb, 
 VQ_API int vq_workspace_bytes(int64_t T, int K, int D, int flags, size_t* out);
 VQ_API int vq_forward(const float* z, int layout, int64_t T, int64_t hw,
                const float* weight, void* cb, int K, int D, int form, float beta, int flags, int64_t n_elem_total,
-               float* z_q, int64_t* idx, float* loss, int32_t* hist, int64_t* stats,
+               float* z_q, void* idx, float* loss, int32_t* hist, int64_t* stats,
                float* saved_zn, float* saved_denom, int64_t* seg_sums,
                void* ws, size_t ws_bytes, void* stream);
 
@@ -230,6 +234,11 @@ VQ_API int vq_backward_sharded(const void* const* peer_bufs, int world, int rank
  * stats[VQ_STAT_BAD_INDEX] (the Python side raises IndexError like the reference) and produce 0. */
 VQ_API int vq_gather(const int64_t* idx, int64_t T, int64_t hw, const float* weight, const void* cb,
               int K, int D, int normalise, int layout_out, float* out, int64_t* stats, void* stream);
+/* ... from tokens in a narrow wire format: token_bits = 16 (uint16), 32 (int32) or 64 (int64) */
+VQ_API int vq_gather_tokens(const void* tokens, int token_bits, int64_t T, int64_t hw, const float* weight, const void* cb,
+              int K, int D, int normalise, int layout_out, float* out, int64_t* stats, void* stream);
+/* tokens between the wire formats (uint16 / int32 / int64); values that do not fit the target are the caller's error */
+VQ_API int vq_tokens_convert(const void* in, int in_bits, void* out, int out_bits, int64_t T, void* stream);
 
 /* ---- first consumer of the tokens ------------------------------------------
  * The mask-fill + token-embedding lookup the generative models do right behind encode_imgs, in one pass:
@@ -243,6 +252,10 @@ VQ_API int vq_token_embed(const int64_t* tokens, const uint8_t* mask, int64_t T,
                           int64_t mask_token_id, int64_t ignore_index, const float* table, int64_t vocab, int dim,
                           const float* pos, float* embeds, int64_t* input_ids, int64_t* labels, int64_t* stats,
                           void* stream);
+VQ_API int vq_token_embed_tokens(const void* tokens, int token_bits, const uint8_t* mask, int64_t T, int64_t n_per_seq,
+                          int64_t mask_token_id, int64_t ignore_index, const float* table, int64_t vocab, int dim,
+                          const float* pos, float* embeds, int64_t* input_ids, int64_t* labels, int64_t* stats,
+                          void* stream);   /* tokens: uint16 / int32 / int64 by token_bits; input_ids, labels stay int64 */
 
 /* The autoregressive consumer (Parti, models/parti.py:98-106): the decoder input of a (b, n) token batch is
  *   embeds[b, 0] = start_token ;  embeds[b, i] = table[tokens[b, i - 1]] + pos[i - 1]   (i = 1 .. n - 1)
@@ -250,6 +263,9 @@ VQ_API int vq_token_embed(const int64_t* tokens, const uint8_t* mask, int64_t T,
  * caller's) and `cat(start_token, ...)` in one pass; the labels are the tokens themselves.  T = b * n_per_seq.      */
 VQ_API int vq_token_embed_causal(const int64_t* tokens, int64_t T, int64_t n_per_seq, const float* table, int64_t vocab,
                                  int dim, const float* pos, const float* start, float* embeds, int64_t* stats, void* stream);
+VQ_API int vq_token_embed_causal_tokens(const void* tokens, int token_bits, int64_t T, int64_t n_per_seq, const float* table,
+                                 int64_t vocab, int dim, const float* pos, const float* start, float* embeds, int64_t* stats,
+                                 void* stream);
 
 /* Backward of an embedding lookup, deterministic: grad_table[ids[j]] += grad_out[row(j)], accumulated as 64-bit
  * integers at a per-call fixed-point scale derived from max |grad_out| (exact, order-free sums), converted once.

@@ -131,3 +131,67 @@ def test_decode_gradient_matches_reference_fixture(dev, name):
     assert _rel(m.embedding.weight.grad.cpu().numpy(), g["grad_weight"]) < 1e-5
     with torch.no_grad():
         assert not m.indices_to_embeddings(torch.from_numpy(g["indices"]).to(dev)).requires_grad
+
+
+@pytest.mark.parametrize("index_dtype", [torch.int32, torch.uint16])
+@pytest.mark.parametrize("form", ["vit", "vqgan"])
+def test_narrow_token_wire_format_end_to_end(dev, form, index_dtype):
+    """encode -> tokens as int32 / uint16 (VQ_FLAG_IDX32 / IDX16) -> decode, masked and causal consumers reading them
+    directly: everything equal to the int64 path (the reference's dtype), including the gradients behind the consumers.
+    Codes up to 65535 must survive the uint16 format; the format is refused where it cannot hold the codes."""
+    from vq_b200 import functional as F_vq
+    from vq_b200.consumers import causal_token_embeddings, masked_token_embeddings
+    g = torch.Generator().manual_seed(11)
+    if form == "vit":
+        K, D, shape = 65536, 32, (4, 256, 32)
+    else:
+        K, D, shape = 1024, 64, (4, 64, 16, 16)
+    w = vo.make_codebook(form, K, D, 3).to(dev)
+    z = vo.make_latents(shape, 4).to(dev)
+    if form == "vit":
+        z[0, :8] = w[K - 8:] * 1.5           # rows that land on the highest codes: 65528 .. 65535
+    idx64 = F_vq.encode_indices(z, w, form)
+    idx = F_vq.encode_indices(z, w, form, index_dtype=index_dtype)
+    assert idx.dtype == index_dtype and idx64.dtype == torch.int64
+    assert torch.equal(F_vq.convert_tokens(idx, torch.int64), idx64)
+    assert torch.equal(F_vq.convert_tokens(idx64, index_dtype).view(torch.uint8), idx.view(torch.uint8))
+    if form == "vit":
+        assert int(idx64[:8].min()) >= K - 8
+    b = shape[0]
+    tok64, tok = idx64.view(b, -1), idx.view(b, -1)
+    # decode
+    wg = w.clone().requires_grad_(True)
+    d64 = F_vq.indices_to_embeddings(tok64, wg, form)
+    up = torch.randn(d64.shape, generator=g).to(dev)
+    (d64 * up).sum().backward()
+    g64 = wg.grad.clone()
+    wg.grad = None
+    dn = F_vq.indices_to_embeddings(tok, wg, form)
+    (dn * up).sum().backward()
+    assert torch.equal(dn, d64) and torch.equal(wg.grad, g64)
+    # consumers
+    n = tok.shape[1]
+    table = torch.randn(K + 1, 64, generator=g).to(dev).requires_grad_(True)
+    pos = (0.02 * torch.randn(n, 64, generator=g)).to(dev)
+    mask = (torch.rand(b, n, generator=g) < 0.5).to(dev)
+    outs = []
+    for t in (tok64, tok):
+        table.grad = None
+        e, ids, labels = masked_token_embeddings(t, mask, K, table, pos, -100)
+        e.square().sum().backward()
+        outs.append((e.detach(), ids, labels, table.grad.clone()))
+    for a, c in zip(*outs):
+        assert torch.equal(a, c)
+    assert outs[1][1].dtype == torch.int64 and outs[1][2].dtype == torch.int64       # what cross_entropy wants
+    start = torch.randn(64, generator=g).to(dev)
+    e64, _ = causal_token_embeddings(tok64, table.detach(), pos, start)
+    en, lab = causal_token_embeddings(tok, table.detach(), pos, start)
+    assert torch.equal(en, e64) and lab.dtype == index_dtype
+    # a format that cannot hold the codes is refused; narrow indices only without z_q / backward state
+    if index_dtype == torch.uint16:
+        from vq_b200._lib import VQLibraryError
+        big = vo.make_codebook("vit", 65536 + 512, 32, 5).to(dev)
+        with pytest.raises(VQLibraryError, match="IDX16"):
+            F_vq.encode_indices(vo.make_latents((1, 256, 32), 6).to(dev), big, "vit", index_dtype=torch.uint16)
+    with pytest.raises(TypeError):
+        F_vq.encode_indices(z, w, form, index_dtype=torch.int16)
