@@ -754,6 +754,7 @@ static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, int D, u
 
 // vq_dist_tc16.cu: D = 32 with fp16 accumulators and packed 16-bit maxima
 bool tc16_supported(int64_t T, int K, int D);
+int tc16_max_clusters();
 cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T, const __half* zn16, const float* zn32,
                              const float* row_sq, const CodebookView& cb, int* cand, int* flagged, int* n_flagged, int64_t* stats,
                              void* records, cudaStream_t s);
@@ -915,8 +916,11 @@ cudaError_t launch_dist_tc(const __half* zn16, const float* zn32, const float* r
     if (T == 0) return cudaSuccess;
     CUtensorMap ma, mb;
     if (tc16_supported(T, cb.K, cb.D)) {
-        // one 256-row box per row tile, one 128-code box per n-tile
-        if (!tc::make_map(&ma, zn16, (uint64_t)T, cb.D, 256) || !tc::make_map(&mb, cb.en16, (uint64_t)cb.K, cb.D, 128))
+        // one 256-row box per row tile, one 128-code box per n-tile; clusters of two CTAs: 128 rows, and each CTA fetches
+        // (and multicasts) one 64-code half of every n-tile
+        const bool cl = tc16_max_clusters() > 0;
+        if (!tc::make_map(&ma, zn16, (uint64_t)T, cb.D, cl ? 128 : 256) ||
+            !tc::make_map(&mb, cb.en16, (uint64_t)cb.K, cb.D, cl ? 64 : 128))
             return cudaErrorInvalidValue;
         return launch_dist_tc16(ma, mb, (int)T, zn16, zn32, row_sq, cb, cand, flagged, n_flagged, stats, tc_ws, s);
     }

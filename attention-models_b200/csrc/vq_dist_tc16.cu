@@ -93,16 +93,23 @@ constexpr int kRecCells = 8;
 constexpr int kAreas = 4;
 
 struct SmemLayout {
-    uint32_t a, b, snap, bars, tmem_slot, total;
+    uint32_t a, b, snap, bars, tmem_slot, xch, total;
 };
-__host__ __device__ inline SmemLayout smem_layout() {
+constexpr int kSnapRowH = 128;                      // halves = 1: unpadded snapshot rows, 16-byte chunks swizzled by the row
+constexpr int kXchBytes = 128 * (2 * 4 + 2 * 4 + 8);  // per row: two best scores, two "decided" flags, one record half
+// halves = 2: a CTA owns 256 rows (two MMA row halves).  halves = 1: 128 rows, CTAs run in clusters of two that share the
+// codebook stream (see k_dist_tc16); the ring then has 8 stages: with four issuers taking the tiles in turn a stage must
+// always come back to the same issuer (a parity wait by a thread that skipped a phase returns early).
+__host__ __device__ constexpr int b_stages16(int halves) { return halves == 1 ? 8 : kBStages; }
+__host__ __device__ inline SmemLayout smem_layout(int halves = 2) {
     SmemLayout L;
     L.a = 0;
-    L.b = L.a + kAStages * kABytes;
-    L.snap = L.b + kBStages * kBStageBytes;
-    L.bars = L.snap + kAreas * kSnapArea;
+    L.b = L.a + kAStages * (kABytes / 2 * halves);
+    L.snap = L.b + b_stages16(halves) * kBStageBytes;
+    L.bars = L.snap + (halves == 1 ? kAreas * 256 * kSnapRowH : kAreas * kSnapArea);
     L.tmem_slot = L.bars + 8 * 32;
-    L.total = L.tmem_slot + 16;
+    L.xch = L.tmem_slot + 16;
+    L.total = L.xch + (halves == 1 ? kXchBytes : 0);
     return L;
 }
 
@@ -125,6 +132,9 @@ __device__ __forceinline__ void tmem_ld_tile(uint32_t taddr, uint32_t (&v)[64]) 
         : "r"(taddr));
 }
 
+__device__ __forceinline__ void pair_barrier(int id) {      // the two warps that own the same 32 rows (64 threads)
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
 __device__ __forceinline__ int lo16(uint32_t p) { return (int)(p << 16) >> 16; }
 __device__ __forceinline__ int hi16(uint32_t p) { return (int)p >> 16; }
 
@@ -145,13 +155,36 @@ __device__ __forceinline__ void best3_merge(Best3& a, float d1, int i1, float d2
 }
 
 // kServiceHigh: the TMA / MMA / TMEM warps take the highest warp ids (the issue arbiter favours high ids).
-template <bool kServiceHigh>
+//
+// HALVES = 1 (VQ_TC16_CLUSTER=1; MEASURED SLOWER, kept as the measured alternative): a CTA owns ONE 128-row half and all
+// four accumulator stages belong to it; CTAs run in clusters of two that share the codebook stream (each fetches one
+// 64-code half of every tile and TMA-multicasts it into both; a stage is released by both CTAs' issuers through a
+// multicast tcgen05.commit).  The idea: with 256 rows per CTA a row half has only two accumulator stages, and the hand-off
+// chain of a stage (MMAs retire -> mbarrier -> the epilogue warp wakes -> tcgen05.ld of the tile -> release -> the issuer
+// wakes) is ~570 cycles for ~128 cycles of tensor work; four stages per half let the MMAs run up to four tiles ahead of
+// the drain.  Issuer q owns stage q and the tiles n = q mod 4; eight epilogue warps drain them, two per TMEM lane
+// quarter taking alternate tiles (see the epilogue).  Correct on the first run both times, and: 176.9 us with four
+// epilogue warps (issuers waiting for free stages 83 % of the time: one warp per scheduler cannot drain a tile in less
+// than ~400 cycles), 173.9 us with eight (two threads per row) against 124.1 us for the 256-row kernel on the same box.
+// What the instrumented build shows: an epilogue warp is busy ~620 cycles per tile it drains (510 in the 256-row
+// kernel; here every thread also runs the per-group bookkeeping for its half of the tiles), two such warps per
+// scheduler, so the drain - not the accumulator ring - paces the kernel at D = 32, where a tile is only two MMAs; and
+// the MMAs themselves cannot go below ~77-84 cycles each per SM (tools/ubench_mma.cu; the D = 256 kernel, which has 16
+// MMAs per tile to hide its drain behind, sits at 77), i.e. ~75 us for this shape.  Getting past both needs
+// cta_group::2 MMAs (one instruction per CTA pair: half the issue cost per SM) and a cheaper drain, not more stages.
+template <bool kServiceHigh, int HALVES>
 __global__ void __launch_bounds__(kThreads, 1)
 k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int T, int K,
             const int* __restrict__ cb_info, int4* __restrict__ rec, int* __restrict__ cand,
             int* __restrict__ flagged, int* __restrict__ n_flagged, int64_t* __restrict__ stats) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const SmemLayout L = smem_layout();
+    static_assert(HALVES == 2 || kIssuers == 4, "the one-half form has one issuer per accumulator stage");
+    constexpr int CL = HALVES == 1 ? 2 : 1;                   // CTAs per cluster (launch attribute)
+    constexpr int kRows = 128 * HALVES;                       // token rows of a CTA
+    constexpr int kABytesH = kRows * kD * 2;
+    constexpr int kBS = b_stages16(HALVES);
+    constexpr uint32_t kSnapAreaH = kRows * kSnapRow;
+    const SmemLayout L = smem_layout(HALVES);
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
     uint8_t* smem = smem_raw + pad;
     const uint32_t smem_base = smem_u32(smem);
@@ -171,12 +204,17 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     constexpr int kEpiWarp0 = kServiceHigh ? 0 : 4;
     constexpr int kTmaWarp = kServiceHigh ? 8 : 0, kMmaWarp = kTmaWarp + 1;
     constexpr int kAllocWarp = kIssuers == 2 ? kTmaWarp + 2 : kTmaWarp + 5;     // (2 issuers: warps kMmaWarp and kMmaWarp + 2)
-    const int n_row_tiles = (T + kRowsPerCta - 1) / kRowsPerCta;
+    // a work unit is the rows of one cluster step: CL consecutive row tiles, one per CTA (a tile past the end reads zeros
+    // and writes nothing)
+    const uint32_t cta_rank = CL == 2 ? cluster_cta_rank() : 0u;
+    const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
+    const int n_units = ((T + kRows - 1) / kRows + CL - 1) / CL;
     const int n_tiles = K / kTileN;
     const int n_groups = n_tiles / kGroupTiles;
 
     if (warp == kMmaWarp && lane == 0) {
-        for (int s = 0; s < kBStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 2); }   // both MMA warps commit
+        // a stage is read by both row halves' issuers, or by its issuer in either CTA of the cluster
+        for (int s = 0; s < kBS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 2); }
         for (int q = 0; q < 4; ++q) { mbar_init(t_full(q), 1); mbar_init(t_empty(q), 4); }     // one arrive per epilogue warp of the half
         for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), kIssuers); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -189,6 +227,7 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL == 2) cluster_sync_all();      // the peer's barriers are initialised before anything is sent to them
     tc_fence_after();
     // barrier init and the TMEM allocation above overlap the tail of the token prep kernel (programmatic dependent
     // launch); nothing before this line reads what that kernel writes
@@ -204,20 +243,25 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
             uint32_t b_cnt = 0;
             int it = 0;
             VQ_INSTR_BEGIN();
-            for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
+            for (int u = unit0; u < n_units; u += unit_step, ++it) {
+                const int rt = u * CL + (int)cta_rank;
                 const int as = it & 1;
                 VQ_TIMED_WAIT(0, a_empty(as), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
                 if (elect_one()) {
-                    mbar_expect_tx(a_full(as), kABytes);
-                    tma_load_2d(smem_base + L.a + as * kABytes, &tm_a, a_full(as), 0, rt * kRowsPerCta);
+                    mbar_expect_tx(a_full(as), kABytesH);
+                    tma_load_2d(smem_base + L.a + as * kABytesH, &tm_a, a_full(as), 0, rt * kRows);
                 }
                 __syncwarp();
                 for (int n = 0; n < n_tiles; ++n, ++b_cnt) {
-                    const int s = b_cnt % kBStages;
-                    VQ_TIMED_WAIT(1, b_empty(s), ((b_cnt / kBStages) & 1u) ^ 1u);
+                    const int s = b_cnt % kBS;
+                    VQ_TIMED_WAIT(1, b_empty(s), ((b_cnt / kBS) & 1u) ^ 1u);
                     if (elect_one()) {
                         mbar_expect_tx(b_full(s), kBStageBytes);
-                        tma_load_2d(smem_base + L.b + s * kBStageBytes, &tm_b, b_full(s), 0, n * kTileN);
+                        if constexpr (CL == 2)      // this CTA's 64-code half of the tile (tm_b boxes are 64 codes), into both CTAs
+                            tma_load_2d_multicast(smem_base + L.b + s * kBStageBytes + cta_rank * (kBStageBytes / 2), &tm_b, b_full(s),
+                                                  0, n * kTileN + (int)cta_rank * (kTileN / 2), (uint16_t)3);
+                        else
+                            tma_load_2d(smem_base + L.b + s * kBStageBytes, &tm_b, b_full(s), 0, n * kTileN);
                     }
                     __syncwarp();
                 }
@@ -227,26 +271,26 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
             // ===================== MMA issuers (whole warp loops, one elected lane issues) ==========
             // r: row half; with 4 issuers also p0: the n-tile parity (= accumulator stage 2 p0 + r) this warp serves
             const int iw = warp - kMmaWarp;
-            const int r = kIssuers == 2 ? (iw >> 1) : (iw & 1);
-            const int p0 = kIssuers == 2 ? 0 : (iw >> 1);
-            constexpr int kStep = kIssuers == 2 ? 1 : 2;               // n-tiles between two tiles of this issuer
+            const int r = HALVES == 1 ? 0 : (kIssuers == 2 ? (iw >> 1) : (iw & 1));
+            const int p0 = HALVES == 1 ? iw : (kIssuers == 2 ? 0 : (iw >> 1));
+            constexpr int kStep = HALVES == 1 ? 4 : (kIssuers == 2 ? 1 : 2);   // n-tiles between two tiles of this issuer
             const uint32_t tmem_base = *tmem_slot;
             uint32_t t_cnt = 0;                                        // tiles issued by this warp
             int it = 0;
             VQ_INSTR_BEGIN();
-            for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
+            for (int u = unit0; u < n_units; u += unit_step, ++it) {
                 const int as = it & 1;
                 VQ_TIMED_WAIT(0, a_full(as), ((uint32_t)(it >> 1)) & 1u);
                 tc_fence_after();
-                const uint32_t a_addr = smem_base + L.a + as * kABytes + r * (128 * 64);
+                const uint32_t a_addr = smem_base + L.a + as * kABytesH + r * (128 * 64);
                 for (int n = p0; n < n_tiles; n += kStep, ++t_cnt) {
-                    const int p = n & 1;                               // accumulator stage 2p + r
+                    const int q = HALVES == 1 ? iw : 2 * (n & 1) + r;    // accumulator stage: own, or 2 (tile parity) + row half
                     const uint32_t b_cnt = (uint32_t)it * (uint32_t)n_tiles + (uint32_t)n;
-                    const int s = b_cnt % kBStages;
-                    VQ_TIMED_WAIT(2, b_full(s), (b_cnt / kBStages) & 1u);
-                    // uses of stage 2p + r so far: every tile of this half with parity p
-                    const uint32_t use = kIssuers == 2 ? (t_cnt >> 1) : t_cnt;
-                    VQ_TIMED_WAIT(1, t_empty(2 * p + r), (use & 1u) ^ 1u);
+                    const int s = b_cnt % kBS;
+                    VQ_TIMED_WAIT(2, b_full(s), (b_cnt / kBS) & 1u);
+                    // uses of the stage so far: every tile this warp issued into it
+                    const uint32_t use = (HALVES == 2 && kIssuers == 2) ? (t_cnt >> 1) : t_cnt;
+                    VQ_TIMED_WAIT(1, t_empty(q), (use & 1u) ^ 1u);
                     tc_fence_after();
                     if (iw == 0 && lane == 0) VQ_TRACE(0, (int)t_cnt, 0);
                     const uint32_t b_addr = smem_base + L.b + s * kBStageBytes;
@@ -254,10 +298,11 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < 2; ++k)
-                            umma_f16(tmem_base + (uint32_t)((p * 2 + r) * kTileN), umma_desc(a_addr + k * 32),
+                            umma_f16(tmem_base + (uint32_t)(q * kTileN), umma_desc(a_addr + k * 32),
                                      umma_desc(b_addr + k * 32), kIdesc, (uint32_t)k);
-                        umma_commit(t_full(2 * p + r));
-                        umma_commit(b_empty(s));
+                        umma_commit(t_full(q));
+                        if constexpr (CL == 2) umma_commit_multicast(b_empty(s), (uint16_t)3);
+                        else umma_commit(b_empty(s));
                     }
                     __syncwarp();
                     if (iw == 0 && lane == 0) VQ_TRACE(0, (int)t_cnt, 1);
@@ -270,21 +315,220 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
             (void)r_report;
             if (iw == 0) { VQ_INSTR_END(3, 4); }
         }
-    } else {
-        // ===================== epilogue: 8 warps, one thread per row =====================
+    } else if (HALVES == 1) {
+        // ===================== epilogue, one row half: TWO threads per row =====================
+        // An epilogue warp's per-tile chain (wait for the tile, tcgen05.ld of 64 registers, release, fold) takes ~400
+        // cycles however idle its scheduler is (measured: four warps draining every tile of their rows made the kernel
+        // 177 us, the issuers waiting for free stages 83 % of the time), so the drain needs two warps per scheduler, as
+        // the 256-row kernel has.  Warp (quarter, par) drains the tiles n = par mod 2 of its 32 rows: of a 512-code group
+        // it sees tiles par and par + 2, and its 32 packed slot registers hold the maxima of 64 sub-cells of 4 codes -
+        // sub-cell (j, half) of thread par and of thread par ^ 1 together are cell (j, half) of the usual layout (2
+        // columns x 4 tiles), so the verdict records and everything behind them are unchanged.  Each thread ranks the
+        // groups by its own sub-cell maxima and snapshots its own best four; the row's two threads meet once per row
+        // tile: the row's best score is the larger of theirs, each marks its sub-cells within 2 eps of it, the row is
+        // decided iff both could (fifth-best own group below the threshold, at most four cells each), and each writes one
+        // half of the record (thread 1 drops the cell ids thread 0 already lists).
         reg_inc<kRegsEpilogue>();
         const int e = warp - kEpiWarp0;
-        const int r_sub = e >> 2;                    // which 128-row MMA tile
+        const int par = e >> 2;
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may read (warp id mod 4)
+        const int row_in_cta = quarter * 32 + lane;
+        const int pair_id = 1 + quarter;
+        const uint32_t tbase = *tmem_slot + ((uint32_t)(quarter * 32) << 16);
+        constexpr uint32_t kAreaStride = 256 * kSnapRowH;
+        const uint32_t snap0 = smem_base + L.snap + (uint32_t)(par * 128 + row_in_cta) * kSnapRowH;
+        const uint32_t swz = (uint32_t)(lane & 7);
+        volatile int* xch = reinterpret_cast<volatile int*>(smem + L.xch);
+        volatile unsigned long long* xrec = reinterpret_cast<volatile unsigned long long*>(smem + L.xch + 128 * 16);
+        const bool force_exhaustive = codebook_degenerate(cb_info);
+        uint32_t own = 0;                            // own tiles drained so far: tile 2 own + par, stage 2 (own & 1) + par
+        auto stage_of = [&](uint32_t o) { return (int)(2u * (o & 1u)) + par; };
+        auto phase_of = [&](uint32_t o) { return (o >> 1) & 1u; };
+        int it = 0;
+        uint32_t bufA[64], bufB[64];
+        VQ_INSTR_BEGIN();
+        for (int u = unit0; u < n_units; u += unit_step, ++it) {
+            const int rt = u * CL + (int)cta_rank;
+            uint32_t slot[32];
+            int m1 = -32768, m2 = -32768, m3 = -32768, m4 = -32768, m5 = -32768;
+            int g1 = 0, g2 = 0, g3 = 0, g4 = 0;
+            uint32_t a1 = 0, a2 = 1, a3 = 2, a4 = 3;  // snapshot areas of this thread's best four groups
+            auto group_end = [&](const int g) {
+                uint32_t t[11];
+#pragma unroll
+                for (int j = 0; j < 10; ++j) t[j] = __vimax3_s16x2(slot[3 * j], slot[3 * j + 1], slot[3 * j + 2]);
+                t[10] = __vmaxs2(slot[30], slot[31]);
+                const uint32_t u0 = __vimax3_s16x2(t[0], t[1], t[2]), u1 = __vimax3_s16x2(t[3], t[4], t[5]),
+                               u2 = __vimax3_s16x2(t[6], t[7], t[8]);
+                const uint32_t pk = __vimax3_s16x2(__vimax3_s16x2(u0, u1, u2), t[9], t[10]);
+                const int c1 = max(lo16(pk), hi16(pk));
+                const bool is1 = c1 > m1, is2 = c1 > m2, is3 = c1 > m3, is4 = c1 > m4;
+                if (is4) {
+                    const uint32_t dst = snap0 + a4 * kAreaStride;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16 * ((uint32_t)q ^ swz)), "r"(slot[4 * q]),
+                                     "r"(slot[4 * q + 1]), "r"(slot[4 * q + 2]), "r"(slot[4 * q + 3])
+                                     : "memory");
+                }
+                const int lo1 = min(c1, m1);
+                m1 = max(c1, m1);
+                const int lo2 = min(lo1, m2);
+                m2 = max(lo1, m2);
+                const int lo3 = min(lo2, m3);
+                m3 = max(lo2, m3);
+                const int lo4 = min(lo3, m4);
+                m4 = max(lo3, m4);
+                m5 = max(lo4, m5);
+                const int ng4 = is3 ? g3 : (is4 ? g : g4);
+                const uint32_t na4 = is3 ? a3 : a4;
+                const int ng3 = is2 ? g2 : (is3 ? g : g3);
+                const uint32_t na3 = is2 ? a2 : (is3 ? a4 : a3);
+                const int ng2 = is1 ? g1 : (is2 ? g : g2);
+                const uint32_t na2 = is1 ? a1 : (is2 ? a4 : a2);
+                const uint32_t na1 = is1 ? a4 : a1;
+                g1 = is1 ? g : g1; g2 = ng2; g3 = ng3; g4 = ng4;
+                a1 = na1; a2 = na2; a3 = na3; a4 = na4;
+            };
+            VQ_TIMED_WAIT(0, t_full(stage_of(own)), phase_of(own));
+            tc_fence_after();
+            tmem_ld_tile(tbase + (uint32_t)(stage_of(own) * kTileN), bufA);
+            for (int g = 0; g < n_groups; ++g) {
+#pragma unroll
+                for (int bb = 0; bb < 2; ++bb) {
+                    uint32_t (&cur)[64] = bb ? bufB : bufA;
+                    uint32_t (&nxt)[64] = bb ? bufA : bufB;
+                    VQ_TIMED_BEGIN();
+                    tmem_ld_wait();                                   // the tile is in registers: its TMEM stage is free
+                    VQ_TIMED_END(2);
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(t_empty(stage_of(own)));
+                    ++own;
+                    if (bb == 0 || g + 1 < n_groups) {
+                        VQ_TIMED_WAIT(0, t_full(stage_of(own)), phase_of(own));
+                        tc_fence_after();
+                        tmem_ld_tile(tbase + (uint32_t)(stage_of(own) * kTileN), nxt);
+                    }
+                    if (bb == 0) {
+                        if (g > 0) group_end(g - 1);                  // behind the hand-off of this tile's stage
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) slot[j] = __vmaxs2(cur[j], cur[j + 32]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) slot[j] = __vimax3_s16x2(slot[j], cur[j], cur[j + 32]);
+                    }
+                }
+            }
+            group_end(n_groups - 1);
+            // ---- row verdict, taken by the row's two threads ----
+            xch[row_in_cta * 2 + par] = m1;
+            pair_barrier(pair_id);
+            const int m1_row = max(m1, xch[row_in_cta * 2 + (par ^ 1)]);
+            const float m1f = __half2float(__ushort_as_half((unsigned short)(m1_row & 0xFFFF)));
+            const float thr_f = m1f - (m1f < 0.9f ? kTwoEps : kTwoEpsNearOne);
+            const bool thr_ok = (m1_row >= 0) && (m1_row < 0x7C00) && (thr_f >= kMinThreshold);
+            const int thr = thr_ok ? (int)__half_as_ushort(__float2half_rd(thr_f)) : 0x7BFF;
+            const uint32_t thr2 = (uint32_t)thr * 0x10001u;
+            uint32_t mask[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            const int mv[4] = {m1, m2, m3, m4};
+            const uint32_t av[4] = {a1, a2, a3, a4};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                if (mv[a] >= thr) {
+                    const uint32_t src = snap0 + av[a] * kAreaStride;
+                    uint32_t kept[32];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(kept[4 * q]), "=r"(kept[4 * q + 1]), "=r"(kept[4 * q + 2]), "=r"(kept[4 * q + 3])
+                                     : "r"(src + 16 * ((uint32_t)q ^ swz)));
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        bool ph, pl;
+                        (void)__vibmax_s16x2(kept[j], thr2, &ph, &pl);      // per half: kept >= thr
+                        const uint32_t bits = (pl ? (1u << ((2 * j) & 31)) : 0u) | (ph ? (1u << ((2 * j + 1) & 31)) : 0u);
+                        mask[2 * a + (j >> 4)] |= bits;
+                    }
+                }
+            }
+            const int n_cand = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]) + __popc(mask[4]) + __popc(mask[5]) +
+                               __popc(mask[6]) + __popc(mask[7]);
+            const bool mine_ok = thr_ok && (m5 < thr) && (n_cand <= kRecCells / 2) && !force_exhaustive;
+            // this thread's half of the record: its surviving cells as 16-bit ids (group * 64 + slot), 0xFFFF = none
+            unsigned long long half_rec = ~0ull;
+            if (mine_ok) {
+                const int gv[4] = {g1, g2, g3, g4};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t w = mask[2 * a + h];
+                        while (w) {
+                            const uint32_t id = (uint32_t)gv[a] * 64u + 32u * h + (uint32_t)(__ffs((int)w) - 1);
+                            w &= w - 1;
+                            half_rec = (half_rec << 16) | id;
+                        }
+                    }
+            }
+            xch[256 + row_in_cta * 2 + par] = mine_ok ? 1 : 0;
+            if (par == 0) xrec[row_in_cta] = half_rec;
+            pair_barrier(pair_id);
+            const bool decided = mine_ok && (xch[256 + row_in_cta * 2 + (par ^ 1)] != 0);
+            if (par == 1 && decided) {
+                // cells both threads list (both halves of the cell near the best score) stay in thread 0's half only
+                const unsigned long long other = xrec[row_in_cta];
+                unsigned long long mine = ~0ull;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const uint32_t id = (uint32_t)(half_rec >> (16 * f)) & 0xFFFFu;
+                    bool dup = id == 0xFFFFu;
+#pragma unroll
+                    for (int f2 = 0; f2 < 4; ++f2) dup = dup || (id == ((uint32_t)(other >> (16 * f2)) & 0xFFFFu));
+                    if (!dup) mine = (mine << 16) | id;
+                }
+                half_rec = mine;
+            }
+            if (!decided) half_rec = ~0ull;
+            const int row = rt * kRows + row_in_cta;
+            const bool in_range = row < T;
+            if (in_range) reinterpret_cast<uint2*>(rec)[2 * (int64_t)row + par] = make_uint2((uint32_t)half_rec, (uint32_t)(half_rec >> 32));
+            if (par == 0) {                          // warp-uniform: one of the two warps lists the undecided rows
+                const bool flag = in_range && !decided;
+                const uint32_t ballot = __ballot_sync(VQ_FULL, flag);
+                if (ballot) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(n_flagged, __popc(ballot));
+                    base = __shfl_sync(VQ_FULL, base, 0);
+                    if (flag) flagged[base + __popc(ballot & ((1u << lane) - 1))] = row;
+                    if (lane == 0 && stats)
+                        atomicAdd(reinterpret_cast<unsigned long long*>(stats + VQ_STAT_FALLBACK_ROWS),
+                                  (unsigned long long)__popc(ballot));
+                }
+            }
+            pair_barrier(pair_id);                   // the exchange words are free for the next row tile
+        }
+        if (threadIdx.x == kEpiWarp0 * 32) { VQ_INSTR_END(8, 3); }
+    } else {
+        // ===================== epilogue: one thread per row (8 warps, or 4 with one row half) =====================
+        reg_inc<kRegsEpilogue>();
+        const int e = warp - kEpiWarp0;
+        const int r_sub = HALVES == 2 ? (e >> 2) : 0;   // which 128-row MMA tile
         const int quarter = warp & 3;                // TMEM lane quarter this warp may read (warp id mod 4)
         const int row_in_cta = r_sub * 128 + quarter * 32 + lane;
         const uint32_t tbase = *tmem_slot + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(r_sub * kTileN);
+        // tile b of a group (n_tiles is a multiple of 4, so b = tile count mod 4): its accumulator stage, the stage's
+        // TMEM column, and the parity of the stage's use the running tile count t stands for
+        auto stage_of = [&](int b) { return HALVES == 2 ? 2 * (b & 1) + r_sub : b; };
+        auto col_of = [&](int b) { return (uint32_t)((HALVES == 2 ? 2 * (b & 1) : b) * kTileN); };
+        auto phase_of = [&](uint32_t t) { return HALVES == 2 ? (t >> 1) & 1u : (t >> 2) & 1u; };
         const uint32_t snap0 = smem_base + L.snap + (uint32_t)row_in_cta * kSnapRow;
         const bool force_exhaustive = codebook_degenerate(cb_info);
         uint32_t t_cnt = 0;                          // n-tiles drained so far (same sequence as the MMA warp)
         int it = 0;
         uint32_t bufA[64], bufB[64];
         VQ_INSTR_BEGIN();
-        for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++it) {
+        for (int u = unit0; u < n_units; u += unit_step, ++it) {
+            const int rt = u * CL + (int)cta_rank;
             uint32_t slot[32];
             int m1 = -32768, m2 = -32768, m3 = -32768, m4 = -32768, m5 = -32768;
             int g1 = 0, g2 = 0, g3 = 0, g4 = 0;
@@ -302,7 +546,7 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                 const bool is1 = c1 > m1, is2 = c1 > m2, is3 = c1 > m3, is4 = c1 > m4;
                 if (is4) {
                     // whichever rank the group takes, the group that drops out is the current last one: reuse its area
-                    const uint32_t dst = snap0 + a4 * kSnapArea;
+                    const uint32_t dst = snap0 + a4 * kSnapAreaH;
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16 * q), "r"(slot[4 * q]),
@@ -329,9 +573,9 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                 g1 = is1 ? g : g1; g2 = ng2; g3 = ng3; g4 = ng4;
                 a1 = na1; a2 = na2; a3 = na3; a4 = na4;
             };
-            VQ_TIMED_WAIT(0, t_full(r_sub), (t_cnt >> 1) & 1u);
+            VQ_TIMED_WAIT(0, t_full(stage_of(0)), phase_of(t_cnt));
             tc_fence_after();
-            tmem_ld_tile(tbase, bufA);
+            tmem_ld_tile(tbase + col_of(0), bufA);
             for (int g = 0; g < n_groups; ++g) {
 #pragma unroll
                 for (int b = 0; b < kGroupTiles; ++b) {
@@ -345,15 +589,15 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                     if (e == 0 && lane == 0) { asm volatile("" ::"r"(cur[0]), "r"(cur[63])); VQ_TRACE(1, (int)t_cnt, 1); }
 #endif
                     tc_fence_before();
-                    if (lane == 0) mbar_arrive(t_empty(2 * (b & 1) + r_sub));
+                    if (lane == 0) mbar_arrive(t_empty(stage_of(b)));
                     if (e == 0 && lane == 0) VQ_TRACE(1, (int)t_cnt, 2);
                     ++t_cnt;
                     if (has_next) {
                         // (probing this barrier with mbarrier.test_wait ahead of the tcgen05.wait::ld above was measured: no gain)
-                        VQ_TIMED_WAIT(0, t_full(2 * ((b + 1) & 1) + r_sub), (t_cnt >> 1) & 1u);
+                        VQ_TIMED_WAIT(0, t_full(stage_of((b + 1) & 3)), phase_of(t_cnt));
                         if (e == 0 && lane == 0) VQ_TRACE(1, (int)t_cnt, 0);
                         tc_fence_after();
-                        tmem_ld_tile(tbase + (uint32_t)(((b + 1) & 1) * 2 * kTileN), nxt);
+                        tmem_ld_tile(tbase + col_of((b + 1) & 3), nxt);
                     }
                     if (b == 0) {
                         // the previous group's bookkeeping runs here, behind the hand-off of this tile's TMEM stage: the
@@ -387,7 +631,7 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 if (a == 0 || mv[a] >= thr) {
-                    const uint32_t src = snap0 + av[a] * kSnapArea;
+                    const uint32_t src = snap0 + av[a] * kSnapAreaH;
                     uint32_t kept[32];
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
@@ -407,7 +651,7 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
             const int n_cand = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]) + __popc(mask[4]) + __popc(mask[5]) +
                                __popc(mask[6]) + __popc(mask[7]);
             const bool decided = thr_ok && (m5 < thr) && ((mask[0] | mask[1]) != 0) && (n_cand <= kRecCells) && !force_exhaustive;
-            const int row = rt * kRowsPerCta + row_in_cta;
+            const int row = rt * kRows + row_in_cta;
             const bool in_range = row < T;
             const bool flag = in_range && !decided;
             // verdict record: the surviving cells as 16-bit cell ids (group * 64 + slot), pushed into a 128-bit shift register
@@ -444,6 +688,7 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL == 2) cluster_sync_all();      // nothing of the peer's (multicast tiles, stage releases) is still on its way
     if (warp == kAllocWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(512u) : "memory");
@@ -495,9 +740,6 @@ __device__ __forceinline__ void tmem_ld_half_tile(uint32_t taddr, uint32_t (&v)[
           "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
-}
-__device__ __forceinline__ void pair_barrier(int id) {      // the two warps that own the same 32 rows (64 threads)
-    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
 
 __global__ void __launch_bounds__(kThreadsW, 1)
@@ -1565,6 +1807,45 @@ bool tc16_supported(int64_t T, int K, int D) {
 
 size_t tc16_workspace_bytes(int64_t T) { return (size_t)(T > 0 ? T : 1) * tc16::kRecordBytes; }
 
+// VQ_TC16_CLUSTER=1: the filter as clusters of two 128-row CTAs (k_dist_tc16<true, 1>; measured slower than the 256-row
+// default, see the kernel's header).  Returns how many such clusters the device can hold at once; 0 = use the 256-row
+// kernel (the default, a build with two issuers, the wide-drain / rows-in-TMEM variants, or a device that cannot
+// co-schedule the pairs).
+int tc16_max_clusters() {
+    if constexpr (tc16::kIssuers != 4) {
+        return 0;
+    } else {
+        static PerDeviceOnce once;
+        static int n_of[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (once.need()) {
+            const char* e = getenv("VQ_TC16_CLUSTER");
+            const bool alt = (getenv("VQ_TC16_TS") && atoi(getenv("VQ_TC16_TS")) != 0) || tc16_wide_drain();
+            int n = 0;
+            if (e && e[0] == '1' && !alt) {
+                const tc16::SmemLayout L = tc16::smem_layout(1);
+                if (cudaFuncSetAttribute(tc16::k_dist_tc16<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)L.total + 1024) == cudaSuccess) {
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(2 * sm_count());
+                    cfg.blockDim = dim3(tc16::kThreads);
+                    cfg.dynamicSmemBytes = L.total + 1024;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at;
+                    cfg.numAttrs = 1;
+                    if (cudaOccupancyMaxActiveClusters(&n, tc16::k_dist_tc16<true, 1>, &cfg) != cudaSuccess) n = 0;
+                }
+                cudaGetLastError();
+            }
+            n_of[dev & 63] = n;
+        }
+        return n_of[dev & 63];
+    }
+}
+
 cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T, const __half* zn16, const float* zn32,
                              const float* row_sq, const CodebookView& cb, int* cand, int* flagged, int* n_flagged, int64_t* stats,
                              void* records, cudaStream_t s) {
@@ -1572,7 +1853,7 @@ cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T
     static const bool ss_form = !(getenv("VQ_TC16_TS") && atoi(getenv("VQ_TC16_TS")) != 0);
     int4* rec = static_cast<int4*>(records);
     const int n_row_tiles = (T + tc16::kRowsPerCta - 1) / tc16::kRowsPerCta;
-    const int grid = n_row_tiles < sm_count() ? n_row_tiles : sm_count();
+    int grid = n_row_tiles < sm_count() ? n_row_tiles : sm_count();
     cudaError_t e;
     if (cb.cell_kind == 3) {
         const tc16::SmemLayoutW L = tc16::smem_layout_w();
@@ -1583,14 +1864,26 @@ cudaError_t launch_dist_tc16(const CUtensorMap& ma, const CUtensorMap& mb, int T
         }
         e = launch_pdl(tc16::k_dist_tc16_w16, dim3(grid), dim3(tc16::kThreadsW), L.total + 1024, s, ma, mb, T, cb.K, cb.info,
                        reinterpret_cast<uint2*>(rec), flagged, n_flagged, stats);
+    } else if (ss_form && tc16_max_clusters() > 0) {
+        // (the caller built the tensor maps for this form: 128-row token boxes, 64-code codebook boxes)
+        if constexpr (tc16::kIssuers == 4) {
+            const tc16::SmemLayout L = tc16::smem_layout(1);
+            const int n_units = ((T + 127) / 128 + 1) / 2;
+            const int clusters = n_units < tc16_max_clusters() ? n_units : tc16_max_clusters();
+            grid = 2 * clusters;
+            e = launch_pdl_cluster(tc16::k_dist_tc16<true, 1>, dim3(grid), dim3(tc16::kThreads), L.total + 1024, s, 2, ma, mb, T, cb.K,
+                                   cb.info, rec, cand, flagged, n_flagged, stats);
+        } else {
+            e = cudaErrorInvalidValue;
+        }
     } else if (ss_form) {
-        const tc16::SmemLayout L = tc16::smem_layout();
+        const tc16::SmemLayout L = tc16::smem_layout(2);
         static PerDeviceOnce once;
         if (once.need()) {
-            e = cudaFuncSetAttribute(tc16::k_dist_tc16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
+            e = cudaFuncSetAttribute(tc16::k_dist_tc16<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
             if (e != cudaSuccess) return e;
         }
-        e = launch_pdl(tc16::k_dist_tc16<true>, dim3(grid), dim3(tc16::kThreads), L.total + 1024, s, ma, mb, T, cb.K, cb.info, rec,
+        e = launch_pdl(tc16::k_dist_tc16<true, 2>, dim3(grid), dim3(tc16::kThreads), L.total + 1024, s, ma, mb, T, cb.K, cb.info, rec,
                        cand, flagged, n_flagged, stats);
     } else {
         const tc16::SmemLayoutTs L = tc16::smem_layout_ts();

@@ -80,6 +80,7 @@ cudaError_t launch_scan_listed_tail(const float* zn32, const float* row_sq, cons
 
 // ---- vq_dist_tc16.cu (D = 32: fp16 accumulators, packed 16-bit maxima) ------------------------
 bool tc16_supported(int64_t T, int K, int D);
+int tc16_max_clusters();      // > 0: the D = 32 filter runs as clusters of two 128-row CTAs (token boxes of 128 rows, code boxes of 64)
 constexpr int kFlaggedCap = 4096;     // listed rows that get the sliced per-row search (and a done counter each)
 // exact rescoring of the filter's records + sliced search of the listed rows + the finish pass, one launch
 cudaError_t launch_exact_finish16(const void* records, const float* zn32, const float* row_sq, const CodebookView& cb, int64_t T,
@@ -254,6 +255,20 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// ... as thread-block clusters of `cluster` CTAs along x (grid.x a multiple of it)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster,
+                                      Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

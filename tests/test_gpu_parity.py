@@ -717,12 +717,14 @@ def test_generic_filter_undecided_rows_take_the_exhaustive_paths(dev, D, T, few)
     assert torch.equal(again, got)
 
 
-@pytest.mark.parametrize("env", [{"VQ_TC16_W16": "1"}, {"VQ_TC16_TS": "1"}, {"VQ_TC16_DISABLE": "1"}],
-                         ids=["wide-drain", "rows-in-tmem", "generic-filter"])
+@pytest.mark.parametrize("env", [{"VQ_TC16_W16": "1"}, {"VQ_TC16_TS": "1"}, {"VQ_TC16_DISABLE": "1"}, {"VQ_TC16_CLUSTER": "1"},
+                                 {"VQ_TC_CLUSTER": "0"}],
+                         ids=["wide-drain", "rows-in-tmem", "generic-filter", "cluster-pairs-d32", "no-clusters-d256"])
 def test_alternative_filter_kernels_equal_exhaustive_search(env):
-    """The measured alternatives of the D = 32 filter that stay in the library behind environment switches (16 epilogue
-    warps / token rows in tensor memory / the generic fp32-accumulator filter) return the exhaustive search's indices on
-    every row; the library reads the switches when it is loaded, hence a fresh process."""
+    """The measured alternatives of the filters that stay in the library behind environment switches (D = 32: 16 epilogue
+    warps / token rows in tensor memory / the generic fp32-accumulator filter / clusters of two 128-row CTAs; D = 256: the
+    256-row kernel instead of the cluster pairs) return the exhaustive search's indices on every row; the library reads
+    the switches when it is loaded, hence a fresh process."""
     import subprocess
     import sys
     code = (
@@ -740,6 +742,10 @@ def test_alternative_filter_kernels_equal_exhaustive_search(env):
         "    assert torch.equal(a, b), int((a != b).sum())\n"
         "    zq, idx, loss, hist, stats = F.quantise(z, w, 'vit', prepared=p)\n"
         "    assert torch.equal(idx, b.reshape(-1)) and int(hist.sum()) == idx.numel()\n"
+        "w = vo.make_codebook('vit', 2048, 256, 3).to(dev)\n"
+        "z = vo.make_latents((9, 500, 256), 4).to(dev)\n"
+        "p = F.prepare_codebook(w)\n"
+        "assert torch.equal(F.encode_indices(z, w, 'vit', prepared=p), F.encode_indices(z, w, 'vit', prepared=p, exact_scan=True))\n"
         "print('ok')\n") % (ROOT, os.path.join(ROOT, "attention-models_b200"))
     out = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
