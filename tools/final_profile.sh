@@ -10,6 +10,8 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 6 --warmup 3 --no-graphs --skip-cpu --skip-e2e --skip-sustained --skip-module > gpurun_out/${R}_ncu.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_prep_rows_fused|k_dist_tc16|k_exact_finish16|k_backward_fused' -s 8 -c 4 -o gpurun_out/${R}_full -f \
     python bench.py --steps 6 --warmup 3 --no-graphs --skip-cpu --skip-e2e --skip-sustained --skip-module > gpurun_out/${R}_ncufull.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_prep_nchw_fused|k_dist_tc<|k_rescore_g|k_finish' -s 12 -c 4 -o gpurun_out/${R}_full_cfg2 -f \
+    python bench.py --config cfg2 --steps 6 --warmup 3 --no-graphs --skip-cpu --skip-e2e --skip-sustained --skip-module > gpurun_out/${R}_ncufull_cfg2.log 2>&1
 timeout 300 python tools/sweep.py > gpurun_out/${R}_sweep_configs.txt 2>&1
 timeout 60 python tools/exact_modes.py > gpurun_out/${R}_exact_modes.txt 2>&1
 ls -la gpurun_out/${R}_*
