@@ -1503,12 +1503,16 @@ __device__ __forceinline__ float ord_dist(uint32_t o) {
     return (o == 0u) ? __int_as_float(0x7fc00000) : __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
 }
 
+// kCellKind: the cell layout of the records (vq_kernels.h) as a compile-time constant - the kernel is bound by its
+// instruction stream, and with the default layout the 8 members of a cell are 8 KB apart from ONE base address
+// (immediate offsets instead of eight 64-bit address computations behind a runtime switch).
+template <int kCellKind>
 __global__ void __launch_bounds__(kExactThreads, VQ_EXACT_MIN_BLOCKS)
 k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, const float* __restrict__ row_sq,
                  const float* __restrict__ en32, const float4* __restrict__ en32c, const float* __restrict__ csq_cell, int T,
                  int K, const int* __restrict__ flagged, const int* __restrict__ n_flagged, int flagged_cap,
-                 FlaggedPartial* __restrict__ partial, int* __restrict__ done, FinishOut out, int64_t* __restrict__ stats,
-                 int cell_kind) {
+                 FlaggedPartial* __restrict__ partial, int* __restrict__ done, FinishOut out, int64_t* __restrict__ stats) {
+    constexpr int cell_kind = kCellKind;
     __shared__ unsigned long long s_best[kExactThreads / 32];
     __shared__ float s_second[kExactThreads / 32];
     // Row strides of 9 / 10 float4 put the 4 rows of a warp in different banks: the broadcast LDS.128 of the rescoring
@@ -1568,51 +1572,51 @@ k_exact_finish16(const int4* __restrict__ rec, const float* __restrict__ zn32, c
         {
             bo = so = 0xFFFFFFFFu; bc = 0x7FFFFFFF; n_cells = 0;
             uint32_t w0 = w0i, w1 = w1i, w2 = w2i, w3 = w3i;
-            // cells of this group (record fields that are not 0xFFFF; the wide-drain filter fills the two halves of a
-            // record separately); the loop is warp-uniform (shuffles inside): groups with fewer cells idle
+            // cells of this group: the record fields that are not 0xFFFF (some filters fill the two halves of a record
+            // separately, so empty fields may sit between full ones).  The loop diverges per 8-lane group - a group's
+            // lanes share the record - and its shuffles name only the group: groups with fewer cells skip the body.
             int mine = 0;
             if (valid) {
-#pragma unroll
-                for (int f = 0; f < 8; ++f) {
-                    const uint32_t wsel = f < 2 ? w0i : (f < 4 ? w1i : (f < 6 ? w2i : w3i));
-                    mine += (((wsel >> (16 * (f & 1))) & 0xFFFFu) != 0xFFFFu) ? 1 : 0;
-                }
+                const uint32_t t0 = ~w0i, t1 = ~w1i, t2 = ~w2i, t3 = ~w3i;      // a half is zero iff its field is empty
+                mine = ((t0 & 0xFFFFu) != 0u) + ((t0 >> 16) != 0u) + ((t1 & 0xFFFFu) != 0u) + ((t1 >> 16) != 0u) +
+                       ((t2 & 0xFFFFu) != 0u) + ((t2 >> 16) != 0u) + ((t3 & 0xFFFFu) != 0u) + ((t3 >> 16) != 0u);
             }
-            const int trips = __reduce_max_sync(VQ_FULL, mine);
             n_cells = mine;
-            for (int c = 0; c < trips; ++c) {
-                const bool on = c < mine;
+            for (int c = 0; c < mine; ++c) {
                 // next non-empty field
-                while (on && (w0 & 0xFFFFu) == 0xFFFFu) {
+                while ((w0 & 0xFFFFu) == 0xFFFFu) {
                     w0 = __funnelshift_r(w0, w1, 16); w1 = __funnelshift_r(w1, w2, 16); w2 = __funnelshift_r(w2, w3, 16);
                     w3 = (w3 >> 16) | 0xFFFF0000u;
                 }
-                const int ci = on ? (int)(w0 & 0xFFFFu) : 0;
+                const int ci = (int)(w0 & 0xFFFFu);
                 w0 = __funnelshift_r(w0, w1, 16); w1 = __funnelshift_r(w1, w2, 16); w2 = __funnelshift_r(w2, w3, 16);
                 w3 = (w3 >> 16) | 0xFFFF0000u;
                 float p[8];
+                const float4* e_base = en4 + (int64_t)tc16_code_of(ci, 0, cell_kind) * (kD / 4) + m;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (on) e = __ldg(en4 + (int64_t)tc16_code_of(ci, j, cell_kind) * (kD / 4) + m);
+                    float4 e;
+                    if constexpr (kCellKind == 1) e = __ldg(e_base + j * (64 * (kD / 4)));      // member j: 64 codes further
+                    else e = __ldg(en4 + (int64_t)tc16_code_of(ci, j, cell_kind) * (kD / 4) + m);
                     p[j] = __fmaf_rn(nz.w, e.w, __fmaf_rn(nz.z, e.z, __fmaf_rn(nz.y, e.y, __fmul_rn(nz.x, e.x))));
                 }
-                const float csq = on ? __ldg(csq_cell + ci * 8 + m) : 0.f;
+                const float csq = __ldg(csq_cell + ci * 8 + m);
                 float q4[4], q2[2];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float recv = __shfl_xor_sync(VQ_FULL, (m & 4) ? p[i] : p[i + 4], 4);
+                    const float recv = __shfl_xor_sync(gmask, (m & 4) ? p[i] : p[i + 4], 4);
                     q4[i] = ((m & 4) ? p[i + 4] : p[i]) + recv;
                 }
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const float recv = __shfl_xor_sync(VQ_FULL, (m & 2) ? q4[i] : q4[i + 2], 2);
+                    const float recv = __shfl_xor_sync(gmask, (m & 2) ? q4[i] : q4[i + 2], 2);
                     q2[i] = ((m & 2) ? q4[i + 2] : q4[i]) + recv;
                 }
-                const float recv = __shfl_xor_sync(VQ_FULL, (m & 1) ? q2[0] : q2[1], 1);
+                const float recv = __shfl_xor_sync(gmask, (m & 1) ? q2[0] : q2[1], 1);
                 const float dot = ((m & 1) ? q2[1] : q2[0]) + recv;
-                if (on) take(ref_distance(a_sq, csq, dot), tc16_code_of(ci, m, cell_kind));
+                take(ref_distance(a_sq, csq, dot), tc16_code_of(ci, m, cell_kind));
             }
+            __syncwarp();
         }
         uint32_t omin;
         int code;
@@ -1916,10 +1920,11 @@ cudaError_t launch_exact_finish16(const void* records, const float* zn32, const 
     tc16::FinishOut out;
     out.zq = zq_tok; out.idx = idx_out; out.idx_bits = idx_bits; out.hist = hist;
     out.seg = zq_tok ? reinterpret_cast<unsigned long long*>(seg_sums) : nullptr;
-    cudaError_t e = launch_pdl(tc16::k_exact_finish16, dim3((unsigned)blocks), dim3(tc16::kExactThreads), 0, s,
+    auto* kernel = cb.cell_kind == 3 ? tc16::k_exact_finish16<3> : tc16::k_exact_finish16<1>;
+    cudaError_t e = launch_pdl(kernel, dim3((unsigned)blocks), dim3(tc16::kExactThreads), 0, s,
                                static_cast<const int4*>(records), zn32, row_sq, cb.en32, reinterpret_cast<const float4*>(cb.en32c),
                                cb.csq_cell, (int)T, cb.K, flagged, n_flagged, cap, static_cast<tc16::FlaggedPartial*>(partial_ws),
-                               done_counters, out, stats, cb.cell_kind);
+                               done_counters, out, stats);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }
