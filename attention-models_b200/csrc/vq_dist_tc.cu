@@ -529,10 +529,12 @@ __device__ __forceinline__ float cell_distance_g(const float4* __restrict__ en32
     return ref_distance(a_sq, csq, dot);
 }
 
-// (Measured and rejected, twice: screening a cell's 8 members with their fp16 rows first (512 B per code instead of
-// 1 KB, exact chain only for members within 2 eps of the row's best approximate score).  Fewer bytes, but a lane then
-// walks its own 512-byte row - 32 lines per warp-level load instead of the 4 whole lines of the cell copies - and
-// the kernel is bound by L1 wavefronts, not by bytes: 55 vs 31 us for cfg 2, 1.83 vs 0.66 ms for 1 M tokens.)
+// (Measured and rejected, three times: screening a cell's 8 members with their fp16 values first (512 B per code instead
+// of 1 KB, exact chain only for members within 2 eps of the row's best approximate score).  From the row-major fp16
+// codes a lane walks its own 512-byte row - 32 lines per warp-level load instead of 4: 55 vs 31 us for cfg 2, 1.83 vs
+// 0.66 ms for 1 M tokens.  From coalesced fp16 cell copies (whole lines, like the fp32 ones): 46 vs 31 us, 1.07 vs 0.66
+// ms - the screen and the exact chain are two dependent load -> fma-chain phases per cell, and the kernel is bound by
+// that per-warp latency, not by bytes.)
 // Without a minimum-blocks bound ptxas settles on 48-64 registers for this kernel and serialises the 32 loads a batch
 // wants in flight; 4 blocks per SM = up to 128 registers keeps them all outstanding.
 #ifndef VQ_RESCORE_MINBLOCKS
