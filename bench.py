@@ -149,8 +149,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port of the reference's Codebook, CPU, all host threads
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_tokens_per_s(cfg, sample_tokens: int, repeats: int, warmup: int):
-    """The config's mode on a bounded sample (whole batch items up to `sample_tokens` tokens) through oracle/vq_oracle.py."""
+def cpu_reference_tokens_per_s(cfg, sample_tokens: int, repeats: int, warmup: int, min_seconds: float = 0.0):
+    """The config's mode on a bounded sample (whole batch items up to `sample_tokens` tokens) through oracle/vq_oracle.py.
+    `min_seconds` > 0: keep repeating (at most 200 passes) until the timed passes add up to that much CPU work."""
     import torch
     from oracle import vq_oracle as vo
     cores = os.cpu_count() or 1
@@ -174,17 +175,19 @@ def cpu_reference_tokens_per_s(cfg, sample_tokens: int, repeats: int, warmup: in
                 vo.indices_to_embeddings(form, out.indices.reshape(items, -1), w)
 
     times = []
-    for i in range(warmup + repeats):
+    i = 0
+    while i < warmup + repeats or (min_seconds > 0 and sum(times) < min_seconds and len(times) < 200):
         t0 = time.perf_counter()
         run()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+        i += 1
     sec = sum(times) / len(times)
     what = {"step": "fwd + autograd backward", "encode": "forward (encode_imgs keeps the indices)",
             "roundtrip": "forward + indices_to_embeddings"}[cfg["mode"]]
     sample = (f"{tokens} tokens ({items} batch items) of the workload, token-chunked {chunk}, torch CPU ops restating the "
-              f"reference Codebook ({what}), {sec:.2f} s per pass")
+              f"reference Codebook ({what}), {sec:.2f} s per pass, {len(times)} timed passes = {sum(times):.1f} s of CPU work")
     return tokens / sec, cores, tokens, sec, sample
 
 
@@ -644,8 +647,8 @@ def run_b200(args, cfg):
     # ---- cpu_baseline: oracle port on this box's host cores, bounded sample (N = 1 only) ------------------------------
     cpu = None
     if not args.skip_cpu and world == 1:
-        tps, cores, tokens, sec, sample = cpu_reference_tokens_per_s(cfg, 16384, repeats=3, warmup=1)
-        cpu = {"value": tps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + ", mean of 3"}
+        tps, cores, tokens, sec, sample = cpu_reference_tokens_per_s(cfg, 131072, repeats=3, warmup=1, min_seconds=10.0)
+        cpu = {"value": tps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     workload = (cfg["desc"] + f"; {args.scaling} scaling: {shape[0]} batch items = {T} tokens per GPU, "
                 f"{world * T} tokens over {world} GPU(s), fp32")
