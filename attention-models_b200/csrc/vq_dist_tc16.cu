@@ -215,7 +215,11 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     if (warp == kMmaWarp && lane == 0) {
         // a stage is read by both row halves' issuers, or by its issuer in either CTA of the cluster
         for (int s = 0; s < kBS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 2); }
-        for (int q = 0; q < 4; ++q) { mbar_init(t_full(q), 1); mbar_init(t_empty(q), 4); }     // one arrive per epilogue warp of the half
+        // accumulator hand-off.  256-row CTAs: four stages of 128 columns (tile parity x row half), one issuer each, drained
+        // by the half's four warps.  One row half: TWO stages of 256 columns (= two code tiles, one issuer each) - a
+        // hand-off (wait for the stage, tcgen05.ld, release) costs an epilogue warp ~350 cycles whatever the stage holds
+        // against ~110 for folding a tile, so it is paid once per 256 codes.
+        for (int q = 0; q < 4; ++q) { mbar_init(t_full(q), HALVES == 1 ? 2 : 1); mbar_init(t_empty(q), 4); }
         for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), kIssuers); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -290,7 +294,8 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                     VQ_TIMED_WAIT(2, b_full(s), (b_cnt / kBS) & 1u);
                     // uses of the stage so far: every tile this warp issued into it
                     const uint32_t use = (HALVES == 2 && kIssuers == 2) ? (t_cnt >> 1) : t_cnt;
-                    VQ_TIMED_WAIT(1, t_empty(q), (use & 1u) ^ 1u);
+                    const int qb = HALVES == 1 ? (q >> 1) : q;      // hand-off barriers: per 256-column stage, or per tile
+                    VQ_TIMED_WAIT(1, t_empty(qb), (use & 1u) ^ 1u);
                     tc_fence_after();
                     if (iw == 0 && lane == 0) VQ_TRACE(0, (int)t_cnt, 0);
                     const uint32_t b_addr = smem_base + L.b + s * kBStageBytes;
@@ -300,7 +305,7 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                         for (int k = 0; k < 2; ++k)
                             umma_f16(tmem_base + (uint32_t)(q * kTileN), umma_desc(a_addr + k * 32),
                                      umma_desc(b_addr + k * 32), kIdesc, (uint32_t)k);
-                        umma_commit(t_full(q));
+                        umma_commit(t_full(qb));
                         if constexpr (CL == 2) umma_commit_multicast(b_empty(s), (uint16_t)3);
                         else umma_commit(b_empty(s));
                     }
@@ -320,8 +325,8 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
         // An epilogue warp's per-tile chain (wait for the tile, tcgen05.ld of 64 registers, release, fold) takes ~400
         // cycles however idle its scheduler is (measured: four warps draining every tile of their rows made the kernel
         // 177 us, the issuers waiting for free stages 83 % of the time), so the drain needs two warps per scheduler, as
-        // the 256-row kernel has.  Warp (quarter, par) drains the tiles n = par mod 2 of its 32 rows: of a 512-code group
-        // it sees tiles par and par + 2, and its 32 packed slot registers hold the maxima of 64 sub-cells of 4 codes -
+        // the 256-row kernel has.  Warp (quarter, par) drains accumulator stage `par` of its 32 rows: of a 512-code group
+        // it sees tiles 2 par and 2 par + 1, and its 32 packed slot registers hold the maxima of 64 sub-cells of 4 codes -
         // sub-cell (j, half) of thread par and of thread par ^ 1 together are cell (j, half) of the usual layout (2
         // columns x 4 tiles), so the verdict records and everything behind them are unchanged.  Each thread ranks the
         // groups by its own sub-cell maxima and snapshots its own best four; the row's two threads meet once per row
@@ -341,9 +346,7 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
         volatile int* xch = reinterpret_cast<volatile int*>(smem + L.xch);
         volatile unsigned long long* xrec = reinterpret_cast<volatile unsigned long long*>(smem + L.xch + 128 * 16);
         const bool force_exhaustive = codebook_degenerate(cb_info);
-        uint32_t own = 0;                            // own tiles drained so far: tile 2 own + par, stage 2 (own & 1) + par
-        auto stage_of = [&](uint32_t o) { return (int)(2u * (o & 1u)) + par; };
-        auto phase_of = [&](uint32_t o) { return (o >> 1) & 1u; };
+        uint32_t uses = 0;                           // hand-offs of this warp's stage so far (one per group)
         int it = 0;
         uint32_t bufA[64], bufB[64];
         VQ_INSTR_BEGIN();
@@ -390,34 +393,21 @@ k_dist_tc16(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                 g1 = is1 ? g : g1; g2 = ng2; g3 = ng3; g4 = ng4;
                 a1 = na1; a2 = na2; a3 = na3; a4 = na4;
             };
-            VQ_TIMED_WAIT(0, t_full(stage_of(own)), phase_of(own));
-            tc_fence_after();
-            tmem_ld_tile(tbase + (uint32_t)(stage_of(own) * kTileN), bufA);
             for (int g = 0; g < n_groups; ++g) {
+                // stage `par` holds the tiles 2 par and 2 par + 1 of the group
+                VQ_TIMED_WAIT(0, t_full(par), uses & 1u);
+                tc_fence_after();
+                tmem_ld_tile(tbase + (uint32_t)((2 * par) * kTileN), bufA);
+                tmem_ld_tile(tbase + (uint32_t)((2 * par + 1) * kTileN), bufB);
+                if (g > 0) group_end(g - 1);                      // the previous group's bookkeeping hides in the loads' latency
+                VQ_TIMED_BEGIN();
+                tmem_ld_wait();                                   // both tiles are in registers: the stage is free
+                VQ_TIMED_END(2);
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(t_empty(par));
+                ++uses;
 #pragma unroll
-                for (int bb = 0; bb < 2; ++bb) {
-                    uint32_t (&cur)[64] = bb ? bufB : bufA;
-                    uint32_t (&nxt)[64] = bb ? bufA : bufB;
-                    VQ_TIMED_BEGIN();
-                    tmem_ld_wait();                                   // the tile is in registers: its TMEM stage is free
-                    VQ_TIMED_END(2);
-                    tc_fence_before();
-                    if (lane == 0) mbar_arrive(t_empty(stage_of(own)));
-                    ++own;
-                    if (bb == 0 || g + 1 < n_groups) {
-                        VQ_TIMED_WAIT(0, t_full(stage_of(own)), phase_of(own));
-                        tc_fence_after();
-                        tmem_ld_tile(tbase + (uint32_t)(stage_of(own) * kTileN), nxt);
-                    }
-                    if (bb == 0) {
-                        if (g > 0) group_end(g - 1);                  // behind the hand-off of this tile's stage
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) slot[j] = __vmaxs2(cur[j], cur[j + 32]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) slot[j] = __vimax3_s16x2(slot[j], cur[j], cur[j + 32]);
-                    }
-                }
+                for (int j = 0; j < 32; ++j) slot[j] = __vimax3_s16x2(__vmaxs2(bufA[j], bufA[j + 32]), bufB[j], bufB[j + 32]);
             }
             group_end(n_groups - 1);
             // ---- row verdict, taken by the row's two threads ----
