@@ -165,10 +165,12 @@ __device__ __forceinline__ void best3_merge(Best3& a, float d1, int i1, float d2
 // the drain.  Issuer q owns stage q and the tiles n = q mod 4; eight epilogue warps drain them, two per TMEM lane
 // quarter taking alternate tiles (see the epilogue).  Correct on the first run both times, and: 176.9 us with four
 // epilogue warps (issuers waiting for free stages 83 % of the time: one warp per scheduler cannot drain a tile in less
-// than ~400 cycles), 173.9 us with eight (two threads per row) against 124.1 us for the 256-row kernel on the same box.
-// What the instrumented build shows: an epilogue warp is busy ~620 cycles per tile it drains (510 in the 256-row
-// kernel; here every thread also runs the per-group bookkeeping for its half of the tiles), two such warps per
-// scheduler, so the drain - not the accumulator ring - paces the kernel at D = 32, where a tile is only two MMAs; and
+// than ~400 cycles), 173.9 us with eight (two threads per row on alternate tiles), 178.2 us with eight and one hand-off
+// per 256-column stage (the form below: the hand-off is not what costs) against 124.1 us for the 256-row kernel on the
+// same box.  What the instrumented build shows: an epilogue warp is busy ~500-620 cycles per 32 x 128 tile it drains
+// however the tiles are handed over (510 in the 256-row kernel; here every thread also runs the per-group bookkeeping,
+// ~350 cycles, for its half of the tiles), two such warps per scheduler, so the drain - not the accumulator ring -
+// paces the kernel at D = 32, where a tile is only two MMAs; and
 // the MMAs themselves cannot go below ~77-84 cycles each per SM (tools/ubench_mma.cu; the D = 256 kernel, which has 16
 // MMAs per tile to hide its drain behind, sits at 77), i.e. ~75 us for this shape.  Getting past both needs
 // cta_group::2 MMAs (one instruction per CTA pair: half the issue cost per SM) and a cheaper drain, not more stages.
