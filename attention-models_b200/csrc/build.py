@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libvq_b200.so")
-SOURCES = ["vq_abi.cu", "vq_prep.cu", "vq_dist_simt.cu", "vq_dist_tc.cu", "vq_dist_tc16.cu", "vq_finish.cu", "vq_backward.cu", "vq_peer.cu", "vq_tokens.cu"]
+SOURCES = ["vq_abi.cu", "vq_prep.cu", "vq_dist_simt.cu", "vq_dist_tc.cu", "vq_dist_tc16.cu", "vq_finish.cu", "vq_backward.cu", "vq_peer.cu", "vq_tokens.cu", "vq_prequant.cu"]
 HEADERS = ["vq_common.cuh", "vq_kernels.h", "vq_tc_common.cuh", "vq_backward_body.cuh",
            os.path.join("..", "..", "include", "vq_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

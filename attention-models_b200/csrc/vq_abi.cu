@@ -177,15 +177,83 @@ int vq_workspace_bytes(int64_t T, int K, int D, int flags, size_t* out) {
     return VQ_OK;
 }
 
+namespace {
+// pre_quant projection in front of the quantiser (vq_forward_projected): z = x W^T + b is formed inside the token prep
+struct Projection {
+    const float* x; int C; const float* w; const float* bias; float* z_out;
+};
+
+int forward_impl(const float* z, const Projection* pj, int layout, int64_t T, int64_t hw, const float* weight, void* cb, int K,
+                 int D, int form, float beta, int flags, int64_t n_elem_total, float* z_q, void* idx, float* loss, int32_t* hist,
+                 int64_t* stats, float* saved_zn, float* saved_denom, int64_t* seg_sums, void* ws, size_t ws_bytes, void* stream);
+}  // namespace
+
 int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* weight, void* cb, int K, int D, int form, float beta,
                int flags, int64_t n_elem_total, float* z_q, void* idx, float* loss, int32_t* hist, int64_t* stats,
                float* saved_zn, float* saved_denom, int64_t* seg_sums, void* ws, size_t ws_bytes, void* stream) {
+    return forward_impl(z, nullptr, layout, T, hw, weight, cb, K, D, form, beta, flags, n_elem_total, z_q, idx, loss, hist, stats,
+                        saved_zn, saved_denom, seg_sums, ws, ws_bytes, stream);
+}
+
+int vq_prequant_supported(int C, int D) { return vq::prequant_supported(C, D) ? 1 : 0; }
+
+int vq_forward_projected(const float* x, int C, const float* w_pre, const float* b_pre, int64_t T, const float* weight, void* cb,
+                         int K, int D, int form, float beta, int flags, int64_t n_elem_total, float* z_q, void* idx, float* loss,
+                         int32_t* hist, int64_t* stats, float* saved_zn, float* saved_denom, int64_t* seg_sums, float* z_out,
+                         void* ws, size_t ws_bytes, void* stream) {
+    if (form != VQ_FORM_VIT) return fail(VQ_ERR_ARG, "vq_forward_projected: the Linear pre_quant belongs to the ViT form (form %d)", form);
+    if (!vq::prequant_supported(C, D))
+        return fail(VQ_ERR_ARG, "vq_forward_projected: in_features %d -> codebook_dim %d unsupported (D = 32, C a multiple of 64 "
+                                "up to 768); project with a GEMM and call vq_forward", C, D);
+    if ((!x && T > 0) || !w_pre) return fail(VQ_ERR_ARG, "x/w_pre is NULL");
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return fail(VQ_ERR_ARG, "x must be 16-byte aligned");
+    const Projection pj{x, C, w_pre, b_pre, z_out};
+    return forward_impl(nullptr, &pj, VQ_LAYOUT_TOKEN_MAJOR, T, 0, weight, cb, K, D, form, beta, flags, n_elem_total, z_q, idx, loss,
+                        hist, stats, saved_zn, saved_denom, seg_sums, ws, ws_bytes, stream);
+}
+
+int vq_project_codebook(const float* weight, const void* cb, int K, int D, int normalise, const float* w_post, const float* b_post,
+                        int C, float* table, void* stream) {
+    if (int r = check_dims(0, K, D)) return r;
+    if (C <= 0 || !w_post || !table) return fail(VQ_ERR_ARG, "w_post/table is NULL or out_features %d <= 0", C);
+    if ((reinterpret_cast<uintptr_t>(w_post) & 15) != 0) return fail(VQ_ERR_ARG, "w_post must be 16-byte aligned");
+    const float* y = nullptr;
+    if (normalise) {
+        if (!cb) return fail(VQ_ERR_ARG, "normalise=1 needs the prepared codebook");
+        y = vq::codebook_view(const_cast<void*>(cb), K, D).en32;
+    } else {
+        if (!weight) return fail(VQ_ERR_ARG, "normalise=0 needs the raw weight");
+        y = weight;
+    }
+    VQ_CUDA(vq::launch_project_codebook(y, K, D, w_post, b_post, C, table, static_cast<cudaStream_t>(stream)));
+    return VQ_OK;
+}
+
+int vq_gather_projected(const void* tokens, int token_bits, int64_t T, int64_t hw, const float* table, int K, int C, int layout_out,
+                        float* out, int64_t* stats, void* stream) {
+    if (K <= 0 || K >= (1 << 30)) return fail(VQ_ERR_ARG, "codebook_size %d out of range", K);
+    if (T < 0 || T >= (1ll << 31)) return fail(VQ_ERR_ARG, "token count %lld out of range", (long long)T);
+    if (C <= 0 || (layout_out == VQ_LAYOUT_TOKEN_MAJOR && C % 4 != 0))
+        return fail(VQ_ERR_ARG, "out_features %d: positive, and a multiple of 4 for token-major output", C);
+    if (int r = check_layout(layout_out, T, hw)) return r;
+    if (token_bits != 16 && token_bits != 32 && token_bits != 64) return fail(VQ_ERR_ARG, "token_bits %d: 16, 32 or 64", token_bits);
+    if (!tokens || !out || !table) return fail(VQ_ERR_ARG, "tokens/table/out is NULL");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (stats) VQ_CUDA(cudaMemsetAsync(stats + VQ_STAT_BAD_INDEX, 0, sizeof(int64_t), s));
+    VQ_CUDA(vq::launch_gather(tokens, T, hw, table, K, C, layout_out, out, stats, s, token_bits));
+    return VQ_OK;
+}
+
+namespace {
+int forward_impl(const float* z, const Projection* pj, int layout, int64_t T, int64_t hw, const float* weight, void* cb, int K,
+                 int D, int form, float beta, int flags, int64_t n_elem_total, float* z_q, void* idx, float* loss, int32_t* hist,
+                 int64_t* stats, float* saved_zn, float* saved_denom, int64_t* seg_sums, void* ws, size_t ws_bytes, void* stream) {
     if (int r = check_dims(T, K, D)) return r;
     if (int r = check_layout(layout, T, hw)) return r;
     if (form != VQ_FORM_VIT && form != VQ_FORM_VQGAN && form != VQ_FORM_VQGAN_L2) return fail(VQ_ERR_ARG, "unknown form %d", form);
     const bool raw = form == VQ_FORM_VQGAN_L2;
     if (raw) flags |= VQ_FLAG_EXACT_SCAN;       // the filters' error bounds assume unit rows
-    if (!cb || !idx || (!z && T > 0)) return fail(VQ_ERR_ARG, "z/cb/idx is NULL");
+    if (!cb || !idx || (!pj && !z && T > 0)) return fail(VQ_ERR_ARG, "z/cb/idx is NULL");
     const bool indices_only = (flags & VQ_FLAG_INDICES_ONLY) != 0;
     if (!indices_only && !z_q) return fail(VQ_ERR_ARG, "z_q is NULL without VQ_FLAG_INDICES_ONLY");
     if (indices_only && seg_sums) return fail(VQ_ERR_ARG, "seg_sums needs the full forward (no VQ_FLAG_INDICES_ONLY)");
@@ -201,7 +269,7 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
     vq::CodebookView cbv = vq::codebook_view(cb, K, D);
     if (g_profiling) g_sampled = (g_profile_calls++ % g_profile_every) == 0;
     // `weight` given: the codebook is prepared by this call -- in the token prep launch when the shape allows it
-    const bool fuse_prep = weight && layout == VQ_LAYOUT_TOKEN_MAJOR && vq::prep_fusable(D) && !raw;
+    const bool fuse_prep = weight && layout == VQ_LAYOUT_TOKEN_MAJOR && vq::prep_fusable(D) && !raw && !pj;
     if (weight && !fuse_prep) {
         SlotTimer cb_timer(s, VQ_PROFILE_PREP_CODEBOOK);
         VQ_CUDA(vq::launch_prep_codebook(weight, cbv, s, raw));
@@ -229,7 +297,10 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
 
     // 1. unit rows (ATen-order norms), fp16 copy for the tensor cores
     SlotTimer prep_timer(s, VQ_PROFILE_PREP_TOKENS);
-    if (fuse_prep) {
+    if (pj) {
+        // pre_quant Linear + token prep in one pass over the encoder rows (vq_prequant.cu)
+        VQ_CUDA(vq::launch_prequant_prep(pj->x, T, pj->C, pj->w, pj->bias, D, zn32, w.row_sq, denom, zn16, pj->z_out, zl, s));
+    } else if (fuse_prep) {
         VQ_CUDA(vq::launch_prep_fused(weight, cbv, z, T, zn32, w.row_sq, denom, zn16, zl, s));
     } else if (layout == VQ_LAYOUT_TOKEN_MAJOR) {
         VQ_CUDA(vq::launch_prep_tokens(z, T, D, zn32, w.row_sq, denom, zn16, zl, s, raw));
@@ -293,6 +364,7 @@ int vq_forward(const float* z, int layout, int64_t T, int64_t hw, const float* w
     }
     return VQ_OK;
 }
+}  // namespace
 
 int vq_loss_finalize(const int64_t* stats, int64_t n_elem_total, int form, float beta, float* loss, void* stream) {
     if (!stats || !loss || n_elem_total <= 0) return fail(VQ_ERR_ARG, "bad argument to vq_loss_finalize");

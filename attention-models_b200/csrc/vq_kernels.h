@@ -57,6 +57,15 @@ bool prep_nchw_fused_supported(int64_t T, int64_t hw, int D);
 cudaError_t launch_prep_nchw_fused(const float* z, int64_t T, int64_t hw, int D, float* denom, float* zn32, __half* zn16,
                                    float* row_sq, const ZeroList& zl, bool raw, cudaStream_t s);
 
+// ---- vq_prequant.cu (pre_quant / post_quant projection fusion) ------------------------------
+// z = x W^T + b (x: (T, C), W: (D, C)) and the token preparation above in one pass; z itself is written only if z_out != null
+bool prequant_supported(int C, int D);
+cudaError_t launch_prequant_prep(const float* x, int64_t T, int C, const float* w, const float* bias, int D, float* zn32,
+                                 float* row_sq, float* denom, __half* zn16, float* z_out, const ZeroList& zl, cudaStream_t s);
+// table[k] = W y_k + b over K rows of y (K, D); W: (C, D)
+cudaError_t launch_project_codebook(const float* y, int K, int D, const float* w, const float* bias, int C, float* table,
+                                    cudaStream_t s);
+
 // ---- vq_dist_simt.cu -------------------------------------------------------------------------
 // Exhaustive fp32 search.  rows == nullptr: all T rows; else the first *n_rows entries of `rows`.
 // Writes cand[row] = index | kCandExactBit and counts near-tie rows into stats.

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("VQ_B200_LIB") or os.path.join(_PKG_DIR, "lib", "libvq
 BUILD_SCRIPT = os.path.join(_PKG_DIR, "csrc", "build.py")
 
 # constants mirrored from include/vq_b200.h
-ABI_VERSION = 5
+ABI_VERSION = 6
 FORM_VIT, FORM_VQGAN, FORM_VQGAN_L2 = 0, 1, 2
 LAYOUT_TOKEN_MAJOR, LAYOUT_NCHW = 0, 1
 FLAG_INDICES_ONLY, FLAG_EXACT_SCAN, FLAG_KEEP_STATS, FLAG_IDX32, FLAG_IDX16 = 1, 2, 4, 8, 16
@@ -39,6 +39,13 @@ SIGNATURES = {
     "vq_forward": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int64,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_size_t, c_void_p]),
+    "vq_prequant_supported": (c_int, [c_int, c_int]),
+    "vq_forward_projected": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                     c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vq_project_codebook": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "vq_gather_projected": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p]),
     "vq_loss_finalize": (c_int, [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]),
     "vq_backward_workspace_bytes": (c_int, [c_int64, c_int, c_int, POINTER(c_size_t)]),
     "vq_backward_tokens": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

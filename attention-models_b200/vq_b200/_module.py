@@ -33,6 +33,7 @@ class _CodebookBase(nn.Module):
         self.last_histogram: Optional[torch.Tensor] = None
         self.last_stats: Optional[torch.Tensor] = None
         self._prepared: Optional[F_vq.PreparedCodebook] = None
+        self._table = None               # projected codes behind post_quant (decode_projected)
 
     # The prepared codebook (unit codes, fp16 copy, ...) is a cache keyed on the weight's storage and version counter: a
     # frozen tokeniser (MaskGIT / Muse / Parti) prepares once.  A forward that can train the codebook never trusts the
@@ -42,13 +43,14 @@ class _CodebookBase(nn.Module):
     # invalidate by themselves.
     def invalidate_codebook(self) -> None:
         self._prepared = None
+        self._table = None
 
     def _load_from_state_dict(self, *args, **kwargs):
-        self._prepared = None
+        self._prepared = self._table = None
         return super()._load_from_state_dict(*args, **kwargs)
 
     def _apply(self, fn, *args, **kwargs):
-        self._prepared = None
+        self._prepared = self._table = None
         return super()._apply(fn, *args, **kwargs)
 
     def _prepared_codebook(self) -> F_vq.PreparedCodebook:
@@ -81,6 +83,53 @@ class _CodebookBase(nn.Module):
     def indices_to_embeddings(self, indices: torch.Tensor) -> torch.Tensor:
         prepared = self._prepared_codebook() if self.form == "vit" else None
         return F_vq.indices_to_embeddings(indices, self.embedding.weight, self.form, prepared=prepared)
+
+    # ---- pre_quant / post_quant fused with the quantiser (vq_b200/projected.py) ----------
+    def supports_fused_pre_quant(self, pre_quant: nn.Module) -> bool:
+        """ViT form behind an ``nn.Linear(C, 32)`` with C a multiple of 64 up to 768, fp32, not the forced exhaustive scan
+        of a layout the fused kernel does not write."""
+        from . import projected
+        return (self.form == "vit" and isinstance(pre_quant, nn.Linear) and pre_quant.weight.dtype == torch.float32
+                and pre_quant.out_features == self.codebook_dim
+                and projected.prequant_supported(pre_quant.in_features, self.codebook_dim))
+
+    def forward_projected(self, x: torch.Tensor, pre_quant: nn.Linear):
+        """``self(pre_quant(x))`` (models/vitvqgan.py:192-193) with the projection formed inside the token preparation:
+        ``(z_q (..., D), indices (...), loss)``; gradients reach ``x``, ``pre_quant`` and the codebook."""
+        from . import projected
+        w = self.embedding.weight
+        if self._prepared is None or not self._prepared.fits(w):
+            self._prepared = F_vq.prepare_codebook(w)
+        trainable = torch.is_grad_enabled() and w.requires_grad
+        z_q, flat_idx, loss, hist, stats = projected.quantise_projected(
+            x, pre_quant.weight, pre_quant.bias, w, self.beta, prepared=self._prepared, exact_scan=self.exact_scan,
+            always_refresh=trainable)
+        self.last_histogram, self.last_stats = hist, stats
+        return z_q, flat_idx.view(*x.shape[:-1]), loss
+
+    def encode_projected(self, x: torch.Tensor, pre_quant: nn.Linear, index_dtype: torch.dtype = torch.int64) -> torch.Tensor:
+        """Tokens of ``pre_quant(x)`` (models/vitvqgan.py:207-209), indices-only path."""
+        from . import projected
+        idx = projected.encode_indices_projected(x, pre_quant.weight, pre_quant.bias, self.embedding.weight,
+                                                 prepared=self._prepared_codebook(), exact_scan=self.exact_scan,
+                                                 index_dtype=index_dtype)
+        return idx.view(*x.shape[:-1])
+
+    def decode_projected(self, indices: torch.Tensor, post_quant: nn.Module) -> torch.Tensor:
+        """``post_quant(self.indices_to_embeddings(indices))`` (models/vitvqgan.py:199-200, models/vqgan.py:241-242) as
+        one gather from the table of projected codes; the table is rebuilt when the codebook or ``post_quant`` change
+        (same caveat about edits through ``.data`` as above: ``invalidate_codebook()``).  Inference only (no autograd
+        graph): a training step goes through ``forward``."""
+        from . import projected
+        if self.form not in ("vit", "vqgan"):
+            raise ValueError("decode_projected: the reference's two forms only")
+        w, wp, bp = self.embedding.weight, post_quant.weight, post_quant.bias
+        if isinstance(post_quant, nn.Conv2d) and (post_quant.kernel_size != (1, 1) or post_quant.groups != 1):
+            raise ValueError("post_quant must be a 1x1 convolution (models/vqgan.py:228)")
+        if self._table is None or not self._table.matches(w, wp, bp):
+            prepared = self._prepared_codebook() if self.form == "vit" else None
+            self._table = projected.ProjectedTable(w, wp, bp, self.form, prepared)
+        return self._table.gather(indices)
 
     def near_tie_rows(self) -> int:
         """Rows of the last forward whose two best fp32 distances were < 1e-6 relative apart (host sync)."""

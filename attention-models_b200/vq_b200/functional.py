@@ -136,35 +136,42 @@ class _Quantise(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, g_zq, g_idx, g_loss, g_hist, g_stats):
-        lib = _lib.load()
-        saved_zn, saved_denom, idx, blob, hist, seg_saved = ctx.saved_tensors
-        form, beta, layout, T, hw, K, D, n_total, z_shape = ctx.meta
-        dev = saved_zn.device
-        want_z, want_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        if g_zq is not None:
-            g_zq = g_zq.contiguous().float()
-        g_loss = torch.zeros(1, dtype=torch.float32, device=dev) if g_loss is None else g_loss.reshape(1).float()
-        grad_z = torch.empty(z_shape, dtype=torch.float32, device=dev) if want_z else None
-        seg, from_forward = (seg_saved if ctx.has_seg else None), ctx.has_seg
-        if want_w and seg is None:
-            seg = torch.empty(K * D + K, dtype=torch.int64, device=dev)
-        grad_w = torch.empty(K, D, dtype=torch.float32, device=dev) if want_w else None
-        ws_bytes = _lib.size_query("vq_backward_workspace_bytes", T, K, D)
-        ws = _scratch(ws_bytes, dev)
-        with torch.cuda.device(dev):
-            s = _stream(dev)
-            if want_w and from_forward:        # one launch: grad_z + grad_weight from the forward's segment sums
-                _lib.check(lib.vq_backward(_ptr(g_zq), layout, T, hw, _ptr(saved_zn), _ptr(saved_denom), _ptr(idx), _ptr(blob),
-                                           K, D, form, beta, _ptr(g_loss), n_total, _ptr(seg), None, _ptr(grad_z), _ptr(grad_w),
-                                           None, _ptr(ws), ws_bytes, s))
-                return grad_z, grad_w, None, None, None, None, None, None, None, None
-            _lib.check(lib.vq_backward_tokens(_ptr(g_zq), layout, T, hw, _ptr(saved_zn), _ptr(saved_denom), _ptr(idx),
-                                              _ptr(hist), _ptr(blob), K, D, form, beta, _ptr(g_loss), n_total, _ptr(grad_z),
-                                              None if from_forward or not want_w else _ptr(seg), _ptr(ws), ws_bytes, s))
-            if want_w:
-                _lib.check(lib.vq_backward_codebook(_ptr(seg), _ptr(blob), K, D, form, beta, _ptr(g_loss), n_total,
-                                                    _ptr(grad_w), None, None, s))
+        grad_z, grad_w = _quantise_backward(ctx.saved_tensors, ctx.meta, ctx.has_seg, g_zq, g_loss,
+                                            ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return grad_z, grad_w, None, None, None, None, None, None, None, None
+
+
+def _quantise_backward(saved, meta, has_seg, g_zq, g_loss, want_z, want_w):
+    """grad_z / grad_weight of one quantiser forward from what it saved (vq_backward*); shared by ``_Quantise`` and
+    the projected forward (vq_b200/projected.py)."""
+    lib = _lib.load()
+    saved_zn, saved_denom, idx, blob, hist, seg_saved = saved
+    form, beta, layout, T, hw, K, D, n_total, z_shape = meta
+    dev = saved_zn.device
+    if g_zq is not None:
+        g_zq = g_zq.contiguous().float()
+    g_loss = torch.zeros(1, dtype=torch.float32, device=dev) if g_loss is None else g_loss.reshape(1).float()
+    grad_z = torch.empty(z_shape, dtype=torch.float32, device=dev) if want_z else None
+    seg, from_forward = (seg_saved if has_seg else None), has_seg
+    if want_w and seg is None:
+        seg = torch.empty(K * D + K, dtype=torch.int64, device=dev)
+    grad_w = torch.empty(K, D, dtype=torch.float32, device=dev) if want_w else None
+    ws_bytes = _lib.size_query("vq_backward_workspace_bytes", T, K, D)
+    ws = _scratch(ws_bytes, dev)
+    with torch.cuda.device(dev):
+        s = _stream(dev)
+        if want_w and from_forward:        # one launch: grad_z + grad_weight from the forward's segment sums
+            _lib.check(lib.vq_backward(_ptr(g_zq), layout, T, hw, _ptr(saved_zn), _ptr(saved_denom), _ptr(idx), _ptr(blob),
+                                       K, D, form, beta, _ptr(g_loss), n_total, _ptr(seg), None, _ptr(grad_z), _ptr(grad_w),
+                                       None, _ptr(ws), ws_bytes, s))
+            return grad_z, grad_w
+        _lib.check(lib.vq_backward_tokens(_ptr(g_zq), layout, T, hw, _ptr(saved_zn), _ptr(saved_denom), _ptr(idx),
+                                          _ptr(hist), _ptr(blob), K, D, form, beta, _ptr(g_loss), n_total, _ptr(grad_z),
+                                          None if from_forward or not want_w else _ptr(seg), _ptr(ws), ws_bytes, s))
+        if want_w:
+            _lib.check(lib.vq_backward_codebook(_ptr(seg), _ptr(blob), K, D, form, beta, _ptr(g_loss), n_total,
+                                                _ptr(grad_w), None, None, s))
+    return grad_z, grad_w
 
 
 def _as_fp32_input(z: torch.Tensor) -> torch.Tensor:

@@ -4,6 +4,7 @@ from __future__ import annotations
 import types
 from typing import Optional
 
+import torch
 import torch.nn as nn
 
 
@@ -20,7 +21,29 @@ def _encode_imgs_vqgan(self, imgs):
     return self.codebook.encode(enc_imgs).view(b, -1)
 
 
-def patch_reference_model(model: nn.Module, form: Optional[str] = None, fast_encode: bool = True) -> nn.Module:
+def _forward_vit_fused(self, imgs):
+    """models/vitvqgan.py:190-196 with ``pre_quant`` formed inside the quantiser's token preparation."""
+    enc_imgs = self.encoder(imgs)
+    embeds, _, loss = self.codebook.forward_projected(enc_imgs, self.pre_quant)
+    return self.decoder(self.post_quant(embeds)), loss
+
+
+def _encode_imgs_vit_fused(self, imgs):
+    """models/vitvqgan.py:204-210: encoder -> (pre_quant + quantiser, indices only) -> indices (b, n)."""
+    return self.codebook.encode_projected(self.encoder(imgs), self.pre_quant)
+
+
+def _decode_indices_fused(self, indices):
+    """models/vitvqgan.py:198-202 / models/vqgan.py:239-243: lookup + ``post_quant`` as one gather from the projected
+    codes when nothing on the way needs a gradient (generation); the reference's composition otherwise."""
+    params = [self.codebook.embedding.weight, *self.post_quant.parameters()]
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        return self.decoder(self.post_quant(self.codebook.indices_to_embeddings(indices)))
+    return self.decoder(self.codebook.decode_projected(indices, self.post_quant))
+
+
+def patch_reference_model(model: nn.Module, form: Optional[str] = None, fast_encode: bool = True,
+                          fuse_projections: bool = False) -> nn.Module:
     """Replace ``model.codebook`` (a reference ``Codebook`` from models/vitvqgan.py or models/vqgan.py)
     by the B200 drop-in carrying the same weights, ``beta`` and sizes.  The wrappers' call sites
     (vitvqgan.py:193,200,208; vqgan.py:234,241,249) keep working unchanged.  Returns ``model``.
@@ -29,6 +52,11 @@ def patch_reference_model(model: nn.Module, form: Optional[str] = None, fast_enc
     ``fast_encode``: also rebind ``model.encode_imgs`` so that tokenisation (what MaskGIT / Muse / Parti call) takes the
     indices-only path of the quantiser (VQ_FLAG_INDICES_ONLY: no z_q, no loss, nothing saved) instead of running the
     whole forward and dropping two of its three results; same indices, same shape.
+    ``fuse_projections``: also rebind ``forward`` / ``encode_imgs`` so that the ViT form's
+    ``pre_quant`` Linear is computed inside the quantiser's first kernel (shapes ``supports_fused_pre_quant`` covers), and
+    ``decode_indices`` (both forms) so that lookup + ``post_quant`` is one gather from the K projected codes.  Off by
+    default: the fused GEMM sums in another order than cuBLAS, so z -- and with it an index on a row whose two best codes
+    are closer than fp32 rounding -- can differ from the unfused path by rounding.
     """
     from . import vitvqgan, vqgan
 
@@ -47,4 +75,11 @@ def patch_reference_model(model: nn.Module, form: Optional[str] = None, fast_enc
     model.codebook = new
     if fast_encode and all(hasattr(model, a) for a in ("encoder", "pre_quant", "encode_imgs")):
         model.encode_imgs = types.MethodType(_encode_imgs_vqgan if form == "vqgan" else _encode_imgs_vit, model)
+    if fuse_projections:
+        if all(hasattr(model, a) for a in ("decoder", "post_quant", "decode_indices")):
+            model.decode_indices = types.MethodType(_decode_indices_fused, model)
+        if (form == "vit" and all(hasattr(model, a) for a in ("encoder", "pre_quant", "post_quant", "decoder"))
+                and new.supports_fused_pre_quant(model.pre_quant)):
+            model.forward = types.MethodType(_forward_vit_fused, model)
+            model.encode_imgs = types.MethodType(_encode_imgs_vit_fused, model)
     return model

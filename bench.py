@@ -2,7 +2,7 @@
 """bench.py -- VQ codebook quantiser throughput (BASELINE.json metric) on N B200s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--config cfg1|cfg2|cfg2fwd|cfg3|cfg4|sweep:T,K,D] [--scaling weak|strong]
+                    [--config cfg1|cfg2|cfg2fwd|cfg3|cfg4|sweep:T,K,D|cfg3pre] [--scaling weak|strong]
 
 Default workload (config.workload): BASELINE.json configs[2] -- the ViT-VQGAN training-step quantiser, fwd + bwd
 (straight-through + codebook gradient), K = 8192 codes x D = 32, batch 256 x 1024 tokens (262 144 tokens), fp32,
@@ -680,7 +680,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="cfg3", help="cfg1 | cfg2 | cfg2fwd | cfg3 (default) | cfg4 | sweep:T,K,D")
+    ap.add_argument("--config", default="cfg3", help="cfg1 | cfg2 | cfg2fwd | cfg3 (default) | cfg4 | sweep:T,K,D | cfg3pre (cfg3 behind the fused pre_quant Linear(512, 32), encode)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the config's batch on every GPU; strong: the config's batch split over the GPUs")
     ap.add_argument("--sets", type=int, default=4, help="resident input sets rotated between steps (at least; more for small shapes)")
@@ -696,6 +696,14 @@ def main():
     ap.add_argument("--skip-module", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.config == "cfg3pre":
+        # SURVEY.md 8(f) rank 1 (pre_quant fused into the quantiser): its own workload, measured to the same contract
+        import bench_projected
+        if args.impl == "reference":
+            bench_projected.run_reference(args)
+        else:
+            bench_projected.run_b200(args, _peaks(), ClockSampler)
+        return
     cfg = bi.resolve_config(args.config)
     if args.impl == "reference":
         run_reference(args, cfg)

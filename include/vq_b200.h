@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 5
+#define VQ_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define VQ_API __attribute__((visibility("default")))
@@ -132,6 +132,27 @@ VQ_API int vq_forward(const float* z, int layout, int64_t T, int64_t hw,
                const float* weight, void* cb, int K, int D, int form, float beta, int flags, int64_t n_elem_total,
                float* z_q, void* idx, float* loss, int32_t* hist, int64_t* stats,
                float* saved_zn, float* saved_denom, int64_t* seg_sums,
+               void* ws, size_t ws_bytes, void* stream);
+
+/* ---- pre_quant fused into the forward ------------------------------------
+ * Replaces `enc = self.pre_quant(enc); self.codebook(enc)` of ViTVQGAN.forward / encode_imgs
+ * (models/vitvqgan.py:185, 192-193, 207-208; pre_quant = nn.Linear(dim, codebook_dim)):
+ *   z = x W_pre^T + b_pre   (x: (T, C) encoder rows, W_pre: (D, C) = pre_quant.weight, b_pre: D floats or NULL)
+ * is formed inside the token preparation -- x is read once, z never travels through HBM -- and everything behind it is
+ * vq_forward's (same arguments, same outputs, form = VQ_FORM_VIT, token-major).  The GEMM runs on the tensor cores in the
+ * 3xTF32 split (fp32-GEMM-level rounding, in an order of its own like any two fp32 GEMMs): z agrees with F.linear to a
+ * few fp32 ulps of sum|x_c W_dc|; an index can differ from F.linear + vq_forward only on a row whose two best codes are
+ * closer than that rounding (tests count them like near-ties).  Given the same z all outputs are bit-identical to
+ * vq_forward's.
+ * z_out: optional (T, D) copy of z (NULL: not written -- the backward needs saved_zn / saved_denom only).
+ * Supported: D = 32, C a multiple of 64 up to 768 (vq_prequant_supported; else VQ_ERR_ARG: project with a GEMM and call
+ * vq_forward).  x must be 16-byte aligned.  The backward is vq_backward for grad_z followed by the caller's two GEMMs
+ * (grad_x = grad_z W_pre, grad_W_pre = grad_z^T x).                                                              */
+VQ_API int vq_prequant_supported(int C, int D);
+VQ_API int vq_forward_projected(const float* x, int C, const float* w_pre, const float* b_pre, int64_t T,
+               const float* weight, void* cb, int K, int D, int form, float beta, int flags, int64_t n_elem_total,
+               float* z_q, void* idx, float* loss, int32_t* hist, int64_t* stats,
+               float* saved_zn, float* saved_denom, int64_t* seg_sums, float* z_out,
                void* ws, size_t ws_bytes, void* stream);
 
 /* loss = the reference's two-term expression from the fixed-point sum (after an all-reduce). */
@@ -239,6 +260,22 @@ VQ_API int vq_gather_tokens(const void* tokens, int token_bits, int64_t T, int64
               int K, int D, int normalise, int layout_out, float* out, int64_t* stats, void* stream);
 /* tokens between the wire formats (uint16 / int32 / int64); values that do not fit the target are the caller's error */
 VQ_API int vq_tokens_convert(const void* in, int in_bits, void* out, int out_bits, int64_t T, void* stream);
+
+/* ---- post_quant fused into the decode -------------------------------------
+ * Replaces `self.post_quant(self.codebook.indices_to_embeddings(indices))` of decode_indices
+ * (models/vitvqgan.py:199-200 with nn.Linear(codebook_dim, dim); models/vqgan.py:241-242 with nn.Conv2d(dim, dim, 1)):
+ * the projection of a code does not depend on the token, so it is applied to the K codes once,
+ *   table[k] = W_post y_k + b_post     y_k = l2norm(E_k) (normalise=1, from `cb`) or E_k (normalise=0, from `weight`)
+ * (W_post: (C, D) row-major = post_quant.weight, also the (C, D, 1, 1) conv kernel; b_post: C floats or NULL; fp32 fma
+ * chain over d then the bias), and decode_indices becomes ONE gather of (T, C) rows -- token-major, or (b, C, hw) for
+ * the CNN form -- from a table that stays in L2 (16 MB at K = 8192, C = 512).  Re-run vq_project_codebook when the
+ * codebook or post_quant change.  Results agree with F.linear / F.conv2d on the gathered codes to fp32 rounding of a
+ * D-term dot product.  vq_gather_projected: any C > 0 (C % 4 == 0 for token-major), tokens as for vq_gather_tokens,
+ * out-of-range tokens counted in stats[VQ_STAT_BAD_INDEX] and written as 0.                                      */
+VQ_API int vq_project_codebook(const float* weight, const void* cb, int K, int D, int normalise,
+                               const float* w_post, const float* b_post, int C, float* table, void* stream);
+VQ_API int vq_gather_projected(const void* tokens, int token_bits, int64_t T, int64_t hw, const float* table, int K, int C,
+                               int layout_out, float* out, int64_t* stats, void* stream);
 
 /* ---- first consumer of the tokens ------------------------------------------
  * The mask-fill + token-embedding lookup the generative models do right behind encode_imgs, in one pass:

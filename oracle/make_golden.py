@@ -160,6 +160,52 @@ def decode_grad_case(name, form, K, D, b, n, seed):
     print(name, "ok")
 
 
+def projected_case(name, K, D, C, b, n, seed, beta=0.25):
+    """The ViT wrapper's call sites around the quantiser on the reference's own modules (models/vitvqgan.py:185-187
+    wiring, :192-194 forward, :199-200 decode_indices): nn.Linear pre_quant -> reference Codebook -> nn.Linear post_quant,
+    forward + autograd, and post_quant(indices_to_embeddings(indices)) for seeded tokens."""
+    w = vo.make_codebook(vo.VIT, K, D, seed)
+    w_pre, b_pre = vo.projection_inputs(C, D, seed + 1)
+    w_post, b_post = vo.projection_inputs(D, C, seed + 2)
+    x = vo.make_latents((b, n, C), seed + 3).requires_grad_(True)
+    up = vo.make_latents((b, n, D), seed + 4)
+    pre, post = torch.nn.Linear(C, D), torch.nn.Linear(D, C)
+    with torch.no_grad():
+        pre.weight.copy_(w_pre); pre.bias.copy_(b_pre); post.weight.copy_(w_post); post.bias.copy_(b_post)
+    cb = _module(vo.VIT, K, D, beta, w)
+    enc = pre(x)                                   # vitvqgan.py:192
+    z_q, idx, loss = cb(enc)                       # vitvqgan.py:193
+    ((z_q * up).sum() + loss).backward()
+    g = torch.Generator().manual_seed(seed + 5)
+    tokens = torch.randint(0, K, (b, n), generator=g)
+    with torch.no_grad():
+        dec = post(cb.indices_to_embeddings(tokens))      # vitvqgan.py:199-200
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), K=K, D=D, C=C, b=b, n=n, seed=seed, beta=beta,
+                        z=enc.detach().numpy(), z_q=z_q.detach().numpy(), indices=idx.numpy().astype(np.uint16),
+                        loss=loss.detach().numpy(), grad_x=x.grad.numpy(), grad_w_pre=pre.weight.grad.numpy(),
+                        grad_b_pre=pre.bias.grad.numpy(), grad_weight=cb.embedding.weight.grad.numpy(),
+                        tokens=tokens.numpy().astype(np.uint16), decoded=dec.numpy())
+    print(name, "loss", float(loss), "idx[:4]", idx.reshape(-1)[:4].tolist())
+
+
+def projected_conv_case(name, K, D, b, side, seed):
+    """models/vqgan.py:241-242 on the reference's own Codebook: post_quant (nn.Conv2d(dim, dim, 1), :228) of
+    indices_to_embeddings(indices)."""
+    w = vo.make_codebook(vo.VQGAN, K, D, seed)
+    w_post, b_post = vo.projection_inputs(D, D, seed + 2, conv=True)
+    post = torch.nn.Conv2d(D, D, 1)
+    with torch.no_grad():
+        post.weight.copy_(w_post); post.bias.copy_(b_post)
+    cb = _module(vo.VQGAN, K, D, 0.25, w)
+    g = torch.Generator().manual_seed(seed + 5)
+    tokens = torch.randint(0, K, (b, side * side), generator=g)
+    with torch.no_grad():
+        dec = post(cb.indices_to_embeddings(tokens))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), K=K, D=D, b=b, side=side, seed=seed,
+                        tokens=tokens.numpy().astype(np.uint16), decoded=dec.numpy())
+    print(name, tuple(dec.shape))
+
+
 def degenerate_rows(z, w):
     """zero row, NaN row, a row equal to a code, a zero code (SURVEY.md section 7 'Degenerate rows')."""
     z[0, 0] = 0.0
@@ -199,3 +245,6 @@ if __name__ == "__main__":
     token_grad_case("token_consumers_grad", 512, 64, 3, 16, 51)
     decode_grad_case("vit_decode_grad", "vit", 512, 32, 3, 16, 52)
     decode_grad_case("vqgan_decode_grad", "vqgan", 256, 64, 2, 16, 53)
+    # pre_quant / post_quant around the quantiser
+    _selected(projected_case)("vit_projected_step", 1024, 32, 128, 3, 96, 60)
+    _selected(projected_conv_case)("vqgan_projected_decode", 512, 64, 2, 4, 61)

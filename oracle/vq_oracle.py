@@ -314,3 +314,34 @@ def causal_token_embeddings(tokens: torch.Tensor, table: torch.Tensor, pe, start
         e = e + pe[: e.size(1)]
     start = start_token.reshape(1, 1, -1).expand(tokens.shape[0], 1, -1)
     return torch.cat((start, e), dim=1), labels
+
+
+# ---------------------------------------------------------------------------------------------------
+# pre_quant / post_quant around the quantiser
+# ---------------------------------------------------------------------------------------------------
+def projection_inputs(C: int, D: int, seed: int, conv: bool = False):
+    """Seeded weights of one projection: nn.Linear(C -> D) (``(D, C)``, ``(D,)``) or, with ``conv``, the 1x1
+    nn.Conv2d(C -> D) (``(D, C, 1, 1)``, ``(D,)``); the same draws, in the same order, as
+    oracle/make_golden.py::projected_case (uniform(-1/sqrt(C), 1/sqrt(C)) like both modules' default init)."""
+    g = torch.Generator().manual_seed(seed)
+    bound = 1.0 / (C ** 0.5)
+    w = (torch.rand(D, C, generator=g) * 2 - 1) * bound
+    b = (torch.rand(D, generator=g) * 2 - 1) * bound
+    return (w.reshape(D, C, 1, 1) if conv else w), b
+
+
+def quantise_projected(x: torch.Tensor, w_pre: torch.Tensor, b_pre, weight: torch.Tensor, beta: float = 0.25):
+    """/root/reference/models/vitvqgan.py:192-193: ``enc_imgs = self.pre_quant(enc_imgs)`` (nn.Linear, ``:185``), then
+    ``self.codebook(enc_imgs)``.  Returns ``(z, QuantiserOut)``."""
+    z = torch.nn.functional.linear(x, w_pre, b_pre)
+    return z, quantise(VIT, z, weight, beta)
+
+
+def decode_projected(form: str, indices: torch.Tensor, weight: torch.Tensor, w_post: torch.Tensor, b_post):
+    """/root/reference/models/vitvqgan.py:199-200 (``post_quant`` = nn.Linear, ``:187``) and
+    /root/reference/models/vqgan.py:241-242 (``post_quant`` = nn.Conv2d(dim, dim, 1), ``:228``):
+    ``embeds = self.codebook.indices_to_embeddings(indices); embeds = self.post_quant(embeds)``."""
+    e = indices_to_embeddings(form, indices, weight)
+    if form == VIT:
+        return torch.nn.functional.linear(e, w_post, b_post)
+    return torch.nn.functional.conv2d(e, w_post.reshape(w_post.shape[0], -1, 1, 1), b_post)

@@ -207,3 +207,36 @@ def test_decode_is_differentiable_like_the_reference(name):
     (out * torch.from_numpy(g["upstream"])).sum().backward()
     assert np.array_equal(out.detach().numpy(), g["out"])
     assert rel_err(w.grad.numpy(), g["grad_weight"]) < 1e-6
+
+
+def test_projected_quantiser_oracle_matches_reference_fixture():
+    """pre_quant -> Codebook -> autograd and post_quant(indices_to_embeddings) of the ViT wrapper
+    as the reference's own modules computed them (oracle/make_golden.py::projected_case)."""
+    g = load_golden("vit_projected_step")
+    K, D, C, b, n, seed = (int(g[k]) for k in ("K", "D", "C", "b", "n", "seed"))
+    w = vo.make_codebook(vo.VIT, K, D, seed).requires_grad_(True)
+    w_pre, b_pre = (t.requires_grad_(True) for t in vo.projection_inputs(C, D, seed + 1))
+    w_post, b_post = vo.projection_inputs(D, C, seed + 2)
+    x = vo.make_latents((b, n, C), seed + 3).requires_grad_(True)
+    up = vo.make_latents((b, n, D), seed + 4)
+    z, o = vo.quantise_projected(x, w_pre, b_pre, w, float(g["beta"]))
+    assert ulp_distance(z.detach().numpy(), g["z"]).max() <= 4
+    bad = _assert_indices(vo.VIT, o.indices, g["indices"].astype(np.int64), z.detach(), w.detach())
+    _assert_zq(vo.VIT, o.z_q.detach(), g["z_q"], bad)
+    assert rel_err(o.loss.detach().numpy(), g["loss"]) < 1e-6
+    ((o.z_q * up).sum() + o.loss).backward()
+    for name, t in (("grad_x", x), ("grad_w_pre", w_pre), ("grad_b_pre", b_pre), ("grad_weight", w)):
+        assert rel_err(t.grad.numpy(), g[name]) < 1e-5, name
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64))
+    dec = vo.decode_projected(vo.VIT, tokens, w.detach(), w_post, b_post)
+    assert dec.shape == (b, n, C) and rel_err(dec.numpy(), g["decoded"]) < 1e-6
+
+
+def test_projected_decode_oracle_matches_reference_fixture_cnn_form():
+    g = load_golden("vqgan_projected_decode")
+    K, D, b, side, seed = (int(g[k]) for k in ("K", "D", "b", "side", "seed"))
+    w = vo.make_codebook(vo.VQGAN, K, D, seed)
+    w_post, b_post = vo.projection_inputs(D, D, seed + 2, conv=True)
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64))
+    dec = vo.decode_projected(vo.VQGAN, tokens, w, w_post, b_post)
+    assert dec.shape == (b, D, side, side) and rel_err(dec.numpy(), g["decoded"]) < 1e-6
