@@ -18,15 +18,15 @@
 //     each k8 step is a 3-MMA chain from a zero accumulator and the running sum over k is added outside with
 //     round-to-nearest FADDs (they issue in the shadow of the MMAs).  Measured error: tests/test_gpu_projected.py prints
 //     it next to cuBLAS's fp32 error on the same inputs.
-//   * the contraction index is permuted so that a lane's A fragments are 16 consecutive floats of its row (four 16-byte
-//     loads, 256 B per row and quad): fragment "k" slots (t, t + 4) of step s hold k = 64 c + 16 t + 2 s, + 1.  W is split
+//   * the contraction index is permuted so that a lane's A fragments are 8 consecutive floats of its row (two 16-byte
+//     loads, one 128-byte line per row and quad): fragment "k" slots (t, t + 4) of step s hold k = 32 c + 8 t + 2 s, + 1.  W is split
 //     and stored in shared memory once per block in that fragment order: one conflict-free 16-byte load per (step, n-block)
 //     gives {b0 hi, b1 hi, b0 lo, b1 lo}.
 //   * normalisation: the accumulators go through a per-warp shared-memory tile into K1's lane mapping and then through
 //     K1's own instruction sequence (ATen's summation order, explicit _rn intrinsics): given the same z the outputs are
 //     bit-identical to vq_prep.cu's.
-// Persistent blocks (one per SM, 8 warps, 32 rows per warp and iteration); the next 64-column chunk of x is in flight
-// while the current one is multiplied (64 KB of loads in flight per SM).
+// Persistent blocks (one per SM, 8 warps, 32 rows per warp and iteration); the next 32-column chunk of x is in flight
+// while the current one is multiplied (32 KB of loads in flight per SM).
 //
 // k_project_codebook: table[k] = W_post y_k + b_post over the K codes (y = unit code or raw code): with it
 // decode_indices' lookup + projection is ONE gather from a (K, C) table (16 MB at K = 8192, C = 512: L2-resident)
@@ -42,7 +42,9 @@ constexpr int kPqD = 32;              // codebook_dim this kernel is built for (
 constexpr int kPqWarps = 8;
 constexpr int kPqThreads = kPqWarps * 32;
 constexpr int kPqRows = 32;           // rows per warp and iteration: two m16 tiles
-constexpr int kPqChunk = 64;          // columns of x per pipeline stage (16 per lane of a quad)
+constexpr int kPqChunk = 32;          // columns of x per pipeline stage (8 per lane of a quad: one 128-byte line per row)
+constexpr int kPqSteps = kPqChunk / 8;      // k8 MMA steps per chunk
+constexpr int kPqColMultiple = 64;    // in_features the ABI accepts: multiples of 64
 constexpr int kPqZStride = 40;        // floats per row of the staging tile: conflict-free float2 stores / float4 loads
 constexpr int kPqZTile = 16 * kPqZStride;   // one m16 tile per warp
 
@@ -93,7 +95,7 @@ k_prequant_prep(const float* __restrict__ x, int64_t T, int C, const float* __re
                 float4* __restrict__ unit32, float* __restrict__ sq, float* __restrict__ denom, uint2* __restrict__ unit16,
                 float4* __restrict__ z_out, ZeroList zl) {
     extern __shared__ __align__(16) unsigned char pq_smem[];
-    float4* wfrag = reinterpret_cast<float4*>(pq_smem);                       // [C/64][4 n-blocks][8 steps][32 lanes]
+    float4* wfrag = reinterpret_cast<float4*>(pq_smem);                       // [C/32][4 n-blocks][4 steps][32 lanes]
     float* ztile = reinterpret_cast<float*>(pq_smem + (size_t)C * kPqD * 8);   // [warps][16][kPqZStride]
 
     pdl_trigger();
@@ -108,10 +110,10 @@ k_prequant_prep(const float* __restrict__ x, int64_t T, int C, const float* __re
             const float v = __ldg(w + e);
             const uint32_t hi = tf32_of(v);
             const uint32_t lo = tf32_of(__fsub_rn(v, __uint_as_float(hi)));
-            const int chunk = k >> 6, within = k & 63;
-            const int t = within >> 4, s = (within & 15) >> 1, which = within & 1;
+            const int chunk = k >> 5, within = k & 31;
+            const int t = within >> 3, s = (within & 7) >> 1, which = within & 1;
             const int j = n >> 3, g = n & 7;
-            const int slot = ((chunk * 4 + j) * 8 + s) * 32 + g * 4 + t;
+            const int slot = ((chunk * 4 + j) * kPqSteps + s) * 32 + g * 4 + t;
             wf[slot * 4 + which] = __uint_as_float(hi);
             wf[slot * 4 + 2 + which] = __uint_as_float(lo);
         }
@@ -139,7 +141,7 @@ k_prequant_prep(const float* __restrict__ x, int64_t T, int C, const float* __re
         for (int i = 0; i < 4; ++i) {
             int64_t r = r0 + 8 * i + g;
             if (r >= T) r = T - 1;
-            xp[i] = reinterpret_cast<const float4*>(x + r * C + 16 * t);
+            xp[i] = reinterpret_cast<const float4*>(x + r * C + 8 * t);
         }
         float acc[2][4][4];
 #pragma unroll
@@ -149,22 +151,22 @@ k_prequant_prep(const float* __restrict__ x, int64_t T, int C, const float* __re
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
 
-        float4 cur[4][4], nxt[4][4];
+        float4 cur[4][2], nxt[4][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) cur[i][q] = __ldcs(xp[i] + q);
+            for (int q = 0; q < 2; ++q) cur[i][q] = __ldcs(xp[i] + q);
 
         for (int c = 0; c < n_chunks; ++c) {
             if (c + 1 < n_chunks) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) nxt[i][q] = __ldcs(xp[i] + (c + 1) * (kPqChunk / 4) + q);
+                    for (int q = 0; q < 2; ++q) nxt[i][q] = __ldcs(xp[i] + (c + 1) * (kPqChunk / 4) + q);
             }
-            const float4* wb = wfrag + (size_t)c * (4 * 8 * 32) + lane;
+            const float4* wb = wfrag + (size_t)c * (4 * kPqSteps * 32) + lane;
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
+            for (int s = 0; s < kPqSteps; ++s) {
                 uint32_t ah[2][4], al[2][4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -176,29 +178,41 @@ k_prequant_prep(const float* __restrict__ x, int64_t T, int C, const float* __re
                     ah[i >> 1][(i & 1)] = h0;     ah[i >> 1][(i & 1) + 2] = h1;
                     al[i >> 1][(i & 1)] = l0;     al[i >> 1][(i & 1) + 2] = l1;
                 }
+                float4 b[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 b = wb[(j * 8 + s) * 32];
-                    const uint32_t bh0 = __float_as_uint(b.x), bh1 = __float_as_uint(b.y);
-                    const uint32_t bl0 = __float_as_uint(b.z), bl1 = __float_as_uint(b.w);
+                for (int j = 0; j < 4; ++j) b[j] = wb[(j * kPqSteps + s) * 32];
+                // One k8 step inside the tensor core per (n-block, row tile): a 3-MMA chain from a zero accumulator, small
+                // terms first.  The eight chains are issued phase by phase (asm volatile keeps this order), so that a
+                // dependent MMA sits eight MMAs behind the one it waits for instead of right behind it: issued chain by
+                // chain the warp stalled for the full MMA latency three times per chain (first measured version: 230 us,
+                // 21 cycles per MMA and scheduler).
+                float d[2][4][4];
 #pragma unroll
-                    for (int m = 0; m < 2; ++m) {
-                        // one k8 step inside the tensor core, small terms first; the running sum over k is kept
-                        // outside it with round-to-nearest adds (the MMA's own accumulate truncates)
-                        float d[4];
-                        mma_tf32_zero(d, al[m], bh0, bh1);
-                        mma_tf32(d, ah[m], bl0, bl1);
-                        mma_tf32(d, ah[m], bh0, bh1);
+                for (int j = 0; j < 4; ++j)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[m][j][q] = __fadd_rn(acc[m][j][q], d[q]);
-                    }
-                }
+                    for (int m = 0; m < 2; ++m) mma_tf32_zero(d[m][j], al[m], __float_as_uint(b[j].x), __float_as_uint(b[j].y));
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) mma_tf32(d[m][j], ah[m], __float_as_uint(b[j].z), __float_as_uint(b[j].w));
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) mma_tf32(d[m][j], ah[m], __float_as_uint(b[j].x), __float_as_uint(b[j].y));
+                // the running sum over k stays outside the tensor core: round-to-nearest adds (the MMA's own accumulate
+                // truncates)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int m = 0; m < 2; ++m)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[m][j][q] = __fadd_rn(acc[m][j][q], d[m][j][q]);
             }
             if (c + 1 < n_chunks) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) cur[i][q] = nxt[i][q];
+                    for (int q = 0; q < 2; ++q) cur[i][q] = nxt[i][q];
             }
         }
 
@@ -247,7 +261,7 @@ k_prequant_prep(const float* __restrict__ x, int64_t T, int C, const float* __re
 size_t prequant_smem_bytes(int C) { return (size_t)C * kPqD * 8 + (size_t)kPqWarps * kPqZTile * sizeof(float); }
 
 bool prequant_supported(int C, int D) {
-    return D == kPqD && C >= kPqChunk && C % kPqChunk == 0 && prequant_smem_bytes(C) <= 227 * 1024;
+    return D == kPqD && C >= kPqColMultiple && C % kPqColMultiple == 0 && prequant_smem_bytes(C) <= 227 * 1024;
 }
 
 cudaError_t launch_prequant_prep(const float* x, int64_t T, int C, const float* w, const float* bias, int D, float* zn32,
