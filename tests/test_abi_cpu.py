@@ -184,6 +184,53 @@ def test_patch_reference_model_swaps_the_quantiser_in_place():
             model.codebook(z)
 
 
+def test_projection_fusion_host_logic(lib):
+    """SURVEY.md 8(f) rank 1, host side only: which Linear shapes the fused pre_quant covers, argument errors of the new
+    entry points (they are refused before any CUDA call), and which wrapper methods patch_reference_model rebinds."""
+    import torch.nn as nn
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from standins import ViTVQGANStandIn, VQGANStandIn
+    from vq_b200 import projected
+    from vq_b200.integration import patch_reference_model
+    from vq_b200.vitvqgan import Codebook as Vit
+    from vq_b200.vqgan import Codebook as Vqgan
+    cdll = lib.load()
+    assert [c for c in (32, 64, 96, 128, 256, 512, 640, 768, 832, 1024) if projected.prequant_supported(c, 32)] == \
+        [64, 128, 256, 512, 640, 768]
+    assert not projected.prequant_supported(512, 64) and not projected.prequant_supported(512, 16)
+    # unsupported shape / wrong form / misaligned rows: VQ_ERR_ARG with a message, no device needed
+    # (weight, cb, K, D, form, beta, flags, n_elem_total, z_q, idx, loss, hist, stats, saved_zn, saved_denom, seg_sums, z_out,
+    #  ws, ws_bytes, stream)
+    args_tail = (None, 1, 512, 32, 0, ctypes.c_float(0.25), 0, 32, None, 1, None, None, None, None, None, None, None, 1, 1, None)
+    assert len(args_tail) + 5 == len(lib.SIGNATURES["vq_forward_projected"][1])
+    assert cdll.vq_forward_projected(16, 96, 16, None, 1, *args_tail) == 1
+    assert b"unsupported" in cdll.vq_last_error()
+    bad_form = list(args_tail); bad_form[4] = 1
+    assert cdll.vq_forward_projected(16, 128, 16, None, 1, *bad_form) == 1 and b"ViT form" in cdll.vq_last_error()
+    assert cdll.vq_forward_projected(20, 128, 16, None, 1, *args_tail) == 1 and b"aligned" in cdll.vq_last_error()
+    assert cdll.vq_project_codebook(None, None, 512, 32, 1, 16, None, 128, 16, None) == 1       # normalise=1 without cb
+    assert cdll.vq_gather_projected(16, 64, 4, 0, 16, 512, 130, 0, 16, None, None) == 1         # token-major needs C % 4 == 0
+    assert cdll.vq_gather_projected(16, 8, 4, 0, 16, 512, 128, 0, 16, None, None) == 1          # token_bits
+    # the modules know what they cover
+    assert Vit(512, 32).supports_fused_pre_quant(nn.Linear(128, 32))
+    assert not Vit(512, 32).supports_fused_pre_quant(nn.Linear(100, 32))
+    assert not Vit(512, 64).supports_fused_pre_quant(nn.Linear(128, 64))
+    assert not Vqgan(512, 64).supports_fused_pre_quant(nn.Conv2d(64, 64, 1))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Vit(512, 32).forward_projected(torch.randn(2, 4, 128), nn.Linear(128, 32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Vit(512, 32).decode_projected(torch.zeros(1, 4, dtype=torch.long), nn.Linear(32, 128))
+    # wrapper rebinding
+    names = lambda m: tuple(getattr(getattr(m, a), "__func__", getattr(m, a)).__name__ for a in ("forward", "encode_imgs", "decode_indices"))
+    assert names(patch_reference_model(ViTVQGANStandIn(48, 128, 512, 32), form="vit", fuse_projections=True)) == \
+        ("_forward_vit_fused", "_encode_imgs_vit_fused", "_decode_indices_fused")
+    assert names(patch_reference_model(ViTVQGANStandIn(48, 100, 512, 32), form="vit", fuse_projections=True)) == \
+        ("forward", "_encode_imgs_vit", "_decode_indices_fused")          # Linear(100, 32): the reference's two calls stay
+    assert names(patch_reference_model(VQGANStandIn(3, 64, 256), form="vqgan", fuse_projections=True)) == \
+        ("forward", "_encode_imgs_vqgan", "_decode_indices_fused")
+    assert names(patch_reference_model(ViTVQGANStandIn(48, 128, 512, 32), form="vit")) == ("forward", "_encode_imgs_vit", "decode_indices")
+
+
 def test_header_is_plain_c(tmp_path):
     """include/vq_b200.h is a C ABI: it must compile as C99 (no C++ types, no torch types in any signature)."""
     src = tmp_path / "h.c"
