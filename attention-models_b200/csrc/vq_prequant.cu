@@ -19,14 +19,20 @@
 //     round-to-nearest FADDs (they issue in the shadow of the MMAs).  Measured error: tests/test_gpu_projected.py prints
 //     it next to cuBLAS's fp32 error on the same inputs.
 //   * the contraction index is permuted so that a lane's A fragments are 8 consecutive floats of its row (two 16-byte
-//     loads, one 128-byte line per row and quad): fragment "k" slots (t, t + 4) of step s hold k = 32 c + 8 t + 2 s, + 1.  W is split
-//     and stored in shared memory once per block in that fragment order: one conflict-free 16-byte load per (step, n-block)
-//     gives {b0 hi, b1 hi, b0 lo, b1 lo}.
+//     shared-memory loads): fragment "k" slots (t, t + 4) of step s hold k = 32 c + 8 t + 2 s, + 1.  W sits in shared memory
+//     once per block in that fragment order ({b0, b1} per lane, one conflict-free 8-byte load per (step, n-block)) and is
+//     split into its tf32 halves where it is used.
+//   * the encoder rows reach the MMAs through a per-warp ring of three 32-row x 32-column tiles filled by cp.async
+//     (16-byte copies, L2-only, 144-byte row pitch: conflict-free fragment loads): two chunks are always in flight per warp
+//     -- 64 KB per SM -- and nothing about it is up to the compiler.  The first version prefetched into registers; at 255
+//     registers ptxas sank those loads to the end of the loop body, and 29 % of all stall samples sat on the first use of
+//     the loaded value (profiles/r02b_prequant_ncu_variantB.md: 226 us, tensor pipe 44 %).
 //   * normalisation: the accumulators go through a per-warp shared-memory tile into K1's lane mapping and then through
 //     K1's own instruction sequence (ATen's summation order, explicit _rn intrinsics): given the same z the outputs are
 //     bit-identical to vq_prep.cu's.
-// Persistent blocks (one per SM, 8 warps, 32 rows per warp and iteration); the next 32-column chunk of x is in flight
-// while the current one is multiplied (32 KB of loads in flight per SM).
+// Persistent blocks (one per SM, 8 warps, 32 rows per warp and iteration; a warp's (tile, chunk) pairs form one stream, so
+// the ring stays full across tile boundaries).  Bound: 12.6 M warp MMAs at the 8 cycles per m16n8k8 and sub-partition the
+// legacy tensor path sustains (profiles/r02_ubench_hmma.txt: 269 TFLOP/s tf32) = 86 us, next to 82 us of HBM time.
 //
 // k_project_codebook: table[k] = W_post y_k + b_post over the K codes (y = unit code or raw code): with it
 // decode_indices' lookup + projection is ONE gather from a (K, C) table (16 MB at K = 8192, C = 512: L2-resident)
@@ -47,6 +53,17 @@ constexpr int kPqSteps = kPqChunk / 8;      // k8 MMA steps per chunk
 constexpr int kPqColMultiple = 64;    // in_features the ABI accepts: multiples of 64
 constexpr int kPqZStride = 40;        // floats per row of the staging tile: conflict-free float2 stores / float4 loads
 constexpr int kPqZTile = 16 * kPqZStride;   // one m16 tile per warp
+constexpr int kPqStages = 3;          // x tiles per warp: one being multiplied, two in flight
+constexpr int kPqXStride = 36;        // floats per row of an x tile (144 B): conflict-free 16-byte fragment loads
+constexpr int kPqXTile = kPqRows * kPqXStride;
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
 __device__ __forceinline__ uint32_t tf32_of(float v) {
     uint32_t u;
@@ -95,27 +112,24 @@ k_prequant_prep(const float* __restrict__ x, int64_t T, int C, const float* __re
                 float4* __restrict__ unit32, float* __restrict__ sq, float* __restrict__ denom, uint2* __restrict__ unit16,
                 float4* __restrict__ z_out, ZeroList zl) {
     extern __shared__ __align__(16) unsigned char pq_smem[];
-    float4* wfrag = reinterpret_cast<float4*>(pq_smem);                       // [C/32][4 n-blocks][4 steps][32 lanes]
-    float* ztile = reinterpret_cast<float*>(pq_smem + (size_t)C * kPqD * 8);   // [warps][16][kPqZStride]
+    float2* wraw = reinterpret_cast<float2*>(pq_smem);                                  // [C/32][4 n-blocks][4 steps][32 lanes]
+    float* xring = reinterpret_cast<float*>(pq_smem + (size_t)C * kPqD * 4);             // [warps][stages][32][kPqXStride]
+    float* ztile = xring + kPqWarps * kPqStages * kPqXTile;                               // [warps][16][kPqZStride]
 
     pdl_trigger();
     pdl_wait();
     zero_ranges(zl, blockIdx.x, gridDim.x);
 
-    // ---- W (32, C) -> split tf32 pairs in fragment order -------------------------------------------------------
+    // ---- W (32, C) -> fragment order ---------------------------------------------------------------------------
     {
-        float* wf = reinterpret_cast<float*>(wfrag);
+        float* wf = reinterpret_cast<float*>(wraw);
         for (int e = threadIdx.x; e < kPqD * C; e += kPqThreads) {
             const int n = e / C, k = e - n * C;
-            const float v = __ldg(w + e);
-            const uint32_t hi = tf32_of(v);
-            const uint32_t lo = tf32_of(__fsub_rn(v, __uint_as_float(hi)));
             const int chunk = k >> 5, within = k & 31;
             const int t = within >> 3, s = (within & 7) >> 1, which = within & 1;
             const int j = n >> 3, g = n & 7;
             const int slot = ((chunk * 4 + j) * kPqSteps + s) * 32 + g * 4 + t;
-            wf[slot * 4 + which] = __uint_as_float(hi);
-            wf[slot * 4 + 2 + which] = __uint_as_float(lo);
+            wf[slot * 2 + which] = __ldg(w + e);
         }
     }
     __syncthreads();
@@ -124,6 +138,7 @@ k_prequant_prep(const float* __restrict__ x, int64_t T, int C, const float* __re
     const int g = lane >> 2, t = lane & 3;        // MMA fragment coordinates
     const int grp = lane >> 3, sub = lane & 7;     // K1's row mapping: 8 lanes per row
     float* zt = ztile + warp * kPqZTile;
+    float* xr = xring + warp * (kPqStages * kPqXTile);
     float bias_r[4][2];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -132,89 +147,101 @@ k_prequant_prep(const float* __restrict__ x, int64_t T, int C, const float* __re
     }
     const int n_chunks = C / kPqChunk;
     const int64_t n_tiles = (T + kPqRows - 1) / kPqRows;
+    // this warp's tiles: first, first + stride, ...; its (tile, chunk) pairs are one stream of n_items work items
+    const int64_t first = (int64_t)warp * gridDim.x + blockIdx.x, stride = (int64_t)kPqWarps * gridDim.x;
+    const int my_tiles = first < n_tiles ? (int)((n_tiles - first + stride - 1) / stride) : 0;
+    const int n_items = my_tiles * n_chunks;
 
-    for (int64_t tile = (int64_t)warp * gridDim.x + blockIdx.x; tile < n_tiles; tile += (int64_t)kPqWarps * gridDim.x) {
-        const int64_t r0 = tile * kPqRows;
-        // rows of this lane's A fragments: r0 + 8 i + g (i = 0, 1: first m16 tile; 2, 3: second); clamped, stores are guarded
-        const float4* xp[4];
+    // item n -> stage n % 3: 32 rows x 32 columns, lane l copies the 16-byte pieces l, l + 32, ... (8 lanes per row)
+    auto issue = [&](int n) {
+        if (n < n_items) {
+            const int ti = n / n_chunks, c = n - ti * n_chunks;
+            const int64_t r0 = (first + (int64_t)ti * stride) * kPqRows;
+            float* dst = xr + (n % kPqStages) * kPqXTile;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int64_t r = r0 + 8 * i + g;
-            if (r >= T) r = T - 1;
-            xp[i] = reinterpret_cast<const float4*>(x + r * C + 8 * t);
+            for (int q = 0; q < 8; ++q) {
+                const int id = q * 32 + lane, row = id >> 3, piece = id & 7;
+                int64_t r = r0 + row;
+                if (r >= T) r = T - 1;          // clamped: the stores of such rows are guarded
+                cp_async16(dst + row * kPqXStride + piece * 4, x + r * C + c * kPqChunk + piece * 4);
+            }
         }
-        float acc[2][4][4];
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
+        cp_async_commit();                      // (an empty group keeps the wait count uniform)
+    };
+    issue(0);
+    issue(1);
 
-        float4 cur[4][2], nxt[4][2];
+    float acc[2][4][4];
+    for (int n = 0; n < n_items; ++n) {
+        const int ti = n / n_chunks, c = n - ti * n_chunks;
+        const int64_t r0 = (first + (int64_t)ti * stride) * kPqRows;
+        if (c == 0) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
+        }
+        issue(n + 2);                 // refills the stage item n - 1 was read from (all lanes left it: __syncwarp below)
+        cp_async_wait<2>();           // this lane's copies of item n have landed ...
+        __syncwarp();                 // ... and so have the other lanes'
+        const float* xs = xr + (n % kPqStages) * kPqXTile;
+        // rows of this lane's A fragments: 8 i + g (i = 0, 1: first m16 tile; 2, 3: second), columns 8 t .. 8 t + 7
+        float4 cur[4][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int q = 0; q < 2; ++q) cur[i][q] = __ldcs(xp[i] + q);
-
-        for (int c = 0; c < n_chunks; ++c) {
-            if (c + 1 < n_chunks) {
+            for (int q = 0; q < 2; ++q)
+                cur[i][q] = *reinterpret_cast<const float4*>(xs + (8 * i + g) * kPqXStride + 8 * t + 4 * q);
+        const float2* wb = wraw + (size_t)c * (4 * kPqSteps * 32) + lane;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+        for (int s = 0; s < kPqSteps; ++s) {
+            uint32_t ah[2][4], al[2][4];
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) nxt[i][q] = __ldcs(xp[i] + (c + 1) * (kPqChunk / 4) + q);
+            for (int i = 0; i < 4; ++i) {
+                const float e0 = comp(cur[i][s >> 1], (s & 1) * 2), e1 = comp(cur[i][s >> 1], (s & 1) * 2 + 1);
+                const uint32_t h0 = tf32_of(e0), h1 = tf32_of(e1);
+                const uint32_t l0 = tf32_of(__fsub_rn(e0, __uint_as_float(h0)));
+                const uint32_t l1 = tf32_of(__fsub_rn(e1, __uint_as_float(h1)));
+                // i even: rows g (a0, a2); i odd: rows g + 8 (a1, a3)
+                ah[i >> 1][(i & 1)] = h0;     ah[i >> 1][(i & 1) + 2] = h1;
+                al[i >> 1][(i & 1)] = l0;     al[i >> 1][(i & 1) + 2] = l1;
             }
-            const float4* wb = wfrag + (size_t)c * (4 * kPqSteps * 32) + lane;
+            uint32_t bh[4][2], bl[4][2];
 #pragma unroll
-            for (int s = 0; s < kPqSteps; ++s) {
-                uint32_t ah[2][4], al[2][4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float e0 = comp(cur[i][s >> 1], (s & 1) * 2), e1 = comp(cur[i][s >> 1], (s & 1) * 2 + 1);
-                    const uint32_t h0 = tf32_of(e0), h1 = tf32_of(e1);
-                    const uint32_t l0 = tf32_of(__fsub_rn(e0, __uint_as_float(h0)));
-                    const uint32_t l1 = tf32_of(__fsub_rn(e1, __uint_as_float(h1)));
-                    // i even: rows g (a0, a2); i odd: rows g + 8 (a1, a3)
-                    ah[i >> 1][(i & 1)] = h0;     ah[i >> 1][(i & 1) + 2] = h1;
-                    al[i >> 1][(i & 1)] = l0;     al[i >> 1][(i & 1) + 2] = l1;
-                }
-                float4 b[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = wb[(j * kPqSteps + s) * 32];
-                // One k8 step inside the tensor core per (n-block, row tile): a 3-MMA chain from a zero accumulator, small
-                // terms first.  The eight chains are issued phase by phase (asm volatile keeps this order), so that a
-                // dependent MMA sits eight MMAs behind the one it waits for instead of right behind it: issued chain by
-                // chain the warp stalled for the full MMA latency three times per chain (first measured version: 230 us,
-                // 21 cycles per MMA and scheduler).
-                float d[2][4][4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int m = 0; m < 2; ++m) mma_tf32_zero(d[m][j], al[m], __float_as_uint(b[j].x), __float_as_uint(b[j].y));
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int m = 0; m < 2; ++m) mma_tf32(d[m][j], ah[m], __float_as_uint(b[j].z), __float_as_uint(b[j].w));
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int m = 0; m < 2; ++m) mma_tf32(d[m][j], ah[m], __float_as_uint(b[j].x), __float_as_uint(b[j].y));
-                // the running sum over k stays outside the tensor core: round-to-nearest adds (the MMA's own accumulate
-                // truncates)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int m = 0; m < 2; ++m)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[m][j][q] = __fadd_rn(acc[m][j][q], d[m][j][q]);
+            for (int j = 0; j < 4; ++j) {
+                const float2 b = wb[(j * kPqSteps + s) * 32];
+                bh[j][0] = tf32_of(b.x);
+                bh[j][1] = tf32_of(b.y);
+                bl[j][0] = tf32_of(__fsub_rn(b.x, __uint_as_float(bh[j][0])));
+                bl[j][1] = tf32_of(__fsub_rn(b.y, __uint_as_float(bh[j][1])));
             }
-            if (c + 1 < n_chunks) {
+            // One k8 step inside the tensor core per (n-block, row tile): a 3-MMA chain from a zero accumulator, small terms
+            // first, the eight chains phase by phase.  The running sum over k stays outside the tensor core: round-to-nearest
+            // adds (the MMA's own accumulate truncates).
+            float d[2][4][4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) cur[i][q] = nxt[i][q];
-            }
+                for (int m = 0; m < 2; ++m) mma_tf32_zero(d[m][j], al[m], bh[j][0], bh[j][1]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int m = 0; m < 2; ++m) mma_tf32(d[m][j], ah[m], bl[j][0], bl[j][1]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int m = 0; m < 2; ++m) mma_tf32(d[m][j], ah[m], bh[j][0], bh[j][1]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[m][j][q] = __fadd_rn(acc[m][j][q], d[m][j][q]);
         }
+        __syncwarp();                 // every lane has read its fragments: the stage may be refilled
+        if (c + 1 < n_chunks) continue;
 
         // ---- z = acc + bias -> K1's mapping -> unit rows ---------------------------------------------------------
 #pragma unroll
@@ -258,7 +285,9 @@ k_prequant_prep(const float* __restrict__ x, int64_t T, int C, const float* __re
     }
 }
 
-size_t prequant_smem_bytes(int C) { return (size_t)C * kPqD * 8 + (size_t)kPqWarps * kPqZTile * sizeof(float); }
+size_t prequant_smem_bytes(int C) {
+    return (size_t)C * kPqD * 4 + sizeof(float) * (size_t)kPqWarps * (kPqStages * kPqXTile + kPqZTile);
+}
 
 bool prequant_supported(int C, int D) {
     return D == kPqD && C >= kPqColMultiple && C % kPqColMultiple == 0 && prequant_smem_bytes(C) <= 227 * 1024;
