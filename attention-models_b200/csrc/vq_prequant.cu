@@ -31,8 +31,17 @@
 //     K1's own instruction sequence (ATen's summation order, explicit _rn intrinsics): given the same z the outputs are
 //     bit-identical to vq_prep.cu's.
 // Persistent blocks (one per SM, 8 warps, 32 rows per warp and iteration; a warp's (tile, chunk) pairs form one stream, so
-// the ring stays full across tile boundaries).  Bound: 12.6 M warp MMAs at the 8 cycles per m16n8k8 and sub-partition the
-// legacy tensor path sustains (profiles/r02_ubench_hmma.txt: 269 TFLOP/s tf32) = 86 us, next to 82 us of HBM time.
+// the ring stays full across tile boundaries).
+// Measured (cfg3 rows x 512 features, profiles/r02b_*): 228 us = 0.35 of the HBM roofline, 8 % faster than cuBLAS's fp32
+// Linear alone (249 us) and 1.11x over Linear + K1 + the quantiser for the whole encode.  The floors are 82 us of HBM time
+// and 86 us of tensor time (12.6 M warp MMAs at the 8 cycles per m16n8k8 and sub-partition the legacy path sustains,
+// profiles/r02_ubench_hmma.txt); what keeps the kernel 2.7x above them is instruction issue: 1007 instructions per warp
+// and chunk around 96 MMAs -- cvt.rna.tf32.f32 is a 4-instruction sequence on sm_100a (FSETP / add / LOP3 / SEL), 128 of
+// them per chunk -- with two warps per scheduler at 230 registers (issue slots 57 % busy, tensor pipe 43 %, the rest
+// fixed-latency dependencies; profiles/r02b_prequant_ncu.md).  Next: the split as two integer ops (rna = add 0x1000 to the bit
+// pattern, the MMA truncates the operand itself; NaN payloads need one guard per fragment, not per value), W split once
+// into shared memory again for C <= 512, the tile/chunk division hoisted, and 16 rows per warp at <= 128 registers so that
+// four warps per scheduler cover the dependency latency.
 //
 // k_project_codebook: table[k] = W_post y_k + b_post over the K codes (y = unit code or raw code): with it
 // decode_indices' lookup + projection is ONE gather from a (K, C) table (16 MB at K = 8192, C = 512: L2-resident)

@@ -16,6 +16,10 @@ import os
 import time
 
 T_ROWS, C_IN, K_CODES, D_CODE = 262144, 512, 8192, 32
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_prequant_prep launch at this size (ncu --set full,
+# profiles/r02b_prequant_ncu.md): 537.0 MB read (= the encoder rows, nothing re-read) + 43.8 MB of the 52.4 MB of outputs
+# written back inside the launch (the rest is still in L2 when it ends)
+DRAM_TRAFFIC_PREQUANT_CFG3 = 580.8e6
 DESC = ("cfg3pre: ViTVQGAN.encode_imgs behind the encoder -- pre_quant Linear(512, 32) fused into the quantiser's token "
         "preparation + nearest code of 8192x32, 256 img x 1024 tok (262144 rows x 512 features), indices only")
 METRIC = f"vq_tokens_per_sec_prequant_encode_K{K_CODES}_D{D_CODE}_C{C_IN}"
@@ -207,7 +211,11 @@ def run_b200(args, peaks, ClockSampler):
     ach = alg / (prep_ms * 1e-3) / 1e9 if prep_ms > 0 else 0.0
     roofline = {"kernel": "vq::k_prequant_prep (Linear 512 -> 32 as 3xTF32 warp MMAs + normalise + fp16 copy, one pass)",
                 "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                "traffic": None, "peak_source": peaks["source"], "avg_launch_ms": prep_ms,
+                "traffic": DRAM_TRAFFIC_PREQUANT_CFG3, "peak_source": peaks["source"], "avg_launch_ms": prep_ms,
+                "what_bounds_it": "not HBM yet (0.35 of the measured copy bandwidth): 1007 issued instructions per warp and "
+                                  "32-column chunk around 96 warp MMAs (cvt.rna.tf32 is a 4-instruction sequence on sm_100a) "
+                                  "with two warps per scheduler -- issue slots 57 % busy, tensor pipe 43 % of the legacy "
+                                  "path's 8 cycles per m16n8k8 (profiles/r02b_prequant_ncu.md, r02_ubench_hmma.txt)",
                 "algorithmic_bytes_per_launch": alg,
                 "algorithmic_bytes_what": "T*C*4 encoder rows + D*C*4 weights (what any implementation reads); the z round "
                                           "trip of the unfused path is gone",
