@@ -23,5 +23,5 @@ class Codebook(_CodebookBase):
         z_q, flat_idx, loss = self._quantise(z)
         return z_q, flat_idx.view(*z.shape[:-1]), loss
 
-    def encode(self, z: torch.Tensor) -> torch.Tensor:
-        return super().encode(z).view(*z.shape[:-1])
+    def encode(self, z: torch.Tensor, index_dtype: torch.dtype = torch.int64) -> torch.Tensor:
+        return super().encode(z, index_dtype).view(*z.shape[:-1])
