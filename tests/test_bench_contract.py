@@ -46,3 +46,15 @@ def test_b200_arm_line_on_gpu():
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["value"] > 0 and c["cores"] >= 1 and "sample" in c
     assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"]
+
+
+def test_reference_arm_line_of_the_fused_pre_quant_workload_on_cpu():
+    """`--config cfg3pre` (pre_quant + quantiser, indices only) keeps the same contract; its reference
+    arm is the oracle port of `pre_quant` + `Codebook.forward` on a bounded sample."""
+    d = _run("--impl", "reference", "--config", "cfg3pre", "--steps", "1", "--warmup", "1")
+    assert BASE_KEYS <= set(d)
+    assert d["impl"] == "reference" and d["metric"] == "vq_tokens_per_sec_prequant_encode_K8192_D32_C512"
+    assert d["unit"] == "tokens/s" and d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and "sample" in d["cpu_baseline"]
+    assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["config"]["C"] == 512 and "model" not in d["config"]

@@ -240,3 +240,24 @@ def test_projected_decode_oracle_matches_reference_fixture_cnn_form():
     tokens = torch.from_numpy(g["tokens"].astype(np.int64))
     dec = vo.decode_projected(vo.VQGAN, tokens, w, w_post, b_post)
     assert dec.shape == (b, D, side, side) and rel_err(dec.numpy(), g["decoded"]) < 1e-6
+
+
+def test_3xtf32_model_of_the_fused_pre_quant_gemm_is_fp32_level():
+    """The arithmetic of k_prequant_prep restated in numpy (oracle/tf32_split.py): its error against a float64 product is at
+    the level of a plain fp32 GEMM under both models of the tensor core's internal sums, far inside the GPU tests' Z_TOL
+    (2e-5 of sum |x_c W_dc|); measured on a B200: 1.1e-7, cuBLAS fp32 2.6e-7 (profiles/r02b_bench_cfg3pre.json)."""
+    from oracle import tf32_split as ts
+    C, D, T = 512, 32, 256
+    w, b = (t.numpy() for t in vo.projection_inputs(C, D, 1))
+    x = vo.make_latents((T, C), 3).numpy()
+    hi, lo = ts.split_tf32(x)
+    assert np.all((hi.view(np.uint32) & 0x1FFF) == 0) and np.all((lo.view(np.uint32) & 0x1FFF) == 0)
+    assert np.max(np.abs((x - hi - lo) / x)) < 2.0 ** -21          # what the dropped xl.wl term and lo's rounding leave
+    e_fp32 = ts.error_over_sum_abs_terms(torch.nn.functional.linear(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b)).numpy(), x, w, b)
+    e_exact = ts.error_over_sum_abs_terms(ts.linear_3xtf32(x, w, b, "exact"), x, w, b)
+    e_trunc = ts.error_over_sum_abs_terms(ts.linear_3xtf32(x, w, b, "truncate"), x, w, b)
+    assert e_exact < 5e-7 and e_trunc < 1e-6 and e_fp32 < 1e-6
+    assert e_trunc < 20 * max(e_fp32, 5e-8)
+    # a tf32-only GEMM (no split) would NOT be: that is what the split buys
+    e_tf32 = ts.error_over_sum_abs_terms((ts.rna_tf32(x).astype(np.float64) @ ts.rna_tf32(w).astype(np.float64).T + b).astype(np.float32), x, w, b)
+    assert e_tf32 > 20 * e_exact
