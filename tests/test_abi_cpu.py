@@ -231,6 +231,31 @@ def test_projection_fusion_host_logic(lib):
     assert names(patch_reference_model(ViTVQGANStandIn(48, 128, 512, 32), form="vit")) == ("forward", "_encode_imgs_vit", "decode_indices")
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="the reference is only present in the build container")
+def test_patch_reference_model_on_the_unmodified_reference_vqgan():
+    """INTEGRATION.md route 1 on the reference's own wrapper class (models/vqgan.py:221-251; ViTVQGAN cannot be constructed at
+    all: its FeedForward is broken): the codebook is swapped, checkpoints keep their keys, encode_imgs /
+    decode_indices are rebound (fast encode, projected decode), forward stays the reference's."""
+    sys.path.insert(0, "/root/reference")
+    sys.dont_write_bytecode = True
+    from models.vqgan import VQGAN
+    from vq_b200 import vqgan as b_vqgan
+    from vq_b200.integration import patch_reference_model
+    model = VQGAN(64, 512)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    reference_forward = model.forward.__func__
+    patch_reference_model(model, fuse_projections=True)
+    assert type(model.codebook) is b_vqgan.Codebook and model.codebook.codebook_dim == 64
+    after = model.state_dict()
+    assert list(after) == list(before) and all(torch.equal(after[k], before[k]) for k in before)
+    assert model.forward.__func__ is reference_forward
+    assert model.encode_imgs.__func__.__name__ == "_encode_imgs_vqgan"
+    assert model.decode_indices.__func__.__name__ == "_decode_indices_fused"
+    with pytest.raises(RuntimeError, match="CUDA"):
+        with torch.no_grad():
+            model.decode_indices(torch.zeros(1, 16, dtype=torch.long))
+
+
 def test_header_is_plain_c(tmp_path):
     """include/vq_b200.h is a C ABI: it must compile as C99 (no C++ types, no torch types in any signature)."""
     src = tmp_path / "h.c"
