@@ -174,6 +174,17 @@ def _quantise_backward(saved, meta, has_seg, g_zq, g_loss, want_z, want_w):
     return grad_z, grad_w
 
 
+def _empty_result(z_q_shape, K: int, device):
+    """What the reference returns for a batch without tokens (argmin over a (0, K) matrix, ``torch.mean`` of nothing): empty
+    z_q and indices, a NaN loss; no kernel is launched (the ABI takes no NULL buffers)."""
+    z_q = torch.empty(z_q_shape, dtype=torch.float32, device=device)
+    idx = torch.empty(0, dtype=torch.int64, device=device)
+    loss = torch.full((), float("nan"), dtype=torch.float32, device=device)
+    hist = torch.zeros(K, dtype=torch.int32, device=device)
+    stats = torch.zeros(STATS_LEN, dtype=torch.int64, device=device)
+    return z_q, idx, loss, hist, stats
+
+
 def _as_fp32_input(z: torch.Tensor) -> torch.Tensor:
     # under autocast the pre_quant projection hands over bf16; the reference's F.normalize returns fp32,
     # so all quantiser maths is fp32 (SURVEY.md section 8b "modes")
@@ -192,6 +203,8 @@ def quantise(z: torch.Tensor, weight: torch.Tensor, form: str = "vit", beta: flo
     """
     _require_cuda(z, "z")
     _require_cuda(weight, "the codebook weight")
+    if z.numel() == 0:
+        return _empty_result(tuple(z.shape), weight.shape[0], z.device)
     refresh = False
     raw = form == "l2"
     if prepared is None or not prepared.fits(weight) or prepared.raw != raw:
@@ -242,6 +255,9 @@ def encode_indices(z: torch.Tensor, weight: torch.Tensor, form: str = "vit",
     torch.int64 as the reference returns them, or the narrow wire formats torch.int32 / torch.uint16 (K <= 65536) that
     ``indices_to_embeddings`` and the token consumers read directly."""
     _require_cuda(z, "z")
+    if z.numel() == 0:
+        idx = torch.empty(0, dtype=index_dtype, device=z.device)
+        return (idx, torch.zeros(weight.shape[0], dtype=torch.int32, device=z.device)) if want_hist else idx
     if prepared is None or not prepared.matches(weight, form == "l2"):
         prepared = prepare_codebook(weight, form == "l2")
     lib = _lib.load()

@@ -133,6 +133,9 @@ def quantise_projected(x: torch.Tensor, w_pre: torch.Tensor, b_pre: Optional[tor
     Returns ``(z_q (..., D), flat_indices, loss, histogram, stats)`` (+ the projected rows ``z`` with ``return_z``).
     Differentiable with respect to ``x``, ``w_pre``, ``b_pre`` and ``weight``."""
     C, D = _check_projection(x, w_pre, b_pre, weight)
+    if x.numel() == 0:          # no rows: what the reference returns (empty z_q / indices, NaN loss); nothing is launched
+        out = F_vq._empty_result((*x.shape[:-1], D), weight.shape[0], x.device)
+        return (*out, torch.empty((*x.shape[:-1], D), dtype=torch.float32, device=x.device)) if return_z else out
     refresh = False
     if prepared is None or not prepared.fits(weight) or prepared.raw:
         prepared = F_vq.prepare_codebook(weight)
@@ -149,6 +152,8 @@ def encode_indices_projected(x: torch.Tensor, w_pre: torch.Tensor, b_pre: Option
                              index_dtype: torch.dtype = torch.int64) -> torch.Tensor:
     """``encode_imgs`` behind the encoder (vitvqgan.py:207-209): flat indices of ``pre_quant(x)``, nothing else."""
     C, D = _check_projection(x, w_pre, b_pre, weight)
+    if x.numel() == 0:
+        return torch.empty(0, dtype=index_dtype, device=x.device)
     if prepared is None or not prepared.matches(weight):
         prepared = F_vq.prepare_codebook(weight)
     lib = _lib.load()

@@ -260,3 +260,23 @@ def test_full_size_cfg3_fused_pre_quant(dev):
     assert n_bad <= T // 2000
     hist = torch.bincount(idx, minlength=K)
     assert int(hist.sum()) == T
+
+
+@pytest.mark.parametrize("form", ["vit", "vqgan"])
+def test_empty_batch_matches_the_reference_convention(dev, form):
+    """No tokens: empty z_q / indices, NaN loss like the reference's ``torch.mean`` of nothing; nothing is launched."""
+    from vq_b200 import projected, vitvqgan, vqgan
+    if form == "vit":
+        m, z = vitvqgan.Codebook(512, 32).to(dev), torch.empty(0, 4, 32, device=dev)
+    else:
+        m, z = vqgan.Codebook(512, 64).to(dev), torch.empty(0, 64, 2, 2, device=dev)
+    o = vo.quantise(form, z, m.embedding.weight.detach(), m.beta)
+    z_q, idx, loss = m(z)
+    assert z_q.shape == o.z_q.shape and idx.shape == o.indices.shape and idx.dtype == torch.int64
+    assert bool(torch.isnan(loss)) and bool(torch.isnan(o.loss))
+    assert m.encode(z).numel() == 0 and int(m.last_histogram.sum()) == 0
+    if form == "vit":
+        x, w_pre, b_pre, w = _case(0, 128, 512, 5, dev)
+        z_q, idx, loss, hist, stats = projected.quantise_projected(x, w_pre, b_pre, w, 0.25)
+        assert z_q.shape == (0, 32) and idx.numel() == 0 and bool(torch.isnan(loss)) and int(hist.sum()) == 0
+        assert projected.encode_indices_projected(x, w_pre, b_pre, w).numel() == 0

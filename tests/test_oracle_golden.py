@@ -261,3 +261,18 @@ def test_3xtf32_model_of_the_fused_pre_quant_gemm_is_fp32_level():
     # a tf32-only GEMM (no split) would NOT be: that is what the split buys
     e_tf32 = ts.error_over_sum_abs_terms((ts.rna_tf32(x).astype(np.float64) @ ts.rna_tf32(w).astype(np.float64).T + b).astype(np.float32), x, w, b)
     assert e_tf32 > 20 * e_exact
+
+
+@pytest.mark.parametrize("form,shape", [(vo.VIT, (0, 4, 32)), (vo.VQGAN, (0, 32, 2, 2))])
+def test_empty_batch_convention(form, shape):
+    """A batch without tokens: the reference (and so the oracle) returns empty z_q / indices and a NaN loss
+    (``torch.mean`` of nothing).  The product mirrors that without launching anything (functional._empty_result)."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "attention-models_b200"))
+    from vq_b200 import functional as F_vq
+    o = vo.quantise(form, torch.empty(*shape), vo.make_codebook(form, 64, 32, 0), 0.25)
+    z_q, idx, loss, hist, stats = F_vq._empty_result(shape, 64, torch.device("cpu"))
+    assert z_q.shape == o.z_q.shape and z_q.dtype == o.z_q.dtype
+    assert idx.numel() == o.indices.numel() == 0 and idx.dtype == o.indices.dtype
+    assert torch.isnan(loss) and torch.isnan(o.loss) and loss.dim() == 0
+    assert int(hist.sum()) == 0 and hist.shape == (64,)
