@@ -21,23 +21,36 @@ def _encode_imgs_vqgan(self, imgs):
     return self.codebook.encode(enc_imgs).view(b, -1)
 
 
+def _fusable_now(enc_imgs) -> bool:
+    # under autocast the reference's pre_quant Linear runs in bf16 and hands the quantiser bf16 rows (SURVEY.md section 8b
+    # "modes"); the fused projection computes in fp32, which would be a different (better, but different) result -- so the
+    # reference's two calls stay whenever autocast is on or the encoder's output is not fp32
+    return enc_imgs.dtype == torch.float32 and not torch.is_autocast_enabled(enc_imgs.device.type)
+
+
 def _forward_vit_fused(self, imgs):
     """models/vitvqgan.py:190-196 with ``pre_quant`` formed inside the quantiser's token preparation."""
     enc_imgs = self.encoder(imgs)
-    embeds, _, loss = self.codebook.forward_projected(enc_imgs, self.pre_quant)
+    if _fusable_now(enc_imgs):
+        embeds, _, loss = self.codebook.forward_projected(enc_imgs, self.pre_quant)
+    else:
+        embeds, _, loss = self.codebook(self.pre_quant(enc_imgs))
     return self.decoder(self.post_quant(embeds)), loss
 
 
 def _encode_imgs_vit_fused(self, imgs):
     """models/vitvqgan.py:204-210: encoder -> (pre_quant + quantiser, indices only) -> indices (b, n)."""
-    return self.codebook.encode_projected(self.encoder(imgs), self.pre_quant)
+    enc_imgs = self.encoder(imgs)
+    if _fusable_now(enc_imgs):
+        return self.codebook.encode_projected(enc_imgs, self.pre_quant)
+    return self.codebook.encode(self.pre_quant(enc_imgs))
 
 
 def _decode_indices_fused(self, indices):
     """models/vitvqgan.py:198-202 / models/vqgan.py:239-243: lookup + ``post_quant`` as one gather from the projected
     codes when nothing on the way needs a gradient (generation); the reference's composition otherwise."""
     params = [self.codebook.embedding.weight, *self.post_quant.parameters()]
-    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+    if (torch.is_grad_enabled() and any(p.requires_grad for p in params)) or torch.is_autocast_enabled(indices.device.type):
         return self.decoder(self.post_quant(self.codebook.indices_to_embeddings(indices)))
     return self.decoder(self.codebook.decode_projected(indices, self.post_quant))
 

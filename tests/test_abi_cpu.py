@@ -220,6 +220,11 @@ def test_projection_fusion_host_logic(lib):
         Vit(512, 32).forward_projected(torch.randn(2, 4, 128), nn.Linear(128, 32))
     with pytest.raises(RuntimeError, match="CUDA"):
         Vit(512, 32).decode_projected(torch.zeros(1, 4, dtype=torch.long), nn.Linear(32, 128))
+    # under autocast (the reference's pre_quant then runs in bf16) or for non-fp32 rows the fused wrappers keep the two calls
+    from vq_b200 import integration
+    assert integration._fusable_now(torch.zeros(2, 4)) and not integration._fusable_now(torch.zeros(2, 4, dtype=torch.bfloat16))
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        assert not integration._fusable_now(torch.zeros(2, 4))
     # wrapper rebinding
     names = lambda m: tuple(getattr(getattr(m, a), "__func__", getattr(m, a)).__name__ for a in ("forward", "encode_imgs", "decode_indices"))
     assert names(patch_reference_model(ViTVQGANStandIn(48, 128, 512, 32), form="vit", fuse_projections=True)) == \
