@@ -270,7 +270,7 @@ def test_empty_batch_matches_the_reference_convention(dev, form):
         m, z = vitvqgan.Codebook(512, 32).to(dev), torch.empty(0, 4, 32, device=dev)
     else:
         m, z = vqgan.Codebook(512, 64).to(dev), torch.empty(0, 64, 2, 2, device=dev)
-    o = vo.quantise(form, z, m.embedding.weight.detach(), m.beta)
+    o = vo.quantise(form, z.cpu(), m.embedding.weight.detach().cpu(), m.beta)
     z_q, idx, loss = m(z)
     assert z_q.shape == o.z_q.shape and idx.shape == o.indices.shape and idx.dtype == torch.int64
     assert bool(torch.isnan(loss)) and bool(torch.isnan(o.loss))
