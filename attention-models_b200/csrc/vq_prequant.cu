@@ -75,9 +75,26 @@ template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
 __device__ __forceinline__ uint32_t tf32_of(float v) {
+#ifdef VQ_PQ_INTSPLIT
+    // Experiment build (build.py -DVQ_PQ_INTSPLIT --suffix=intsplit; NOT the default, not yet run on a GPU): round to nearest,
+    // ties away, as two integer ops on the bit pattern -- what cvt.rna.tf32.f32 computes for every finite value; ptxas
+    // expands the cvt itself into a 4-instruction sequence on sm_100a, and 128 of them per chunk are what makes the
+    // kernel issue-bound (profiles/r02b_prequant_ncu.md).  A NaN still reaches z through the low part (x - hi).
+    return (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+#else
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
     return u;
+#endif
+}
+// the low part of the split: x - hi is exact in fp32; the default rounds it to tf32 as well, the experiment build hands the
+// MMA the fp32 bits (the tensor core reads the top 19 bits: a truncation of the low part, below 2^-21 of x)
+__device__ __forceinline__ uint32_t tf32_low_of(float v, uint32_t hi) {
+#ifdef VQ_PQ_INTSPLIT
+    return __float_as_uint(__fsub_rn(v, __uint_as_float(hi)));
+#else
+    return tf32_of(__fsub_rn(v, __uint_as_float(hi)));
+#endif
 }
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -211,8 +228,8 @@ k_prequant_prep(const float* __restrict__ x, int64_t T, int C, const float* __re
             for (int i = 0; i < 4; ++i) {
                 const float e0 = comp(cur[i][s >> 1], (s & 1) * 2), e1 = comp(cur[i][s >> 1], (s & 1) * 2 + 1);
                 const uint32_t h0 = tf32_of(e0), h1 = tf32_of(e1);
-                const uint32_t l0 = tf32_of(__fsub_rn(e0, __uint_as_float(h0)));
-                const uint32_t l1 = tf32_of(__fsub_rn(e1, __uint_as_float(h1)));
+                const uint32_t l0 = tf32_low_of(e0, h0);
+                const uint32_t l1 = tf32_low_of(e1, h1);
                 // i even: rows g (a0, a2); i odd: rows g + 8 (a1, a3)
                 ah[i >> 1][(i & 1)] = h0;     ah[i >> 1][(i & 1) + 2] = h1;
                 al[i >> 1][(i & 1)] = l0;     al[i >> 1][(i & 1) + 2] = l1;
@@ -223,8 +240,8 @@ k_prequant_prep(const float* __restrict__ x, int64_t T, int C, const float* __re
                 const float2 b = wb[(j * kPqSteps + s) * 32];
                 bh[j][0] = tf32_of(b.x);
                 bh[j][1] = tf32_of(b.y);
-                bl[j][0] = tf32_of(__fsub_rn(b.x, __uint_as_float(bh[j][0])));
-                bl[j][1] = tf32_of(__fsub_rn(b.y, __uint_as_float(bh[j][1])));
+                bl[j][0] = tf32_low_of(b.x, bh[j][0]);
+                bl[j][1] = tf32_low_of(b.y, bh[j][1]);
             }
             // One k8 step inside the tensor core per (n-block, row tile): a 3-MMA chain from a zero accumulator, small terms
             // first, the eight chains phase by phase.  The running sum over k stays outside the tensor core: round-to-nearest
