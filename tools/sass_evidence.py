@@ -22,7 +22,7 @@ for obj in sorted(glob.glob(os.path.join(ROOT, "attention-models_b200", "lib", "
                 counts[kernel][mm.group(0)] += 1
     print(f"== {os.path.basename(obj)}")
     for k, c in counts.items():
-        tc = {op: n for op, n in c.items() if op.split(".")[0] in ("HMMA", "UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTCBAR", "VIMNMX3", "SETMAXREG", "USETMAXREG", "SYNCS", "ELECT", "REDG", "RED", "ATOMG")}
+        tc = {op: n for op, n in c.items() if op.split(".")[0] in ("HMMA", "LDGSTS", "UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTCBAR", "VIMNMX3", "SETMAXREG", "USETMAXREG", "SYNCS", "ELECT", "REDG", "RED", "ATOMG")}
         if tc:
             print(f"  {k}")
             print("     " + "  ".join(f"{op} x{n}" for op, n in sorted(tc.items())))
