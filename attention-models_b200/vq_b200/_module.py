@@ -86,8 +86,8 @@ class _CodebookBase(nn.Module):
 
     # ---- pre_quant / post_quant fused with the quantiser (vq_b200/projected.py) ----------
     def supports_fused_pre_quant(self, pre_quant: nn.Module) -> bool:
-        """ViT form behind an ``nn.Linear(C, 32)`` with C a multiple of 64 up to 768, fp32, not the forced exhaustive scan
-        of a layout the fused kernel does not write."""
+        """Whether ``forward_projected`` / ``encode_projected`` cover this ``pre_quant``: the ViT form behind an fp32
+        ``nn.Linear(C, 32)`` with C a multiple of 64 up to 768 (``vq_prequant_supported``)."""
         from . import projected
         return (self.form == "vit" and isinstance(pre_quant, nn.Linear) and pre_quant.weight.dtype == torch.float32
                 and pre_quant.out_features == self.codebook_dim
