@@ -32,7 +32,11 @@ def _forward_vit_fused(self, imgs):
     """models/vitvqgan.py:190-196 with ``pre_quant`` formed inside the quantiser's token preparation."""
     enc_imgs = self.encoder(imgs)
     if _fusable_now(enc_imgs):
-        embeds, _, loss = self.codebook.forward_projected(enc_imgs, self.pre_quant)
+        embeds, indices, loss = self.codebook.forward_projected(enc_imgs, self.pre_quant)
+        if not torch.is_grad_enabled():
+            # evaluation (vitvqgan.py:194 without a graph): post_quant of the winning codes is a row of the projected table;
+            # z_q = zn + (q - zn) equals q to an ulp, so this agrees with post_quant(z_q) to fp32 rounding
+            return self.decoder(self.codebook.decode_projected(indices, self.post_quant)), loss
     else:
         embeds, _, loss = self.codebook(self.pre_quant(enc_imgs))
     return self.decoder(self.post_quant(embeds)), loss

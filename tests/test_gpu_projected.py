@@ -224,6 +224,11 @@ def test_wrapper_call_sites_with_fused_projections(dev, form):
         # decode_indices: one gather from the projected codes, then the decoder
         assert rel_err(new.decode_indices(t_ref).cpu().numpy(), ref.decode_indices(t_ref).cpu().numpy()) < 1e-5
     if form == "vit" and bool(same.all()):
+        with torch.no_grad():       # evaluation forward: post_quant comes from the projected table
+            out_ref, loss_ref = ref(imgs)
+            out_new, loss_new = new(imgs)
+        assert rel_err(out_new.cpu().numpy(), out_ref.cpu().numpy()) < 1e-5
+        assert rel_err(loss_new.cpu().numpy(), loss_ref.cpu().numpy()) < 1e-5
         target = torch.randn_like(imgs)
         outs = []
         for m in (ref, new):
